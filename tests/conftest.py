@@ -1,0 +1,22 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a real B200 (run with -m gpu under gpurun)")
+
+
+def golden_files(prefix=""):
+    return sorted(f for f in os.listdir(GOLDEN) if f.endswith(".pt") and f.startswith(prefix))
+
+
+@pytest.fixture(scope="session")
+def golden_dir():
+    return GOLDEN
