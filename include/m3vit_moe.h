@@ -1,0 +1,214 @@
+/*
+ * m3vit_moe.h -- C ABI of the B200-native M3ViT MoE-layer hot path.
+ *
+ * The reference (aapdo/M3ViT) has no native code and no FFI of its own: its MoE
+ * layer (models/moe/origin/custom_moe_layer.py:161-314) reaches the arithmetic
+ * through the third-party FastMoE python package (`fmoe`, pinned @4edeccd,
+ * README.md:42-50), whose `fmoe_cuda` pybind ops are the seams this ABI replaces.
+ * Every entry point below names the reference call site / fmoe op it stands in for.
+ *
+ * Conventions
+ *   - plain pointers + sizes, no torch types.  All pointers are DEVICE pointers
+ *     unless stated otherwise.  The library never allocates, frees or retains
+ *     device memory: every buffer (outputs, workspaces) is caller-owned.
+ *   - every launch goes to the `stream` passed in (a cudaStream_t); no implicit
+ *     device synchronisation, no host read-back.  Re-entrant, no global state.
+ *   - return value: 0 ok; <0 argument error (m3_status); >0 a cudaError_t.
+ *   - activations may be fp32 or bf16 (m3_dtype); router math is always fp32.
+ *   - expert queues use the PADDED layout: expert e owns rows
+ *     [offsets[e], offsets[e]+counts[e]) of the queue buffer, offsets[] is a
+ *     multiple of `pad` (128 for the tensor-core path); padding rows are zero.
+ *
+ * Symbols T tokens, K top-k, E total experts, D model dim, Dt task-feature dim
+ * (0 if none), Dg = D + Dt router input dim, H expert hidden dim, K1 = min(K+1,E).
+ */
+#ifndef M3VIT_MOE_H_
+#define M3VIT_MOE_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define M3_ABI_VERSION 1
+#define M3_PAD_ROWS 128 /* queue padding / M-tile of the grouped GEMM */
+
+typedef void* m3_stream_t; /* cudaStream_t */
+
+typedef enum { M3_F32 = 0, M3_BF16 = 1 } m3_dtype;
+
+typedef enum {
+  M3_OK = 0,
+  M3_ERR_ARG = -1,         /* null pointer / negative size */
+  M3_ERR_SHAPE = -2,       /* unsupported shape (see each function) */
+  M3_ERR_ALIGN = -3,       /* pointer or leading dimension not 16-byte aligned */
+  M3_ERR_UNSUPPORTED = -4, /* dtype / feature not implemented */
+  M3_ERR_DEVICE = -5,      /* current device is not sm_100 */
+  M3_ERR_WORKSPACE = -6    /* workspace too small */
+} m3_status;
+
+int m3_abi_version(void);
+const char* m3_status_string(int status);
+/* 0 if the current CUDA device can run this library (compute capability 10.x). */
+int m3_check_device(void);
+
+/* ------------------------------------------------------------------ router --
+ * Fused noisy_vmoe gate.  Replaces NoisyGate_VMoE.forward
+ * (models/moe/origin/noisy_gate_vmoe.py:168-297): logits = [x, task_feat] @ w_gate,
+ * (+ noise * noise_stddev), softmax over ALL E, top-K1 on the probabilities,
+ * first K kept un-renormalised.  One kernel; per-CTA partial importance / load.
+ *
+ *   x            [T, D]  (x_dtype), row stride ldx elements
+ *   task_feat    [Dt] fp32 or NULL (Dt == 0)       (custom_moe_layer.py:176-179)
+ *   w_gate       [D+Dt, E] fp32
+ *   noise        [T, E] fp32 standard-normal or NULL (eval / std 0)
+ *   idx          [T, K]  int64  (what fmoe's prepare_forward consumes)
+ *   idx_full     [T, K1] int32  (saved for backward)
+ *   score        [T, K]  fp32;  top_vals [T, K1] fp32
+ *   clean_logits [T, E] fp32;   noisy_logits [T, E] fp32 or NULL (then == clean)
+ *   gates        [T, E] fp32 dense scatter(idx, score) or NULL
+ *   imp_partial  [m3_gate_num_partials, E] fp32, load_partial same shape int32
+ * Supported: E in {4,8,16,32,64,128}; D % 32 == 0; 1 <= K <= min(E, 8).
+ */
+int m3_gate_num_partials(int T, int E);
+int m3_gate_fwd(const void* x, int x_dtype, int64_t ldx, const float* task_feat, const float* w_gate,
+                const float* noise, float noise_stddev, int T, int D, int Dt, int E, int K,
+                int64_t* idx, int32_t* idx_full, float* score, float* top_vals, float* clean_logits,
+                float* noisy_logits, float* gates, float* imp_partial, int32_t* load_partial,
+                m3_stream_t stream);
+
+/* Router backward (autograd through noisy_gate_vmoe.py:179-265): softmax
+ * Jacobian over all E from the gradients of every differentiable gate output,
+ * then dw_gate = [x,tf]^T dz and dtask_feat.  dz is written for m3_dispatch_bwd,
+ * which adds dz @ w_gate[:D]^T into dx.   Any of the d* inputs may be NULL (= 0).
+ *   logits [T,E] = the (noisy) logits the forward soft-maxed
+ *   dz [T,E] out;  dw_gate [D+Dt, E] out (overwritten);  dtask_feat [Dt] out or NULL
+ *   dx_gate [T,D] fp32 out or NULL: dz @ w_gate[:D]^T, for callers whose gate input
+ *            is not the layer input (Block.gate_input_ahead)
+ */
+size_t m3_gate_bwd_workspace_bytes(int T, int D, int Dt, int E);
+int m3_gate_bwd(const void* x, int x_dtype, int64_t ldx, const float* task_feat, const float* w_gate,
+                const float* logits, const int32_t* idx_full, int T, int D, int Dt, int E, int K,
+                const float* dscore, const float* dtop_vals, const float* dgates,
+                const float* dimportance, const float* dclean, const float* dnoisy, float* dz,
+                float* dw_gate, float* dtask_feat, float* dx_gate, void* workspace,
+                size_t workspace_bytes, m3_stream_t stream);
+
+/* -------------------------------------------------------------- route plan --
+ * Replaces fmoe_cuda.expert_count + assign_pos (+ the host-side cumsum and the
+ * D2H sync of fmoe.functions.prepare_forward; reference call site
+ * custom_moe_layer.py:255-257).  Deterministic and stable: rows of one expert
+ * keep flat-slot order.  Everything stays on the device.
+ *   idx [T,K] int64 -> counts[E], offsets[E+1] (padded exclusive prefix),
+ *   pos[T*K] (slot t*K+k -> queue row), tile_expert[offsets[E]/pad] (expert of
+ *   every pad-row tile; capacity m3_route_max_tiles), and, if the partials of
+ *   m3_gate_fwd are passed, importance[E] / load[E] fp32 (fixed-order sums).
+ */
+size_t m3_route_plan_workspace_bytes(int T, int K, int E);
+int m3_route_max_rows(int T, int K, int E, int pad);   /* queue capacity in rows  */
+int m3_route_max_tiles(int T, int K, int E, int pad);  /* = max_rows / pad        */
+int m3_route_plan(const int64_t* idx, int T, int K, int E, int pad, const float* imp_partial,
+                  const int32_t* load_partial, int n_partial, int32_t* counts, int32_t* offsets,
+                  int32_t* pos, int32_t* tile_expert, float* importance, float* load,
+                  void* workspace, size_t workspace_bytes, m3_stream_t stream);
+
+/* -------------------------------------------------------- dispatch/combine --
+ * HBM-bound row movers, 128-bit vectorised.  D % 8 == 0.
+ * m3_dispatch_fwd : MOEScatter.forward (index_select by pos//K): xq[pos[t,k]] = x[t],
+ *                   with dtype cast; zeroes the padding rows of every queue.
+ * m3_dispatch_bwd : MOEScatter.backward (index_add): dx[t] = sum_k dxq[pos[t,k]]
+ *                   (+ dz[t] @ w_gate[:D]^T when dz != NULL: router dx, gate_inp is inp)
+ * m3_combine_fwd  : MOEGather.forward + torch.bmm (custom_moe_layer.py:283-297):
+ *                   out[t] = sum_k score[t,k] * yq[pos[t,k]], fp32 accumulation in k order
+ * m3_combine_bwd  : their backward: dscore[t,k] = <g[t], yq[pos[t,k]]>,
+ *                   dyq[pos[t,k]] = score[t,k] * g[t]; zeroes dyq padding rows.
+ */
+int m3_dispatch_fwd(const void* x, int x_dtype, const int32_t* pos, const int32_t* counts,
+                    const int32_t* offsets, int T, int K, int D, int E, void* xq, int xq_dtype,
+                    m3_stream_t stream);
+int m3_dispatch_bwd(const void* dxq, int dxq_dtype, const int32_t* pos, int T, int K, int D,
+                    const float* dz, const float* w_gate, int E, void* dx, int dx_dtype,
+                    m3_stream_t stream);
+int m3_combine_fwd(const void* yq, int yq_dtype, const int32_t* pos, const float* score, int T,
+                   int K, int D, void* out, int out_dtype, m3_stream_t stream);
+int m3_combine_bwd(const void* g, int g_dtype, const void* yq, int yq_dtype, const int32_t* pos,
+                   const float* score, const int32_t* counts, const int32_t* offsets, int T, int K,
+                   int D, int E, void* dyq, int dyq_dtype, float* dscore, m3_stream_t stream);
+
+/* --------------------------------------------------------------- expert FFN --
+ * Replaces _Expert.forward (custom_moe_layer.py:36-44) = FMoELinear -> GELU(erf)
+ * -> FMoELinear, i.e. fmoe_cuda.linear_forward/backward's per-expert cuBLAS loop,
+ * as a grouped GEMM over the padded expert queues.
+ *   dtype M3_F32 : fp32 SIMT path (parity mode; the reference trains in fp32)
+ *   dtype M3_BF16: tcgen05/TMEM/TMA path (bf16 operands, fp32 accumulation)
+ *   xq [rows, D], hpre [rows, H] (saved pre-activation, NULL when not training),
+ *   yq [rows, D]; rows = offsets[E] (<= cap_rows); w1 [E,H,D], w2 [E,D,H] in `dtype`;
+ *   b1 [E,H], b2 [E,D] fp32.   tile_expert / offsets from m3_route_plan (pad 128).
+ *   bf16 backward additionally needs transposed weight copies w1t [E,D,H], w2t [E,H,D].
+ *   Weight / bias gradients are fp32 and OVERWRITTEN (caller accumulates).
+ */
+size_t m3_ffn_workspace_bytes(int dtype, int cap_rows, int D, int H, int E, int backward);
+int m3_ffn_fwd(int dtype, const void* xq, const int32_t* offsets, const int32_t* tile_expert,
+               int cap_rows, int E, int D, int H, const void* w1, const float* b1, const void* w2,
+               const float* b2, void* hpre, void* yq, void* workspace, size_t workspace_bytes,
+               m3_stream_t stream);
+int m3_ffn_bwd(int dtype, const void* xq, const void* hpre, const void* dyq, const int32_t* counts,
+               const int32_t* offsets, const int32_t* tile_expert, int cap_rows, int E, int D, int H,
+               const void* w1, const void* w2, const void* w1t, const void* w2t, void* dxq,
+               float* dw1, float* db1, float* dw2, float* db2, void* workspace,
+               size_t workspace_bytes, m3_stream_t stream);
+
+/* fp32 master weights [E,R,C] -> bf16 copy [E,R,C] and (optional) bf16 transpose [E,C,R]. */
+int m3_cast_weights_bf16(const float* w, int E, int R, int C, void* w_bf16, void* wt_bf16,
+                         m3_stream_t stream);
+
+/* ------------------------------------------------- expert-parallel exchange --
+ * Replace fmoe_cuda.global_scatter / global_gather (grouped ncclSend/ncclRecv with
+ * host-side counts, reached from MOEScatter/MOEGather when world_size > 1) by
+ * direct NVLink peer access: every rank writes its rows straight into the OWNER
+ * rank's receive queue and reads results straight out of it (peer pointers
+ * obtained once by the host through CUDA IPC), so the row movers ARE the
+ * all-to-all and no host count read-back is needed.  See DESIGN.md, section EP.
+ *   peer_*[W]     device array of W queue base pointers (one per rank, own rank too)
+ *   dst_rank[T*K] owner rank of every local slot;  dst_row[T*K] its row there
+ * Same arithmetic as the local row movers above; padding rows are zeroed by the
+ * owner with m3_zero_pad_rows.
+ *
+ * m3_ep_plan: from the all-gathered count matrix cnt[W][E_tot] (E_tot = W*E_loc,
+ * expert e lives on rank e / E_loc: utils/common_config.py:179-185) and this
+ * rank's local stable plan (pos_local from m3_route_plan with pad = 1), derive
+ *   dst_rank/dst_row for every local slot, and this rank's receive layout:
+ *   recv_counts[E_loc], recv_offsets[E_loc+1] (padded), recv_tile_expert[].
+ * Receive queue of local expert le: sources in rank order, each source's rows in
+ * that source's slot order.
+ */
+int m3_ep_plan(const int64_t* idx, const int32_t* pos_local, const int32_t* cnt_all, int rank, int W,
+               int E_loc, int T, int K, int pad, int32_t* dst_rank, int32_t* dst_row,
+               int32_t* recv_counts, int32_t* recv_offsets, int32_t* recv_tile_expert,
+               m3_stream_t stream);
+int m3_ep_dispatch_fwd(const void* x, int x_dtype, const int32_t* dst_rank, const int32_t* dst_row,
+                       int T, int K, int D, void* const* peer_xq, int xq_dtype, m3_stream_t stream);
+int m3_ep_combine_fwd(void* const* peer_yq, int yq_dtype, const int32_t* dst_rank,
+                      const int32_t* dst_row, const float* score, int T, int K, int D, void* out,
+                      int out_dtype, m3_stream_t stream);
+int m3_ep_combine_bwd(const void* g, int g_dtype, void* const* peer_yq, void* const* peer_dyq,
+                      int q_dtype, const int32_t* dst_rank, const int32_t* dst_row,
+                      const float* score, int T, int K, int D, float* dscore, m3_stream_t stream);
+int m3_ep_dispatch_bwd(void* const* peer_dxq, int dxq_dtype, const int32_t* dst_rank,
+                       const int32_t* dst_row, int T, int K, int D, const float* dz,
+                       const float* w_gate, int E, void* dx, int dx_dtype, m3_stream_t stream);
+int m3_zero_pad_rows(void* q, int dtype, const int32_t* counts, const int32_t* offsets, int E, int D,
+                     m3_stream_t stream);
+
+/* CUDA IPC plumbing for the peer queues (host pointers in/out; 64-byte handles). */
+int m3_ipc_alloc(size_t bytes, void** dev_ptr, void* handle64);
+int m3_ipc_open(const void* handle64, void** dev_ptr);
+int m3_ipc_close(void* dev_ptr);
+int m3_ipc_free(void* dev_ptr);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* M3VIT_MOE_H_ */

@@ -1,0 +1,19 @@
+"""m3vit_b200 -- B200-native implementation of the M3ViT MoE-layer hot path.
+
+Public surface (mirrors the reference's `models/moe` names):
+
+    FMoETransformerMLP, FMoETransformerMLPCkpt   m3vit_b200.custom_moe_layer
+    NoisyGate_VMoE                               m3vit_b200.noisy_gate_vmoe
+    build_moe_mlp, MoEBlockMlp                   m3vit_b200.block
+    ops (one wrapper per C-ABI entry point)      m3vit_b200.ops
+
+Everything computes in hand-written CUDA behind the C ABI of include/m3vit_moe.h
+(m3vit_b200/lib/libm3vit_moe.so).  Importing this package does not need a GPU;
+calling anything does, and fails loudly otherwise.
+"""
+from .custom_moe_layer import FMoETransformerMLP, FMoETransformerMLPCkpt, FMoELinear  # noqa: F401
+from .noisy_gate_vmoe import NoisyGate_VMoE, cv_squared  # noqa: F401
+from .block import build_moe_mlp, MoEBlockMlp, collect_noisy_gating_loss  # noqa: F401
+
+__all__ = ["FMoETransformerMLP", "FMoETransformerMLPCkpt", "FMoELinear", "NoisyGate_VMoE", "cv_squared",
+           "build_moe_mlp", "MoEBlockMlp", "collect_noisy_gating_loss"]

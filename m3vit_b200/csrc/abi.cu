@@ -1,0 +1,235 @@
+// C-ABI glue: status strings, device check, FFN dtype dispatch, weight casts,
+// expert-parallel plan, CUDA-IPC plumbing.  See include/m3vit_moe.h.
+#include "common.cuh"
+
+// implemented in ffn_f32.cu / ffn_bf16.cu
+int m3_ffn_fwd_f32(const float* xq, const int32_t* offsets, const int32_t* tile_expert, int cap_rows, int E, int D,
+                   int H, const float* w1, const float* b1, const float* w2, const float* b2, float* hpre,
+                   float* yq, void* workspace, size_t workspace_bytes, cudaStream_t st);
+int m3_ffn_bwd_f32(const float* xq, const float* hpre, const float* dyq, const int32_t* counts,
+                   const int32_t* offsets, const int32_t* tile_expert, int cap_rows, int E, int D, int H,
+                   const float* w1, const float* w2, float* dxq, float* dw1, float* db1, float* dw2, float* db2,
+                   void* workspace, size_t workspace_bytes, cudaStream_t st);
+size_t m3_ffn_bf16_workspace_bytes(int cap_rows, int D, int H, int E, int backward);
+int m3_ffn_fwd_bf16(const void* xq, const int32_t* offsets, const int32_t* tile_expert, int cap_rows, int E, int D,
+                    int H, const void* w1, const float* b1, const void* w2, const float* b2, void* hpre, void* yq,
+                    void* workspace, size_t workspace_bytes, cudaStream_t st);
+int m3_ffn_bwd_bf16(const void* xq, const void* hpre, const void* dyq, const int32_t* counts,
+                    const int32_t* offsets, const int32_t* tile_expert, int cap_rows, int E, int D, int H,
+                    const void* w1, const void* w2, const void* w1t, const void* w2t, void* dxq, float* dw1,
+                    float* db1, float* dw2, float* db2, void* workspace, size_t workspace_bytes, cudaStream_t st);
+
+extern "C" int m3_abi_version(void) { return M3_ABI_VERSION; }
+
+extern "C" const char* m3_status_string(int status) {
+  switch (status) {
+    case M3_OK: return "ok";
+    case M3_ERR_ARG: return "invalid argument (null pointer or negative size)";
+    case M3_ERR_SHAPE: return "unsupported shape";
+    case M3_ERR_ALIGN: return "pointer or leading dimension not 16-byte aligned";
+    case M3_ERR_UNSUPPORTED: return "unsupported dtype or feature";
+    case M3_ERR_DEVICE: return "current CUDA device is not sm_100 (B200)";
+    case M3_ERR_WORKSPACE: return "workspace too small";
+    default: break;
+  }
+  if (status > 0) return cudaGetErrorString(static_cast<cudaError_t>(status));
+  return "unknown m3 status";
+}
+
+extern "C" int m3_check_device(void) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return (int)e;
+  int major = 0;
+  e = cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+  if (e != cudaSuccess) return (int)e;
+  return major == 10 ? M3_OK : M3_ERR_DEVICE;
+}
+
+// ------------------------------------------------------------------ expert FFN
+extern "C" size_t m3_ffn_workspace_bytes(int dtype, int cap_rows, int D, int H, int E, int backward) {
+  if (dtype == M3_F32) return (size_t)cap_rows * H * sizeof(float);
+  return m3_ffn_bf16_workspace_bytes(cap_rows, D, H, E, backward);
+}
+
+extern "C" int m3_ffn_fwd(int dtype, const void* xq, const int32_t* offsets, const int32_t* tile_expert, int cap_rows,
+                          int E, int D, int H, const void* w1, const float* b1, const void* w2, const float* b2,
+                          void* hpre, void* yq, void* workspace, size_t workspace_bytes, m3_stream_t stream) {
+  M3_CHECK_ARG(xq && offsets && tile_expert && w1 && b1 && w2 && b2 && yq);
+  M3_CHECK_ARG(cap_rows >= 0 && E >= 1 && D > 0 && H > 0);
+  M3_CHECK_SHAPE(cap_rows % M3_PAD_ROWS == 0);
+  M3_CHECK_ALIGN16(xq); M3_CHECK_ALIGN16(yq); M3_CHECK_ALIGN16(w1); M3_CHECK_ALIGN16(w2);
+  M3_CHECK_ALIGN16(b1); M3_CHECK_ALIGN16(b2);
+  if (hpre) M3_CHECK_ALIGN16(hpre);
+  if (workspace) M3_CHECK_ALIGN16(workspace);
+  if (cap_rows == 0) return M3_OK;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (dtype == M3_F32)
+    return m3_ffn_fwd_f32((const float*)xq, offsets, tile_expert, cap_rows, E, D, H, (const float*)w1, b1,
+                          (const float*)w2, b2, (float*)hpre, (float*)yq, workspace, workspace_bytes, st);
+  if (dtype == M3_BF16)
+    return m3_ffn_fwd_bf16(xq, offsets, tile_expert, cap_rows, E, D, H, w1, b1, w2, b2, hpre, yq, workspace,
+                           workspace_bytes, st);
+  return M3_ERR_UNSUPPORTED;
+}
+
+extern "C" int m3_ffn_bwd(int dtype, const void* xq, const void* hpre, const void* dyq, const int32_t* counts,
+                          const int32_t* offsets, const int32_t* tile_expert, int cap_rows, int E, int D, int H,
+                          const void* w1, const void* w2, const void* w1t, const void* w2t, void* dxq, float* dw1,
+                          float* db1, float* dw2, float* db2, void* workspace, size_t workspace_bytes,
+                          m3_stream_t stream) {
+  M3_CHECK_ARG(xq && hpre && dyq && counts && offsets && tile_expert && w1 && w2 && dxq && dw1 && db1 && dw2 && db2);
+  M3_CHECK_ARG(cap_rows >= 0 && E >= 1 && D > 0 && H > 0 && workspace);
+  M3_CHECK_SHAPE(cap_rows % M3_PAD_ROWS == 0);
+  M3_CHECK_ALIGN16(xq); M3_CHECK_ALIGN16(hpre); M3_CHECK_ALIGN16(dyq); M3_CHECK_ALIGN16(dxq);
+  M3_CHECK_ALIGN16(w1); M3_CHECK_ALIGN16(w2); M3_CHECK_ALIGN16(dw1); M3_CHECK_ALIGN16(dw2);
+  M3_CHECK_ALIGN16(workspace);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (dtype == M3_F32)
+    return m3_ffn_bwd_f32((const float*)xq, (const float*)hpre, (const float*)dyq, counts, offsets, tile_expert,
+                          cap_rows, E, D, H, (const float*)w1, (const float*)w2, (float*)dxq, dw1, db1, dw2, db2,
+                          workspace, workspace_bytes, st);
+  if (dtype == M3_BF16) {
+    M3_CHECK_ARG(w1t && w2t);
+    return m3_ffn_bwd_bf16(xq, hpre, dyq, counts, offsets, tile_expert, cap_rows, E, D, H, w1, w2, w1t, w2t, dxq,
+                           dw1, db1, dw2, db2, workspace, workspace_bytes, st);
+  }
+  return M3_ERR_UNSUPPORTED;
+}
+
+// ------------------------------------------------------------------ weight cast
+namespace m3 {
+// 32x32 tile: coalesced fp32 read, bf16 straight copy + bf16 transpose via smem
+__global__ void cast_weights_kernel(const float* __restrict__ w, int R, int C, __nv_bfloat16* __restrict__ o,
+                                    __nv_bfloat16* __restrict__ ot) {
+  __shared__ float tile[32][33];
+  const int e = blockIdx.z;
+  const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+  const float* we = w + (int64_t)e * R * C;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int r = r0 + i, c = c0 + threadIdx.x;
+    float v = 0.f;
+    if (r < R && c < C) {
+      v = we[(int64_t)r * C + c];
+      if (o) o[(int64_t)e * R * C + (int64_t)r * C + c] = __float2bfloat16_rn(v);
+    }
+    tile[i][threadIdx.x] = v;
+  }
+  if (ot == nullptr) return;
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int c = c0 + i, r = r0 + threadIdx.x;
+    if (r < R && c < C) ot[(int64_t)e * R * C + (int64_t)c * R + r] = __float2bfloat16_rn(tile[threadIdx.x][i]);
+  }
+}
+
+__global__ void ep_plan_kernel(const int64_t* __restrict__ idx, const int32_t* __restrict__ pos_local,
+                               const int32_t* __restrict__ cnt_all, int rank, int W, int E_loc, int R, int pad,
+                               int32_t* __restrict__ dst_rank, int32_t* __restrict__ dst_row,
+                               int32_t* __restrict__ recv_counts, int32_t* __restrict__ recv_offsets,
+                               int32_t* __restrict__ recv_tile_expert) {
+  extern __shared__ int sm[];
+  const int E_tot = W * E_loc;
+  int* loc_off = sm;            // [E_tot] exclusive prefix of this rank's counts (pad 1)
+  int* base = loc_off + E_tot;  // [E_tot] first row of my segment in the owner's queue
+  int* tot = base + E_tot;      // [E_tot] rows of global expert ge over all sources
+  for (int ge = threadIdx.x; ge < E_tot; ge += blockDim.x) {
+    int t = 0, before = 0;
+    for (int s = 0; s < W; ++s) {
+      const int c = cnt_all[s * E_tot + ge];
+      t += c;
+      if (s < rank) before += c;
+    }
+    tot[ge] = t;
+    base[ge] = before;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int run = 0;
+    for (int ge = 0; ge < E_tot; ++ge) { loc_off[ge] = run; run += cnt_all[rank * E_tot + ge]; }
+    for (int o = 0; o < W; ++o) {
+      int roff = 0;
+      for (int le = 0; le < E_loc; ++le) {
+        const int ge = o * E_loc + le;
+        base[ge] += roff;
+        if (o == rank && blockIdx.x == 0) { recv_counts[le] = tot[ge]; recv_offsets[le] = roff; }
+        roff += (tot[ge] + pad - 1) / pad * pad;
+      }
+      if (o == rank && blockIdx.x == 0) recv_offsets[E_loc] = roff;
+    }
+  }
+  __syncthreads();
+  for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < R; s += gridDim.x * blockDim.x) {
+    const int64_t ge = idx[s];
+    const int p = pos_local[s];
+    if (ge < 0 || ge >= E_tot || p < 0) { dst_rank[s] = 0; dst_row[s] = -1; continue; }
+    dst_rank[s] = (int)(ge / E_loc);
+    dst_row[s] = base[ge] + (p - loc_off[ge]);
+  }
+  if (blockIdx.x == 0) {
+    // tile map of my receive queue
+    int roff = 0;
+    for (int le = 0; le < E_loc; ++le) {
+      const int n = (tot[rank * E_loc + le] + pad - 1) / pad;
+      for (int i = threadIdx.x; i < n; i += blockDim.x) recv_tile_expert[roff / pad + i] = le;
+      roff += n * pad;
+    }
+  }
+}
+}  // namespace m3
+
+extern "C" int m3_cast_weights_bf16(const float* w, int E, int R, int C, void* w_bf16, void* wt_bf16,
+                                    m3_stream_t stream) {
+  M3_CHECK_ARG(w && (w_bf16 || wt_bf16) && E >= 1 && R >= 1 && C >= 1);
+  dim3 grid(m3_ceil_div(C, 32), m3_ceil_div(R, 32), E), block(32, 8);
+  m3::cast_weights_kernel<<<grid, block, 0, static_cast<cudaStream_t>(stream)>>>(
+      w, R, C, static_cast<__nv_bfloat16*>(w_bf16), static_cast<__nv_bfloat16*>(wt_bf16));
+  M3_LAUNCH_CHECK();
+  return M3_OK;
+}
+
+extern "C" int m3_ep_plan(const int64_t* idx, const int32_t* pos_local, const int32_t* cnt_all, int rank, int W,
+                          int E_loc, int T, int K, int pad, int32_t* dst_rank, int32_t* dst_row,
+                          int32_t* recv_counts, int32_t* recv_offsets, int32_t* recv_tile_expert,
+                          m3_stream_t stream) {
+  M3_CHECK_ARG(idx && pos_local && cnt_all && dst_rank && dst_row && recv_counts && recv_offsets && recv_tile_expert);
+  M3_CHECK_ARG(W >= 1 && rank >= 0 && rank < W && E_loc >= 1 && T >= 0 && K >= 1 && pad >= 1);
+  M3_CHECK_SHAPE(W * E_loc <= 1024);
+  const int R = T * K;
+  int grid = m3_ceil_div(R, 256);
+  if (grid < 1) grid = 1;
+  if (grid > 2 * m3::kNumSMs) grid = 2 * m3::kNumSMs;
+  m3::ep_plan_kernel<<<grid, 256, 3 * W * E_loc * sizeof(int), static_cast<cudaStream_t>(stream)>>>(
+      idx, pos_local, cnt_all, rank, W, E_loc, R, pad, dst_rank, dst_row, recv_counts, recv_offsets,
+      recv_tile_expert);
+  M3_LAUNCH_CHECK();
+  return M3_OK;
+}
+
+// ------------------------------------------------------------------ CUDA IPC
+extern "C" int m3_ipc_alloc(size_t bytes, void** dev_ptr, void* handle64) {
+  M3_CHECK_ARG(dev_ptr && handle64 && bytes > 0);
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  cudaError_t e = cudaMalloc(dev_ptr, bytes);
+  if (e != cudaSuccess) return (int)e;
+  e = cudaIpcGetMemHandle(static_cast<cudaIpcMemHandle_t*>(handle64), *dev_ptr);
+  if (e != cudaSuccess) { cudaFree(*dev_ptr); *dev_ptr = nullptr; return (int)e; }
+  return M3_OK;
+}
+extern "C" int m3_ipc_open(const void* handle64, void** dev_ptr) {
+  M3_CHECK_ARG(handle64 && dev_ptr);
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle64, sizeof(h));
+  cudaError_t e = cudaIpcOpenMemHandle(dev_ptr, h, cudaIpcMemLazyEnablePeerAccess);
+  return e == cudaSuccess ? M3_OK : (int)e;
+}
+extern "C" int m3_ipc_close(void* dev_ptr) {
+  M3_CHECK_ARG(dev_ptr);
+  cudaError_t e = cudaIpcCloseMemHandle(dev_ptr);
+  return e == cudaSuccess ? M3_OK : (int)e;
+}
+extern "C" int m3_ipc_free(void* dev_ptr) {
+  M3_CHECK_ARG(dev_ptr);
+  cudaError_t e = cudaFree(dev_ptr);
+  return e == cudaSuccess ? M3_OK : (int)e;
+}

@@ -1,0 +1,130 @@
+// Shared device/host helpers for the M3ViT MoE hot-path kernels (sm_100a only).
+#pragma once
+
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/m3vit_moe.h"
+
+#define M3_CHECK_ARG(cond)      \
+  do {                          \
+    if (!(cond)) return M3_ERR_ARG; \
+  } while (0)
+#define M3_CHECK_SHAPE(cond)      \
+  do {                            \
+    if (!(cond)) return M3_ERR_SHAPE; \
+  } while (0)
+#define M3_CHECK_ALIGN16(p)                                   \
+  do {                                                        \
+    if ((reinterpret_cast<uintptr_t>(p) & 15u) != 0) return M3_ERR_ALIGN; \
+  } while (0)
+#define M3_LAUNCH_CHECK()                      \
+  do {                                         \
+    cudaError_t e__ = cudaGetLastError();      \
+    if (e__ != cudaSuccess) return (int)e__;   \
+  } while (0)
+
+static inline int m3_ceil_div(int a, int b) { return (a + b - 1) / b; }
+static inline int m3_round_up(int a, int b) { return (a + b - 1) / b * b; }
+
+namespace m3 {
+
+constexpr int kNumSMs = 148;  // B200
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// ---- 16-byte vector access -------------------------------------------------
+// Streaming (read-once) global load / store hints: the row movers touch every
+// byte exactly once, so keep them out of L1.
+__device__ __forceinline__ uint4 ldg_stream(const void* p) {
+  uint4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+               : "l"(p));
+  return r;
+}
+__device__ __forceinline__ void stg_stream(void* p, const uint4& v) {
+  asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y),
+               "r"(v.z), "r"(v.w)
+               : "memory");
+}
+
+__device__ __forceinline__ float2 bf16x2_to_float2(uint32_t u) {
+  __nv_bfloat162 h = *reinterpret_cast<__nv_bfloat162*>(&u);
+  return __bfloat1622float2(h);
+}
+__device__ __forceinline__ uint32_t float2_to_bf16x2(float a, float b) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+
+// An 8-element slice of a row, held as fp32 in registers, loadable/storable as
+// fp32 (2 x 16 B) or bf16 (1 x 16 B).
+struct Vec8 {
+  float v[8];
+};
+
+template <typename T>
+__device__ __forceinline__ Vec8 load8(const T* p);
+
+template <>
+__device__ __forceinline__ Vec8 load8<float>(const float* p) {
+  Vec8 r;
+  uint4 a = ldg_stream(p), b = ldg_stream(p + 4);
+  r.v[0] = __uint_as_float(a.x); r.v[1] = __uint_as_float(a.y);
+  r.v[2] = __uint_as_float(a.z); r.v[3] = __uint_as_float(a.w);
+  r.v[4] = __uint_as_float(b.x); r.v[5] = __uint_as_float(b.y);
+  r.v[6] = __uint_as_float(b.z); r.v[7] = __uint_as_float(b.w);
+  return r;
+}
+template <>
+__device__ __forceinline__ Vec8 load8<__nv_bfloat16>(const __nv_bfloat16* p) {
+  Vec8 r;
+  uint4 a = ldg_stream(p);
+  float2 f;
+  f = bf16x2_to_float2(a.x); r.v[0] = f.x; r.v[1] = f.y;
+  f = bf16x2_to_float2(a.y); r.v[2] = f.x; r.v[3] = f.y;
+  f = bf16x2_to_float2(a.z); r.v[4] = f.x; r.v[5] = f.y;
+  f = bf16x2_to_float2(a.w); r.v[6] = f.x; r.v[7] = f.y;
+  return r;
+}
+
+template <typename T>
+__device__ __forceinline__ void store8(T* p, const Vec8& r);
+
+template <>
+__device__ __forceinline__ void store8<float>(float* p, const Vec8& r) {
+  uint4 a, b;
+  a.x = __float_as_uint(r.v[0]); a.y = __float_as_uint(r.v[1]);
+  a.z = __float_as_uint(r.v[2]); a.w = __float_as_uint(r.v[3]);
+  b.x = __float_as_uint(r.v[4]); b.y = __float_as_uint(r.v[5]);
+  b.z = __float_as_uint(r.v[6]); b.w = __float_as_uint(r.v[7]);
+  stg_stream(p, a);
+  stg_stream(p + 4, b);
+}
+template <>
+__device__ __forceinline__ void store8<__nv_bfloat16>(__nv_bfloat16* p, const Vec8& r) {
+  uint4 a;
+  a.x = float2_to_bf16x2(r.v[0], r.v[1]);
+  a.y = float2_to_bf16x2(r.v[2], r.v[3]);
+  a.z = float2_to_bf16x2(r.v[4], r.v[5]);
+  a.w = float2_to_bf16x2(r.v[6], r.v[7]);
+  stg_stream(p, a);
+}
+
+// exact-erf GELU and its derivative (nn.GELU() default, as the reference's experts use)
+__device__ __forceinline__ float gelu_erf(float x) {
+  return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
+}
+__device__ __forceinline__ float gelu_erf_grad(float x) {
+  const float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752440f));
+  const float pdf = 0.39894228040143267794f * __expf(-0.5f * x * x);
+  return cdf + x * pdf;
+}
+
+}  // namespace m3

@@ -1,0 +1,591 @@
+// Fused noisy_vmoe router (forward + backward) for sm_100a.
+//
+// Replaces NoisyGate_VMoE.forward of the reference
+// (/root/reference/models/moe/origin/noisy_gate_vmoe.py:168-297; ckpt twin
+// models/moe/ckpt/noisy_gate_vmoe.py:80-264): 6-8 tiny ATen kernels (GEMM with
+// N=16, randn add, softmax, topk, slice, scatter, reductions) become ONE kernel.
+//
+// Forward layout: a warp owns TOK_W = (32/EG)*TM tokens, EG = E/4 lanes per token,
+// every lane accumulates TM tokens x 4 experts in registers with sequential fp32
+// FMAs over d (deterministic summation order).  x is staged through shared memory
+// in 32-column chunks with cp.async double buffering; w_gate chunks are shared by
+// the CTA.  Softmax / top-(K+1) run on the registers with warp-shuffle reductions
+// across the EG lanes of a token (lowest index wins ties).
+//
+// Roofline: HBM-bound on reading x once (T*D*el bytes) for large T, FFMA-bound
+// below that; 2*Dg*E flop per token.
+#include "common.cuh"
+
+namespace m3 {
+
+constexpr int kGateDC = 32;  // columns of x per smem chunk
+
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+  uint32_t s = static_cast<uint32_t>(__cvta_generic_to_shared(smem));
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+template <typename XT>
+struct GateRow;  // smem row geometry of one x chunk
+template <>
+struct GateRow<float> {
+  static constexpr int kBytes = kGateDC * 4 + 16;  // +16 B pad: conflict-free LDS.128 over 8 rows
+  __device__ static __forceinline__ float4 ld4(const unsigned char* row, int d) {
+    return *reinterpret_cast<const float4*>(row + d * 4);
+  }
+};
+template <>
+struct GateRow<__nv_bfloat16> {
+  static constexpr int kBytes = kGateDC * 2 + 16;
+  __device__ static __forceinline__ float4 ld4(const unsigned char* row, int d) {
+    uint2 u = *reinterpret_cast<const uint2*>(row + d * 2);
+    float2 a = bf16x2_to_float2(u.x), b = bf16x2_to_float2(u.y);
+    return make_float4(a.x, a.y, b.x, b.y);
+  }
+};
+
+template <int E, int TM, int NW>
+struct GateCfg {
+  static constexpr int EG = E / 4;          // lanes per token
+  static constexpr int TG = 32 / EG;        // tokens per warp "row"
+  static constexpr int TOK_W = TG * TM;     // tokens per warp
+  static constexpr int TOK_CTA = TOK_W * NW;
+};
+
+template <int E, int TM, int NW, typename XT>
+__global__ void __launch_bounds__(NW * 32)
+gate_fwd_kernel(const XT* __restrict__ x, int64_t ldx, const float* __restrict__ task_feat,
+                const float* __restrict__ w_gate, const float* __restrict__ noise, float noise_stddev,
+                int T, int D, int Dt, int K, int K1, int64_t* __restrict__ idx,
+                int32_t* __restrict__ idx_full, float* __restrict__ score, float* __restrict__ top_vals,
+                float* __restrict__ clean_logits, float* __restrict__ noisy_logits,
+                float* __restrict__ gates, float* __restrict__ imp_partial,
+                int32_t* __restrict__ load_partial) {
+  using C = GateCfg<E, TM, NW>;
+  using Row = GateRow<XT>;
+  constexpr int EG = C::EG, TG = C::TG, TOK_W = C::TOK_W;
+  constexpr int ROWB = Row::kBytes;
+  constexpr int XS_STAGE = TOK_W * ROWB;           // bytes per warp per stage
+  constexpr int WS_STAGE = kGateDC * E * 4;        // bytes per stage
+  constexpr int CHUNK_VECS = kGateDC * (int)sizeof(XT) / 16;  // 16-B vectors per x row chunk
+
+  extern __shared__ __align__(16) unsigned char smem[];
+  unsigned char* ws = smem;                                   // [2][DC][E] fp32
+  unsigned char* xs = smem + 2 * WS_STAGE;                    // [NW][2][TOK_W][ROWB]
+  float* red_imp = reinterpret_cast<float*>(xs + NW * 2 * XS_STAGE);  // [NW][E]
+  int* red_load = reinterpret_cast<int*>(red_imp + NW * E);           // [NW][E]
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int eg = lane % EG, tg = lane / EG;
+  const int tok_w0 = blockIdx.x * C::TOK_CTA + warp * TOK_W;
+  unsigned char* my_xs = xs + warp * 2 * XS_STAGE;
+
+  const int NC = D / kGateDC;
+  auto issue = [&](int c, int stage) {
+    // x: TOK_W rows x CHUNK_VECS 16-B vectors, rows clamped to T-1 (never OOB)
+    for (int v = lane; v < TOK_W * CHUNK_VECS; v += 32) {
+      int r = v / CHUNK_VECS, q = v % CHUNK_VECS;
+      int t = min(tok_w0 + r, T - 1);
+      const unsigned char* src = reinterpret_cast<const unsigned char*>(x + (int64_t)t * ldx + c * kGateDC) + q * 16;
+      cp_async16(my_xs + stage * XS_STAGE + r * ROWB + q * 16, src);
+    }
+    // w_gate rows [c*DC, c*DC+DC) are contiguous: DC*E floats
+    const unsigned char* wsrc = reinterpret_cast<const unsigned char*>(w_gate + (int64_t)c * kGateDC * E);
+    for (int v = threadIdx.x; v < WS_STAGE / 16; v += NW * 32) cp_async16(ws + stage * WS_STAGE + v * 16, wsrc + v * 16);
+    cp_async_commit();
+  };
+
+  float acc[TM][4];
+#pragma unroll
+  for (int j = 0; j < TM; ++j)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) acc[j][c] = 0.f;
+
+  issue(0, 0);
+  for (int c = 0; c < NC; ++c) {
+    if (c + 1 < NC) {
+      issue(c + 1, (c + 1) & 1);
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
+    }
+    __syncthreads();
+    const unsigned char* xst = my_xs + (c & 1) * XS_STAGE;
+    const float* wst = reinterpret_cast<const float*>(ws + (c & 1) * WS_STAGE);
+#pragma unroll 2
+    for (int d4 = 0; d4 < kGateDC; d4 += 4) {
+      float4 w[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) w[i] = *reinterpret_cast<const float4*>(wst + (d4 + i) * E + eg * 4);
+#pragma unroll
+      for (int j = 0; j < TM; ++j) {
+        float4 xv = Row::ld4(xst + (tg + TG * j) * ROWB, d4);
+        const float xa[4] = {xv.x, xv.y, xv.z, xv.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          acc[j][0] = fmaf(xa[i], w[i].x, acc[j][0]);
+          acc[j][1] = fmaf(xa[i], w[i].y, acc[j][1]);
+          acc[j][2] = fmaf(xa[i], w[i].z, acc[j][2]);
+          acc[j][3] = fmaf(xa[i], w[i].w, acc[j][3]);
+        }
+      }
+    }
+    __syncthreads();
+  }
+
+  // task-conditioned router: constant contribution of the task feature rows
+  // (the reference concatenates it onto every token, custom_moe_layer.py:176-179)
+  if (Dt > 0) {
+    float tb[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int j = 0; j < Dt; ++j) {
+      float f = __ldg(task_feat + j);
+      float4 w = __ldg(reinterpret_cast<const float4*>(w_gate + (int64_t)(D + j) * E + eg * 4));
+      tb[0] = fmaf(f, w.x, tb[0]); tb[1] = fmaf(f, w.y, tb[1]);
+      tb[2] = fmaf(f, w.z, tb[2]); tb[3] = fmaf(f, w.w, tb[3]);
+    }
+#pragma unroll
+    for (int j = 0; j < TM; ++j)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) acc[j][c] += tb[c];
+  }
+
+  float imp[4] = {0.f, 0.f, 0.f, 0.f};
+  int ld[4] = {0, 0, 0, 0};
+
+#pragma unroll
+  for (int j = 0; j < TM; ++j) {
+    const int t = tok_w0 + tg + TG * j;
+    const bool valid = t < T;
+    const int64_t te = (int64_t)(valid ? t : 0) * E + eg * 4;
+    float z[4] = {acc[j][0], acc[j][1], acc[j][2], acc[j][3]};
+    if (valid) *reinterpret_cast<float4*>(clean_logits + te) = make_float4(z[0], z[1], z[2], z[3]);
+    if (noise != nullptr) {
+      float4 n = valid ? __ldg(reinterpret_cast<const float4*>(noise + te)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      z[0] += n.x * noise_stddev; z[1] += n.y * noise_stddev;
+      z[2] += n.z * noise_stddev; z[3] += n.w * noise_stddev;
+      if (valid && noisy_logits != nullptr)
+        *reinterpret_cast<float4*>(noisy_logits + te) = make_float4(z[0], z[1], z[2], z[3]);
+    }
+    // softmax over all E experts of this token (EG lanes x 4)
+    float m = fmaxf(fmaxf(z[0], z[1]), fmaxf(z[2], z[3]));
+#pragma unroll
+    for (int o = EG / 2; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    float p[4];
+    float s = 0.f;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) { p[c] = expf(z[c] - m); s += p[c]; }
+#pragma unroll
+    for (int o = EG / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+#pragma unroll
+    for (int c = 0; c < 4; ++c) p[c] = p[c] / s;
+
+    // top-K1 on the probabilities, descending, lowest index wins ties
+    unsigned taken = 0, takenK = 0;
+    for (int r = 0; r < K1; ++r) {
+      float bv = -1.f;
+      int bi = 0x7fffffff;
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+        if (!((taken >> c) & 1u) && p[c] > bv) { bv = p[c]; bi = eg * 4 + c; }
+#pragma unroll
+      for (int o = EG / 2; o > 0; o >>= 1) {
+        float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+        int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+      }
+      if (bi >= E) { bi = r; bv = 0.f; }  // NaN row: keep indices in range
+      if ((bi >> 2) == eg) {
+        taken |= 1u << (bi & 3);
+        if (r < K) takenK |= 1u << (bi & 3);
+      }
+      if (valid && eg == 0) {
+        idx_full[(int64_t)t * K1 + r] = bi;
+        top_vals[(int64_t)t * K1 + r] = bv;
+        if (r < K) {
+          idx[(int64_t)t * K + r] = bi;
+          score[(int64_t)t * K + r] = bv;
+        }
+      }
+    }
+    float g[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const bool sel = valid && ((takenK >> c) & 1u);
+      g[c] = sel ? p[c] : 0.f;
+      imp[c] += g[c];
+      ld[c] += (sel && p[c] > 0.f) ? 1 : 0;
+    }
+    if (valid && gates != nullptr) *reinterpret_cast<float4*>(gates + te) = make_float4(g[0], g[1], g[2], g[3]);
+  }
+
+  // importance / load partials: fixed-order reduction -> deterministic
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+#pragma unroll
+    for (int o = EG; o < 32; o <<= 1) {
+      imp[c] += __shfl_xor_sync(0xffffffffu, imp[c], o);
+      ld[c] += __shfl_xor_sync(0xffffffffu, ld[c], o);
+    }
+  }
+  if (tg == 0) {
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      red_imp[warp * E + eg * 4 + c] = imp[c];
+      red_load[warp * E + eg * 4 + c] = ld[c];
+    }
+  }
+  __syncthreads();
+  for (int e = threadIdx.x; e < E; e += NW * 32) {
+    float a = 0.f;
+    int b = 0;
+    for (int w = 0; w < NW; ++w) { a += red_imp[w * E + e]; b += red_load[w * E + e]; }
+    imp_partial[(int64_t)blockIdx.x * E + e] = a;
+    load_partial[(int64_t)blockIdx.x * E + e] = b;
+  }
+}
+
+template <int E, int TM, int NW, typename XT>
+static size_t gate_fwd_smem() {
+  using C = GateCfg<E, TM, NW>;
+  return 2 * kGateDC * E * 4 + (size_t)NW * 2 * C::TOK_W * GateRow<XT>::kBytes + (size_t)NW * E * 8;
+}
+
+// Three tile configurations; pick the largest whose grid still covers the GPU twice.
+//   0: 1 warp  x TG*2 tokens (small T, latency-bound)   1: 2 warps x TG*4   2: 4 warps x TG*8
+template <int E>
+static int gate_cfg_id(int T) {
+  if (T >= 2 * kNumSMs * GateCfg<E, 8, 4>::TOK_CTA) return 2;
+  if (T >= 2 * kNumSMs * GateCfg<E, 4, 2>::TOK_CTA) return 1;
+  return 0;
+}
+
+template <int E, int TM, int NW, typename XT>
+static int launch_gate_fwd(const void* x, int64_t ldx, const float* task_feat, const float* w_gate,
+                           const float* noise, float noise_stddev, int T, int D, int Dt, int K, int K1,
+                           int64_t* idx, int32_t* idx_full, float* score, float* top_vals, float* clean,
+                           float* noisy, float* gates, float* imp_partial, int32_t* load_partial,
+                           cudaStream_t st) {
+  using C = GateCfg<E, TM, NW>;
+  size_t smem = gate_fwd_smem<E, TM, NW, XT>();
+  auto kern = gate_fwd_kernel<E, TM, NW, XT>;
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+  }
+  int grid = m3_ceil_div(T, C::TOK_CTA);
+  kern<<<grid, NW * 32, smem, st>>>(static_cast<const XT*>(x), ldx, task_feat, w_gate, noise, noise_stddev, T,
+                                    D, Dt, K, K1, idx, idx_full, score, top_vals, clean, noisy, gates,
+                                    imp_partial, load_partial);
+  M3_LAUNCH_CHECK();
+  return M3_OK;
+}
+
+template <int E>
+static int gate_tokens_per_cta(int T) {
+  const int id = gate_cfg_id<E>(T);
+  return id == 2 ? GateCfg<E, 8, 4>::TOK_CTA : id == 1 ? GateCfg<E, 4, 2>::TOK_CTA : GateCfg<E, 2, 1>::TOK_CTA;
+}
+
+// ------------------------------------------------------------------ backward
+// dz[t,:] = softmax-Jacobian applied to the gradient of every selected probability.
+template <int E>
+__global__ void __launch_bounds__(256)
+gate_bwd_dz_kernel(const float* __restrict__ logits, const int32_t* __restrict__ idx_full, int T, int K, int K1,
+                   const float* __restrict__ dscore, const float* __restrict__ dtop,
+                   const float* __restrict__ dgates, const float* __restrict__ dimp,
+                   const float* __restrict__ dclean, const float* __restrict__ dnoisy,
+                   float* __restrict__ dz) {
+  constexpr int EG = E / 4;
+  const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int eg = (int)(gid % EG);
+  const int64_t tt = gid / EG;
+  const bool valid = tt < T;
+  const int64_t t = valid ? tt : (T - 1);
+  const int64_t te = t * E + eg * 4;
+  float4 zv = __ldg(reinterpret_cast<const float4*>(logits + te));
+  float z[4] = {zv.x, zv.y, zv.z, zv.w};
+  float m = fmaxf(fmaxf(z[0], z[1]), fmaxf(z[2], z[3]));
+#pragma unroll
+  for (int o = EG / 2; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  float p[4], s = 0.f;
+#pragma unroll
+  for (int c = 0; c < 4; ++c) { p[c] = expf(z[c] - m); s += p[c]; }
+#pragma unroll
+  for (int o = EG / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+#pragma unroll
+  for (int c = 0; c < 4; ++c) p[c] = p[c] / s;
+
+  float dp[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int r = 0; r < K1; ++r) {
+    const int e = __ldg(idx_full + t * K1 + r);
+    float g = 0.f;
+    if (dtop != nullptr) g += __ldg(dtop + t * K1 + r);
+    if (r < K) {
+      if (dscore != nullptr) g += __ldg(dscore + t * K + r);
+      if (dgates != nullptr) g += __ldg(dgates + t * E + e);
+      if (dimp != nullptr) g += __ldg(dimp + e);
+    }
+    if ((e >> 2) == eg) {
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+        if ((e & 3) == c) dp[c] += g;
+    }
+  }
+  float dot = p[0] * dp[0] + p[1] * dp[1] + p[2] * dp[2] + p[3] * dp[3];
+#pragma unroll
+  for (int o = EG / 2; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
+  float o4[4];
+#pragma unroll
+  for (int c = 0; c < 4; ++c) o4[c] = p[c] * (dp[c] - dot);
+  if (dclean != nullptr) {
+    float4 a = __ldg(reinterpret_cast<const float4*>(dclean + te));
+    o4[0] += a.x; o4[1] += a.y; o4[2] += a.z; o4[3] += a.w;
+  }
+  if (dnoisy != nullptr) {
+    float4 a = __ldg(reinterpret_cast<const float4*>(dnoisy + te));
+    o4[0] += a.x; o4[1] += a.y; o4[2] += a.z; o4[3] += a.w;
+  }
+  if (valid) *reinterpret_cast<float4*>(dz + te) = make_float4(o4[0], o4[1], o4[2], o4[3]);
+}
+
+// partial dW[chunk][d][e] = sum_{t in chunk} x[t,d] * dz[t,e]; thread tile 4 d x EW experts.
+template <int EW, typename XT>
+__global__ void gate_bwd_dw_kernel(const XT* __restrict__ x, int64_t ldx, const float* __restrict__ dz, int T,
+                                   int D, int E, int tok_per_chunk, float* __restrict__ part,
+                                   float* __restrict__ cs_part) {
+  const int ngrp = blockDim.x / (D / 4);          // expert groups per CTA (EB / EW)
+  const int dq = threadIdx.x % (D / 4);
+  const int eh = threadIdx.x / (D / 4);
+  const int e0 = blockIdx.y * (EW * ngrp) + eh * EW;
+  const int t0 = blockIdx.x * tok_per_chunk;
+  const int t1 = min(T, t0 + tok_per_chunk);
+  float acc[4][EW];
+  float cs[EW];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int c = 0; c < EW; ++c) acc[i][c] = 0.f;
+#pragma unroll
+  for (int c = 0; c < EW; ++c) cs[c] = 0.f;
+#pragma unroll 4
+  for (int t = t0; t < t1; ++t) {
+    float xv[4];
+    if constexpr (sizeof(XT) == 4) {
+      float4 v = __ldg(reinterpret_cast<const float4*>(x + (int64_t)t * ldx + dq * 4));
+      xv[0] = v.x; xv[1] = v.y; xv[2] = v.z; xv[3] = v.w;
+    } else {
+      uint2 u = __ldg(reinterpret_cast<const uint2*>(x + (int64_t)t * ldx + dq * 4));
+      float2 a = bf16x2_to_float2(u.x), b = bf16x2_to_float2(u.y);
+      xv[0] = a.x; xv[1] = a.y; xv[2] = b.x; xv[3] = b.y;
+    }
+    float dv[EW];
+#pragma unroll
+    for (int c = 0; c < EW; c += 4) {
+      float4 v = __ldg(reinterpret_cast<const float4*>(dz + (int64_t)t * E + e0 + c));
+      dv[c] = v.x; dv[c + 1] = v.y; dv[c + 2] = v.z; dv[c + 3] = v.w;
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int c = 0; c < EW; ++c) acc[i][c] = fmaf(xv[i], dv[c], acc[i][c]);
+    if (dq == 0) {
+#pragma unroll
+      for (int c = 0; c < EW; ++c) cs[c] += dv[c];
+    }
+  }
+  float* dst = part + ((int64_t)blockIdx.x * D + dq * 4) * E + e0;
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int c = 0; c < EW; c += 4)
+      *reinterpret_cast<float4*>(dst + (int64_t)i * E + c) = make_float4(acc[i][c], acc[i][c + 1], acc[i][c + 2], acc[i][c + 3]);
+  if (dq == 0) {
+#pragma unroll
+    for (int c = 0; c < EW; ++c) cs_part[(int64_t)blockIdx.x * E + e0 + c] = cs[c];
+  }
+}
+
+// dW[d][e] = sum_chunks part (fixed order); task rows from the column sums of dz.
+__global__ void gate_bwd_reduce_kernel(const float* __restrict__ part, const float* __restrict__ cs_part,
+                                       int nchunk, int D, int Dt, int E, const float* __restrict__ task_feat,
+                                       const float* __restrict__ w_gate, float* __restrict__ dw,
+                                       float* __restrict__ dtask) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t n_main = (int64_t)D * E;
+  if (i < n_main) {
+    float a = 0.f;
+    for (int c = 0; c < nchunk; ++c) a += part[(int64_t)c * n_main + i];
+    dw[i] = a;
+  } else if (i < n_main + (int64_t)Dt * E) {
+    const int j = (int)((i - n_main) / E), e = (int)((i - n_main) % E);
+    float cs = 0.f;
+    for (int c = 0; c < nchunk; ++c) cs += cs_part[(int64_t)c * E + e];
+    dw[i] = __ldg(task_feat + j) * cs;
+  } else if (dtask != nullptr && i < n_main + (int64_t)Dt * E + Dt) {
+    const int j = (int)(i - n_main - (int64_t)Dt * E);
+    float a = 0.f;
+    for (int e = 0; e < E; ++e) {
+      float cs = 0.f;
+      for (int c = 0; c < nchunk; ++c) cs += cs_part[(int64_t)c * E + e];
+      a = fmaf(__ldg(w_gate + (int64_t)(D + j) * E + e), cs, a);
+    }
+    dtask[j] = a;
+  }
+}
+
+// standalone router dx: dxg[t, d] = sum_e dz[t,e] * w_gate[d,e]
+__global__ void gate_bwd_dx_kernel(const float* __restrict__ dz, const float* __restrict__ w_gate, int T, int D,
+                                   int E, float* __restrict__ dxg) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (int64_t)T * (D / 4)) return;
+  const int64_t t = i / (D / 4);
+  const int dq = (int)(i % (D / 4));
+  float a[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int e = 0; e < E; e += 4) {
+    float4 g = __ldg(reinterpret_cast<const float4*>(dz + t * E + e));
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      float4 w = __ldg(reinterpret_cast<const float4*>(w_gate + (int64_t)(dq * 4 + r) * E + e));
+      a[r] = fmaf(g.x, w.x, a[r]); a[r] = fmaf(g.y, w.y, a[r]);
+      a[r] = fmaf(g.z, w.z, a[r]); a[r] = fmaf(g.w, w.w, a[r]);
+    }
+  }
+  *reinterpret_cast<float4*>(dxg + t * D + dq * 4) = make_float4(a[0], a[1], a[2], a[3]);
+}
+
+static inline int gate_bwd_chunks(int T, int E) {
+  const int yb = (E > 16) ? E / 16 : 1;
+  int n = m3_ceil_div(T, 64);
+  int cap = (2 * kNumSMs) / yb;
+  if (cap < 1) cap = 1;
+  return n < cap ? (n < 1 ? 1 : n) : cap;
+}
+
+}  // namespace m3
+
+using namespace m3;
+
+extern "C" int m3_gate_num_partials(int T, int E) {
+  switch (E) {
+    case 4: return m3_ceil_div(T, gate_tokens_per_cta<4>(T));
+    case 8: return m3_ceil_div(T, gate_tokens_per_cta<8>(T));
+    case 16: return m3_ceil_div(T, gate_tokens_per_cta<16>(T));
+    case 32: return m3_ceil_div(T, gate_tokens_per_cta<32>(T));
+    case 64: return m3_ceil_div(T, gate_tokens_per_cta<64>(T));
+    case 128: return m3_ceil_div(T, gate_tokens_per_cta<128>(T));
+    default: return M3_ERR_SHAPE;
+  }
+}
+
+#define M3_GATE_ARGS x, ldx, task_feat, w_gate, noise, noise_stddev, T, D, Dt, K, K1, idx, idx_full, score, \
+                     top_vals, clean_logits, noisy_logits, gates, imp_partial, load_partial, st
+#define M3_GATE_CASE_T(EE, XT)                                               \
+  switch (gate_cfg_id<EE>(T)) {                                              \
+    case 2: return launch_gate_fwd<EE, 8, 4, XT>(M3_GATE_ARGS);              \
+    case 1: return launch_gate_fwd<EE, 4, 2, XT>(M3_GATE_ARGS);              \
+    default: return launch_gate_fwd<EE, 2, 1, XT>(M3_GATE_ARGS);             \
+  }
+#define M3_GATE_CASE(EE)                                    \
+  case EE:                                                  \
+    if (x_dtype == M3_F32) { M3_GATE_CASE_T(EE, float) }    \
+    else { M3_GATE_CASE_T(EE, __nv_bfloat16) }
+
+extern "C" int m3_gate_fwd(const void* x, int x_dtype, int64_t ldx, const float* task_feat, const float* w_gate,
+                           const float* noise, float noise_stddev, int T, int D, int Dt, int E, int K,
+                           int64_t* idx, int32_t* idx_full, float* score, float* top_vals, float* clean_logits,
+                           float* noisy_logits, float* gates, float* imp_partial, int32_t* load_partial,
+                           m3_stream_t stream) {
+  M3_CHECK_ARG(x && w_gate && idx && idx_full && score && top_vals && clean_logits && imp_partial && load_partial);
+  M3_CHECK_ARG(T >= 0 && D > 0 && Dt >= 0 && (Dt == 0 || task_feat));
+  M3_CHECK_SHAPE(D % kGateDC == 0 && K >= 1 && K <= E && K <= 8);
+  M3_CHECK_SHAPE(x_dtype == M3_F32 || x_dtype == M3_BF16);
+  const int el = x_dtype == M3_F32 ? 4 : 2;
+  M3_CHECK_ALIGN16(x); M3_CHECK_ALIGN16(w_gate); M3_CHECK_ALIGN16(clean_logits);
+  if ((ldx * el) % 16 != 0) return M3_ERR_ALIGN;
+  if (noise) M3_CHECK_ALIGN16(noise);
+  if (noisy_logits) M3_CHECK_ALIGN16(noisy_logits);
+  if (gates) M3_CHECK_ALIGN16(gates);
+  if (T == 0) return M3_OK;
+  const int K1 = K + 1 < E ? K + 1 : E;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  switch (E) {
+    M3_GATE_CASE(4)
+    M3_GATE_CASE(8)
+    M3_GATE_CASE(16)
+    M3_GATE_CASE(32)
+    M3_GATE_CASE(64)
+    M3_GATE_CASE(128)
+    default: return M3_ERR_SHAPE;
+  }
+}
+
+extern "C" size_t m3_gate_bwd_workspace_bytes(int T, int D, int Dt, int E) {
+  (void)Dt;
+  const size_t n = (size_t)gate_bwd_chunks(T, E);
+  return n * ((size_t)D * E + E) * sizeof(float);
+}
+
+extern "C" int m3_gate_bwd(const void* x, int x_dtype, int64_t ldx, const float* task_feat, const float* w_gate,
+                           const float* logits, const int32_t* idx_full, int T, int D, int Dt, int E, int K,
+                           const float* dscore, const float* dtop_vals, const float* dgates,
+                           const float* dimportance, const float* dclean, const float* dnoisy, float* dz,
+                           float* dw_gate, float* dtask_feat, float* dx_gate, void* workspace,
+                           size_t workspace_bytes, m3_stream_t stream) {
+  M3_CHECK_ARG(x && w_gate && logits && idx_full && dz && dw_gate && workspace);
+  M3_CHECK_ARG(T > 0 && D > 0 && Dt >= 0 && (Dt == 0 || task_feat));
+  M3_CHECK_SHAPE(D % 4 == 0 && D / 4 * 2 <= 1024 && K >= 1 && K <= E);
+  M3_CHECK_SHAPE(x_dtype == M3_F32 || x_dtype == M3_BF16);
+  M3_CHECK_ALIGN16(x); M3_CHECK_ALIGN16(w_gate); M3_CHECK_ALIGN16(logits); M3_CHECK_ALIGN16(dz);
+  if (dclean) M3_CHECK_ALIGN16(dclean);
+  if (dnoisy) M3_CHECK_ALIGN16(dnoisy);
+  if (workspace_bytes < m3_gate_bwd_workspace_bytes(T, D, Dt, E)) return M3_ERR_WORKSPACE;
+  const int K1 = K + 1 < E ? K + 1 : E;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  {
+    const int64_t nthr = (int64_t)T * (E / 4);
+    const int grid = (int)((nthr + 255) / 256);
+#define M3_DZ_CASE(EE) \
+  case EE: gate_bwd_dz_kernel<EE><<<grid, 256, 0, st>>>(logits, idx_full, T, K, K1, dscore, dtop_vals, dgates, dimportance, dclean, dnoisy, dz); break;
+    switch (E) {
+      M3_DZ_CASE(4) M3_DZ_CASE(8) M3_DZ_CASE(16) M3_DZ_CASE(32) M3_DZ_CASE(64) M3_DZ_CASE(128)
+      default: return M3_ERR_SHAPE;
+    }
+    M3_LAUNCH_CHECK();
+  }
+  const int nchunk = gate_bwd_chunks(T, E);
+  const int tok_per_chunk = m3_ceil_div(T, nchunk);
+  float* part = static_cast<float*>(workspace);
+  float* cs_part = part + (size_t)nchunk * D * E;
+  {
+    // EB experts per CTA (<=16), EW per thread (<=8)
+    const int EB = E < 16 ? E : 16;
+    const int EW = EB < 8 ? EB : 8;
+    dim3 grid(nchunk, E / EB);
+    const int threads = (D / 4) * (EB / EW);
+    if (x_dtype == M3_F32) {
+      if (EW == 8) gate_bwd_dw_kernel<8, float><<<grid, threads, 0, st>>>(static_cast<const float*>(x), ldx, dz, T, D, E, tok_per_chunk, part, cs_part);
+      else gate_bwd_dw_kernel<4, float><<<grid, threads, 0, st>>>(static_cast<const float*>(x), ldx, dz, T, D, E, tok_per_chunk, part, cs_part);
+    } else {
+      if (EW == 8) gate_bwd_dw_kernel<8, __nv_bfloat16><<<grid, threads, 0, st>>>(static_cast<const __nv_bfloat16*>(x), ldx, dz, T, D, E, tok_per_chunk, part, cs_part);
+      else gate_bwd_dw_kernel<4, __nv_bfloat16><<<grid, threads, 0, st>>>(static_cast<const __nv_bfloat16*>(x), ldx, dz, T, D, E, tok_per_chunk, part, cs_part);
+    }
+    M3_LAUNCH_CHECK();
+  }
+  {
+    const int64_t n = (int64_t)D * E + (int64_t)Dt * E + Dt;
+    gate_bwd_reduce_kernel<<<(int)((n + 255) / 256), 256, 0, st>>>(part, cs_part, nchunk, D, Dt, E, task_feat, w_gate,
+                                                                   dw_gate, dtask_feat);
+    M3_LAUNCH_CHECK();
+  }
+  if (dx_gate != nullptr) {
+    const int64_t n = (int64_t)T * (D / 4);
+    gate_bwd_dx_kernel<<<(int)((n + 255) / 256), 256, 0, st>>>(dz, w_gate, T, D, E, dx_gate);
+    M3_LAUNCH_CHECK();
+  }
+  return M3_OK;
+}

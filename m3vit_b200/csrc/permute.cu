@@ -1,0 +1,428 @@
+// Dispatch / combine row movers (forward + backward) for sm_100a.
+//
+// Replace fmoe's MOEScatter / MOEGather (torch.index_select / index_copy_ /
+// index_add_ on [R, D] buffers) and the torch.bmm gate-weighted combine of the
+// reference (/root/reference/models/moe/origin/custom_moe_layer.py:255-257,283-297).
+//
+// All four kernels are HBM-bound.  A token is owned by 16 lanes (half a warp);
+// each lane moves 8-element slices as single 128-bit transactions, so a queue
+// row (D*2 B in bf16) is written/read as whole 128-byte lines.  Loads are issued
+// before any store (memory-level parallelism), with L1::no_allocate streaming
+// hints: every byte is touched exactly once.
+//
+//   algorithmic bytes per token (bf16 queues, el=2, x fp32 = 4):
+//     dispatch_fwd  D*el_x + K*D*el + K*4            combine_fwd  K*D*el + K*8 + D*el_out
+//     combine_bwd   D*el_g + 2*K*D*el + K*12         dispatch_bwd K*D*el + K*4 + D*el_dx
+#include "common.cuh"
+
+namespace m3 {
+
+constexpr int kLanesPerTok = 16;
+constexpr int kPermThreads = 256;
+constexpr int kTokPerCta = kPermThreads / kLanesPerTok;
+constexpr int kMaxVec = 8;  // per-lane 8-element slices: D <= 16*8*8 = 1024
+
+// Queue addressing.  Single GPU: every queue row lives in the local buffer.
+// Expert parallel (EP): slot s belongs to rank slot_rank[s]; its row lives in that
+// rank's queue, reached through a peer-mapped base pointer (NVLink load/store).
+template <typename T>
+struct Queue {
+  T* local;
+  T* const* bases;           // [W] device array of peer-mapped queue bases (EP only)
+  const int32_t* slot_rank;  // [T*K] owner rank of every slot (EP only)
+  template <bool EP>
+  __device__ __forceinline__ T* row(int64_t slot, int r, int D) const {
+    T* b = EP ? bases[__ldg(slot_rank + slot)] : local;
+    return b + (int64_t)r * D;
+  }
+};
+
+template <typename TO>
+__device__ __forceinline__ void zero_pad_rows(TO* q, const int32_t* counts, const int32_t* offsets, int e, int D) {
+  const int r0 = offsets[e] + counts[e], r1 = offsets[e + 1];
+  const int nvec = D / 8;
+  Vec8 z;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) z.v[i] = 0.f;
+  for (int64_t i = threadIdx.x; i < (int64_t)(r1 - r0) * nvec; i += kPermThreads)
+    store8<TO>(q + ((int64_t)r0 + i / nvec) * D + (i % nvec) * 8, z);
+}
+
+template <typename TO>
+__global__ void __launch_bounds__(kPermThreads)
+zero_pad_rows_kernel(TO* __restrict__ q, const int32_t* __restrict__ counts, const int32_t* __restrict__ offsets, int D) {
+  zero_pad_rows<TO>(q, counts, offsets, blockIdx.x, D);
+}
+
+// xq[pos[t,k]] = cast(x[t]); trailing CTAs zero the padding rows of every queue.
+template <typename TI, typename TO, int NV, bool EP>
+__global__ void __launch_bounds__(kPermThreads)
+dispatch_fwd_kernel(const TI* __restrict__ x, const int32_t* __restrict__ pos, const int32_t* __restrict__ counts,
+                    const int32_t* __restrict__ offsets, int T, int K, int D, int tok_ctas, Queue<TO> xq) {
+  if ((int)blockIdx.x >= tok_ctas) {
+    // zero rows [off[e]+cnt[e], off[e+1]) of expert e (local queue only)
+    zero_pad_rows<TO>(xq.local, counts, offsets, blockIdx.x - tok_ctas, D);
+    return;
+  }
+  const int sub = threadIdx.x % kLanesPerTok;
+  const int t = blockIdx.x * kTokPerCta + threadIdx.x / kLanesPerTok;
+  if (t >= T) return;
+  const int nvec = D / 8;
+  Vec8 v[NV];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int c = sub + i * kLanesPerTok;
+    if (c < nvec) v[i] = load8<TI>(x + (int64_t)t * D + c * 8);
+  }
+  for (int k = 0; k < K; ++k) {
+    const int row = __ldg(pos + (int64_t)t * K + k);
+    if (row < 0) continue;  // dropped slot
+    TO* dst = xq.template row<EP>((int64_t)t * K + k, row, D);
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int c = sub + i * kLanesPerTok;
+      if (c < nvec) store8<TO>(dst + c * 8, v[i]);
+    }
+  }
+}
+
+// out[t] = sum_k score[t,k] * yq[pos[t,k]]   (fp32 accumulation, k ascending like bmm)
+template <typename TI, typename TO, int NV, bool EP>
+__global__ void __launch_bounds__(kPermThreads)
+combine_fwd_kernel(Queue<const TI> yq, const int32_t* __restrict__ pos, const float* __restrict__ score,
+                   int T, int K, int D, TO* __restrict__ out) {
+  const int sub = threadIdx.x % kLanesPerTok;
+  const int t = blockIdx.x * kTokPerCta + threadIdx.x / kLanesPerTok;
+  if (t >= T) return;
+  const int nvec = D / 8;
+  Vec8 acc[NV];
+#pragma unroll
+  for (int i = 0; i < NV; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[i].v[j] = 0.f;
+  for (int k = 0; k < K; ++k) {
+    const int row = __ldg(pos + (int64_t)t * K + k);
+    if (row < 0) continue;
+    const float s = __ldg(score + (int64_t)t * K + k);
+    const TI* src = yq.template row<EP>((int64_t)t * K + k, row, D);
+    Vec8 v[NV];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int c = sub + i * kLanesPerTok;
+      if (c < nvec) v[i] = load8<TI>(src + c * 8);
+    }
+#pragma unroll
+    for (int i = 0; i < NV; ++i)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[i].v[j] = fmaf(s, v[i].v[j], acc[i].v[j]);
+  }
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int c = sub + i * kLanesPerTok;
+    if (c < nvec) store8<TO>(out + (int64_t)t * D + c * 8, acc[i]);
+  }
+}
+
+// dscore[t,k] = <g[t], yq[pos[t,k]]>;  dyq[pos[t,k]] = score[t,k] * g[t];  zero dyq padding rows
+template <typename TG, typename TQ, int NV, bool EP>
+__global__ void __launch_bounds__(kPermThreads)
+combine_bwd_kernel(const TG* __restrict__ g, Queue<const TQ> yq, const int32_t* __restrict__ pos,
+                   const float* __restrict__ score, const int32_t* __restrict__ counts,
+                   const int32_t* __restrict__ offsets, int T, int K, int D, int tok_ctas,
+                   Queue<TQ> dyq, float* __restrict__ dscore) {
+  if ((int)blockIdx.x >= tok_ctas) {
+    zero_pad_rows<TQ>(dyq.local, counts, offsets, blockIdx.x - tok_ctas, D);
+    return;
+  }
+  const int sub = threadIdx.x % kLanesPerTok;
+  const int tt = blockIdx.x * kTokPerCta + threadIdx.x / kLanesPerTok;
+  const bool valid = tt < T;
+  const int t = valid ? tt : T - 1;  // keep all lanes alive for the shuffles
+  const int nvec = D / 8;
+  Vec8 gv[NV];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int c = sub + i * kLanesPerTok;
+    if (c < nvec) gv[i] = load8<TG>(g + (int64_t)t * D + c * 8);
+  }
+  for (int k = 0; k < K; ++k) {
+    const int row = __ldg(pos + (int64_t)t * K + k);
+    const float s = __ldg(score + (int64_t)t * K + k);
+    float dot = 0.f;
+    if (row >= 0) {
+      const TQ* ysrc = yq.template row<EP>((int64_t)t * K + k, row, D);
+      TQ* ddst = dyq.template row<EP>((int64_t)t * K + k, row, D);
+      Vec8 yv[NV];
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        const int c = sub + i * kLanesPerTok;
+        if (c < nvec) yv[i] = load8<TQ>(ysrc + c * 8);
+      }
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        const int c = sub + i * kLanesPerTok;
+        if (c < nvec) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) dot = fmaf(gv[i].v[j], yv[i].v[j], dot);
+          if (valid) {
+            Vec8 o;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) o.v[j] = s * gv[i].v[j];
+            store8<TQ>(ddst + c * 8, o);
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int o = kLanesPerTok / 2; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
+    if (valid && sub == 0) dscore[(int64_t)t * K + k] = dot;
+  }
+}
+
+// dx[t] = sum_k dxq[pos[t,k]]  (+ dz[t] @ w_gate[:D]^T : the router's dx, gate input == layer input)
+template <typename TI, typename TO, int NV, bool EP>
+__global__ void __launch_bounds__(kPermThreads)
+dispatch_bwd_kernel(Queue<const TI> dxq, const int32_t* __restrict__ pos, int T, int K, int D,
+                    const float* __restrict__ dz, const float* __restrict__ w_gate, int E,
+                    TO* __restrict__ dx) {
+  const int sub = threadIdx.x % kLanesPerTok;
+  const int t = blockIdx.x * kTokPerCta + threadIdx.x / kLanesPerTok;
+  if (t >= T) return;
+  const int nvec = D / 8;
+  Vec8 acc[NV];
+#pragma unroll
+  for (int i = 0; i < NV; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[i].v[j] = 0.f;
+  for (int k = 0; k < K; ++k) {
+    const int row = __ldg(pos + (int64_t)t * K + k);
+    if (row < 0) continue;
+    const TI* src = dxq.template row<EP>((int64_t)t * K + k, row, D);
+    Vec8 v[NV];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int c = sub + i * kLanesPerTok;
+      if (c < nvec) v[i] = load8<TI>(src + c * 8);
+    }
+#pragma unroll
+    for (int i = 0; i < NV; ++i)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[i].v[j] += v[i].v[j];
+  }
+  if (dz != nullptr) {
+    for (int e = 0; e < E; e += 4) {
+      const float4 gz = __ldg(reinterpret_cast<const float4*>(dz + (int64_t)t * E + e));
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        const int c = sub + i * kLanesPerTok;
+        if (c < nvec) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 w = __ldg(reinterpret_cast<const float4*>(w_gate + (int64_t)(c * 8 + j) * E + e));
+            float a = acc[i].v[j];
+            a = fmaf(gz.x, w.x, a); a = fmaf(gz.y, w.y, a);
+            a = fmaf(gz.z, w.z, a); a = fmaf(gz.w, w.w, a);
+            acc[i].v[j] = a;
+          }
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int c = sub + i * kLanesPerTok;
+    if (c < nvec) store8<TO>(dx + (int64_t)t * D + c * 8, acc[i]);
+  }
+}
+
+static inline int perm_nv(int D) { return m3_ceil_div(D / 8, kLanesPerTok); }
+
+}  // namespace m3
+
+using namespace m3;
+typedef __nv_bfloat16 bf16;
+
+static int perm_common_check(int T, int K, int D) {
+  if (T < 0 || K < 1 || D < 8) return M3_ERR_ARG;
+  if (D % 8 != 0 || D > kLanesPerTok * kMaxVec * 8) return M3_ERR_SHAPE;
+  const int nv = perm_nv(D);
+  if (!(nv == 1 || nv == 2 || nv == 3 || nv == 4 || nv == 6 || nv == 8)) return M3_ERR_SHAPE;
+  return M3_OK;
+}
+
+#define M3_NV_SWITCH(...)                          \
+  switch (nv) {                                    \
+    case 1: { constexpr int NV = 1; __VA_ARGS__; } break; \
+    case 2: { constexpr int NV = 2; __VA_ARGS__; } break; \
+    case 3: { constexpr int NV = 3; __VA_ARGS__; } break; \
+    case 4: { constexpr int NV = 4; __VA_ARGS__; } break; \
+    case 6: { constexpr int NV = 6; __VA_ARGS__; } break; \
+    case 8: { constexpr int NV = 8; __VA_ARGS__; } break; \
+    default: return M3_ERR_SHAPE;                  \
+  }
+// runs BODY with type aliases TA / TB bound to the two dtypes
+#define M3_DTYPE2_SWITCH(da, db, ...)                                                           \
+  if (da == M3_F32 && db == M3_F32) { using TA = float; using TB = float; __VA_ARGS__ }         \
+  else if (da == M3_F32 && db == M3_BF16) { using TA = float; using TB = bf16; __VA_ARGS__ }    \
+  else if (da == M3_BF16 && db == M3_F32) { using TA = bf16; using TB = float; __VA_ARGS__ }    \
+  else if (da == M3_BF16 && db == M3_BF16) { using TA = bf16; using TB = bf16; __VA_ARGS__ }    \
+  else return M3_ERR_UNSUPPORTED;
+
+template <bool EP>
+static int dispatch_fwd_impl(const void* x, int x_dtype, const int32_t* pos, const int32_t* counts,
+                             const int32_t* offsets, int T, int K, int D, int E, void* xq, void* const* peer,
+                             const int32_t* slot_rank, int xq_dtype, cudaStream_t st) {
+  int rc = perm_common_check(T, K, D);
+  if (rc) return rc;
+  const int nv = perm_nv(D);
+  const int tok_ctas = m3_ceil_div(T, kTokPerCta);
+  const int grid = tok_ctas + (EP ? 0 : E);
+  if (grid == 0) return M3_OK;
+  M3_DTYPE2_SWITCH(x_dtype, xq_dtype, {
+    Queue<TB> q{(TB*)xq, (TB* const*)peer, slot_rank};
+    M3_NV_SWITCH((dispatch_fwd_kernel<TA, TB, NV, EP><<<grid, kPermThreads, 0, st>>>((const TA*)x, pos, counts, offsets, T, K, D, tok_ctas, q)))
+  })
+  M3_LAUNCH_CHECK();
+  return M3_OK;
+}
+
+template <bool EP>
+static int combine_fwd_impl(const void* yq, void* const* peer, const int32_t* slot_rank, int yq_dtype,
+                            const int32_t* pos, const float* score, int T, int K, int D, void* out, int out_dtype,
+                            cudaStream_t st) {
+  int rc = perm_common_check(T, K, D);
+  if (rc) return rc;
+  if (T == 0) return M3_OK;
+  const int nv = perm_nv(D);
+  const int grid = m3_ceil_div(T, kTokPerCta);
+  M3_DTYPE2_SWITCH(yq_dtype, out_dtype, {
+    Queue<const TA> q{(const TA*)yq, (const TA* const*)peer, slot_rank};
+    M3_NV_SWITCH((combine_fwd_kernel<TA, TB, NV, EP><<<grid, kPermThreads, 0, st>>>(q, pos, score, T, K, D, (TB*)out)))
+  })
+  M3_LAUNCH_CHECK();
+  return M3_OK;
+}
+
+template <bool EP>
+static int combine_bwd_impl(const void* g, int g_dtype, const void* yq, void* const* peer_yq, void* dyq,
+                            void* const* peer_dyq, const int32_t* slot_rank, int q_dtype, const int32_t* pos,
+                            const float* score, const int32_t* counts, const int32_t* offsets, int T, int K, int D,
+                            int E, float* dscore, cudaStream_t st) {
+  int rc = perm_common_check(T, K, D);
+  if (rc) return rc;
+  const int nv = perm_nv(D);
+  const int tok_ctas = m3_ceil_div(T, kTokPerCta);
+  const int grid = tok_ctas + (EP ? 0 : E);
+  if (grid == 0) return M3_OK;
+  M3_DTYPE2_SWITCH(g_dtype, q_dtype, {
+    Queue<const TB> qy{(const TB*)yq, (const TB* const*)peer_yq, slot_rank};
+    Queue<TB> qd{(TB*)dyq, (TB* const*)peer_dyq, slot_rank};
+    M3_NV_SWITCH((combine_bwd_kernel<TA, TB, NV, EP><<<grid, kPermThreads, 0, st>>>((const TA*)g, qy, pos, score, counts, offsets, T, K, D, tok_ctas, qd, dscore)))
+  })
+  M3_LAUNCH_CHECK();
+  return M3_OK;
+}
+
+template <bool EP>
+static int dispatch_bwd_impl(const void* dxq, void* const* peer, const int32_t* slot_rank, int dxq_dtype,
+                             const int32_t* pos, int T, int K, int D, const float* dz, const float* w_gate, int E,
+                             void* dx, int dx_dtype, cudaStream_t st) {
+  int rc = perm_common_check(T, K, D);
+  if (rc) return rc;
+  if (T == 0) return M3_OK;
+  const int nv = perm_nv(D);
+  const int grid = m3_ceil_div(T, kTokPerCta);
+  M3_DTYPE2_SWITCH(dxq_dtype, dx_dtype, {
+    Queue<const TA> q{(const TA*)dxq, (const TA* const*)peer, slot_rank};
+    M3_NV_SWITCH((dispatch_bwd_kernel<TA, TB, NV, EP><<<grid, kPermThreads, 0, st>>>(q, pos, T, K, D, dz, w_gate, E, (TB*)dx)))
+  })
+  M3_LAUNCH_CHECK();
+  return M3_OK;
+}
+
+extern "C" int m3_dispatch_fwd(const void* x, int x_dtype, const int32_t* pos, const int32_t* counts,
+                               const int32_t* offsets, int T, int K, int D, int E, void* xq, int xq_dtype,
+                               m3_stream_t stream) {
+  M3_CHECK_ARG(x && pos && counts && offsets && xq && E >= 1);
+  M3_CHECK_ALIGN16(x); M3_CHECK_ALIGN16(xq);
+  return dispatch_fwd_impl<false>(x, x_dtype, pos, counts, offsets, T, K, D, E, xq, nullptr, nullptr, xq_dtype,
+                                  static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int m3_combine_fwd(const void* yq, int yq_dtype, const int32_t* pos, const float* score, int T, int K,
+                              int D, void* out, int out_dtype, m3_stream_t stream) {
+  M3_CHECK_ARG(yq && pos && score && out);
+  M3_CHECK_ALIGN16(yq); M3_CHECK_ALIGN16(out);
+  return combine_fwd_impl<false>(yq, nullptr, nullptr, yq_dtype, pos, score, T, K, D, out, out_dtype,
+                                 static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int m3_combine_bwd(const void* g, int g_dtype, const void* yq, int yq_dtype, const int32_t* pos,
+                              const float* score, const int32_t* counts, const int32_t* offsets, int T, int K,
+                              int D, int E, void* dyq, int dyq_dtype, float* dscore, m3_stream_t stream) {
+  M3_CHECK_ARG(g && yq && pos && score && counts && offsets && dyq && dscore && E >= 1);
+  if (yq_dtype != dyq_dtype) return M3_ERR_UNSUPPORTED;
+  M3_CHECK_ALIGN16(g); M3_CHECK_ALIGN16(yq); M3_CHECK_ALIGN16(dyq);
+  return combine_bwd_impl<false>(g, g_dtype, yq, nullptr, dyq, nullptr, nullptr, yq_dtype, pos, score, counts,
+                                 offsets, T, K, D, E, dscore, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int m3_dispatch_bwd(const void* dxq, int dxq_dtype, const int32_t* pos, int T, int K, int D,
+                               const float* dz, const float* w_gate, int E, void* dx, int dx_dtype,
+                               m3_stream_t stream) {
+  M3_CHECK_ARG(dxq && pos && dx);
+  M3_CHECK_ARG(dz == nullptr || (w_gate != nullptr && E >= 4 && E % 4 == 0));
+  M3_CHECK_ALIGN16(dxq); M3_CHECK_ALIGN16(dx);
+  if (dz) { M3_CHECK_ALIGN16(dz); M3_CHECK_ALIGN16(w_gate); }
+  return dispatch_bwd_impl<false>(dxq, nullptr, nullptr, dxq_dtype, pos, T, K, D, dz, w_gate, E, dx, dx_dtype,
+                                  static_cast<cudaStream_t>(stream));
+}
+
+// ---- expert-parallel variants: rows live in the owner rank's queue (peer pointers)
+extern "C" int m3_ep_dispatch_fwd(const void* x, int x_dtype, const int32_t* dst_rank, const int32_t* dst_row, int T,
+                                  int K, int D, void* const* peer_xq, int xq_dtype, m3_stream_t stream) {
+  M3_CHECK_ARG(x && dst_rank && dst_row && peer_xq);
+  M3_CHECK_ALIGN16(x);
+  return dispatch_fwd_impl<true>(x, x_dtype, dst_row, nullptr, nullptr, T, K, D, 0, nullptr, peer_xq, dst_rank,
+                                 xq_dtype, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int m3_ep_combine_fwd(void* const* peer_yq, int yq_dtype, const int32_t* dst_rank, const int32_t* dst_row,
+                                 const float* score, int T, int K, int D, void* out, int out_dtype,
+                                 m3_stream_t stream) {
+  M3_CHECK_ARG(peer_yq && dst_rank && dst_row && score && out);
+  M3_CHECK_ALIGN16(out);
+  return combine_fwd_impl<true>(nullptr, peer_yq, dst_rank, yq_dtype, dst_row, score, T, K, D, out, out_dtype,
+                                static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int m3_ep_combine_bwd(const void* g, int g_dtype, void* const* peer_yq, void* const* peer_dyq, int q_dtype,
+                                 const int32_t* dst_rank, const int32_t* dst_row, const float* score, int T, int K,
+                                 int D, float* dscore, m3_stream_t stream) {
+  M3_CHECK_ARG(g && peer_yq && peer_dyq && dst_rank && dst_row && score && dscore);
+  M3_CHECK_ALIGN16(g);
+  return combine_bwd_impl<true>(g, g_dtype, nullptr, peer_yq, nullptr, peer_dyq, dst_rank, q_dtype, dst_row, score,
+                                nullptr, nullptr, T, K, D, 0, dscore, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int m3_ep_dispatch_bwd(void* const* peer_dxq, int dxq_dtype, const int32_t* dst_rank,
+                                  const int32_t* dst_row, int T, int K, int D, const float* dz, const float* w_gate,
+                                  int E, void* dx, int dx_dtype, m3_stream_t stream) {
+  M3_CHECK_ARG(peer_dxq && dst_rank && dst_row && dx);
+  M3_CHECK_ARG(dz == nullptr || (w_gate != nullptr && E >= 4 && E % 4 == 0));
+  M3_CHECK_ALIGN16(dx);
+  return dispatch_bwd_impl<true>(nullptr, peer_dxq, dst_rank, dxq_dtype, dst_row, T, K, D, dz, w_gate, E, dx,
+                                 dx_dtype, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int m3_zero_pad_rows(void* q, int dtype, const int32_t* counts, const int32_t* offsets, int E, int D,
+                                m3_stream_t stream) {
+  M3_CHECK_ARG(q && counts && offsets && E >= 1 && D >= 8 && D % 8 == 0);
+  M3_CHECK_ALIGN16(q);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (dtype == M3_F32) zero_pad_rows_kernel<float><<<E, kPermThreads, 0, st>>>((float*)q, counts, offsets, D);
+  else if (dtype == M3_BF16) zero_pad_rows_kernel<bf16><<<E, kPermThreads, 0, st>>>((bf16*)q, counts, offsets, D);
+  else return M3_ERR_UNSUPPORTED;
+  M3_LAUNCH_CHECK();
+  return M3_OK;
+}

@@ -1,0 +1,186 @@
+// Route plan: expert counts, padded prefix sum, stable queue positions, tile map.
+//
+// Replaces fmoe_cuda.expert_count + assign_pos and the host-side cumsum / D2H sync
+// of fmoe.functions.prepare_forward (reached from the reference at
+// /root/reference/models/moe/origin/custom_moe_layer.py:255-257).  Differences by
+// design: (1) positions are STABLE (rows of one expert keep flat-slot order; fmoe's
+// atomicSub order is nondeterministic), (2) every expert queue is padded to a
+// multiple of `pad` rows so the grouped GEMM only ever sees full 128-row tiles,
+// (3) nothing is read back to the host.
+//
+// Two launches: per-block histograms, then a block-local stable rank + the
+// cross-block prefix (each block re-derives its own prefix from the histogram
+// table, so there is no inter-block dependency and no atomics).
+// Integer work only; HBM traffic = 8+4 B per slot.  Bit-exact vs the oracle.
+#include "common.cuh"
+
+namespace m3 {
+
+constexpr int kRouteChunk = 2048;   // slots per block
+constexpr int kRouteThreads = 256;
+constexpr int kRouteBatches = kRouteChunk / 32;
+
+__global__ void __launch_bounds__(kRouteThreads)
+route_count_kernel(const int64_t* __restrict__ idx, int R, int E, int32_t* __restrict__ block_hist) {
+  extern __shared__ int hist[];
+  for (int e = threadIdx.x; e < E; e += kRouteThreads) hist[e] = 0;
+  __syncthreads();
+  const int base = blockIdx.x * kRouteChunk;
+  for (int i = threadIdx.x; i < kRouteChunk; i += kRouteThreads) {
+    const int s = base + i;
+    if (s < R) {
+      const int64_t e = idx[s];
+      if (e >= 0 && e < E) atomicAdd(&hist[(int)e], 1);
+    }
+  }
+  __syncthreads();
+  for (int e = threadIdx.x; e < E; e += kRouteThreads) block_hist[(int64_t)blockIdx.x * E + e] = hist[e];
+}
+
+__global__ void __launch_bounds__(kRouteThreads)
+route_assign_kernel(const int64_t* __restrict__ idx, int R, int E, int pad, int nblk,
+                    const int32_t* __restrict__ block_hist, const float* __restrict__ imp_partial,
+                    const int32_t* __restrict__ load_partial, int n_partial, int32_t* __restrict__ counts,
+                    int32_t* __restrict__ offsets, int32_t* __restrict__ pos,
+                    int32_t* __restrict__ tile_expert, float* __restrict__ importance,
+                    float* __restrict__ load) {
+  extern __shared__ int sm[];
+  int* tot = sm;                     // [E] total count per expert
+  int* pre = tot + E;                // [E] count in blocks before this one
+  int* off = pre + E;                // [E+1] padded offsets
+  int* bh = off + E + 1;             // [kRouteBatches][E] per-warp-batch histogram / prefix
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int b = blockIdx.x;
+
+  for (int i = tid; i < 2 * E; i += kRouteThreads) sm[i] = 0;
+  for (int i = tid; i < kRouteBatches * E; i += kRouteThreads) bh[i] = 0;
+  __syncthreads();
+  // totals and this block's cross-block prefix (integer adds: order-free)
+  for (int i = tid; i < nblk * E; i += kRouteThreads) {
+    const int bb = i / E, e = i % E;
+    const int v = block_hist[i];
+    if (v) {
+      atomicAdd(&tot[e], v);
+      if (bb < b) atomicAdd(&pre[e], v);
+    }
+  }
+  __syncthreads();
+  if (tid == 0) {
+    int run = 0;
+    for (int e = 0; e < E; ++e) {
+      off[e] = run;
+      run += (tot[e] + pad - 1) / pad * pad;
+    }
+    off[E] = run;
+  }
+  // stable rank inside the block: pass 1, per-batch histograms via match_any
+  const int base = b * kRouteChunk;
+  int my_e[kRouteBatches / 8], my_rank[kRouteBatches / 8];
+#pragma unroll
+  for (int i = 0; i < kRouteBatches / 8; ++i) {
+    const int wb = warp + 8 * i;
+    const int s = base + wb * 32 + lane;
+    int e = -1;
+    if (s < R) {
+      const int64_t ee = idx[s];
+      if (ee >= 0 && ee < E) e = (int)ee;
+    }
+    const unsigned mask = __match_any_sync(0xffffffffu, e);
+    const int rank = __popc(mask & ((1u << lane) - 1u));
+    if (e >= 0 && rank == 0) bh[wb * E + e] = __popc(mask);
+    my_e[i] = e;
+    my_rank[i] = rank;
+  }
+  __syncthreads();
+  // exclusive scan over batches, per expert
+  for (int e = tid; e < E; e += kRouteThreads) {
+    int run = 0;
+    for (int wb = 0; wb < kRouteBatches; ++wb) {
+      const int v = bh[wb * E + e];
+      bh[wb * E + e] = run;
+      run += v;
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < kRouteBatches / 8; ++i) {
+    const int wb = warp + 8 * i;
+    const int s = base + wb * 32 + lane;
+    if (s < R) {
+      const int e = my_e[i];
+      pos[s] = e >= 0 ? off[e] + pre[e] + bh[wb * E + e] + my_rank[i] : -1;
+    }
+  }
+  if (b == 0) {
+    for (int e = tid; e < E; e += kRouteThreads) counts[e] = tot[e];
+    for (int e = tid; e <= E; e += kRouteThreads) offsets[e] = off[e];
+    const int ntile = off[E] / pad;
+    for (int i = tid; i < ntile; i += kRouteThreads) {
+      const int row = i * pad;
+      int lo = 0, hi = E;  // largest e with off[e] <= row
+      while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (off[mid] <= row) lo = mid; else hi = mid;
+      }
+      // skip empty experts sharing the same offset: off[lo] <= row < off[lo+1] must hold
+      while (lo + 1 < E && off[lo + 1] <= row) ++lo;
+      tile_expert[i] = lo;
+    }
+    if (importance != nullptr && imp_partial != nullptr) {
+      for (int e = tid; e < E; e += kRouteThreads) {
+        float a = 0.f;
+        int l = 0;
+        for (int i = 0; i < n_partial; ++i) {
+          a += imp_partial[(int64_t)i * E + e];
+          l += load_partial[(int64_t)i * E + e];
+        }
+        importance[e] = a;
+        if (load != nullptr) load[e] = (float)l;
+      }
+    }
+  }
+}
+
+}  // namespace m3
+
+using namespace m3;
+
+extern "C" size_t m3_route_plan_workspace_bytes(int T, int K, int E) {
+  const int64_t R = (int64_t)T * K;
+  const int64_t nblk = (R + kRouteChunk - 1) / kRouteChunk;
+  return (size_t)(nblk > 0 ? nblk : 1) * E * sizeof(int32_t);
+}
+
+extern "C" int m3_route_max_rows(int T, int K, int E, int pad) {
+  // sum_e roundup(c_e, pad) <= R + E*(pad-1), rounded up to a whole tile
+  const int64_t R = (int64_t)T * K;
+  const int64_t cap = (R + (int64_t)E * (pad - 1) + pad - 1) / pad * pad;
+  return (int)cap;
+}
+
+extern "C" int m3_route_max_tiles(int T, int K, int E, int pad) { return m3_route_max_rows(T, K, E, pad) / pad; }
+
+extern "C" int m3_route_plan(const int64_t* idx, int T, int K, int E, int pad, const float* imp_partial,
+                             const int32_t* load_partial, int n_partial, int32_t* counts, int32_t* offsets,
+                             int32_t* pos, int32_t* tile_expert, float* importance, float* load,
+                             void* workspace, size_t workspace_bytes, m3_stream_t stream) {
+  M3_CHECK_ARG(idx && counts && offsets && pos && tile_expert && workspace);
+  M3_CHECK_ARG(T >= 0 && K >= 1 && E >= 1 && pad >= 1);
+  M3_CHECK_SHAPE(E <= 128);
+  if ((int64_t)T * K > (int64_t)1 << 30) return M3_ERR_SHAPE;
+  if (workspace_bytes < m3_route_plan_workspace_bytes(T, K, E)) return M3_ERR_WORKSPACE;
+  if (importance != nullptr && (imp_partial == nullptr || load_partial == nullptr)) return M3_ERR_ARG;
+  const int R = T * K;
+  int nblk = m3_ceil_div(R, kRouteChunk);
+  if (nblk < 1) nblk = 1;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  int32_t* block_hist = static_cast<int32_t*>(workspace);
+  route_count_kernel<<<nblk, kRouteThreads, E * sizeof(int), st>>>(idx, R, E, block_hist);
+  M3_LAUNCH_CHECK();
+  const size_t smem = (size_t)(3 * E + 1 + kRouteBatches * E) * sizeof(int);
+  route_assign_kernel<<<nblk, kRouteThreads, smem, st>>>(idx, R, E, pad, nblk, block_hist, imp_partial, load_partial,
+                                                          n_partial, counts, offsets, pos, tile_expert, importance,
+                                                          load);
+  M3_LAUNCH_CHECK();
+  return M3_OK;
+}

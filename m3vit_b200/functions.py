@@ -1,0 +1,179 @@
+"""Autograd wiring of the MoE hot path over the C-ABI ops (m3vit_b200/ops.py).
+
+`MoEFunction` is the whole layer of the reference in one autograd node
+(/root/reference/models/moe/origin/custom_moe_layer.py:184-314):
+
+    gate -> route plan -> dispatch -> expert FFN -> combine
+
+replacing fmoe's prepare_forward / MOEScatter / MOELinear x2 / MOEGather
+autograd Functions and the torch.bmm.  `GateFunction` and `ExpertsFunction` are
+the same ops split at the routing boundary, for callers that compute or consume
+routing on their own (NoisyGate_VMoE used stand-alone; the token-MoE experts-only
+entry, models/moe/token/custom_moe_layer.py:88-156).
+
+Nothing here touches the host: no .item(), no .cpu() - the reference's
+per-layer D2H sync (fmoe prepare_forward) is gone.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+
+from . import ops
+from ._lib import PAD_ROWS
+
+
+def _c(t):
+    return None if t is None else t.contiguous()
+
+
+class MoEFunction(torch.autograd.Function):
+    """inputs : x[T,D], gate_x[T,Dg0] or None (=x), w_gate[Dg,E], task_feat[Dt]|None,
+                w1[E,H,D], b1[E,H], w2[E,D,H], b2[E,D] (fp32 masters),
+                noise[T,E]|None, then non-tensor config.
+       outputs: out[T,D], score[T,K], top_vals[T,K1], clean[T,E], noisy[T,E],
+                gates[T,E]|empty, importance[E], load[E], idx[T,K], counts[E]"""
+
+    @staticmethod
+    def forward(ctx, x, gate_x, w_gate, task_feat, w1, b1, w2, b2, noise, top_k, noise_stddev, compute_dtype,
+                want_gates, wcache):
+        T, D = x.shape
+        E, H, _ = w1.shape
+        x = _c(x)
+        gx = x if gate_x is None else _c(gate_x)
+        g = ops.gate_fwd(gx, w_gate, top_k, task_feat, noise, noise_stddev, want_gates)
+        plan = ops.route_plan(g.idx, E, PAD_ROWS, g.imp_partial, g.load_partial)
+        xq = ops.dispatch_fwd(x, plan, top_k, out_dtype=compute_dtype)
+        if compute_dtype == torch.bfloat16:
+            w1c, w2c, w1t, w2t = wcache.get_bf16(w1, w2)
+        else:
+            w1c, w2c, w1t, w2t = w1, w2, None, None
+        needs_grad = any(ctx.needs_input_grad)
+        yq, hpre = ops.ffn_fwd(xq, plan, w1c, b1, w2c, b2, save_hpre=needs_grad)
+        out = ops.combine_fwd(yq, plan, g.score, out_dtype=x.dtype)
+        if needs_grad:
+            ctx.save_for_backward(x, gate_x, w_gate, task_feat, w1c, w2c, w1t, w2t, xq, hpre, yq, g.score,
+                                  g.noisy_logits, g.idx_full, plan.counts, plan.offsets, plan.pos, plan.tile_expert)
+            ctx.cfg = (top_k, plan.cap_rows, gate_x is not None)
+        gates = g.gates if g.gates is not None else x.new_empty(0)
+        ctx.mark_non_differentiable(g.idx, plan.load, plan.counts)
+        if noise is None:
+            # clean and noisy logits are the same tensor: hand out one differentiable view each
+            noisy = g.clean_logits.view_as(g.clean_logits)
+        else:
+            noisy = g.noisy_logits
+        return out, g.score, g.top_vals, g.clean_logits, noisy, gates, plan.importance, plan.load, g.idx, plan.counts
+
+    @staticmethod
+    def backward(ctx, d_out, d_score, d_top, d_clean, d_noisy, d_gates, d_imp, _dl, _di, _dc):
+        (x, gate_x, w_gate, task_feat, w1c, w2c, w1t, w2t, xq, hpre, yq, score, logits, idx_full, counts, offsets,
+         pos, tile_expert) = ctx.saved_tensors
+        top_k, cap_rows, separate_gate_inp = ctx.cfg
+        T, D = x.shape
+        plan = ops.Plan(counts, offsets, pos, tile_expert, cap_rows, PAD_ROWS)
+        if d_out is None:
+            d_out = torch.zeros_like(x)
+        dyq, dscore = ops.combine_bwd(_c(d_out), yq, plan, score)
+        dxq, dw1, db1, dw2, db2 = ops.ffn_bwd(xq, hpre, dyq, plan, w1c, w2c, w1t, w2t)
+        if d_score is not None:
+            dscore = dscore + d_score
+        if d_gates is not None and d_gates.numel() == 0:
+            d_gates = None
+        gx = x if gate_x is None else gate_x
+        dz, dwg, dtf, dxg = ops.gate_bwd(gx, w_gate, logits, idx_full, top_k, task_feat, dscore, d_top, d_gates,
+                                         d_imp, d_clean, d_noisy, want_dx_gate=separate_gate_inp)
+        if separate_gate_inp:
+            dx = ops.dispatch_bwd(dxq, plan, T, top_k, out_dtype=x.dtype)
+            dgx = dxg.to(gate_x.dtype)
+        else:
+            dx = ops.dispatch_bwd(dxq, plan, T, top_k, out_dtype=x.dtype, dz=dz, w_gate=w_gate)
+            dgx = None
+        if dtf is not None and task_feat is not None:
+            dtf = dtf.view_as(task_feat).to(task_feat.dtype)
+        return dx, dgx, dwg, dtf, dw1, db1, dw2, db2, None, None, None, None, None, None
+
+
+class GateFunction(torch.autograd.Function):
+    """The router alone (NoisyGate_VMoE.forward).  outputs as MoEFunction minus `out`."""
+
+    @staticmethod
+    def forward(ctx, gx, w_gate, task_feat, noise, top_k, noise_stddev, want_gates):
+        gx = _c(gx)
+        E = w_gate.shape[1]
+        g = ops.gate_fwd(gx, w_gate, top_k, task_feat, noise, noise_stddev, want_gates)
+        plan = ops.route_plan(g.idx, E, PAD_ROWS, g.imp_partial, g.load_partial)
+        ctx.save_for_backward(gx, w_gate, task_feat, g.noisy_logits, g.idx_full)
+        ctx.top_k = top_k
+        gates = g.gates if g.gates is not None else gx.new_empty(0)
+        ctx.mark_non_differentiable(g.idx, plan.load, plan.counts, plan.offsets, plan.pos, plan.tile_expert)
+        noisy = g.clean_logits.view_as(g.clean_logits) if noise is None else g.noisy_logits
+        return (g.score, g.top_vals, g.clean_logits, noisy, gates, plan.importance, plan.load, g.idx,
+                plan.counts, plan.offsets, plan.pos, plan.tile_expert)
+
+    @staticmethod
+    def backward(ctx, d_score, d_top, d_clean, d_noisy, d_gates, d_imp, *_):
+        gx, w_gate, task_feat, logits, idx_full = ctx.saved_tensors
+        if d_gates is not None and d_gates.numel() == 0:
+            d_gates = None
+        dz, dwg, dtf, dxg = ops.gate_bwd(gx, w_gate, logits, idx_full, ctx.top_k, task_feat, d_score, d_top, d_gates,
+                                         d_imp, d_clean, d_noisy, want_dx_gate=True)
+        if dtf is not None and task_feat is not None:
+            dtf = dtf.view_as(task_feat).to(task_feat.dtype)
+        return dxg.to(gx.dtype), dwg, dtf, None, None, None, None
+
+
+class ExpertsFunction(torch.autograd.Function):
+    """dispatch -> expert FFN -> combine for externally supplied routing
+    (idx[T,K] int64, score[T,K]); the token-MoE entry of the reference
+    (models/moe/token/custom_moe_layer.py:88-156)."""
+
+    @staticmethod
+    def forward(ctx, x, idx, score, w1, b1, w2, b2, compute_dtype, wcache, plan: Optional[ops.Plan]):
+        T, D = x.shape
+        E = w1.shape[0]
+        K = idx.shape[1]
+        x = _c(x)
+        score = _c(score).float()
+        if plan is None:
+            plan = ops.route_plan(_c(idx), E, PAD_ROWS)
+        xq = ops.dispatch_fwd(x, plan, K, out_dtype=compute_dtype)
+        if compute_dtype == torch.bfloat16:
+            w1c, w2c, w1t, w2t = wcache.get_bf16(w1, w2)
+        else:
+            w1c, w2c, w1t, w2t = w1, w2, None, None
+        needs_grad = any(ctx.needs_input_grad)
+        yq, hpre = ops.ffn_fwd(xq, plan, w1c, b1, w2c, b2, save_hpre=needs_grad)
+        out = ops.combine_fwd(yq, plan, score, out_dtype=x.dtype)
+        if needs_grad:
+            ctx.save_for_backward(x, w1c, w2c, w1t, w2t, xq, hpre, yq, score, plan.counts, plan.offsets, plan.pos,
+                                  plan.tile_expert)
+            ctx.cfg = (K, plan.cap_rows)
+        return out
+
+    @staticmethod
+    def backward(ctx, d_out):
+        x, w1c, w2c, w1t, w2t, xq, hpre, yq, score, counts, offsets, pos, tile_expert = ctx.saved_tensors
+        K, cap_rows = ctx.cfg
+        plan = ops.Plan(counts, offsets, pos, tile_expert, cap_rows, PAD_ROWS)
+        dyq, dscore = ops.combine_bwd(_c(d_out), yq, plan, score)
+        dxq, dw1, db1, dw2, db2 = ops.ffn_bwd(xq, hpre, dyq, plan, w1c, w2c, w1t, w2t)
+        dx = ops.dispatch_bwd(dxq, plan, x.shape[0], K, out_dtype=x.dtype)
+        return dx, None, dscore, dw1, db1, dw2, db2, None, None, None
+
+
+class WeightCache:
+    """bf16 (and transposed bf16) copies of the fp32 expert weights, re-cast only
+    when a parameter changed (optimizer step / load_state_dict bump `_version`)."""
+
+    def __init__(self):
+        self._key = None
+        self._val = None
+
+    def get_bf16(self, w1, w2):
+        key = (w1.data_ptr(), w1._version, w2.data_ptr(), w2._version, w1.device)
+        if key != self._key:
+            w1c, w1t = ops.cast_weights_bf16(w1.detach(), True, True)
+            w2c, w2t = ops.cast_weights_bf16(w2.detach(), True, True)
+            self._key, self._val = key, (w1c, w2c, w1t, w2t)
+        return self._val

@@ -1,0 +1,104 @@
+"""CPU: host-side mirror of the reference layer API (construction, state dict,
+attributes, error behaviour).  No CUDA calls."""
+import pytest
+import torch
+import torch.nn as nn
+
+import m3vit_b200 as M
+from m3vit_b200._lib import M3Error
+
+
+def act():
+    return nn.Sequential(nn.GELU(), nn.Dropout(0.0))
+
+
+def make(**kw):
+    base = dict(num_expert=16, d_model=64, d_gate=64, d_hidden=128, activation=act(), gate=M.NoisyGate_VMoE,
+                top_k=4, vmoe_noisy_std=0)
+    base.update(kw)
+    return M.FMoETransformerMLP(**base)
+
+
+def test_state_dict_contract_single_gate():
+    # keys and shapes other reference code relies on
+    sd = make().state_dict()
+    assert {k: tuple(v.shape) for k, v in sd.items()} == {
+        "experts.htoh4.weight": (16, 128, 64), "experts.htoh4.bias": (16, 128),
+        "experts.h4toh.weight": (16, 64, 128), "experts.h4toh.bias": (16, 64),
+        "gate.w_gate": (64, 16)}
+
+
+def test_multi_gate_count_is_dgate_minus_dmodel():
+    # origin/custom_moe_layer.py:138,150: number of task gates = d_gate - d_model
+    layer = make(d_gate=64 + 5, multi_gate=True)
+    assert isinstance(layer.gate, nn.ModuleList) and len(layer.gate) == 5
+    assert "gate.4.w_gate" in layer.state_dict()
+
+
+def test_task_conditioned_gate_width():
+    layer = make(gate_task_specific_dim=16)          # origin:127-130
+    assert tuple(layer.gate.w_gate.shape) == (80, 16)
+
+
+def test_world_size_scales_gate_columns():
+    layer = make(num_expert=4, world_size=4)         # BaseGate.tot_expert = num_expert * world_size
+    assert tuple(layer.gate.w_gate.shape) == (64, 16)
+    assert tuple(layer.experts.htoh4.weight.shape) == (4, 128, 64)
+
+
+def test_dp_comm_tags():
+    layer = make()
+    assert all(p.dp_comm == "none" for p in layer.experts.parameters())
+    assert all(p.dp_comm == "gate" for p in layer.gate.parameters())
+
+
+def test_attributes_used_by_reference_utils():
+    layer = make()
+    for a in ("num_expert", "world_size", "top_k", "d_model", "gate", "experts", "gate_hook", "mask", "mask_dict"):
+        assert hasattr(layer, a)
+    g = layer.gate
+    assert not g.has_loss and not g.has_activation and g.select_idx is None and g.tot_expert == 16
+
+
+def test_bad_gate_type_raises_value_error():
+    with pytest.raises(ValueError, match="No such gating type"):
+        make(gate=nn.Linear)
+
+
+@pytest.mark.parametrize("flag", ["regu_sem", "sem_force", "regu_subimage", "expert_prune", "regu_experts_fromtask"])
+def test_research_flags_raise(flag):
+    with pytest.raises(NotImplementedError):
+        make(**{flag: True})
+
+
+def test_cpu_tensor_is_refused_loudly():
+    layer = make()
+    with pytest.raises(M3Error, match="no CPU fallback"):
+        layer(torch.randn(2, 3, 64))
+
+
+def test_multi_gate_without_task_id_is_a_type_error():
+    layer = make(d_gate=66, multi_gate=True)
+    with pytest.raises(TypeError):
+        layer(torch.randn(2, 3, 64))
+
+
+def test_non_gelu_activation_rejected():
+    with pytest.raises(NotImplementedError):
+        make(activation=nn.ReLU())
+
+
+def test_block_adapter_argument_mapping():
+    m = M.build_moe_mlp(384, moe_mlp_ratio=1, moe_experts=16, moe_top_k=4, moe_gate_dim=386,
+                        moe_gate_type="noisy_vmoe", vmoe_noisy_std=0, multi_gate=True)
+    assert m.d_hidden == 384 and len(m.gate) == 2 and m.top_k == 4
+    with pytest.raises(ValueError):
+        M.build_moe_mlp(384, moe_gate_type="bogus")
+    ck = M.build_moe_mlp(64, moe_mlp_ratio=1, moe_experts=8, moe_gate_type="noisy_vmoe", variant="ckpt")
+    assert isinstance(ck, M.FMoETransformerMLPCkpt) and ck.gate.return_summaries
+
+
+def test_cv_squared_matches_reference_formula():
+    x = torch.tensor([1.0, 2.0, 3.0, 6.0])
+    assert torch.allclose(M.cv_squared(x), x.var() / (x.mean() ** 2 + 1e-10))
+    assert float(M.cv_squared(torch.tensor([5.0]))) == 0.0
