@@ -1,8 +1,524 @@
-// placeholder until the tcgen05 path lands (replaced in the next commit)
-#include "common.cuh"
-size_t m3_ffn_bf16_workspace_bytes(int, int, int, int, int) { return 0; }
-int m3_ffn_fwd_bf16(const void*, const int32_t*, const int32_t*, int, int, int, int, const void*, const float*,
-                    const void*, const float*, void*, void*, void*, size_t, cudaStream_t) { return M3_ERR_UNSUPPORTED; }
-int m3_ffn_bwd_bf16(const void*, const void*, const void*, const int32_t*, const int32_t*, const int32_t*, int, int,
-                    int, int, const void*, const void*, const void*, const void*, void*, float*, float*, float*,
-                    float*, void*, size_t, cudaStream_t) { return M3_ERR_UNSUPPORTED; }
+// bf16 expert FFN on the 5th-generation tensor cores (sm_100a): TMA-fed tcgen05.mma
+// with fp32 accumulators in TMEM, grouped over the padded expert queues.
+//
+// Replaces fmoe's FMoELinear pair (per-expert cuBLAS GEMM loop, reached from
+// /root/reference/models/moe/origin/custom_moe_layer.py:36-44) and its backward.
+//
+//   gg_kernel    C[128-row tile, BN] = A[rows,Kd] * B_e[N,Kd]^T   (both K-major)
+//                persistent CTAs over (m_tile, n_tile); warp 0 = TMA producer, warp 1 =
+//                MMA issuer (one thread) + TMEM owner, warps 2-5 = epilogue
+//                (tcgen05.ld -> bias / GELU / GELU' -> bf16 -> global).  Smem ring of
+//                {A 128x64, B BNx64} stages (SWIZZLE_128B), TMEM accumulator double-buffered
+//                so the epilogue of tile i overlaps the MMAs of tile i+1.
+//   wgrad_kernel dW_e[M,N] = sum_rows X1[rows,M]^T X2[rows,N]     (both MN-major operands,
+//                read straight from the row-major queues - no transposes in memory)
+//
+// Expert queues are padded to 128 rows (route plan), so every tile is full and the expert
+// of a tile is a table lookup; padding rows are zero, so they add nothing to dW.
+#include <cstdio>
+#include <mutex>
+
+#include "tc_common.cuh"
+
+namespace m3 {
+namespace tc {
+
+constexpr int BM = 128;  // UMMA M (cta_group::1): accumulator row i <-> TMEM lane i
+constexpr int BK = 64;   // 64 bf16 = 128 B = one swizzle-128B row
+constexpr int UMMA_K = 16;
+constexpr int kThreads = 192;
+
+enum { EPI_STORE = 0, EPI_BIAS = 1, EPI_FC1 = 2, EPI_DGELU = 3 };
+
+struct GGParams {
+  const int32_t* offsets;      // [E+1] padded queue offsets (offsets[E] = rows in use)
+  const int32_t* tile_expert;  // [rows/128]
+  int E, N, Kd;
+  const float* bias;             // [E][N]                      (EPI_BIAS, EPI_FC1)
+  const __nv_bfloat16* aux_in;   // [rows][N] hpre              (EPI_DGELU)
+  __nv_bfloat16* out;            // [rows][N]
+  __nv_bfloat16* out2;           // EPI_FC1: hpre (nullable)    EPI_DGELU: h = gelu(hpre)
+};
+
+template <int BN>
+struct GGCfg {
+  static constexpr int A_BYTES = BM * BK * 2;
+  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int STAGE = A_BYTES + B_BYTES;
+  static constexpr int STAGES = (BN <= 128) ? 6 : (BN <= 192 ? 5 : 4);
+  static constexpr int TMEM_COLS = (2 * BN <= 256) ? 256 : 512;
+  static constexpr int SMEM = STAGES * STAGE + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+__device__ __forceinline__ uint4 pack8(const float* v) {
+  uint4 r;
+  r.x = float2_to_bf16x2(v[0], v[1]);
+  r.y = float2_to_bf16x2(v[2], v[3]);
+  r.z = float2_to_bf16x2(v[4], v[5]);
+  r.w = float2_to_bf16x2(v[6], v[7]);
+  return r;
+}
+
+template <int BN, int EPI>
+__global__ void __launch_bounds__(kThreads, 1)
+gg_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, GGParams p) {
+  using Cfg = GGCfg<BN>;
+  constexpr int STAGES = Cfg::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE);
+  uint64_t* empty = full + STAGES;
+  uint64_t* tfull = empty + STAGES;
+  uint64_t* tempty = tfull + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+  }
+  if (warp == 1) {
+    if (lane == 0) {
+      for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+      for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 128); }
+      fence_barrier_init();
+    }
+    __syncwarp();
+    tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int n_tiles = p.N / BN;
+  const int m_tiles = p.offsets[p.E] / BM;
+  const int total = m_tiles * n_tiles;
+  const int kchunks = p.Kd / BK;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
+        const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
+        const int e = p.tile_expert[m_blk];
+        for (int kc = 0; kc < kchunks; ++kc) {
+          mbar_wait(&empty[stage], phase ^ 1);
+          mbar_expect_tx(&full[stage], Cfg::STAGE);
+          uint8_t* sa = smem + stage * Cfg::STAGE;
+          tma_load_2d(sa, &tmA, &full[stage], kc * BK, m_blk * BM);
+          tma_load_2d(sa + Cfg::A_BYTES, &tmB, &full[stage], kc * BK, e * p.N + n_blk * BN);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(BM, BN, 0, 0);
+      int stage = 0;
+      uint32_t phase = 0, acc = 0, acc_phase = 0;
+      for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
+        mbar_wait(&tempty[acc], acc_phase ^ 1);
+        tcgen05_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kc = 0; kc < kchunks; ++kc) {
+          mbar_wait(&full[stage], phase);
+          tcgen05_fence_after();
+          const uint32_t a_base = smem_u32(smem + stage * Cfg::STAGE);
+          const uint32_t b_base = a_base + Cfg::A_BYTES;
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k) {
+            const uint64_t adesc = make_smem_desc(a_base + k * UMMA_K * 2, 0, 1024);
+            const uint64_t bdesc = make_smem_desc(b_base + k * UMMA_K * 2, 0, 1024);
+            umma_bf16(d_tmem, adesc, bdesc, idesc, (kc | k) != 0);
+          }
+          umma_commit(&empty[stage]);  // frees the smem stage once these MMAs have read it
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&tfull[acc]);  // accumulator complete -> epilogue
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+      }
+    }
+  } else {
+    const int q = warp & 3;  // TMEM lane quarter this warp may read
+    const int row_in_tile = q * 32 + lane;
+    uint32_t acc = 0, acc_phase = 0;
+    for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
+      const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
+      const int e = p.tile_expert[m_blk];
+      const int64_t row = (int64_t)m_blk * BM + row_in_tile;
+      mbar_wait(&tfull[acc], acc_phase);
+      tcgen05_fence_after();
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        float v[32];
+        tmem_ld_32x32(tmem_base + acc * BN + c * 32 + ((uint32_t)(q * 32) << 16), v);
+        const int col = n_blk * BN + c * 32;
+        const int64_t o = row * p.N + col;
+        if (EPI == EPI_BIAS || EPI == EPI_FC1) {
+          const float4* b4 = reinterpret_cast<const float4*>(p.bias + (int64_t)e * p.N + col);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 b = __ldg(b4 + j);
+            v[4 * j] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
+          }
+        }
+        if (EPI == EPI_FC1) {
+          if (p.out2 != nullptr) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) *reinterpret_cast<uint4*>(p.out2 + o + 8 * j) = pack8(v + 8 * j);
+          }
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+        }
+        if (EPI == EPI_DGELU) {
+          float hv[32];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const uint4 u = __ldg(reinterpret_cast<const uint4*>(p.aux_in + o + 8 * j));
+            float2 f;
+            f = bf16x2_to_float2(u.x); hv[8 * j] = f.x; hv[8 * j + 1] = f.y;
+            f = bf16x2_to_float2(u.y); hv[8 * j + 2] = f.x; hv[8 * j + 3] = f.y;
+            f = bf16x2_to_float2(u.z); hv[8 * j + 4] = f.x; hv[8 * j + 5] = f.y;
+            f = bf16x2_to_float2(u.w); hv[8 * j + 6] = f.x; hv[8 * j + 7] = f.y;
+          }
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            v[j] *= gelu_erf_grad(hv[j]);
+            hv[j] = gelu_erf(hv[j]);
+          }
+#pragma unroll
+          for (int j = 0; j < 4; ++j) *reinterpret_cast<uint4*>(p.out2 + o + 8 * j) = pack8(hv + 8 * j);
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) *reinterpret_cast<uint4*>(p.out + o + 8 * j) = pack8(v + 8 * j);
+      }
+      tcgen05_fence_before();
+      mbar_arrive(&tempty[acc]);
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+  }
+}
+
+// ---------------------------------------------------------------------- wgrad
+// dW[e][m0..m0+128][n0..n0+BN] = sum over the expert's rows r of X1[r][m] * X2[r][n]
+struct WGParams {
+  const int32_t* offsets;
+  int M, N;       // dW_e is [M][N]; X1 is [rows][M], X2 is [rows][N]
+  float* dW;      // [E][M][N]
+};
+
+template <int BN>
+struct WGCfg {
+  static constexpr int A_BYTES = BK * BM * 2;   // 2 boxes of [64 rows][64 cols]
+  static constexpr int B_BYTES = BK * BN * 2;   // BN/64 boxes
+  static constexpr int BOX = BK * 64 * 2;       // 8192 B
+  static constexpr int STAGE = A_BYTES + B_BYTES;
+  static constexpr int STAGES = (BN <= 128) ? 6 : 4;
+  static constexpr int TMEM_COLS = (BN <= 128) ? 128 : 256;
+  static constexpr int SMEM = STAGES * STAGE + 1024 + 256;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(kThreads, 1)
+wgrad_kernel(const __grid_constant__ CUtensorMap tm1, const __grid_constant__ CUtensorMap tm2, WGParams p) {
+  using Cfg = WGCfg<BN>;
+  constexpr int STAGES = Cfg::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE);
+  uint64_t* empty = full + STAGES;
+  uint64_t* tfull = empty + STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tfull + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int e = blockIdx.z, m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+  if (warp == 0 && lane == 0) { tma_prefetch_desc(&tm1); tma_prefetch_desc(&tm2); }
+  if (warp == 1) {
+    if (lane == 0) {
+      for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+      mbar_init(tfull, 1);
+      fence_barrier_init();
+    }
+    __syncwarp();
+    tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int r0 = p.offsets[e], r1 = p.offsets[e + 1];
+  const int kchunks = (r1 - r0) / BK;   // queues are padded to 128 rows
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int kc = 0; kc < kchunks; ++kc) {
+        mbar_wait(&empty[stage], phase ^ 1);
+        mbar_expect_tx(&full[stage], Cfg::STAGE);
+        uint8_t* sa = smem + stage * Cfg::STAGE;
+        const int r = r0 + kc * BK;
+#pragma unroll
+        for (int b = 0; b < BM / 64; ++b) tma_load_2d(sa + b * Cfg::BOX, &tm1, &full[stage], m0 + b * 64, r);
+#pragma unroll
+        for (int b = 0; b < BN / 64; ++b)
+          tma_load_2d(sa + Cfg::A_BYTES + b * Cfg::BOX, &tm2, &full[stage], n0 + b * 64, r);
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(BM, BN, 1, 1);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int kc = 0; kc < kchunks; ++kc) {
+        mbar_wait(&full[stage], phase);
+        tcgen05_fence_after();
+        const uint32_t a_base = smem_u32(smem + stage * Cfg::STAGE);
+        const uint32_t b_base = a_base + Cfg::A_BYTES;
+#pragma unroll
+        for (int k = 0; k < BK / UMMA_K; ++k) {
+          // MN-major: 16 k-rows = 2 swizzle groups of 8 rows (1024 B each)
+          const uint64_t adesc = make_smem_desc(a_base + k * 2048, Cfg::BOX, 1024);
+          const uint64_t bdesc = make_smem_desc(b_base + k * 2048, Cfg::BOX, 1024);
+          umma_bf16(tmem_base, adesc, bdesc, idesc, (kc | k) != 0);
+        }
+        umma_commit(&empty[stage]);
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+      umma_commit(tfull);
+    }
+  } else {
+    const int q = warp & 3;
+    const int row = m0 + q * 32 + lane;
+    float* dst = p.dW + ((int64_t)e * p.M + row) * p.N + n0;
+    if (kchunks == 0) {  // expert received no rows: dW_e = 0
+#pragma unroll 1
+      for (int c = 0; c < BN / 4; ++c) *reinterpret_cast<float4*>(dst + 4 * c) = make_float4(0.f, 0.f, 0.f, 0.f);
+    } else {
+      mbar_wait(tfull, 0);
+      tcgen05_fence_after();
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        float v[32];
+        tmem_ld_32x32(tmem_base + c * 32 + ((uint32_t)(q * 32) << 16), v);
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          *reinterpret_cast<float4*>(dst + c * 32 + 4 * j) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+      }
+    }
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+  }
+}
+
+// ------------------------------------------------------------ bias gradients
+// stage 1: per 128-row tile column sums (fully parallel, reads the matrix once)
+__global__ void __launch_bounds__(256)
+colsum_tile_kernel(const __nv_bfloat16* __restrict__ G, const int32_t* __restrict__ offsets, int E, int N,
+                   float* __restrict__ part) {
+  const int m_blk = blockIdx.y;
+  if (m_blk * BM >= offsets[E]) return;
+  __shared__ float red[8][64];
+  const int cp = threadIdx.x & 31, rg = threadIdx.x >> 5;  // column pair, row group
+  const int col = blockIdx.x * 64 + cp * 2;
+  float a0 = 0.f, a1 = 0.f;
+  if (col < N) {
+    const __nv_bfloat16* g = G + (int64_t)m_blk * BM * N + col;
+#pragma unroll 4
+    for (int r = rg; r < BM; r += 8) {
+      const float2 f = bf16x2_to_float2(__ldg(reinterpret_cast<const uint32_t*>(g + (int64_t)r * N)));
+      a0 += f.x; a1 += f.y;
+    }
+  }
+  red[rg][cp * 2] = a0;
+  red[rg][cp * 2 + 1] = a1;
+  __syncthreads();
+  if (threadIdx.x < 64 && blockIdx.x * 64 + threadIdx.x < N) {
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s += red[i][threadIdx.x];
+    part[(int64_t)m_blk * N + blockIdx.x * 64 + threadIdx.x] = s;
+  }
+}
+// stage 2: db[e][n] = sum of the expert's tile partials, fixed order
+__global__ void colsum_reduce_kernel(const float* __restrict__ part, const int32_t* __restrict__ offsets, int N,
+                                     float* __restrict__ db) {
+  const int e = blockIdx.y, n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  float s = 0.f;
+  for (int t = offsets[e] / BM; t < offsets[e + 1] / BM; ++t) s += part[(int64_t)t * N + n];
+  db[(int64_t)e * N + n] = s;
+}
+
+// ------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(f);
+  });
+  return fn;
+}
+
+// 2-D bf16 row-major tensor [rows][cols], box [box_rows][64 cols] (128 B inner), SWIZZLE_128B
+static int make_map(CUtensorMap* m, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return M3_ERR_UNSUPPORTED;
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {cols * 2};
+  cuuint32_t box[2] = {64, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? M3_OK : M3_ERR_ARG;
+}
+
+static int pick_bn(int N) { return N % 192 == 0 ? 192 : (N % 256 == 0 ? 256 : (N % 128 == 0 ? 128 : 0)); }
+
+template <int BN, int EPI>
+static int launch_gg_t(const CUtensorMap& tA, const CUtensorMap& tB, const GGParams& p, int max_tiles, cudaStream_t st) {
+  using Cfg = GGCfg<BN>;
+  auto kern = gg_kernel<BN, EPI>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
+  if (e != cudaSuccess) return (int)e;
+  int grid = max_tiles < kNumSMs ? max_tiles : kNumSMs;
+  if (grid < 1) grid = 1;
+  kern<<<grid, kThreads, Cfg::SMEM, st>>>(tA, tB, p);
+  M3_LAUNCH_CHECK();
+  return M3_OK;
+}
+
+// A [cap_rows][Kd] bf16, B [E*N][Kd] bf16 -> out [cap_rows][N]
+template <int EPI>
+static int launch_gg(const void* A, const void* B, GGParams p, int cap_rows, cudaStream_t st) {
+  const int BN = pick_bn(p.N);
+  if (BN == 0 || p.Kd % BK != 0 || cap_rows % BM != 0) return M3_ERR_SHAPE;
+  CUtensorMap tA, tB;
+  int rc = make_map(&tA, A, (uint64_t)cap_rows, (uint64_t)p.Kd, BM);
+  if (rc) return rc;
+  rc = make_map(&tB, B, (uint64_t)p.E * p.N, (uint64_t)p.Kd, (uint32_t)BN);
+  if (rc) return rc;
+  const int max_tiles = (cap_rows / BM) * (p.N / BN);
+  switch (BN) {
+    case 128: return launch_gg_t<128, EPI>(tA, tB, p, max_tiles, st);
+    case 192: return launch_gg_t<192, EPI>(tA, tB, p, max_tiles, st);
+    default: return launch_gg_t<256, EPI>(tA, tB, p, max_tiles, st);
+  }
+}
+
+// dW [E][M][N] fp32 = X1[rows][M]^T X2[rows][N] per expert
+static int launch_wgrad(const void* X1, const void* X2, const int32_t* offsets, int cap_rows, int E, int M, int N,
+                        float* dW, cudaStream_t st) {
+  constexpr int BN = 128;
+  if (M % BM != 0 || N % BN != 0) return M3_ERR_SHAPE;
+  CUtensorMap t1, t2;
+  int rc = make_map(&t1, X1, (uint64_t)cap_rows, (uint64_t)M, BK);
+  if (rc) return rc;
+  rc = make_map(&t2, X2, (uint64_t)cap_rows, (uint64_t)N, BK);
+  if (rc) return rc;
+  using Cfg = WGCfg<BN>;
+  auto kern = wgrad_kernel<BN>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
+  if (e != cudaSuccess) return (int)e;
+  WGParams p{offsets, M, N, dW};
+  kern<<<dim3(M / BM, N / BN, E), kThreads, Cfg::SMEM, st>>>(t1, t2, p);
+  M3_LAUNCH_CHECK();
+  return M3_OK;
+}
+
+static int launch_colsum(const __nv_bfloat16* G, const int32_t* offsets, int cap_rows, int E, int N, float* part,
+                         float* db, cudaStream_t st) {
+  colsum_tile_kernel<<<dim3(m3_ceil_div(N, 64), cap_rows / BM), 256, 0, st>>>(G, offsets, E, N, part);
+  M3_LAUNCH_CHECK();
+  colsum_reduce_kernel<<<dim3(m3_ceil_div(N, 128), E), 128, 0, st>>>(part, offsets, N, db);
+  M3_LAUNCH_CHECK();
+  return M3_OK;
+}
+
+static size_t align256(size_t x) { return (x + 255) & ~size_t(255); }
+
+}  // namespace tc
+}  // namespace m3
+
+using namespace m3;
+using namespace m3::tc;
+typedef __nv_bfloat16 bf16;
+
+// workspace: forward  : h [cap][H] bf16
+//            backward : dhpre [cap][H] bf16 | h [cap][H] bf16 | colsum partials [cap/128][max(D,H)] fp32
+size_t m3_ffn_bf16_workspace_bytes(int cap_rows, int D, int H, int E, int backward) {
+  (void)E;
+  const size_t hbytes = align256((size_t)cap_rows * H * 2);
+  if (!backward) return hbytes;
+  return 2 * hbytes + align256((size_t)(cap_rows / BM) * (D > H ? D : H) * 4);
+}
+
+int m3_ffn_fwd_bf16(const void* xq, const int32_t* offsets, const int32_t* tile_expert, int cap_rows, int E, int D,
+                    int H, const void* w1, const float* b1, const void* w2, const float* b2, void* hpre, void* yq,
+                    void* workspace, size_t workspace_bytes, cudaStream_t st) {
+  if (workspace == nullptr || workspace_bytes < m3_ffn_bf16_workspace_bytes(cap_rows, D, H, E, 0)) return M3_ERR_WORKSPACE;
+  bf16* h = static_cast<bf16*>(workspace);
+  GGParams p{};
+  p.offsets = offsets; p.tile_expert = tile_expert; p.E = E;
+  // fc1: h = gelu(xq W1^T + b1), hpre saved for backward
+  p.N = H; p.Kd = D; p.bias = b1; p.out = h; p.out2 = static_cast<bf16*>(hpre);
+  int rc = launch_gg<EPI_FC1>(xq, w1, p, cap_rows, st);
+  if (rc) return rc;
+  // fc2: yq = h W2^T + b2
+  p.N = D; p.Kd = H; p.bias = b2; p.out = static_cast<bf16*>(yq); p.out2 = nullptr;
+  return launch_gg<EPI_BIAS>(h, w2, p, cap_rows, st);
+}
+
+int m3_ffn_bwd_bf16(const void* xq, const void* hpre, const void* dyq, const int32_t* counts, const int32_t* offsets,
+                    const int32_t* tile_expert, int cap_rows, int E, int D, int H, const void* w1, const void* w2,
+                    const void* w1t, const void* w2t, void* dxq, float* dw1, float* db1, float* dw2, float* db2,
+                    void* workspace, size_t workspace_bytes, cudaStream_t st) {
+  (void)counts; (void)w1; (void)w2;
+  if (workspace_bytes < m3_ffn_bf16_workspace_bytes(cap_rows, D, H, E, 1)) return M3_ERR_WORKSPACE;
+  const size_t hbytes = align256((size_t)cap_rows * H * 2);
+  bf16* dhpre = static_cast<bf16*>(workspace);
+  bf16* h = reinterpret_cast<bf16*>(static_cast<uint8_t*>(workspace) + hbytes);
+  float* part = reinterpret_cast<float*>(static_cast<uint8_t*>(workspace) + 2 * hbytes);
+  GGParams p{};
+  p.offsets = offsets; p.tile_expert = tile_expert; p.E = E;
+  // dhpre = (dyq W2) * gelu'(hpre);  h = gelu(hpre)      B = W2^T [E][H][D] (K-major in D)
+  p.N = H; p.Kd = D; p.aux_in = static_cast<const bf16*>(hpre); p.out = dhpre; p.out2 = h;
+  int rc = launch_gg<EPI_DGELU>(dyq, w2t, p, cap_rows, st);
+  if (rc) return rc;
+  // dxq = dhpre W1                                       B = W1^T [E][D][H] (K-major in H)
+  p.N = D; p.Kd = H; p.aux_in = nullptr; p.out = static_cast<bf16*>(dxq); p.out2 = nullptr;
+  rc = launch_gg<EPI_STORE>(dhpre, w1t, p, cap_rows, st);
+  if (rc) return rc;
+  // dW2[e] = dyq_e^T h_e  [D][H];   dW1[e] = dhpre_e^T xq_e  [H][D]
+  rc = launch_wgrad(dyq, h, offsets, cap_rows, E, D, H, dw2, st);
+  if (rc) return rc;
+  rc = launch_wgrad(dhpre, xq, offsets, cap_rows, E, H, D, dw1, st);
+  if (rc) return rc;
+  rc = launch_colsum(static_cast<const bf16*>(dyq), offsets, cap_rows, E, D, part, db2, st);
+  if (rc) return rc;
+  return launch_colsum(dhpre, offsets, cap_rows, E, H, part, db1, st);
+}

@@ -16,6 +16,17 @@ from . import _lib as L
 from ._lib import PAD_ROWS, check, dtype_code, load, ptr, require_device, stream_ptr
 
 
+# kernels launched by each C entry point (our own kernels; used for bench.py's `gpu_launches`)
+LAUNCHES = {"gate_fwd": 1, "gate_bwd": 3, "gate_bwd_dx": 1, "route_plan": 2, "dispatch_fwd": 1, "dispatch_bwd": 1,
+            "combine_fwd": 1, "combine_bwd": 1, "cast_weights": 1, "ffn_fwd": 2, "ffn_bwd_f32": 6, "ffn_bwd_bf16": 8}
+launch_count = 0
+
+
+def _count(name, n=1):
+    global launch_count
+    launch_count += LAUNCHES[name] * n
+
+
 def _i32(n, dev):
     return torch.empty(n, dtype=torch.int32, device=dev)
 
@@ -74,6 +85,7 @@ def gate_fwd(x, w_gate, top_k, task_feat=None, noise=None, noise_stddev=0.0, wan
     check(lib.m3_gate_fwd(ptr(x), dtype_code(x), x.stride(0), ptr(task_feat), ptr(w_gate), ptr(noise),
                           float(noise_stddev), T, D, Dt, E, K, ptr(idx), ptr(idx_full), ptr(score), ptr(top_vals),
                           ptr(clean), ptr(noisy), ptr(gates), ptr(imp_p), ptr(load_p), stream_ptr()), "m3_gate_fwd")
+    _count("gate_fwd")
     return GateOut(idx, idx_full, score, top_vals, clean, noisy if noisy is not None else clean, gates,
                    imp_p[:n_part], load_p[:n_part])
 
@@ -103,6 +115,9 @@ def gate_bwd(x, w_gate, logits, idx_full, top_k, task_feat=None, dscore=None, dt
                           T, D, Dt, E, top_k, ptr(dscore), ptr(dtop_vals), ptr(dgates), ptr(dimportance), ptr(dclean),
                           ptr(dnoisy), ptr(dz), ptr(dw), ptr(dtf), ptr(dxg), ptr(ws), ws.numel(), stream_ptr()),
           "m3_gate_bwd")
+    _count("gate_bwd")
+    if want_dx_gate:
+        _count("gate_bwd_dx")
     return dz, dw, dtf, dxg
 
 
@@ -138,6 +153,7 @@ def route_plan(idx, num_expert, pad=PAD_ROWS, imp_partial=None, load_partial=Non
     check(lib.m3_route_plan(ptr(idx), T, K, E, pad, ptr(imp_partial), ptr(load_partial), n_part, ptr(counts),
                             ptr(offsets), ptr(pos), ptr(tile_expert), ptr(imp), ptr(load_v), ptr(ws), ws.numel(),
                             stream_ptr()), "m3_route_plan")
+    _count("route_plan")
     return Plan(counts, offsets, pos, tile_expert, cap_rows, pad, imp, load_v)
 
 
@@ -151,6 +167,7 @@ def dispatch_fwd(x, plan: Plan, top_k, out_dtype=None):
     E = plan.counts.numel()
     check(load().m3_dispatch_fwd(ptr(x), dtype_code(x), ptr(plan.pos), ptr(plan.counts), ptr(plan.offsets), T, top_k,
                                  D, E, ptr(xq), dtype_code(xq), stream_ptr()), "m3_dispatch_fwd")
+    _count("dispatch_fwd")
     return xq
 
 
@@ -161,6 +178,7 @@ def dispatch_bwd(dxq, plan: Plan, T, top_k, out_dtype=torch.float32, dz=None, w_
     E = w_gate.shape[1] if w_gate is not None else 0
     check(load().m3_dispatch_bwd(ptr(dxq), dtype_code(dxq), ptr(plan.pos), T, top_k, D, ptr(dz), ptr(w_gate), E,
                                  ptr(dx), dtype_code(dx), stream_ptr()), "m3_dispatch_bwd")
+    _count("dispatch_bwd")
     return dx
 
 
@@ -171,6 +189,7 @@ def combine_fwd(yq, plan: Plan, score, out_dtype=torch.float32):
     out = torch.empty(T, D, dtype=out_dtype, device=yq.device)
     check(load().m3_combine_fwd(ptr(yq), dtype_code(yq), ptr(plan.pos), ptr(score), T, K, D, ptr(out), dtype_code(out),
                                 stream_ptr()), "m3_combine_fwd")
+    _count("combine_fwd")
     return out
 
 
@@ -185,6 +204,7 @@ def combine_bwd(g, yq, plan: Plan, score):
     check(load().m3_combine_bwd(ptr(g), dtype_code(g), ptr(yq), dtype_code(yq), ptr(plan.pos), ptr(score),
                                 ptr(plan.counts), ptr(plan.offsets), T, K, D, E, ptr(dyq), dtype_code(dyq),
                                 ptr(dscore), stream_ptr()), "m3_combine_bwd")
+    _count("combine_bwd")
     return dyq, dscore
 
 
@@ -197,6 +217,7 @@ def cast_weights_bf16(w, want_plain=True, want_transposed=False):
     o = torch.empty(E, R, Cc, dtype=torch.bfloat16, device=w.device) if want_plain else None
     ot = torch.empty(E, Cc, R, dtype=torch.bfloat16, device=w.device) if want_transposed else None
     check(load().m3_cast_weights_bf16(ptr(w), E, R, Cc, ptr(o), ptr(ot), stream_ptr()), "m3_cast_weights_bf16")
+    _count("cast_weights")
     return o, ot
 
 
@@ -213,6 +234,7 @@ def ffn_fwd(xq, plan: Plan, w1, b1, w2, b2, save_hpre=True):
     ws = _ws(lib.m3_ffn_workspace_bytes(dt, cap, D, H, E, 0), xq.device)
     check(lib.m3_ffn_fwd(dt, ptr(xq), ptr(plan.offsets), ptr(plan.tile_expert), cap, E, D, H, ptr(w1), ptr(b1),
                          ptr(w2), ptr(b2), ptr(hpre), ptr(yq), ptr(ws), ws.numel(), stream_ptr()), "m3_ffn_fwd")
+    _count("ffn_fwd")
     return yq, hpre
 
 
@@ -230,4 +252,5 @@ def ffn_bwd(xq, hpre, dyq, plan: Plan, w1, w2, w1t=None, w2t=None):
     check(lib.m3_ffn_bwd(dt, ptr(xq), ptr(hpre), ptr(dyq), ptr(plan.counts), ptr(plan.offsets), ptr(plan.tile_expert),
                          cap, E, D, H, ptr(w1), ptr(w2), ptr(w1t), ptr(w2t), ptr(dxq), ptr(dw1), ptr(db1), ptr(dw2),
                          ptr(db2), ptr(ws), ws.numel(), stream_ptr()), "m3_ffn_bwd")
+    _count("ffn_bwd_bf16" if dt == L.M3_BF16 else "ffn_bwd_f32")
     return dxq, dw1, db1, dw2, db2

@@ -40,6 +40,7 @@ SMALL = [
     MoECase("S5_e8k2_tiny", batch=1, tokens=3, d_model=64, d_hidden=64, num_expert=8, top_k=2),
     MoECase("S6_e16k4_starved", batch=1, tokens=97, d_model=64, d_hidden=128, num_expert=16, top_k=4, num_gates=3),
     MoECase("S7_e4k4_all", batch=1, tokens=40, d_model=64, d_hidden=64, num_expert=4, top_k=4),
+    MoECase("S8_d128h256_g2", batch=2, tokens=77, d_model=128, d_hidden=256, num_expert=16, top_k=4, num_gates=2),
 ]
 LARGE = [C1, C3S, C4S]
 

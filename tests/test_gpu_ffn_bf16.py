@@ -1,0 +1,109 @@
+"""GPU: the tcgen05/TMEM/TMA grouped expert FFN (bf16) against the fp32 oracle fed the
+same bf16-rounded operands.  Tolerance: bf16 storage of h/hpre/y (2^-8 relative) dominates;
+outputs within 2e-2 of the tensor's max magnitude, weight grads within 2e-2 normalised."""
+import pytest
+import torch
+
+from oracle import moe_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def nerr(a, b):
+    return float((a.float() - b.float()).abs().max() / b.float().abs().max().clamp_min(1e-12))
+
+
+def make(T, K, E, D, H, seed, skew=False):
+    gen = torch.Generator().manual_seed(seed)
+    x = torch.randn(T, D, generator=gen)
+    if skew:   # Zipf-like popularity, some experts empty
+        pri = torch.rand(T, E, generator=gen) * (1.0 / torch.arange(1, E + 1).float()) ** 1.5
+        pri[:, E - 1] = -1.0
+        idx = pri.topk(K, 1).indices
+    else:
+        idx = torch.stack([torch.randperm(E, generator=gen)[:K] for _ in range(T)])
+    w1 = (torch.rand(E, H, D, generator=gen) * 2 - 1) / D ** 0.5
+    w2 = (torch.rand(E, D, H, generator=gen) * 2 - 1) / H ** 0.5
+    b1 = (torch.rand(E, H, generator=gen) * 2 - 1) * 0.1
+    b2 = (torch.rand(E, D, generator=gen) * 2 - 1) * 0.1
+    return x, idx, w1, b1, w2, b2
+
+
+@pytest.mark.parametrize("T,K,E,D,H,skew", [
+    (300, 4, 16, 128, 128, False),
+    (777, 2, 8, 128, 256, True),
+    (2402, 4, 16, 384, 384, False),     # C1
+    (1025, 4, 16, 768, 768, True),      # C3-shaped, skewed, an empty expert
+    (513, 1, 64, 384, 1536, False),     # ratio 4, top-1, many experts
+])
+def test_ffn_bf16_forward_backward(T, K, E, D, H, skew):
+    from m3vit_b200 import ops
+    dev = torch.device("cuda:0")
+    x, idx, w1, b1, w2, b2 = make(T, K, E, D, H, seed=T + D, skew=skew)
+    bf = lambda t: t.bfloat16().float()
+    c, o, p, _ = O.route_plan(idx, E, 128)
+    n = int(o[-1])
+    xq_ref = O.dispatch(bf(x), p, K, n).requires_grad_(True)
+    w = dict(w1=bf(w1).requires_grad_(True), b1=b1.clone().requires_grad_(True),
+             w2=bf(w2).requires_grad_(True), b2=b2.clone().requires_grad_(True))
+    yq_ref = O.expert_ffn(xq_ref, c, o, w["w1"], w["b1"], w["w2"], w["b2"])
+    gen = torch.Generator().manual_seed(5)
+    dy = bf(torch.randn(n, D, generator=gen))
+    valid = torch.zeros(n, dtype=torch.bool)
+    valid[p.long()] = True
+    dy[~valid] = 0
+    yq_ref.backward(dy)
+
+    plan = ops.route_plan(idx.to(dev), E, 128)
+    assert torch.equal(plan.counts.cpu(), c)
+    xq = ops.dispatch_fwd(x.to(dev), plan, K, out_dtype=torch.bfloat16)
+    w1c, w1t = ops.cast_weights_bf16(w1.to(dev), True, True)
+    w2c, w2t = ops.cast_weights_bf16(w2.to(dev), True, True)
+    yq, hpre = ops.ffn_fwd(xq, plan, w1c, b1.to(dev), w2c, b2.to(dev))
+    torch.cuda.synchronize()
+    assert nerr(yq[:n].cpu()[valid], yq_ref.detach()[valid]) < 2e-2
+    dyq = torch.zeros(plan.cap_rows, D, device=dev, dtype=torch.bfloat16)
+    dyq[:n] = dy.to(dev).bfloat16()
+    dxq, dw1, db1, dw2, db2 = ops.ffn_bwd(xq, hpre, dyq, plan, w1c, w2c, w1t, w2t)
+    torch.cuda.synchronize()
+    assert nerr(dxq[:n].cpu()[valid], xq_ref.grad[valid]) < 2e-2
+    assert nerr(dw2.cpu(), w["w2"].grad) < 2e-2
+    assert nerr(dw1.cpu(), w["w1"].grad) < 2e-2
+    assert nerr(db2.cpu(), w["b2"].grad) < 2e-2
+    assert nerr(db1.cpu(), w["b1"].grad) < 2e-2
+    # experts that received no rows get exactly-zero weight gradients
+    for e in (c == 0).nonzero().flatten().tolist():
+        assert float(dw1[e].abs().max()) == 0.0 and float(dw2[e].abs().max()) == 0.0
+
+
+def test_ffn_bf16_tile_exactness():
+    """Integer-valued operands: bf16 products and fp32 sums are exact, so the tensor-core
+    result must equal the oracle bit for bit (catches any descriptor / swizzle / tile-index bug)."""
+    from m3vit_b200 import ops
+    dev = torch.device("cuda:0")
+    T, K, E, D, H = 640, 2, 4, 128, 128
+    gen = torch.Generator().manual_seed(0)
+    x = torch.randint(-2, 3, (T, D), generator=gen).float()
+    idx = torch.stack([torch.randperm(E, generator=gen)[:K] for _ in range(T)])
+    w1 = torch.randint(-1, 2, (E, H, D), generator=gen).float()
+    w2 = torch.zeros(E, D, H)
+    for e in range(E):
+        w2[e] = torch.eye(D, H) * (e + 1)            # fc2 = scaled identity: isolates fc1
+    b1 = torch.zeros(E, H)
+    b2 = torch.zeros(E, D)
+    c, o, p, _ = O.route_plan(idx, E, 128)
+    n = int(o[-1])
+    plan = ops.route_plan(idx.to(dev), E, 128)
+    xq = ops.dispatch_fwd(x.to(dev), plan, K, out_dtype=torch.bfloat16)
+    w1c, _ = ops.cast_weights_bf16(w1.to(dev), True, False)
+    w2c, _ = ops.cast_weights_bf16(w2.to(dev), True, False)
+    yq, hpre = ops.ffn_fwd(xq, plan, w1c, b1.to(dev), w2c, b2.to(dev))
+    xq_ref = O.dispatch(x, p, K, n)
+    want_hpre = torch.zeros(n, H)
+    for e in range(E):
+        s = int(o[e]); m = int(c[e])
+        want_hpre[s:s + m] = xq_ref[s:s + m] @ w1[e].t()
+    valid = torch.zeros(n, dtype=torch.bool)
+    valid[p.long()] = True
+    got = hpre[:n].float().cpu()
+    assert torch.equal(got[valid], want_hpre[valid].bfloat16().float()), "fc1 accumulators differ"
