@@ -26,7 +26,10 @@ namespace tc {
 constexpr int BM = 128;  // UMMA M (cta_group::1): accumulator row i <-> TMEM lane i
 constexpr int BK = 64;   // 64 bf16 = 128 B = one swizzle-128B row
 constexpr int UMMA_K = 16;
-constexpr int kThreads = 192;
+constexpr int kThreads = 192;        // wgrad kernel: 2 + 4 warps
+constexpr int kEpiWarps = 8;          // gg kernel: two warps per TMEM lane quarter
+constexpr int kGGThreads = 64 + kEpiWarps * 32;
+constexpr int BOX_BYTES = BM * 64 * 2;  // one [128 rows][64 bf16] swizzle-128B box = 16 KB
 
 enum { EPI_STORE = 0, EPI_BIAS = 1, EPI_FC1 = 2, EPI_DGELU = 3 };
 
@@ -34,20 +37,24 @@ struct GGParams {
   const int32_t* offsets;      // [E+1] padded queue offsets (offsets[E] = rows in use)
   const int32_t* tile_expert;  // [rows/128]
   int E, N, Kd;
-  const float* bias;             // [E][N]                      (EPI_BIAS, EPI_FC1)
-  const __nv_bfloat16* aux_in;   // [rows][N] hpre              (EPI_DGELU)
-  __nv_bfloat16* out;            // [rows][N]
-  __nv_bfloat16* out2;           // EPI_FC1: hpre (nullable)    EPI_DGELU: h = gelu(hpre)
+  const float* bias;           // [E][N]   (EPI_BIAS, EPI_FC1)
+  int save_out2;               // EPI_FC1: also store the pre-activation (training)
 };
 
-template <int BN>
+template <int BN, int EPI>
 struct GGCfg {
   static constexpr int A_BYTES = BM * BK * 2;
   static constexpr int B_BYTES = BN * BK * 2;
   static constexpr int STAGE = A_BYTES + B_BYTES;
-  static constexpr int STAGES = (BN <= 128) ? 6 : (BN <= 192 ? 5 : 4);
+  // epilogue staging: double-buffered 16 KB boxes per output tensor (+ per TMA-loaded aux input)
+  static constexpr int N_OUT = (EPI == EPI_FC1 || EPI == EPI_DGELU) ? 2 : 1;
+  static constexpr int N_AUX = (EPI == EPI_DGELU) ? 1 : 0;
+  static constexpr int STAGING = (N_OUT + N_AUX) * 2 * BOX_BYTES;
+  static constexpr int BUDGET = 227 * 1024 - 1024 - 512 - STAGING;
+  static constexpr int STAGES = (BUDGET / STAGE) < 6 ? (BUDGET / STAGE) : 6;
   static constexpr int TMEM_COLS = (2 * BN <= 256) ? 256 : 512;
-  static constexpr int SMEM = STAGES * STAGE + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int SMEM = STAGES * STAGE + STAGING + 1024 /*align slack*/ + 512 /*barriers*/;
+  static_assert(STAGES >= 3, "smem ring too shallow");
 };
 
 __device__ __forceinline__ uint4 pack8(const float* v) {
@@ -58,29 +65,50 @@ __device__ __forceinline__ uint4 pack8(const float* v) {
   r.w = float2_to_bf16x2(v[6], v[7]);
   return r;
 }
+__device__ __forceinline__ void unpack8(const uint4& u, float* v) {
+  float2 f;
+  f = bf16x2_to_float2(u.x); v[0] = f.x; v[1] = f.y;
+  f = bf16x2_to_float2(u.y); v[2] = f.x; v[3] = f.y;
+  f = bf16x2_to_float2(u.z); v[4] = f.x; v[5] = f.y;
+  f = bf16x2_to_float2(u.w); v[6] = f.x; v[7] = f.y;
+}
+// 16-byte chunk c (0..7) of row r inside a [rows][64 bf16] swizzle-128B box (what TMA reads / writes)
+__device__ __forceinline__ uint32_t box_off(int r, int c) { return (uint32_t)r * 128u + (uint32_t)((c ^ (r & 7)) << 4); }
+
+__device__ __forceinline__ void epi_barrier() { asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory"); }
 
 template <int BN, int EPI>
-__global__ void __launch_bounds__(kThreads, 1)
-gg_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, GGParams p) {
-  using Cfg = GGCfg<BN>;
+__global__ void __launch_bounds__(kGGThreads, 1)
+gg_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+          const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmOut2,
+          const __grid_constant__ CUtensorMap tmAux, GGParams p) {
+  using Cfg = GGCfg<BN, EPI>;
   constexpr int STAGES = Cfg::STAGES;
+  constexpr int NB = BN / 64;  // 64-column boxes per tile
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE);
+  uint8_t* stg = smem + STAGES * Cfg::STAGE;                 // staging boxes (1024-aligned)
+  uint64_t* full = reinterpret_cast<uint64_t*>(stg + Cfg::STAGING);
   uint64_t* empty = full + STAGES;
   uint64_t* tfull = empty + STAGES;
   uint64_t* tempty = tfull + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  uint64_t* aux_full = tempty + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(aux_full + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
+    tma_prefetch_desc(&tmOut);
   }
   if (warp == 1) {
     if (lane == 0) {
       for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-      for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 128); }
+      for (int a = 0; a < 2; ++a) {
+        mbar_init(&tfull[a], 1);
+        mbar_init(&tempty[a], kEpiWarps * 32);
+        mbar_init(&aux_full[a], 1);
+      }
       fence_barrier_init();
     }
     __syncwarp();
@@ -142,21 +170,53 @@ gg_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
       }
     }
   } else {
-    const int q = warp & 3;  // TMEM lane quarter this warp may read
-    const int row_in_tile = q * 32 + lane;
-    uint32_t acc = 0, acc_phase = 0;
+    // ---- epilogue: TMEM -> registers -> (bias / GELU / GELU') -> bf16 -> swizzled smem box -> TMA store.
+    // Warp w reads TMEM lanes 32*(w%4).. (hardware rule); the two warps of a quarter split each
+    // 64-column box into 32-column halves.
+    const int q = warp & 3;
+    const int hh = (warp - 2) >> 2;
+    const int r = q * 32 + lane;                 // row inside the tile
+    const bool leader = threadIdx.x == 64;       // issues the TMA stores / aux loads
+    uint8_t* st_out = stg;
+    uint8_t* st_out2 = stg + 2 * BOX_BYTES;
+    uint8_t* st_aux = stg + 4 * BOX_BYTES;
+    uint32_t acc = 0, acc_phase = 0, g = 0;      // g: running box counter (staging buffer parity)
+    const bool two_out = (EPI == EPI_DGELU) || (EPI == EPI_FC1 && p.save_out2);
+    if (EPI == EPI_DGELU && leader && blockIdx.x < total) {
+      const int m_blk = blockIdx.x / n_tiles, n_blk = blockIdx.x % n_tiles;
+      mbar_expect_tx(&aux_full[0], BOX_BYTES);
+      tma_load_2d(st_aux, &tmAux, &aux_full[0], n_blk * BN, m_blk * BM);
+    }
     for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
       const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
       const int e = p.tile_expert[m_blk];
-      const int64_t row = (int64_t)m_blk * BM + row_in_tile;
       mbar_wait(&tfull[acc], acc_phase);
       tcgen05_fence_after();
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
+      for (int cb = 0; cb < NB; ++cb, ++g) {
+        const uint32_t buf = g & 1;
+        // the TMA store that last read staging buffer `buf` (two boxes ago) must have drained it
+        if (leader) tma_store_wait_read<1>();
+        epi_barrier();
+        if (EPI == EPI_DGELU) {
+          if (leader) {  // prefetch the hpre box of the NEXT (tile, box) into the other aux buffer
+            int nt = tile, ncb = cb + 1;
+            if (ncb == NB) { ncb = 0; nt += gridDim.x; }
+            if (nt < total) {
+              mbar_expect_tx(&aux_full[buf ^ 1], BOX_BYTES);
+              tma_load_2d(st_aux + (buf ^ 1) * BOX_BYTES, &tmAux, &aux_full[buf ^ 1],
+                          (nt % n_tiles) * BN + ncb * 64, (nt / n_tiles) * BM);
+            }
+          }
+          mbar_wait(&aux_full[buf], (g >> 1) & 1);
+        }
         float v[32];
-        tmem_ld_32x32(tmem_base + acc * BN + c * 32 + ((uint32_t)(q * 32) << 16), v);
-        const int col = n_blk * BN + c * 32;
-        const int64_t o = row * p.N + col;
+        tmem_ld_32x32(tmem_base + acc * BN + cb * 64 + hh * 32 + ((uint32_t)(q * 32) << 16), v);
+        if (cb == NB - 1) {  // last TMEM read of this accumulator: hand it back to the MMA warp early
+          tcgen05_fence_before();
+          mbar_arrive(&tempty[acc]);
+        }
+        const int col = n_blk * BN + cb * 64 + hh * 32;
         if (EPI == EPI_BIAS || EPI == EPI_FC1) {
           const float4* b4 = reinterpret_cast<const float4*>(p.bias + (int64_t)e * p.N + col);
 #pragma unroll
@@ -165,41 +225,45 @@ gg_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
             v[4 * j] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
           }
         }
+        uint8_t* o1 = st_out + buf * BOX_BYTES;
+        uint8_t* o2 = st_out2 + buf * BOX_BYTES;
         if (EPI == EPI_FC1) {
-          if (p.out2 != nullptr) {
+          if (p.save_out2) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) *reinterpret_cast<uint4*>(p.out2 + o + 8 * j) = pack8(v + 8 * j);
+            for (int j = 0; j < 4; ++j) *reinterpret_cast<uint4*>(o2 + box_off(r, hh * 4 + j)) = pack8(v + 8 * j);
           }
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+          for (int j = 0; j < 32; ++j) v[j] = gelu_fast(v[j]);
         }
         if (EPI == EPI_DGELU) {
-          float hv[32];
+          const uint8_t* ax = st_aux + buf * BOX_BYTES;
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
-            const uint4 u = __ldg(reinterpret_cast<const uint4*>(p.aux_in + o + 8 * j));
-            float2 f;
-            f = bf16x2_to_float2(u.x); hv[8 * j] = f.x; hv[8 * j + 1] = f.y;
-            f = bf16x2_to_float2(u.y); hv[8 * j + 2] = f.x; hv[8 * j + 3] = f.y;
-            f = bf16x2_to_float2(u.z); hv[8 * j + 4] = f.x; hv[8 * j + 5] = f.y;
-            f = bf16x2_to_float2(u.w); hv[8 * j + 6] = f.x; hv[8 * j + 7] = f.y;
-          }
+            float hv[8];
+            unpack8(*reinterpret_cast<const uint4*>(ax + box_off(r, hh * 4 + j)), hv);
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            v[j] *= gelu_erf_grad(hv[j]);
-            hv[j] = gelu_erf(hv[j]);
+            for (int i = 0; i < 8; ++i) {
+              float gl;
+              v[8 * j + i] *= gelu_fast_grad(hv[i], &gl);
+              hv[i] = gl;
+            }
+            *reinterpret_cast<uint4*>(o2 + box_off(r, hh * 4 + j)) = pack8(hv);   // h = gelu(hpre) for wgrad
           }
-#pragma unroll
-          for (int j = 0; j < 4; ++j) *reinterpret_cast<uint4*>(p.out2 + o + 8 * j) = pack8(hv + 8 * j);
         }
 #pragma unroll
-        for (int j = 0; j < 4; ++j) *reinterpret_cast<uint4*>(p.out + o + 8 * j) = pack8(v + 8 * j);
+        for (int j = 0; j < 4; ++j) *reinterpret_cast<uint4*>(o1 + box_off(r, hh * 4 + j)) = pack8(v + 8 * j);
+        fence_proxy_async_smem();
+        epi_barrier();
+        if (leader) {
+          tma_store_2d(&tmOut, o1, n_blk * BN + cb * 64, m_blk * BM);
+          if (two_out) tma_store_2d(&tmOut2, o2, n_blk * BN + cb * 64, m_blk * BM);
+          tma_store_commit();
+        }
       }
-      tcgen05_fence_before();
-      mbar_arrive(&tempty[acc]);
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
     }
+    if (leader) tma_store_wait_read<0>();
   }
   tcgen05_fence_before();
   __syncthreads();
@@ -397,36 +461,51 @@ static int make_map(CUtensorMap* m, const void* base, uint64_t rows, uint64_t co
   return r == CUDA_SUCCESS ? M3_OK : M3_ERR_ARG;
 }
 
-static int pick_bn(int N) { return N % 192 == 0 ? 192 : (N % 256 == 0 ? 256 : (N % 128 == 0 ? 128 : 0)); }
+// BN = 256 leaves too little smem for the two-output epilogues: those use 192 or 128
+static int pick_bn(int N, bool heavy_epilogue) {
+  if (N % 192 == 0) return 192;
+  if (N % 256 == 0 && !heavy_epilogue) return 256;
+  return N % 128 == 0 ? 128 : 0;
+}
 
 template <int BN, int EPI>
-static int launch_gg_t(const CUtensorMap& tA, const CUtensorMap& tB, const GGParams& p, int max_tiles, cudaStream_t st) {
-  using Cfg = GGCfg<BN>;
+static int launch_gg_t(const CUtensorMap* maps, const GGParams& p, int max_tiles, cudaStream_t st) {
+  using Cfg = GGCfg<BN, EPI>;
   auto kern = gg_kernel<BN, EPI>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
   if (e != cudaSuccess) return (int)e;
   int grid = max_tiles < kNumSMs ? max_tiles : kNumSMs;
   if (grid < 1) grid = 1;
-  kern<<<grid, kThreads, Cfg::SMEM, st>>>(tA, tB, p);
+  kern<<<grid, kGGThreads, Cfg::SMEM, st>>>(maps[0], maps[1], maps[2], maps[3], maps[4], p);
   M3_LAUNCH_CHECK();
   return M3_OK;
 }
 
-// A [cap_rows][Kd] bf16, B [E*N][Kd] bf16 -> out [cap_rows][N]
+// A [cap_rows][Kd] bf16, B [E*N][Kd] bf16 -> out [cap_rows][N] (+ out2 / aux of the same shape)
 template <int EPI>
-static int launch_gg(const void* A, const void* B, GGParams p, int cap_rows, cudaStream_t st) {
-  const int BN = pick_bn(p.N);
+static int launch_gg(const void* A, const void* B, void* out, void* out2, const void* aux, GGParams p, int cap_rows,
+                     cudaStream_t st) {
+  constexpr bool heavy = (EPI == EPI_FC1 || EPI == EPI_DGELU);
+  const int BN = pick_bn(p.N, heavy);
   if (BN == 0 || p.Kd % BK != 0 || cap_rows % BM != 0) return M3_ERR_SHAPE;
-  CUtensorMap tA, tB;
-  int rc = make_map(&tA, A, (uint64_t)cap_rows, (uint64_t)p.Kd, BM);
+  CUtensorMap maps[5];
+  int rc = make_map(&maps[0], A, (uint64_t)cap_rows, (uint64_t)p.Kd, BM);
   if (rc) return rc;
-  rc = make_map(&tB, B, (uint64_t)p.E * p.N, (uint64_t)p.Kd, (uint32_t)BN);
+  rc = make_map(&maps[1], B, (uint64_t)p.E * p.N, (uint64_t)p.Kd, (uint32_t)BN);
+  if (rc) return rc;
+  rc = make_map(&maps[2], out, (uint64_t)cap_rows, (uint64_t)p.N, BM);
+  if (rc) return rc;
+  rc = make_map(&maps[3], out2 ? out2 : out, (uint64_t)cap_rows, (uint64_t)p.N, BM);
+  if (rc) return rc;
+  rc = make_map(&maps[4], aux ? aux : out, (uint64_t)cap_rows, (uint64_t)p.N, BM);
   if (rc) return rc;
   const int max_tiles = (cap_rows / BM) * (p.N / BN);
   switch (BN) {
-    case 128: return launch_gg_t<128, EPI>(tA, tB, p, max_tiles, st);
-    case 192: return launch_gg_t<192, EPI>(tA, tB, p, max_tiles, st);
-    default: return launch_gg_t<256, EPI>(tA, tB, p, max_tiles, st);
+    case 128: return launch_gg_t<128, EPI>(maps, p, max_tiles, st);
+    case 192: return launch_gg_t<192, EPI>(maps, p, max_tiles, st);
+    default:
+      if constexpr (!heavy) return launch_gg_t<256, EPI>(maps, p, max_tiles, st);
+      return M3_ERR_SHAPE;
   }
 }
 
@@ -485,12 +564,12 @@ int m3_ffn_fwd_bf16(const void* xq, const int32_t* offsets, const int32_t* tile_
   GGParams p{};
   p.offsets = offsets; p.tile_expert = tile_expert; p.E = E;
   // fc1: h = gelu(xq W1^T + b1), hpre saved for backward
-  p.N = H; p.Kd = D; p.bias = b1; p.out = h; p.out2 = static_cast<bf16*>(hpre);
-  int rc = launch_gg<EPI_FC1>(xq, w1, p, cap_rows, st);
+  p.N = H; p.Kd = D; p.bias = b1; p.save_out2 = hpre != nullptr;
+  int rc = launch_gg<EPI_FC1>(xq, w1, h, hpre, nullptr, p, cap_rows, st);
   if (rc) return rc;
   // fc2: yq = h W2^T + b2
-  p.N = D; p.Kd = H; p.bias = b2; p.out = static_cast<bf16*>(yq); p.out2 = nullptr;
-  return launch_gg<EPI_BIAS>(h, w2, p, cap_rows, st);
+  p.N = D; p.Kd = H; p.bias = b2; p.save_out2 = 0;
+  return launch_gg<EPI_BIAS>(h, w2, yq, nullptr, nullptr, p, cap_rows, st);
 }
 
 int m3_ffn_bwd_bf16(const void* xq, const void* hpre, const void* dyq, const int32_t* counts, const int32_t* offsets,
@@ -506,12 +585,12 @@ int m3_ffn_bwd_bf16(const void* xq, const void* hpre, const void* dyq, const int
   GGParams p{};
   p.offsets = offsets; p.tile_expert = tile_expert; p.E = E;
   // dhpre = (dyq W2) * gelu'(hpre);  h = gelu(hpre)      B = W2^T [E][H][D] (K-major in D)
-  p.N = H; p.Kd = D; p.aux_in = static_cast<const bf16*>(hpre); p.out = dhpre; p.out2 = h;
-  int rc = launch_gg<EPI_DGELU>(dyq, w2t, p, cap_rows, st);
+  p.N = H; p.Kd = D;
+  int rc = launch_gg<EPI_DGELU>(dyq, w2t, dhpre, h, hpre, p, cap_rows, st);
   if (rc) return rc;
   // dxq = dhpre W1                                       B = W1^T [E][D][H] (K-major in H)
-  p.N = D; p.Kd = H; p.aux_in = nullptr; p.out = static_cast<bf16*>(dxq); p.out2 = nullptr;
-  rc = launch_gg<EPI_STORE>(dhpre, w1t, p, cap_rows, st);
+  p.N = D; p.Kd = H;
+  rc = launch_gg<EPI_STORE>(dhpre, w1t, dxq, nullptr, nullptr, p, cap_rows, st);
   if (rc) return rc;
   // dW2[e] = dyq_e^T h_e  [D][H];   dW1[e] = dhpre_e^T xq_e  [H][D]
   rc = launch_wgrad(dyq, h, offsets, cap_rows, E, D, H, dw2, st);
