@@ -372,7 +372,7 @@ __global__ void gate_bwd_dw_kernel(const XT* __restrict__ x, int64_t ldx, const 
     for (int c = 0; c < EW; ++c) acc[i][c] = 0.f;
 #pragma unroll
   for (int c = 0; c < EW; ++c) cs[c] = 0.f;
-#pragma unroll 4
+#pragma unroll 8
   for (int t = t0; t < t1; ++t) {
     float xv[4];
     if constexpr (sizeof(XT) == 4) {
@@ -411,30 +411,47 @@ __global__ void gate_bwd_dw_kernel(const XT* __restrict__ x, int64_t ldx, const 
 }
 
 // dW[d][e] = sum_chunks part (fixed order); task rows from the column sums of dz.
-__global__ void gate_bwd_reduce_kernel(const float* __restrict__ part, const float* __restrict__ cs_part,
-                                       int nchunk, int D, int Dt, int E, const float* __restrict__ task_feat,
-                                       const float* __restrict__ w_gate, float* __restrict__ dw,
-                                       float* __restrict__ dtask) {
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+// A block of 256 threads owns 32 consecutive outputs; its 8 warps stride over the chunks and
+// are combined in a fixed order (deterministic), so every output is summed 8-wide.
+__global__ void __launch_bounds__(256)
+gate_bwd_reduce_kernel(const float* __restrict__ part, const float* __restrict__ cs_part, int nchunk, int D, int Dt,
+                       int E, const float* __restrict__ task_feat, const float* __restrict__ w_gate,
+                       float* __restrict__ dw, float* __restrict__ dtask) {
+  __shared__ float red[8][32];
+  __shared__ float cs_s[128];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int64_t n_main = (int64_t)D * E;
-  if (i < n_main) {
+  const int64_t i = (int64_t)blockIdx.x * 32 + lane;
+  if ((int64_t)blockIdx.x * 32 < n_main) {
     float a = 0.f;
-    for (int c = 0; c < nchunk; ++c) a += part[(int64_t)c * n_main + i];
-    dw[i] = a;
-  } else if (i < n_main + (int64_t)Dt * E) {
-    const int j = (int)((i - n_main) / E), e = (int)((i - n_main) % E);
-    float cs = 0.f;
-    for (int c = 0; c < nchunk; ++c) cs += cs_part[(int64_t)c * E + e];
-    dw[i] = __ldg(task_feat + j) * cs;
-  } else if (dtask != nullptr && i < n_main + (int64_t)Dt * E + Dt) {
-    const int j = (int)(i - n_main - (int64_t)Dt * E);
-    float a = 0.f;
-    for (int e = 0; e < E; ++e) {
-      float cs = 0.f;
-      for (int c = 0; c < nchunk; ++c) cs += cs_part[(int64_t)c * E + e];
-      a = fmaf(__ldg(w_gate + (int64_t)(D + j) * E + e), cs, a);
+    if (i < n_main)
+      for (int c = w; c < nchunk; c += 8) a += part[(int64_t)c * n_main + i];
+    red[w][lane] = a;
+    __syncthreads();
+    if (w == 0 && i < n_main) {
+      float s = 0.f;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) s += red[q][lane];
+      dw[i] = s;
     }
-    dtask[j] = a;
+    return;
+  }
+  // trailing block(s): task-feature rows.  column sums of dz first (E <= 128)
+  if (threadIdx.x < E) {
+    float cs = 0.f;
+    for (int c = 0; c < nchunk; ++c) cs += cs_part[(int64_t)c * E + threadIdx.x];
+    cs_s[threadIdx.x] = cs;
+  }
+  __syncthreads();
+  for (int k = threadIdx.x; k < Dt * E + Dt; k += 256) {
+    if (k < Dt * E) {
+      dw[n_main + k] = __ldg(task_feat + k / E) * cs_s[k % E];
+    } else if (dtask != nullptr) {
+      const int j = k - Dt * E;
+      float a = 0.f;
+      for (int e = 0; e < E; ++e) a = fmaf(__ldg(w_gate + (int64_t)(D + j) * E + e), cs_s[e], a);
+      dtask[j] = a;
+    }
   }
 }
 
@@ -461,7 +478,7 @@ __global__ void gate_bwd_dx_kernel(const float* __restrict__ dz, const float* __
 static inline int gate_bwd_chunks(int T, int E) {
   const int yb = (E > 16) ? E / 16 : 1;
   int n = m3_ceil_div(T, 64);
-  int cap = (2 * kNumSMs) / yb;
+  int cap = (4 * kNumSMs) / yb;
   if (cap < 1) cap = 1;
   return n < cap ? (n < 1 ? 1 : n) : cap;
 }
@@ -577,9 +594,9 @@ extern "C" int m3_gate_bwd(const void* x, int x_dtype, int64_t ldx, const float*
     M3_LAUNCH_CHECK();
   }
   {
-    const int64_t n = (int64_t)D * E + (int64_t)Dt * E + Dt;
-    gate_bwd_reduce_kernel<<<(int)((n + 255) / 256), 256, 0, st>>>(part, cs_part, nchunk, D, Dt, E, task_feat, w_gate,
-                                                                   dw_gate, dtask_feat);
+    const int main_blocks = (int)(((int64_t)D * E + 31) / 32);
+    gate_bwd_reduce_kernel<<<main_blocks + (Dt > 0 ? 1 : 0), 256, 0, st>>>(part, cs_part, nchunk, D, Dt, E, task_feat,
+                                                                          w_gate, dw_gate, dtask_feat);
     M3_LAUNCH_CHECK();
   }
   if (dx_gate != nullptr) {

@@ -180,58 +180,71 @@ combine_bwd_kernel(const TG* __restrict__ g, Queue<const TQ> yq, const int32_t* 
 }
 
 // dx[t] = sum_k dxq[pos[t,k]]  (+ dz[t] @ w_gate[:D]^T : the router's dx, gate input == layer input)
+// Grid-stride over 16-token batches.  With the router term, w_gate[:D] is staged ONCE per CTA
+// in shared memory, transposed to [E][D] so that the 16 lanes of a token read consecutive
+// 32-byte slices (conflict-free; the two tokens of a warp broadcast).
 template <typename TI, typename TO, int NV, bool EP>
 __global__ void __launch_bounds__(kPermThreads)
 dispatch_bwd_kernel(Queue<const TI> dxq, const int32_t* __restrict__ pos, int T, int K, int D,
                     const float* __restrict__ dz, const float* __restrict__ w_gate, int E,
                     TO* __restrict__ dx) {
-  const int sub = threadIdx.x % kLanesPerTok;
-  const int t = blockIdx.x * kTokPerCta + threadIdx.x / kLanesPerTok;
-  if (t >= T) return;
-  const int nvec = D / 8;
-  Vec8 acc[NV];
-#pragma unroll
-  for (int i = 0; i < NV; ++i)
-#pragma unroll
-    for (int j = 0; j < 8; ++j) acc[i].v[j] = 0.f;
-  for (int k = 0; k < K; ++k) {
-    const int row = __ldg(pos + (int64_t)t * K + k);
-    if (row < 0) continue;
-    const TI* src = dxq.template row<EP>((int64_t)t * K + k, row, D);
-    Vec8 v[NV];
-#pragma unroll
-    for (int i = 0; i < NV; ++i) {
-      const int c = sub + i * kLanesPerTok;
-      if (c < nvec) v[i] = load8<TI>(src + c * 8);
+  extern __shared__ __align__(16) float wt[];  // [E][D] (only when dz != nullptr)
+  if (dz != nullptr) {
+    for (int i = threadIdx.x; i < D * E; i += kPermThreads) {
+      const int d = i / E, e = i % E;           // coalesced read of w_gate[d][e]
+      wt[e * D + d] = __ldg(w_gate + i);
     }
+    __syncthreads();
+  }
+  const int sub = threadIdx.x % kLanesPerTok;
+  const int nvec = D / 8;
+  for (int t = blockIdx.x * kTokPerCta + threadIdx.x / kLanesPerTok; t < T; t += gridDim.x * kTokPerCta) {
+    Vec8 acc[NV];
 #pragma unroll
     for (int i = 0; i < NV; ++i)
 #pragma unroll
-      for (int j = 0; j < 8; ++j) acc[i].v[j] += v[i].v[j];
-  }
-  if (dz != nullptr) {
-    for (int e = 0; e < E; e += 4) {
-      const float4 gz = __ldg(reinterpret_cast<const float4*>(dz + (int64_t)t * E + e));
+      for (int j = 0; j < 8; ++j) acc[i].v[j] = 0.f;
+    for (int k = 0; k < K; ++k) {
+      const int row = __ldg(pos + (int64_t)t * K + k);
+      if (row < 0) continue;
+      const TI* src = dxq.template row<EP>((int64_t)t * K + k, row, D);
+      Vec8 v[NV];
 #pragma unroll
       for (int i = 0; i < NV; ++i) {
         const int c = sub + i * kLanesPerTok;
-        if (c < nvec) {
+        if (c < nvec) v[i] = load8<TI>(src + c * 8);
+      }
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const float4 w = __ldg(reinterpret_cast<const float4*>(w_gate + (int64_t)(c * 8 + j) * E + e));
-            float a = acc[i].v[j];
-            a = fmaf(gz.x, w.x, a); a = fmaf(gz.y, w.y, a);
-            a = fmaf(gz.z, w.z, a); a = fmaf(gz.w, w.w, a);
-            acc[i].v[j] = a;
+      for (int i = 0; i < NV; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i].v[j] += v[i].v[j];
+    }
+    if (dz != nullptr) {
+      for (int e = 0; e < E; e += 4) {
+        const float4 gz4 = __ldg(reinterpret_cast<const float4*>(dz + (int64_t)t * E + e));
+        const float gz[4] = {gz4.x, gz4.y, gz4.z, gz4.w};
+#pragma unroll
+        for (int ee = 0; ee < 4; ++ee) {
+#pragma unroll
+          for (int i = 0; i < NV; ++i) {
+            const int c = sub + i * kLanesPerTok;
+            if (c < nvec) {
+              const float4 w0 = *reinterpret_cast<const float4*>(wt + (e + ee) * D + c * 8);
+              const float4 w1 = *reinterpret_cast<const float4*>(wt + (e + ee) * D + c * 8 + 4);
+              acc[i].v[0] = fmaf(gz[ee], w0.x, acc[i].v[0]); acc[i].v[1] = fmaf(gz[ee], w0.y, acc[i].v[1]);
+              acc[i].v[2] = fmaf(gz[ee], w0.z, acc[i].v[2]); acc[i].v[3] = fmaf(gz[ee], w0.w, acc[i].v[3]);
+              acc[i].v[4] = fmaf(gz[ee], w1.x, acc[i].v[4]); acc[i].v[5] = fmaf(gz[ee], w1.y, acc[i].v[5]);
+              acc[i].v[6] = fmaf(gz[ee], w1.z, acc[i].v[6]); acc[i].v[7] = fmaf(gz[ee], w1.w, acc[i].v[7]);
+            }
           }
         }
       }
     }
-  }
 #pragma unroll
-  for (int i = 0; i < NV; ++i) {
-    const int c = sub + i * kLanesPerTok;
-    if (c < nvec) store8<TO>(dx + (int64_t)t * D + c * 8, acc[i]);
+    for (int i = 0; i < NV; ++i) {
+      const int c = sub + i * kLanesPerTok;
+      if (c < nvec) store8<TO>(dx + (int64_t)t * D + c * 8, acc[i]);
+    }
   }
 }
 
@@ -331,10 +344,26 @@ static int dispatch_bwd_impl(const void* dxq, void* const* peer, const int32_t* 
   if (rc) return rc;
   if (T == 0) return M3_OK;
   const int nv = perm_nv(D);
-  const int grid = m3_ceil_div(T, kTokPerCta);
+  int grid = m3_ceil_div(T, kTokPerCta);
+  size_t smem = 0;
+  if (dz != nullptr) {
+    // router term: stage w_gate[:D] once per CTA -> fewer, grid-striding CTAs
+    smem = (size_t)D * E * sizeof(float);
+    if (smem > 200 * 1024) return M3_ERR_SHAPE;
+    const int per_sm = smem > 0 ? (int)((200 * 1024) / smem) : 8;
+    const int cap = kNumSMs * (per_sm < 1 ? 1 : (per_sm > 6 ? 6 : per_sm));
+    if (grid > cap) grid = cap;
+  }
   M3_DTYPE2_SWITCH(dxq_dtype, dx_dtype, {
     Queue<const TA> q{(const TA*)dxq, (const TA* const*)peer, slot_rank};
-    M3_NV_SWITCH((dispatch_bwd_kernel<TA, TB, NV, EP><<<grid, kPermThreads, 0, st>>>(q, pos, T, K, D, dz, w_gate, E, (TB*)dx)))
+    M3_NV_SWITCH({
+      auto kern = dispatch_bwd_kernel<TA, TB, NV, EP>;
+      if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return (int)e;
+      }
+      kern<<<grid, kPermThreads, smem, st>>>(q, pos, T, K, D, dz, w_gate, E, (TB*)dx);
+    })
   })
   M3_LAUNCH_CHECK();
   return M3_OK;

@@ -127,13 +127,27 @@ route_assign_kernel(const int64_t* __restrict__ idx, int R, int E, int pad, int 
       tile_expert[i] = lo;
     }
     if (importance != nullptr && imp_partial != nullptr) {
-      for (int e = tid; e < E; e += kRouteThreads) {
+      // fixed assignment (thread -> partials p = part, part+P, ...) and fixed-order final sum:
+      // deterministic, but 256 threads wide instead of E
+      float* fs = reinterpret_cast<float*>(bh + kRouteBatches * E);   // [P][E] scratch behind bh
+      int* is = bh + kRouteBatches * E + kRouteThreads;               // [P][E]
+      const int P = kRouteThreads / E > 0 ? kRouteThreads / E : 1;
+      if (tid < P * E) {
+        const int e = tid % E, part = tid / E;
         float a = 0.f;
         int l = 0;
-        for (int i = 0; i < n_partial; ++i) {
+        for (int i = part; i < n_partial; i += P) {
           a += imp_partial[(int64_t)i * E + e];
           l += load_partial[(int64_t)i * E + e];
         }
+        fs[part * E + e] = a;
+        is[part * E + e] = l;
+      }
+      __syncthreads();
+      for (int e = tid; e < E; e += kRouteThreads) {
+        float a = 0.f;
+        int l = 0;
+        for (int q = 0; q < P; ++q) { a += fs[q * E + e]; l += is[q * E + e]; }
         importance[e] = a;
         if (load != nullptr) load[e] = (float)l;
       }
@@ -177,7 +191,7 @@ extern "C" int m3_route_plan(const int64_t* idx, int T, int K, int E, int pad, c
   int32_t* block_hist = static_cast<int32_t*>(workspace);
   route_count_kernel<<<nblk, kRouteThreads, E * sizeof(int), st>>>(idx, R, E, block_hist);
   M3_LAUNCH_CHECK();
-  const size_t smem = (size_t)(3 * E + 1 + kRouteBatches * E) * sizeof(int);
+  const size_t smem = (size_t)(3 * E + 1 + kRouteBatches * E + 2 * kRouteThreads) * sizeof(int);
   route_assign_kernel<<<nblk, kRouteThreads, smem, st>>>(idx, R, E, pad, nblk, block_hist, imp_partial, load_partial,
                                                           n_partial, counts, offsets, pos, tile_expert, importance,
                                                           load);
