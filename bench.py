@@ -149,12 +149,19 @@ def build_layers(dev, compute_dtype):
     return layers
 
 
+_CV_W = {}
+
+
 def one_call(layer, x, g, task):
+    """forward + backward of one layer call: d(out) = g (what the next block would hand back) and the
+    balance loss with weight 0.01 (train/train_utils.py:437-449)."""
     out = layer(x, task_id=task)
     gate_loss = layer.gate[task].get_loss()
-    loss = (out * g).sum() + 0.01 * gate_loss        # cv-loss weight 0.01 (train/train_utils.py:437-449)
-    loss.backward()
-    return loss
+    w = _CV_W.get(x.device)
+    if w is None:
+        w = _CV_W[x.device] = torch.tensor(0.01, device=x.device)
+    torch.autograd.backward([out, gate_loss], [g, w])
+    return gate_loss
 
 
 def main():
@@ -346,7 +353,7 @@ def kernel_rooflines(layer, x, dev, cdt, pk, iters=20):
     add("ffn_fwd", lambda: ops.ffn_fwd(xq, plan, w1c, b1, w2c, b2), 2, flops=4.0 * R * D * H)
     add("combine_fwd", lambda: ops.combine_fwd(yq, plan, g.score), 1, nbytes=T * (K * D * el + K * 8 + D * 4))
     add("combine_bwd", lambda: ops.combine_bwd(go, yq, plan, g.score), 1, nbytes=T * (D * 4 + 2 * K * D * el + K * 12))
-    nb = 8 if cdt == torch.bfloat16 else 6
+    nb = 4 if cdt == torch.bfloat16 else 6
     add("ffn_bwd", lambda: ops.ffn_bwd(xq, hpre, dyq, plan, w1c, w2c, w1t, w2t), nb, flops=8.0 * R * D * H)
     dxq = ops.ffn_bwd(xq, hpre, dyq, plan, w1c, w2c, w1t, w2t)[0]
     dz = ops.gate_bwd(x, wg, g.noisy_logits, g.idx_full, K, dscore=dscore)[0]

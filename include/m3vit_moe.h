@@ -84,6 +84,8 @@ int m3_gate_fwd(const void* x, int x_dtype, int64_t ldx, const float* task_feat,
  * then dw_gate = [x,tf]^T dz and dtask_feat.  dz is written for m3_dispatch_bwd,
  * which adds dz @ w_gate[:D]^T into dx.   Any of the d* inputs may be NULL (= 0).
  *   logits [T,E] = the (noisy) logits the forward soft-maxed
+ *   importance[E] + dcv_loss[1] (both or neither): gradient of m3_route_plan's cv_loss,
+ *            chained analytically through cv^2(importance) (the load term is piecewise constant)
  *   dz [T,E] out;  dw_gate [D+Dt, E] out (overwritten);  dtask_feat [Dt] out or NULL
  *   dx_gate [T,D] fp32 out or NULL: dz @ w_gate[:D]^T, for callers whose gate input
  *            is not the layer input (Block.gate_input_ahead)
@@ -92,9 +94,10 @@ size_t m3_gate_bwd_workspace_bytes(int T, int D, int Dt, int E);
 int m3_gate_bwd(const void* x, int x_dtype, int64_t ldx, const float* task_feat, const float* w_gate,
                 const float* logits, const int32_t* idx_full, int T, int D, int Dt, int E, int K,
                 const float* dscore, const float* dtop_vals, const float* dgates,
-                const float* dimportance, const float* dclean, const float* dnoisy, float* dz,
-                float* dw_gate, float* dtask_feat, float* dx_gate, void* workspace,
-                size_t workspace_bytes, m3_stream_t stream);
+                const float* dimportance, const float* dclean, const float* dnoisy,
+                const float* importance, const float* dcv_loss, float* dz, float* dw_gate,
+                float* dtask_feat, float* dx_gate, void* workspace, size_t workspace_bytes,
+                m3_stream_t stream);
 
 /* -------------------------------------------------------------- route plan --
  * Replaces fmoe_cuda.expert_count + assign_pos (+ the host-side cumsum and the
@@ -104,7 +107,9 @@ int m3_gate_bwd(const void* x, int x_dtype, int64_t ldx, const float* task_feat,
  *   idx [T,K] int64 -> counts[E], offsets[E+1] (padded exclusive prefix),
  *   pos[T*K] (slot t*K+k -> queue row), tile_expert[offsets[E]/pad] (expert of
  *   every pad-row tile; capacity m3_route_max_tiles), and, if the partials of
- *   m3_gate_fwd are passed, importance[E] / load[E] fp32 (fixed-order sums).
+ *   m3_gate_fwd are passed, importance[E] / load[E] fp32 (fixed-order sums) and
+ *   cv_loss[1] = cv^2(importance) + cv^2(load), cv^2(u) = var_unbiased(u)/(mean(u)^2+1e-10)
+ *   (noisy_gate_vmoe.py:127-141,278-283; the hard-count load of the noise-free path).
  */
 size_t m3_route_plan_workspace_bytes(int T, int K, int E);
 int m3_route_max_rows(int T, int K, int E, int pad);   /* queue capacity in rows  */
@@ -112,7 +117,7 @@ int m3_route_max_tiles(int T, int K, int E, int pad);  /* = max_rows / pad      
 int m3_route_plan(const int64_t* idx, int T, int K, int E, int pad, const float* imp_partial,
                   const int32_t* load_partial, int n_partial, int32_t* counts, int32_t* offsets,
                   int32_t* pos, int32_t* tile_expert, float* importance, float* load,
-                  void* workspace, size_t workspace_bytes, m3_stream_t stream);
+                  float* cv_loss, void* workspace, size_t workspace_bytes, m3_stream_t stream);
 
 /* -------------------------------------------------------- dispatch/combine --
  * HBM-bound row movers, 128-bit vectorised.  D % 8 == 0.

@@ -31,11 +31,11 @@ SIGNATURES = {
     "m3_gate_fwd": (_i, [_p, _i, _i64, _p, _p, _p, _f, _i, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
     "m3_gate_bwd_workspace_bytes": (_sz, [_i, _i, _i, _i]),
     "m3_gate_bwd": (_i, [_p, _i, _i64, _p, _p, _p, _p, _i, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p,
-                         _p, _sz, _p]),
+                         _p, _p, _p, _sz, _p]),
     "m3_route_plan_workspace_bytes": (_sz, [_i, _i, _i]),
     "m3_route_max_rows": (_i, [_i, _i, _i, _i]),
     "m3_route_max_tiles": (_i, [_i, _i, _i, _i]),
-    "m3_route_plan": (_i, [_p, _i, _i, _i, _i, _p, _p, _i, _p, _p, _p, _p, _p, _p, _p, _sz, _p]),
+    "m3_route_plan": (_i, [_p, _i, _i, _i, _i, _p, _p, _i, _p, _p, _p, _p, _p, _p, _p, _p, _sz, _p]),
     "m3_dispatch_fwd": (_i, [_p, _i, _p, _p, _p, _i, _i, _i, _i, _p, _i, _p]),
     "m3_dispatch_bwd": (_i, [_p, _i, _p, _i, _i, _i, _p, _p, _i, _p, _i, _p]),
     "m3_combine_fwd": (_i, [_p, _i, _p, _p, _i, _i, _i, _p, _i, _p]),

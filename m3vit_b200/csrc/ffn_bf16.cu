@@ -279,6 +279,7 @@ struct WGParams {
   const int32_t* offsets;
   int M, N;       // dW_e is [M][N]; X1 is [rows][M], X2 is [rows][N]
   float* dW;      // [E][M][N]
+  float* db;      // [E][M] = column sums of X1 over the expert's rows (bias gradient)
 };
 
 template <int BN>
@@ -288,8 +289,10 @@ struct WGCfg {
   static constexpr int BOX = BK * 64 * 2;       // 8192 B
   static constexpr int STAGE = A_BYTES + B_BYTES;
   static constexpr int STAGES = (BN <= 128) ? 6 : 4;
-  static constexpr int TMEM_COLS = (BN <= 128) ? 128 : 256;
-  static constexpr int SMEM = STAGES * STAGE + 1024 + 256;
+  static constexpr int TMEM_COLS = 256;         // BN accumulator columns + 16 for the bias-grad MMA
+  static constexpr int ONES_BYTES = BK * 64 * 2;  // [64 k][64 n] box of bf16 ones
+  static constexpr int SMEM = STAGES * STAGE + ONES_BYTES + 1024 + 256;
+  static_assert(BN + 16 <= TMEM_COLS, "TMEM");
 };
 
 template <int BN>
@@ -299,13 +302,20 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tm1, const __grid_constant__ CU
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE);
+  uint8_t* ones = smem + STAGES * Cfg::STAGE;
+  uint64_t* full = reinterpret_cast<uint64_t*>(ones + Cfg::ONES_BYTES);
   uint64_t* empty = full + STAGES;
   uint64_t* tfull = empty + STAGES;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tfull + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int e = blockIdx.z, m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+  // db = X1^T * 1: the n0 == 0 CTAs run one extra N=16 MMA per k-step against a tile of ones
+  const bool with_db = (blockIdx.y == 0) && (p.db != nullptr);
+  if (with_db) {
+    for (int i = threadIdx.x; i < Cfg::ONES_BYTES / 4; i += kThreads) reinterpret_cast<uint32_t*>(ones)[i] = 0x3F803F80u;
+    fence_proxy_async_smem();
+  }
   if (warp == 0 && lane == 0) { tma_prefetch_desc(&tm1); tma_prefetch_desc(&tm2); }
   if (warp == 1) {
     if (lane == 0) {
@@ -343,6 +353,8 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tm1, const __grid_constant__ CU
   } else if (warp == 1) {
     if (lane == 0) {
       constexpr uint32_t idesc = make_idesc_bf16(BM, BN, 1, 1);
+      constexpr uint32_t idesc_db = make_idesc_bf16(BM, 16, 1, 1);
+      const uint32_t ones_base = smem_u32(ones);
       int stage = 0;
       uint32_t phase = 0;
       for (int kc = 0; kc < kchunks; ++kc) {
@@ -356,6 +368,10 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tm1, const __grid_constant__ CU
           const uint64_t adesc = make_smem_desc(a_base + k * 2048, Cfg::BOX, 1024);
           const uint64_t bdesc = make_smem_desc(b_base + k * 2048, Cfg::BOX, 1024);
           umma_bf16(tmem_base, adesc, bdesc, idesc, (kc | k) != 0);
+          if (with_db) {
+            const uint64_t odesc = make_smem_desc(ones_base + k * 2048, Cfg::BOX, 1024);
+            umma_bf16(tmem_base + BN, adesc, odesc, idesc_db, (kc | k) != 0);
+          }
         }
         umma_commit(&empty[stage]);
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -369,6 +385,7 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tm1, const __grid_constant__ CU
     if (kchunks == 0) {  // expert received no rows: dW_e = 0
 #pragma unroll 1
       for (int c = 0; c < BN / 4; ++c) *reinterpret_cast<float4*>(dst + 4 * c) = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (with_db) p.db[(int64_t)e * p.M + row] = 0.f;
     } else {
       mbar_wait(tfull, 0);
       tcgen05_fence_after();
@@ -379,6 +396,11 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tm1, const __grid_constant__ CU
 #pragma unroll
         for (int j = 0; j < 8; ++j)
           *reinterpret_cast<float4*>(dst + c * 32 + 4 * j) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+      }
+      if (with_db) {
+        float v[32];   // 16 identical columns (+16 unused): every column of X1^T * ones is the column sum
+        tmem_ld_32x32(tmem_base + BN + ((uint32_t)(q * 32) << 16), v);
+        p.db[(int64_t)e * p.M + row] = v[0];
       }
     }
   }
@@ -511,7 +533,7 @@ static int launch_gg(const void* A, const void* B, void* out, void* out2, const 
 
 // dW [E][M][N] fp32 = X1[rows][M]^T X2[rows][N] per expert
 static int launch_wgrad(const void* X1, const void* X2, const int32_t* offsets, int cap_rows, int E, int M, int N,
-                        float* dW, cudaStream_t st) {
+                        float* dW, float* db, cudaStream_t st) {
   constexpr int BN = 128;
   if (M % BM != 0 || N % BN != 0) return M3_ERR_SHAPE;
   CUtensorMap t1, t2;
@@ -523,7 +545,7 @@ static int launch_wgrad(const void* X1, const void* X2, const int32_t* offsets, 
   auto kern = wgrad_kernel<BN>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
   if (e != cudaSuccess) return (int)e;
-  WGParams p{offsets, M, N, dW};
+  WGParams p{offsets, M, N, dW, db};
   kern<<<dim3(M / BM, N / BN, E), kThreads, Cfg::SMEM, st>>>(t1, t2, p);
   M3_LAUNCH_CHECK();
   return M3_OK;
@@ -593,11 +615,9 @@ int m3_ffn_bwd_bf16(const void* xq, const void* hpre, const void* dyq, const int
   rc = launch_gg<EPI_STORE>(dhpre, w1t, dxq, nullptr, nullptr, p, cap_rows, st);
   if (rc) return rc;
   // dW2[e] = dyq_e^T h_e  [D][H];   dW1[e] = dhpre_e^T xq_e  [H][D]
-  rc = launch_wgrad(dyq, h, offsets, cap_rows, E, D, H, dw2, st);
+  // the bias gradients ride along as one extra N=16 MMA against a tile of ones
+  (void)part;
+  rc = launch_wgrad(dyq, h, offsets, cap_rows, E, D, H, dw2, db2, st);
   if (rc) return rc;
-  rc = launch_wgrad(dhpre, xq, offsets, cap_rows, E, H, D, dw1, st);
-  if (rc) return rc;
-  rc = launch_colsum(static_cast<const bf16*>(dyq), offsets, cap_rows, E, D, part, db2, st);
-  if (rc) return rc;
-  return launch_colsum(dhpre, offsets, cap_rows, E, H, part, db1, st);
+  return launch_wgrad(dhpre, xq, offsets, cap_rows, E, H, D, dw1, db1, st);
 }

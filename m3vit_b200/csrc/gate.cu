@@ -299,8 +299,27 @@ gate_bwd_dz_kernel(const float* __restrict__ logits, const int32_t* __restrict__
                    const float* __restrict__ dscore, const float* __restrict__ dtop,
                    const float* __restrict__ dgates, const float* __restrict__ dimp,
                    const float* __restrict__ dclean, const float* __restrict__ dnoisy,
+                   const float* __restrict__ importance, const float* __restrict__ dcv,
                    float* __restrict__ dz) {
   constexpr int EG = E / 4;
+  // gradient of cv^2(importance) w.r.t. importance[e], scaled by d(cv_loss) (added to dimp)
+  __shared__ float gimp[E];
+  if (dcv != nullptr) {
+    if (threadIdx.x == 0) {
+      float m = 0.f;
+      for (int e = 0; e < E; ++e) m += importance[e];
+      m /= (float)E;
+      float var = 0.f;
+      for (int e = 0; e < E; ++e) { const float d = importance[e] - m; var = fmaf(d, d, var); }
+      var /= (float)(E > 1 ? E - 1 : 1);
+      const float den = m * m + 1e-10f;
+      const float up = __ldg(dcv);
+      for (int e = 0; e < E; ++e)
+        gimp[e] = E > 1 ? up * (2.f * (importance[e] - m) / ((float)(E - 1) * den) - var * 2.f * m / ((float)E * den * den))
+                        : 0.f;
+    }
+    __syncthreads();
+  }
   const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int eg = (int)(gid % EG);
   const int64_t tt = gid / EG;
@@ -329,6 +348,7 @@ gate_bwd_dz_kernel(const float* __restrict__ logits, const int32_t* __restrict__
       if (dscore != nullptr) g += __ldg(dscore + t * K + r);
       if (dgates != nullptr) g += __ldg(dgates + t * E + e);
       if (dimp != nullptr) g += __ldg(dimp + e);
+      if (dcv != nullptr) g += gimp[e];
     }
     if ((e >> 2) == eg) {
 #pragma unroll
@@ -550,9 +570,11 @@ extern "C" size_t m3_gate_bwd_workspace_bytes(int T, int D, int Dt, int E) {
 extern "C" int m3_gate_bwd(const void* x, int x_dtype, int64_t ldx, const float* task_feat, const float* w_gate,
                            const float* logits, const int32_t* idx_full, int T, int D, int Dt, int E, int K,
                            const float* dscore, const float* dtop_vals, const float* dgates,
-                           const float* dimportance, const float* dclean, const float* dnoisy, float* dz,
-                           float* dw_gate, float* dtask_feat, float* dx_gate, void* workspace,
-                           size_t workspace_bytes, m3_stream_t stream) {
+                           const float* dimportance, const float* dclean, const float* dnoisy,
+                           const float* importance, const float* dcv_loss, float* dz, float* dw_gate,
+                           float* dtask_feat, float* dx_gate, void* workspace, size_t workspace_bytes,
+                           m3_stream_t stream) {
+  if ((importance == nullptr) != (dcv_loss == nullptr)) return M3_ERR_ARG;
   M3_CHECK_ARG(x && w_gate && logits && idx_full && dz && dw_gate && workspace);
   M3_CHECK_ARG(T > 0 && D > 0 && Dt >= 0 && (Dt == 0 || task_feat));
   M3_CHECK_SHAPE(D % 4 == 0 && D / 4 * 2 <= 1024 && K >= 1 && K <= E);
@@ -567,7 +589,7 @@ extern "C" int m3_gate_bwd(const void* x, int x_dtype, int64_t ldx, const float*
     const int64_t nthr = (int64_t)T * (E / 4);
     const int grid = (int)((nthr + 255) / 256);
 #define M3_DZ_CASE(EE) \
-  case EE: gate_bwd_dz_kernel<EE><<<grid, 256, 0, st>>>(logits, idx_full, T, K, K1, dscore, dtop_vals, dgates, dimportance, dclean, dnoisy, dz); break;
+  case EE: gate_bwd_dz_kernel<EE><<<grid, 256, 0, st>>>(logits, idx_full, T, K, K1, dscore, dtop_vals, dgates, dimportance, dclean, dnoisy, importance, dcv_loss, dz); break;
     switch (E) {
       M3_DZ_CASE(4) M3_DZ_CASE(8) M3_DZ_CASE(16) M3_DZ_CASE(32) M3_DZ_CASE(64) M3_DZ_CASE(128)
       default: return M3_ERR_SHAPE;

@@ -43,7 +43,7 @@ route_assign_kernel(const int64_t* __restrict__ idx, int R, int E, int pad, int 
                     const int32_t* __restrict__ load_partial, int n_partial, int32_t* __restrict__ counts,
                     int32_t* __restrict__ offsets, int32_t* __restrict__ pos,
                     int32_t* __restrict__ tile_expert, float* __restrict__ importance,
-                    float* __restrict__ load) {
+                    float* __restrict__ load, float* __restrict__ cv_loss) {
   extern __shared__ int sm[];
   int* tot = sm;                     // [E] total count per expert
   int* pre = tot + E;                // [E] count in blocks before this one
@@ -150,6 +150,26 @@ route_assign_kernel(const int64_t* __restrict__ idx, int R, int E, int pad, int 
         for (int q = 0; q < P; ++q) { a += fs[q * E + e]; l += is[q * E + e]; }
         importance[e] = a;
         if (load != nullptr) load[e] = (float)l;
+        fs[e] = a;                  // P*E >= E: reuse the first row for the cv^2 pass
+        is[e] = l;
+      }
+      __syncthreads();
+      if (tid == 0 && cv_loss != nullptr) {
+        // cv^2(u) = var_unbiased(u) / (mean(u)^2 + 1e-10); 0 for a single expert
+        float loss = 0.f;
+        if (E > 1) {
+          float mi = 0.f, ml = 0.f;
+          for (int e = 0; e < E; ++e) { mi += fs[e]; ml += (float)is[e]; }
+          mi /= (float)E; ml /= (float)E;
+          float vi = 0.f, vl = 0.f;
+          for (int e = 0; e < E; ++e) {
+            const float di = fs[e] - mi, dl = (float)is[e] - ml;
+            vi = fmaf(di, di, vi); vl = fmaf(dl, dl, vl);
+          }
+          vi /= (float)(E - 1); vl /= (float)(E - 1);
+          loss = vi / (mi * mi + 1e-10f) + vl / (ml * ml + 1e-10f);
+        }
+        *cv_loss = loss;
       }
     }
   }
@@ -176,7 +196,7 @@ extern "C" int m3_route_max_tiles(int T, int K, int E, int pad) { return m3_rout
 
 extern "C" int m3_route_plan(const int64_t* idx, int T, int K, int E, int pad, const float* imp_partial,
                              const int32_t* load_partial, int n_partial, int32_t* counts, int32_t* offsets,
-                             int32_t* pos, int32_t* tile_expert, float* importance, float* load,
+                             int32_t* pos, int32_t* tile_expert, float* importance, float* load, float* cv_loss,
                              void* workspace, size_t workspace_bytes, m3_stream_t stream) {
   M3_CHECK_ARG(idx && counts && offsets && pos && tile_expert && workspace);
   M3_CHECK_ARG(T >= 0 && K >= 1 && E >= 1 && pad >= 1);
@@ -184,6 +204,7 @@ extern "C" int m3_route_plan(const int64_t* idx, int T, int K, int E, int pad, c
   if ((int64_t)T * K > (int64_t)1 << 30) return M3_ERR_SHAPE;
   if (workspace_bytes < m3_route_plan_workspace_bytes(T, K, E)) return M3_ERR_WORKSPACE;
   if (importance != nullptr && (imp_partial == nullptr || load_partial == nullptr)) return M3_ERR_ARG;
+  if (cv_loss != nullptr && importance == nullptr) return M3_ERR_ARG;
   const int R = T * K;
   int nblk = m3_ceil_div(R, kRouteChunk);
   if (nblk < 1) nblk = 1;
@@ -194,7 +215,7 @@ extern "C" int m3_route_plan(const int64_t* idx, int T, int K, int E, int pad, c
   const size_t smem = (size_t)(3 * E + 1 + kRouteBatches * E + 2 * kRouteThreads) * sizeof(int);
   route_assign_kernel<<<nblk, kRouteThreads, smem, st>>>(idx, R, E, pad, nblk, block_hist, imp_partial, load_partial,
                                                           n_partial, counts, offsets, pos, tile_expert, importance,
-                                                          load);
+                                                          load, cv_loss);
   M3_LAUNCH_CHECK();
   return M3_OK;
 }

@@ -213,11 +213,11 @@ class FMoETransformerMLP(nn.Module):
                 x, gx, gate.w_gate, tf, self.experts.htoh4.weight, self.experts.htoh4.bias,
                 self.experts.h4toh.weight, self.experts.h4toh.bias, noise, self.top_k, nstd, cdt,
                 self.RETURN_SUMMARIES, self._wcache)
-        out, score, top_vals, clean, noisy, gates, importance, load, idx, counts = res
+        out, score, top_vals, clean, noisy, gates, importance, load, idx, counts, cv_loss = res
         self.last_counts = counts                 # device tensor, no sync: for monitoring / tests
         if self.gate_hook is not None:
             self.gate_hook(idx, score, None)                                                       # origin:240-241
-        gate._record(clean, noisy, importance, load, top_vals)
+        gate._record(clean, noisy, importance, load, top_vals, cv_loss)
         if self.RETURN_SUMMARIES and self.multi_gate:
             # ckpt:214-217: keep the unused task gates in the autograd graph (DDP "marked ready twice")
             others = [p for g in self.gate if g is not gate for p in g.parameters()]

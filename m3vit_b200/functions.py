@@ -33,7 +33,8 @@ class MoEFunction(torch.autograd.Function):
                 w1[E,H,D], b1[E,H], w2[E,D,H], b2[E,D] (fp32 masters),
                 noise[T,E]|None, then non-tensor config.
        outputs: out[T,D], score[T,K], top_vals[T,K1], clean[T,E], noisy[T,E],
-                gates[T,E]|empty, importance[E], load[E], idx[T,K], counts[E]"""
+                gates[T,E]|empty, importance[E], load[E], idx[T,K], counts[E],
+                cv_loss[] = cv^2(importance) + cv^2(load) (fused, differentiable)"""
 
     @staticmethod
     def forward(ctx, x, gate_x, w_gate, task_feat, w1, b1, w2, b2, noise, top_k, noise_stddev, compute_dtype,
@@ -54,7 +55,8 @@ class MoEFunction(torch.autograd.Function):
         out = ops.combine_fwd(yq, plan, g.score, out_dtype=x.dtype)
         if needs_grad:
             ctx.save_for_backward(x, gate_x, w_gate, task_feat, w1c, w2c, w1t, w2t, xq, hpre, yq, g.score,
-                                  g.noisy_logits, g.idx_full, plan.counts, plan.offsets, plan.pos, plan.tile_expert)
+                                  g.noisy_logits, g.idx_full, plan.counts, plan.offsets, plan.pos, plan.tile_expert,
+                                  plan.importance)
             ctx.cfg = (top_k, plan.cap_rows, gate_x is not None)
         gates = g.gates if g.gates is not None else x.new_empty(0)
         ctx.mark_non_differentiable(g.idx, plan.load, plan.counts)
@@ -63,12 +65,13 @@ class MoEFunction(torch.autograd.Function):
             noisy = g.clean_logits.view_as(g.clean_logits)
         else:
             noisy = g.noisy_logits
-        return out, g.score, g.top_vals, g.clean_logits, noisy, gates, plan.importance, plan.load, g.idx, plan.counts
+        return (out, g.score, g.top_vals, g.clean_logits, noisy, gates, plan.importance, plan.load, g.idx,
+                plan.counts, plan.cv_loss)
 
     @staticmethod
-    def backward(ctx, d_out, d_score, d_top, d_clean, d_noisy, d_gates, d_imp, _dl, _di, _dc):
+    def backward(ctx, d_out, d_score, d_top, d_clean, d_noisy, d_gates, d_imp, _dl, _di, _dc, d_cv):
         (x, gate_x, w_gate, task_feat, w1c, w2c, w1t, w2t, xq, hpre, yq, score, logits, idx_full, counts, offsets,
-         pos, tile_expert) = ctx.saved_tensors
+         pos, tile_expert, importance) = ctx.saved_tensors
         top_k, cap_rows, separate_gate_inp = ctx.cfg
         T, D = x.shape
         plan = ops.Plan(counts, offsets, pos, tile_expert, cap_rows, PAD_ROWS)
@@ -82,7 +85,8 @@ class MoEFunction(torch.autograd.Function):
             d_gates = None
         gx = x if gate_x is None else gate_x
         dz, dwg, dtf, dxg = ops.gate_bwd(gx, w_gate, logits, idx_full, top_k, task_feat, dscore, d_top, d_gates,
-                                         d_imp, d_clean, d_noisy, want_dx_gate=separate_gate_inp)
+                                         d_imp, d_clean, d_noisy, want_dx_gate=separate_gate_inp,
+                                         importance=importance, dcv_loss=d_cv)
         if separate_gate_inp:
             dx = ops.dispatch_bwd(dxq, plan, T, top_k, out_dtype=x.dtype)
             dgx = dxg.to(gate_x.dtype)
@@ -103,21 +107,22 @@ class GateFunction(torch.autograd.Function):
         E = w_gate.shape[1]
         g = ops.gate_fwd(gx, w_gate, top_k, task_feat, noise, noise_stddev, want_gates)
         plan = ops.route_plan(g.idx, E, PAD_ROWS, g.imp_partial, g.load_partial)
-        ctx.save_for_backward(gx, w_gate, task_feat, g.noisy_logits, g.idx_full)
+        ctx.save_for_backward(gx, w_gate, task_feat, g.noisy_logits, g.idx_full, plan.importance)
         ctx.top_k = top_k
         gates = g.gates if g.gates is not None else gx.new_empty(0)
         ctx.mark_non_differentiable(g.idx, plan.load, plan.counts, plan.offsets, plan.pos, plan.tile_expert)
         noisy = g.clean_logits.view_as(g.clean_logits) if noise is None else g.noisy_logits
-        return (g.score, g.top_vals, g.clean_logits, noisy, gates, plan.importance, plan.load, g.idx,
+        return (g.score, g.top_vals, g.clean_logits, noisy, gates, plan.importance, plan.cv_loss, plan.load, g.idx,
                 plan.counts, plan.offsets, plan.pos, plan.tile_expert)
 
     @staticmethod
-    def backward(ctx, d_score, d_top, d_clean, d_noisy, d_gates, d_imp, *_):
-        gx, w_gate, task_feat, logits, idx_full = ctx.saved_tensors
+    def backward(ctx, d_score, d_top, d_clean, d_noisy, d_gates, d_imp, d_cv, *_):
+        gx, w_gate, task_feat, logits, idx_full, importance = ctx.saved_tensors
         if d_gates is not None and d_gates.numel() == 0:
             d_gates = None
         dz, dwg, dtf, dxg = ops.gate_bwd(gx, w_gate, logits, idx_full, ctx.top_k, task_feat, d_score, d_top, d_gates,
-                                         d_imp, d_clean, d_noisy, want_dx_gate=True)
+                                         d_imp, d_clean, d_noisy, want_dx_gate=True, importance=importance,
+                                         dcv_loss=d_cv)
         if dtf is not None and task_feat is not None:
             dtf = dtf.view_as(task_feat).to(task_feat.dtype)
         return dxg.to(gx.dtype), dwg, dtf, None, None, None, None

@@ -145,11 +145,20 @@ class NoisyGate_VMoE(BaseGate):
             return torch.randn(T, self.tot_expert, device=device, dtype=torch.float32)
         return None
 
-    def _record(self, clean_logits, noisy_logits, importance, load, top_vals):
+    def _record(self, clean_logits, noisy_logits, importance, load, top_vals, cv_loss=None):
+        """origin:267-284: set self.loss (origin variant only) and remember the activation."""
         nstd = self.noise_stddev()
         if not self.return_summaries:
-            self.set_loss(balance_loss(importance, load, clean_logits, noisy_logits, nstd, top_vals, self.top_k,
-                                       self.tot_expert, self.training))
+            hard_load = not (self.top_k < self.tot_expert and abs(nstd) > 1e-6)
+            if not self.training:
+                self.set_loss(0)
+            elif hard_load and cv_loss is not None:
+                # noise-free path: cv^2(importance) + cv^2(hard load) comes fused out of the
+                # route-plan kernel (forward) and is chained inside the gate-backward kernel
+                self.set_loss(cv_loss)
+            else:
+                self.set_loss(balance_loss(importance, load, clean_logits, noisy_logits, nstd, top_vals, self.top_k,
+                                           self.tot_expert, self.training))
         self._last_logits = noisy_logits.detach()
 
     def get_activation(self, clear=True):
@@ -175,9 +184,9 @@ class NoisyGate_VMoE(BaseGate):
         inp2 = inp.reshape(-1, shape_input[-1])
         T = inp2.shape[0]
         noise = self.draw_noise(T, inp2.device)
-        (score, top_vals, clean, noisy, gates, importance, load, idx, *_plan) = GateFunction.apply(
+        (score, top_vals, clean, noisy, gates, importance, cv_loss, load, idx, *_plan) = GateFunction.apply(
             inp2, self.w_gate, None, noise, self.top_k, float(self.noise_stddev()), self.return_summaries)
-        self._record(clean, noisy, importance, load, top_vals)
+        self._record(clean, noisy, importance, load, top_vals, cv_loss)
         self.last_plan = _plan
         top_k_indices = idx.reshape(other_dim + [self.top_k])
         top_k_gates = score.reshape(other_dim + [self.top_k])

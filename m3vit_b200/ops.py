@@ -18,7 +18,7 @@ from ._lib import PAD_ROWS, check, dtype_code, load, ptr, require_device, stream
 
 # kernels launched by each C entry point (our own kernels; used for bench.py's `gpu_launches`)
 LAUNCHES = {"gate_fwd": 1, "gate_bwd": 3, "gate_bwd_dx": 1, "route_plan": 2, "dispatch_fwd": 1, "dispatch_bwd": 1,
-            "combine_fwd": 1, "combine_bwd": 1, "cast_weights": 1, "ffn_fwd": 2, "ffn_bwd_f32": 6, "ffn_bwd_bf16": 8}
+            "combine_fwd": 1, "combine_bwd": 1, "cast_weights": 1, "ffn_fwd": 2, "ffn_bwd_f32": 6, "ffn_bwd_bf16": 4}
 launch_count = 0
 
 
@@ -91,7 +91,7 @@ def gate_fwd(x, w_gate, top_k, task_feat=None, noise=None, noise_stddev=0.0, wan
 
 
 def gate_bwd(x, w_gate, logits, idx_full, top_k, task_feat=None, dscore=None, dtop_vals=None, dgates=None,
-             dimportance=None, dclean=None, dnoisy=None, want_dx_gate=False):
+             dimportance=None, dclean=None, dnoisy=None, want_dx_gate=False, importance=None, dcv_loss=None):
     """returns dz [T,E], dw_gate [Dg,E], dtask_feat [Dt] or None, dx_gate [T,D] or None"""
     require_device(x)
     lib = load()
@@ -105,6 +105,9 @@ def gate_bwd(x, w_gate, logits, idx_full, top_k, task_feat=None, dscore=None, dt
     def c(t):
         return None if t is None else t.contiguous().float()
     dscore, dtop_vals, dgates, dimportance, dclean, dnoisy = map(c, (dscore, dtop_vals, dgates, dimportance, dclean, dnoisy))
+    if dcv_loss is not None:
+        dcv_loss = dcv_loss.reshape(1).contiguous().float()
+        assert importance is not None
     dz = _f32((T, E), dev)
     dw = _f32((Dg, E), dev)
     dtf = _f32((Dt,), dev) if Dt > 0 else None
@@ -113,7 +116,8 @@ def gate_bwd(x, w_gate, logits, idx_full, top_k, task_feat=None, dscore=None, dt
     ws = _ws(nbytes, dev)
     check(lib.m3_gate_bwd(ptr(x), dtype_code(x), x.stride(0), ptr(task_feat), ptr(w_gate), ptr(logits), ptr(idx_full),
                           T, D, Dt, E, top_k, ptr(dscore), ptr(dtop_vals), ptr(dgates), ptr(dimportance), ptr(dclean),
-                          ptr(dnoisy), ptr(dz), ptr(dw), ptr(dtf), ptr(dxg), ptr(ws), ws.numel(), stream_ptr()),
+                          ptr(dnoisy), ptr(importance) if dcv_loss is not None else None, ptr(dcv_loss), ptr(dz),
+                          ptr(dw), ptr(dtf), ptr(dxg), ptr(ws), ws.numel(), stream_ptr()),
           "m3_gate_bwd")
     _count("gate_bwd")
     if want_dx_gate:
@@ -132,6 +136,7 @@ class Plan:
     pad: int
     importance: Optional[torch.Tensor] = None
     load: Optional[torch.Tensor] = None
+    cv_loss: Optional[torch.Tensor] = None      # 0-dim: cv^2(importance) + cv^2(load)
 
 
 def route_plan(idx, num_expert, pad=PAD_ROWS, imp_partial=None, load_partial=None) -> Plan:
@@ -144,17 +149,17 @@ def route_plan(idx, num_expert, pad=PAD_ROWS, imp_partial=None, load_partial=Non
     cap_rows = lib.m3_route_max_rows(T, K, E, pad)
     counts, offsets, pos = _i32(E, dev), _i32(E + 1, dev), _i32(T * K, dev)
     tile_expert = _i32(max(cap_rows // pad, 1), dev)
-    imp = load_v = None
+    imp = load_v = cv = None
     n_part = 0
     if imp_partial is not None:
         n_part = imp_partial.shape[0]
-        imp, load_v = _f32((E,), dev), _f32((E,), dev)
+        imp, load_v, cv = _f32((E,), dev), _f32((E,), dev), _f32((), dev)
     ws = _ws(lib.m3_route_plan_workspace_bytes(T, K, E), dev)
     check(lib.m3_route_plan(ptr(idx), T, K, E, pad, ptr(imp_partial), ptr(load_partial), n_part, ptr(counts),
-                            ptr(offsets), ptr(pos), ptr(tile_expert), ptr(imp), ptr(load_v), ptr(ws), ws.numel(),
-                            stream_ptr()), "m3_route_plan")
+                            ptr(offsets), ptr(pos), ptr(tile_expert), ptr(imp), ptr(load_v), ptr(cv), ptr(ws),
+                            ws.numel(), stream_ptr()), "m3_route_plan")
     _count("route_plan")
-    return Plan(counts, offsets, pos, tile_expert, cap_rows, pad, imp, load_v)
+    return Plan(counts, offsets, pos, tile_expert, cap_rows, pad, imp, load_v, cv)
 
 
 # --------------------------------------------------------------- dispatch/combine
