@@ -187,12 +187,14 @@ int m3_cast_weights_bf16(const float* w, int E, int R, int C, void* w_bf16, void
  *   dst_rank/dst_row for every local slot, and this rank's receive layout:
  *   recv_counts[E_loc], recv_offsets[E_loc+1] (padded), recv_tile_expert[].
  * Receive queue of local expert le: sources in rank order, each source's rows in
- * that source's slot order.
+ * that source's slot order.  cap_rows = capacity of every rank's receive queue: slots
+ * whose destination row would not fit are dropped (dst_row = -1) and *overflow_flag is
+ * set to 1 (the host checks it lazily; size queues with capacity_factor, see ep.py).
  */
 int m3_ep_plan(const int64_t* idx, const int32_t* pos_local, const int32_t* cnt_all, int rank, int W,
-               int E_loc, int T, int K, int pad, int32_t* dst_rank, int32_t* dst_row,
+               int E_loc, int T, int K, int pad, int cap_rows, int32_t* dst_rank, int32_t* dst_row,
                int32_t* recv_counts, int32_t* recv_offsets, int32_t* recv_tile_expert,
-               m3_stream_t stream);
+               int32_t* overflow_flag, m3_stream_t stream);
 int m3_ep_dispatch_fwd(const void* x, int x_dtype, const int32_t* dst_rank, const int32_t* dst_row,
                        int T, int K, int D, void* const* peer_xq, int xq_dtype, m3_stream_t stream);
 int m3_ep_combine_fwd(void* const* peer_yq, int yq_dtype, const int32_t* dst_rank,

@@ -125,9 +125,9 @@ __global__ void cast_weights_kernel(const float* __restrict__ w, int R, int C, _
 
 __global__ void ep_plan_kernel(const int64_t* __restrict__ idx, const int32_t* __restrict__ pos_local,
                                const int32_t* __restrict__ cnt_all, int rank, int W, int E_loc, int R, int pad,
-                               int32_t* __restrict__ dst_rank, int32_t* __restrict__ dst_row,
+                               int cap_rows, int32_t* __restrict__ dst_rank, int32_t* __restrict__ dst_row,
                                int32_t* __restrict__ recv_counts, int32_t* __restrict__ recv_offsets,
-                               int32_t* __restrict__ recv_tile_expert) {
+                               int32_t* __restrict__ recv_tile_expert, int32_t* __restrict__ overflow_flag) {
   extern __shared__ int sm[];
   const int E_tot = W * E_loc;
   int* loc_off = sm;            // [E_tot] exclusive prefix of this rank's counts (pad 1)
@@ -163,16 +163,29 @@ __global__ void ep_plan_kernel(const int64_t* __restrict__ idx, const int32_t* _
     const int64_t ge = idx[s];
     const int p = pos_local[s];
     if (ge < 0 || ge >= E_tot || p < 0) { dst_rank[s] = 0; dst_row[s] = -1; continue; }
+    const int row = base[ge] + (p - loc_off[ge]);
     dst_rank[s] = (int)(ge / E_loc);
-    dst_row[s] = base[ge] + (p - loc_off[ge]);
+    if (row >= cap_rows) {           // receive queue too small: drop the slot, tell the host
+      dst_row[s] = -1;
+      if (overflow_flag != nullptr) *overflow_flag = 1;
+    } else {
+      dst_row[s] = row;
+    }
   }
   if (blockIdx.x == 0) {
     // tile map of my receive queue
     int roff = 0;
     for (int le = 0; le < E_loc; ++le) {
       const int n = (tot[rank * E_loc + le] + pad - 1) / pad;
-      for (int i = threadIdx.x; i < n; i += blockDim.x) recv_tile_expert[roff / pad + i] = le;
+      for (int i = threadIdx.x; i < n; i += blockDim.x)
+        if (roff + (i + 1) * pad <= cap_rows) recv_tile_expert[roff / pad + i] = le;
       roff += n * pad;
+    }
+    // if the padded total exceeds the capacity, clamp what the GEMM sees to whole tiles that fit
+    if (threadIdx.x == 0 && roff > cap_rows) {
+      if (overflow_flag != nullptr) *overflow_flag = 1;
+      for (int le = 0; le <= E_loc; ++le)
+        if (recv_offsets[le] > cap_rows) recv_offsets[le] = cap_rows / pad * pad;
     }
   }
 }
@@ -189,19 +202,19 @@ extern "C" int m3_cast_weights_bf16(const float* w, int E, int R, int C, void* w
 }
 
 extern "C" int m3_ep_plan(const int64_t* idx, const int32_t* pos_local, const int32_t* cnt_all, int rank, int W,
-                          int E_loc, int T, int K, int pad, int32_t* dst_rank, int32_t* dst_row,
+                          int E_loc, int T, int K, int pad, int cap_rows, int32_t* dst_rank, int32_t* dst_row,
                           int32_t* recv_counts, int32_t* recv_offsets, int32_t* recv_tile_expert,
-                          m3_stream_t stream) {
+                          int32_t* overflow_flag, m3_stream_t stream) {
   M3_CHECK_ARG(idx && pos_local && cnt_all && dst_rank && dst_row && recv_counts && recv_offsets && recv_tile_expert);
-  M3_CHECK_ARG(W >= 1 && rank >= 0 && rank < W && E_loc >= 1 && T >= 0 && K >= 1 && pad >= 1);
+  M3_CHECK_ARG(W >= 1 && rank >= 0 && rank < W && E_loc >= 1 && T >= 0 && K >= 1 && pad >= 1 && cap_rows >= 0);
   M3_CHECK_SHAPE(W * E_loc <= 1024);
   const int R = T * K;
   int grid = m3_ceil_div(R, 256);
   if (grid < 1) grid = 1;
   if (grid > 2 * m3::kNumSMs) grid = 2 * m3::kNumSMs;
   m3::ep_plan_kernel<<<grid, 256, 3 * W * E_loc * sizeof(int), static_cast<cudaStream_t>(stream)>>>(
-      idx, pos_local, cnt_all, rank, W, E_loc, R, pad, dst_rank, dst_row, recv_counts, recv_offsets,
-      recv_tile_expert);
+      idx, pos_local, cnt_all, rank, W, E_loc, R, pad, cap_rows, dst_rank, dst_row, recv_counts, recv_offsets,
+      recv_tile_expert, overflow_flag);
   M3_LAUNCH_CHECK();
   return M3_OK;
 }

@@ -1,0 +1,412 @@
+"""Expert-parallel (EP) execution of the MoE layer over the GPUs of one NVLink box.
+
+Sharding is the reference's (utils/common_config.py:179-185, utils/moe_utils.py:191-198):
+tokens stay data-parallel, the router is replicated over all E_tot = W * E_loc experts,
+rank r owns global experts [r*E_loc, (r+1)*E_loc).  What changes is the exchange.
+FastMoE's global_scatter / global_gather (grouped ncclSend/ncclRecv sized by HOST
+counts, i.e. one D2H sync per layer, reached from MOEScatter/MOEGather when
+world_size > 1) is replaced by peer-mapped expert queues:
+
+  * every rank owns one CUDA-IPC "arena"; all ranks sub-allocate it in lockstep, so a
+    queue lives at the same offset on every rank and `base[p] + offset` is rank p's queue;
+  * forward : all-gather of the [E_tot] count vector (tiny, NCCL, stream-ordered, NO host
+    read-back) -> m3_ep_plan (every slot's owner rank + row) -> the dispatch kernel STORES
+    token rows straight into the owners' queues over NVLink -> barrier -> grouped expert FFN
+    on the local queue -> barrier -> the combine kernel LOADS result rows from the owners;
+  * backward: the same movers mirrored (combine_bwd pushes dyq, dispatch_bwd pulls dxq).
+    Expert weight gradients need no reduction (each expert's rows are all on its owner).
+
+The protocol is written as explicit phases so that it runs either over torch.distributed
+(one process per GPU, NCCL) or as a single-process multi-rank simulation (tests; one GPU
+holds every rank's arena, the "peers" are just other device pointers).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import List, Optional
+
+import torch
+
+from . import ops
+from ._lib import PAD_ROWS, check, dtype_code, load, ptr, stream_ptr
+
+
+# ----------------------------------------------------------------------------- arena
+class _CAI:
+    def __init__(self, p, nbytes):
+        self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (p, False), "version": 2}
+
+
+class Arena:
+    """A cudaMalloc'ed, IPC-exportable slab with a deterministic size-class allocator.
+    Every rank performs the same alloc/free sequence, hence gets the same offsets."""
+
+    ALIGN = 1024
+
+    def __init__(self, nbytes: int, device: torch.device):
+        self.nbytes = int(nbytes)
+        self.device = device
+        p = C.c_void_p()
+        self.handle = (C.c_ubyte * 64)()
+        with torch.cuda.device(device):
+            check(load().m3_ipc_alloc(self.nbytes, C.byref(p), self.handle), "m3_ipc_alloc")
+        self.base = p.value
+        self._bytes = torch.as_tensor(_CAI(self.base, self.nbytes), device=device)
+        self._top = 0
+        self._free = {}       # size -> [offsets]
+
+    def alloc(self, nbytes: int) -> int:
+        n = (int(nbytes) + self.ALIGN - 1) // self.ALIGN * self.ALIGN
+        lst = self._free.get(n)
+        if lst:
+            return lst.pop()
+        off = self._top
+        if off + n > self.nbytes:
+            raise MemoryError(f"EP arena exhausted ({self.nbytes} B): raise arena_bytes or lower capacity_factor")
+        self._top = off + n
+        return off
+
+    def free(self, off: int, nbytes: int) -> None:
+        n = (int(nbytes) + self.ALIGN - 1) // self.ALIGN * self.ALIGN
+        self._free.setdefault(n, []).append(off)
+
+    def view(self, off: int, rows: int, cols: int, dtype: torch.dtype) -> torch.Tensor:
+        nb = rows * cols * torch.empty((), dtype=dtype).element_size()
+        return self._bytes[off:off + nb].view(dtype).view(rows, cols)
+
+    def handle_bytes(self) -> bytes:
+        return bytes(self.handle)
+
+    def close(self):
+        if self.base:
+            self._bytes = None
+            load().m3_ipc_free(C.c_void_p(self.base))
+            self.base = 0
+
+
+# ----------------------------------------------------------------------------- groups
+class TorchDistGroup:
+    """torch.distributed (NCCL on GPUs; gloo in the CPU tests of the count exchange)."""
+
+    def __init__(self, group=None):
+        import torch.distributed as dist
+        self.dist = dist
+        self.group = group
+        self.rank = dist.get_rank(group)
+        self.world = dist.get_world_size(group)
+        self._flag = None
+
+    def all_gather_counts(self, counts: torch.Tensor) -> torch.Tensor:
+        out = torch.empty(self.world * counts.numel(), dtype=counts.dtype, device=counts.device)
+        self.dist.all_gather_into_tensor(out, counts.contiguous().view(-1), group=self.group)
+        return out.view(self.world, counts.numel())
+
+    def barrier(self, device) -> None:
+        """Stream-ordered rendezvous: a 1-element all-reduce.  No host synchronisation."""
+        if self._flag is None or self._flag.device != device:
+            self._flag = torch.zeros(1, dtype=torch.int32, device=device)
+        self.dist.all_reduce(self._flag, group=self.group)
+
+    def exchange_bytes(self, payload: bytes) -> List[bytes]:
+        out = [None] * self.world
+        self.dist.all_gather_object(out, payload, group=self.group)
+        return out
+
+
+@dataclass
+class EPContext:
+    """Per-rank EP state: arena + peer-mapped bases of every rank's arena."""
+    rank: int
+    world: int
+    group: object
+    arena: Arena
+    bases: torch.Tensor                 # [W] int64 device tensor: arena base pointer of every rank
+    capacity_factor: Optional[float]    # receive-queue rows = factor * T*K (None: worst case W)
+    overflow: torch.Tensor              # [1] int32 device flag set by m3_ep_plan
+
+    def peer_ptrs(self, off: int) -> torch.Tensor:
+        return self.bases + off
+
+    def cap_rows(self, T: int, K: int, E_loc: int) -> int:
+        f = float(self.world) if self.capacity_factor is None else min(float(self.world), self.capacity_factor)
+        rows = int(f * T * K) + E_loc * (PAD_ROWS - 1)
+        return (rows + PAD_ROWS - 1) // PAD_ROWS * PAD_ROWS
+
+    def check_overflow(self) -> None:
+        """Host-synchronising check (call outside the hot loop)."""
+        if int(self.overflow.item()) != 0:
+            raise RuntimeError("EP receive queue overflow: tokens were dropped; raise capacity_factor")
+
+
+def make_context(group, device, arena_bytes: int, capacity_factor: Optional[float] = 2.0) -> EPContext:
+    """Collective: allocates the arena, exchanges IPC handles, maps the peers."""
+    arena = Arena(arena_bytes, device)
+    handles = group.exchange_bytes(arena.handle_bytes())
+    bases = []
+    lib = load()
+    with torch.cuda.device(device):
+        for r, h in enumerate(handles):
+            if r == group.rank:
+                bases.append(arena.base)
+            else:
+                p = C.c_void_p()
+                buf = (C.c_ubyte * 64).from_buffer_copy(h)
+                check(lib.m3_ipc_open(buf, C.byref(p)), "m3_ipc_open")
+                bases.append(p.value)
+    bases_t = torch.tensor(bases, dtype=torch.int64, device=device)
+    return EPContext(group.rank, group.world, group, arena, bases_t, capacity_factor,
+                     torch.zeros(1, dtype=torch.int32, device=device))
+
+
+# ----------------------------------------------------------------------------- phases
+@dataclass
+class EPFwdState:
+    g: ops.GateOut
+    plan_local: ops.Plan
+    dst_rank: Optional[torch.Tensor] = None
+    dst_row: Optional[torch.Tensor] = None
+    recv: Optional[ops.Plan] = None
+    cap: int = 0
+    off_xq: int = -1
+    off_yq: int = -1
+    xq: Optional[torch.Tensor] = None
+    yq: Optional[torch.Tensor] = None
+    hpre: Optional[torch.Tensor] = None
+    nbytes_q: int = 0
+
+
+def phase_a_gate(gx, w_gate, top_k, task_feat, noise, noise_stddev, want_gates, E_tot) -> EPFwdState:
+    """local: router over all E_tot experts + local stable plan (pad 1) -> this rank's count vector"""
+    g = ops.gate_fwd(gx, w_gate, top_k, task_feat, noise, noise_stddev, want_gates)
+    plan_local = ops.route_plan(g.idx, E_tot, 1, g.imp_partial, g.load_partial)
+    return EPFwdState(g, plan_local)
+
+
+def phase_b_dispatch(ctx: EPContext, st: EPFwdState, x, cnt_all, E_loc, top_k, cdt) -> None:
+    """m3_ep_plan, then PUSH token rows into the owners' queues (NVLink stores)."""
+    lib = load()
+    T, D = x.shape
+    dev = x.device
+    W = ctx.world
+    st.cap = ctx.cap_rows(T, top_k, E_loc)
+    R = T * top_k
+    st.dst_rank = torch.empty(R, dtype=torch.int32, device=dev)
+    st.dst_row = torch.empty(R, dtype=torch.int32, device=dev)
+    rc = torch.empty(E_loc, dtype=torch.int32, device=dev)
+    ro = torch.empty(E_loc + 1, dtype=torch.int32, device=dev)
+    rt = torch.empty(st.cap // PAD_ROWS, dtype=torch.int32, device=dev)
+    check(lib.m3_ep_plan(ptr(st.g.idx), ptr(st.plan_local.pos), ptr(cnt_all), ctx.rank, W, E_loc, T, top_k, PAD_ROWS,
+                         st.cap, ptr(st.dst_rank), ptr(st.dst_row), ptr(rc), ptr(ro), ptr(rt), ptr(ctx.overflow),
+                         stream_ptr()), "m3_ep_plan")
+    st.recv = ops.Plan(rc, ro, None, rt, st.cap, PAD_ROWS)
+    el = 2 if cdt == torch.bfloat16 else 4
+    st.nbytes_q = st.cap * D * el
+    st.off_xq = ctx.arena.alloc(st.nbytes_q)
+    st.xq = ctx.arena.view(st.off_xq, st.cap, D, cdt)
+    peers = ctx.peer_ptrs(st.off_xq)
+    check(lib.m3_ep_dispatch_fwd(ptr(x), dtype_code(x), ptr(st.dst_rank), ptr(st.dst_row), T, top_k, D, ptr(peers),
+                                 dtype_code(st.xq), stream_ptr()), "m3_ep_dispatch_fwd")
+    check(lib.m3_zero_pad_rows(ptr(st.xq), dtype_code(st.xq), ptr(rc), ptr(ro), E_loc, D, stream_ptr()),
+          "m3_zero_pad_rows")
+    ops.launch_count += 3
+
+
+def phase_c_ffn(ctx: EPContext, st: EPFwdState, w1c, b1, w2c, b2, save_hpre: bool) -> None:
+    """local: grouped expert FFN over this rank's receive queue -> yq (in the arena, peers read it)"""
+    lib = load()
+    cap, D = st.xq.shape
+    E_loc, H, _ = w1c.shape
+    dt = dtype_code(st.xq)
+    st.off_yq = ctx.arena.alloc(st.nbytes_q)
+    st.yq = ctx.arena.view(st.off_yq, cap, D, st.xq.dtype)
+    st.hpre = torch.empty(cap, H, dtype=st.xq.dtype, device=st.xq.device) if save_hpre else None
+    ws = torch.empty(max(lib.m3_ffn_workspace_bytes(dt, cap, D, H, E_loc, 0), 16), dtype=torch.uint8, device=st.xq.device)
+    check(lib.m3_ffn_fwd(dt, ptr(st.xq), ptr(st.recv.offsets), ptr(st.recv.tile_expert), cap, E_loc, D, H, ptr(w1c),
+                         ptr(b1), ptr(w2c), ptr(b2), ptr(st.hpre), ptr(st.yq), ptr(ws), ws.numel(), stream_ptr()),
+          "m3_ffn_fwd")
+    ops.launch_count += 2
+
+
+def phase_d_combine(ctx: EPContext, st: EPFwdState, T, D, top_k, out_dtype) -> torch.Tensor:
+    """PULL result rows from the owners' yq queues and combine with the gate scores."""
+    out = torch.empty(T, D, dtype=out_dtype, device=st.g.score.device)
+    peers = ctx.peer_ptrs(st.off_yq)
+    check(load().m3_ep_combine_fwd(ptr(peers), dtype_code(st.yq), ptr(st.dst_rank), ptr(st.dst_row), ptr(st.g.score),
+                                   T, top_k, D, ptr(out), dtype_code(out), stream_ptr()), "m3_ep_combine_fwd")
+    ops.launch_count += 1
+    return out
+
+
+@dataclass
+class EPBwdState:
+    off_dyq: int = -1
+    off_dxq: int = -1
+    dyq: Optional[torch.Tensor] = None
+    dxq: Optional[torch.Tensor] = None
+    dscore: Optional[torch.Tensor] = None
+    grads: Optional[tuple] = None
+
+
+def phase_e_combine_bwd(ctx: EPContext, st: EPFwdState, g_out, top_k) -> EPBwdState:
+    """dscore from the owners' yq rows (pull); dyq = score * g pushed into the owners' dyq queues."""
+    lib = load()
+    bs = EPBwdState()
+    T, D = g_out.shape
+    E_loc = st.recv.counts.numel()
+    bs.off_dyq = ctx.arena.alloc(st.nbytes_q)
+    bs.dyq = ctx.arena.view(bs.off_dyq, st.cap, D, st.xq.dtype)
+    bs.dscore = torch.empty(T, top_k, dtype=torch.float32, device=g_out.device)
+    py, pd = ctx.peer_ptrs(st.off_yq), ctx.peer_ptrs(bs.off_dyq)
+    check(lib.m3_ep_combine_bwd(ptr(g_out), dtype_code(g_out), ptr(py), ptr(pd), dtype_code(bs.dyq), ptr(st.dst_rank),
+                                ptr(st.dst_row), ptr(st.g.score), T, top_k, D, ptr(bs.dscore), stream_ptr()),
+          "m3_ep_combine_bwd")
+    check(lib.m3_zero_pad_rows(ptr(bs.dyq), dtype_code(bs.dyq), ptr(st.recv.counts), ptr(st.recv.offsets), E_loc, D,
+                               stream_ptr()), "m3_zero_pad_rows")
+    ops.launch_count += 2
+    return bs
+
+
+def phase_f_ffn_bwd(ctx: EPContext, st: EPFwdState, bs: EPBwdState, w1c, w2c, w1t, w2t) -> None:
+    lib = load()
+    cap, D = st.xq.shape
+    E_loc, H, _ = w1c.shape
+    dt = dtype_code(st.xq)
+    dev = st.xq.device
+    bs.off_dxq = ctx.arena.alloc(st.nbytes_q)
+    bs.dxq = ctx.arena.view(bs.off_dxq, cap, D, st.xq.dtype)
+    dw1 = torch.empty(E_loc, H, D, dtype=torch.float32, device=dev)
+    db1 = torch.empty(E_loc, H, dtype=torch.float32, device=dev)
+    dw2 = torch.empty(E_loc, D, H, dtype=torch.float32, device=dev)
+    db2 = torch.empty(E_loc, D, dtype=torch.float32, device=dev)
+    ws = torch.empty(max(lib.m3_ffn_workspace_bytes(dt, cap, D, H, E_loc, 1), 16), dtype=torch.uint8, device=dev)
+    check(lib.m3_ffn_bwd(dt, ptr(st.xq), ptr(st.hpre), ptr(bs.dyq), ptr(st.recv.counts), ptr(st.recv.offsets),
+                         ptr(st.recv.tile_expert), cap, E_loc, D, H, ptr(w1c), ptr(w2c), ptr(w1t), ptr(w2t),
+                         ptr(bs.dxq), ptr(dw1), ptr(db1), ptr(dw2), ptr(db2), ptr(ws), ws.numel(), stream_ptr()),
+          "m3_ffn_bwd")
+    ops.launch_count += 4 if dt == 1 else 6
+    bs.grads = (dw1, db1, dw2, db2)
+
+
+def phase_g_dispatch_bwd(ctx: EPContext, st: EPFwdState, bs: EPBwdState, T, D, top_k, dz, w_gate, out_dtype):
+    """PULL dxq rows from the owners and sum them per token (+ the router's dx)."""
+    dx = torch.empty(T, D, dtype=out_dtype, device=st.g.score.device)
+    peers = ctx.peer_ptrs(bs.off_dxq)
+    E = w_gate.shape[1] if dz is not None else 0
+    check(load().m3_ep_dispatch_bwd(ptr(peers), dtype_code(bs.dxq), ptr(st.dst_rank), ptr(st.dst_row), T, top_k, D,
+                                    ptr(dz), ptr(w_gate) if dz is not None else None, E, ptr(dx), dtype_code(dx),
+                                    stream_ptr()), "m3_ep_dispatch_bwd")
+    ops.launch_count += 1
+    return dx
+
+
+def release_fwd(ctx: EPContext, st: EPFwdState) -> None:
+    for off in (st.off_yq, st.off_xq):
+        if off >= 0:
+            ctx.arena.free(off, st.nbytes_q)
+    st.off_xq = st.off_yq = -1
+    st.xq = st.yq = None
+
+
+def release_bwd(ctx: EPContext, st: EPFwdState, bs: EPBwdState) -> None:
+    for off in (bs.off_dxq, bs.off_dyq):
+        if off >= 0:
+            ctx.arena.free(off, st.nbytes_q)
+    bs.off_dxq = bs.off_dyq = -1
+    bs.dxq = bs.dyq = None
+
+
+# ----------------------------------------------------------------------------- autograd over torch.distributed
+class EPMoEFunction(torch.autograd.Function):
+    """Same contract as functions.MoEFunction, experts sharded over `ctx_ep.world` ranks.
+    w1/b1/w2/b2 are this rank's LOCAL experts [E_loc, ...]; w_gate is [Dg, W*E_loc]."""
+
+    @staticmethod
+    def forward(ctx, x, gate_x, w_gate, task_feat, w1, b1, w2, b2, noise, top_k, noise_stddev, compute_dtype,
+                want_gates, wcache, ep: EPContext):
+        T, D = x.shape
+        E_loc = w1.shape[0]
+        E_tot = w_gate.shape[1]
+        assert E_tot == E_loc * ep.world, "w_gate must have world_size * num_expert columns"
+        x = x.contiguous()
+        gx = x if gate_x is None else gate_x.contiguous()
+        grp = ep.group
+        st = phase_a_gate(gx, w_gate, top_k, task_feat, noise, noise_stddev, want_gates, E_tot)
+        cnt_all = grp.all_gather_counts(st.plan_local.counts)         # also: "all queues are free" rendezvous
+        phase_b_dispatch(ep, st, x, cnt_all, E_loc, top_k, compute_dtype)
+        if compute_dtype == torch.bfloat16:
+            w1c, w2c, w1t, w2t = wcache.get_bf16(w1, w2)
+        else:
+            w1c, w2c, w1t, w2t = w1, w2, None, None
+        needs_grad = any(ctx.needs_input_grad)
+        grp.barrier(x.device)                                         # every push has landed
+        phase_c_ffn(ep, st, w1c, b1, w2c, b2, needs_grad)
+        grp.barrier(x.device)                                         # every owner's yq is complete
+        out = phase_d_combine(ep, st, T, D, top_k, x.dtype)
+        g, pl = st.g, st.plan_local
+        if needs_grad:
+            ctx.st, ctx.ep = st, ep
+            ctx.save_for_backward(x, gate_x, w_gate, task_feat, w1c, w2c, w1t, w2t, pl.importance)
+            ctx.cfg = (top_k, gate_x is not None)
+        else:
+            grp.barrier(x.device)                                     # peers are done reading my yq
+            release_fwd(ep, st)
+        gates = g.gates if g.gates is not None else x.new_empty(0)
+        ctx.mark_non_differentiable(g.idx, pl.load, pl.counts)
+        noisy = g.clean_logits.view_as(g.clean_logits) if noise is None else g.noisy_logits
+        return out, g.score, g.top_vals, g.clean_logits, noisy, gates, pl.importance, pl.load, g.idx, pl.counts, pl.cv_loss
+
+    @staticmethod
+    def backward(ctx, d_out, d_score, d_top, d_clean, d_noisy, d_gates, d_imp, _dl, _di, _dc, d_cv):
+        x, gate_x, w_gate, task_feat, w1c, w2c, w1t, w2t, importance = ctx.saved_tensors
+        st, ep = ctx.st, ctx.ep
+        top_k, separate = ctx.cfg
+        T, D = x.shape
+        grp = ep.group
+        if d_out is None:
+            d_out = torch.zeros_like(x)
+        grp.barrier(x.device)                                         # previous backward's pulls are finished
+        bs = phase_e_combine_bwd(ep, st, d_out.contiguous(), top_k)
+        grp.barrier(x.device)
+        phase_f_ffn_bwd(ep, st, bs, w1c, w2c, w1t, w2t)
+        dscore = bs.dscore if d_score is None else bs.dscore + d_score
+        if d_gates is not None and d_gates.numel() == 0:
+            d_gates = None
+        gx = x if gate_x is None else gate_x
+        dz, dwg, dtf, dxg = ops.gate_bwd(gx, w_gate, st.g.noisy_logits, st.g.idx_full, top_k, task_feat, dscore, d_top,
+                                         d_gates, d_imp, d_clean, d_noisy, want_dx_gate=separate,
+                                         importance=importance, dcv_loss=d_cv)
+        grp.barrier(x.device)                                         # every owner's dxq is complete
+        if separate:
+            dx = phase_g_dispatch_bwd(ep, st, bs, T, D, top_k, None, w_gate, x.dtype)
+            dgx = dxg.to(gate_x.dtype)
+        else:
+            dx = phase_g_dispatch_bwd(ep, st, bs, T, D, top_k, dz, w_gate, x.dtype)
+            dgx = None
+        dw1, db1, dw2, db2 = bs.grads
+        grp.barrier(x.device)                                         # peers are done pulling my dxq / yq
+        release_bwd(ep, st, bs)
+        release_fwd(ep, st)
+        ctx.st = None
+        if dtf is not None and task_feat is not None:
+            dtf = dtf.view_as(task_feat).to(task_feat.dtype)
+        return dx, dgx, dwg, dtf, dw1, db1, dw2, db2, None, None, None, None, None, None, None
+
+
+class _EPRunner:
+    def __init__(self, ep: EPContext):
+        self.ep = ep
+
+    def forward(self, layer, gate, x, gx, tf, noise, nstd, cdt):
+        return EPMoEFunction.apply(
+            x, gx, gate.w_gate, tf, layer.experts.htoh4.weight, layer.experts.htoh4.bias,
+            layer.experts.h4toh.weight, layer.experts.h4toh.bias, noise, layer.top_k, nstd, cdt,
+            layer.RETURN_SUMMARIES, layer._wcache, self.ep)
+
+
+def attach(layer, ep: EPContext) -> None:
+    """Enable expert parallelism on an FMoETransformerMLP built with world_size = ep.world
+    (num_expert = experts per rank, as the reference's get_backbone does)."""
+    if layer.world_size != ep.world:
+        raise ValueError(f"layer.world_size={layer.world_size} but the EP group has {ep.world} ranks")
+    layer._ep = _EPRunner(ep)

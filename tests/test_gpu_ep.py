@@ -1,0 +1,152 @@
+"""GPU: expert-parallel path.  One GPU holds every simulated rank's arena ("peer" pointers are
+just other device pointers), the phases of m3vit_b200.ep run in lockstep, and the result must
+equal the single-GPU layer on the same global batch (the replicated layer is the
+parity target for EP).  The m3_ep_plan kernel is compared bit-exactly with oracle/ep_oracle.py."""
+import pytest
+import torch
+
+from oracle import ep_oracle
+
+pytestmark = pytest.mark.gpu
+
+
+class SimGroup:
+    def __init__(self, rank, world):
+        self.rank, self.world = rank, world
+
+    def barrier(self, device):
+        pass
+
+
+def make_sim(W, dev, arena_bytes, capacity_factor=None):
+    from m3vit_b200 import ep
+    arenas = [ep.Arena(arena_bytes, dev) for _ in range(W)]
+    bases = torch.tensor([a.base for a in arenas], dtype=torch.int64, device=dev)
+    return [ep.EPContext(r, W, SimGroup(r, W), arenas[r], bases, capacity_factor,
+                         torch.zeros(1, dtype=torch.int32, device=dev)) for r in range(W)]
+
+
+@pytest.mark.parametrize("W,E_loc,K", [(2, 8, 4), (4, 4, 2), (8, 2, 4)])
+def test_ep_plan_kernel_bit_exact(W, E_loc, K):
+    from m3vit_b200 import ops, _lib
+    dev = torch.device("cuda:0")
+    E_tot = W * E_loc
+    Ts = [300 + 11 * r for r in range(W)]
+    gen = torch.Generator().manual_seed(W)
+    idxs = [torch.stack([torch.randperm(E_tot, generator=gen)[:K] for _ in range(T)]) for T in Ts]
+    cnt_all = torch.stack([torch.bincount(i.reshape(-1), minlength=E_tot) for i in idxs]).int()
+    lib = _lib.load()
+    for r in range(W):
+        dr, drow, rc, ro = ep_oracle.ep_plan(idxs[r], cnt_all, r, W, E_loc, 128)
+        idx = idxs[r].to(dev)
+        pl = ops.route_plan(idx, E_tot, 1)
+        R = Ts[r] * K
+        cap = int(ro[-1]) + 256
+        o = dict(dst_rank=torch.empty(R, dtype=torch.int32, device=dev), dst_row=torch.empty(R, dtype=torch.int32, device=dev),
+                 rc=torch.empty(E_loc, dtype=torch.int32, device=dev), ro=torch.empty(E_loc + 1, dtype=torch.int32, device=dev),
+                 rt=torch.full((cap // 128,), -7, dtype=torch.int32, device=dev), fl=torch.zeros(1, dtype=torch.int32, device=dev))
+        _lib.check(lib.m3_ep_plan(idx.data_ptr(), pl.pos.data_ptr(), cnt_all.to(dev).data_ptr(), r, W, E_loc, Ts[r], K,
+                                  128, cap, o["dst_rank"].data_ptr(), o["dst_row"].data_ptr(), o["rc"].data_ptr(),
+                                  o["ro"].data_ptr(), o["rt"].data_ptr(), o["fl"].data_ptr(),
+                                  torch.cuda.current_stream().cuda_stream), "m3_ep_plan")
+        assert torch.equal(o["dst_rank"].cpu(), dr) and torch.equal(o["dst_row"].cpu(), drow)
+        assert torch.equal(o["rc"].cpu(), rc) and torch.equal(o["ro"].cpu(), ro)
+        assert int(o["fl"]) == 0
+        te = o["rt"].cpu()[: int(ro[-1]) // 128]
+        for i, e in enumerate(te.tolist()):
+            assert int(ro[e]) <= i * 128 < int(ro[e + 1])
+
+
+@pytest.mark.parametrize("W", [2, 4])
+@pytest.mark.parametrize("cdt", [torch.float32, torch.bfloat16])
+def test_ep_simulation_matches_single_gpu(W, cdt):
+    from m3vit_b200 import ep, ops, functions as F_
+    dev = torch.device("cuda:0")
+    E_tot, K, D, H, T = 16, 4, 128, 256, 333
+    E_loc = E_tot // W
+    gen = torch.Generator().manual_seed(5)
+    xs = [torch.randn(T, D, generator=gen).to(dev) for _ in range(W)]
+    gos = [torch.randn(T, D, generator=gen).to(dev) for _ in range(W)]
+    wg = ((torch.rand(D, E_tot, generator=gen) * 2 - 1) * 0.25).to(dev)
+    w1 = ((torch.rand(E_tot, H, D, generator=gen) * 2 - 1) / D ** 0.5).to(dev)
+    w2 = ((torch.rand(E_tot, D, H, generator=gen) * 2 - 1) / H ** 0.5).to(dev)
+    b1 = ((torch.rand(E_tot, H, generator=gen) * 2 - 1) * 0.1).to(dev)
+    b2 = ((torch.rand(E_tot, D, generator=gen) * 2 - 1) * 0.1).to(dev)
+
+    # ---- single GPU reference (all experts local), one call per "rank" batch
+    ref = []
+    for r in range(W):
+        x = xs[r].clone().requires_grad_(True)
+        ps = [t.clone().requires_grad_(True) for t in (wg, w1, b1, w2, b2)]
+        res = F_.MoEFunction.apply(x, None, ps[0], None, ps[1], ps[2], ps[3], ps[4], None, K, 0.0, cdt, False,
+                                   F_.WeightCache())
+        res[0].backward(gos[r])
+        ref.append(dict(out=res[0].detach(), dx=x.grad, dwg=ps[0].grad, dw1=ps[1].grad, db1=ps[2].grad,
+                        dw2=ps[3].grad, db2=ps[4].grad, counts=res[9]))
+
+    # ---- EP simulation in lockstep
+    ctxs = make_sim(W, dev, 64 << 20)
+    sl = lambda t, r: t[r * E_loc:(r + 1) * E_loc].contiguous()
+    if cdt == torch.bfloat16:
+        wl = []
+        for r in range(W):
+            a, at = ops.cast_weights_bf16(sl(w1, r), True, True)
+            b, bt = ops.cast_weights_bf16(sl(w2, r), True, True)
+            wl.append((a, b, at, bt))
+    else:
+        wl = [(sl(w1, r), sl(w2, r), None, None) for r in range(W)]
+    sts = [ep.phase_a_gate(xs[r], wg, K, None, None, 0.0, False, E_tot) for r in range(W)]
+    cnt_all = torch.stack([s.plan_local.counts for s in sts])
+    for r in range(W):
+        assert torch.equal(sts[r].plan_local.counts, ref[r]["counts"])
+        ep.phase_b_dispatch(ctxs[r], sts[r], xs[r], cnt_all, E_loc, K, cdt)
+    for r in range(W):
+        ep.phase_c_ffn(ctxs[r], sts[r], wl[r][0], sl(b1, r), wl[r][1], sl(b2, r), True)
+    outs = [ep.phase_d_combine(ctxs[r], sts[r], T, D, K, torch.float32) for r in range(W)]
+    for c in ctxs:
+        c.check_overflow()
+    tol = dict(rtol=0, atol=0) if cdt == torch.float32 else dict(rtol=0, atol=0)
+    for r in range(W):
+        # per-row arithmetic is identical (row-independent FFN, same k order): bit-exact
+        torch.testing.assert_close(outs[r], ref[r]["out"], **tol)
+    bss = [ep.phase_e_combine_bwd(ctxs[r], sts[r], gos[r], K) for r in range(W)]
+    for r in range(W):
+        ep.phase_f_ffn_bwd(ctxs[r], sts[r], bss[r], *wl[r])
+    g_tol = 1e-5 if cdt == torch.float32 else 2e-2
+    sum_ref = {k: sum(ref[r][k] for r in range(W)) for k in ("dw1", "db1", "dw2", "db2")}
+    for r in range(W):
+        dz, dwg, _, _ = ops.gate_bwd(xs[r], wg, sts[r].g.noisy_logits, sts[r].g.idx_full, K, dscore=bss[r].dscore)
+        dx = ep.phase_g_dispatch_bwd(ctxs[r], sts[r], bss[r], T, D, K, dz, wg, torch.float32)
+        torch.testing.assert_close(dx, ref[r]["dx"], rtol=0, atol=0)
+        torch.testing.assert_close(dwg, ref[r]["dwg"], rtol=1e-5, atol=1e-6)
+        dw1, db1, dw2, db2 = bss[r].grads
+        # an expert's gradient on its owner already sums the rows of every source rank
+        for name, got in (("dw1", dw1), ("db1", db1), ("dw2", dw2), ("db2", db2)):
+            want = sl(sum_ref[name], r)
+            err = float((got - want).abs().max() / want.abs().max().clamp_min(1e-12))
+            assert err <= g_tol, (name, err)
+    for r in range(W):
+        ep.release_bwd(ctxs[r], sts[r], bss[r])
+        ep.release_fwd(ctxs[r], sts[r])
+        assert ctxs[r].arena._top == ctxs[0].arena._top
+    for c in ctxs:
+        c.arena.close()
+
+
+def test_ep_capacity_overflow_is_reported():
+    from m3vit_b200 import ep
+    dev = torch.device("cuda:0")
+    W, E_tot, K, D, T = 2, 16, 4, 128, 400
+    ctxs = make_sim(W, dev, 32 << 20, capacity_factor=0.5)      # queues deliberately too small
+    gen = torch.Generator().manual_seed(1)
+    wg = ((torch.rand(D, E_tot, generator=gen) * 2 - 1) * 0.25).to(dev)
+    xs = [torch.randn(T, D, generator=gen).to(dev) for _ in range(W)]
+    sts = [ep.phase_a_gate(xs[r], wg, K, None, None, 0.0, False, E_tot) for r in range(W)]
+    cnt_all = torch.stack([s.plan_local.counts for s in sts])
+    for r in range(W):
+        ep.phase_b_dispatch(ctxs[r], sts[r], xs[r], cnt_all, E_tot // W, K, torch.float32)
+    with pytest.raises(RuntimeError, match="overflow"):
+        for c in ctxs:
+            c.check_overflow()
+    for c in ctxs:
+        c.arena.close()
