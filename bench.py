@@ -128,22 +128,29 @@ def cpu_reference(steps, warmup, batch=2, threads=None):
 
 
 # ----------------------------------------------------------------------------- our arm
-def build_layers(dev, compute_dtype):
+def build_layers(dev, compute_dtype, rank=0, world=1, ep_ctx=None):
+    """6 MoE layers.  world > 1: expert parallel exactly like the reference's get_backbone
+    (utils/common_config.py:179-185): moe_experts //= world, rank r owns experts [r*E_loc, (r+1)*E_loc)."""
     import m3vit_b200 as M
     from m3vit_b200.synthetic import MoECase, make_weights
+    e_loc = N_EXP // world
     layers = []
     for li in range(N_LAYER):
         case = MoECase("C2", batch=1, tokens=N_TOK, d_model=D_MODEL, d_hidden=D_HID, num_expert=N_EXP, top_k=TOP_K,
                        num_gates=N_TASK)
-        w = make_weights(case, li)
-        layer = M.build_moe_mlp(D_MODEL, moe_mlp_ratio=D_HID / D_MODEL, moe_experts=N_EXP, moe_top_k=TOP_K,
+        w = make_weights(case, li)                     # same seed on every rank: replicated router
+        layer = M.build_moe_mlp(D_MODEL, moe_mlp_ratio=D_HID / D_MODEL, moe_experts=e_loc, moe_top_k=TOP_K,
                                 moe_gate_dim=D_MODEL + N_TASK, moe_gate_type="noisy_vmoe", vmoe_noisy_std=0,
-                                multi_gate=True, compute_dtype=compute_dtype).to(dev)
+                                multi_gate=True, world_size=world, compute_dtype=compute_dtype).to(dev)
+        sl = slice(rank * e_loc, (rank + 1) * e_loc)
         with torch.no_grad():
-            layer.experts.htoh4.weight.copy_(w["w1"]); layer.experts.htoh4.bias.copy_(w["b1"])
-            layer.experts.h4toh.weight.copy_(w["w2"]); layer.experts.h4toh.bias.copy_(w["b2"])
+            layer.experts.htoh4.weight.copy_(w["w1"][sl]); layer.experts.htoh4.bias.copy_(w["b1"][sl])
+            layer.experts.h4toh.weight.copy_(w["w2"][sl]); layer.experts.h4toh.bias.copy_(w["b2"][sl])
             for g, wg in zip(layer.gate, w["w_gate"]):
                 g.w_gate.copy_(wg)
+        if ep_ctx is not None:
+            from m3vit_b200 import ep
+            ep.attach(layer, ep_ctx)
         layer.train()
         layers.append(layer)
     return layers
@@ -173,6 +180,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--capacity-factor", type=float, default=2.0,
+                    help="EP receive-queue rows as a multiple of the local T*K (overflow is detected and raised)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -205,9 +214,18 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     from m3vit_b200 import ops
     cdt = torch.bfloat16 if args.dtype == "bf16" else torch.float32
-    layers = build_layers(dev, cdt)
-    from m3vit_b200.synthetic import device_tokens
     T = args.batch * N_TOK
+    ep_ctx = None
+    if world > 1:
+        # expert parallel over the GPUs of the box: peer-mapped queues (CUDA IPC over NVLink), see m3vit_b200/ep.py
+        from m3vit_b200 import ep
+        assert N_EXP % world == 0
+        el = 2 if cdt == torch.bfloat16 else 4
+        q_bytes = ((int(args.capacity_factor * T * TOP_K) + (N_EXP // world) * 127 + 127) // 128 * 128) * D_MODEL * el
+        ep_ctx = ep.make_context(ep.TorchDistGroup(), dev, arena_bytes=6 * (q_bytes + 4096),
+                                 capacity_factor=args.capacity_factor)
+    layers = build_layers(dev, cdt, rank, world, ep_ctx)
+    from m3vit_b200.synthetic import device_tokens
     calls = [(li, t) for t in range(N_TASK) for li in range(N_LAYER)]      # per task: a full backbone pass
     xs = [device_tokens(T, D_MODEL, 100 * rank + i, dev).requires_grad_(True) for i in range(len(calls))]
     gs = [torch.randn(T, D_MODEL, device=dev) * 0.01 for _ in range(2)]
@@ -282,15 +300,20 @@ def main():
     # ---- roofline of the dominant kernel family, timed live on this stream
     pk = peaks()
     roof, stages = None, {}
+    if ep_ctx is not None:
+        ep_ctx.check_overflow()
     if rank == 0:
-        roof, stages = kernel_rooflines(layers[0], xs[0].detach(), dev, cdt, pk)
+        ref_layer = layers[0] if world == 1 else build_layers(dev, cdt)[0]     # all-experts-local layer for the table
+        roof, stages = kernel_rooflines(ref_layer, xs[0].detach(), dev, cdt, pk)
 
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": "tokens/s", "n_gpus": world, "steps": args.steps,
                 "warmup": warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": args.dtype, "data": "synthetic", "config": config,
                 "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roof, "stages": stages,
-                "parallelism": "replicas (each GPU routes its own tokens over all experts)" if world > 1 else "single"}
+                "parallelism": (f"expert-parallel ep{world}: {N_EXP // world} experts/GPU, router replicated, token rows "
+                                "pushed/pulled over NVLink peer queues (no NCCL on the data path)") if world > 1
+                else "single GPU, all experts local"}
         if not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_reference(5, 2)
         print(json.dumps(line))

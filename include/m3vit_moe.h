@@ -208,6 +208,16 @@ int m3_ep_dispatch_bwd(void* const* peer_dxq, int dxq_dtype, const int32_t* dst_
                        const float* w_gate, int E, void* dx, int dx_dtype, m3_stream_t stream);
 int m3_zero_pad_rows(void* q, int dtype, const int32_t* counts, const int32_t* offsets, int E, int D,
                      m3_stream_t stream);
+/* Device-side rendezvous of the W ranks over peer memory (replaces an NCCL barrier / the
+ * fmoe expert_exchange count all-to-all): a 1-warp kernel stores `epoch` into slot `rank` of every
+ * peer's flag array (system-scope release) and, if `payload` != NULL, first copies `payload_ints`
+ * int32 into row `rank` of every peer's gather buffer; it then spins (bounded, acquire) until all W
+ * slots of ITS OWN flag array have reached `epoch`.  Every rank must call it with the same epoch.
+ *   peer_flags[W]  device array: base of every rank's flag array (W int32 each)
+ *   peer_gather[W] device array: base of every rank's gather buffer [W][payload_ints] (or NULL)
+ * Only valid with one process per GPU (ranks must be co-resident on different devices). */
+int m3_ep_barrier(void* const* peer_flags, void* const* peer_gather, const int32_t* payload,
+                  int payload_ints, int rank, int W, int epoch, m3_stream_t stream);
 
 /* CUDA IPC plumbing for the peer queues (host pointers in/out; 64-byte handles). */
 int m3_ipc_alloc(size_t bytes, void** dev_ptr, void* handle64);

@@ -1,5 +1,7 @@
 // C-ABI glue: status strings, device check, FFN dtype dispatch, weight casts,
 // expert-parallel plan, CUDA-IPC plumbing.  See include/m3vit_moe.h.
+#include <cstdio>
+
 #include "common.cuh"
 
 // implemented in ffn_f32.cu / ffn_bf16.cu
@@ -189,7 +191,48 @@ __global__ void ep_plan_kernel(const int64_t* __restrict__ idx, const int32_t* _
     }
   }
 }
+// Flag barrier (+ optional small all-gather) over peer memory; see m3_ep_barrier in the header.
+__global__ void ep_barrier_kernel(int32_t* const* __restrict__ peer_flags, int32_t* const* __restrict__ peer_gather,
+                                  const int32_t* __restrict__ payload, int n, int rank, int W, int epoch) {
+  const int lane = threadIdx.x;
+  if (peer_gather != nullptr) {
+    for (int p = 0; p < W; ++p) {
+      int32_t* dst = peer_gather[p] + (int64_t)rank * n;
+      for (int i = lane; i < n; i += 32) dst[i] = payload[i];
+    }
+  }
+  __threadfence_system();          // payload (and everything earlier in this stream) before the flag
+  __syncwarp();
+  if (lane < W) {
+    volatile int32_t* f = peer_flags[lane] + rank;
+    asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(f), "r"(epoch) : "memory");
+  }
+  if (lane < W) {
+    const int32_t* mine = peer_flags[rank] + lane;
+    const long long t0 = clock64();
+    int v;
+    do {
+      asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(mine) : "memory");
+      if (clock64() - t0 > 20000000000LL) {   // ~10 s: a peer never arrived
+        printf("m3_ep_barrier: rank %d timed out waiting for rank %d (epoch %d, have %d)\n", rank, lane, epoch, v);
+        __trap();
+      }
+    } while (v < epoch);
+  }
+  __threadfence_system();
+}
 }  // namespace m3
+
+extern "C" int m3_ep_barrier(void* const* peer_flags, void* const* peer_gather, const int32_t* payload,
+                             int payload_ints, int rank, int W, int epoch, m3_stream_t stream) {
+  M3_CHECK_ARG(peer_flags && W >= 1 && W <= 32 && rank >= 0 && rank < W && epoch > 0);
+  M3_CHECK_ARG((peer_gather == nullptr) == (payload == nullptr) && payload_ints >= 0);
+  m3::ep_barrier_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<int32_t* const*>(peer_flags), reinterpret_cast<int32_t* const*>(peer_gather), payload,
+      payload_ints, rank, W, epoch);
+  M3_LAUNCH_CHECK();
+  return M3_OK;
+}
 
 extern "C" int m3_cast_weights_bf16(const float* w, int E, int R, int C, void* w_bf16, void* wt_bf16,
                                     m3_stream_t stream) {

@@ -278,8 +278,9 @@ gg_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
 struct WGParams {
   const int32_t* offsets;
   int M, N;       // dW_e is [M][N]; X1 is [rows][M], X2 is [rows][N]
-  float* dW;      // [E][M][N]
-  float* db;      // [E][M] = column sums of X1 over the expert's rows (bias gradient)
+  float* dW;      // [S][E][M][N]  (S = gridDim.z / E row-splits; S == 1: the final gradient)
+  float* db;      // [S][E][M] = column sums of X1 over the expert's rows (bias gradient)
+  int E;
 };
 
 template <int BN>
@@ -309,7 +310,10 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tm1, const __grid_constant__ CU
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tfull + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int e = blockIdx.z, m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+  // split-K over the expert's rows: blockIdx.z = split * E + e, split s owns a contiguous range of
+  // 64-row chunks, partial results are reduced in a fixed order afterwards (deterministic)
+  const int e = blockIdx.z % p.E, split = blockIdx.z / p.E, nsplit = gridDim.z / p.E;
+  const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
   // db = X1^T * 1: the n0 == 0 CTAs run one extra N=16 MMA per k-step against a tile of ones
   const bool with_db = (blockIdx.y == 0) && (p.db != nullptr);
   if (with_db) {
@@ -330,8 +334,11 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tm1, const __grid_constant__ CU
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const int r0 = p.offsets[e], r1 = p.offsets[e + 1];
-  const int kchunks = (r1 - r0) / BK;   // queues are padded to 128 rows
+  const int all_chunks = (p.offsets[e + 1] - p.offsets[e]) / BK;   // queues are padded to 128 rows
+  const int per_split = (all_chunks + nsplit - 1) / nsplit;
+  const int c_begin = min(split * per_split, all_chunks), c_end = min(c_begin + per_split, all_chunks);
+  const int r0 = p.offsets[e] + c_begin * BK;
+  const int kchunks = c_end - c_begin;
 
   if (warp == 0) {
     if (lane == 0) {
@@ -381,11 +388,12 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tm1, const __grid_constant__ CU
   } else {
     const int q = warp & 3;
     const int row = m0 + q * 32 + lane;
-    float* dst = p.dW + ((int64_t)e * p.M + row) * p.N + n0;
+    const int64_t se = (int64_t)split * p.E + e;
+    float* dst = p.dW + (se * p.M + row) * p.N + n0;
     if (kchunks == 0) {  // expert received no rows: dW_e = 0
 #pragma unroll 1
       for (int c = 0; c < BN / 4; ++c) *reinterpret_cast<float4*>(dst + 4 * c) = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (with_db) p.db[(int64_t)e * p.M + row] = 0.f;
+      if (with_db) p.db[se * p.M + row] = 0.f;
     } else {
       mbar_wait(tfull, 0);
       tcgen05_fence_after();
@@ -400,7 +408,7 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tm1, const __grid_constant__ CU
       if (with_db) {
         float v[32];   // 16 identical columns (+16 unused): every column of X1^T * ones is the column sum
         tmem_ld_32x32(tmem_base + BN + ((uint32_t)(q * 32) << 16), v);
-        p.db[(int64_t)e * p.M + row] = v[0];
+        p.db[se * p.M + row] = v[0];
       }
     }
   }
@@ -410,45 +418,6 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tm1, const __grid_constant__ CU
     __syncwarp();
     tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
   }
-}
-
-// ------------------------------------------------------------ bias gradients
-// stage 1: per 128-row tile column sums (fully parallel, reads the matrix once)
-__global__ void __launch_bounds__(256)
-colsum_tile_kernel(const __nv_bfloat16* __restrict__ G, const int32_t* __restrict__ offsets, int E, int N,
-                   float* __restrict__ part) {
-  const int m_blk = blockIdx.y;
-  if (m_blk * BM >= offsets[E]) return;
-  __shared__ float red[8][64];
-  const int cp = threadIdx.x & 31, rg = threadIdx.x >> 5;  // column pair, row group
-  const int col = blockIdx.x * 64 + cp * 2;
-  float a0 = 0.f, a1 = 0.f;
-  if (col < N) {
-    const __nv_bfloat16* g = G + (int64_t)m_blk * BM * N + col;
-#pragma unroll 4
-    for (int r = rg; r < BM; r += 8) {
-      const float2 f = bf16x2_to_float2(__ldg(reinterpret_cast<const uint32_t*>(g + (int64_t)r * N)));
-      a0 += f.x; a1 += f.y;
-    }
-  }
-  red[rg][cp * 2] = a0;
-  red[rg][cp * 2 + 1] = a1;
-  __syncthreads();
-  if (threadIdx.x < 64 && blockIdx.x * 64 + threadIdx.x < N) {
-    float s = 0.f;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) s += red[i][threadIdx.x];
-    part[(int64_t)m_blk * N + blockIdx.x * 64 + threadIdx.x] = s;
-  }
-}
-// stage 2: db[e][n] = sum of the expert's tile partials, fixed order
-__global__ void colsum_reduce_kernel(const float* __restrict__ part, const int32_t* __restrict__ offsets, int N,
-                                     float* __restrict__ db) {
-  const int e = blockIdx.y, n = blockIdx.x * blockDim.x + threadIdx.x;
-  if (n >= N) return;
-  float s = 0.f;
-  for (int t = offsets[e] / BM; t < offsets[e + 1] / BM; ++t) s += part[(int64_t)t * N + n];
-  db[(int64_t)e * N + n] = s;
 }
 
 // ------------------------------------------------------------------ host side
@@ -531,11 +500,34 @@ static int launch_gg(const void* A, const void* B, void* out, void* out2, const 
   }
 }
 
-// dW [E][M][N] fp32 = X1[rows][M]^T X2[rows][N] per expert
+// out[i] = sum_s part[s][i] (fixed order), float4-wide
+__global__ void splitk_reduce_kernel(const float* __restrict__ part, int nsplit, int64_t n4, float* __restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n4) return;
+  float4 a = reinterpret_cast<const float4*>(part)[i];
+  for (int s = 1; s < nsplit; ++s) {
+    const float4 b = reinterpret_cast<const float4*>(part)[(int64_t)s * n4 + i];
+    a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+  }
+  reinterpret_cast<float4*>(out)[i] = a;
+}
+
+// row-splits per expert so that the wgrad grid fills the GPU once (few local experts under EP)
+static int wgrad_splits(int E, int M, int N) {
+  const int tiles = (M / BM) * (N / 128) * E;
+  int s = kNumSMs / tiles;
+  return s < 1 ? 1 : (s > 16 ? 16 : s);
+}
+static size_t wgrad_ws_bytes(int E, int M, int N) {
+  const int S = wgrad_splits(E, M, N);
+  return S > 1 ? (size_t)S * E * ((size_t)M * N + M) * sizeof(float) : 0;
+}
+
+// dW [E][M][N] fp32 = X1[rows][M]^T X2[rows][N] per expert (+ db [E][M] = column sums of X1)
 static int launch_wgrad(const void* X1, const void* X2, const int32_t* offsets, int cap_rows, int E, int M, int N,
-                        float* dW, float* db, cudaStream_t st) {
+                        float* dW, float* db, float* ws, cudaStream_t st) {
   constexpr int BN = 128;
-  if (M % BM != 0 || N % BN != 0) return M3_ERR_SHAPE;
+  if (M % BM != 0 || N % BN != 0 || (M * (int64_t)N) % 4 != 0) return M3_ERR_SHAPE;
   CUtensorMap t1, t2;
   int rc = make_map(&t1, X1, (uint64_t)cap_rows, (uint64_t)M, BK);
   if (rc) return rc;
@@ -545,18 +537,20 @@ static int launch_wgrad(const void* X1, const void* X2, const int32_t* offsets, 
   auto kern = wgrad_kernel<BN>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
   if (e != cudaSuccess) return (int)e;
-  WGParams p{offsets, M, N, dW, db};
-  kern<<<dim3(M / BM, N / BN, E), kThreads, Cfg::SMEM, st>>>(t1, t2, p);
+  const int S = wgrad_splits(E, M, N);
+  float* pW = S > 1 ? ws : dW;
+  float* pb = S > 1 ? ws + (size_t)S * E * M * N : db;
+  WGParams p{offsets, M, N, pW, pb, E};
+  kern<<<dim3(M / BM, N / BN, E * S), kThreads, Cfg::SMEM, st>>>(t1, t2, p);
   M3_LAUNCH_CHECK();
-  return M3_OK;
-}
-
-static int launch_colsum(const __nv_bfloat16* G, const int32_t* offsets, int cap_rows, int E, int N, float* part,
-                         float* db, cudaStream_t st) {
-  colsum_tile_kernel<<<dim3(m3_ceil_div(N, 64), cap_rows / BM), 256, 0, st>>>(G, offsets, E, N, part);
-  M3_LAUNCH_CHECK();
-  colsum_reduce_kernel<<<dim3(m3_ceil_div(N, 128), E), 128, 0, st>>>(part, offsets, N, db);
-  M3_LAUNCH_CHECK();
+  if (S > 1) {
+    const int64_t n4 = (int64_t)E * M * N / 4;
+    splitk_reduce_kernel<<<(int)((n4 + 255) / 256), 256, 0, st>>>(pW, S, n4, dW);
+    M3_LAUNCH_CHECK();
+    const int64_t b4 = (int64_t)E * M / 4;
+    splitk_reduce_kernel<<<(int)((b4 + 255) / 256), 256, 0, st>>>(pb, S, b4, db);
+    M3_LAUNCH_CHECK();
+  }
   return M3_OK;
 }
 
@@ -570,12 +564,13 @@ using namespace m3::tc;
 typedef __nv_bfloat16 bf16;
 
 // workspace: forward  : h [cap][H] bf16
-//            backward : dhpre [cap][H] bf16 | h [cap][H] bf16 | colsum partials [cap/128][max(D,H)] fp32
+//            backward : dhpre [cap][H] bf16 | h [cap][H] bf16 | wgrad split-K partials [S][E][M][N]+[S][E][M] fp32
 size_t m3_ffn_bf16_workspace_bytes(int cap_rows, int D, int H, int E, int backward) {
   (void)E;
   const size_t hbytes = align256((size_t)cap_rows * H * 2);
   if (!backward) return hbytes;
-  return 2 * hbytes + align256((size_t)(cap_rows / BM) * (D > H ? D : H) * 4);
+  const size_t wg = wgrad_ws_bytes(E, D, H) > wgrad_ws_bytes(E, H, D) ? wgrad_ws_bytes(E, D, H) : wgrad_ws_bytes(E, H, D);
+  return 2 * hbytes + align256(wg);
 }
 
 int m3_ffn_fwd_bf16(const void* xq, const int32_t* offsets, const int32_t* tile_expert, int cap_rows, int E, int D,
@@ -616,8 +611,7 @@ int m3_ffn_bwd_bf16(const void* xq, const void* hpre, const void* dyq, const int
   if (rc) return rc;
   // dW2[e] = dyq_e^T h_e  [D][H];   dW1[e] = dhpre_e^T xq_e  [H][D]
   // the bias gradients ride along as one extra N=16 MMA against a tile of ones
-  (void)part;
-  rc = launch_wgrad(dyq, h, offsets, cap_rows, E, D, H, dw2, db2, st);
+  rc = launch_wgrad(dyq, h, offsets, cap_rows, E, D, H, dw2, db2, part, st);
   if (rc) return rc;
-  return launch_wgrad(dhpre, xq, offsets, cap_rows, E, H, D, dw1, db1, st);
+  return launch_wgrad(dhpre, xq, offsets, cap_rows, E, H, D, dw1, db1, part, st);
 }

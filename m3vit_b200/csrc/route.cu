@@ -114,7 +114,7 @@ route_assign_kernel(const int64_t* __restrict__ idx, int R, int E, int pad, int 
   if (b == 0) {
     for (int e = tid; e < E; e += kRouteThreads) counts[e] = tot[e];
     for (int e = tid; e <= E; e += kRouteThreads) offsets[e] = off[e];
-    const int ntile = off[E] / pad;
+    const int ntile = tile_expert != nullptr ? off[E] / pad : 0;
     for (int i = tid; i < ntile; i += kRouteThreads) {
       const int row = i * pad;
       int lo = 0, hi = E;  // largest e with off[e] <= row
@@ -198,7 +198,7 @@ extern "C" int m3_route_plan(const int64_t* idx, int T, int K, int E, int pad, c
                              const int32_t* load_partial, int n_partial, int32_t* counts, int32_t* offsets,
                              int32_t* pos, int32_t* tile_expert, float* importance, float* load, float* cv_loss,
                              void* workspace, size_t workspace_bytes, m3_stream_t stream) {
-  M3_CHECK_ARG(idx && counts && offsets && pos && tile_expert && workspace);
+  M3_CHECK_ARG(idx && counts && offsets && pos && workspace);   // tile_expert may be NULL (pad-1 plans)
   M3_CHECK_ARG(T >= 0 && K >= 1 && E >= 1 && pad >= 1);
   M3_CHECK_SHAPE(E <= 128);
   if ((int64_t)T * K > (int64_t)1 << 30) return M3_ERR_SHAPE;

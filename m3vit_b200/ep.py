@@ -114,6 +114,50 @@ class TorchDistGroup:
         return out
 
 
+class PeerFlagGroup:
+    """Rendezvous + count all-gather done by OUR kernel over peer memory (m3_ep_barrier) instead of
+    NCCL: ~1 launch of a 1-warp kernel per synchronisation point, no host involvement.  Uses the
+    first HEADER bytes of every rank's arena (flags [W] + gather buffer)."""
+    HEADER = 64 * 1024
+
+    def __init__(self, rank, world, arena: "Arena", bases: torch.Tensor, bootstrap):
+        self.rank, self.world = rank, world
+        self.bootstrap = bootstrap                         # TorchDistGroup: only for setup / teardown
+        self.arena, self.bases = arena, bases
+        self.epoch = 0
+        off_flags = arena.alloc(4096)
+        self.off_gather = arena.alloc(self.HEADER - 4096)
+        assert off_flags == 0
+        arena._bytes[: self.HEADER].zero_()
+        self.flag_ptrs = bases + off_flags
+        self.gather_ptrs = bases + self.off_gather
+        torch.cuda.synchronize(arena.device)
+        bootstrap.barrier(arena.device)                    # flags are zeroed everywhere before first use
+        torch.cuda.synchronize(arena.device)
+
+    def _sync(self, payload, n):
+        self.epoch += 1
+        check(load().m3_ep_barrier(ptr(self.flag_ptrs), ptr(self.gather_ptrs) if payload is not None else None,
+                                   ptr(payload), n, self.rank, self.world, self.epoch, stream_ptr()), "m3_ep_barrier")
+        ops.launch_count += 1
+
+    def barrier(self, device) -> None:
+        self._sync(None, 0)
+
+    def all_gather_counts(self, counts: torch.Tensor) -> torch.Tensor:
+        n = counts.numel()
+        assert counts.dtype == torch.int32 and 2 * self.world * n * 4 <= self.HEADER - 4096
+        # double-buffered rows: a fast peer may already push the NEXT layer's counts while I still read these
+        half = (self.epoch + 1) & 1
+        goff = self.off_gather + half * (self.HEADER - 4096) // 2
+        self.epoch += 1
+        gp = self.bases + goff
+        check(load().m3_ep_barrier(ptr(self.flag_ptrs), ptr(gp), ptr(counts), n, self.rank, self.world, self.epoch,
+                                   stream_ptr()), "m3_ep_barrier")
+        ops.launch_count += 1
+        return self.arena.view(goff, self.world, n, torch.int32).clone()
+
+
 @dataclass
 class EPContext:
     """Per-rank EP state: arena + peer-mapped bases of every rank's arena."""
@@ -139,9 +183,12 @@ class EPContext:
             raise RuntimeError("EP receive queue overflow: tokens were dropped; raise capacity_factor")
 
 
-def make_context(group, device, arena_bytes: int, capacity_factor: Optional[float] = 2.0) -> EPContext:
-    """Collective: allocates the arena, exchanges IPC handles, maps the peers."""
-    arena = Arena(arena_bytes, device)
+def make_context(group, device, arena_bytes: int, capacity_factor: Optional[float] = 2.0,
+                 device_barrier: bool = True) -> EPContext:
+    """Collective: allocates the arena, exchanges IPC handles, maps the peers.  With
+    device_barrier=True (default) the per-layer rendezvous / count exchange run as our own
+    peer-memory kernel; otherwise through the torch.distributed group (NCCL)."""
+    arena = Arena(arena_bytes + PeerFlagGroup.HEADER, device)
     handles = group.exchange_bytes(arena.handle_bytes())
     bases = []
     lib = load()
@@ -155,7 +202,8 @@ def make_context(group, device, arena_bytes: int, capacity_factor: Optional[floa
                 check(lib.m3_ipc_open(buf, C.byref(p)), "m3_ipc_open")
                 bases.append(p.value)
     bases_t = torch.tensor(bases, dtype=torch.int64, device=device)
-    return EPContext(group.rank, group.world, group, arena, bases_t, capacity_factor,
+    sync_group = PeerFlagGroup(group.rank, group.world, arena, bases_t, group) if device_barrier else group
+    return EPContext(group.rank, group.world, sync_group, arena, bases_t, capacity_factor,
                      torch.zeros(1, dtype=torch.int32, device=device))
 
 

@@ -148,7 +148,7 @@ def route_plan(idx, num_expert, pad=PAD_ROWS, imp_partial=None, load_partial=Non
     dev = idx.device
     cap_rows = lib.m3_route_max_rows(T, K, E, pad)
     counts, offsets, pos = _i32(E, dev), _i32(E + 1, dev), _i32(T * K, dev)
-    tile_expert = _i32(max(cap_rows // pad, 1), dev)
+    tile_expert = _i32(max(cap_rows // pad, 1), dev) if pad >= 16 else None   # no tile map for pad-1 plans
     imp = load_v = cv = None
     n_part = 0
     if imp_partial is not None:
@@ -257,5 +257,12 @@ def ffn_bwd(xq, hpre, dyq, plan: Plan, w1, w2, w1t=None, w2t=None):
     check(lib.m3_ffn_bwd(dt, ptr(xq), ptr(hpre), ptr(dyq), ptr(plan.counts), ptr(plan.offsets), ptr(plan.tile_expert),
                          cap, E, D, H, ptr(w1), ptr(w2), ptr(w1t), ptr(w2t), ptr(dxq), ptr(dw1), ptr(db1), ptr(dw2),
                          ptr(db2), ptr(ws), ws.numel(), stream_ptr()), "m3_ffn_bwd")
-    _count("ffn_bwd_bf16" if dt == L.M3_BF16 else "ffn_bwd_f32")
+    if dt == L.M3_BF16:
+        tiles = (D // 128) * (H // 128) * E          # mirrors wgrad_splits() in ffn_bf16.cu
+        splits = min(16, max(1, 148 // tiles))
+        _count("ffn_bwd_bf16")
+        if splits > 1:
+            _count("cast_weights", 4)                # 2 x (dW + db) split-K reduce launches
+    else:
+        _count("ffn_bwd_f32")
     return dxq, dw1, db1, dw2, db2
