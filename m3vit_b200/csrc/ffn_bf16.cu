@@ -41,15 +41,18 @@ struct GGParams {
   int save_out2;               // EPI_FC1: also store the pre-activation (training)
 };
 
+constexpr int WBOX_BYTES = 32 * 64 * 2;  // one warp's [32 rows][64 bf16] swizzle-128B box = 4 KB
+
 template <int BN, int EPI>
 struct GGCfg {
   static constexpr int A_BYTES = BM * BK * 2;
   static constexpr int B_BYTES = BN * BK * 2;
   static constexpr int STAGE = A_BYTES + B_BYTES;
-  // epilogue staging: double-buffered 16 KB boxes per output tensor (+ per TMA-loaded aux input)
+  // epilogue staging: one private 4 KB box per epilogue warp per output tensor (+ per TMA-loaded aux input)
   static constexpr int N_OUT = (EPI == EPI_FC1 || EPI == EPI_DGELU) ? 2 : 1;
   static constexpr int N_AUX = (EPI == EPI_DGELU) ? 1 : 0;
-  static constexpr int STAGING = (N_OUT + N_AUX) * 2 * BOX_BYTES;
+  static constexpr int WARP_STAGING = (N_OUT + N_AUX) * WBOX_BYTES;
+  static constexpr int STAGING = kEpiWarps * WARP_STAGING;
   static constexpr int BUDGET = 227 * 1024 - 1024 - 512 - STAGING;
   static constexpr int STAGES = (BUDGET / STAGE) < 6 ? (BUDGET / STAGE) : 6;
   static constexpr int TMEM_COLS = (2 * BN <= 256) ? 256 : 512;
@@ -57,25 +60,17 @@ struct GGCfg {
   static_assert(STAGES >= 3, "smem ring too shallow");
 };
 
-__device__ __forceinline__ uint4 pack8(const float* v) {
-  uint4 r;
-  r.x = float2_to_bf16x2(v[0], v[1]);
-  r.y = float2_to_bf16x2(v[2], v[3]);
-  r.z = float2_to_bf16x2(v[4], v[5]);
-  r.w = float2_to_bf16x2(v[6], v[7]);
-  return r;
+__device__ __forceinline__ uint32_t pack_bf16x2(f32x2 v) {
+  float a, b;
+  unpk2(v, a, b);
+  return float2_to_bf16x2(a, b);
 }
-__device__ __forceinline__ void unpack8(const uint4& u, float* v) {
-  float2 f;
-  f = bf16x2_to_float2(u.x); v[0] = f.x; v[1] = f.y;
-  f = bf16x2_to_float2(u.y); v[2] = f.x; v[3] = f.y;
-  f = bf16x2_to_float2(u.z); v[4] = f.x; v[5] = f.y;
-  f = bf16x2_to_float2(u.w); v[6] = f.x; v[7] = f.y;
+__device__ __forceinline__ f32x2 unpack_bf16x2(uint32_t u) {
+  const float2 f = bf16x2_to_float2(u);
+  return pk2(f.x, f.y);
 }
 // 16-byte chunk c (0..7) of row r inside a [rows][64 bf16] swizzle-128B box (what TMA reads / writes)
 __device__ __forceinline__ uint32_t box_off(int r, int c) { return (uint32_t)r * 128u + (uint32_t)((c ^ (r & 7)) << 4); }
-
-__device__ __forceinline__ void epi_barrier() { asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory"); }
 
 template <int BN, int EPI>
 __global__ void __launch_bounds__(kGGThreads, 1)
@@ -92,8 +87,8 @@ gg_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
   uint64_t* empty = full + STAGES;
   uint64_t* tfull = empty + STAGES;
   uint64_t* tempty = tfull + 2;
-  uint64_t* aux_full = tempty + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(aux_full + 2);
+  uint64_t* aux_full = tempty + 2;                            // [kEpiWarps]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(aux_full + kEpiWarps);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (warp == 0 && lane == 0) {
@@ -104,11 +99,8 @@ gg_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
   if (warp == 1) {
     if (lane == 0) {
       for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-      for (int a = 0; a < 2; ++a) {
-        mbar_init(&tfull[a], 1);
-        mbar_init(&tempty[a], kEpiWarps * 32);
-        mbar_init(&aux_full[a], 1);
-      }
+      for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 4 * 32); }
+      for (int w = 0; w < kEpiWarps; ++w) mbar_init(&aux_full[w], 1);
       fence_barrier_init();
     }
     __syncwarp();
@@ -170,100 +162,118 @@ gg_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
       }
     }
   } else {
-    // ---- epilogue: TMEM -> registers -> (bias / GELU / GELU') -> bf16 -> swizzled smem box -> TMA store.
-    // Warp w reads TMEM lanes 32*(w%4).. (hardware rule); the two warps of a quarter split each
-    // 64-column box into 32-column halves.
+    // ---- epilogue.  Every warp is an independent pipeline: TMEM -> registers -> bias / GELU / GELU'
+    // (packed f32x2) -> bf16 -> its private swizzled [32 x 64] smem box -> its own TMA store.  No
+    // CTA-wide barrier.  Warp w reads TMEM lanes 32*(w%4).. (hardware rule); warps 2-5 serve
+    // accumulator buffer 0 (even tiles of this CTA), warps 6-9 buffer 1 (odd tiles), so two tiles
+    // are always in flight in the epilogue.
     const int q = warp & 3;
-    const int hh = (warp - 2) >> 2;
-    const int r = q * 32 + lane;                 // row inside the tile
-    const bool leader = threadIdx.x == 64;       // issues the TMA stores / aux loads
-    uint8_t* st_out = stg;
-    uint8_t* st_out2 = stg + 2 * BOX_BYTES;
-    uint8_t* st_aux = stg + 4 * BOX_BYTES;
-    uint32_t acc = 0, acc_phase = 0, g = 0;      // g: running box counter (staging buffer parity)
+    const int ew = warp - 2;                     // 0..7
+    const uint32_t grp = (uint32_t)ew >> 2;      // accumulator buffer served
+    uint8_t* my = stg + ew * Cfg::WARP_STAGING;
+    uint8_t* o1 = my;
+    uint8_t* o2 = my + WBOX_BYTES;
+    uint8_t* ax = my + 2 * WBOX_BYTES;
+    uint64_t* my_aux = &aux_full[ew];
     const bool two_out = (EPI == EPI_DGELU) || (EPI == EPI_FC1 && p.save_out2);
-    if (EPI == EPI_DGELU && leader && blockIdx.x < total) {
-      const int m_blk = blockIdx.x / n_tiles, n_blk = blockIdx.x % n_tiles;
-      mbar_expect_tx(&aux_full[0], BOX_BYTES);
-      tma_load_2d(st_aux, &tmAux, &aux_full[0], n_blk * BN, m_blk * BM);
+    uint32_t aux_uses = 0;
+    const int first = blockIdx.x + (int)grp * gridDim.x;
+    if (EPI == EPI_DGELU && lane == 0 && first < total) {
+      mbar_expect_tx(my_aux, WBOX_BYTES);
+      tma_load_2d(ax, &tmAux, my_aux, (first % n_tiles) * BN, (first / n_tiles) * BM + q * 32);
     }
-    for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
+    uint32_t it = grp;
+    for (int tile = first; tile < total; tile += 2 * gridDim.x, it += 2) {
       const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
       const int e = p.tile_expert[m_blk];
-      mbar_wait(&tfull[acc], acc_phase);
+      const int row0 = m_blk * BM + q * 32;
+      mbar_wait(&tfull[grp], (it >> 1) & 1);
       tcgen05_fence_after();
 #pragma unroll 1
-      for (int cb = 0; cb < NB; ++cb, ++g) {
-        const uint32_t buf = g & 1;
-        // the TMA store that last read staging buffer `buf` (two boxes ago) must have drained it
-        if (leader) tma_store_wait_read<1>();
-        epi_barrier();
-        if (EPI == EPI_DGELU) {
-          if (leader) {  // prefetch the hpre box of the NEXT (tile, box) into the other aux buffer
-            int nt = tile, ncb = cb + 1;
-            if (ncb == NB) { ncb = 0; nt += gridDim.x; }
-            if (nt < total) {
-              mbar_expect_tx(&aux_full[buf ^ 1], BOX_BYTES);
-              tma_load_2d(st_aux + (buf ^ 1) * BOX_BYTES, &tmAux, &aux_full[buf ^ 1],
-                          (nt % n_tiles) * BN + ncb * 64, (nt / n_tiles) * BM);
-            }
-          }
-          mbar_wait(&aux_full[buf], (g >> 1) & 1);
-        }
-        float v[32];
-        tmem_ld_32x32(tmem_base + acc * BN + cb * 64 + hh * 32 + ((uint32_t)(q * 32) << 16), v);
+      for (int cb = 0; cb < NB; ++cb) {
+        const int col = n_blk * BN + cb * 64;
+        float v[64];
+        const uint32_t taddr = tmem_base + grp * BN + cb * 64 + ((uint32_t)(q * 32) << 16);
+        tmem_ld_32x32(taddr, v);
+        tmem_ld_32x32(taddr + 32, v + 32);
         if (cb == NB - 1) {  // last TMEM read of this accumulator: hand it back to the MMA warp early
           tcgen05_fence_before();
-          mbar_arrive(&tempty[acc]);
+          mbar_arrive(&tempty[grp]);
         }
-        const int col = n_blk * BN + cb * 64 + hh * 32;
+        f32x2 w2[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) w2[j] = pk2(v[2 * j], v[2 * j + 1]);
         if (EPI == EPI_BIAS || EPI == EPI_FC1) {
           const float4* b4 = reinterpret_cast<const float4*>(p.bias + (int64_t)e * p.N + col);
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
+          for (int j = 0; j < 16; ++j) {
             const float4 b = __ldg(b4 + j);
-            v[4 * j] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
+            w2[2 * j] = add2(w2[2 * j], pk2(b.x, b.y));
+            w2[2 * j + 1] = add2(w2[2 * j + 1], pk2(b.z, b.w));
           }
         }
-        uint8_t* o1 = st_out + buf * BOX_BYTES;
-        uint8_t* o2 = st_out2 + buf * BOX_BYTES;
+        // the previous box's TMA stores must have drained this warp's staging boxes
+        if (lane == 0) tma_store_wait_read<0>();
+        __syncwarp();
         if (EPI == EPI_FC1) {
           if (p.save_out2) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) *reinterpret_cast<uint4*>(o2 + box_off(r, hh * 4 + j)) = pack8(v + 8 * j);
+            for (int c = 0; c < 8; ++c) {
+              uint4 u;
+              u.x = pack_bf16x2(w2[4 * c]); u.y = pack_bf16x2(w2[4 * c + 1]);
+              u.z = pack_bf16x2(w2[4 * c + 2]); u.w = pack_bf16x2(w2[4 * c + 3]);
+              *reinterpret_cast<uint4*>(o2 + box_off(lane, c)) = u;
+            }
           }
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = gelu_fast(v[j]);
+          for (int j = 0; j < 32; ++j) w2[j] = gelu_fast2(w2[j]);
         }
         if (EPI == EPI_DGELU) {
-          const uint8_t* ax = st_aux + buf * BOX_BYTES;
+          mbar_wait(my_aux, aux_uses & 1);
+          ++aux_uses;
+          uint4 hraw[8];
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            float hv[8];
-            unpack8(*reinterpret_cast<const uint4*>(ax + box_off(r, hh * 4 + j)), hv);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              float gl;
-              v[8 * j + i] *= gelu_fast_grad(hv[i], &gl);
-              hv[i] = gl;
+          for (int c = 0; c < 8; ++c) hraw[c] = *reinterpret_cast<const uint4*>(ax + box_off(lane, c));
+          __syncwarp();
+          if (lane == 0) {  // aux box consumed into registers: prefetch the next one behind the math
+            int nt = tile, ncb = cb + 1;
+            if (ncb == NB) { ncb = 0; nt += 2 * gridDim.x; }
+            if (nt < total) {
+              mbar_expect_tx(my_aux, WBOX_BYTES);
+              tma_load_2d(ax, &tmAux, my_aux, (nt % n_tiles) * BN + ncb * 64, (nt / n_tiles) * BM + q * 32);
             }
-            *reinterpret_cast<uint4*>(o2 + box_off(r, hh * 4 + j)) = pack8(hv);   // h = gelu(hpre) for wgrad
+          }
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            const uint32_t hw[4] = {hraw[c].x, hraw[c].y, hraw[c].z, hraw[c].w};
+            uint32_t ho[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              f32x2 gl;
+              const f32x2 gr = gelu_fast_grad2(unpack_bf16x2(hw[i]), &gl);
+              w2[4 * c + i] = mul2(w2[4 * c + i], gr);
+              ho[i] = pack_bf16x2(gl);
+            }
+            *reinterpret_cast<uint4*>(o2 + box_off(lane, c)) = make_uint4(ho[0], ho[1], ho[2], ho[3]);   // h = gelu(hpre)
           }
         }
 #pragma unroll
-        for (int j = 0; j < 4; ++j) *reinterpret_cast<uint4*>(o1 + box_off(r, hh * 4 + j)) = pack8(v + 8 * j);
+        for (int c = 0; c < 8; ++c) {
+          uint4 u;
+          u.x = pack_bf16x2(w2[4 * c]); u.y = pack_bf16x2(w2[4 * c + 1]);
+          u.z = pack_bf16x2(w2[4 * c + 2]); u.w = pack_bf16x2(w2[4 * c + 3]);
+          *reinterpret_cast<uint4*>(o1 + box_off(lane, c)) = u;
+        }
         fence_proxy_async_smem();
-        epi_barrier();
-        if (leader) {
-          tma_store_2d(&tmOut, o1, n_blk * BN + cb * 64, m_blk * BM);
-          if (two_out) tma_store_2d(&tmOut2, o2, n_blk * BN + cb * 64, m_blk * BM);
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_2d(&tmOut, o1, col, row0);
+          if (two_out) tma_store_2d(&tmOut2, o2, col, row0);
           tma_store_commit();
         }
       }
-      acc ^= 1;
-      if (acc == 0) acc_phase ^= 1;
     }
-    if (leader) tma_store_wait_read<0>();
+    if (lane == 0) tma_store_wait_read<0>();
   }
   tcgen05_fence_before();
   __syncthreads();
@@ -279,7 +289,7 @@ struct WGParams {
   const int32_t* offsets;
   int M, N;       // dW_e is [M][N]; X1 is [rows][M], X2 is [rows][N]
   float* dW;      // [S][E][M][N]  (S = gridDim.z / E row-splits; S == 1: the final gradient)
-  float* db;      // [S][E][M] = column sums of X1 over the expert's rows (bias gradient)
+  float* db;      // [S*NT][E][M] partial column sums of X1 (bias gradient), NT = gridDim.y n-tile CTAs
   int E;
 };
 
@@ -314,8 +324,11 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tm1, const __grid_constant__ CU
   // 64-row chunks, partial results are reduced in a fixed order afterwards (deterministic)
   const int e = blockIdx.z % p.E, split = blockIdx.z / p.E, nsplit = gridDim.z / p.E;
   const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
-  // db = X1^T * 1: the n0 == 0 CTAs run one extra N=16 MMA per k-step against a tile of ones
-  const bool with_db = (blockIdx.y == 0) && (p.db != nullptr);
+  // db = X1^T * 1 as an extra N=16 MMA per k-step against a tile of ones.  The NT CTAs that share
+  // (m0, e, split) each take every NT-th k-chunk, so no CTA is slower than its neighbours; the
+  // S*NT partial vectors are reduced afterwards in a fixed order.
+  const bool with_db = p.db != nullptr;
+  const int nt = gridDim.y, my_nt = blockIdx.y;
   if (with_db) {
     for (int i = threadIdx.x; i < Cfg::ONES_BYTES / 4; i += kThreads) reinterpret_cast<uint32_t*>(ones)[i] = 0x3F803F80u;
     fence_proxy_async_smem();
@@ -375,9 +388,9 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tm1, const __grid_constant__ CU
           const uint64_t adesc = make_smem_desc(a_base + k * 2048, Cfg::BOX, 1024);
           const uint64_t bdesc = make_smem_desc(b_base + k * 2048, Cfg::BOX, 1024);
           umma_bf16(tmem_base, adesc, bdesc, idesc, (kc | k) != 0);
-          if (with_db) {
+          if (with_db && (kc % nt) == my_nt) {
             const uint64_t odesc = make_smem_desc(ones_base + k * 2048, Cfg::BOX, 1024);
-            umma_bf16(tmem_base + BN, adesc, odesc, idesc_db, (kc | k) != 0);
+            umma_bf16(tmem_base + BN, adesc, odesc, idesc_db, (kc >= nt) || (k != 0));
           }
         }
         umma_commit(&empty[stage]);
@@ -389,11 +402,13 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tm1, const __grid_constant__ CU
     const int q = warp & 3;
     const int row = m0 + q * 32 + lane;
     const int64_t se = (int64_t)split * p.E + e;
+    const int64_t sbe = ((int64_t)split * nt + my_nt) * p.E + e;     // db partial index
+    const bool db_any = with_db && kchunks > my_nt;                   // this CTA issued at least one db MMA
     float* dst = p.dW + (se * p.M + row) * p.N + n0;
     if (kchunks == 0) {  // expert received no rows: dW_e = 0
 #pragma unroll 1
       for (int c = 0; c < BN / 4; ++c) *reinterpret_cast<float4*>(dst + 4 * c) = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (with_db) p.db[se * p.M + row] = 0.f;
+      if (with_db) p.db[sbe * p.M + row] = 0.f;
     } else {
       mbar_wait(tfull, 0);
       tcgen05_fence_after();
@@ -408,7 +423,7 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tm1, const __grid_constant__ CU
       if (with_db) {
         float v[32];   // 16 identical columns (+16 unused): every column of X1^T * ones is the column sum
         tmem_ld_32x32(tmem_base + BN + ((uint32_t)(q * 32) << 16), v);
-        p.db[se * p.M + row] = v[0];
+        p.db[sbe * p.M + row] = db_any ? v[0] : 0.f;
       }
     }
   }
@@ -484,11 +499,11 @@ static int launch_gg(const void* A, const void* B, void* out, void* out2, const 
   if (rc) return rc;
   rc = make_map(&maps[1], B, (uint64_t)p.E * p.N, (uint64_t)p.Kd, (uint32_t)BN);
   if (rc) return rc;
-  rc = make_map(&maps[2], out, (uint64_t)cap_rows, (uint64_t)p.N, BM);
+  rc = make_map(&maps[2], out, (uint64_t)cap_rows, (uint64_t)p.N, 32);      // per-warp [32 x 64] boxes
   if (rc) return rc;
-  rc = make_map(&maps[3], out2 ? out2 : out, (uint64_t)cap_rows, (uint64_t)p.N, BM);
+  rc = make_map(&maps[3], out2 ? out2 : out, (uint64_t)cap_rows, (uint64_t)p.N, 32);
   if (rc) return rc;
-  rc = make_map(&maps[4], aux ? aux : out, (uint64_t)cap_rows, (uint64_t)p.N, BM);
+  rc = make_map(&maps[4], aux ? aux : out, (uint64_t)cap_rows, (uint64_t)p.N, 32);
   if (rc) return rc;
   const int max_tiles = (cap_rows / BM) * (p.N / BN);
   switch (BN) {
@@ -520,7 +535,7 @@ static int wgrad_splits(int E, int M, int N) {
 }
 static size_t wgrad_ws_bytes(int E, int M, int N) {
   const int S = wgrad_splits(E, M, N);
-  return S > 1 ? (size_t)S * E * ((size_t)M * N + M) * sizeof(float) : 0;
+  return ((S > 1 ? (size_t)S * E * M * N : 0) + (size_t)S * (N / 128) * E * M) * sizeof(float);
 }
 
 // dW [E][M][N] fp32 = X1[rows][M]^T X2[rows][N] per expert (+ db [E][M] = column sums of X1)
@@ -539,7 +554,7 @@ static int launch_wgrad(const void* X1, const void* X2, const int32_t* offsets, 
   if (e != cudaSuccess) return (int)e;
   const int S = wgrad_splits(E, M, N);
   float* pW = S > 1 ? ws : dW;
-  float* pb = S > 1 ? ws + (size_t)S * E * M * N : db;
+  float* pb = S > 1 ? ws + (size_t)S * E * M * N : ws;       // [S * N/BN][E][M]
   WGParams p{offsets, M, N, pW, pb, E};
   kern<<<dim3(M / BM, N / BN, E * S), kThreads, Cfg::SMEM, st>>>(t1, t2, p);
   M3_LAUNCH_CHECK();
@@ -547,10 +562,10 @@ static int launch_wgrad(const void* X1, const void* X2, const int32_t* offsets, 
     const int64_t n4 = (int64_t)E * M * N / 4;
     splitk_reduce_kernel<<<(int)((n4 + 255) / 256), 256, 0, st>>>(pW, S, n4, dW);
     M3_LAUNCH_CHECK();
-    const int64_t b4 = (int64_t)E * M / 4;
-    splitk_reduce_kernel<<<(int)((b4 + 255) / 256), 256, 0, st>>>(pb, S, b4, db);
-    M3_LAUNCH_CHECK();
   }
+  const int64_t b4 = (int64_t)E * M / 4;
+  splitk_reduce_kernel<<<(int)((b4 + 255) / 256), 256, 0, st>>>(pb, S * (N / BN), b4, db);
+  M3_LAUNCH_CHECK();
   return M3_OK;
 }
 

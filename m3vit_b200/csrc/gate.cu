@@ -431,39 +431,45 @@ __global__ void gate_bwd_dw_kernel(const XT* __restrict__ x, int64_t ldx, const 
 }
 
 // dW[d][e] = sum_chunks part (fixed order); task rows from the column sums of dz.
-// A block of 256 threads owns 32 consecutive outputs; its 8 warps stride over the chunks and
-// are combined in a fixed order (deterministic), so every output is summed 8-wide.
-__global__ void __launch_bounds__(256)
+// A block owns 32 consecutive outputs; its 32 warps stride over the chunks (coalesced 128-B
+// reads, many loads in flight) and are combined in a fixed order -> deterministic.
+__global__ void __launch_bounds__(1024)
 gate_bwd_reduce_kernel(const float* __restrict__ part, const float* __restrict__ cs_part, int nchunk, int D, int Dt,
                        int E, const float* __restrict__ task_feat, const float* __restrict__ w_gate,
                        float* __restrict__ dw, float* __restrict__ dtask) {
-  __shared__ float red[8][32];
+  __shared__ float red[32][33];
   __shared__ float cs_s[128];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int64_t n_main = (int64_t)D * E;
   const int64_t i = (int64_t)blockIdx.x * 32 + lane;
   if ((int64_t)blockIdx.x * 32 < n_main) {
-    float a = 0.f;
-    if (i < n_main)
-      for (int c = w; c < nchunk; c += 8) a += part[(int64_t)c * n_main + i];
-    red[w][lane] = a;
+    float a0 = 0.f, a1 = 0.f;
+    if (i < n_main) {
+      int c = w;
+      for (; c + 32 < nchunk; c += 64) {
+        a0 += part[(int64_t)c * n_main + i];
+        a1 += part[(int64_t)(c + 32) * n_main + i];
+      }
+      if (c < nchunk) a0 += part[(int64_t)c * n_main + i];
+    }
+    red[w][lane] = a0 + a1;
     __syncthreads();
     if (w == 0 && i < n_main) {
       float s = 0.f;
 #pragma unroll
-      for (int q = 0; q < 8; ++q) s += red[q][lane];
+      for (int q = 0; q < 32; ++q) s += red[q][lane];
       dw[i] = s;
     }
     return;
   }
-  // trailing block(s): task-feature rows.  column sums of dz first (E <= 128)
+  // trailing block: task-feature rows.  column sums of dz first (E <= 128)
   if (threadIdx.x < E) {
     float cs = 0.f;
     for (int c = 0; c < nchunk; ++c) cs += cs_part[(int64_t)c * E + threadIdx.x];
     cs_s[threadIdx.x] = cs;
   }
   __syncthreads();
-  for (int k = threadIdx.x; k < Dt * E + Dt; k += 256) {
+  for (int k = threadIdx.x; k < Dt * E + Dt; k += 1024) {
     if (k < Dt * E) {
       dw[n_main + k] = __ldg(task_feat + k / E) * cs_s[k % E];
     } else if (dtask != nullptr) {
@@ -617,7 +623,7 @@ extern "C" int m3_gate_bwd(const void* x, int x_dtype, int64_t ldx, const float*
   }
   {
     const int main_blocks = (int)(((int64_t)D * E + 31) / 32);
-    gate_bwd_reduce_kernel<<<main_blocks + (Dt > 0 ? 1 : 0), 256, 0, st>>>(part, cs_part, nchunk, D, Dt, E, task_feat,
+    gate_bwd_reduce_kernel<<<main_blocks + (Dt > 0 ? 1 : 0), 1024, 0, st>>>(part, cs_part, nchunk, D, Dt, E, task_feat,
                                                                           w_gate, dw_gate, dtask_feat);
     M3_LAUNCH_CHECK();
   }

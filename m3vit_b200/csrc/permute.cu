@@ -179,62 +179,107 @@ combine_bwd_kernel(const TG* __restrict__ g, Queue<const TQ> yq, const int32_t* 
   }
 }
 
-// dx[t] = sum_k dxq[pos[t,k]]  (+ dz[t] @ w_gate[:D]^T : the router's dx, gate input == layer input)
-// Grid-stride over 16-token batches.  With the router term, w_gate[:D] is staged ONCE per CTA
-// in shared memory, transposed to [E][D] so that the 16 lanes of a token read consecutive
-// 32-byte slices (conflict-free; the two tokens of a warp broadcast).
+// dx[t] = sum_k dxq[pos[t,k]]
 template <typename TI, typename TO, int NV, bool EP>
 __global__ void __launch_bounds__(kPermThreads)
-dispatch_bwd_kernel(Queue<const TI> dxq, const int32_t* __restrict__ pos, int T, int K, int D,
-                    const float* __restrict__ dz, const float* __restrict__ w_gate, int E,
-                    TO* __restrict__ dx) {
-  extern __shared__ __align__(16) float wt[];  // [E][D] (only when dz != nullptr)
-  if (dz != nullptr) {
-    for (int i = threadIdx.x; i < D * E; i += kPermThreads) {
-      const int d = i / E, e = i % E;           // coalesced read of w_gate[d][e]
-      wt[e * D + d] = __ldg(w_gate + i);
-    }
-    __syncthreads();
-  }
+dispatch_bwd_kernel(Queue<const TI> dxq, const int32_t* __restrict__ pos, int T, int K, int D, TO* __restrict__ dx) {
   const int sub = threadIdx.x % kLanesPerTok;
+  const int t = blockIdx.x * kTokPerCta + threadIdx.x / kLanesPerTok;
+  if (t >= T) return;
   const int nvec = D / 8;
-  for (int t = blockIdx.x * kTokPerCta + threadIdx.x / kLanesPerTok; t < T; t += gridDim.x * kTokPerCta) {
-    Vec8 acc[NV];
+  Vec8 acc[NV];
+#pragma unroll
+  for (int i = 0; i < NV; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[i].v[j] = 0.f;
+  for (int k = 0; k < K; ++k) {
+    const int row = __ldg(pos + (int64_t)t * K + k);
+    if (row < 0) continue;
+    const TI* src = dxq.template row<EP>((int64_t)t * K + k, row, D);
+    Vec8 v[NV];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int c = sub + i * kLanesPerTok;
+      if (c < nvec) v[i] = load8<TI>(src + c * 8);
+    }
 #pragma unroll
     for (int i = 0; i < NV; ++i)
 #pragma unroll
-      for (int j = 0; j < 8; ++j) acc[i].v[j] = 0.f;
+      for (int j = 0; j < 8; ++j) acc[i].v[j] += v[i].v[j];
+  }
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int c = sub + i * kLanesPerTok;
+    if (c < nvec) store8<TO>(dx + (int64_t)t * D + c * 8, acc[i]);
+  }
+}
+
+// Same, plus the router's dx:  dx[t] += dz[t] @ w_gate[:D]^T  (gate input == layer input).
+// w_gate[:D] is staged ONCE per CTA in shared memory, transposed to [E][D] so that the 16 lanes of
+// a token read consecutive 32-byte slices (conflict-free).  Every 16-lane group owns TWO tokens, so
+// each weight slice read from smem feeds two tokens (the kernel was smem-bound with one).
+template <typename TI, typename TO, int NV, bool EP>
+__global__ void __launch_bounds__(kPermThreads)
+dispatch_bwd_gate_kernel(Queue<const TI> dxq, const int32_t* __restrict__ pos, int T, int K, int D,
+                         const float* __restrict__ dz, const float* __restrict__ w_gate, int E,
+                         TO* __restrict__ dx) {
+  extern __shared__ __align__(16) float wt[];  // [E][D]
+  for (int i = threadIdx.x; i < D * E; i += kPermThreads) {
+    const int e = i / D, d = i % D;             // conflict-free smem writes; strided (L2-resident) reads
+    wt[i] = __ldg(w_gate + (int64_t)d * E + e);
+  }
+  __syncthreads();
+  const int sub = threadIdx.x % kLanesPerTok;
+  const int grp = threadIdx.x / kLanesPerTok;
+  const int nvec = D / 8;
+  for (int tb = blockIdx.x * (2 * kTokPerCta); tb < T; tb += gridDim.x * (2 * kTokPerCta)) {
+    const int t0 = tb + 2 * grp;
+    if (t0 >= T) continue;
+    const bool has1 = t0 + 1 < T;
+    const int t1 = has1 ? t0 + 1 : t0;
+    Vec8 a0[NV], a1[NV];
+#pragma unroll
+    for (int i = 0; i < NV; ++i)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { a0[i].v[j] = 0.f; a1[i].v[j] = 0.f; }
     for (int k = 0; k < K; ++k) {
-      const int row = __ldg(pos + (int64_t)t * K + k);
-      if (row < 0) continue;
-      const TI* src = dxq.template row<EP>((int64_t)t * K + k, row, D);
-      Vec8 v[NV];
+      const int r0 = __ldg(pos + (int64_t)t0 * K + k);
+      const int r1 = __ldg(pos + (int64_t)t1 * K + k);
+      Vec8 v0[NV], v1[NV];
 #pragma unroll
       for (int i = 0; i < NV; ++i) {
         const int c = sub + i * kLanesPerTok;
-        if (c < nvec) v[i] = load8<TI>(src + c * 8);
+        if (c < nvec) {
+          if (r0 >= 0) v0[i] = load8<TI>(dxq.template row<EP>((int64_t)t0 * K + k, r0, D) + c * 8);
+          if (r1 >= 0) v1[i] = load8<TI>(dxq.template row<EP>((int64_t)t1 * K + k, r1, D) + c * 8);
+        }
       }
 #pragma unroll
       for (int i = 0; i < NV; ++i)
 #pragma unroll
-        for (int j = 0; j < 8; ++j) acc[i].v[j] += v[i].v[j];
+        for (int j = 0; j < 8; ++j) {
+          if (r0 >= 0) a0[i].v[j] += v0[i].v[j];
+          if (r1 >= 0) a1[i].v[j] += v1[i].v[j];
+        }
     }
-    if (dz != nullptr) {
-      for (int e = 0; e < E; e += 4) {
-        const float4 gz4 = __ldg(reinterpret_cast<const float4*>(dz + (int64_t)t * E + e));
-        const float gz[4] = {gz4.x, gz4.y, gz4.z, gz4.w};
+    for (int e = 0; e < E; e += 4) {
+      const float4 g0 = __ldg(reinterpret_cast<const float4*>(dz + (int64_t)t0 * E + e));
+      const float4 g1 = __ldg(reinterpret_cast<const float4*>(dz + (int64_t)t1 * E + e));
+      const float z0[4] = {g0.x, g0.y, g0.z, g0.w};
+      const float z1[4] = {g1.x, g1.y, g1.z, g1.w};
 #pragma unroll
-        for (int ee = 0; ee < 4; ++ee) {
+      for (int ee = 0; ee < 4; ++ee) {
 #pragma unroll
-          for (int i = 0; i < NV; ++i) {
-            const int c = sub + i * kLanesPerTok;
-            if (c < nvec) {
-              const float4 w0 = *reinterpret_cast<const float4*>(wt + (e + ee) * D + c * 8);
-              const float4 w1 = *reinterpret_cast<const float4*>(wt + (e + ee) * D + c * 8 + 4);
-              acc[i].v[0] = fmaf(gz[ee], w0.x, acc[i].v[0]); acc[i].v[1] = fmaf(gz[ee], w0.y, acc[i].v[1]);
-              acc[i].v[2] = fmaf(gz[ee], w0.z, acc[i].v[2]); acc[i].v[3] = fmaf(gz[ee], w0.w, acc[i].v[3]);
-              acc[i].v[4] = fmaf(gz[ee], w1.x, acc[i].v[4]); acc[i].v[5] = fmaf(gz[ee], w1.y, acc[i].v[5]);
-              acc[i].v[6] = fmaf(gz[ee], w1.z, acc[i].v[6]); acc[i].v[7] = fmaf(gz[ee], w1.w, acc[i].v[7]);
+        for (int i = 0; i < NV; ++i) {
+          const int c = sub + i * kLanesPerTok;
+          if (c < nvec) {
+            const float4 wa = *reinterpret_cast<const float4*>(wt + (e + ee) * D + c * 8);
+            const float4 wb = *reinterpret_cast<const float4*>(wt + (e + ee) * D + c * 8 + 4);
+            const float w8[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              a0[i].v[j] = fmaf(z0[ee], w8[j], a0[i].v[j]);
+              a1[i].v[j] = fmaf(z1[ee], w8[j], a1[i].v[j]);
             }
           }
         }
@@ -243,7 +288,10 @@ dispatch_bwd_kernel(Queue<const TI> dxq, const int32_t* __restrict__ pos, int T,
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
       const int c = sub + i * kLanesPerTok;
-      if (c < nvec) store8<TO>(dx + (int64_t)t * D + c * 8, acc[i]);
+      if (c < nvec) {
+        store8<TO>(dx + (int64_t)t0 * D + c * 8, a0[i]);
+        if (has1) store8<TO>(dx + (int64_t)t1 * D + c * 8, a1[i]);
+      }
     }
   }
 }
@@ -344,27 +392,30 @@ static int dispatch_bwd_impl(const void* dxq, void* const* peer, const int32_t* 
   if (rc) return rc;
   if (T == 0) return M3_OK;
   const int nv = perm_nv(D);
-  int grid = m3_ceil_div(T, kTokPerCta);
-  size_t smem = 0;
-  if (dz != nullptr) {
-    // router term: stage w_gate[:D] once per CTA -> fewer, grid-striding CTAs
-    smem = (size_t)D * E * sizeof(float);
-    if (smem > 200 * 1024) return M3_ERR_SHAPE;
-    const int per_sm = smem > 0 ? (int)((200 * 1024) / smem) : 8;
-    const int cap = kNumSMs * (per_sm < 1 ? 1 : (per_sm > 6 ? 6 : per_sm));
-    if (grid > cap) grid = cap;
-  }
-  M3_DTYPE2_SWITCH(dxq_dtype, dx_dtype, {
-    Queue<const TA> q{(const TA*)dxq, (const TA* const*)peer, slot_rank};
-    M3_NV_SWITCH({
-      auto kern = dispatch_bwd_kernel<TA, TB, NV, EP>;
-      if (smem > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return (int)e;
-      }
-      kern<<<grid, kPermThreads, smem, st>>>(q, pos, T, K, D, dz, w_gate, E, (TB*)dx);
+  if (dz == nullptr) {
+    const int grid = m3_ceil_div(T, kTokPerCta);
+    M3_DTYPE2_SWITCH(dxq_dtype, dx_dtype, {
+      Queue<const TA> q{(const TA*)dxq, (const TA* const*)peer, slot_rank};
+      M3_NV_SWITCH((dispatch_bwd_kernel<TA, TB, NV, EP><<<grid, kPermThreads, 0, st>>>(q, pos, T, K, D, (TB*)dx)))
     })
-  })
+  } else {
+    // router term: w_gate[:D]^T staged once per CTA -> few, grid-striding CTAs (2 per SM)
+    const size_t smem = (size_t)D * E * sizeof(float);
+    if (smem > 100 * 1024) return M3_ERR_SHAPE;
+    int grid = m3_ceil_div(T, 2 * kTokPerCta);
+    if (grid > 2 * kNumSMs) grid = 2 * kNumSMs;
+    M3_DTYPE2_SWITCH(dxq_dtype, dx_dtype, {
+      Queue<const TA> q{(const TA*)dxq, (const TA* const*)peer, slot_rank};
+      M3_NV_SWITCH({
+        auto kern = dispatch_bwd_gate_kernel<TA, TB, NV, EP>;
+        if (smem > 48 * 1024) {
+          cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+          if (e != cudaSuccess) return (int)e;
+        }
+        kern<<<grid, kPermThreads, smem, st>>>(q, pos, T, K, D, dz, w_gate, E, (TB*)dx);
+      })
+    })
+  }
   M3_LAUNCH_CHECK();
   return M3_OK;
 }
