@@ -289,7 +289,7 @@ struct WGParams {
   const int32_t* offsets;
   int M, N;       // dW_e is [M][N]; X1 is [rows][M], X2 is [rows][N]
   float* dW;      // [S][E][M][N]  (S = gridDim.z / E row-splits; S == 1: the final gradient)
-  float* db;      // [S*NT][E][M] partial column sums of X1 (bias gradient), NT = gridDim.y n-tile CTAs
+  float* db;      // [S][E][M] column sums of X1 over the split's rows (bias gradient)
   int E;
 };
 
@@ -298,11 +298,12 @@ struct WGCfg {
   static constexpr int A_BYTES = BK * BM * 2;   // 2 boxes of [64 rows][64 cols]
   static constexpr int B_BYTES = BK * BN * 2;   // BN/64 boxes
   static constexpr int BOX = BK * 64 * 2;       // 8192 B
-  static constexpr int STAGE = A_BYTES + B_BYTES;
-  static constexpr int STAGES = (BN <= 128) ? 6 : 4;
-  static constexpr int TMEM_COLS = 256;         // BN accumulator columns + 16 for the bias-grad MMA
-  static constexpr int ONES_BYTES = BK * 64 * 2;  // [64 k][64 n] box of bf16 ones
-  static constexpr int SMEM = STAGES * STAGE + ONES_BYTES + 1024 + 256;
+  static constexpr int ONES_BYTES = BK * 64 * 2;  // [64 k][64 n] box of bf16 ones, one per stage, right behind B:
+  static constexpr int TMA_BYTES = A_BYTES + B_BYTES;          // what TMA delivers per stage
+  static constexpr int STAGE = TMA_BYTES + ONES_BYTES;         // B | ones is ONE contiguous MN-major operand
+  static constexpr int STAGES = (BN <= 128) ? 5 : 3;
+  static constexpr int TMEM_COLS = 256;         // BN accumulator columns + 16 bias-gradient columns
+  static constexpr int SMEM = STAGES * STAGE + 1024 + 256;
   static_assert(BN + 16 <= TMEM_COLS, "TMEM");
 };
 
@@ -313,8 +314,7 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tm1, const __grid_constant__ CU
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* ones = smem + STAGES * Cfg::STAGE;
-  uint64_t* full = reinterpret_cast<uint64_t*>(ones + Cfg::ONES_BYTES);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE);
   uint64_t* empty = full + STAGES;
   uint64_t* tfull = empty + STAGES;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tfull + 1);
@@ -324,13 +324,15 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tm1, const __grid_constant__ CU
   // 64-row chunks, partial results are reduced in a fixed order afterwards (deterministic)
   const int e = blockIdx.z % p.E, split = blockIdx.z / p.E, nsplit = gridDim.z / p.E;
   const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
-  // db = X1^T * 1 as an extra N=16 MMA per k-step against a tile of ones.  The NT CTAs that share
-  // (m0, e, split) each take every NT-th k-chunk, so no CTA is slower than its neighbours; the
-  // S*NT partial vectors are reduced afterwards in a fixed order.
-  const bool with_db = p.db != nullptr;
-  const int nt = gridDim.y, my_nt = blockIdx.y;
+  // db = X1^T * 1: the n0 == 0 CTAs widen their MMA from N = BN to N = BN + 16, the extra 16
+  // B columns being a box of ones that sits right behind the B boxes of every stage (an extra MMA
+  // would re-read the whole A tile from smem and cost as much as the main one).
+  const bool with_db = (blockIdx.y == 0) && (p.db != nullptr);
   if (with_db) {
-    for (int i = threadIdx.x; i < Cfg::ONES_BYTES / 4; i += kThreads) reinterpret_cast<uint32_t*>(ones)[i] = 0x3F803F80u;
+    for (int st = 0; st < STAGES; ++st) {
+      uint32_t* ones = reinterpret_cast<uint32_t*>(smem + st * Cfg::STAGE + Cfg::TMA_BYTES);
+      for (int i = threadIdx.x; i < Cfg::ONES_BYTES / 4; i += kThreads) ones[i] = 0x3F803F80u;
+    }
     fence_proxy_async_smem();
   }
   if (warp == 0 && lane == 0) { tma_prefetch_desc(&tm1); tma_prefetch_desc(&tm2); }
@@ -359,7 +361,7 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tm1, const __grid_constant__ CU
       uint32_t phase = 0;
       for (int kc = 0; kc < kchunks; ++kc) {
         mbar_wait(&empty[stage], phase ^ 1);
-        mbar_expect_tx(&full[stage], Cfg::STAGE);
+        mbar_expect_tx(&full[stage], Cfg::TMA_BYTES);
         uint8_t* sa = smem + stage * Cfg::STAGE;
         const int r = r0 + kc * BK;
 #pragma unroll
@@ -372,9 +374,7 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tm1, const __grid_constant__ CU
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16(BM, BN, 1, 1);
-      constexpr uint32_t idesc_db = make_idesc_bf16(BM, 16, 1, 1);
-      const uint32_t ones_base = smem_u32(ones);
+      const uint32_t idesc = with_db ? make_idesc_bf16(BM, BN + 16, 1, 1) : make_idesc_bf16(BM, BN, 1, 1);
       int stage = 0;
       uint32_t phase = 0;
       for (int kc = 0; kc < kchunks; ++kc) {
@@ -388,10 +388,6 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tm1, const __grid_constant__ CU
           const uint64_t adesc = make_smem_desc(a_base + k * 2048, Cfg::BOX, 1024);
           const uint64_t bdesc = make_smem_desc(b_base + k * 2048, Cfg::BOX, 1024);
           umma_bf16(tmem_base, adesc, bdesc, idesc, (kc | k) != 0);
-          if (with_db && (kc % nt) == my_nt) {
-            const uint64_t odesc = make_smem_desc(ones_base + k * 2048, Cfg::BOX, 1024);
-            umma_bf16(tmem_base + BN, adesc, odesc, idesc_db, (kc >= nt) || (k != 0));
-          }
         }
         umma_commit(&empty[stage]);
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -402,8 +398,7 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tm1, const __grid_constant__ CU
     const int q = warp & 3;
     const int row = m0 + q * 32 + lane;
     const int64_t se = (int64_t)split * p.E + e;
-    const int64_t sbe = ((int64_t)split * nt + my_nt) * p.E + e;     // db partial index
-    const bool db_any = with_db && kchunks > my_nt;                   // this CTA issued at least one db MMA
+    const int64_t sbe = se;                                           // db partial index [S][E][M]
     float* dst = p.dW + (se * p.M + row) * p.N + n0;
     if (kchunks == 0) {  // expert received no rows: dW_e = 0
 #pragma unroll 1
@@ -423,7 +418,7 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tm1, const __grid_constant__ CU
       if (with_db) {
         float v[32];   // 16 identical columns (+16 unused): every column of X1^T * ones is the column sum
         tmem_ld_32x32(tmem_base + BN + ((uint32_t)(q * 32) << 16), v);
-        p.db[sbe * p.M + row] = db_any ? v[0] : 0.f;
+        p.db[sbe * p.M + row] = v[0];
       }
     }
   }
@@ -535,7 +530,7 @@ static int wgrad_splits(int E, int M, int N) {
 }
 static size_t wgrad_ws_bytes(int E, int M, int N) {
   const int S = wgrad_splits(E, M, N);
-  return ((S > 1 ? (size_t)S * E * M * N : 0) + (size_t)S * (N / 128) * E * M) * sizeof(float);
+  return S > 1 ? (size_t)S * E * ((size_t)M * N + M) * sizeof(float) : 0;
 }
 
 // dW [E][M][N] fp32 = X1[rows][M]^T X2[rows][N] per expert (+ db [E][M] = column sums of X1)
@@ -554,7 +549,7 @@ static int launch_wgrad(const void* X1, const void* X2, const int32_t* offsets, 
   if (e != cudaSuccess) return (int)e;
   const int S = wgrad_splits(E, M, N);
   float* pW = S > 1 ? ws : dW;
-  float* pb = S > 1 ? ws + (size_t)S * E * M * N : ws;       // [S * N/BN][E][M]
+  float* pb = S > 1 ? ws + (size_t)S * E * M * N : db;
   WGParams p{offsets, M, N, pW, pb, E};
   kern<<<dim3(M / BM, N / BN, E * S), kThreads, Cfg::SMEM, st>>>(t1, t2, p);
   M3_LAUNCH_CHECK();
@@ -562,10 +557,10 @@ static int launch_wgrad(const void* X1, const void* X2, const int32_t* offsets, 
     const int64_t n4 = (int64_t)E * M * N / 4;
     splitk_reduce_kernel<<<(int)((n4 + 255) / 256), 256, 0, st>>>(pW, S, n4, dW);
     M3_LAUNCH_CHECK();
+    const int64_t b4 = (int64_t)E * M / 4;
+    splitk_reduce_kernel<<<(int)((b4 + 255) / 256), 256, 0, st>>>(pb, S, b4, db);
+    M3_LAUNCH_CHECK();
   }
-  const int64_t b4 = (int64_t)E * M / 4;
-  splitk_reduce_kernel<<<(int)((b4 + 255) / 256), 256, 0, st>>>(pb, S * (N / BN), b4, db);
-  M3_LAUNCH_CHECK();
   return M3_OK;
 }
 

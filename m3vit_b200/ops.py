@@ -261,7 +261,8 @@ def ffn_bwd(xq, hpre, dyq, plan: Plan, w1, w2, w1t=None, w2t=None):
         tiles = (D // 128) * (H // 128) * E          # mirrors wgrad_splits() in ffn_bf16.cu
         splits = min(16, max(1, 148 // tiles))
         _count("ffn_bwd_bf16")                       # 2 gg + 2 wgrad
-        _count("cast_weights", 2 + (2 if splits > 1 else 0))   # db partial reduces (+ dW split-K reduces)
+        if splits > 1:
+            _count("cast_weights", 4)                # 2 x (dW + db) split-K reduce launches
     else:
         _count("ffn_bwd_f32")
     return dxq, dw1, db1, dw2, db2
