@@ -221,7 +221,7 @@ def main():
         from m3vit_b200 import ep
         assert N_EXP % world == 0
         el = 2 if cdt == torch.bfloat16 else 4
-        q_bytes = ((int(args.capacity_factor * T * TOP_K) + (N_EXP // world) * 127 + 127) // 128 * 128) * D_MODEL * el
+        q_bytes = ((int(args.capacity_factor * T * TOP_K) + (N_EXP // world) * 255 + 255) // 256 * 256) * D_MODEL * el
         ep_ctx = ep.make_context(ep.TorchDistGroup(), dev, arena_bytes=6 * (q_bytes + 4096),
                                  capacity_factor=args.capacity_factor)
     layers = build_layers(dev, cdt, rank, world, ep_ctx)
@@ -336,7 +336,7 @@ def kernel_rooflines(layer, x, dev, cdt, pk, iters=20):
     else:
         w1c, w2c, w1t, w2t = w1, w2, None, None
     g = ops.gate_fwd(x, wg, K)
-    plan = ops.route_plan(g.idx, E, 128, g.imp_partial, g.load_partial)
+    plan = ops.route_plan(g.idx, E, imp_partial=g.imp_partial, load_partial=g.load_partial)
     xq = ops.dispatch_fwd(x, plan, K, out_dtype=cdt)
     yq, hpre = ops.ffn_fwd(xq, plan, w1c, b1, w2c, b2)
     go = torch.randn(T, D, device=dev)
@@ -371,7 +371,7 @@ def kernel_rooflines(layer, x, dev, cdt, pk, iters=20):
         st[name] = d
 
     add("gate_fwd", lambda: ops.gate_fwd(x, wg, K), 1, nbytes=T * D * 4 + T * (E * 4 + K * 16 + (K + 1) * 8))
-    add("route_plan", lambda: ops.route_plan(g.idx, E, 128, g.imp_partial, g.load_partial), 2, nbytes=R * (8 + 8 + 4))
+    add("route_plan", lambda: ops.route_plan(g.idx, E, imp_partial=g.imp_partial, load_partial=g.load_partial), 2, nbytes=R * (8 + 8 + 4))
     add("dispatch_fwd", lambda: ops.dispatch_fwd(x, plan, K, out_dtype=cdt), 1, nbytes=T * (D * 4 + K * D * el + K * 4))
     add("ffn_fwd", lambda: ops.ffn_fwd(xq, plan, w1c, b1, w2c, b2), 2, flops=4.0 * R * D * H)
     add("combine_fwd", lambda: ops.combine_fwd(yq, plan, g.score), 1, nbytes=T * (K * D * el + K * 8 + D * 4))

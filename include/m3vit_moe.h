@@ -17,7 +17,7 @@
  *   - activations may be fp32 or bf16 (m3_dtype); router math is always fp32.
  *   - expert queues use the PADDED layout: expert e owns rows
  *     [offsets[e], offsets[e]+counts[e]) of the queue buffer, offsets[] is a
- *     multiple of `pad` (128 for the tensor-core path); padding rows are zero.
+ *     multiple of `pad` (M3_PAD_ROWS for the tensor-core path); padding rows are zero.
  *
  * Symbols T tokens, K top-k, E total experts, D model dim, Dt task-feature dim
  * (0 if none), Dg = D + Dt router input dim, H expert hidden dim, K1 = min(K+1,E).
@@ -33,7 +33,7 @@ extern "C" {
 #endif
 
 #define M3_ABI_VERSION 1
-#define M3_PAD_ROWS 128 /* queue padding / M-tile of the grouped GEMM */
+#define M3_PAD_ROWS 256 /* queue padding = M-tile of a CTA pair (cta_group::2) in the grouped GEMM */
 
 typedef void* m3_stream_t; /* cudaStream_t */
 

@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "lib", "libm3vit_moe.so")
 
 M3_F32, M3_BF16 = 0, 1
-PAD_ROWS = 128
+PAD_ROWS = 256     # expert queues are padded to the 256-row CTA-pair tile of the tensor-core GEMM
 
 _p = C.c_void_p
 _i = C.c_int

@@ -39,17 +39,19 @@ struct GGParams {
   int E, N, Kd;
   const float* bias;           // [E][N]   (EPI_BIAS, EPI_FC1)
   int save_out2;               // EPI_FC1: also store the pre-activation (training)
+  __nv_bfloat16* out;          // [rows][N]
+  __nv_bfloat16* out2;         // EPI_FC1: hpre   EPI_DGELU: h = gelu(hpre)
 };
 
 constexpr int WBOX_BYTES = 32 * 64 * 2;  // one warp's [32 rows][64 bf16] swizzle-128B box = 4 KB
 
-template <int BN, int EPI>
+template <int BN, int EPI, int NCTA>
 struct GGCfg {
   static constexpr int A_BYTES = BM * BK * 2;
-  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int B_BYTES = (BN / NCTA) * BK * 2;      // a CTA pair splits the B tile
   static constexpr int STAGE = A_BYTES + B_BYTES;
   // epilogue staging: one private 4 KB box per epilogue warp per output tensor (+ per TMA-loaded aux input)
-  static constexpr int N_OUT = (EPI == EPI_FC1 || EPI == EPI_DGELU) ? 2 : 1;
+  static constexpr int N_OUT = 1;                            // outputs share one transpose box, flushed in turn
   static constexpr int N_AUX = (EPI == EPI_DGELU) ? 1 : 0;
   static constexpr int WARP_STAGING = (N_OUT + N_AUX) * WBOX_BYTES;
   static constexpr int STAGING = kEpiWarps * WARP_STAGING;
@@ -72,12 +74,15 @@ __device__ __forceinline__ f32x2 unpack_bf16x2(uint32_t u) {
 // 16-byte chunk c (0..7) of row r inside a [rows][64 bf16] swizzle-128B box (what TMA reads / writes)
 __device__ __forceinline__ uint32_t box_off(int r, int c) { return (uint32_t)r * 128u + (uint32_t)((c ^ (r & 7)) << 4); }
 
-template <int BN, int EPI>
+template <int BN, int EPI, int NCTA>
 __global__ void __launch_bounds__(kGGThreads, 1)
 gg_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
           const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmOut2,
           const __grid_constant__ CUtensorMap tmAux, GGParams p) {
-  using Cfg = GGCfg<BN, EPI>;
+  using Cfg = GGCfg<BN, EPI, NCTA>;
+  // NCTA == 2: CTA pair (cluster of 2) sharing one 256 x BN MMA tile, see tc_common.cuh
+  const uint32_t cta_rank = NCTA == 2 ? cluster_ctarank() : 0u;
+  const bool leader_cta = cta_rank == 0;
   constexpr int STAGES = Cfg::STAGES;
   constexpr int NB = BN / 64;  // 64-column boxes per tile
   extern __shared__ uint8_t smem_raw[];
@@ -94,51 +99,65 @@ gg_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
-    tma_prefetch_desc(&tmOut);
   }
   if (warp == 1) {
     if (lane == 0) {
-      for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-      for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 4 * 32); }
+      for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], NCTA); mbar_init(&empty[s], 1); }
+      for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], NCTA * 4 * 32); }
       for (int w = 0; w < kEpiWarps; ++w) mbar_init(&aux_full[w], 1);
       fence_barrier_init();
     }
     __syncwarp();
-    tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
+    if (NCTA == 2) tmem_alloc_2sm<Cfg::TMEM_COLS>(tmem_slot);
+    else tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
   }
   tcgen05_fence_before();
-  __syncthreads();
+  if (NCTA == 2) cluster_sync(); else __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
+  // Tile schedule: a "unit" (CTA or CTA pair) walks pair-tiles pt = unit, unit + n_units, ...;
+  // pair-tile pt covers M-tiles (pt / n_tiles) * NCTA + cta_rank (queues are padded to NCTA*128 rows,
+  // so both halves of a pair belong to the same expert) and N-tile pt % n_tiles.
   const int n_tiles = p.N / BN;
   const int m_tiles = p.offsets[p.E] / BM;
-  const int total = m_tiles * n_tiles;
+  const int total = (m_tiles / NCTA) * n_tiles;
   const int kchunks = p.Kd / BK;
+  const int unit = blockIdx.x / NCTA, n_units = gridDim.x / NCTA;
 
   if (warp == 0) {
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
-        const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
-        const int e = p.tile_expert[m_blk];
+      for (int tile = unit; tile < total; tile += n_units) {
+        const int m_blk = (tile / n_tiles) * NCTA + (int)cta_rank, n_blk = tile % n_tiles;
+        const int e = p.tile_expert[(m_blk * BM) / M3_PAD_ROWS];
+        const int b_row = e * p.N + n_blk * BN + (int)cta_rank * (BN / NCTA);
         for (int kc = 0; kc < kchunks; ++kc) {
           mbar_wait(&empty[stage], phase ^ 1);
-          mbar_expect_tx(&full[stage], Cfg::STAGE);
           uint8_t* sa = smem + stage * Cfg::STAGE;
-          tma_load_2d(sa, &tmA, &full[stage], kc * BK, m_blk * BM);
-          tma_load_2d(sa + Cfg::A_BYTES, &tmB, &full[stage], kc * BK, e * p.N + n_blk * BN);
+          if (NCTA == 2) {
+            // both CTAs' bytes are accounted on the LEADER's full barrier
+            const uint32_t bar = mapa_u32(smem_u32(&full[stage]), 0);
+            if (leader_cta) mbar_expect_tx(&full[stage], Cfg::STAGE * NCTA);
+            else mbar_arrive_remote(bar);
+            tma_load_2d_2sm(sa, &tmA, bar, kc * BK, m_blk * BM);
+            tma_load_2d_2sm(sa + Cfg::A_BYTES, &tmB, bar, kc * BK, b_row);
+          } else {
+            mbar_expect_tx(&full[stage], Cfg::STAGE);
+            tma_load_2d(sa, &tmA, &full[stage], kc * BK, m_blk * BM);
+            tma_load_2d(sa + Cfg::A_BYTES, &tmB, &full[stage], kc * BK, b_row);
+          }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16(BM, BN, 0, 0);
+    if (lane == 0 && leader_cta) {
+      constexpr uint32_t idesc = make_idesc_bf16(BM * NCTA, BN, 0, 0);
       int stage = 0;
       uint32_t phase = 0, acc = 0, acc_phase = 0;
-      for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
+      for (int tile = unit; tile < total; tile += n_units) {
         mbar_wait(&tempty[acc], acc_phase ^ 1);
         tcgen05_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN;
@@ -151,12 +170,15 @@ gg_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
           for (int k = 0; k < BK / UMMA_K; ++k) {
             const uint64_t adesc = make_smem_desc(a_base + k * UMMA_K * 2, 0, 1024);
             const uint64_t bdesc = make_smem_desc(b_base + k * UMMA_K * 2, 0, 1024);
-            umma_bf16(d_tmem, adesc, bdesc, idesc, (kc | k) != 0);
+            if (NCTA == 2) umma_bf16_2sm(d_tmem, adesc, bdesc, idesc, (kc | k) != 0);
+            else umma_bf16(d_tmem, adesc, bdesc, idesc, (kc | k) != 0);
           }
-          umma_commit(&empty[stage]);  // frees the smem stage once these MMAs have read it
+          // frees the smem stage (in both CTAs of a pair) once these MMAs have read it
+          if (NCTA == 2) umma_commit_2sm(&empty[stage], 3); else umma_commit(&empty[stage]);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        umma_commit(&tfull[acc]);  // accumulator complete -> epilogue
+        // accumulator complete -> epilogue warps (of both CTAs)
+        if (NCTA == 2) umma_commit_2sm(&tfull[acc], 3); else umma_commit(&tfull[acc]);
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1;
       }
@@ -171,21 +193,33 @@ gg_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
     const int ew = warp - 2;                     // 0..7
     const uint32_t grp = (uint32_t)ew >> 2;      // accumulator buffer served
     uint8_t* my = stg + ew * Cfg::WARP_STAGING;
-    uint8_t* o1 = my;
-    uint8_t* o2 = my + WBOX_BYTES;
-    uint8_t* ax = my + 2 * WBOX_BYTES;
+    uint8_t* box = my;                     // [32 rows][64 bf16] transpose box (swizzled, conflict-free both ways)
+    uint8_t* ax = my + WBOX_BYTES;
     uint64_t* my_aux = &aux_full[ew];
-    const bool two_out = (EPI == EPI_DGELU) || (EPI == EPI_FC1 && p.save_out2);
+    // registers -> swizzled box (one row per lane) -> coalesced 128-B row segments in global memory.
+    // Plain st.global: fire-and-forget, so the box is reusable right away (a TMA store would have to
+    // drain first, and that latency set the tile period through the 2-deep TMEM pipeline).
+    auto flush = [&](__nv_bfloat16* dst, int row0, int col) {
+      __syncwarp();
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int rr = i * 4 + (lane >> 3), ch = lane & 7;
+        const uint4 u = *reinterpret_cast<const uint4*>(box + box_off(rr, ch));
+        stg_stream(dst + (int64_t)(row0 + rr) * p.N + col + ch * 8, u);
+      }
+      __syncwarp();
+    };
     uint32_t aux_uses = 0;
-    const int first = blockIdx.x + (int)grp * gridDim.x;
+    const int first = unit + (int)grp * n_units;
+    const uint32_t tempty_remote = NCTA == 2 ? mapa_u32(smem_u32(&tempty[grp]), 0) : 0u;
     if (EPI == EPI_DGELU && lane == 0 && first < total) {
       mbar_expect_tx(my_aux, WBOX_BYTES);
-      tma_load_2d(ax, &tmAux, my_aux, (first % n_tiles) * BN, (first / n_tiles) * BM + q * 32);
+      tma_load_2d(ax, &tmAux, my_aux, (first % n_tiles) * BN, ((first / n_tiles) * NCTA + (int)cta_rank) * BM + q * 32);
     }
     uint32_t it = grp;
-    for (int tile = first; tile < total; tile += 2 * gridDim.x, it += 2) {
-      const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
-      const int e = p.tile_expert[m_blk];
+    for (int tile = first; tile < total; tile += 2 * n_units, it += 2) {
+      const int m_blk = (tile / n_tiles) * NCTA + (int)cta_rank, n_blk = tile % n_tiles;
+      const int e = p.tile_expert[(m_blk * BM) / M3_PAD_ROWS];
       const int row0 = m_blk * BM + q * 32;
       mbar_wait(&tfull[grp], (it >> 1) & 1);
       tcgen05_fence_after();
@@ -198,7 +232,8 @@ gg_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         tmem_ld_32x32(taddr + 32, v + 32);
         if (cb == NB - 1) {  // last TMEM read of this accumulator: hand it back to the MMA warp early
           tcgen05_fence_before();
-          mbar_arrive(&tempty[grp]);
+          if (NCTA == 2 && !leader_cta) mbar_arrive_remote(tempty_remote);   // the MMA issuer lives in the leader CTA
+          else mbar_arrive(&tempty[grp]);
         }
         f32x2 w2[32];
 #pragma unroll
@@ -212,9 +247,6 @@ gg_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
             w2[2 * j + 1] = add2(w2[2 * j + 1], pk2(b.z, b.w));
           }
         }
-        // the previous box's TMA stores must have drained this warp's staging boxes
-        if (lane == 0) tma_store_wait_read<0>();
-        __syncwarp();
         if (EPI == EPI_FC1) {
           if (p.save_out2) {
 #pragma unroll
@@ -222,8 +254,9 @@ gg_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
               uint4 u;
               u.x = pack_bf16x2(w2[4 * c]); u.y = pack_bf16x2(w2[4 * c + 1]);
               u.z = pack_bf16x2(w2[4 * c + 2]); u.w = pack_bf16x2(w2[4 * c + 3]);
-              *reinterpret_cast<uint4*>(o2 + box_off(lane, c)) = u;
+              *reinterpret_cast<uint4*>(box + box_off(lane, c)) = u;
             }
+            flush(p.out2, row0, col);
           }
 #pragma unroll
           for (int j = 0; j < 32; ++j) w2[j] = gelu_fast2(w2[j]);
@@ -237,10 +270,11 @@ gg_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
           __syncwarp();
           if (lane == 0) {  // aux box consumed into registers: prefetch the next one behind the math
             int nt = tile, ncb = cb + 1;
-            if (ncb == NB) { ncb = 0; nt += 2 * gridDim.x; }
+            if (ncb == NB) { ncb = 0; nt += 2 * n_units; }
             if (nt < total) {
               mbar_expect_tx(my_aux, WBOX_BYTES);
-              tma_load_2d(ax, &tmAux, my_aux, (nt % n_tiles) * BN + ncb * 64, (nt / n_tiles) * BM + q * 32);
+              tma_load_2d(ax, &tmAux, my_aux, (nt % n_tiles) * BN + ncb * 64,
+                          ((nt / n_tiles) * NCTA + (int)cta_rank) * BM + q * 32);
             }
           }
 #pragma unroll
@@ -254,32 +288,27 @@ gg_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
               w2[4 * c + i] = mul2(w2[4 * c + i], gr);
               ho[i] = pack_bf16x2(gl);
             }
-            *reinterpret_cast<uint4*>(o2 + box_off(lane, c)) = make_uint4(ho[0], ho[1], ho[2], ho[3]);   // h = gelu(hpre)
+            *reinterpret_cast<uint4*>(box + box_off(lane, c)) = make_uint4(ho[0], ho[1], ho[2], ho[3]);   // h = gelu(hpre)
           }
+          flush(p.out2, row0, col);
         }
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
           uint4 u;
           u.x = pack_bf16x2(w2[4 * c]); u.y = pack_bf16x2(w2[4 * c + 1]);
           u.z = pack_bf16x2(w2[4 * c + 2]); u.w = pack_bf16x2(w2[4 * c + 3]);
-          *reinterpret_cast<uint4*>(o1 + box_off(lane, c)) = u;
+          *reinterpret_cast<uint4*>(box + box_off(lane, c)) = u;
         }
-        fence_proxy_async_smem();
-        __syncwarp();
-        if (lane == 0) {
-          tma_store_2d(&tmOut, o1, col, row0);
-          if (two_out) tma_store_2d(&tmOut2, o2, col, row0);
-          tma_store_commit();
-        }
+        flush(p.out, row0, col);
       }
     }
-    if (lane == 0) tma_store_wait_read<0>();
   }
   tcgen05_fence_before();
-  __syncthreads();
+  if (NCTA == 2) cluster_sync(); else __syncthreads();     // a pair's smem / TMEM stay alive until both are done
   if (warp == 1) {
     __syncwarp();
-    tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+    if (NCTA == 2) tmem_dealloc_2sm<Cfg::TMEM_COLS>(tmem_base);
+    else tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
   }
 }
 
@@ -469,15 +498,31 @@ static int pick_bn(int N, bool heavy_epilogue) {
   return N % 128 == 0 ? 128 : 0;
 }
 
+constexpr int kGGNcta = 2;   // CTA pairs: halves the per-SM weight traffic (the GEMMs are L2 -> SM bound at K = 384)
+
 template <int BN, int EPI>
 static int launch_gg_t(const CUtensorMap* maps, const GGParams& p, int max_tiles, cudaStream_t st) {
-  using Cfg = GGCfg<BN, EPI>;
-  auto kern = gg_kernel<BN, EPI>;
+  using Cfg = GGCfg<BN, EPI, kGGNcta>;
+  auto kern = gg_kernel<BN, EPI, kGGNcta>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
   if (e != cudaSuccess) return (int)e;
   int grid = max_tiles < kNumSMs ? max_tiles : kNumSMs;
-  if (grid < 1) grid = 1;
-  kern<<<grid, kGGThreads, Cfg::SMEM, st>>>(maps[0], maps[1], maps[2], maps[3], maps[4], p);
+  grid = grid / kGGNcta * kGGNcta;
+  if (grid < kGGNcta) grid = kGGNcta;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(kGGThreads);
+  cfg.dynamicSmemBytes = Cfg::SMEM;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = kGGNcta;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  e = cudaLaunchKernelEx(&cfg, kern, maps[0], maps[1], maps[2], maps[3], maps[4], p);
+  if (e != cudaSuccess) return (int)e;
   M3_LAUNCH_CHECK();
   return M3_OK;
 }
@@ -488,11 +533,11 @@ static int launch_gg(const void* A, const void* B, void* out, void* out2, const 
                      cudaStream_t st) {
   constexpr bool heavy = (EPI == EPI_FC1 || EPI == EPI_DGELU);
   const int BN = pick_bn(p.N, heavy);
-  if (BN == 0 || p.Kd % BK != 0 || cap_rows % BM != 0) return M3_ERR_SHAPE;
+  if (BN == 0 || p.Kd % BK != 0 || cap_rows % (BM * kGGNcta) != 0) return M3_ERR_SHAPE;
   CUtensorMap maps[5];
   int rc = make_map(&maps[0], A, (uint64_t)cap_rows, (uint64_t)p.Kd, BM);
   if (rc) return rc;
-  rc = make_map(&maps[1], B, (uint64_t)p.E * p.N, (uint64_t)p.Kd, (uint32_t)BN);
+  rc = make_map(&maps[1], B, (uint64_t)p.E * p.N, (uint64_t)p.Kd, (uint32_t)(BN / kGGNcta));
   if (rc) return rc;
   rc = make_map(&maps[2], out, (uint64_t)cap_rows, (uint64_t)p.N, 32);      // per-warp [32 x 64] boxes
   if (rc) return rc;
@@ -500,6 +545,8 @@ static int launch_gg(const void* A, const void* B, void* out, void* out2, const 
   if (rc) return rc;
   rc = make_map(&maps[4], aux ? aux : out, (uint64_t)cap_rows, (uint64_t)p.N, 32);
   if (rc) return rc;
+  p.out = static_cast<__nv_bfloat16*>(out);
+  p.out2 = static_cast<__nv_bfloat16*>(out2);
   const int max_tiles = (cap_rows / BM) * (p.N / BN);
   switch (BN) {
     case 128: return launch_gg_t<128, EPI>(maps, p, max_tiles, st);

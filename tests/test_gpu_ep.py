@@ -8,6 +8,7 @@ import torch
 from oracle import ep_oracle
 
 pytestmark = pytest.mark.gpu
+from m3vit_b200._lib import PAD_ROWS as PAD  # noqa: E402
 
 
 class SimGroup:
@@ -37,24 +38,24 @@ def test_ep_plan_kernel_bit_exact(W, E_loc, K):
     cnt_all = torch.stack([torch.bincount(i.reshape(-1), minlength=E_tot) for i in idxs]).int()
     lib = _lib.load()
     for r in range(W):
-        dr, drow, rc, ro = ep_oracle.ep_plan(idxs[r], cnt_all, r, W, E_loc, 128)
+        dr, drow, rc, ro = ep_oracle.ep_plan(idxs[r], cnt_all, r, W, E_loc, PAD)
         idx = idxs[r].to(dev)
         pl = ops.route_plan(idx, E_tot, 1)
         R = Ts[r] * K
-        cap = int(ro[-1]) + 256
+        cap = int(ro[-1]) + 2 * PAD
         o = dict(dst_rank=torch.empty(R, dtype=torch.int32, device=dev), dst_row=torch.empty(R, dtype=torch.int32, device=dev),
                  rc=torch.empty(E_loc, dtype=torch.int32, device=dev), ro=torch.empty(E_loc + 1, dtype=torch.int32, device=dev),
-                 rt=torch.full((cap // 128,), -7, dtype=torch.int32, device=dev), fl=torch.zeros(1, dtype=torch.int32, device=dev))
+                 rt=torch.full((cap // PAD,), -7, dtype=torch.int32, device=dev), fl=torch.zeros(1, dtype=torch.int32, device=dev))
         _lib.check(lib.m3_ep_plan(idx.data_ptr(), pl.pos.data_ptr(), cnt_all.to(dev).data_ptr(), r, W, E_loc, Ts[r], K,
-                                  128, cap, o["dst_rank"].data_ptr(), o["dst_row"].data_ptr(), o["rc"].data_ptr(),
+                                  PAD, cap, o["dst_rank"].data_ptr(), o["dst_row"].data_ptr(), o["rc"].data_ptr(),
                                   o["ro"].data_ptr(), o["rt"].data_ptr(), o["fl"].data_ptr(),
                                   torch.cuda.current_stream().cuda_stream), "m3_ep_plan")
         assert torch.equal(o["dst_rank"].cpu(), dr) and torch.equal(o["dst_row"].cpu(), drow)
         assert torch.equal(o["rc"].cpu(), rc) and torch.equal(o["ro"].cpu(), ro)
         assert int(o["fl"]) == 0
-        te = o["rt"].cpu()[: int(ro[-1]) // 128]
+        te = o["rt"].cpu()[: int(ro[-1]) // PAD]
         for i, e in enumerate(te.tolist()):
-            assert int(ro[e]) <= i * 128 < int(ro[e + 1])
+            assert int(ro[e]) <= i * PAD < int(ro[e + 1])
 
 
 @pytest.mark.parametrize("W", [2, 4])
@@ -136,8 +137,8 @@ def test_ep_simulation_matches_single_gpu(W, cdt):
 def test_ep_capacity_overflow_is_reported():
     from m3vit_b200 import ep
     dev = torch.device("cuda:0")
-    W, E_tot, K, D, T = 2, 16, 4, 128, 400
-    ctxs = make_sim(W, dev, 32 << 20, capacity_factor=0.5)      # queues deliberately too small
+    W, E_tot, K, D, T = 2, 16, 4, 128, 4000
+    ctxs = make_sim(W, dev, 32 << 20, capacity_factor=0.05)     # queues deliberately too small
     gen = torch.Generator().manual_seed(1)
     wg = ((torch.rand(D, E_tot, generator=gen) * 2 - 1) * 0.25).to(dev)
     xs = [torch.randn(T, D, generator=gen).to(dev) for _ in range(W)]

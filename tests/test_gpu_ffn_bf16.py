@@ -7,6 +7,7 @@ import torch
 from oracle import moe_oracle as O
 
 pytestmark = pytest.mark.gpu
+from m3vit_b200._lib import PAD_ROWS as PAD  # noqa: E402
 
 
 def nerr(a, b):
@@ -41,7 +42,7 @@ def test_ffn_bf16_forward_backward(T, K, E, D, H, skew):
     dev = torch.device("cuda:0")
     x, idx, w1, b1, w2, b2 = make(T, K, E, D, H, seed=T + D, skew=skew)
     bf = lambda t: t.bfloat16().float()
-    c, o, p, _ = O.route_plan(idx, E, 128)
+    c, o, p, _ = O.route_plan(idx, E, PAD)
     n = int(o[-1])
     xq_ref = O.dispatch(bf(x), p, K, n).requires_grad_(True)
     w = dict(w1=bf(w1).requires_grad_(True), b1=b1.clone().requires_grad_(True),
@@ -54,7 +55,7 @@ def test_ffn_bf16_forward_backward(T, K, E, D, H, skew):
     dy[~valid] = 0
     yq_ref.backward(dy)
 
-    plan = ops.route_plan(idx.to(dev), E, 128)
+    plan = ops.route_plan(idx.to(dev), E, PAD)
     assert torch.equal(plan.counts.cpu(), c)
     xq = ops.dispatch_fwd(x.to(dev), plan, K, out_dtype=torch.bfloat16)
     w1c, w1t = ops.cast_weights_bf16(w1.to(dev), True, True)
@@ -91,9 +92,9 @@ def test_ffn_bf16_tile_exactness():
         w2[e] = torch.eye(D, H) * (e + 1)            # fc2 = scaled identity: isolates fc1
     b1 = torch.zeros(E, H)
     b2 = torch.zeros(E, D)
-    c, o, p, _ = O.route_plan(idx, E, 128)
+    c, o, p, _ = O.route_plan(idx, E, PAD)
     n = int(o[-1])
-    plan = ops.route_plan(idx.to(dev), E, 128)
+    plan = ops.route_plan(idx.to(dev), E, PAD)
     xq = ops.dispatch_fwd(x.to(dev), plan, K, out_dtype=torch.bfloat16)
     w1c, _ = ops.cast_weights_bf16(w1.to(dev), True, False)
     w2c, _ = ops.cast_weights_bf16(w2.to(dev), True, False)

@@ -7,6 +7,7 @@ from helpers import all_fixtures, load_fixture
 from oracle import moe_oracle as O
 
 pytestmark = pytest.mark.gpu
+from m3vit_b200._lib import PAD_ROWS as PAD  # noqa: E402
 
 SMALL = [f for f in all_fixtures() if f.startswith("S")]
 ALL = all_fixtures()
@@ -35,7 +36,7 @@ def test_gate_fwd_matches_reference_fixture(fname, dev):
             continue
         wg = data["w_gate"][task if task is not None else 0].to(dev)
         g = ops.gate_fwd(x, wg, case.top_k, tf, want_gates=True)
-        plan = ops.route_plan(g.idx, case.num_expert, 128, g.imp_partial, g.load_partial)
+        plan = ops.route_plan(g.idx, case.num_expert, PAD, g.imp_partial, g.load_partial)
         assert torch.equal(g.idx.cpu().to(torch.int16), rec["idx"]), "routing indices differ"
         assert torch.equal(plan.counts.cpu(), rec["counts"]), "expert counts differ"
         torch.testing.assert_close(g.score.cpu(), rec["score"], rtol=1e-5, atol=2e-6)
@@ -72,7 +73,7 @@ def test_gate_fwd_bf16_input_and_noise(fname, dev):
     torch.testing.assert_close(g.score.cpu()[ok], ref["score"][ok], rtol=1e-5, atol=2e-6)
 
 
-@pytest.mark.parametrize("pad", [1, 128])
+@pytest.mark.parametrize("pad", [1, 128, 256])
 @pytest.mark.parametrize("T,K,E", [(1, 1, 4), (3, 2, 8), (513, 4, 16), (2402, 4, 16), (5000, 2, 64), (777, 1, 128)])
 def test_route_plan_bit_exact(T, K, E, pad, dev):
     from m3vit_b200 import ops
@@ -114,8 +115,8 @@ def test_dispatch_combine_roundtrip(D, qdtype, dev):
     x = torch.randn(T, D, generator=gen)
     idx = torch.stack([torch.randperm(E, generator=gen)[:K] for _ in range(T)])
     score = torch.rand(T, K, generator=gen)
-    c, o, p, row_slot = O.route_plan(idx, E, 128)
-    plan = ops.route_plan(idx.to(dev), E, 128)
+    c, o, p, row_slot = O.route_plan(idx, E, PAD)
+    plan = ops.route_plan(idx.to(dev), E, PAD)
     xq = ops.dispatch_fwd(x.to(dev), plan, K, out_dtype=qdtype)
     ref_xq = O.dispatch(x, p, K, int(o[-1]))
     n = int(o[-1])
@@ -145,7 +146,7 @@ def test_ffn_f32_forward_backward(fname, dev):
     E, D, H, K = case.num_expert, case.d_model, case.d_hidden, case.top_k
     gd = O.gate_forward(O.torch.cat((data["x"].reshape(-1, D), data["task_feat"].view(1, -1).expand(case.T, -1)), 1)
                         if data["task_feat"] is not None else data["x"].reshape(-1, D), data["w_gate"][0], K)
-    c, o, p, _ = O.route_plan(gd["idx"], E, 128)
+    c, o, p, _ = O.route_plan(gd["idx"], E, PAD)
     n = int(o[-1])
     xq_ref = O.dispatch(data["x"].reshape(-1, D), p, K, n).requires_grad_(True)
     w = {k: data[k].clone().requires_grad_(True) for k in ("w1", "b1", "w2", "b2")}
@@ -157,7 +158,7 @@ def test_ffn_f32_forward_backward(fname, dev):
     dy[~valid] = 0
     yq_ref.backward(dy)
 
-    plan = ops.route_plan(gd["idx"].to(dev), E, 128)
+    plan = ops.route_plan(gd["idx"].to(dev), E, PAD)
     xq = ops.dispatch_fwd(data["x"].reshape(-1, D).to(dev), plan, K)
     yq, hpre = ops.ffn_fwd(xq, plan, data["w1"].to(dev), data["b1"].to(dev), data["w2"].to(dev), data["b2"].to(dev))
     torch.testing.assert_close(yq[:n].cpu()[valid], yq_ref.detach()[valid], rtol=1e-4, atol=1e-5)

@@ -21,7 +21,7 @@ def main():
     T, D, H, K, E = B * bench.N_TOK, bench.D_MODEL, bench.D_HID, bench.TOP_K, bench.N_EXP
     E_loc = E // world
     cdt = torch.bfloat16
-    q_bytes = ((int(2.0 * T * K) + E_loc * 127 + 127) // 128 * 128) * D * 2
+    q_bytes = ((int(2.0 * T * K) + E_loc * 255 + 255) // 256 * 256) * D * 2
     ctx = ep.make_context(ep.TorchDistGroup(), dev, arena_bytes=6 * (q_bytes + 4096), capacity_factor=2.0)
     w = make_weights(MoECase("C2", 1, bench.N_TOK, D, H, E, K, 2), 0)
     sl = slice(rank * E_loc, (rank + 1) * E_loc)
