@@ -11,9 +11,10 @@ Everything computes in hand-written CUDA behind the C ABI of include/m3vit_moe.h
 (m3vit_b200/lib/libm3vit_moe.so).  Importing this package does not need a GPU;
 calling anything does, and fails loudly otherwise.
 """
-from .custom_moe_layer import FMoETransformerMLP, FMoETransformerMLPCkpt, FMoELinear  # noqa: F401
+from .custom_moe_layer import (FMoETransformerMLP, FMoETransformerMLPCkpt, TokenFMoETransformerMLP,  # noqa: F401
+                               FMoELinear)
 from .noisy_gate_vmoe import NoisyGate_VMoE, cv_squared  # noqa: F401
 from .block import build_moe_mlp, MoEBlockMlp, collect_noisy_gating_loss  # noqa: F401
 
-__all__ = ["FMoETransformerMLP", "FMoETransformerMLPCkpt", "FMoELinear", "NoisyGate_VMoE", "cv_squared",
+__all__ = ["FMoETransformerMLP", "FMoETransformerMLPCkpt", "TokenFMoETransformerMLP", "FMoELinear", "NoisyGate_VMoE", "cv_squared",
            "build_moe_mlp", "MoEBlockMlp", "collect_noisy_gating_loss"]

@@ -230,3 +230,40 @@ class FMoETransformerMLPCkpt(FMoETransformerMLP):
     """models/moe/ckpt/custom_moe_layer.py: returns
     (out, clean_logits, noisy_logits, noise_stddev, top_logits, gates)."""
     RETURN_SUMMARIES = True
+
+
+class TokenFMoETransformerMLP(nn.Module):
+    """Experts-only entry of the reference's token-MoE variant
+    (/root/reference/models/moe/token/custom_moe_layer.py:55-156): routing (`gate_top_k_idx [T,K]` int64,
+    `gate_score [T,K]`) is computed by the caller; the layer runs dispatch -> expert FFN -> combine.
+    Same state-dict keys for the experts; no gate parameters."""
+
+    def __init__(self, num_expert=32, d_model=1024, d_gate=1024, d_hidden=4096, activation=torch.nn.GELU(),
+                 expert_dp_comm="none", expert_rank=0, world_size=1, top_k=2,
+                 compute_dtype: Optional[torch.dtype] = None, **kwargs):
+        super().__init__()
+        if kwargs:
+            raise TypeError(f"unexpected keyword arguments {sorted(kwargs)}")
+        if world_size != 1:
+            raise NotImplementedError("TokenFMoETransformerMLP: expert parallelism is wired for FMoETransformerMLP only")
+        self.num_expert, self.d_model, self.world_size, self.top_k = num_expert, d_model, world_size, top_k
+        self.our_d_model = d_model
+        self.d_hidden = d_hidden
+        self.drop_p = _check_activation(activation)
+        self.experts = _Expert(num_expert, d_model, d_hidden, activation, rank=expert_rank)
+        for p in self.experts.parameters():
+            setattr(p, "dp_comm", expert_dp_comm)
+        self.compute_dtype = compute_dtype
+        self._wcache = F_.WeightCache()
+
+    def forward(self, inp: torch.Tensor, gate_top_k_idx: torch.Tensor, gate_score: torch.Tensor):
+        if self.drop_p > 0 and self.training:
+            raise NotImplementedError("expert dropout > 0 in training is not implemented")
+        shape = inp.shape
+        x = inp.reshape(-1, self.d_model)
+        idx = gate_top_k_idx.reshape(-1, self.top_k)
+        score = gate_score.reshape(-1, self.top_k)
+        cdt = self.compute_dtype or (torch.bfloat16 if x.dtype == torch.bfloat16 else torch.float32)
+        out = F_.ExpertsFunction.apply(x, idx, score, self.experts.htoh4.weight, self.experts.htoh4.bias,
+                                       self.experts.h4toh.weight, self.experts.h4toh.bias, cdt, self._wcache, None)
+        return out.reshape(shape)

@@ -158,3 +158,95 @@ def test_full_size_properties_bf16_and_fp32():
             yp = layer(x[perm], task_id=0)
             assert torch.equal(layer.last_counts, c1)
             torch.testing.assert_close(yp, y1[perm], rtol=0, atol=0)
+
+
+def test_token_moe_experts_only_entry():
+    """f2: TokenFMoETransformerMLP.forward(inp, gate_top_k_idx, gate_score) (models/moe/token/custom_moe_layer.py:88-156):
+    externally supplied routing, compared with the oracle's dispatch / expert FFN / combine."""
+    from oracle import moe_oracle as O
+    dev = torch.device("cuda:0")
+    E, K, D, H, B, N = 16, 2, 128, 256, 2, 61
+    gen = torch.Generator().manual_seed(3)
+    layer = M.TokenFMoETransformerMLP(num_expert=E, d_model=D, d_gate=D, d_hidden=H, top_k=K,
+                                      activation=nn.Sequential(nn.GELU(), nn.Dropout(0.0))).to(dev)
+    with torch.no_grad():
+        layer.experts.htoh4.bias.uniform_(-0.1, 0.1)
+        layer.experts.h4toh.bias.uniform_(-0.1, 0.1)
+    x = torch.randn(B, N, D, generator=gen)
+    idx = torch.stack([torch.randperm(E, generator=gen)[:K] for _ in range(B * N)])
+    score = torch.rand(B * N, K, generator=gen)
+    g = torch.randn(B, N, D, generator=gen)
+    xd, sd = x.to(dev).requires_grad_(True), score.to(dev).requires_grad_(True)
+    out = layer(xd, idx.to(dev), sd)
+    out.backward(g.to(dev))
+    w1, b1 = layer.experts.htoh4.weight.detach().cpu(), layer.experts.htoh4.bias.detach().cpu()
+    w2, b2 = layer.experts.h4toh.weight.detach().cpu(), layer.experts.h4toh.bias.detach().cpu()
+    xr, sr = x.clone().requires_grad_(True), score.clone().requires_grad_(True)
+    c, o, p, _ = O.route_plan(idx, E, 1)
+    ref = O.combine(O.expert_ffn(O.dispatch(xr.view(-1, D), p, K, int(o[-1])), c, o, w1, b1, w2, b2), p, sr)
+    ref.backward(g.view(-1, D))
+    torch.testing.assert_close(out.detach().cpu().view(-1, D), ref.detach(), rtol=2e-4, atol=2e-5)
+    torch.testing.assert_close(xd.grad.cpu(), xr.grad, rtol=2e-4, atol=2e-5)
+    torch.testing.assert_close(sd.grad.cpu(), sr.grad, rtol=2e-4, atol=2e-4)
+
+
+def test_noisy_training_path_matches_oracle_with_same_noise():
+    """f4: vmoe_noisy_std > 0 in training.  The noise is drawn by torch on the device; replaying the same
+    generator state gives the oracle the identical noise tensor, so routing and the normal-CDF load loss
+    (origin/noisy_gate_vmoe.py:82-125,267-283) can be compared directly."""
+    from oracle import moe_oracle as O
+    dev = torch.device("cuda:0")
+    fx, case, data = load_fixture("S8_d128h256_g2_s0.pt")
+    layer = build_layer(case, data, "origin", dev)
+    for g in layer.gate:
+        g.noise_std = 1.0
+    layer.train()
+    x = data["x"].to(dev).requires_grad_(True)
+    torch.manual_seed(1234)
+    out = layer(x, task_id=1)
+    loss = layer.gate[1].get_loss()
+    (out.sum() + loss).backward()
+    torch.manual_seed(1234)
+    noise = torch.randn(case.T, case.num_expert, device=dev).cpu()
+    xr = data["x"].clone().requires_grad_(True)
+    wg = data["w_gate"][1].clone().requires_grad_(True)
+    ref, gd = O.layer_forward(xr, wg, data["w1"], data["b1"], data["w2"], data["b2"], case.top_k,
+                              noise_std=1.0, training=True, noise=noise)
+    (ref.sum() + gd["loss"]).backward()
+    p64 = torch.softmax(gd["noisy_logits"].double(), 1)
+    ok = O.min_topk_gap(p64, case.top_k + 1) > 1e-5
+    assert int((~ok).sum()) <= 2
+    torch.testing.assert_close(out.detach().cpu().view(case.T, -1)[ok], ref.detach().view(case.T, -1)[ok], rtol=2e-4, atol=2e-5)
+    assert float(loss) == pytest.approx(float(gd["loss"]), rel=1e-3)
+    if bool(ok.all()):
+        assert nerr(layer.gate[1].w_gate.grad.cpu(), wg.grad) <= 1e-3
+        torch.testing.assert_close(x.grad.cpu().view(case.T, -1), xr.grad.view(case.T, -1), rtol=1e-3, atol=1e-5)
+
+
+def test_layer_is_cuda_graph_capturable():
+    """No host synchronisation anywhere on the single-GPU path: forward + backward of the layer can be
+    captured into a CUDA graph and replayed (the reference's fmoe path syncs every layer)."""
+    dev = torch.device("cuda:0")
+    fx, case, data = load_fixture("S8_d128h256_g2_s0.pt")
+    for cdt in (torch.float32, torch.bfloat16):
+        layer = build_layer(case, data, "origin", dev, compute_dtype=cdt).train()
+        x = data["x"].to(dev).requires_grad_(True)
+        go = data["grad_out"].to(dev)
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            for _ in range(3):                      # warm-up (allocator, weight cache) outside capture
+                layer.zero_grad(set_to_none=True); x.grad = None
+                layer(x, task_id=0).backward(go)
+        torch.cuda.current_stream().wait_stream(s)
+        want_dx, want_out = x.grad.clone(), layer(x, task_id=0).detach().clone()
+        layer.zero_grad(set_to_none=True); x.grad = None
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            out = layer(x, task_id=0)
+            out.backward(go)
+        x.grad.zero_()
+        graph.replay()
+        torch.cuda.synchronize()
+        assert torch.equal(out, want_out)
+        torch.testing.assert_close(x.grad, want_dx, rtol=0, atol=0)
