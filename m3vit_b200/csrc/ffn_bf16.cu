@@ -16,6 +16,7 @@
 // Expert queues are padded to 128 rows (route plan), so every tile is full and the expert
 // of a tile is a table lookup; padding rows are zero, so they add nothing to dW.
 #include <cstdio>
+#include <cstdlib>
 #include <mutex>
 
 #include "tc_common.cuh"
@@ -620,6 +621,20 @@ using namespace m3;
 using namespace m3::tc;
 typedef __nv_bfloat16 bf16;
 
+// ffn_fused.cu
+int m3_ffn_fused_supported(int D, int H);
+int m3_ffn_fused_fwd(const void* xq, const int32_t* offsets, const int32_t* tile_expert, int cap_rows, int E, int D,
+                     int H, const void* w1, const float* b1, const void* w2, const float* b2, void* hpre, void* yq,
+                     cudaStream_t st);
+int m3_ffn_fused_bwd(const void* dyq, const void* hpre, const int32_t* offsets, const int32_t* tile_expert,
+                     int cap_rows, int E, int D, int H, const void* w2t, const void* w1t, void* dhpre, void* h,
+                     void* dxq, cudaStream_t st);
+// M3_FFN_UNFUSED=1 forces the two-kernel path (A/B measurements, shapes the fused kernel does not cover)
+static bool use_fused(int D, int H) {
+  static const bool off = [] { const char* v = getenv("M3_FFN_UNFUSED"); return v != nullptr && v[0] == '1'; }();
+  return !off && m3_ffn_fused_supported(D, H);
+}
+
 // workspace: forward  : h [cap][H] bf16
 //            backward : dhpre [cap][H] bf16 | h [cap][H] bf16 | wgrad split-K partials [S][E][M][N]+[S][E][M] fp32
 size_t m3_ffn_bf16_workspace_bytes(int cap_rows, int D, int H, int E, int backward) {
@@ -634,6 +649,8 @@ int m3_ffn_fwd_bf16(const void* xq, const int32_t* offsets, const int32_t* tile_
                     int H, const void* w1, const float* b1, const void* w2, const float* b2, void* hpre, void* yq,
                     void* workspace, size_t workspace_bytes, cudaStream_t st) {
   if (workspace == nullptr || workspace_bytes < m3_ffn_bf16_workspace_bytes(cap_rows, D, H, E, 0)) return M3_ERR_WORKSPACE;
+  if (use_fused(D, H))
+    return m3_ffn_fused_fwd(xq, offsets, tile_expert, cap_rows, E, D, H, w1, b1, w2, b2, hpre, yq, st);
   bf16* h = static_cast<bf16*>(workspace);
   GGParams p{};
   p.offsets = offsets; p.tile_expert = tile_expert; p.E = E;
@@ -656,16 +673,23 @@ int m3_ffn_bwd_bf16(const void* xq, const void* hpre, const void* dyq, const int
   bf16* dhpre = static_cast<bf16*>(workspace);
   bf16* h = reinterpret_cast<bf16*>(static_cast<uint8_t*>(workspace) + hbytes);
   float* part = reinterpret_cast<float*>(static_cast<uint8_t*>(workspace) + 2 * hbytes);
-  GGParams p{};
-  p.offsets = offsets; p.tile_expert = tile_expert; p.E = E;
-  // dhpre = (dyq W2) * gelu'(hpre);  h = gelu(hpre)      B = W2^T [E][H][D] (K-major in D)
-  p.N = H; p.Kd = D;
-  int rc = launch_gg<EPI_DGELU>(dyq, w2t, dhpre, h, hpre, p, cap_rows, st);
-  if (rc) return rc;
-  // dxq = dhpre W1                                       B = W1^T [E][D][H] (K-major in H)
-  p.N = D; p.Kd = H;
-  rc = launch_gg<EPI_STORE>(dhpre, w1t, dxq, nullptr, nullptr, p, cap_rows, st);
-  if (rc) return rc;
+  int rc;
+  if (use_fused(D, H)) {
+    // one kernel: dhpre = (dyq W2) * gelu'(hpre), h = gelu(hpre), dxq = dhpre W1
+    rc = m3_ffn_fused_bwd(dyq, hpre, offsets, tile_expert, cap_rows, E, D, H, w2t, w1t, dhpre, h, dxq, st);
+    if (rc) return rc;
+  } else {
+    GGParams p{};
+    p.offsets = offsets; p.tile_expert = tile_expert; p.E = E;
+    // dhpre = (dyq W2) * gelu'(hpre);  h = gelu(hpre)      B = W2^T [E][H][D] (K-major in D)
+    p.N = H; p.Kd = D;
+    rc = launch_gg<EPI_DGELU>(dyq, w2t, dhpre, h, hpre, p, cap_rows, st);
+    if (rc) return rc;
+    // dxq = dhpre W1                                       B = W1^T [E][D][H] (K-major in H)
+    p.N = D; p.Kd = H;
+    rc = launch_gg<EPI_STORE>(dhpre, w1t, dxq, nullptr, nullptr, p, cap_rows, st);
+    if (rc) return rc;
+  }
   // dW2[e] = dyq_e^T h_e  [D][H];   dW1[e] = dhpre_e^T xq_e  [H][D]
   // the bias gradients ride along as one extra N=16 MMA against a tile of ones
   rc = launch_wgrad(dyq, h, offsets, cap_rows, E, D, H, dw2, db2, part, st);
