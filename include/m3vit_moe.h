@@ -219,6 +219,10 @@ int m3_zero_pad_rows(void* q, int dtype, const int32_t* counts, const int32_t* o
 int m3_ep_barrier(void* const* peer_flags, void* const* peer_gather, const int32_t* payload,
                   int payload_ints, int rank, int W, int epoch, m3_stream_t stream);
 
+/* Debug only: clock64 timeline of CTA 0 of the fused FFN kernel (enable, then call again with a host
+ * buffer of 2*max_events uint64 to fetch {tag, clock} pairs).  Synchronises the device. */
+int m3_debug_trace(int enable, unsigned long long* host_out, int max_events);
+
 /* CUDA IPC plumbing for the peer queues (host pointers in/out; 64-byte handles). */
 int m3_ipc_alloc(size_t bytes, void** dev_ptr, void* handle64);
 int m3_ipc_open(const void* handle64, void** dev_ptr);

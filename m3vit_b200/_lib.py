@@ -51,6 +51,7 @@ SIGNATURES = {
     "m3_ep_dispatch_bwd": (_i, [_p, _i, _p, _p, _i, _i, _i, _p, _p, _i, _p, _i, _p]),
     "m3_zero_pad_rows": (_i, [_p, _i, _p, _p, _i, _i, _p]),
     "m3_ep_barrier": (_i, [_p, _p, _p, _i, _i, _i, _i, _p]),
+    "m3_debug_trace": (_i, [_i, _p, _i]),
     "m3_ipc_alloc": (_i, [_sz, C.POINTER(_p), _p]),
     "m3_ipc_open": (_i, [_p, C.POINTER(_p)]),
     "m3_ipc_close": (_i, [_p]),

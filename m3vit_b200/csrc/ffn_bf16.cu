@@ -629,10 +629,13 @@ int m3_ffn_fused_fwd(const void* xq, const int32_t* offsets, const int32_t* tile
 int m3_ffn_fused_bwd(const void* dyq, const void* hpre, const int32_t* offsets, const int32_t* tile_expert,
                      int cap_rows, int E, int D, int H, const void* w2t, const void* w1t, void* dhpre, void* h,
                      void* dxq, cudaStream_t st);
-// M3_FFN_UNFUSED=1 forces the two-kernel path (A/B measurements, shapes the fused kernel does not cover)
+// M3_FFN_FUSED=1 selects the single-kernel fc1->GELU->fc2 chain (ffn_fused.cu) where the shape allows.
+// It is parity-tested but currently slower than the two CTA-pair GEMMs at D = H = 384 (its N = 64
+// chunk MMAs re-read the whole resident x tile from shared memory), so the
+// two-kernel path stays the default.
 static bool use_fused(int D, int H) {
-  static const bool off = [] { const char* v = getenv("M3_FFN_UNFUSED"); return v != nullptr && v[0] == '1'; }();
-  return !off && m3_ffn_fused_supported(D, H);
+  static const bool on = [] { const char* v = getenv("M3_FFN_FUSED"); return v != nullptr && v[0] == '1'; }();
+  return on && m3_ffn_fused_supported(D, H);
 }
 
 // workspace: forward  : h [cap][H] bf16

@@ -32,6 +32,17 @@ constexpr int TBOX = 32 * 32 * 2;                         // 2 KB per-warp trans
 
 enum { MODE_FWD = 0, MODE_BWD = 1 };
 
+// Debug timeline (M3_FUSED_TRACE=1): clock64 stamps written by CTA 0; read with m3_debug_read_trace.
+__device__ unsigned long long g_trace[8192];
+__device__ unsigned int g_trace_n;
+__device__ int g_trace_on;
+__device__ __forceinline__ void trace(int role, int ev, int j) {
+  if (g_trace_on && blockIdx.x == 0) {
+    const unsigned int i = atomicAdd(&g_trace_n, 1u);
+    if (i < 4096) { g_trace[2 * i] = ((unsigned long long)role << 48) | ((unsigned long long)ev << 32) | (unsigned)j; g_trace[2 * i + 1] = clock64(); }
+  }
+}
+
 struct FusedParams {
   const int32_t* offsets;      // [E+1]
   const int32_t* tile_expert;  // per 256-row tile
@@ -150,7 +161,9 @@ ffn_chain_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
         const int e = p.tile_expert[pt];
         const int row0 = (pt * 2 + (int)cta_rank) * FBM;
         // resident A tile (free once the previous tile's last G1 has been read)
+        trace(0, 0, xuse);
         mbar_wait(x_empty, (xuse & 1) ^ 1);
+        trace(0, 1, xuse);
         {
           const uint32_t bar = mapa_u32(smem_u32(x_full), 0);
           if (leader_cta) mbar_expect_tx(x_full, 2 * Cfg::X_BYTES); else mbar_arrive_remote(bar);
@@ -193,14 +206,17 @@ ffn_chain_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
       auto next_slot = [&]() { if (++slot == NSLOT) { slot = 0; sphase ^= 1; } };
       const uint32_t xs_a = smem_u32(xs), hs_a = smem_u32(hs), ring_a = smem_u32(ring);
       for (int pt = unit; pt < total; pt += n_units, ++tile_it) {
+        trace(1, 0, tile_it);
         mbar_wait(x_full, tile_it & 1);
         tcgen05_fence_after();
+        trace(1, 1, tile_it);
         for (int j = 0; j <= NH; ++j) {
           if (j < NH) {                                    // ---- G1(j): acc1[j&1] = x * W1_j^T
             const int b = j & 1;
             mbar_wait(&a1_empty[b], (use1[b] & 1) ^ 1);
             ++use1[b];
             tcgen05_fence_after();
+            trace(1, 2, j);
             const uint32_t d1 = tmem_base + acc1_col + b * FHC;
             for (int s = 0; s < W1S; ++s) {
               mbar_wait(&w_full[slot], sphase);
@@ -219,6 +235,7 @@ ffn_chain_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
               next_slot();
             }
             umma_commit_2sm(&a1_full[b], 3);
+            trace(1, 3, j);
             if (j == NH - 1) umma_commit_2sm(x_empty, 3);   // A tile no longer needed: next tile may load
           }
           if (j > 0) {                                     // ---- G2(j-1): acc2 += h_{j-1} * W2_{j-1}^T
@@ -230,6 +247,7 @@ ffn_chain_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
             mbar_wait(&h_full[b], useh[b] & 1);
             ++useh[b];
             tcgen05_fence_after();
+            trace(1, 4, jj);
             for (int part = 0; part < NPART; ++part) {
               mbar_wait(&w_full[slot], sphase);
               tcgen05_fence_after();
@@ -244,6 +262,7 @@ ffn_chain_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
               next_slot();
             }
             umma_commit_2sm(&h_empty[b], 3);
+            trace(1, 5, jj);
             if (jj == NH - 1) umma_commit_2sm(a2_full, 3);
           }
         }
@@ -289,13 +308,16 @@ ffn_chain_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
 #pragma unroll
           for (int c = 0; c < 4; ++c) hraw[c] = __ldg(src + c);
         }
+        if (warp == 2 && lane == 0) trace(2, 0, j);
         mbar_wait(&a1_full[b], use1[b] & 1);
         ++use1[b];
         tcgen05_fence_after();
+        if (warp == 2 && lane == 0) trace(2, 1, j);
         float v[32];
         tmem_ld_32x32(tmem_base + acc1_col + b * FHC + half * 32 + ((uint32_t)(q * 32) << 16), v);
         tcgen05_fence_before();
         arrive_leader(&a1_empty[b], b ? a1e_remote1 : a1e_remote);   // acc1[b] may be overwritten by G1(j+2)
+        if (warp == 2 && lane == 0) trace(2, 2, j);
         f32x2 w2[16];
 #pragma unroll
         for (int i = 0; i < 16; ++i) w2[i] = pk2(v[2 * i], v[2 * i + 1]);
@@ -338,6 +360,7 @@ ffn_chain_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
           flush(p.mid_out, p.H, grow0, hcol);
         }
         // h chunk (A operand of G2): wait until G2(j-2) has finished reading this buffer
+        if (warp == 2 && lane == 0) trace(2, 3, j);
         mbar_wait(&h_empty[b], (useh[b] & 1) ^ 1);
         ++useh[b];
         uint8_t* hb = hs + b * XBOX;
@@ -346,6 +369,7 @@ ffn_chain_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
           *reinterpret_cast<uint4*>(hb + fbox_off(r, half * 4 + c)) = make_uint4(hq[4 * c], hq[4 * c + 1], hq[4 * c + 2], hq[4 * c + 3]);
         fence_proxy_async_smem();
         arrive_leader(&h_full[b], b ? hf_remote1 : hf_remote);
+        if (warp == 2 && lane == 0) trace(2, 4, j);
       }
       // ---- final epilogue: out = acc2 (+ b2)
       mbar_wait(a2_full, tile_it & 1);
@@ -378,6 +402,7 @@ ffn_chain_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
               make_uint4(pk_bf16x2(w2[4 * cc]), pk_bf16x2(w2[4 * cc + 1]), pk_bf16x2(w2[4 * cc + 2]), pk_bf16x2(w2[4 * cc + 3]));
         flush(p.out, D, grow0, col);
       }
+      if (warp == 2 && lane == 0) trace(2, 7, tile_it);
     }
   }
   tcgen05_fence_before();
@@ -455,6 +480,22 @@ static int launch_chain_t(const void* A, const void* B1, const void* B2, const F
 }  // namespace m3
 
 using namespace m3::tc;
+
+// debug: enable / read the clock64 timeline of CTA 0 (not part of the public ABI contract)
+extern "C" int m3_debug_trace(int enable, unsigned long long* host_out, int max_events) {
+  int on = enable;
+  unsigned int n = 0;
+  if (host_out != nullptr) {
+    cudaDeviceSynchronize();
+    cudaMemcpyFromSymbol(&n, g_trace_n, sizeof(n));
+    if ((int)n > max_events) n = max_events;
+    cudaMemcpyFromSymbol(host_out, g_trace, (size_t)n * 16);
+  }
+  unsigned int zero = 0;
+  cudaMemcpyToSymbol(g_trace_n, &zero, sizeof(zero));
+  cudaMemcpyToSymbol(g_trace_on, &on, sizeof(on));
+  return (int)n;
+}
 
 // 1 if the fused chain kernel supports this shape (else the un-fused gg kernels are used)
 int m3_ffn_fused_supported(int D, int H) { return (D == 128 || D == 256 || D == 384) && H % 64 == 0 && H >= 64; }

@@ -108,3 +108,42 @@ def test_ffn_bf16_tile_exactness():
     valid[p.long()] = True
     got = hpre[:n].float().cpu()
     assert torch.equal(got[valid], want_hpre[valid].bfloat16().float()), "fc1 accumulators differ"
+
+
+def test_fused_chain_kernel_matches_two_kernel_path():
+    """The single-kernel fc1->GELU->fc2 chain (M3_FFN_FUSED=1, ffn_fused.cu) against the default two-kernel
+    path, in a subprocess because the switch is read once per process."""
+    import os
+    import subprocess
+    import sys
+    code = r"""
+import torch, sys
+sys.path.insert(0, %r)
+from m3vit_b200 import ops
+dev = torch.device('cuda:0')
+torch.manual_seed(0)
+T, K, E, D, H = 1500, 4, 16, 384, 384
+x = torch.randn(T, D, device=dev)
+idx = torch.stack([torch.randperm(E)[:K] for _ in range(T)]).to(dev)
+plan = ops.route_plan(idx, E)
+xq = ops.dispatch_fwd(x, plan, K, out_dtype=torch.bfloat16)
+w1c, w1t = ops.cast_weights_bf16(torch.randn(E, H, D, device=dev) / D ** 0.5, True, True)
+w2c, w2t = ops.cast_weights_bf16(torch.randn(E, D, H, device=dev) / H ** 0.5, True, True)
+b1, b2 = torch.randn(E, H, device=dev) * 0.1, torch.randn(E, D, device=dev) * 0.1
+yq, hpre = ops.ffn_fwd(xq, plan, w1c, b1, w2c, b2)
+dyq = torch.randn_like(yq)
+dxq, dw1, db1, dw2, db2 = ops.ffn_bwd(xq, hpre, dyq, plan, w1c, w2c, w1t, w2t)
+n = int(plan.offsets[-1])          # rows beyond the live queues are never written
+torch.save([t.float().cpu() for t in (yq[:n], hpre[:n], dxq[:n], dw1, db1, dw2, db2)], sys.argv[1])
+""" % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    outs = []
+    for fused in ("0", "1"):
+        path = f"/tmp/m3_fused_{fused}.pt"
+        env = dict(os.environ, M3_FFN_FUSED=fused)
+        subprocess.run([sys.executable, "-c", code, path], check=True, env=env, timeout=300)
+        outs.append(torch.load(path))
+    n_rows = None
+    for a, b, name in zip(outs[0], outs[1], ("yq", "hpre", "dxq", "dw1", "db1", "dw2", "db2")):
+        # identical arithmetic up to the order of the fp32 accumulation over hidden chunks
+        assert nerr(b, a) < 1e-2, (name, nerr(b, a))
+    assert torch.equal(outs[0][1], outs[1][1]), "saved pre-activation must be bit-identical (same K order)"
