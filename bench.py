@@ -48,18 +48,21 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region: the sampler runs from
+    before the warm-up, every sample carries nvidia-smi's own timestamp, and only samples between
+    mark_start() and mark_end() are reported (all of them were taken under load)."""
+    Q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
         self.index, self.proc, self.lines = index, None, []
+        self.t0 = self.t1 = None
 
     def start(self):
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -70,30 +73,45 @@ class ClockSampler:
         for ln in self.proc.stdout:
             self.lines.append(ln.strip())
 
+    def mark_start(self):
+        import datetime
+        self.t0 = datetime.datetime.now()
+
+    def mark_end(self):
+        import datetime
+        self.t1 = datetime.datetime.now()
+
     def stop(self):
+        import datetime
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.05)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
-        sm, mx, reasons = [], None, set()
+        rows = []
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for ln in self.lines:
             f = [x.strip() for x in ln.split(",")]
-            if len(f) < 7:
+            if len(f) < 8:
                 continue
             try:
-                sm.append(float(f[0]))
-                mx = float(f[1])
+                ts = datetime.datetime.strptime(f[0], "%Y/%m/%d %H:%M:%S.%f")
+                rows.append((ts, float(f[1]), float(f[2]), f[4:8]))
             except ValueError:
                 continue
-            for n, v in zip(names, f[3:7]):
+        inside = [r for r in rows if self.t0 is not None and self.t0 <= r[0] <= self.t1]
+        used, window = (inside, "timed region") if inside else (rows[-5:], "nearest samples (region shorter than the sampling period)")
+        reasons = set()
+        for r in used:
+            for n, v in zip(names, r[3]):
                 if v.lower().startswith("active"):
                     reasons.add(n)
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx, "samples": len(sm),
-                "reasons": sorted(reasons)}
+        sm = [r[1] for r in used]
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": used[-1][2] if used else None,
+                "samples": len(sm), "window": window, "reasons": sorted(reasons)}
 
 
 # ----------------------------------------------------------------------------- CPU reference arm
@@ -174,7 +192,7 @@ def one_call(layer, x, g, task):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--batch", type=int, default=32, help="images per GPU")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
@@ -240,13 +258,14 @@ def main():
             xs[i].grad = None
             one_call(layers[li], xs[i], gs[i & 1], t)
 
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     for _ in range(warmup):
         step_resident()
     for l in layers:
         l.zero_grad(set_to_none=True)
     barrier()
-    sampler = ClockSampler(local_rank)
-    sampler.start()
+    sampler.mark_start()
     ops.launch_count = 0
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
@@ -254,6 +273,7 @@ def main():
         step_resident()
     e1.record()
     barrier()
+    sampler.mark_end()
     ms = e0.elapsed_time(e1)
     launches = ops.launch_count
     clocks = sampler.stop()
