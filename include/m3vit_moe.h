@@ -219,6 +219,45 @@ int m3_zero_pad_rows(void* q, int dtype, const int32_t* counts, const int32_t* o
 int m3_ep_barrier(void* const* peer_flags, void* const* peer_gather, const int32_t* payload,
                   int payload_ints, int rank, int W, int epoch, m3_stream_t stream);
 
+/* ---- Block-level fusion around the layer --------------------
+ * Replaces, in the reference Block,  x + drop_path(mlp_drop(mlp(norm2(x), ...)))
+ * (models/moe/origin/vision_transformer_moe.py:278-283; ckpt twin :441-451), the separate
+ * LayerNorm (norm2) and residual-add passes.  x is the RAW fp32 residual stream [T, D]; the
+ * normalised tokens are never written to memory.
+ *   m3_ln_stats        mean[T], rstd[T] = 1/sqrt(var_biased + eps)      (torch.nn.LayerNorm)
+ *   m3_ln_fold_gate    w_fold[Dg,E] = gamma (.) w_gate (rows >= D copied), gb[2,E] = {gamma^T W, beta^T W}
+ *   m3_gate_fwd_ln     m3_gate_fwd on raw x:  z = rstd * (x @ w_fold - mean * gb[0]) + gb[1]
+ *   m3_dispatch_fwd_ln m3_dispatch_fwd with LayerNorm applied on the fly
+ *   m3_combine_fwd_res out[T,D] (fp32) = residual + sum_k score * yq[pos]
+ *   m3_gate_bwd_ln     m3_gate_bwd with x normalised on load (w_gate = the ORIGINAL weights)
+ *   m3_ln_bwd_res      dx = dres + LayerNorm'(dxn);  dgamma[D], dbeta[D]   (deterministic)           */
+int m3_ln_stats(const float* x, int T, int D, float eps, float* mean, float* rstd, m3_stream_t stream);
+int m3_ln_fold_gate(const float* w_gate, const float* gamma, const float* beta, int D, int Dg, int E,
+                    float* w_fold, float* gb, m3_stream_t stream);
+int m3_gate_fwd_ln(const float* x, int64_t ldx, const float* ln_mean, const float* ln_rstd,
+                   const float* ln_gb, const float* task_feat, const float* w_gate_folded,
+                   const float* noise, float noise_stddev, int T, int D, int Dt, int E, int K,
+                   int64_t* idx, int32_t* idx_full, float* score, float* top_vals, float* clean_logits,
+                   float* noisy_logits, float* gates, float* imp_partial, int32_t* load_partial,
+                   m3_stream_t stream);
+int m3_dispatch_fwd_ln(const float* x, const float* mean, const float* rstd, const float* gamma,
+                       const float* beta, const int32_t* pos, const int32_t* counts,
+                       const int32_t* offsets, int T, int K, int D, int E, void* xq, int xq_dtype,
+                       m3_stream_t stream);
+int m3_combine_fwd_res(const void* yq, int yq_dtype, const int32_t* pos, const float* score,
+                       const float* residual, int T, int K, int D, float* out, m3_stream_t stream);
+int m3_gate_bwd_ln(const float* x, int64_t ldx, const float* ln_mean, const float* ln_rstd,
+                   const float* ln_gamma, const float* ln_beta, const float* task_feat,
+                   const float* w_gate, const float* logits, const int32_t* idx_full, int T, int D, int Dt,
+                   int E, int K, const float* dscore, const float* dtop_vals, const float* dgates,
+                   const float* dimportance, const float* dclean, const float* dnoisy,
+                   const float* importance, const float* dcv_loss, float* dz, float* dw_gate,
+                   float* dtask_feat, void* workspace, size_t workspace_bytes, m3_stream_t stream);
+size_t m3_ln_bwd_workspace_bytes(int T, int D);
+int m3_ln_bwd_res(const float* dxn, const float* x, const float* mean, const float* rstd,
+                  const float* gamma, const float* dres, int T, int D, float* dx, float* dgamma,
+                  float* dbeta, void* workspace, size_t workspace_bytes, m3_stream_t stream);
+
 /* Debug only: clock64 timeline of CTA 0 of the fused FFN kernel (enable, then call again with a host
  * buffer of 2*max_events uint64 to fetch {tag, clock} pairs).  Synchronises the device. */
 int m3_debug_trace(int enable, unsigned long long* host_out, int max_events);

@@ -51,6 +51,16 @@ SIGNATURES = {
     "m3_ep_dispatch_bwd": (_i, [_p, _i, _p, _p, _i, _i, _i, _p, _p, _i, _p, _i, _p]),
     "m3_zero_pad_rows": (_i, [_p, _i, _p, _p, _i, _i, _p]),
     "m3_ep_barrier": (_i, [_p, _p, _p, _i, _i, _i, _i, _p]),
+    "m3_ln_stats": (_i, [_p, _i, _i, _f, _p, _p, _p]),
+    "m3_ln_fold_gate": (_i, [_p, _p, _p, _i, _i, _i, _p, _p, _p]),
+    "m3_gate_fwd_ln": (_i, [_p, _i64, _p, _p, _p, _p, _p, _p, _f, _i, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p,
+                            _p, _p]),
+    "m3_dispatch_fwd_ln": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _p, _i, _p]),
+    "m3_combine_fwd_res": (_i, [_p, _i, _p, _p, _p, _i, _i, _i, _p, _p]),
+    "m3_gate_bwd_ln": (_i, [_p, _i64, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p,
+                            _p, _p, _p, _p, _p, _sz, _p]),
+    "m3_ln_bwd_workspace_bytes": (_sz, [_i, _i]),
+    "m3_ln_bwd_res": (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _p, _p, _p, _p, _sz, _p]),
     "m3_debug_trace": (_i, [_i, _p, _i]),
     "m3_ipc_alloc": (_i, [_sz, C.POINTER(_p), _p]),
     "m3_ipc_open": (_i, [_p, C.POINTER(_p)]),

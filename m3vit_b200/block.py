@@ -54,9 +54,11 @@ class MoEBlockMlp(nn.Module):
     variant="ckpt"  : returns (x, cv_loss) computed like ckpt/vision_transformer_moe.py:452-459,538-542.
     """
 
-    def __init__(self, dim, norm_layer=nn.LayerNorm, drop=0.0, drop_path=0.0, variant="origin", **moe_kwargs):
+    def __init__(self, dim, norm_layer=nn.LayerNorm, drop=0.0, drop_path=0.0, variant="origin", fuse=True,
+                 **moe_kwargs):
         super().__init__()
         self.variant = variant
+        self.fuse = fuse
         self.norm2 = norm_layer(dim)
         self.mlp = build_moe_mlp(dim, drop=drop, variant=variant, **moe_kwargs)
         self.mlp_drop = nn.Dropout(drop)
@@ -66,13 +68,24 @@ class MoEBlockMlp(nn.Module):
         self.moe_top_k = self.mlp.top_k
         self.tot_expert = self.mlp.num_expert * self.mlp.world_size
 
+    def _fusable(self, x, gate_inp):
+        """Block-level fusion: norm2 + residual inside the layer's kernels."""
+        drop_active = self.training and self.mlp_drop.p > 0
+        return (self.fuse and isinstance(self.norm2, nn.LayerNorm) and x.is_cuda and x.dtype == torch.float32
+                and gate_inp is None and self.mlp.world_size == 1 and not drop_active
+                and tuple(self.norm2.normalized_shape) == (x.shape[-1],))
+
     def forward(self, x, gate_inp=None, task_id=None, task_specific_feature=None, sem=None):
-        normed = self.norm2(x)
+        fused = self._fusable(x, gate_inp)
+        if fused:
+            # x + mlp(norm2(x)) in one pass: ret already contains the residual
+            ret = self.mlp(x, None, task_id, task_specific_feature, sem, fused_norm=self.norm2)
+        else:
+            ret = self.mlp(self.norm2(x), gate_inp, task_id, task_specific_feature, sem)
         if self.variant != "ckpt":
-            return x + self.drop_path(self.mlp_drop(self.mlp(normed, gate_inp, task_id, task_specific_feature, sem)))
-        moe_output, clean_logits, noisy_logits, noise_stddev, top_logits, gates = self.mlp(
-            normed, gate_inp, task_id, task_specific_feature, sem)
-        x = x + self.drop_path(self.mlp_drop(moe_output))
+            return ret if fused else x + self.drop_path(self.mlp_drop(ret))
+        moe_output, clean_logits, noisy_logits, noise_stddev, top_logits, gates = ret
+        x = moe_output if fused else x + self.drop_path(self.mlp_drop(moe_output))
         importance = gates.sum(0)
         if self.moe_top_k < self.tot_expert and abs(noise_stddev) > 1e-6:
             load = _prob_in_top_k(clean_logits, noisy_logits, noise_stddev, top_logits, self.moe_top_k).sum(0)

@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libm3vit_moe.so")
-SOURCES = ["abi.cu", "gate.cu", "route.cu", "permute.cu", "ffn_f32.cu", "ffn_bf16.cu", "ffn_fused.cu"]
+SOURCES = ["abi.cu", "gate.cu", "route.cu", "permute.cu", "ffn_f32.cu", "ffn_bf16.cu", "ffn_fused.cu", "block.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC",     # no --use_fast_math: exact erf/exp/div, parity first

@@ -65,7 +65,8 @@ gate_fwd_kernel(const XT* __restrict__ x, int64_t ldx, const float* __restrict__
                 int32_t* __restrict__ idx_full, float* __restrict__ score, float* __restrict__ top_vals,
                 float* __restrict__ clean_logits, float* __restrict__ noisy_logits,
                 float* __restrict__ gates, float* __restrict__ imp_partial,
-                int32_t* __restrict__ load_partial) {
+                int32_t* __restrict__ load_partial, const float* __restrict__ ln_mean,
+                const float* __restrict__ ln_rstd, const float* __restrict__ ln_gb) {
   using C = GateCfg<E, TM, NW>;
   using Row = GateRow<XT>;
   constexpr int EG = C::EG, TG = C::TG, TOK_W = C::TOK_W;
@@ -136,6 +137,22 @@ gate_fwd_kernel(const XT* __restrict__ x, int64_t ldx, const float* __restrict__
       }
     }
     __syncthreads();
+  }
+
+  // Block-level fusion (block.cu): x is the RAW residual stream and w_gate is gamma-folded, so
+  //   LayerNorm(x) @ W = rstd * (x @ W' - mean * G) + B,   G = ln_gb[0:E], B = ln_gb[E:2E]
+  if (ln_mean != nullptr) {
+    const float4 G = __ldg(reinterpret_cast<const float4*>(ln_gb + eg * 4));
+    const float4 B = __ldg(reinterpret_cast<const float4*>(ln_gb + E + eg * 4));
+#pragma unroll
+    for (int j = 0; j < TM; ++j) {
+      const int t = min(tok_w0 + tg + TG * j, T - 1);
+      const float mu = __ldg(ln_mean + t), rs = __ldg(ln_rstd + t);
+      acc[j][0] = fmaf(rs, acc[j][0] - mu * G.x, B.x);
+      acc[j][1] = fmaf(rs, acc[j][1] - mu * G.y, B.y);
+      acc[j][2] = fmaf(rs, acc[j][2] - mu * G.z, B.z);
+      acc[j][3] = fmaf(rs, acc[j][3] - mu * G.w, B.w);
+    }
   }
 
   // task-conditioned router: constant contribution of the task feature rows
@@ -269,7 +286,7 @@ static int launch_gate_fwd(const void* x, int64_t ldx, const float* task_feat, c
                            const float* noise, float noise_stddev, int T, int D, int Dt, int K, int K1,
                            int64_t* idx, int32_t* idx_full, float* score, float* top_vals, float* clean,
                            float* noisy, float* gates, float* imp_partial, int32_t* load_partial,
-                           cudaStream_t st) {
+                           const float* ln_mean, const float* ln_rstd, const float* ln_gb, cudaStream_t st) {
   using C = GateCfg<E, TM, NW>;
   size_t smem = gate_fwd_smem<E, TM, NW, XT>();
   auto kern = gate_fwd_kernel<E, TM, NW, XT>;
@@ -280,7 +297,7 @@ static int launch_gate_fwd(const void* x, int64_t ldx, const float* task_feat, c
   int grid = m3_ceil_div(T, C::TOK_CTA);
   kern<<<grid, NW * 32, smem, st>>>(static_cast<const XT*>(x), ldx, task_feat, w_gate, noise, noise_stddev, T,
                                     D, Dt, K, K1, idx, idx_full, score, top_vals, clean, noisy, gates,
-                                    imp_partial, load_partial);
+                                    imp_partial, load_partial, ln_mean, ln_rstd, ln_gb);
   M3_LAUNCH_CHECK();
   return M3_OK;
 }
@@ -377,7 +394,9 @@ gate_bwd_dz_kernel(const float* __restrict__ logits, const int32_t* __restrict__
 template <int EW, typename XT>
 __global__ void gate_bwd_dw_kernel(const XT* __restrict__ x, int64_t ldx, const float* __restrict__ dz, int T,
                                    int D, int E, int tok_per_chunk, float* __restrict__ part,
-                                   float* __restrict__ cs_part) {
+                                   float* __restrict__ cs_part, const float* __restrict__ ln_mean,
+                                   const float* __restrict__ ln_rstd, const float* __restrict__ ln_gamma,
+                                   const float* __restrict__ ln_beta) {
   const int ngrp = blockDim.x / (D / 4);          // expert groups per CTA (EB / EW)
   const int dq = threadIdx.x % (D / 4);
   const int eh = threadIdx.x / (D / 4);
@@ -392,6 +411,12 @@ __global__ void gate_bwd_dw_kernel(const XT* __restrict__ x, int64_t ldx, const 
     for (int c = 0; c < EW; ++c) acc[i][c] = 0.f;
 #pragma unroll
   for (int c = 0; c < EW; ++c) cs[c] = 0.f;
+  // Block-level fusion: x is the raw residual stream, normalised on load
+  float lg[4] = {1.f, 1.f, 1.f, 1.f}, lb[4] = {0.f, 0.f, 0.f, 0.f};
+  if (ln_mean != nullptr) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { lg[i] = __ldg(ln_gamma + dq * 4 + i); lb[i] = __ldg(ln_beta + dq * 4 + i); }
+  }
 #pragma unroll 8
   for (int t = t0; t < t1; ++t) {
     float xv[4];
@@ -402,6 +427,11 @@ __global__ void gate_bwd_dw_kernel(const XT* __restrict__ x, int64_t ldx, const 
       uint2 u = __ldg(reinterpret_cast<const uint2*>(x + (int64_t)t * ldx + dq * 4));
       float2 a = bf16x2_to_float2(u.x), b = bf16x2_to_float2(u.y);
       xv[0] = a.x; xv[1] = a.y; xv[2] = b.x; xv[3] = b.y;
+    }
+    if (ln_mean != nullptr) {
+      const float mu = __ldg(ln_mean + t), rs = __ldg(ln_rstd + t);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) xv[i] = fmaf((xv[i] - mu) * rs, lg[i], lb[i]);
     }
     float dv[EW];
 #pragma unroll
@@ -526,7 +556,8 @@ extern "C" int m3_gate_num_partials(int T, int E) {
 }
 
 #define M3_GATE_ARGS x, ldx, task_feat, w_gate, noise, noise_stddev, T, D, Dt, K, K1, idx, idx_full, score, \
-                     top_vals, clean_logits, noisy_logits, gates, imp_partial, load_partial, st
+                     top_vals, clean_logits, noisy_logits, gates, imp_partial, load_partial, ln_mean, ln_rstd, \
+                     ln_gb, st
 #define M3_GATE_CASE_T(EE, XT)                                               \
   switch (gate_cfg_id<EE>(T)) {                                              \
     case 2: return launch_gate_fwd<EE, 8, 4, XT>(M3_GATE_ARGS);              \
@@ -538,11 +569,11 @@ extern "C" int m3_gate_num_partials(int T, int E) {
     if (x_dtype == M3_F32) { M3_GATE_CASE_T(EE, float) }    \
     else { M3_GATE_CASE_T(EE, __nv_bfloat16) }
 
-extern "C" int m3_gate_fwd(const void* x, int x_dtype, int64_t ldx, const float* task_feat, const float* w_gate,
-                           const float* noise, float noise_stddev, int T, int D, int Dt, int E, int K,
-                           int64_t* idx, int32_t* idx_full, float* score, float* top_vals, float* clean_logits,
-                           float* noisy_logits, float* gates, float* imp_partial, int32_t* load_partial,
-                           m3_stream_t stream) {
+static int gate_fwd_impl(const void* x, int x_dtype, int64_t ldx, const float* task_feat, const float* w_gate,
+                         const float* noise, float noise_stddev, int T, int D, int Dt, int E, int K,
+                         int64_t* idx, int32_t* idx_full, float* score, float* top_vals, float* clean_logits,
+                         float* noisy_logits, float* gates, float* imp_partial, int32_t* load_partial,
+                         const float* ln_mean, const float* ln_rstd, const float* ln_gb, m3_stream_t stream) {
   M3_CHECK_ARG(x && w_gate && idx && idx_full && score && top_vals && clean_logits && imp_partial && load_partial);
   M3_CHECK_ARG(T >= 0 && D > 0 && Dt >= 0 && (Dt == 0 || task_feat));
   M3_CHECK_SHAPE(D % kGateDC == 0 && K >= 1 && K <= E && K <= 8);
@@ -567,19 +598,45 @@ extern "C" int m3_gate_fwd(const void* x, int x_dtype, int64_t ldx, const float*
   }
 }
 
+extern "C" int m3_gate_fwd(const void* x, int x_dtype, int64_t ldx, const float* task_feat, const float* w_gate,
+                           const float* noise, float noise_stddev, int T, int D, int Dt, int E, int K,
+                           int64_t* idx, int32_t* idx_full, float* score, float* top_vals, float* clean_logits,
+                           float* noisy_logits, float* gates, float* imp_partial, int32_t* load_partial,
+                           m3_stream_t stream) {
+  return gate_fwd_impl(x, x_dtype, ldx, task_feat, w_gate, noise, noise_stddev, T, D, Dt, E, K, idx, idx_full, score,
+                       top_vals, clean_logits, noisy_logits, gates, imp_partial, load_partial, nullptr, nullptr,
+                       nullptr, stream);
+}
+
+// Block-level fusion: x = RAW fp32 residual stream, w_gate_folded / ln_gb from m3_ln_fold_gate,
+// ln_mean / ln_rstd from m3_ln_stats.
+extern "C" int m3_gate_fwd_ln(const float* x, int64_t ldx, const float* ln_mean, const float* ln_rstd,
+                              const float* ln_gb, const float* task_feat, const float* w_gate_folded,
+                              const float* noise, float noise_stddev, int T, int D, int Dt, int E, int K,
+                              int64_t* idx, int32_t* idx_full, float* score, float* top_vals, float* clean_logits,
+                              float* noisy_logits, float* gates, float* imp_partial, int32_t* load_partial,
+                              m3_stream_t stream) {
+  M3_CHECK_ARG(ln_mean && ln_rstd && ln_gb);
+  M3_CHECK_ALIGN16(ln_gb);
+  return gate_fwd_impl(x, M3_F32, ldx, task_feat, w_gate_folded, noise, noise_stddev, T, D, Dt, E, K, idx, idx_full,
+                       score, top_vals, clean_logits, noisy_logits, gates, imp_partial, load_partial, ln_mean,
+                       ln_rstd, ln_gb, stream);
+}
+
 extern "C" size_t m3_gate_bwd_workspace_bytes(int T, int D, int Dt, int E) {
   (void)Dt;
   const size_t n = (size_t)gate_bwd_chunks(T, E);
   return n * ((size_t)D * E + E) * sizeof(float);
 }
 
-extern "C" int m3_gate_bwd(const void* x, int x_dtype, int64_t ldx, const float* task_feat, const float* w_gate,
-                           const float* logits, const int32_t* idx_full, int T, int D, int Dt, int E, int K,
-                           const float* dscore, const float* dtop_vals, const float* dgates,
-                           const float* dimportance, const float* dclean, const float* dnoisy,
-                           const float* importance, const float* dcv_loss, float* dz, float* dw_gate,
-                           float* dtask_feat, float* dx_gate, void* workspace, size_t workspace_bytes,
-                           m3_stream_t stream) {
+static int gate_bwd_impl(const void* x, int x_dtype, int64_t ldx, const float* task_feat, const float* w_gate,
+                         const float* logits, const int32_t* idx_full, int T, int D, int Dt, int E, int K,
+                         const float* dscore, const float* dtop_vals, const float* dgates,
+                         const float* dimportance, const float* dclean, const float* dnoisy,
+                         const float* importance, const float* dcv_loss, float* dz, float* dw_gate,
+                         float* dtask_feat, float* dx_gate, void* workspace, size_t workspace_bytes,
+                         const float* ln_mean, const float* ln_rstd, const float* ln_gamma, const float* ln_beta,
+                         m3_stream_t stream) {
   if ((importance == nullptr) != (dcv_loss == nullptr)) return M3_ERR_ARG;
   M3_CHECK_ARG(x && w_gate && logits && idx_full && dz && dw_gate && workspace);
   M3_CHECK_ARG(T > 0 && D > 0 && Dt >= 0 && (Dt == 0 || task_feat));
@@ -613,11 +670,11 @@ extern "C" int m3_gate_bwd(const void* x, int x_dtype, int64_t ldx, const float*
     dim3 grid(nchunk, E / EB);
     const int threads = (D / 4) * (EB / EW);
     if (x_dtype == M3_F32) {
-      if (EW == 8) gate_bwd_dw_kernel<8, float><<<grid, threads, 0, st>>>(static_cast<const float*>(x), ldx, dz, T, D, E, tok_per_chunk, part, cs_part);
-      else gate_bwd_dw_kernel<4, float><<<grid, threads, 0, st>>>(static_cast<const float*>(x), ldx, dz, T, D, E, tok_per_chunk, part, cs_part);
+      if (EW == 8) gate_bwd_dw_kernel<8, float><<<grid, threads, 0, st>>>(static_cast<const float*>(x), ldx, dz, T, D, E, tok_per_chunk, part, cs_part, ln_mean, ln_rstd, ln_gamma, ln_beta);
+      else gate_bwd_dw_kernel<4, float><<<grid, threads, 0, st>>>(static_cast<const float*>(x), ldx, dz, T, D, E, tok_per_chunk, part, cs_part, ln_mean, ln_rstd, ln_gamma, ln_beta);
     } else {
-      if (EW == 8) gate_bwd_dw_kernel<8, __nv_bfloat16><<<grid, threads, 0, st>>>(static_cast<const __nv_bfloat16*>(x), ldx, dz, T, D, E, tok_per_chunk, part, cs_part);
-      else gate_bwd_dw_kernel<4, __nv_bfloat16><<<grid, threads, 0, st>>>(static_cast<const __nv_bfloat16*>(x), ldx, dz, T, D, E, tok_per_chunk, part, cs_part);
+      if (EW == 8) gate_bwd_dw_kernel<8, __nv_bfloat16><<<grid, threads, 0, st>>>(static_cast<const __nv_bfloat16*>(x), ldx, dz, T, D, E, tok_per_chunk, part, cs_part, ln_mean, ln_rstd, ln_gamma, ln_beta);
+      else gate_bwd_dw_kernel<4, __nv_bfloat16><<<grid, threads, 0, st>>>(static_cast<const __nv_bfloat16*>(x), ldx, dz, T, D, E, tok_per_chunk, part, cs_part, ln_mean, ln_rstd, ln_gamma, ln_beta);
     }
     M3_LAUNCH_CHECK();
   }
@@ -633,4 +690,31 @@ extern "C" int m3_gate_bwd(const void* x, int x_dtype, int64_t ldx, const float*
     M3_LAUNCH_CHECK();
   }
   return M3_OK;
+}
+
+extern "C" int m3_gate_bwd(const void* x, int x_dtype, int64_t ldx, const float* task_feat, const float* w_gate,
+                           const float* logits, const int32_t* idx_full, int T, int D, int Dt, int E, int K,
+                           const float* dscore, const float* dtop_vals, const float* dgates,
+                           const float* dimportance, const float* dclean, const float* dnoisy,
+                           const float* importance, const float* dcv_loss, float* dz, float* dw_gate,
+                           float* dtask_feat, float* dx_gate, void* workspace, size_t workspace_bytes,
+                           m3_stream_t stream) {
+  return gate_bwd_impl(x, x_dtype, ldx, task_feat, w_gate, logits, idx_full, T, D, Dt, E, K, dscore, dtop_vals, dgates,
+                       dimportance, dclean, dnoisy, importance, dcv_loss, dz, dw_gate, dtask_feat, dx_gate, workspace,
+                       workspace_bytes, nullptr, nullptr, nullptr, nullptr, stream);
+}
+
+// Block-level fusion: x = RAW fp32 residual stream, normalised on load (dw_gate is w.r.t. the
+// ORIGINAL w_gate, which is also what must be passed here).
+extern "C" int m3_gate_bwd_ln(const float* x, int64_t ldx, const float* ln_mean, const float* ln_rstd,
+                              const float* ln_gamma, const float* ln_beta, const float* task_feat,
+                              const float* w_gate, const float* logits, const int32_t* idx_full, int T, int D, int Dt,
+                              int E, int K, const float* dscore, const float* dtop_vals, const float* dgates,
+                              const float* dimportance, const float* dclean, const float* dnoisy,
+                              const float* importance, const float* dcv_loss, float* dz, float* dw_gate,
+                              float* dtask_feat, void* workspace, size_t workspace_bytes, m3_stream_t stream) {
+  M3_CHECK_ARG(ln_mean && ln_rstd && ln_gamma && ln_beta);
+  return gate_bwd_impl(x, M3_F32, ldx, task_feat, w_gate, logits, idx_full, T, D, Dt, E, K, dscore, dtop_vals, dgates,
+                       dimportance, dclean, dnoisy, importance, dcv_loss, dz, dw_gate, dtask_feat, nullptr, workspace,
+                       workspace_bytes, ln_mean, ln_rstd, ln_gamma, ln_beta, stream);
 }

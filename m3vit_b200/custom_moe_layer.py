@@ -176,7 +176,11 @@ class FMoETransformerMLP(nn.Module):
             raise TypeError("'ModuleList' object is not callable: multi_gate=True requires a task_id")
         return self.gate
 
-    def forward(self, inp: torch.Tensor, gate_inp=None, task_id=None, task_specific_feature=None, sem=None):
+    def forward(self, inp: torch.Tensor, gate_inp=None, task_id=None, task_specific_feature=None, sem=None,
+                fused_norm: Optional[nn.LayerNorm] = None):
+        """Reference signature (origin:161).  `fused_norm` is the B200 Block-level extension:
+        when given, `inp` is the RAW residual stream and the call returns  inp + MoE(fused_norm(inp))
+        with the LayerNorm and the residual add fused into the layer's kernels (MoEBlockMlp uses it)."""
         if self.drop_p > 0 and self.training:
             raise NotImplementedError("expert dropout > 0 in training is not implemented (SURVEY.md 8 f4)")
         original_shape = inp.shape
@@ -189,13 +193,13 @@ class FMoETransformerMLP(nn.Module):
             assert self.multi_gate is False                                                       # origin:177
             tf = task_specific_feature.reshape(-1)
         gate = self._select_gate(task_id)
-        out, summaries = self.forward_moe(gate, x, gx, tf)
+        out, summaries = self.forward_moe(gate, x, gx, tf, fused_norm)
         out = out.reshape(original_shape)
         if self.RETURN_SUMMARIES:
             return (out, *summaries)
         return out
 
-    def forward_moe(self, gate: NoisyGate_VMoE, x, gx, tf):
+    def forward_moe(self, gate: NoisyGate_VMoE, x, gx, tf, fused_norm=None):
         if gate.select_idx is not None:
             raise NotImplementedError("gate.select_idx (pruning research path) is not implemented")
         T = x.shape[0]
@@ -204,7 +208,17 @@ class FMoETransformerMLP(nn.Module):
             raise ValueError(f"unsupported input dtype {x.dtype}")
         nstd = float(gate.noise_stddev())
         noise = gate.draw_noise(T, x.device)
-        if self.world_size > 1:
+        if fused_norm is not None:
+            if self.world_size > 1 or gx is not None or x.dtype != torch.float32:
+                raise NotImplementedError("fused_norm: single-GPU, fp32 residual stream, gate_inp is inp")
+            D = x.shape[1]
+            ln_w = fused_norm.weight if fused_norm.weight is not None else x.new_ones(D)
+            ln_b = fused_norm.bias if fused_norm.bias is not None else x.new_zeros(D)
+            res = F_.MoEBlockFunction.apply(
+                x, ln_w, ln_b, gate.w_gate, tf, self.experts.htoh4.weight, self.experts.htoh4.bias,
+                self.experts.h4toh.weight, self.experts.h4toh.bias, noise, float(fused_norm.eps), self.top_k, nstd,
+                cdt, self.RETURN_SUMMARIES, self._wcache)
+        elif self.world_size > 1:
             if self._ep is None:
                 raise RuntimeError("world_size > 1 needs m3vit_b200.ep.attach(layer, group) before the first forward")
             res = self._ep.forward(self, gate, x, gx, tf, noise, nstd, cdt)

@@ -98,6 +98,66 @@ class MoEFunction(torch.autograd.Function):
         return dx, dgx, dwg, dtf, dw1, db1, dw2, db2, None, None, None, None, None, None
 
 
+class MoEBlockFunction(torch.autograd.Function):
+    """out = x + MoE(LayerNorm(x)): the MoE half of a reference Block
+    (/root/reference/models/moe/origin/vision_transformer_moe.py:278-283) with norm2 and the residual add
+    fused into the layer's kernels - the normalised tokens are never materialised.
+
+       inputs : x[T,D] RAW fp32 residual stream, ln_w[D], ln_b[D], then as MoEFunction (gate input == LN(x))
+       outputs: as MoEFunction (out already contains the residual)"""
+
+    @staticmethod
+    def forward(ctx, x, ln_w, ln_b, w_gate, task_feat, w1, b1, w2, b2, noise, eps, top_k, noise_stddev,
+                compute_dtype, want_gates, wcache):
+        T, D = x.shape
+        E = w1.shape[0]
+        x = _c(x)
+        ln = ops.ln_prepare(x, ln_w.detach(), ln_b.detach(), eps, w_gate.detach())
+        g = ops.gate_fwd_ln(x, ln, top_k, task_feat, noise, noise_stddev, want_gates)
+        plan = ops.route_plan(g.idx, E, PAD_ROWS, g.imp_partial, g.load_partial)
+        xq = ops.dispatch_fwd_ln(x, ln, plan, top_k, out_dtype=compute_dtype)
+        if compute_dtype == torch.bfloat16:
+            w1c, w2c, w1t, w2t = wcache.get_bf16(w1, w2)
+        else:
+            w1c, w2c, w1t, w2t = w1, w2, None, None
+        needs_grad = any(ctx.needs_input_grad)
+        yq, hpre = ops.ffn_fwd(xq, plan, w1c, b1, w2c, b2, save_hpre=needs_grad)
+        out = ops.combine_fwd_res(yq, plan, g.score, x)
+        if needs_grad:
+            ctx.save_for_backward(x, ln.mean, ln.rstd, ln.gamma, ln.beta, w_gate, task_feat, w1c, w2c, w1t, w2t, xq,
+                                  hpre, yq, g.score, g.noisy_logits, g.idx_full, plan.counts, plan.offsets, plan.pos,
+                                  plan.tile_expert, plan.importance)
+            ctx.cfg = (top_k, plan.cap_rows)
+        gates = g.gates if g.gates is not None else x.new_empty(0)
+        ctx.mark_non_differentiable(g.idx, plan.load, plan.counts)
+        noisy = g.clean_logits.view_as(g.clean_logits) if noise is None else g.noisy_logits
+        return (out, g.score, g.top_vals, g.clean_logits, noisy, gates, plan.importance, plan.load, g.idx,
+                plan.counts, plan.cv_loss)
+
+    @staticmethod
+    def backward(ctx, d_out, d_score, d_top, d_clean, d_noisy, d_gates, d_imp, _dl, _di, _dc, d_cv):
+        (x, mean, rstd, gamma, beta, w_gate, task_feat, w1c, w2c, w1t, w2t, xq, hpre, yq, score, logits, idx_full,
+         counts, offsets, pos, tile_expert, importance) = ctx.saved_tensors
+        top_k, cap_rows = ctx.cfg
+        T, D = x.shape
+        plan = ops.Plan(counts, offsets, pos, tile_expert, cap_rows, PAD_ROWS)
+        ln = ops.LnState(mean, rstd, gamma, beta, None, None)
+        d_out = torch.zeros_like(x) if d_out is None else _c(d_out).float()
+        dyq, dscore = ops.combine_bwd(d_out, yq, plan, score)
+        dxq, dw1, db1, dw2, db2 = ops.ffn_bwd(xq, hpre, dyq, plan, w1c, w2c, w1t, w2t)
+        if d_score is not None:
+            dscore = dscore + d_score
+        if d_gates is not None and d_gates.numel() == 0:
+            d_gates = None
+        dz, dwg, dtf = ops.gate_bwd_ln(x, ln, w_gate, logits, idx_full, top_k, task_feat, dscore, d_top, d_gates,
+                                       d_imp, d_clean, d_noisy, importance=importance, dcv_loss=d_cv)
+        dxn = ops.dispatch_bwd(dxq, plan, T, top_k, out_dtype=torch.float32, dz=dz, w_gate=w_gate)
+        dx, dgamma, dbeta = ops.ln_bwd_res(dxn, x, ln, d_out)
+        if dtf is not None and task_feat is not None:
+            dtf = dtf.view_as(task_feat).to(task_feat.dtype)
+        return dx, dgamma, dbeta, dwg, dtf, dw1, db1, dw2, db2, None, None, None, None, None, None, None
+
+
 class GateFunction(torch.autograd.Function):
     """The router alone (NoisyGate_VMoE.forward).  outputs as MoEFunction minus `out`."""
 

@@ -18,7 +18,8 @@ from ._lib import PAD_ROWS, check, dtype_code, load, ptr, require_device, stream
 
 # kernels launched by each C entry point (our own kernels; used for bench.py's `gpu_launches`)
 LAUNCHES = {"gate_fwd": 1, "gate_bwd": 3, "gate_bwd_dx": 1, "route_plan": 2, "dispatch_fwd": 1, "dispatch_bwd": 1,
-            "combine_fwd": 1, "combine_bwd": 1, "cast_weights": 1, "ffn_fwd": 2, "ffn_bwd_f32": 6, "ffn_bwd_bf16": 4}
+            "combine_fwd": 1, "combine_bwd": 1, "cast_weights": 1, "ffn_fwd": 2, "ffn_bwd_f32": 6, "ffn_bwd_bf16": 4,
+            "ln_stats": 1, "ln_fold_gate": 1, "ln_bwd_res": 2}
 launch_count = 0
 
 
@@ -266,3 +267,137 @@ def ffn_bwd(xq, hpre, dyq, plan: Plan, w1, w2, w1t=None, w2t=None):
     else:
         _count("ffn_bwd_f32")
     return dxq, dw1, db1, dw2, db2
+
+
+# ------------------------------------------------- Block-level fusion
+@dataclass
+class LnState:
+    """LayerNorm(norm2) folded into the layer: statistics of the raw residual stream + folded router."""
+    mean: torch.Tensor      # [T]
+    rstd: torch.Tensor      # [T]
+    gamma: torch.Tensor     # [D]
+    beta: torch.Tensor      # [D]
+    w_fold: torch.Tensor    # [Dg,E] gamma-scaled router weights
+    gb: torch.Tensor        # [2,E]  {gamma^T W, beta^T W}
+
+
+def ln_prepare(x, gamma, beta, eps, w_gate) -> LnState:
+    """x [T,D] raw fp32 residual stream; gamma/beta [D]; w_gate [Dg,E]."""
+    require_device(x)
+    lib = load()
+    T, D = x.shape
+    Dg, E = w_gate.shape
+    assert x.dtype == torch.float32 and x.is_contiguous() and w_gate.is_contiguous()
+    gamma, beta = gamma.contiguous().float(), beta.contiguous().float()
+    dev = x.device
+    mean, rstd = _f32((T,), dev), _f32((T,), dev)
+    w_fold, gb = _f32((Dg, E), dev), _f32((2, E), dev)
+    check(lib.m3_ln_stats(ptr(x), T, D, float(eps), ptr(mean), ptr(rstd), stream_ptr()), "m3_ln_stats")
+    check(lib.m3_ln_fold_gate(ptr(w_gate), ptr(gamma), ptr(beta), D, Dg, E, ptr(w_fold), ptr(gb), stream_ptr()),
+          "m3_ln_fold_gate")
+    _count("ln_stats")
+    _count("ln_fold_gate")
+    return LnState(mean, rstd, gamma, beta, w_fold, gb)
+
+
+def gate_fwd_ln(x, ln: LnState, top_k, task_feat=None, noise=None, noise_stddev=0.0, want_gates=False) -> GateOut:
+    """gate_fwd of LayerNorm(x) computed from the RAW x (never materialises the normalised tokens)."""
+    require_device(x)
+    lib = load()
+    T, D = x.shape
+    Dg, E = ln.w_fold.shape
+    Dt = Dg - D
+    assert x.dtype == torch.float32 and x.stride(1) == 1
+    assert (Dt == 0) == (task_feat is None), "task_feat must be given iff w_gate has task rows"
+    if task_feat is not None:
+        task_feat = task_feat.reshape(-1).contiguous().float()
+    dev = x.device
+    K = top_k
+    K1 = min(K + 1, E)
+    n_part = lib.m3_gate_num_partials(T, E)
+    if n_part < 0:
+        check(n_part, "m3_gate_num_partials")
+    idx = torch.empty(T, K, dtype=torch.int64, device=dev)
+    idx_full = torch.empty(T, K1, dtype=torch.int32, device=dev)
+    score, top_vals, clean = _f32((T, K), dev), _f32((T, K1), dev), _f32((T, E), dev)
+    noisy = _f32((T, E), dev) if noise is not None else None
+    gates = _f32((T, E), dev) if want_gates else None
+    imp_p = _f32((max(n_part, 1), E), dev)
+    load_p = torch.empty(max(n_part, 1), E, dtype=torch.int32, device=dev)
+    check(lib.m3_gate_fwd_ln(ptr(x), x.stride(0), ptr(ln.mean), ptr(ln.rstd), ptr(ln.gb), ptr(task_feat),
+                             ptr(ln.w_fold), ptr(noise), float(noise_stddev), T, D, Dt, E, K, ptr(idx), ptr(idx_full),
+                             ptr(score), ptr(top_vals), ptr(clean), ptr(noisy), ptr(gates), ptr(imp_p), ptr(load_p),
+                             stream_ptr()), "m3_gate_fwd_ln")
+    _count("gate_fwd")
+    return GateOut(idx, idx_full, score, top_vals, clean, noisy if noisy is not None else clean, gates,
+                   imp_p[:n_part], load_p[:n_part])
+
+
+def dispatch_fwd_ln(x, ln: LnState, plan: Plan, top_k, out_dtype=torch.float32):
+    require_device(x)
+    T, D = x.shape
+    xq = torch.empty(plan.cap_rows, D, dtype=out_dtype, device=x.device)
+    E = plan.counts.numel()
+    check(load().m3_dispatch_fwd_ln(ptr(x), ptr(ln.mean), ptr(ln.rstd), ptr(ln.gamma), ptr(ln.beta), ptr(plan.pos),
+                                    ptr(plan.counts), ptr(plan.offsets), T, top_k, D, E, ptr(xq), dtype_code(xq),
+                                    stream_ptr()), "m3_dispatch_fwd_ln")
+    _count("dispatch_fwd")
+    return xq
+
+
+def combine_fwd_res(yq, plan: Plan, score, residual):
+    require_device(yq)
+    T, K = score.shape
+    D = yq.shape[1]
+    assert residual.dtype == torch.float32 and residual.is_contiguous() and residual.shape == (T, D)
+    out = _f32((T, D), yq.device)
+    check(load().m3_combine_fwd_res(ptr(yq), dtype_code(yq), ptr(plan.pos), ptr(score), ptr(residual), T, K, D,
+                                    ptr(out), stream_ptr()), "m3_combine_fwd_res")
+    _count("combine_fwd")
+    return out
+
+
+def gate_bwd_ln(x, ln: LnState, w_gate, logits, idx_full, top_k, task_feat=None, dscore=None, dtop_vals=None,
+                dgates=None, dimportance=None, dclean=None, dnoisy=None, importance=None, dcv_loss=None):
+    """gate_bwd with x normalised on load.  returns dz [T,E], dw_gate [Dg,E], dtask_feat [Dt] or None"""
+    require_device(x)
+    lib = load()
+    T, D = x.shape
+    Dg, E = w_gate.shape
+    Dt = Dg - D
+    dev = x.device
+    if task_feat is not None:
+        task_feat = task_feat.reshape(-1).contiguous().float()
+
+    def c(t):
+        return None if t is None else t.contiguous().float()
+    dscore, dtop_vals, dgates, dimportance, dclean, dnoisy = map(c, (dscore, dtop_vals, dgates, dimportance, dclean, dnoisy))
+    if dcv_loss is not None:
+        dcv_loss = dcv_loss.reshape(1).contiguous().float()
+        assert importance is not None
+    dz, dw = _f32((T, E), dev), _f32((Dg, E), dev)
+    dtf = _f32((Dt,), dev) if Dt > 0 else None
+    ws = _ws(lib.m3_gate_bwd_workspace_bytes(T, D, Dt, E), dev)
+    check(lib.m3_gate_bwd_ln(ptr(x), x.stride(0), ptr(ln.mean), ptr(ln.rstd), ptr(ln.gamma), ptr(ln.beta),
+                             ptr(task_feat), ptr(w_gate), ptr(logits), ptr(idx_full), T, D, Dt, E, top_k, ptr(dscore),
+                             ptr(dtop_vals), ptr(dgates), ptr(dimportance), ptr(dclean), ptr(dnoisy),
+                             ptr(importance) if dcv_loss is not None else None, ptr(dcv_loss), ptr(dz), ptr(dw),
+                             ptr(dtf), ptr(ws), ws.numel(), stream_ptr()), "m3_gate_bwd_ln")
+    _count("gate_bwd")
+    return dz, dw, dtf
+
+
+def ln_bwd_res(dxn, x, ln: LnState, dres):
+    """dx = dres + LayerNorm'(dxn) wrt the raw x;  returns dx [T,D], dgamma [D], dbeta [D]"""
+    require_device(dxn)
+    lib = load()
+    T, D = x.shape
+    dev = x.device
+    dxn, dres = dxn.contiguous(), dres.contiguous()
+    assert dxn.dtype == torch.float32 and dres.dtype == torch.float32
+    dx, dgamma, dbeta = _f32((T, D), dev), _f32((D,), dev), _f32((D,), dev)
+    ws = _ws(lib.m3_ln_bwd_workspace_bytes(T, D), dev)
+    check(lib.m3_ln_bwd_res(ptr(dxn), ptr(x), ptr(ln.mean), ptr(ln.rstd), ptr(ln.gamma), ptr(dres), T, D, ptr(dx),
+                            ptr(dgamma), ptr(dbeta), ptr(ws), ws.numel(), stream_ptr()), "m3_ln_bwd_res")
+    _count("ln_bwd_res")
+    return dx, dgamma, dbeta

@@ -112,6 +112,45 @@ def make_case(case: MoECase, seed: int, min_gap: float = 1e-5, max_rounds: int =
     return dict(x=x, grad_out=grad_out, task_feat=tfeat, resampled=resampled, **w)
 
 
+def make_block_case(case: MoECase, seed: int, min_gap: float = 1e-5, max_rounds: int = 50):
+    """Inputs for the Block-level path  x + mlp(norm2(x))  (SURVEY.md 8 f1): a RAW residual stream
+    (per-token mean ~ N(0,1), scale ~ U(0.5,3)) and non-trivial LayerNorm affine parameters.  Routing gaps are
+    certified in fp64 on the normalised gate input, like make_case."""
+    d = make_case(case, seed, min_gap=0.0)
+    gen = torch.Generator().manual_seed(3000 + seed)
+    D = case.d_model
+    ln_w = 1.0 + 0.1 * torch.randn(D, generator=gen, dtype=torch.float32)
+    ln_b = 0.1 * torch.randn(D, generator=gen, dtype=torch.float32)
+    eps = 1e-6                                      # partial(nn.LayerNorm, eps=1e-6) in the reference ViT
+
+    def raw(n):
+        z = torch.randn(n, D, generator=gen, dtype=torch.float32)
+        scale = 0.5 + 2.5 * torch.rand(n, 1, generator=gen, dtype=torch.float32)
+        shift = torch.randn(n, 1, generator=gen, dtype=torch.float32)
+        return z * scale + shift
+    flat = raw(case.T)
+    tfeat = d["task_feat"]
+    kk = min(case.top_k + 2, case.num_expert)
+    resampled = 0
+    for _ in range(max_rounds):
+        g = torch.nn.functional.layer_norm(flat.double(), (D,), ln_w.double(), ln_b.double(), eps)
+        if tfeat is not None:
+            g = torch.cat((g, tfeat.double().view(1, -1).expand(g.shape[0], -1)), 1)
+        bad = torch.zeros(flat.shape[0], dtype=torch.bool)
+        for wg in d["w_gate"]:
+            v = torch.softmax(g @ wg.double(), 1).topk(kk, 1).values
+            bad |= (v[:, :-1] - v[:, 1:]).min(1).values < min_gap
+        n_bad = int(bad.sum())
+        if n_bad == 0 or min_gap <= 0:
+            break
+        resampled += n_bad
+        flat[bad] = raw(n_bad)
+    else:
+        raise RuntimeError("could not certify routing gaps")
+    d.update(x=flat.view(case.batch, case.tokens, D), ln_w=ln_w, ln_b=ln_b, ln_eps=eps, resampled=resampled)
+    return d
+
+
 def device_tokens(T: int, d_model: int, seed: int, device, dtype=torch.float32):
     """Benchmark-size tokens generated on the device (no gap certification)."""
     gen = torch.Generator(device=device).manual_seed(2000 + seed)

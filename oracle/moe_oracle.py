@@ -19,6 +19,7 @@ layer hot path.  Each function cites the reference lines it follows
                     restated in oracle/shim/fmoe/functions.py)
   expert_ffn        models/moe/origin/custom_moe_layer.py:36-44 (+ FMoELinear)
   layer_forward     models/moe/origin/custom_moe_layer.py:161-314
+  block_mlp_forward models/moe/origin/vision_transformer_moe.py:278-283 (MoE half of Block)
 
 PARITY PIN: the reference ships no tests or golden vectors for this path
 (SURVEY.md section 4).  The oracle is pinned instead against outputs of the
@@ -202,6 +203,17 @@ def layer_forward(
     out = combine(yq, pos, gd["score"])
     gd["counts"] = counts
     return out.reshape(shape), gd
+
+
+def block_mlp_forward(x, ln_w, ln_b, ln_eps, w_gate, w1, b1, w2, b2, top_k, task_specific_feature=None,
+                      noise_std: float = 0.0, training: bool = False, noise=None):
+    """The MoE half of the reference Block, origin/vision_transformer_moe.py:282-283 with drop = drop_path = 0:
+        x = x + self.drop_path(self.mlp_drop(self.mlp(self.norm2(x), gate_inp, task_id, task_specific_feature, sem)))
+    norm2 = nn.LayerNorm(dim, eps) (:246), gate_inp = None.  Returns (x_out, gate dict)."""
+    normed = F.layer_norm(x, (x.shape[-1],), ln_w, ln_b, ln_eps)
+    out, gd = layer_forward(normed, w_gate, w1, b1, w2, b2, top_k, None, task_specific_feature, noise_std,
+                            training, noise)
+    return x + out, gd
 
 
 def min_topk_gap(probs64: torch.Tensor, k_plus_1: int) -> torch.Tensor:

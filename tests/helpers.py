@@ -3,7 +3,7 @@ import os
 
 import torch
 
-from m3vit_b200.synthetic import MoECase, make_case
+from m3vit_b200.synthetic import MoECase, make_block_case, make_case
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
@@ -11,7 +11,7 @@ GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 def load_fixture(fname):
     fx = torch.load(os.path.join(GOLDEN, fname), weights_only=False)
     case = MoECase(**fx["case"])
-    data = make_case(case, fx["seed"])
+    data = make_block_case(case, fx["seed"]) if fx.get("block") else make_case(case, fx["seed"])
     if case.name.startswith("S6"):   # same starvation edit as oracle/make_golden.py
         for w in data["w_gate"]:
             w[:, 3] = 0.0
@@ -21,10 +21,15 @@ def load_fixture(fname):
         data["x"][..., 0] = data["x"][..., 0].abs() + 0.1
     # RNG drift check: regenerated tensors must be the ones the fixture was made from
     for k, (s, a) in fx["checksums"].items():
-        t = data["w_gate"][int(k[6:])] if k.startswith("w_gate") else data[k]
+        t = data["w_gate"][int(k[6:])] if k.startswith("w_gate") and k != "w_gate" else data[k]
         assert abs(float(t.double().sum()) - s) <= 1e-9 * max(1.0, a), f"RNG drift in {k}"
     return fx, case, data
 
 
 def all_fixtures(prefix=""):
-    return sorted(f for f in os.listdir(GOLDEN) if f.endswith(".pt") and f.startswith(prefix))
+    """MoE-layer fixtures (S*, C*); the Block-level ones (B*) are listed by block_fixtures()."""
+    return sorted(f for f in os.listdir(GOLDEN) if f.endswith(".pt") and f.startswith(prefix) and not f.startswith("B"))
+
+
+def block_fixtures():
+    return sorted(f for f in os.listdir(GOLDEN) if f.endswith(".pt") and f.startswith("B"))

@@ -3,7 +3,7 @@ fixtures produced by the reference's own files (oracle/make_golden.py)."""
 import pytest
 import torch
 
-from helpers import all_fixtures, load_fixture
+from helpers import all_fixtures, block_fixtures, load_fixture
 from oracle import moe_oracle as O
 
 
@@ -56,6 +56,33 @@ def test_ckpt_variant_summaries(fname):
         assert torch.equal(imp, rec["importance"])
         assert torch.equal(load, rec["load"])
         assert float(loss) == pytest.approx(rec["loss"], rel=1e-6)
+
+
+@pytest.mark.parametrize("fname", block_fixtures())
+def test_block_restatement_matches_reference_block_fixture(fname):
+    """Block-level path: O.block_mlp_forward against the reference Block.forward
+    (origin/vision_transformer_moe.py:274-283, attention stubbed to zero) run by oracle/make_golden.py."""
+    fx, case, data = load_fixture(fname)
+    stride = fx["row_stride"]
+    for (task, mode), rec in fx["tasks"].items():
+        train = mode == "train"
+        x = data["x"].clone().requires_grad_(train)
+        lw, lb = data["ln_w"].clone().requires_grad_(train), data["ln_b"].clone().requires_grad_(train)
+        wg = data["w_gate"][task if task is not None else 0].clone().requires_grad_(train)
+        out, gd = O.block_mlp_forward(x, lw, lb, data["ln_eps"], wg, data["w1"], data["b1"], data["w2"], data["b2"],
+                                      case.top_k, task_specific_feature=data["task_feat"], training=train)
+        assert torch.equal(gd["idx"].to(torch.int16), rec["idx"])
+        assert torch.equal(gd["counts"], rec["counts"])
+        assert torch.equal(gd["score"], rec["score"])
+        assert torch.equal(out.reshape(case.T, -1)[::stride], rec["out"])
+        if train:
+            assert float(gd["loss"]) == pytest.approx(rec["loss"], rel=1e-6)
+            (out * data["grad_out"]).sum().backward()
+            torch.testing.assert_close(x.grad.reshape(case.T, -1)[::stride], rec["dx"], rtol=1e-5, atol=1e-6)
+            torch.testing.assert_close(lw.grad, rec["grads"]["norm2.weight"], rtol=1e-4, atol=1e-5)
+            torch.testing.assert_close(lb.grad, rec["grads"]["norm2.bias"], rtol=1e-4, atol=1e-5)
+            gname = f"mlp.gate.{task}.w_gate" if task is not None else "mlp.gate.w_gate"
+            torch.testing.assert_close(wg.grad, rec["grads"][gname], rtol=1e-5, atol=1e-6)
 
 
 def test_fixture_gaps_are_certified():
