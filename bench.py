@@ -12,8 +12,8 @@ Metric: MoE-layer tokens/s = (layer calls x B x N) / time, whole job.
 
 value  : tokens resident in HBM, CUDA-event timed, max over ranks.
 e2e    : same step through the public module API with HOST (pinned) token buffers:
-         per layer call H2D of the tokens and D2H of the loss scalars inside the
-         timed region.
+         per layer call H2D of the tokens (prefetched one call ahead on a copy stream,
+         double-buffered) and D2H of the loss scalars inside the timed region.
 roofline: the grouped expert-FFN GEMM kernel (gg_kernel), tensor-bound, timed live.
 cpu_baseline / --impl reference: the CPU oracle port of the reference layer
          (oracle/moe_oracle.py, fp32 PyTorch on the host cores) on a bounded
@@ -292,14 +292,36 @@ def main():
     hloss = torch.empty(len(calls), dtype=torch.float32).pin_memory()
     dloss = torch.empty(len(calls), dtype=torch.float32, device=dev)
 
+    # The next call's tokens are prefetched on a copy stream into a double-buffered device slot
+    # while the current call computes (what an input pipeline does); every byte still crosses PCIe
+    # inside the timed region and the compute stream waits for each copy's event.
+    copy_stream = torch.cuda.Stream(device=dev)
+    xbuf = [torch.empty(T, D_MODEL, device=dev) for _ in range(2)]
+    ev_ready = [torch.cuda.Event() for _ in range(2)]
+    ev_free = [torch.cuda.Event() for _ in range(2)]
+
+    def prefetch(i):
+        b = i & 1
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(ev_free[b])          # slot b's previous fwd+bwd has finished
+            xbuf[b].copy_(hx[b], non_blocking=True)
+            ev_ready[b].record(copy_stream)
+
     def step_e2e():
+        cur = torch.cuda.current_stream()
+        for b in range(2):
+            ev_free[b].record(cur)
+        prefetch(0)
         for i, (li, t) in enumerate(calls):
-            x = torch.empty(T, D_MODEL, device=dev)
-            x.copy_(hx[i & 1], non_blocking=True)
-            x.requires_grad_(True)
-            dloss[i] = one_call(layers[li], x, gs[i & 1], t).detach()
+            b = i & 1
+            if i + 1 < len(calls):
+                prefetch(i + 1)
+            cur.wait_event(ev_ready[b])
+            x = xbuf[b].detach().requires_grad_(True)
+            dloss[i] = one_call(layers[li], x, gs[b], t).detach()
+            ev_free[b].record(cur)
         hloss.copy_(dloss, non_blocking=True)
-        torch.cuda.current_stream().synchronize()
+        cur.synchronize()
 
     e2e_steps = max(2, min(args.steps, 5))
     step_e2e()

@@ -225,8 +225,9 @@ int m3_ep_barrier(void* const* peer_flags, void* const* peer_gather, const int32
  * LayerNorm (norm2) and residual-add passes.  x is the RAW fp32 residual stream [T, D]; the
  * normalised tokens are never written to memory.
  *   m3_ln_stats        mean[T], rstd[T] = 1/sqrt(var_biased + eps)      (torch.nn.LayerNorm)
- *   m3_ln_fold_gate    w_fold[Dg,E] = gamma (.) w_gate (rows >= D copied), gb[2,E] = {gamma^T W, beta^T W}
- *   m3_gate_fwd_ln     m3_gate_fwd on raw x:  z = rstd * (x @ w_fold - mean * gb[0]) + gb[1]
+ *   m3_ln_fold_gate    gb[2,E] = {G = gamma^T W, B = beta^T W};  w_fold[Dg,E] = gamma (.) w_gate - G/D
+ *                      (column-centred, so the token mean cancels exactly; rows >= D copied)
+ *   m3_gate_fwd_ln     m3_gate_fwd on raw x:  z = rstd * (x @ w_fold) + gb[1]
  *   m3_dispatch_fwd_ln m3_dispatch_fwd with LayerNorm applied on the fly
  *   m3_combine_fwd_res out[T,D] (fp32) = residual + sum_k score * yq[pos]
  *   m3_gate_bwd_ln     m3_gate_bwd with x normalised on load (w_gate = the ORIGINAL weights)

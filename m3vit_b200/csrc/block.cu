@@ -6,8 +6,8 @@
 // on each side of the hot path.  Here the normalised tokens are never materialised:
 //
 //   ln_stats_kernel         per-token mean / rstd of the raw residual stream (one read of x)
-//   ln_fold_gate_kernel     W' = gamma (.) w_gate,  G = gamma^T w_gate,  B = beta^T w_gate, so
-//                           that the gate kernel runs on RAW x:  z = rstd*(x W' - mean*G) + B
+//   ln_fold_gate_kernel     W' = gamma (.) w_gate - colmean,  B = beta^T w_gate, so that the gate
+//                           kernel runs on RAW x:  z = rstd * (x W') + B
 //   dispatch_fwd_ln_kernel  normalises on the fly while copying a token to its K queue rows
 //   combine_fwd_res_kernel  out = x + sum_k score*yq                 (residual fused)
 //   ln_bwd_res_kernel       dx = d_out + LayerNorm'(dxn), per-CTA partial dgamma / dbeta
@@ -66,24 +66,39 @@ ln_stats_kernel(const float* __restrict__ x, int T, int D, float eps, float* __r
   }
 }
 
-// w_fold[d,e] = gamma[d]*w_gate[d,e] (d < D; task-feature rows d >= D copied),
-// gb[0,e] = sum_d gamma[d]*w_gate[d,e],  gb[1,e] = sum_d beta[d]*w_gate[d,e]   (sequential in d)
+// gb[0,e] = G_e = sum_d gamma[d]*w_gate[d,e],  gb[1,e] = B_e = sum_d beta[d]*w_gate[d,e]
+// w_fold[d,e] = gamma[d]*w_gate[d,e] - G_e/D  for d < D  (task-feature rows d >= D copied).
+// The columns are CENTRED: since sum_d (x_d - mean) = 0,
+//   LayerNorm(x) @ W = rstd * sum_d (x_d - mean) * gamma_d W_de + B_e = rstd * (x @ w_fold)_e + B_e
+// holds with the raw x and no  "- mean * G"  correction term (which would cancel catastrophically
+// for tokens whose |mean| is large against their spread).
 __global__ void __launch_bounds__(1024)
 ln_fold_gate_kernel(const float* __restrict__ w_gate, const float* __restrict__ gamma, const float* __restrict__ beta,
                     int D, int Dg, int E, float* __restrict__ w_fold, float* __restrict__ gb) {
-  for (int i = threadIdx.x; i < Dg * E; i += blockDim.x) {
-    const int d = i / E;
-    w_fold[i] = d < D ? gamma[d] * w_gate[i] : w_gate[i];
-  }
-  for (int e = threadIdx.x; e < E; e += blockDim.x) {
+  __shared__ float cm[1024];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int e = warp; e < E; e += 32) {     // one warp per column, fixed reduction order
     float g = 0.f, b = 0.f;
-    for (int d = 0; d < D; ++d) {
+    for (int d = lane; d < D; d += 32) {
       const float w = w_gate[(int64_t)d * E + e];
       g = fmaf(gamma[d], w, g);
       b = fmaf(beta[d], w, b);
     }
-    gb[e] = g;
-    gb[E + e] = b;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      g += __shfl_xor_sync(0xffffffffu, g, o);
+      b += __shfl_xor_sync(0xffffffffu, b, o);
+    }
+    if (lane == 0) {
+      gb[e] = g;
+      gb[E + e] = b;
+      cm[e] = g / (float)D;
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < Dg * E; i += blockDim.x) {
+    const int d = i / E, e = i % E;
+    w_fold[i] = d < D ? fmaf(gamma[d], w_gate[i], -cm[e]) : w_gate[i];
   }
 }
 
@@ -184,85 +199,89 @@ combine_fwd_res_kernel(const TI* __restrict__ yq, const int32_t* __restrict__ po
 // LayerNorm backward + residual:
 //   xh = (x-mean)*rstd, gg = dxn*gamma, dx = dres + rstd*(gg - mean_d(gg) - xh*mean_d(gg*xh))
 //   part[cta][0][d] = sum_t dxn*xh (dgamma),  part[cta][1][d] = sum_t dxn (dbeta)
-// Grid-stride over tokens; per-thread partials are combined group by group in a fixed order.
-template <int NV>
+// One WARP per token, float4 slices (NQ per lane): the six per-token arrays stay at 4*NQ registers
+// each, so several CTAs fit an SM.  Grid-stride over tokens; per-thread partials are combined warp
+// by warp in a fixed order.
+constexpr int kLnbWarps = kBlkThreads / 32;
+
+__device__ __forceinline__ float4 ld4_stream(const float* p) {
+  const uint4 u = ldg_stream(p);
+  return make_float4(__uint_as_float(u.x), __uint_as_float(u.y), __uint_as_float(u.z), __uint_as_float(u.w));
+}
+template <int NQ>
 __global__ void __launch_bounds__(kBlkThreads)
 ln_bwd_res_kernel(const float* __restrict__ dxn, const float* __restrict__ x, const float* __restrict__ mean,
                   const float* __restrict__ rstd, const float* __restrict__ gamma, const float* __restrict__ dres,
                   int T, int D, float* __restrict__ dx, float* __restrict__ part) {
   extern __shared__ __align__(16) float red[];  // [2][D]
-  const int sub = threadIdx.x % kBlkLanes;
-  const int grp = threadIdx.x / kBlkLanes;
-  const int nvec = D / 8;
-  Vec8 gm[NV], dg[NV], db[NV];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int nq = D / 4;
+  float4 gm[NQ], dg[NQ], db[NQ];
 #pragma unroll
-  for (int i = 0; i < NV; ++i) {
-    const int c = sub + i * kBlkLanes;
-#pragma unroll
-    for (int j = 0; j < 8; ++j) { dg[i].v[j] = 0.f; db[i].v[j] = 0.f; gm[i].v[j] = 0.f; }
-    if (c < nvec) gm[i] = load8<float>(gamma + c * 8);
+  for (int i = 0; i < NQ; ++i) {
+    const int c = lane + i * 32;
+    dg[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    db[i] = dg[i];
+    gm[i] = c < nq ? __ldg(reinterpret_cast<const float4*>(gamma) + c) : dg[i];
   }
   const float invD = 1.f / (float)D;
-  for (int tb = blockIdx.x * kBlkTok; tb < T; tb += gridDim.x * kBlkTok) {
-    const int tt = tb + grp;
-    const bool valid = tt < T;
-    const int t = valid ? tt : T - 1;
+  for (int t = blockIdx.x * kLnbWarps + warp; t < T; t += gridDim.x * kLnbWarps) {
     const float mu = __ldg(mean + t), rs = __ldg(rstd + t);
-    Vec8 g[NV], xh[NV], dr[NV];
+    float4 g[NQ], xh[NQ], dr[NQ];
+#pragma unroll
+    for (int i = 0; i < NQ; ++i) {
+      const int c = lane + i * 32;
+      if (c < nq) {
+        g[i] = ld4_stream(dxn + (int64_t)t * D + c * 4);
+        xh[i] = ld4_stream(x + (int64_t)t * D + c * 4);
+        dr[i] = ld4_stream(dres + (int64_t)t * D + c * 4);
+      }
+    }
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-    for (int i = 0; i < NV; ++i) {
-      const int c = sub + i * kBlkLanes;
-      if (c < nvec) {
-        g[i] = load8<float>(dxn + (int64_t)t * D + c * 8);
-        xh[i] = load8<float>(x + (int64_t)t * D + c * 8);
-        dr[i] = load8<float>(dres + (int64_t)t * D + c * 8);
-      }
-    }
+    for (int i = 0; i < NQ; ++i) {
+      const int c = lane + i * 32;
+      if (c < nq) {
+        float* gp = &g[i].x; float* xp = &xh[i].x; const float* mp = &gm[i].x;
+        float* dgp = &dg[i].x; float* dbp = &db[i].x;
 #pragma unroll
-    for (int i = 0; i < NV; ++i) {
-      const int c = sub + i * kBlkLanes;
-      if (c < nvec) {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          xh[i].v[j] = (xh[i].v[j] - mu) * rs;
-          const float gg = g[i].v[j] * gm[i].v[j];
-          s1 += gg;
-          s2 = fmaf(gg, xh[i].v[j], s2);
-          if (valid) {
-            dg[i].v[j] = fmaf(g[i].v[j], xh[i].v[j], dg[i].v[j]);
-            db[i].v[j] += g[i].v[j];
-          }
+        for (int j = 0; j < 4; ++j) {
+          xp[j] = (xp[j] - mu) * rs;
+          dgp[j] = fmaf(gp[j], xp[j], dgp[j]);
+          dbp[j] += gp[j];
+          gp[j] *= mp[j];                 // gg
+          s1 += gp[j];
+          s2 = fmaf(gp[j], xp[j], s2);
         }
       }
     }
-    const float c1 = group16_sum(s1) * invD, c2 = group16_sum(s2) * invD;
-    if (valid) {
+    const float c1 = warp_sum(s1) * invD, c2 = warp_sum(s2) * invD;
 #pragma unroll
-      for (int i = 0; i < NV; ++i) {
-        const int c = sub + i * kBlkLanes;
-        if (c < nvec) {
-          Vec8 o;
-#pragma unroll
-          for (int j = 0; j < 8; ++j)
-            o.v[j] = fmaf(rs, g[i].v[j] * gm[i].v[j] - c1 - xh[i].v[j] * c2, dr[i].v[j]);
-          store8<float>(dx + (int64_t)t * D + c * 8, o);
-        }
+    for (int i = 0; i < NQ; ++i) {
+      const int c = lane + i * 32;
+      if (c < nq) {
+        uint4 o;
+        o.x = __float_as_uint(fmaf(rs, g[i].x - c1 - xh[i].x * c2, dr[i].x));
+        o.y = __float_as_uint(fmaf(rs, g[i].y - c1 - xh[i].y * c2, dr[i].y));
+        o.z = __float_as_uint(fmaf(rs, g[i].z - c1 - xh[i].z * c2, dr[i].z));
+        o.w = __float_as_uint(fmaf(rs, g[i].w - c1 - xh[i].w * c2, dr[i].w));
+        stg_stream(dx + (int64_t)t * D + c * 4, o);
       }
     }
   }
   for (int i = threadIdx.x; i < 2 * D; i += kBlkThreads) red[i] = 0.f;
   __syncthreads();
-  for (int gq = 0; gq < kBlkTok; ++gq) {
-    if (grp == gq) {
+  for (int w = 0; w < kLnbWarps; ++w) {
+    if (warp == w) {
 #pragma unroll
-      for (int i = 0; i < NV; ++i) {
-        const int c = sub + i * kBlkLanes;
-        if (c < nvec) {
+      for (int i = 0; i < NQ; ++i) {
+        const int c = lane + i * 32;
+        if (c < nq) {
+          const float* dgp = &dg[i].x; const float* dbp = &db[i].x;
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            red[c * 8 + j] += dg[i].v[j];
-            red[D + c * 8 + j] += db[i].v[j];
+          for (int j = 0; j < 4; ++j) {
+            red[c * 4 + j] += dgp[j];
+            red[D + c * 4 + j] += dbp[j];
           }
         }
       }
@@ -295,7 +314,7 @@ ln_bwd_reduce_kernel(const float* __restrict__ part, int nparts, int D, float* _
 
 static inline int blk_nv(int D) { return m3_ceil_div(D / 8, kBlkLanes); }
 static inline int ln_bwd_ctas(int T) {
-  int n = m3_ceil_div(T, kBlkTok);
+  int n = m3_ceil_div(T, kLnbWarps);
   if (n > 2 * kNumSMs) n = 2 * kNumSMs;
   return n < 1 ? 1 : n;
 }
@@ -341,7 +360,7 @@ extern "C" int m3_ln_stats(const float* x, int T, int D, float eps, float* mean,
 extern "C" int m3_ln_fold_gate(const float* w_gate, const float* gamma, const float* beta, int D, int Dg, int E,
                                float* w_fold, float* gb, m3_stream_t stream) {
   M3_CHECK_ARG(w_gate && gamma && beta && w_fold && gb);
-  M3_CHECK_ARG(D > 0 && Dg >= D && E > 0);
+  M3_CHECK_ARG(D > 0 && Dg >= D && E > 0 && E <= 1024);
   ln_fold_gate_kernel<<<1, 1024, 0, static_cast<cudaStream_t>(stream)>>>(w_gate, gamma, beta, D, Dg, E, w_fold, gb);
   M3_LAUNCH_CHECK();
   return M3_OK;
@@ -406,11 +425,15 @@ extern "C" int m3_ln_bwd_res(const float* dxn, const float* x, const float* mean
   M3_CHECK_ALIGN16(dxn); M3_CHECK_ALIGN16(x); M3_CHECK_ALIGN16(dres); M3_CHECK_ALIGN16(dx); M3_CHECK_ALIGN16(gamma);
   if (workspace_bytes < m3_ln_bwd_workspace_bytes(T, D)) return M3_ERR_WORKSPACE;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  const int nv = blk_nv(D);
   const int grid = ln_bwd_ctas(T);
   const size_t smem = 2 * (size_t)D * sizeof(float);
   float* part = static_cast<float*>(workspace);
-  M3_BLK_NV_SWITCH((ln_bwd_res_kernel<NV><<<grid, kBlkThreads, smem, st>>>(dxn, x, mean, rstd, gamma, dres, T, D, dx, part)))
+  switch (m3_ceil_div(D / 4, 32)) {
+#define M3_LNB_CASE(Q) \
+  case Q: ln_bwd_res_kernel<Q><<<grid, kBlkThreads, smem, st>>>(dxn, x, mean, rstd, gamma, dres, T, D, dx, part); break;
+    M3_LNB_CASE(1) M3_LNB_CASE(2) M3_LNB_CASE(3) M3_LNB_CASE(4) M3_LNB_CASE(5) M3_LNB_CASE(6) M3_LNB_CASE(7) M3_LNB_CASE(8)
+    default: return M3_ERR_SHAPE;
+  }
   M3_LAUNCH_CHECK();
   ln_bwd_reduce_kernel<<<m3_ceil_div(2 * D, 32), 1024, 0, st>>>(part, grid, D, dgamma, dbeta);
   M3_LAUNCH_CHECK();

@@ -139,19 +139,18 @@ gate_fwd_kernel(const XT* __restrict__ x, int64_t ldx, const float* __restrict__
     __syncthreads();
   }
 
-  // Block-level fusion (block.cu): x is the RAW residual stream and w_gate is gamma-folded, so
-  //   LayerNorm(x) @ W = rstd * (x @ W' - mean * G) + B,   G = ln_gb[0:E], B = ln_gb[E:2E]
+  // Block-level fusion (block.cu): x is the RAW residual stream and w_gate is gamma-folded and
+  // column-centred, so  LayerNorm(x) @ W = rstd * (x @ W') + B,   B = ln_gb[E:2E]
   if (ln_mean != nullptr) {
-    const float4 G = __ldg(reinterpret_cast<const float4*>(ln_gb + eg * 4));
     const float4 B = __ldg(reinterpret_cast<const float4*>(ln_gb + E + eg * 4));
 #pragma unroll
     for (int j = 0; j < TM; ++j) {
       const int t = min(tok_w0 + tg + TG * j, T - 1);
-      const float mu = __ldg(ln_mean + t), rs = __ldg(ln_rstd + t);
-      acc[j][0] = fmaf(rs, acc[j][0] - mu * G.x, B.x);
-      acc[j][1] = fmaf(rs, acc[j][1] - mu * G.y, B.y);
-      acc[j][2] = fmaf(rs, acc[j][2] - mu * G.z, B.z);
-      acc[j][3] = fmaf(rs, acc[j][3] - mu * G.w, B.w);
+      const float rs = __ldg(ln_rstd + t);
+      acc[j][0] = fmaf(rs, acc[j][0], B.x);
+      acc[j][1] = fmaf(rs, acc[j][1], B.y);
+      acc[j][2] = fmaf(rs, acc[j][2], B.z);
+      acc[j][3] = fmaf(rs, acc[j][3], B.w);
     }
   }
 
@@ -391,8 +390,9 @@ gate_bwd_dz_kernel(const float* __restrict__ logits, const int32_t* __restrict__
 }
 
 // partial dW[chunk][d][e] = sum_{t in chunk} x[t,d] * dz[t,e]; thread tile 4 d x EW experts.
-template <int EW, typename XT>
-__global__ void gate_bwd_dw_kernel(const XT* __restrict__ x, int64_t ldx, const float* __restrict__ dz, int T,
+template <int EW, typename XT, bool LN, int TB>
+__global__ void __launch_bounds__(TB == 8 ? 384 : TB == 4 ? 512 : 1024)
+gate_bwd_dw_kernel(const XT* __restrict__ x, int64_t ldx, const float* __restrict__ dz, int T,
                                    int D, int E, int tok_per_chunk, float* __restrict__ part,
                                    float* __restrict__ cs_part, const float* __restrict__ ln_mean,
                                    const float* __restrict__ ln_rstd, const float* __restrict__ ln_gamma,
@@ -413,39 +413,51 @@ __global__ void gate_bwd_dw_kernel(const XT* __restrict__ x, int64_t ldx, const 
   for (int c = 0; c < EW; ++c) cs[c] = 0.f;
   // Block-level fusion: x is the raw residual stream, normalised on load
   float lg[4] = {1.f, 1.f, 1.f, 1.f}, lb[4] = {0.f, 0.f, 0.f, 0.f};
-  if (ln_mean != nullptr) {
+  if constexpr (LN) {
 #pragma unroll
     for (int i = 0; i < 4; ++i) { lg[i] = __ldg(ln_gamma + dq * 4 + i); lb[i] = __ldg(ln_beta + dq * 4 + i); }
   }
-#pragma unroll 8
-  for (int t = t0; t < t1; ++t) {
-    float xv[4];
-    if constexpr (sizeof(XT) == 4) {
-      float4 v = __ldg(reinterpret_cast<const float4*>(x + (int64_t)t * ldx + dq * 4));
-      xv[0] = v.x; xv[1] = v.y; xv[2] = v.z; xv[3] = v.w;
-    } else {
-      uint2 u = __ldg(reinterpret_cast<const uint2*>(x + (int64_t)t * ldx + dq * 4));
-      float2 a = bf16x2_to_float2(u.x), b = bf16x2_to_float2(u.y);
-      xv[0] = a.x; xv[1] = a.y; xv[2] = b.x; xv[3] = b.y;
+  // Tokens are processed in batches of TB with ALL loads of a batch issued before the first FMA
+  // (a plain `#pragma unroll` leaves one token's loads in flight per thread: latency-bound).  The
+  // batch tail re-reads the last token with its dz zeroed, so the summation order stays t-ascending.
+  for (int tb = t0; tb < t1; tb += TB) {
+    float xv[TB][4], dv[TB][EW], mu[TB], rs[TB];
+#pragma unroll
+    for (int u = 0; u < TB; ++u) {
+      const int t = min(tb + u, t1 - 1);
+      if constexpr (sizeof(XT) == 4) {
+        float4 v = __ldg(reinterpret_cast<const float4*>(x + (int64_t)t * ldx + dq * 4));
+        xv[u][0] = v.x; xv[u][1] = v.y; xv[u][2] = v.z; xv[u][3] = v.w;
+      } else {
+        uint2 w = __ldg(reinterpret_cast<const uint2*>(x + (int64_t)t * ldx + dq * 4));
+        float2 a = bf16x2_to_float2(w.x), b = bf16x2_to_float2(w.y);
+        xv[u][0] = a.x; xv[u][1] = a.y; xv[u][2] = b.x; xv[u][3] = b.y;
+      }
+#pragma unroll
+      for (int c = 0; c < EW; c += 4) {
+        float4 v = __ldg(reinterpret_cast<const float4*>(dz + (int64_t)t * E + e0 + c));
+        dv[u][c] = v.x; dv[u][c + 1] = v.y; dv[u][c + 2] = v.z; dv[u][c + 3] = v.w;
+      }
+      if constexpr (LN) { mu[u] = __ldg(ln_mean + t); rs[u] = __ldg(ln_rstd + t); }
     }
-    if (ln_mean != nullptr) {
-      const float mu = __ldg(ln_mean + t), rs = __ldg(ln_rstd + t);
 #pragma unroll
-      for (int i = 0; i < 4; ++i) xv[i] = fmaf((xv[i] - mu) * rs, lg[i], lb[i]);
-    }
-    float dv[EW];
+    for (int u = 0; u < TB; ++u) {
+      if (tb + u >= t1) {
 #pragma unroll
-    for (int c = 0; c < EW; c += 4) {
-      float4 v = __ldg(reinterpret_cast<const float4*>(dz + (int64_t)t * E + e0 + c));
-      dv[c] = v.x; dv[c + 1] = v.y; dv[c + 2] = v.z; dv[c + 3] = v.w;
-    }
+        for (int c = 0; c < EW; ++c) dv[u][c] = 0.f;
+      }
+      if constexpr (LN) {
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
+        for (int i = 0; i < 4; ++i) xv[u][i] = fmaf((xv[u][i] - mu[u]) * rs[u], lg[i], lb[i]);
+      }
 #pragma unroll
-      for (int c = 0; c < EW; ++c) acc[i][c] = fmaf(xv[i], dv[c], acc[i][c]);
-    if (dq == 0) {
+      for (int i = 0; i < 4; ++i)
 #pragma unroll
-      for (int c = 0; c < EW; ++c) cs[c] += dv[c];
+        for (int c = 0; c < EW; ++c) acc[i][c] = fmaf(xv[u][i], dv[u][c], acc[i][c]);
+      if (dq == 0) {
+#pragma unroll
+        for (int c = 0; c < EW; ++c) cs[c] += dv[u][c];
+      }
     }
   }
   float* dst = part + ((int64_t)blockIdx.x * D + dq * 4) * E + e0;
@@ -669,12 +681,20 @@ static int gate_bwd_impl(const void* x, int x_dtype, int64_t ldx, const float* t
     const int EW = EB < 8 ? EB : 8;
     dim3 grid(nchunk, E / EB);
     const int threads = (D / 4) * (EB / EW);
-    if (x_dtype == M3_F32) {
-      if (EW == 8) gate_bwd_dw_kernel<8, float><<<grid, threads, 0, st>>>(static_cast<const float*>(x), ldx, dz, T, D, E, tok_per_chunk, part, cs_part, ln_mean, ln_rstd, ln_gamma, ln_beta);
-      else gate_bwd_dw_kernel<4, float><<<grid, threads, 0, st>>>(static_cast<const float*>(x), ldx, dz, T, D, E, tok_per_chunk, part, cs_part, ln_mean, ln_rstd, ln_gamma, ln_beta);
+#define M3_DW_ARGS(XT) static_cast<const XT*>(x), ldx, dz, T, D, E, tok_per_chunk, part, cs_part, ln_mean, ln_rstd, ln_gamma, ln_beta
+    // token batch (loads in flight per thread) limited by the register file at large CTAs
+#define M3_DW_LAUNCH(EWV, XT, LNV)                                                                                   \
+  do {                                                                                                              \
+    if (threads <= 384) gate_bwd_dw_kernel<EWV, XT, LNV, 8><<<grid, threads, 0, st>>>(M3_DW_ARGS(XT));             \
+    else if (threads <= 512) gate_bwd_dw_kernel<EWV, XT, LNV, 4><<<grid, threads, 0, st>>>(M3_DW_ARGS(XT));        \
+    else gate_bwd_dw_kernel<EWV, XT, LNV, 2><<<grid, threads, 0, st>>>(M3_DW_ARGS(XT));                            \
+  } while (0)
+    if (ln_mean != nullptr) {
+      if (EW == 8) M3_DW_LAUNCH(8, float, true); else M3_DW_LAUNCH(4, float, true);
+    } else if (x_dtype == M3_F32) {
+      if (EW == 8) M3_DW_LAUNCH(8, float, false); else M3_DW_LAUNCH(4, float, false);
     } else {
-      if (EW == 8) gate_bwd_dw_kernel<8, __nv_bfloat16><<<grid, threads, 0, st>>>(static_cast<const __nv_bfloat16*>(x), ldx, dz, T, D, E, tok_per_chunk, part, cs_part, ln_mean, ln_rstd, ln_gamma, ln_beta);
-      else gate_bwd_dw_kernel<4, __nv_bfloat16><<<grid, threads, 0, st>>>(static_cast<const __nv_bfloat16*>(x), ldx, dz, T, D, E, tok_per_chunk, part, cs_part, ln_mean, ln_rstd, ln_gamma, ln_beta);
+      if (EW == 8) M3_DW_LAUNCH(8, __nv_bfloat16, false); else M3_DW_LAUNCH(4, __nv_bfloat16, false);
     }
     M3_LAUNCH_CHECK();
   }

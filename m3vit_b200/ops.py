@@ -277,7 +277,7 @@ class LnState:
     rstd: torch.Tensor      # [T]
     gamma: torch.Tensor     # [D]
     beta: torch.Tensor      # [D]
-    w_fold: torch.Tensor    # [Dg,E] gamma-scaled router weights
+    w_fold: torch.Tensor    # [Dg,E] gamma-scaled, column-centred router weights
     gb: torch.Tensor        # [2,E]  {gamma^T W, beta^T W}
 
 

@@ -141,7 +141,8 @@ def test_block_ops_against_torch():
         var = x.double().var(1, unbiased=False)
         torch.testing.assert_close(ln.mean.double(), mu, rtol=1e-5, atol=1e-6)
         torch.testing.assert_close(ln.rstd.double(), (var + eps).rsqrt(), rtol=1e-5, atol=1e-6)
-        torch.testing.assert_close(ln.w_fold, gamma[:, None] * wg, rtol=1e-6, atol=1e-7)
+        torch.testing.assert_close(ln.w_fold, gamma[:, None] * wg - (gamma[:, None] * wg).mean(0, keepdim=True),
+                                   rtol=1e-5, atol=1e-6)
         torch.testing.assert_close(ln.gb[0].double(), (gamma.double()[:, None] * wg.double()).sum(0), rtol=1e-5, atol=1e-5)
         torch.testing.assert_close(ln.gb[1].double(), (beta.double()[:, None] * wg.double()).sum(0), rtol=1e-5, atol=1e-5)
         # gate on raw x == gate on LayerNorm(x)
