@@ -148,18 +148,22 @@ int m3_combine_bwd(const void* g, int g_dtype, const void* yq, int yq_dtype, con
  * as a grouped GEMM over the padded expert queues.
  *   dtype M3_F32 : fp32 SIMT path (parity mode; the reference trains in fp32)
  *   dtype M3_BF16: tcgen05/TMEM/TMA path (bf16 operands, fp32 accumulation)
- *   xq [rows, D], hpre [rows, H] (saved pre-activation, NULL when not training),
- *   yq [rows, D]; rows = offsets[E] (<= cap_rows); w1 [E,H,D], w2 [E,D,H] in `dtype`;
- *   b1 [E,H], b2 [E,D] fp32.   tile_expert / offsets from m3_route_plan (pad 128).
+ *   xq [rows, D], yq [rows, D]; rows = offsets[E] (<= cap_rows); w1 [E,H,D], w2 [E,D,H] in
+ *   `dtype`; b1 [E,H], b2 [E,D] fp32.   tile_expert / offsets from m3_route_plan (pad M3_PAD_ROWS).
+ *   saved: OPAQUE activation state of m3_ffn_saved_bytes(dtype, cap_rows, H) bytes that m3_ffn_fwd
+ *   fills and m3_ffn_bwd consumes (NULL when not training).  fp32: the pre-activation z [rows, H];
+ *   bf16: gelu'(z) and h = gelu(z) as two [rows, H] planes, so that the backward GEMM epilogue is a
+ *   single multiply and h is not recomputed (autograd would keep z and re-evaluate erf/exp).
  *   bf16 backward additionally needs transposed weight copies w1t [E,D,H], w2t [E,H,D].
  *   Weight / bias gradients are fp32 and OVERWRITTEN (caller accumulates).
  */
 size_t m3_ffn_workspace_bytes(int dtype, int cap_rows, int D, int H, int E, int backward);
+size_t m3_ffn_saved_bytes(int dtype, int cap_rows, int H);
 int m3_ffn_fwd(int dtype, const void* xq, const int32_t* offsets, const int32_t* tile_expert,
                int cap_rows, int E, int D, int H, const void* w1, const float* b1, const void* w2,
-               const float* b2, void* hpre, void* yq, void* workspace, size_t workspace_bytes,
+               const float* b2, void* saved, void* yq, void* workspace, size_t workspace_bytes,
                m3_stream_t stream);
-int m3_ffn_bwd(int dtype, const void* xq, const void* hpre, const void* dyq, const int32_t* counts,
+int m3_ffn_bwd(int dtype, const void* xq, const void* saved, const void* dyq, const int32_t* counts,
                const int32_t* offsets, const int32_t* tile_expert, int cap_rows, int E, int D, int H,
                const void* w1, const void* w2, const void* w1t, const void* w2t, void* dxq,
                float* dw1, float* db1, float* dw2, float* db2, void* workspace,

@@ -41,6 +41,7 @@ SIGNATURES = {
     "m3_combine_fwd": (_i, [_p, _i, _p, _p, _i, _i, _i, _p, _i, _p]),
     "m3_combine_bwd": (_i, [_p, _i, _p, _i, _p, _p, _p, _p, _i, _i, _i, _i, _p, _i, _p, _p]),
     "m3_ffn_workspace_bytes": (_sz, [_i, _i, _i, _i, _i, _i]),
+    "m3_ffn_saved_bytes": (_sz, [_i, _i, _i]),
     "m3_ffn_fwd": (_i, [_i, _p, _p, _p, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _sz, _p]),
     "m3_ffn_bwd": (_i, [_i, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _sz, _p]),
     "m3_cast_weights_bf16": (_i, [_p, _i, _i, _i, _p, _p, _p]),

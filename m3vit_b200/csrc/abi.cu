@@ -13,6 +13,7 @@ int m3_ffn_bwd_f32(const float* xq, const float* hpre, const float* dyq, const i
                    const float* w1, const float* w2, float* dxq, float* dw1, float* db1, float* dw2, float* db2,
                    void* workspace, size_t workspace_bytes, cudaStream_t st);
 size_t m3_ffn_bf16_workspace_bytes(int cap_rows, int D, int H, int E, int backward);
+size_t m3_ffn_bf16_saved_bytes(int cap_rows, int H);
 int m3_ffn_fwd_bf16(const void* xq, const int32_t* offsets, const int32_t* tile_expert, int cap_rows, int E, int D,
                     int H, const void* w1, const float* b1, const void* w2, const float* b2, void* hpre, void* yq,
                     void* workspace, size_t workspace_bytes, cudaStream_t st);
@@ -52,6 +53,12 @@ extern "C" int m3_check_device(void) {
 extern "C" size_t m3_ffn_workspace_bytes(int dtype, int cap_rows, int D, int H, int E, int backward) {
   if (dtype == M3_F32) return (size_t)cap_rows * H * sizeof(float);
   return m3_ffn_bf16_workspace_bytes(cap_rows, D, H, E, backward);
+}
+
+extern "C" size_t m3_ffn_saved_bytes(int dtype, int cap_rows, int H) {
+  if (cap_rows < 0 || H <= 0) return 0;
+  if (dtype == M3_BF16) return m3_ffn_bf16_saved_bytes(cap_rows, H);
+  return (size_t)cap_rows * H * sizeof(float);      // fp32 parity path: the pre-activation
 }
 
 extern "C" int m3_ffn_fwd(int dtype, const void* xq, const int32_t* offsets, const int32_t* tile_expert, int cap_rows,

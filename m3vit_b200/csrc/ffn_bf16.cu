@@ -39,9 +39,9 @@ struct GGParams {
   const int32_t* tile_expert;  // [rows/128]
   int E, N, Kd;
   const float* bias;           // [E][N]   (EPI_BIAS, EPI_FC1)
-  int save_out2;               // EPI_FC1: also store the pre-activation (training)
+  int save_out2;               // EPI_FC1: also store gelu'(pre-activation) for the backward pass (training)
   __nv_bfloat16* out;          // [rows][N]
-  __nv_bfloat16* out2;         // EPI_FC1: hpre   EPI_DGELU: h = gelu(hpre)
+  __nv_bfloat16* out2;         // EPI_FC1: gelu'(pre-activation)
 };
 
 constexpr int WBOX_BYTES = 32 * 64 * 2;  // one warp's [32 rows][64 bf16] swizzle-128B box = 4 KB
@@ -53,7 +53,7 @@ struct GGCfg {
   static constexpr int STAGE = A_BYTES + B_BYTES;
   // epilogue staging: one private 4 KB box per epilogue warp per output tensor (+ per TMA-loaded aux input)
   static constexpr int N_OUT = 1;                            // outputs share one transpose box, flushed in turn
-  static constexpr int N_AUX = (EPI == EPI_DGELU) ? 1 : 0;
+  static constexpr int N_AUX = (EPI == EPI_DGELU) ? 1 : 0;   // EPI_DGELU: gelu'(pre-activation) saved by fc1
   static constexpr int WARP_STAGING = (N_OUT + N_AUX) * WBOX_BYTES;
   static constexpr int STAGING = kEpiWarps * WARP_STAGING;
   static constexpr int BUDGET = 227 * 1024 - 1024 - 512 - STAGING;
@@ -250,17 +250,25 @@ gg_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         }
         if (EPI == EPI_FC1) {
           if (p.save_out2) {
+            // training: h = gelu(z) goes on to fc2 (and is kept for dW2); the backward pass only ever
+            // needs gelu'(z), so THAT is saved instead of z: dgelu becomes one multiply per element
 #pragma unroll
             for (int c = 0; c < 8; ++c) {
-              uint4 u;
-              u.x = pack_bf16x2(w2[4 * c]); u.y = pack_bf16x2(w2[4 * c + 1]);
-              u.z = pack_bf16x2(w2[4 * c + 2]); u.w = pack_bf16x2(w2[4 * c + 3]);
-              *reinterpret_cast<uint4*>(box + box_off(lane, c)) = u;
+              uint32_t go[4];
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                f32x2 gl;
+                const f32x2 gr = gelu_fast_grad2(w2[4 * c + i], &gl);
+                w2[4 * c + i] = gl;
+                go[i] = pack_bf16x2(gr);
+              }
+              *reinterpret_cast<uint4*>(box + box_off(lane, c)) = make_uint4(go[0], go[1], go[2], go[3]);
             }
             flush(p.out2, row0, col);
-          }
+          } else {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) w2[j] = gelu_fast2(w2[j]);
+            for (int j = 0; j < 32; ++j) w2[j] = gelu_fast2(w2[j]);
+          }
         }
         if (EPI == EPI_DGELU) {
           mbar_wait(my_aux, aux_uses & 1);
@@ -281,17 +289,9 @@ gg_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
 #pragma unroll
           for (int c = 0; c < 8; ++c) {
             const uint32_t hw[4] = {hraw[c].x, hraw[c].y, hraw[c].z, hraw[c].w};
-            uint32_t ho[4];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              f32x2 gl;
-              const f32x2 gr = gelu_fast_grad2(unpack_bf16x2(hw[i]), &gl);
-              w2[4 * c + i] = mul2(w2[4 * c + i], gr);
-              ho[i] = pack_bf16x2(gl);
-            }
-            *reinterpret_cast<uint4*>(box + box_off(lane, c)) = make_uint4(ho[0], ho[1], ho[2], ho[3]);   // h = gelu(hpre)
+            for (int i = 0; i < 4; ++i) w2[4 * c + i] = mul2(w2[4 * c + i], unpack_bf16x2(hw[i]));   // * gelu'(z)
           }
-          flush(p.out2, row0, col);
         }
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
@@ -638,8 +638,12 @@ static bool use_fused(int D, int H) {
   return on && m3_ffn_fused_supported(D, H);
 }
 
-// workspace: forward  : h [cap][H] bf16
-//            backward : dhpre [cap][H] bf16 | h [cap][H] bf16 | wgrad split-K partials [S][E][M][N]+[S][E][M] fp32
+// Opaque activation state handed from m3_ffn_fwd to m3_ffn_bwd (bf16): two [cap][H] planes,
+//   plane 0 = gelu'(z) (two-kernel path) or z (fused chain kernel),  plane 1 = h = gelu(z) (two-kernel path).
+size_t m3_ffn_bf16_saved_bytes(int cap_rows, int H) { return 2 * align256((size_t)cap_rows * H * 2); }
+
+// workspace: forward  : h [cap][H] bf16 (inference only; training keeps h in the saved state)
+//            backward : dz [cap][H] bf16 | h [cap][H] bf16 (fused path only) | wgrad split-K partials fp32
 size_t m3_ffn_bf16_workspace_bytes(int cap_rows, int D, int H, int E, int backward) {
   (void)E;
   const size_t hbytes = align256((size_t)cap_rows * H * 2);
@@ -649,24 +653,26 @@ size_t m3_ffn_bf16_workspace_bytes(int cap_rows, int D, int H, int E, int backwa
 }
 
 int m3_ffn_fwd_bf16(const void* xq, const int32_t* offsets, const int32_t* tile_expert, int cap_rows, int E, int D,
-                    int H, const void* w1, const float* b1, const void* w2, const float* b2, void* hpre, void* yq,
+                    int H, const void* w1, const float* b1, const void* w2, const float* b2, void* saved, void* yq,
                     void* workspace, size_t workspace_bytes, cudaStream_t st) {
   if (workspace == nullptr || workspace_bytes < m3_ffn_bf16_workspace_bytes(cap_rows, D, H, E, 0)) return M3_ERR_WORKSPACE;
   if (use_fused(D, H))
-    return m3_ffn_fused_fwd(xq, offsets, tile_expert, cap_rows, E, D, H, w1, b1, w2, b2, hpre, yq, st);
-  bf16* h = static_cast<bf16*>(workspace);
+    return m3_ffn_fused_fwd(xq, offsets, tile_expert, cap_rows, E, D, H, w1, b1, w2, b2, saved, yq, st);
+  const size_t hbytes = align256((size_t)cap_rows * H * 2);
+  bf16* gp = static_cast<bf16*>(saved);
+  bf16* h = saved ? reinterpret_cast<bf16*>(static_cast<uint8_t*>(saved) + hbytes) : static_cast<bf16*>(workspace);
   GGParams p{};
   p.offsets = offsets; p.tile_expert = tile_expert; p.E = E;
-  // fc1: h = gelu(xq W1^T + b1), hpre saved for backward
-  p.N = H; p.Kd = D; p.bias = b1; p.save_out2 = hpre != nullptr;
-  int rc = launch_gg<EPI_FC1>(xq, w1, h, hpre, nullptr, p, cap_rows, st);
+  // fc1: h = gelu(xq W1^T + b1); gelu'(.) saved for backward
+  p.N = H; p.Kd = D; p.bias = b1; p.save_out2 = saved != nullptr;
+  int rc = launch_gg<EPI_FC1>(xq, w1, h, gp, nullptr, p, cap_rows, st);
   if (rc) return rc;
   // fc2: yq = h W2^T + b2
   p.N = D; p.Kd = H; p.bias = b2; p.save_out2 = 0;
   return launch_gg<EPI_BIAS>(h, w2, yq, nullptr, nullptr, p, cap_rows, st);
 }
 
-int m3_ffn_bwd_bf16(const void* xq, const void* hpre, const void* dyq, const int32_t* counts, const int32_t* offsets,
+int m3_ffn_bwd_bf16(const void* xq, const void* saved, const void* dyq, const int32_t* counts, const int32_t* offsets,
                     const int32_t* tile_expert, int cap_rows, int E, int D, int H, const void* w1, const void* w2,
                     const void* w1t, const void* w2t, void* dxq, float* dw1, float* db1, float* dw2, float* db2,
                     void* workspace, size_t workspace_bytes, cudaStream_t st) {
@@ -674,27 +680,30 @@ int m3_ffn_bwd_bf16(const void* xq, const void* hpre, const void* dyq, const int
   if (workspace_bytes < m3_ffn_bf16_workspace_bytes(cap_rows, D, H, E, 1)) return M3_ERR_WORKSPACE;
   const size_t hbytes = align256((size_t)cap_rows * H * 2);
   bf16* dhpre = static_cast<bf16*>(workspace);
-  bf16* h = reinterpret_cast<bf16*>(static_cast<uint8_t*>(workspace) + hbytes);
   float* part = reinterpret_cast<float*>(static_cast<uint8_t*>(workspace) + 2 * hbytes);
+  const bf16* h;
   int rc;
   if (use_fused(D, H)) {
-    // one kernel: dhpre = (dyq W2) * gelu'(hpre), h = gelu(hpre), dxq = dhpre W1
-    rc = m3_ffn_fused_bwd(dyq, hpre, offsets, tile_expert, cap_rows, E, D, H, w2t, w1t, dhpre, h, dxq, st);
+    // one kernel: dz = (dyq W2) * gelu'(z), h = gelu(z), dxq = dz W1      (saved plane 0 = z)
+    bf16* hw = reinterpret_cast<bf16*>(static_cast<uint8_t*>(workspace) + hbytes);
+    rc = m3_ffn_fused_bwd(dyq, saved, offsets, tile_expert, cap_rows, E, D, H, w2t, w1t, dhpre, hw, dxq, st);
     if (rc) return rc;
+    h = hw;
   } else {
+    h = reinterpret_cast<const bf16*>(static_cast<const uint8_t*>(saved) + hbytes);
     GGParams p{};
     p.offsets = offsets; p.tile_expert = tile_expert; p.E = E;
-    // dhpre = (dyq W2) * gelu'(hpre);  h = gelu(hpre)      B = W2^T [E][H][D] (K-major in D)
+    // dz = (dyq W2) * gelu'(z)                              B = W2^T [E][H][D] (K-major in D)
     p.N = H; p.Kd = D;
-    rc = launch_gg<EPI_DGELU>(dyq, w2t, dhpre, h, hpre, p, cap_rows, st);
+    rc = launch_gg<EPI_DGELU>(dyq, w2t, dhpre, nullptr, saved, p, cap_rows, st);
     if (rc) return rc;
-    // dxq = dhpre W1                                       B = W1^T [E][D][H] (K-major in H)
+    // dxq = dz W1                                           B = W1^T [E][D][H] (K-major in H)
     p.N = D; p.Kd = H;
     rc = launch_gg<EPI_STORE>(dhpre, w1t, dxq, nullptr, nullptr, p, cap_rows, st);
     if (rc) return rc;
   }
-  // dW2[e] = dyq_e^T h_e  [D][H];   dW1[e] = dhpre_e^T xq_e  [H][D]
-  // the bias gradients ride along as one extra N=16 MMA against a tile of ones
+  // dW2[e] = dyq_e^T h_e  [D][H];   dW1[e] = dz_e^T xq_e  [H][D]
+  // the bias gradients ride along in the same MMA against a tile of ones
   rc = launch_wgrad(dyq, h, offsets, cap_rows, E, D, H, dw2, db2, part, st);
   if (rc) return rc;
   return launch_wgrad(dhpre, xq, offsets, cap_rows, E, H, D, dw1, db1, part, st);

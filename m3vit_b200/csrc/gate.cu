@@ -19,6 +19,7 @@
 namespace m3 {
 
 constexpr int kGateDC = 32;  // columns of x per smem chunk
+constexpr int kGateStages = 4;  // cp.async ring depth (chunks in flight per CTA)
 
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
   uint32_t s = static_cast<uint32_t>(__cvta_generic_to_shared(smem));
@@ -76,15 +77,16 @@ gate_fwd_kernel(const XT* __restrict__ x, int64_t ldx, const float* __restrict__
   constexpr int CHUNK_VECS = kGateDC * (int)sizeof(XT) / 16;  // 16-B vectors per x row chunk
 
   extern __shared__ __align__(16) unsigned char smem[];
-  unsigned char* ws = smem;                                   // [2][DC][E] fp32
-  unsigned char* xs = smem + 2 * WS_STAGE;                    // [NW][2][TOK_W][ROWB]
-  float* red_imp = reinterpret_cast<float*>(xs + NW * 2 * XS_STAGE);  // [NW][E]
+  constexpr int S = kGateStages;
+  unsigned char* ws = smem;                                   // [S][DC][E] fp32
+  unsigned char* xs = smem + S * WS_STAGE;                    // [NW][S][TOK_W][ROWB]
+  float* red_imp = reinterpret_cast<float*>(xs + NW * S * XS_STAGE);  // [NW][E]
   int* red_load = reinterpret_cast<int*>(red_imp + NW * E);           // [NW][E]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int eg = lane % EG, tg = lane / EG;
   const int tok_w0 = blockIdx.x * C::TOK_CTA + warp * TOK_W;
-  unsigned char* my_xs = xs + warp * 2 * XS_STAGE;
+  unsigned char* my_xs = xs + warp * S * XS_STAGE;
 
   const int NC = D / kGateDC;
   auto issue = [&](int c, int stage) {
@@ -107,17 +109,20 @@ gate_fwd_kernel(const XT* __restrict__ x, int64_t ldx, const float* __restrict__
 #pragma unroll
     for (int c = 0; c < 4; ++c) acc[j][c] = 0.f;
 
-  issue(0, 0);
+  // S-deep ring: chunks c .. c+S-2 are in flight while chunk c is consumed.  One barrier per chunk:
+  // it publishes chunk c and proves that every warp has finished chunk c-1, whose stage is refilled.
+#pragma unroll
+  for (int p = 0; p < S - 1; ++p) {
+    if (p < NC) issue(p, p);
+    else cp_async_commit();
+  }
   for (int c = 0; c < NC; ++c) {
-    if (c + 1 < NC) {
-      issue(c + 1, (c + 1) & 1);
-      cp_async_wait<1>();
-    } else {
-      cp_async_wait<0>();
-    }
+    cp_async_wait<S - 2>();
     __syncthreads();
-    const unsigned char* xst = my_xs + (c & 1) * XS_STAGE;
-    const float* wst = reinterpret_cast<const float*>(ws + (c & 1) * WS_STAGE);
+    if (c + S - 1 < NC) issue(c + S - 1, (c + S - 1) % S);
+    else cp_async_commit();
+    const unsigned char* xst = my_xs + (c % S) * XS_STAGE;
+    const float* wst = reinterpret_cast<const float*>(ws + (c % S) * WS_STAGE);
 #pragma unroll 2
     for (int d4 = 0; d4 < kGateDC; d4 += 4) {
       float4 w[4];
@@ -136,7 +141,6 @@ gate_fwd_kernel(const XT* __restrict__ x, int64_t ldx, const float* __restrict__
         }
       }
     }
-    __syncthreads();
   }
 
   // Block-level fusion (block.cu): x is the RAW residual stream and w_gate is gamma-folded and
@@ -268,15 +272,18 @@ gate_fwd_kernel(const XT* __restrict__ x, int64_t ldx, const float* __restrict__
 template <int E, int TM, int NW, typename XT>
 static size_t gate_fwd_smem() {
   using C = GateCfg<E, TM, NW>;
-  return 2 * kGateDC * E * 4 + (size_t)NW * 2 * C::TOK_W * GateRow<XT>::kBytes + (size_t)NW * E * 8;
+  return (size_t)kGateStages * kGateDC * E * 4 + (size_t)NW * kGateStages * C::TOK_W * GateRow<XT>::kBytes +
+         (size_t)NW * E * 8;
 }
 
-// Three tile configurations; pick the largest whose grid still covers the GPU twice.
-//   0: 1 warp  x TG*2 tokens (small T, latency-bound)   1: 2 warps x TG*4   2: 4 warps x TG*8
+// Three tile configurations; pick the largest that still puts >= 16 warps on every SM (the kernel
+// hides its smem / HBM latency with warps, not with ILP).
+//   0: 1 warp x TG*2 tokens (small T)   1: 4 warps x TG*2   2: 4 warps x TG*4   3: 4 warps x TG*8
 template <int E>
 static int gate_cfg_id(int T) {
-  if (T >= 2 * kNumSMs * GateCfg<E, 8, 4>::TOK_CTA) return 2;
-  if (T >= 2 * kNumSMs * GateCfg<E, 4, 2>::TOK_CTA) return 1;
+  if (T >= 16 * kNumSMs * GateCfg<E, 8, 4>::TOK_W) return 3;
+  if (T >= 16 * kNumSMs * GateCfg<E, 4, 4>::TOK_W) return 2;
+  if (T >= 16 * kNumSMs * GateCfg<E, 2, 4>::TOK_W) return 1;
   return 0;
 }
 
@@ -304,7 +311,8 @@ static int launch_gate_fwd(const void* x, int64_t ldx, const float* task_feat, c
 template <int E>
 static int gate_tokens_per_cta(int T) {
   const int id = gate_cfg_id<E>(T);
-  return id == 2 ? GateCfg<E, 8, 4>::TOK_CTA : id == 1 ? GateCfg<E, 4, 2>::TOK_CTA : GateCfg<E, 2, 1>::TOK_CTA;
+  return id == 3 ? GateCfg<E, 8, 4>::TOK_CTA : id == 2 ? GateCfg<E, 4, 4>::TOK_CTA
+       : id == 1 ? GateCfg<E, 2, 4>::TOK_CTA : GateCfg<E, 2, 1>::TOK_CTA;
 }
 
 // ------------------------------------------------------------------ backward
@@ -572,8 +580,9 @@ extern "C" int m3_gate_num_partials(int T, int E) {
                      ln_gb, st
 #define M3_GATE_CASE_T(EE, XT)                                               \
   switch (gate_cfg_id<EE>(T)) {                                              \
-    case 2: return launch_gate_fwd<EE, 8, 4, XT>(M3_GATE_ARGS);              \
-    case 1: return launch_gate_fwd<EE, 4, 2, XT>(M3_GATE_ARGS);              \
+    case 3: return launch_gate_fwd<EE, 8, 4, XT>(M3_GATE_ARGS);              \
+    case 2: return launch_gate_fwd<EE, 4, 4, XT>(M3_GATE_ARGS);              \
+    case 1: return launch_gate_fwd<EE, 2, 4, XT>(M3_GATE_ARGS);              \
     default: return launch_gate_fwd<EE, 2, 1, XT>(M3_GATE_ARGS);             \
   }
 #define M3_GATE_CASE(EE)                                    \

@@ -223,10 +223,15 @@ __global__ void __launch_bounds__(kPermThreads)
 dispatch_bwd_gate_kernel(Queue<const TI> dxq, const int32_t* __restrict__ pos, int T, int K, int D,
                          const float* __restrict__ dz, const float* __restrict__ w_gate, int E,
                          TO* __restrict__ dx) {
-  extern __shared__ __align__(16) float wt[];  // [E][D]
+  // wt[e][h][c][4]: the 8 columns c*8..c*8+7 of a lane's slice are kept as two float4 in separate
+  // planes h = 0/1, so that the 16 lanes of a group read CONSECUTIVE 16-byte words (a plain [E][D]
+  // layout makes lanes 32 B apart: 2-way bank conflicts on every read).
+  extern __shared__ __align__(16) float wt[];
+  const int half = D / 2;
   for (int i = threadIdx.x; i < D * E; i += kPermThreads) {
-    const int e = i / D, d = i % D;             // conflict-free smem writes; strided (L2-resident) reads
-    wt[i] = __ldg(w_gate + (int64_t)d * E + e);
+    const int e = i / D, d = i % D;             // strided (L2-resident) reads, once per CTA
+    const int c = d >> 3, h = (d >> 2) & 1, j = d & 3;
+    wt[e * D + h * half + c * 4 + j] = __ldg(w_gate + (int64_t)d * E + e);
   }
   __syncthreads();
   const int sub = threadIdx.x % kLanesPerTok;
@@ -273,8 +278,8 @@ dispatch_bwd_gate_kernel(Queue<const TI> dxq, const int32_t* __restrict__ pos, i
         for (int i = 0; i < NV; ++i) {
           const int c = sub + i * kLanesPerTok;
           if (c < nvec) {
-            const float4 wa = *reinterpret_cast<const float4*>(wt + (e + ee) * D + c * 8);
-            const float4 wb = *reinterpret_cast<const float4*>(wt + (e + ee) * D + c * 8 + 4);
+            const float4 wa = *reinterpret_cast<const float4*>(wt + (e + ee) * D + c * 4);
+            const float4 wb = *reinterpret_cast<const float4*>(wt + (e + ee) * D + half + c * 4);
             const float w8[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
 #pragma unroll
             for (int j = 0; j < 8; ++j) {

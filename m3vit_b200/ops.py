@@ -228,14 +228,16 @@ def cast_weights_bf16(w, want_plain=True, want_transposed=False):
 
 
 def ffn_fwd(xq, plan: Plan, w1, b1, w2, b2, save_hpre=True):
-    """xq [cap,D] (fp32|bf16); w1 [E,H,D], w2 [E,D,H] same dtype as xq; b1,b2 fp32."""
+    """xq [cap,D] (fp32|bf16); w1 [E,H,D], w2 [E,D,H] same dtype as xq; b1,b2 fp32.
+    Returns (yq, saved): `saved` is the library's opaque activation state for ffn_bwd (uint8)."""
     require_device(xq)
     lib = load()
     cap, D = xq.shape
     E, H, _ = w1.shape
     dt = dtype_code(xq)
     assert w1.dtype == xq.dtype and w2.dtype == xq.dtype and b1.dtype == torch.float32
-    hpre = torch.empty(cap, H, dtype=xq.dtype, device=xq.device) if save_hpre else None
+    # opaque activation state for the backward pass (fp32: pre-activation; bf16: gelu'(z) and h planes)
+    hpre = _ws(lib.m3_ffn_saved_bytes(dt, cap, H), xq.device) if save_hpre else None
     yq = torch.empty(cap, D, dtype=xq.dtype, device=xq.device)
     ws = _ws(lib.m3_ffn_workspace_bytes(dt, cap, D, H, E, 0), xq.device)
     check(lib.m3_ffn_fwd(dt, ptr(xq), ptr(plan.offsets), ptr(plan.tile_expert), cap, E, D, H, ptr(w1), ptr(b1),

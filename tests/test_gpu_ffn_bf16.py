@@ -106,8 +106,19 @@ def test_ffn_bf16_tile_exactness():
         want_hpre[s:s + m] = xq_ref[s:s + m] @ w1[e].t()
     valid = torch.zeros(n, dtype=torch.bool)
     valid[p.long()] = True
-    got = hpre[:n].float().cpu()
-    assert torch.equal(got[valid], want_hpre[valid].bfloat16().float()), "fc1 accumulators differ"
+    # the saved state holds gelu'(z) and h = gelu(z) as two [cap, H] bf16 planes (include/m3vit_moe.h);
+    # z is integer valued here, so any mis-indexed tile shows up as a gross error in either plane
+    planes = hpre.view(torch.bfloat16).view(2, -1)[:, :plan.cap_rows * H].view(2, plan.cap_rows, H)
+    z = want_hpre[valid].double()
+    cdf = 0.5 * (1 + torch.erf(z / 2 ** 0.5))
+    pdf = torch.exp(-0.5 * z * z) / (2 * torch.pi) ** 0.5
+    torch.testing.assert_close(planes[1, :n].float().cpu()[valid].double(), z * cdf, rtol=8e-3, atol=2e-3)
+    torch.testing.assert_close(planes[0, :n].float().cpu()[valid].double(), cdf + z * pdf, rtol=8e-3, atol=2e-3)
+    # fc2 is a scaled identity per expert: yq = (e+1) * h exactly (small integers times bf16 values)
+    got_y = yq[:n].float().cpu()
+    for e in range(E):
+        s0 = int(o[e]); m = int(c[e])
+        assert torch.equal(got_y[s0:s0 + m], (planes[1, s0:s0 + m].float().cpu() * (e + 1)).bfloat16().float())
 
 
 def test_fused_chain_kernel_matches_two_kernel_path():
@@ -134,7 +145,7 @@ yq, hpre = ops.ffn_fwd(xq, plan, w1c, b1, w2c, b2)
 dyq = torch.randn_like(yq)
 dxq, dw1, db1, dw2, db2 = ops.ffn_bwd(xq, hpre, dyq, plan, w1c, w2c, w1t, w2t)
 n = int(plan.offsets[-1])          # rows beyond the live queues are never written
-torch.save([t.float().cpu() for t in (yq[:n], hpre[:n], dxq[:n], dw1, db1, dw2, db2)], sys.argv[1])
+torch.save([t.float().cpu() for t in (yq[:n], dxq[:n], dw1, db1, dw2, db2)], sys.argv[1])
 """ % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     outs = []
     for fused in ("0", "1"):
@@ -143,7 +154,7 @@ torch.save([t.float().cpu() for t in (yq[:n], hpre[:n], dxq[:n], dw1, db1, dw2, 
         subprocess.run([sys.executable, "-c", code, path], check=True, env=env, timeout=300)
         outs.append(torch.load(path))
     n_rows = None
-    for a, b, name in zip(outs[0], outs[1], ("yq", "hpre", "dxq", "dw1", "db1", "dw2", "db2")):
-        # identical arithmetic up to the order of the fp32 accumulation over hidden chunks
+    for a, b, name in zip(outs[0], outs[1], ("yq", "dxq", "dw1", "db1", "dw2", "db2")):
+        # identical arithmetic up to the order of the fp32 accumulation over hidden chunks and the rounding of
+        # the saved state (two-kernel path keeps gelu'(z) in bf16, the chain kernel keeps z)
         assert nerr(b, a) < 1e-2, (name, nerr(b, a))
-    assert torch.equal(outs[0][1], outs[1][1]), "saved pre-activation must be bit-identical (same K order)"
