@@ -21,6 +21,7 @@ constexpr int kLanesPerTok = 16;
 constexpr int kPermThreads = 256;
 constexpr int kTokPerCta = kPermThreads / kLanesPerTok;
 constexpr int kMaxVec = 8;  // per-lane 8-element slices: D <= 16*8*8 = 1024
+constexpr int kGatherK = 4; // queue rows gathered per batch (loads in flight per lane = kGatherK * NV)
 
 // Queue addressing.  Single GPU: every queue row lives in the local buffer.
 // Expert parallel (EP): slot s belongs to rank slot_rank[s]; its row lives in that
@@ -100,21 +101,38 @@ combine_fwd_kernel(Queue<const TI> yq, const int32_t* __restrict__ pos, const fl
   for (int i = 0; i < NV; ++i)
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc[i].v[j] = 0.f;
-  for (int k = 0; k < K; ++k) {
-    const int row = __ldg(pos + (int64_t)t * K + k);
-    if (row < 0) continue;
-    const float s = __ldg(score + (int64_t)t * K + k);
-    const TI* src = yq.template row<EP>((int64_t)t * K + k, row, D);
-    Vec8 v[NV];
+  // rows are gathered kGatherK at a time, every load issued (raw, unconverted) before the first FMA
+  for (int k0 = 0; k0 < K; k0 += kGatherK) {
+    int row[kGatherK];
+    float s[kGatherK];
+    Raw8<TI> raw[kGatherK][NV];
 #pragma unroll
-    for (int i = 0; i < NV; ++i) {
-      const int c = sub + i * kLanesPerTok;
-      if (c < nvec) v[i] = load8<TI>(src + c * 8);
+    for (int u = 0; u < kGatherK; ++u) {
+      const int k = k0 + u;
+      row[u] = k < K ? __ldg(pos + (int64_t)t * K + k) : -1;
+      s[u] = row[u] >= 0 ? __ldg(score + (int64_t)t * K + k) : 0.f;
     }
 #pragma unroll
-    for (int i = 0; i < NV; ++i)
+    for (int u = 0; u < kGatherK; ++u) {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) acc[i].v[j] = fmaf(s, v[i].v[j], acc[i].v[j]);
+      for (int i = 0; i < NV; ++i) zero_raw8(raw[u][i]);
+      if (row[u] >= 0) {
+        const TI* src = yq.template row<EP>((int64_t)t * K + k0 + u, row[u], D);
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+          const int c = sub + i * kLanesPerTok;
+          if (c < nvec) load_raw8(raw[u][i], src + c * 8);
+        }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < kGatherK; ++u)    // k ascending, like bmm
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        const Vec8 v = cvt8(raw[u][i]);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i].v[j] = fmaf(s[u], v.v[j], acc[i].v[j]);
+      }
   }
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
@@ -219,7 +237,7 @@ dispatch_bwd_kernel(Queue<const TI> dxq, const int32_t* __restrict__ pos, int T,
 // a token read consecutive 32-byte slices (conflict-free).  Every 16-lane group owns TWO tokens, so
 // each weight slice read from smem feeds two tokens (the kernel was smem-bound with one).
 template <typename TI, typename TO, int NV, bool EP>
-__global__ void __launch_bounds__(kPermThreads)
+__global__ void __launch_bounds__(kPermThreads, 2)
 dispatch_bwd_gate_kernel(Queue<const TI> dxq, const int32_t* __restrict__ pos, int T, int K, int D,
                          const float* __restrict__ dz, const float* __restrict__ w_gate, int E,
                          TO* __restrict__ dx) {
@@ -247,48 +265,70 @@ dispatch_bwd_gate_kernel(Queue<const TI> dxq, const int32_t* __restrict__ pos, i
     for (int i = 0; i < NV; ++i)
 #pragma unroll
       for (int j = 0; j < 8; ++j) { a0[i].v[j] = 0.f; a1[i].v[j] = 0.f; }
-    for (int k = 0; k < K; ++k) {
-      const int r0 = __ldg(pos + (int64_t)t0 * K + k);
-      const int r1 = __ldg(pos + (int64_t)t1 * K + k);
-      Vec8 v0[NV], v1[NV];
+    // Software pipeline inside the thread: each phase ISSUES the (raw) loads of KB queue rows per token,
+    // then does its share of the router-term FMAs (which only touch dz and shared memory) while those
+    // loads are in flight, and only then adds the rows.
+    constexpr int KB = sizeof(TI) == 2 ? 2 : 1;
+    const int P = (K + KB - 1) / KB;
+    for (int ph = 0; ph < P; ++ph) {
+      Raw8<TI> q0[KB][NV], q1[KB][NV];
 #pragma unroll
-      for (int i = 0; i < NV; ++i) {
-        const int c = sub + i * kLanesPerTok;
-        if (c < nvec) {
-          if (r0 >= 0) v0[i] = load8<TI>(dxq.template row<EP>((int64_t)t0 * K + k, r0, D) + c * 8);
-          if (r1 >= 0) v1[i] = load8<TI>(dxq.template row<EP>((int64_t)t1 * K + k, r1, D) + c * 8);
+      for (int u = 0; u < KB; ++u) {
+        const int k = ph * KB + u;
+        const int r0 = k < K ? __ldg(pos + (int64_t)t0 * K + k) : -1;
+        const int r1 = k < K ? __ldg(pos + (int64_t)t1 * K + k) : -1;
+#pragma unroll
+        for (int i = 0; i < NV; ++i) { zero_raw8(q0[u][i]); zero_raw8(q1[u][i]); }
+        if (r0 >= 0) {
+          const TI* src = dxq.template row<EP>((int64_t)t0 * K + k, r0, D);
+#pragma unroll
+          for (int i = 0; i < NV; ++i) {
+            const int c = sub + i * kLanesPerTok;
+            if (c < nvec) load_raw8(q0[u][i], src + c * 8);
+          }
+        }
+        if (r1 >= 0) {
+          const TI* src = dxq.template row<EP>((int64_t)t1 * K + k, r1, D);
+#pragma unroll
+          for (int i = 0; i < NV; ++i) {
+            const int c = sub + i * kLanesPerTok;
+            if (c < nvec) load_raw8(q1[u][i], src + c * 8);
+          }
         }
       }
+      const int e_lo = ((E * ph) / P) & ~3;
+      const int e_hi = ph == P - 1 ? E : (((E * (ph + 1)) / P) & ~3);
+      for (int e = e_lo; e < e_hi; e += 4) {
+        const float4 g0 = __ldg(reinterpret_cast<const float4*>(dz + (int64_t)t0 * E + e));
+        const float4 g1 = __ldg(reinterpret_cast<const float4*>(dz + (int64_t)t1 * E + e));
+        const float z0[4] = {g0.x, g0.y, g0.z, g0.w};
+        const float z1[4] = {g1.x, g1.y, g1.z, g1.w};
 #pragma unroll
-      for (int i = 0; i < NV; ++i)
+        for (int ee = 0; ee < 4; ++ee) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          if (r0 >= 0) a0[i].v[j] += v0[i].v[j];
-          if (r1 >= 0) a1[i].v[j] += v1[i].v[j];
-        }
-    }
-    for (int e = 0; e < E; e += 4) {
-      const float4 g0 = __ldg(reinterpret_cast<const float4*>(dz + (int64_t)t0 * E + e));
-      const float4 g1 = __ldg(reinterpret_cast<const float4*>(dz + (int64_t)t1 * E + e));
-      const float z0[4] = {g0.x, g0.y, g0.z, g0.w};
-      const float z1[4] = {g1.x, g1.y, g1.z, g1.w};
+          for (int i = 0; i < NV; ++i) {
+            const int c = sub + i * kLanesPerTok;
+            if (c < nvec) {
+              const float4 wa = *reinterpret_cast<const float4*>(wt + (e + ee) * D + c * 4);
+              const float4 wb = *reinterpret_cast<const float4*>(wt + (e + ee) * D + half + c * 4);
+              const float w8[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
 #pragma unroll
-      for (int ee = 0; ee < 4; ++ee) {
-#pragma unroll
-        for (int i = 0; i < NV; ++i) {
-          const int c = sub + i * kLanesPerTok;
-          if (c < nvec) {
-            const float4 wa = *reinterpret_cast<const float4*>(wt + (e + ee) * D + c * 4);
-            const float4 wb = *reinterpret_cast<const float4*>(wt + (e + ee) * D + half + c * 4);
-            const float w8[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              a0[i].v[j] = fmaf(z0[ee], w8[j], a0[i].v[j]);
-              a1[i].v[j] = fmaf(z1[ee], w8[j], a1[i].v[j]);
+              for (int j = 0; j < 8; ++j) {
+                a0[i].v[j] = fmaf(z0[ee], w8[j], a0[i].v[j]);
+                a1[i].v[j] = fmaf(z1[ee], w8[j], a1[i].v[j]);
+              }
             }
           }
         }
       }
+#pragma unroll
+      for (int u = 0; u < KB; ++u)
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+          const Vec8 v0 = cvt8(q0[u][i]), v1 = cvt8(q1[u][i]);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) { a0[i].v[j] += v0.v[j]; a1[i].v[j] += v1.v[j]; }
+        }
     }
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
