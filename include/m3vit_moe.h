@@ -201,12 +201,16 @@ int m3_ep_plan(const int64_t* idx, const int32_t* pos_local, const int32_t* cnt_
                int32_t* overflow_flag, m3_stream_t stream);
 int m3_ep_dispatch_fwd(const void* x, int x_dtype, const int32_t* dst_rank, const int32_t* dst_row,
                        int T, int K, int D, void* const* peer_xq, int xq_dtype, m3_stream_t stream);
+/* ysave [T*K, D] (queue dtype, may be NULL): m3_ep_combine_fwd keeps a LOCAL copy, in slot order, of
+ * the result rows it pulls over NVLink; given to m3_ep_combine_bwd, dscore = <g, y> is computed from
+ * that copy and the backward pass only PUSHES dyq (peer_yq may then be NULL). */
 int m3_ep_combine_fwd(void* const* peer_yq, int yq_dtype, const int32_t* dst_rank,
                       const int32_t* dst_row, const float* score, int T, int K, int D, void* out,
-                      int out_dtype, m3_stream_t stream);
+                      int out_dtype, void* ysave, m3_stream_t stream);
 int m3_ep_combine_bwd(const void* g, int g_dtype, void* const* peer_yq, void* const* peer_dyq,
                       int q_dtype, const int32_t* dst_rank, const int32_t* dst_row,
-                      const float* score, int T, int K, int D, float* dscore, m3_stream_t stream);
+                      const float* score, int T, int K, int D, float* dscore, const void* ysave,
+                      m3_stream_t stream);
 int m3_ep_dispatch_bwd(void* const* peer_dxq, int dxq_dtype, const int32_t* dst_rank,
                        const int32_t* dst_row, int T, int K, int D, const float* dz,
                        const float* w_gate, int E, void* dx, int dx_dtype, m3_stream_t stream);

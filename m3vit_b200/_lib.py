@@ -47,8 +47,8 @@ SIGNATURES = {
     "m3_cast_weights_bf16": (_i, [_p, _i, _i, _i, _p, _p, _p]),
     "m3_ep_plan": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p]),
     "m3_ep_dispatch_fwd": (_i, [_p, _i, _p, _p, _i, _i, _i, _p, _i, _p]),
-    "m3_ep_combine_fwd": (_i, [_p, _i, _p, _p, _p, _i, _i, _i, _p, _i, _p]),
-    "m3_ep_combine_bwd": (_i, [_p, _i, _p, _p, _i, _p, _p, _p, _i, _i, _i, _p, _p]),
+    "m3_ep_combine_fwd": (_i, [_p, _i, _p, _p, _p, _i, _i, _i, _p, _i, _p, _p]),
+    "m3_ep_combine_bwd": (_i, [_p, _i, _p, _p, _i, _p, _p, _p, _i, _i, _i, _p, _p, _p]),
     "m3_ep_dispatch_bwd": (_i, [_p, _i, _p, _p, _i, _i, _i, _p, _p, _i, _p, _i, _p]),
     "m3_zero_pad_rows": (_i, [_p, _i, _p, _p, _i, _i, _p]),
     "m3_ep_barrier": (_i, [_p, _p, _p, _i, _i, _i, _i, _p]),

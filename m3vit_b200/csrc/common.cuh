@@ -111,6 +111,8 @@ __device__ __forceinline__ void load_raw8(Raw8<float>& r, const float* p) {
   r.b = ldg_stream(p + 4);
 }
 __device__ __forceinline__ void load_raw8(Raw8<__nv_bfloat16>& r, const __nv_bfloat16* p) { r.a = ldg_stream(p); }
+__device__ __forceinline__ void store_raw8(float* p, const Raw8<float>& r) { stg_stream(p, r.a); stg_stream(p + 4, r.b); }
+__device__ __forceinline__ void store_raw8(__nv_bfloat16* p, const Raw8<__nv_bfloat16>& r) { stg_stream(p, r.a); }
 __device__ __forceinline__ void zero_raw8(Raw8<float>& r) { r.a = make_uint4(0, 0, 0, 0); r.b = r.a; }
 __device__ __forceinline__ void zero_raw8(Raw8<__nv_bfloat16>& r) { r.a = make_uint4(0, 0, 0, 0); }
 __device__ __forceinline__ Vec8 cvt8(const Raw8<float>& q) {
@@ -290,6 +292,70 @@ __device__ __forceinline__ f32x2 gelu_fast_grad2(f32x2 x, f32x2* g) {
   const f32x2 cdf = add2(pk2(copysignf(q0, x0), copysignf(q1, x1)), M3_K2(0.5f));
   *g = mul2(x, cdf);
   return fma2(x, mul2(e, M3_K2(0.39894228040143267794f)), cdf);
+}
+
+// The same for NP independent pairs, written stage by stage: every stage is NP independent instructions,
+// so the dependent chains (rcp -> 5-deep Horner -> exp product) of different pairs overlap instead of
+// being issued back to back (the GEMM epilogues run on 2 warps per scheduler: ILP is all they have).
+// volatile variants: ptxas keeps volatile asm statements in program order, which is how the stage-by-stage
+// order below survives into SASS (left alone, its scheduler re-serialises each pair's dependent chain).
+__device__ __forceinline__ f32x2 fma2v(f32x2 a, f32x2 b, f32x2 c) {
+  f32x2 r;
+  asm volatile("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+__device__ __forceinline__ f32x2 mul2v(f32x2 a, f32x2 b) {
+  f32x2 r;
+  asm volatile("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ float rcp_approx_v(float x) {
+  float r;
+  asm volatile("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ float ex2_approx_v(float x) {
+  float r;
+  asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+template <int NP>
+__device__ __forceinline__ void gelu_fast_grad2_batch(const f32x2* x, f32x2* g, f32x2* gr) {
+  f32x2 t[NP], e[NP], p[NP];
+#pragma unroll
+  for (int i = 0; i < NP; ++i) {
+    float x0, x1, d0, d1;
+    unpk2(x[i], x0, x1);
+    unpk2(fma2(pk2(fabsf(x0), fabsf(x1)), M3_K2(0.3275911f * 0.70710678118654752440f), M3_K2(1.0f)), d0, d1);
+    t[i] = pk2(rcp_approx_v(d0), rcp_approx_v(d1));
+  }
+#pragma unroll
+  for (int i = 0; i < NP; ++i) {
+    float a0, a1;
+    unpk2(mul2(mul2(x[i], x[i]), M3_K2(-0.5f * 1.4426950408889634f)), a0, a1);
+    e[i] = pk2(ex2_approx_v(a0), ex2_approx_v(a1));
+  }
+#pragma unroll
+  for (int i = 0; i < NP; ++i) p[i] = fma2v(M3_K2(1.061405429f), t[i], M3_K2(-1.453152027f));
+#pragma unroll
+  for (int i = 0; i < NP; ++i) p[i] = fma2v(p[i], t[i], M3_K2(1.421413741f));
+#pragma unroll
+  for (int i = 0; i < NP; ++i) p[i] = fma2v(p[i], t[i], M3_K2(-0.284496736f));
+#pragma unroll
+  for (int i = 0; i < NP; ++i) p[i] = fma2v(p[i], t[i], M3_K2(0.254829592f));
+#pragma unroll
+  for (int i = 0; i < NP; ++i) p[i] = mul2v(p[i], t[i]);
+#pragma unroll
+  for (int i = 0; i < NP; ++i) p[i] = fma2(mul2(p[i], e[i]), M3_K2(-0.5f), M3_K2(0.5f));   // |Phi(x) - 1/2|
+#pragma unroll
+  for (int i = 0; i < NP; ++i) {
+    float x0, x1, q0, q1;
+    unpk2(x[i], x0, x1);
+    unpk2(p[i], q0, q1);
+    const f32x2 cdf = add2(pk2(copysignf(q0, x0), copysignf(q1, x1)), M3_K2(0.5f));
+    g[i] = mul2(x[i], cdf);
+    gr[i] = fma2(x[i], mul2(e[i], M3_K2(0.39894228040143267794f)), cdf);
+  }
 }
 
 }  // namespace m3

@@ -91,7 +91,7 @@ dispatch_fwd_kernel(const TI* __restrict__ x, const int32_t* __restrict__ pos, c
 template <typename TI, typename TO, int NV, bool EP>
 __global__ void __launch_bounds__(kPermThreads)
 combine_fwd_kernel(Queue<const TI> yq, const int32_t* __restrict__ pos, const float* __restrict__ score,
-                   int T, int K, int D, TO* __restrict__ out) {
+                   int T, int K, int D, TO* __restrict__ out, TI* __restrict__ ysave) {
   const int sub = threadIdx.x % kLanesPerTok;
   const int t = blockIdx.x * kTokPerCta + threadIdx.x / kLanesPerTok;
   if (t >= T) return;
@@ -133,6 +133,20 @@ combine_fwd_kernel(Queue<const TI> yq, const int32_t* __restrict__ pos, const fl
 #pragma unroll
         for (int j = 0; j < 8; ++j) acc[i].v[j] = fmaf(s[u], v.v[j], acc[i].v[j]);
       }
+    // expert parallel: keep a LOCAL copy of the rows just pulled over NVLink (slot order), so that the
+    // backward pass (dscore = <g, y>) does not have to pull them a second time
+    if (ysave != nullptr) {
+#pragma unroll
+      for (int u = 0; u < kGatherK; ++u) {
+        if (row[u] < 0) continue;
+        TI* dst = ysave + ((int64_t)t * K + k0 + u) * D;
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+          const int c = sub + i * kLanesPerTok;
+          if (c < nvec) store_raw8(dst + c * 8, raw[u][i]);
+        }
+      }
+    }
   }
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
@@ -147,7 +161,7 @@ __global__ void __launch_bounds__(kPermThreads)
 combine_bwd_kernel(const TG* __restrict__ g, Queue<const TQ> yq, const int32_t* __restrict__ pos,
                    const float* __restrict__ score, const int32_t* __restrict__ counts,
                    const int32_t* __restrict__ offsets, int T, int K, int D, int tok_ctas,
-                   Queue<TQ> dyq, float* __restrict__ dscore) {
+                   Queue<TQ> dyq, float* __restrict__ dscore, const TQ* __restrict__ ysave) {
   if ((int)blockIdx.x >= tok_ctas) {
     zero_pad_rows<TQ>(dyq.local, counts, offsets, blockIdx.x - tok_ctas, D);
     return;
@@ -168,7 +182,8 @@ combine_bwd_kernel(const TG* __restrict__ g, Queue<const TQ> yq, const int32_t* 
     const float s = __ldg(score + (int64_t)t * K + k);
     float dot = 0.f;
     if (row >= 0) {
-      const TQ* ysrc = yq.template row<EP>((int64_t)t * K + k, row, D);
+      const TQ* ysrc = ysave != nullptr ? ysave + ((int64_t)t * K + k) * D      // local copy kept by combine_fwd (EP)
+                                        : yq.template row<EP>((int64_t)t * K + k, row, D);
       TQ* ddst = dyq.template row<EP>((int64_t)t * K + k, row, D);
       Vec8 yv[NV];
 #pragma unroll
@@ -395,7 +410,7 @@ static int dispatch_fwd_impl(const void* x, int x_dtype, const int32_t* pos, con
 template <bool EP>
 static int combine_fwd_impl(const void* yq, void* const* peer, const int32_t* slot_rank, int yq_dtype,
                             const int32_t* pos, const float* score, int T, int K, int D, void* out, int out_dtype,
-                            cudaStream_t st) {
+                            void* ysave, cudaStream_t st) {
   int rc = perm_common_check(T, K, D);
   if (rc) return rc;
   if (T == 0) return M3_OK;
@@ -403,7 +418,7 @@ static int combine_fwd_impl(const void* yq, void* const* peer, const int32_t* sl
   const int grid = m3_ceil_div(T, kTokPerCta);
   M3_DTYPE2_SWITCH(yq_dtype, out_dtype, {
     Queue<const TA> q{(const TA*)yq, (const TA* const*)peer, slot_rank};
-    M3_NV_SWITCH((combine_fwd_kernel<TA, TB, NV, EP><<<grid, kPermThreads, 0, st>>>(q, pos, score, T, K, D, (TB*)out)))
+    M3_NV_SWITCH((combine_fwd_kernel<TA, TB, NV, EP><<<grid, kPermThreads, 0, st>>>(q, pos, score, T, K, D, (TB*)out, (TA*)ysave)))
   })
   M3_LAUNCH_CHECK();
   return M3_OK;
@@ -413,7 +428,7 @@ template <bool EP>
 static int combine_bwd_impl(const void* g, int g_dtype, const void* yq, void* const* peer_yq, void* dyq,
                             void* const* peer_dyq, const int32_t* slot_rank, int q_dtype, const int32_t* pos,
                             const float* score, const int32_t* counts, const int32_t* offsets, int T, int K, int D,
-                            int E, float* dscore, cudaStream_t st) {
+                            int E, float* dscore, const void* ysave, cudaStream_t st) {
   int rc = perm_common_check(T, K, D);
   if (rc) return rc;
   const int nv = perm_nv(D);
@@ -423,7 +438,7 @@ static int combine_bwd_impl(const void* g, int g_dtype, const void* yq, void* co
   M3_DTYPE2_SWITCH(g_dtype, q_dtype, {
     Queue<const TB> qy{(const TB*)yq, (const TB* const*)peer_yq, slot_rank};
     Queue<TB> qd{(TB*)dyq, (TB* const*)peer_dyq, slot_rank};
-    M3_NV_SWITCH((combine_bwd_kernel<TA, TB, NV, EP><<<grid, kPermThreads, 0, st>>>((const TA*)g, qy, pos, score, counts, offsets, T, K, D, tok_ctas, qd, dscore)))
+    M3_NV_SWITCH((combine_bwd_kernel<TA, TB, NV, EP><<<grid, kPermThreads, 0, st>>>((const TA*)g, qy, pos, score, counts, offsets, T, K, D, tok_ctas, qd, dscore, (const TB*)ysave)))
   })
   M3_LAUNCH_CHECK();
   return M3_OK;
@@ -478,7 +493,7 @@ extern "C" int m3_combine_fwd(const void* yq, int yq_dtype, const int32_t* pos, 
                               int D, void* out, int out_dtype, m3_stream_t stream) {
   M3_CHECK_ARG(yq && pos && score && out);
   M3_CHECK_ALIGN16(yq); M3_CHECK_ALIGN16(out);
-  return combine_fwd_impl<false>(yq, nullptr, nullptr, yq_dtype, pos, score, T, K, D, out, out_dtype,
+  return combine_fwd_impl<false>(yq, nullptr, nullptr, yq_dtype, pos, score, T, K, D, out, out_dtype, nullptr,
                                  static_cast<cudaStream_t>(stream));
 }
 
@@ -489,7 +504,7 @@ extern "C" int m3_combine_bwd(const void* g, int g_dtype, const void* yq, int yq
   if (yq_dtype != dyq_dtype) return M3_ERR_UNSUPPORTED;
   M3_CHECK_ALIGN16(g); M3_CHECK_ALIGN16(yq); M3_CHECK_ALIGN16(dyq);
   return combine_bwd_impl<false>(g, g_dtype, yq, nullptr, dyq, nullptr, nullptr, yq_dtype, pos, score, counts,
-                                 offsets, T, K, D, E, dscore, static_cast<cudaStream_t>(stream));
+                                 offsets, T, K, D, E, dscore, nullptr, static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int m3_dispatch_bwd(const void* dxq, int dxq_dtype, const int32_t* pos, int T, int K, int D,
@@ -513,21 +528,23 @@ extern "C" int m3_ep_dispatch_fwd(const void* x, int x_dtype, const int32_t* dst
 }
 
 extern "C" int m3_ep_combine_fwd(void* const* peer_yq, int yq_dtype, const int32_t* dst_rank, const int32_t* dst_row,
-                                 const float* score, int T, int K, int D, void* out, int out_dtype,
+                                 const float* score, int T, int K, int D, void* out, int out_dtype, void* ysave,
                                  m3_stream_t stream) {
   M3_CHECK_ARG(peer_yq && dst_rank && dst_row && score && out);
   M3_CHECK_ALIGN16(out);
-  return combine_fwd_impl<true>(nullptr, peer_yq, dst_rank, yq_dtype, dst_row, score, T, K, D, out, out_dtype,
+  if (ysave) M3_CHECK_ALIGN16(ysave);
+  return combine_fwd_impl<true>(nullptr, peer_yq, dst_rank, yq_dtype, dst_row, score, T, K, D, out, out_dtype, ysave,
                                 static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int m3_ep_combine_bwd(const void* g, int g_dtype, void* const* peer_yq, void* const* peer_dyq, int q_dtype,
                                  const int32_t* dst_rank, const int32_t* dst_row, const float* score, int T, int K,
-                                 int D, float* dscore, m3_stream_t stream) {
-  M3_CHECK_ARG(g && peer_yq && peer_dyq && dst_rank && dst_row && score && dscore);
+                                 int D, float* dscore, const void* ysave, m3_stream_t stream) {
+  M3_CHECK_ARG(g && (peer_yq || ysave) && peer_dyq && dst_rank && dst_row && score && dscore);
   M3_CHECK_ALIGN16(g);
+  if (ysave) M3_CHECK_ALIGN16(ysave);
   return combine_bwd_impl<true>(g, g_dtype, nullptr, peer_yq, nullptr, peer_dyq, dst_rank, q_dtype, dst_row, score,
-                                nullptr, nullptr, T, K, D, 0, dscore, static_cast<cudaStream_t>(stream));
+                                nullptr, nullptr, T, K, D, 0, dscore, ysave, static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int m3_ep_dispatch_bwd(void* const* peer_dxq, int dxq_dtype, const int32_t* dst_rank,

@@ -221,6 +221,7 @@ class EPFwdState:
     xq: Optional[torch.Tensor] = None
     yq: Optional[torch.Tensor] = None
     hpre: Optional[torch.Tensor] = None
+    ysave: Optional[torch.Tensor] = None      # local copy of the pulled result rows [T*K, D]
     nbytes_q: int = 0
 
 
@@ -277,12 +278,15 @@ def phase_c_ffn(ctx: EPContext, st: EPFwdState, w1c, b1, w2c, b2, save_hpre: boo
     ops.launch_count += 2
 
 
-def phase_d_combine(ctx: EPContext, st: EPFwdState, T, D, top_k, out_dtype) -> torch.Tensor:
-    """PULL result rows from the owners' yq queues and combine with the gate scores."""
+def phase_d_combine(ctx: EPContext, st: EPFwdState, T, D, top_k, out_dtype, keep_rows: bool = True) -> torch.Tensor:
+    """PULL result rows from the owners' yq queues and combine with the gate scores.  With `keep_rows` the
+    pulled rows are also kept locally (slot order) so that the backward pass does not pull them again."""
     out = torch.empty(T, D, dtype=out_dtype, device=st.g.score.device)
     peers = ctx.peer_ptrs(st.off_yq)
+    st.ysave = torch.empty(T * top_k, D, dtype=st.yq.dtype, device=out.device) if keep_rows else None
     check(load().m3_ep_combine_fwd(ptr(peers), dtype_code(st.yq), ptr(st.dst_rank), ptr(st.dst_row), ptr(st.g.score),
-                                   T, top_k, D, ptr(out), dtype_code(out), stream_ptr()), "m3_ep_combine_fwd")
+                                   T, top_k, D, ptr(out), dtype_code(out), ptr(st.ysave), stream_ptr()),
+          "m3_ep_combine_fwd")
     ops.launch_count += 1
     return out
 
@@ -308,8 +312,8 @@ def phase_e_combine_bwd(ctx: EPContext, st: EPFwdState, g_out, top_k) -> EPBwdSt
     bs.dscore = torch.empty(T, top_k, dtype=torch.float32, device=g_out.device)
     py, pd = ctx.peer_ptrs(st.off_yq), ctx.peer_ptrs(bs.off_dyq)
     check(lib.m3_ep_combine_bwd(ptr(g_out), dtype_code(g_out), ptr(py), ptr(pd), dtype_code(bs.dyq), ptr(st.dst_rank),
-                                ptr(st.dst_row), ptr(st.g.score), T, top_k, D, ptr(bs.dscore), stream_ptr()),
-          "m3_ep_combine_bwd")
+                                ptr(st.dst_row), ptr(st.g.score), T, top_k, D, ptr(bs.dscore), ptr(st.ysave),
+                                stream_ptr()), "m3_ep_combine_bwd")
     check(lib.m3_zero_pad_rows(ptr(bs.dyq), dtype_code(bs.dyq), ptr(st.recv.counts), ptr(st.recv.offsets), E_loc, D,
                                stream_ptr()), "m3_zero_pad_rows")
     ops.launch_count += 2
@@ -391,7 +395,7 @@ class EPMoEFunction(torch.autograd.Function):
         grp.barrier(x.device)                                         # every push has landed
         phase_c_ffn(ep, st, w1c, b1, w2c, b2, needs_grad)
         grp.barrier(x.device)                                         # every owner's yq is complete
-        out = phase_d_combine(ep, st, T, D, top_k, x.dtype)
+        out = phase_d_combine(ep, st, T, D, top_k, x.dtype, keep_rows=needs_grad)
         g, pl = st.g, st.plan_local
         if needs_grad:
             ctx.st, ctx.ep = st, ep
