@@ -135,7 +135,7 @@ combine_fwd_kernel(Queue<const TI> yq, const int32_t* __restrict__ pos, const fl
       }
     // expert parallel: keep a LOCAL copy of the rows just pulled over NVLink (slot order), so that the
     // backward pass (dscore = <g, y>) does not have to pull them a second time
-    if (ysave != nullptr) {
+    if (EP && ysave != nullptr) {
 #pragma unroll
       for (int u = 0; u < kGatherK; ++u) {
         if (row[u] < 0) continue;
@@ -177,38 +177,63 @@ combine_bwd_kernel(const TG* __restrict__ g, Queue<const TQ> yq, const int32_t* 
     const int c = sub + i * kLanesPerTok;
     if (c < nvec) gv[i] = load8<TG>(g + (int64_t)t * D + c * 8);
   }
-  for (int k = 0; k < K; ++k) {
-    const int row = __ldg(pos + (int64_t)t * K + k);
-    const float s = __ldg(score + (int64_t)t * K + k);
-    float dot = 0.f;
-    if (row >= 0) {
-      const TQ* ysrc = ysave != nullptr ? ysave + ((int64_t)t * K + k) * D      // local copy kept by combine_fwd (EP)
-                                        : yq.template row<EP>((int64_t)t * K + k, row, D);
-      TQ* ddst = dyq.template row<EP>((int64_t)t * K + k, row, D);
-      Vec8 yv[NV];
+  // the y rows of kGatherK slots are loaded (raw) together; the dyq stores do not depend on them and go first
+  for (int k0 = 0; k0 < K; k0 += kGatherK) {
+    int row[kGatherK];
+    float s[kGatherK];
+    Raw8<TQ> raw[kGatherK][NV];
 #pragma unroll
-      for (int i = 0; i < NV; ++i) {
-        const int c = sub + i * kLanesPerTok;
-        if (c < nvec) yv[i] = load8<TQ>(ysrc + c * 8);
+    for (int u = 0; u < kGatherK; ++u) {
+      const int k = k0 + u;
+      row[u] = k < K ? __ldg(pos + (int64_t)t * K + k) : -1;
+      s[u] = row[u] >= 0 ? __ldg(score + (int64_t)t * K + k) : 0.f;
+    }
+#pragma unroll
+    for (int u = 0; u < kGatherK; ++u) {
+#pragma unroll
+      for (int i = 0; i < NV; ++i) zero_raw8(raw[u][i]);
+      if (row[u] >= 0) {
+        const int64_t slot = (int64_t)t * K + k0 + u;
+        const TQ* ysrc = (EP && ysave != nullptr) ? ysave + slot * D        // local copy kept by combine_fwd
+                                                  : yq.template row<EP>(slot, row[u], D);
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+          const int c = sub + i * kLanesPerTok;
+          if (c < nvec) load_raw8(raw[u][i], ysrc + c * 8);
+        }
       }
+    }
 #pragma unroll
-      for (int i = 0; i < NV; ++i) {
-        const int c = sub + i * kLanesPerTok;
-        if (c < nvec) {
+    for (int u = 0; u < kGatherK; ++u) {
+      if (row[u] >= 0 && valid) {
+        TQ* ddst = dyq.template row<EP>((int64_t)t * K + k0 + u, row[u], D);
 #pragma unroll
-          for (int j = 0; j < 8; ++j) dot = fmaf(gv[i].v[j], yv[i].v[j], dot);
-          if (valid) {
+        for (int i = 0; i < NV; ++i) {
+          const int c = sub + i * kLanesPerTok;
+          if (c < nvec) {
             Vec8 o;
 #pragma unroll
-            for (int j = 0; j < 8; ++j) o.v[j] = s * gv[i].v[j];
+            for (int j = 0; j < 8; ++j) o.v[j] = s[u] * gv[i].v[j];
             store8<TQ>(ddst + c * 8, o);
           }
         }
       }
     }
 #pragma unroll
-    for (int o = kLanesPerTok / 2; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
-    if (valid && sub == 0) dscore[(int64_t)t * K + k] = dot;
+    for (int u = 0; u < kGatherK; ++u) {
+      float dot = 0.f;
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        if (sub + i * kLanesPerTok < nvec) {
+          const Vec8 yv = cvt8(raw[u][i]);    // zero where nothing was loaded
+#pragma unroll
+          for (int j = 0; j < 8; ++j) dot = fmaf(gv[i].v[j], yv.v[j], dot);
+        }
+      }
+#pragma unroll
+      for (int o = kLanesPerTok / 2; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
+      if (valid && sub == 0 && k0 + u < K) dscore[(int64_t)t * K + k0 + u] = dot;
+    }
   }
 }
 

@@ -377,6 +377,7 @@ class EPMoEFunction(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, gate_x, w_gate, task_feat, w1, b1, w2, b2, noise, top_k, noise_stddev, compute_dtype,
                 want_gates, wcache, ep: EPContext):
+        ctx.set_materialize_grads(False)      # undefined output grads stay None (no zero fills)
         T, D = x.shape
         E_loc = w1.shape[0]
         E_tot = w_gate.shape[1]

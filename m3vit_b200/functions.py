@@ -39,6 +39,7 @@ class MoEFunction(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, gate_x, w_gate, task_feat, w1, b1, w2, b2, noise, top_k, noise_stddev, compute_dtype,
                 want_gates, wcache):
+        ctx.set_materialize_grads(False)      # undefined output grads stay None (no zero fills)
         T, D = x.shape
         E, H, _ = w1.shape
         x = _c(x)
@@ -109,6 +110,7 @@ class MoEBlockFunction(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, ln_w, ln_b, w_gate, task_feat, w1, b1, w2, b2, noise, eps, top_k, noise_stddev,
                 compute_dtype, want_gates, wcache):
+        ctx.set_materialize_grads(False)      # undefined output grads stay None (no zero fills)
         T, D = x.shape
         E = w1.shape[0]
         x = _c(x)
@@ -163,6 +165,7 @@ class GateFunction(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, gx, w_gate, task_feat, noise, top_k, noise_stddev, want_gates):
+        ctx.set_materialize_grads(False)      # undefined output grads stay None (no zero fills)
         gx = _c(gx)
         E = w_gate.shape[1]
         g = ops.gate_fwd(gx, w_gate, top_k, task_feat, noise, noise_stddev, want_gates)
@@ -195,6 +198,7 @@ class ExpertsFunction(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, idx, score, w1, b1, w2, b2, compute_dtype, wcache, plan: Optional[ops.Plan]):
+        ctx.set_materialize_grads(False)      # undefined output grads stay None (no zero fills)
         T, D = x.shape
         E = w1.shape[0]
         K = idx.shape[1]
@@ -221,6 +225,8 @@ class ExpertsFunction(torch.autograd.Function):
         x, w1c, w2c, w1t, w2t, xq, hpre, yq, score, counts, offsets, pos, tile_expert = ctx.saved_tensors
         K, cap_rows = ctx.cfg
         plan = ops.Plan(counts, offsets, pos, tile_expert, cap_rows, PAD_ROWS)
+        if d_out is None:
+            d_out = torch.zeros_like(x)
         dyq, dscore = ops.combine_bwd(_c(d_out), yq, plan, score)
         dxq, dw1, db1, dw2, db2 = ops.ffn_bwd(xq, hpre, dyq, plan, w1c, w2c, w1t, w2t)
         dx = ops.dispatch_bwd(dxq, plan, x.shape[0], K, out_dtype=x.dtype)
