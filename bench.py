@@ -240,8 +240,14 @@ def main():
         assert N_EXP % world == 0
         el = 2 if cdt == torch.bfloat16 else 4
         q_bytes = ((int(args.capacity_factor * T * TOP_K) + (N_EXP // world) * 255 + 255) // 256 * 256) * D_MODEL * el
-        ep_ctx = ep.make_context(ep.TorchDistGroup(), dev, arena_bytes=6 * (q_bytes + 4096),
-                                 capacity_factor=args.capacity_factor)
+        if os.environ.get("M3_EP_OVERLAP", "0") == "1":
+            # opt-in: two half-batches on two streams, the NVLink movers of one half overlap the GEMMs of the other.
+            # Correct (tools/ep_multiproc_check.py ... pipe) but host-launch-bound from Python today.
+            ep_ctx = ep.make_pipelined_context(ep.TorchDistGroup(), dev, arena_bytes=6 * (q_bytes // 2 + (1 << 20)),
+                                               capacity_factor=args.capacity_factor)
+        else:
+            ep_ctx = ep.make_context(ep.TorchDistGroup(), dev, arena_bytes=6 * (q_bytes + 4096),
+                                     capacity_factor=args.capacity_factor)
     layers = build_layers(dev, cdt, rank, world, ep_ctx)
     from m3vit_b200.synthetic import device_tokens
     calls = [(li, t) for t in range(N_TASK) for li in range(N_LAYER)]      # per task: a full backbone pass
@@ -268,10 +274,19 @@ def main():
     sampler.mark_start()
     ops.launch_count = 0
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    prof = None
+    if os.environ.get("M3_BENCH_CPROFILE") and rank == 0:      # host-side profile of the timed loop (debug)
+        import cProfile
+        prof = cProfile.Profile()
+        prof.enable()
     e0.record()
     for _ in range(args.steps):
         step_resident()
     e1.record()
+    if prof is not None:
+        prof.disable()
+        import pstats
+        pstats.Stats(prof, stream=sys.stderr).sort_stats("tottime").print_stats(28)
     barrier()
     sampler.mark_end()
     ms = e0.elapsed_time(e1)

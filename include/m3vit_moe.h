@@ -159,6 +159,9 @@ int m3_combine_bwd(const void* g, int g_dtype, const void* yq, int yq_dtype, con
  */
 size_t m3_ffn_workspace_bytes(int dtype, int cap_rows, int D, int H, int E, int backward);
 size_t m3_ffn_saved_bytes(int dtype, int cap_rows, int H);
+/* Process-wide tuning knob: SMs the persistent tcgen05 GEMMs may occupy (default / out of range: all 148).
+ * The overlapped expert-parallel mode lowers it so that NVLink row movers run beside a GEMM. */
+int m3_set_gemm_sm_limit(int sms);
 int m3_ffn_fwd(int dtype, const void* xq, const int32_t* offsets, const int32_t* tile_expert,
                int cap_rows, int E, int D, int H, const void* w1, const float* b1, const void* w2,
                const float* b2, void* saved, void* yq, void* workspace, size_t workspace_bytes,
@@ -266,6 +269,9 @@ size_t m3_ln_bwd_workspace_bytes(int T, int D);
 int m3_ln_bwd_res(const float* dxn, const float* x, const float* mean, const float* rstd,
                   const float* gamma, const float* dres, int T, int D, float* dx, float* dgamma,
                   float* dbeta, void* workspace, size_t workspace_bytes, m3_stream_t stream);
+
+/* Debug only: occupy `n_ctas` whole SMs for `cycles` clocks (measures what other kernels get from the rest). */
+int m3_debug_occupy(int n_ctas, long long cycles, int* sink, m3_stream_t stream);
 
 /* Debug only: clock64 timeline of CTA 0 of the fused FFN kernel (enable, then call again with a host
  * buffer of 2*max_events uint64 to fetch {tag, clock} pairs).  Synchronises the device. */

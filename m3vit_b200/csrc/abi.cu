@@ -14,6 +14,7 @@ int m3_ffn_bwd_f32(const float* xq, const float* hpre, const float* dyq, const i
                    void* workspace, size_t workspace_bytes, cudaStream_t st);
 size_t m3_ffn_bf16_workspace_bytes(int cap_rows, int D, int H, int E, int backward);
 size_t m3_ffn_bf16_saved_bytes(int cap_rows, int H);
+int m3_ffn_bf16_set_sm_limit(int sms);
 int m3_ffn_fwd_bf16(const void* xq, const int32_t* offsets, const int32_t* tile_expert, int cap_rows, int E, int D,
                     int H, const void* w1, const float* b1, const void* w2, const float* b2, void* hpre, void* yq,
                     void* workspace, size_t workspace_bytes, cudaStream_t st);
@@ -54,6 +55,8 @@ extern "C" size_t m3_ffn_workspace_bytes(int dtype, int cap_rows, int D, int H, 
   if (dtype == M3_F32) return (size_t)cap_rows * H * sizeof(float);
   return m3_ffn_bf16_workspace_bytes(cap_rows, D, H, E, backward);
 }
+
+extern "C" int m3_set_gemm_sm_limit(int sms) { return m3_ffn_bf16_set_sm_limit(sms); }
 
 extern "C" size_t m3_ffn_saved_bytes(int dtype, int cap_rows, int H) {
   if (cap_rows < 0 || H <= 0) return 0;
@@ -104,6 +107,30 @@ extern "C" int m3_ffn_bwd(int dtype, const void* xq, const void* hpre, const voi
                            dw1, db1, dw2, db2, workspace, workspace_bytes, st);
   }
   return M3_ERR_UNSUPPORTED;
+}
+
+// ------------------------------------------------------------------ debug: SM occupier
+namespace m3 {
+// Fills whole SMs (1024 threads, > 32 registers each, 200 KB of shared memory: nothing else co-resides) and
+// spins for `cycles`.  Used by tools/ep_overlap_probe.py to measure what the NVLink row movers achieve on the
+// SMs a concurrently running persistent GEMM leaves free.
+__global__ void __launch_bounds__(1024) occupy_kernel(long long cycles, int* sink) {
+  extern __shared__ int occupy_smem[];
+  const long long t0 = clock64();
+  int acc = 0;
+  while (clock64() - t0 < cycles) acc += occupy_smem[threadIdx.x & 255];
+  if (acc == 0x7fffffff) *sink = acc;
+}
+}  // namespace m3
+
+extern "C" int m3_debug_occupy(int n_ctas, long long cycles, int* sink, m3_stream_t stream) {
+  M3_CHECK_ARG(n_ctas > 0 && cycles > 0 && sink);
+  const int smem = 200 * 1024;
+  cudaError_t e = cudaFuncSetAttribute(m3::occupy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  if (e != cudaSuccess) return (int)e;
+  m3::occupy_kernel<<<n_ctas, 1024, smem, static_cast<cudaStream_t>(stream)>>>(cycles, sink);
+  M3_LAUNCH_CHECK();
+  return M3_OK;
 }
 
 // ------------------------------------------------------------------ weight cast

@@ -507,13 +507,17 @@ static int pick_bn(int N, bool heavy_epilogue) {
 
 constexpr int kGGNcta = 2;   // CTA pairs: halves the per-SM weight traffic (the GEMMs are L2 -> SM bound at K = 384)
 
+// SMs the persistent grouped GEMMs may occupy.  Expert parallelism with overlap (ep.py) lowers it so that the NVLink row
+// movers of the other half-batch find free SMs while a GEMM runs (they need ~12-20 SMs: tools/ep_overlap_probe.py).
+static int g_gemm_sms = kNumSMs;
+
 template <int BN, int EPI>
 static int launch_gg_t(const CUtensorMap* maps, const GGParams& p, int max_tiles, cudaStream_t st) {
   using Cfg = GGCfg<BN, EPI, kGGNcta>;
   auto kern = gg_kernel<BN, EPI, kGGNcta>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
   if (e != cudaSuccess) return (int)e;
-  int grid = max_tiles < kNumSMs ? max_tiles : kNumSMs;
+  int grid = max_tiles < g_gemm_sms ? max_tiles : g_gemm_sms;
   grid = grid / kGGNcta * kGGNcta;
   if (grid < kGGNcta) grid = kGGNcta;
   cudaLaunchConfig_t cfg{};
@@ -713,4 +717,10 @@ int m3_ffn_bwd_bf16(const void* xq, const void* saved, const void* dyq, const in
   rc = launch_wgrad(dyq, h, offsets, cap_rows, E, D, H, dw2, db2, part, st);
   if (rc) return rc;
   return launch_wgrad(dhpre, xq, offsets, cap_rows, E, H, D, dw1, db1, part, st);
+}
+
+int m3_ffn_bf16_set_sm_limit(int sms) {
+  if (sms < 2 || sms > kNumSMs) sms = kNumSMs;
+  g_gemm_sms = sms;
+  return M3_OK;
 }

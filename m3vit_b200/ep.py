@@ -130,6 +130,7 @@ class PeerFlagGroup:
         assert off_flags == 0
         arena._bytes[: self.HEADER].zero_()
         self.flag_ptrs = bases + off_flags
+        self._gp_cache = {}
         self.gather_ptrs = bases + self.off_gather
         torch.cuda.synchronize(arena.device)
         bootstrap.barrier(arena.device)                    # flags are zeroed everywhere before first use
@@ -151,7 +152,9 @@ class PeerFlagGroup:
         half = (self.epoch + 1) & 1
         goff = self.off_gather + half * (self.HEADER - 4096) // 2
         self.epoch += 1
-        gp = self.bases + goff
+        gp = self._gp_cache.get(goff)
+        if gp is None:
+            gp = self._gp_cache[goff] = self.bases + goff
         check(load().m3_ep_barrier(ptr(self.flag_ptrs), ptr(gp), ptr(counts), n, self.rank, self.world, self.epoch,
                                    stream_ptr()), "m3_ep_barrier")
         ops.launch_count += 1
@@ -170,7 +173,13 @@ class EPContext:
     overflow: torch.Tensor              # [1] int32 device flag set by m3_ep_plan
 
     def peer_ptrs(self, off: int) -> torch.Tensor:
-        return self.bases + off
+        """[W] device array of `arena base + off` of every rank.  Cached: the lockstep allocator hands out the same
+        few offsets call after call, and `bases + off` would otherwise launch a kernel each time."""
+        cache = self.__dict__.setdefault("_peer_cache", {})
+        t = cache.get(off)
+        if t is None:
+            t = cache[off] = self.bases + off
+        return t
 
     def cap_rows(self, T: int, K: int, E_loc: int) -> int:
         f = float(self.world) if self.capacity_factor is None else min(float(self.world), self.capacity_factor)
@@ -278,10 +287,13 @@ def phase_c_ffn(ctx: EPContext, st: EPFwdState, w1c, b1, w2c, b2, save_hpre: boo
     ops.launch_count += 2
 
 
-def phase_d_combine(ctx: EPContext, st: EPFwdState, T, D, top_k, out_dtype, keep_rows: bool = True) -> torch.Tensor:
+def phase_d_combine(ctx: EPContext, st: EPFwdState, T, D, top_k, out_dtype, keep_rows: bool = True,
+                    out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """PULL result rows from the owners' yq queues and combine with the gate scores.  With `keep_rows` the
     pulled rows are also kept locally (slot order) so that the backward pass does not pull them again."""
-    out = torch.empty(T, D, dtype=out_dtype, device=st.g.score.device)
+    if out is None:
+        out = torch.empty(T, D, dtype=out_dtype, device=st.g.score.device)
+    assert out.is_contiguous() and out.shape == (T, D)
     peers = ctx.peer_ptrs(st.off_yq)
     st.ysave = torch.empty(T * top_k, D, dtype=st.yq.dtype, device=out.device) if keep_rows else None
     check(load().m3_ep_combine_fwd(ptr(peers), dtype_code(st.yq), ptr(st.dst_rank), ptr(st.dst_row), ptr(st.g.score),
@@ -341,9 +353,11 @@ def phase_f_ffn_bwd(ctx: EPContext, st: EPFwdState, bs: EPBwdState, w1c, w2c, w1
     bs.grads = (dw1, db1, dw2, db2)
 
 
-def phase_g_dispatch_bwd(ctx: EPContext, st: EPFwdState, bs: EPBwdState, T, D, top_k, dz, w_gate, out_dtype):
+def phase_g_dispatch_bwd(ctx: EPContext, st: EPFwdState, bs: EPBwdState, T, D, top_k, dz, w_gate, out_dtype,
+                         out: Optional[torch.Tensor] = None):
     """PULL dxq rows from the owners and sum them per token (+ the router's dx)."""
-    dx = torch.empty(T, D, dtype=out_dtype, device=st.g.score.device)
+    dx = out if out is not None else torch.empty(T, D, dtype=out_dtype, device=st.g.score.device)
+    assert dx.is_contiguous() and dx.shape == (T, D)
     peers = ctx.peer_ptrs(bs.off_dxq)
     E = w_gate.shape[1] if dz is not None else 0
     check(load().m3_ep_dispatch_bwd(ptr(peers), dtype_code(bs.dxq), ptr(st.dst_rank), ptr(st.dst_row), T, top_k, D,
@@ -447,18 +461,182 @@ class EPMoEFunction(torch.autograd.Function):
         return dx, dgx, dwg, dtf, dw1, db1, dw2, db2, None, None, None, None, None, None, None
 
 
+# ----------------------------------------------------------------------------- overlapped variant
+@dataclass
+class EPPipe:
+    """Two independent EP contexts (arena + flag group each) and two side streams: the token batch is cut in
+    two halves whose phase sequences run on different streams, so the NVLink movers of one half overlap the
+    GEMMs of the other.  The persistent GEMMs are confined to `gemm_sms` SMs (m3_set_gemm_sm_limit) so that
+    the movers always find free SMs (they need 12-20: tools/ep_overlap_probe.py)."""
+    ctxs: List[EPContext]
+    streams: List[torch.cuda.Stream]
+    rank: int
+    world: int
+
+    def check_overflow(self) -> None:
+        for c in self.ctxs:
+            c.check_overflow()
+
+
+def make_pipelined_context(group, device, arena_bytes: int, capacity_factor: Optional[float] = 2.0,
+                           gemm_sms: Optional[int] = None) -> EPPipe:
+    """Collective.  `arena_bytes` is per half-batch context."""
+    import os
+    if gemm_sms is None:
+        gemm_sms = int(os.environ.get("M3_EP_GEMM_SMS", "128"))
+    check(load().m3_set_gemm_sm_limit(int(gemm_sms)), "m3_set_gemm_sm_limit")
+    ctxs = [make_context(group, device, arena_bytes, capacity_factor) for _ in range(2)]
+    with torch.cuda.device(device):
+        streams = [torch.cuda.Stream(device=device) for _ in range(2)]
+    return EPPipe(ctxs, streams, group.rank, group.world)
+
+
+def _cv_squared(v: torch.Tensor) -> torch.Tensor:
+    """noisy_gate_vmoe.py:127-141 on a tiny [E] vector (overlapped mode only: the halves' sums are added first)."""
+    if v.numel() == 1:
+        return v.new_zeros(())
+    v = v.float()
+    return v.var() / (v.mean() ** 2 + 1e-10)
+
+
+class EPPipeMoEFunction(torch.autograd.Function):
+    """EPMoEFunction with the token batch processed as two half-batches on two streams (see EPPipe)."""
+
+    @staticmethod
+    def forward(ctx, x, gate_x, w_gate, task_feat, w1, b1, w2, b2, noise, top_k, noise_stddev, compute_dtype,
+                want_gates, wcache, pipe: EPPipe):
+        ctx.set_materialize_grads(False)
+        if gate_x is not None:
+            raise NotImplementedError("overlapped EP: gate_inp must be the layer input")
+        T, D = x.shape
+        E_loc = w1.shape[0]
+        E_tot = w_gate.shape[1]
+        assert E_tot == E_loc * pipe.world
+        x = x.contiguous()
+        cur = torch.cuda.current_stream()
+        if compute_dtype == torch.bfloat16:
+            w1c, w2c, w1t, w2t = wcache.get_bf16(w1, w2)
+        else:
+            w1c, w2c, w1t, w2t = w1, w2, None, None
+        needs_grad = any(ctx.needs_input_grad)
+        T0 = min(T, ((T + 1) // 2 + 15) // 16 * 16)
+        bounds = [(0, T0), (T0, T)]
+        out = torch.empty(T, D, dtype=x.dtype, device=x.device)
+        sts = []
+        ev_push0 = torch.cuda.Event()
+        for h, (a, b) in enumerate(bounds):
+            s, epc = pipe.streams[h], pipe.ctxs[h]
+            s.wait_stream(cur)
+            with torch.cuda.stream(s):
+                xs = x[a:b]
+                nz = noise[a:b].contiguous() if noise is not None else None
+                st = phase_a_gate(xs, w_gate, top_k, task_feat, nz, noise_stddev, want_gates, E_tot)
+                cnt_all = epc.group.all_gather_counts(st.plan_local.counts)
+                if h == 1:
+                    s.wait_event(ev_push0)          # stagger: my push overlaps the other half's GEMM
+                phase_b_dispatch(epc, st, xs, cnt_all, E_loc, top_k, compute_dtype)
+                if h == 0:
+                    ev_push0.record(s)
+                epc.group.barrier(x.device)
+                phase_c_ffn(epc, st, w1c, b1, w2c, b2, needs_grad)
+                epc.group.barrier(x.device)
+                phase_d_combine(epc, st, b - a, D, top_k, x.dtype, keep_rows=needs_grad, out=out[a:b])
+                if not needs_grad:
+                    epc.group.barrier(x.device)
+                    release_fwd(epc, st)
+            sts.append(st)
+        for s in pipe.streams:
+            cur.wait_stream(s)
+        gs, pls = [st.g for st in sts], [st.plan_local for st in sts]
+
+        def cat(ts):
+            t = torch.cat(ts, 0)
+            for u in ts:
+                u.record_stream(cur)
+            return t
+        score, top_vals, clean, idx = (cat([getattr(g, n) for g in gs]) for n in ("score", "top_vals", "clean_logits", "idx"))
+        noisy = clean.view_as(clean) if noise is None else cat([g.noisy_logits for g in gs])
+        gates = cat([g.gates for g in gs]) if gs[0].gates is not None else x.new_empty(0)
+        for p_ in pls:
+            for t in (p_.importance, p_.load, p_.counts):
+                t.record_stream(cur)
+        importance = pls[0].importance + pls[1].importance
+        load_v = pls[0].load + pls[1].load
+        counts = pls[0].counts + pls[1].counts
+        cv_loss = _cv_squared(importance) + _cv_squared(load_v)
+        if needs_grad:
+            ctx.sts, ctx.pipe, ctx.bounds = sts, pipe, bounds
+            ctx.save_for_backward(x, w_gate, task_feat, w1c, w2c, w1t, w2t, importance)
+            ctx.top_k = top_k
+        ctx.mark_non_differentiable(idx, load_v, counts)
+        return out, score, top_vals, clean, noisy, gates, importance, load_v, idx, counts, cv_loss
+
+    @staticmethod
+    def backward(ctx, d_out, d_score, d_top, d_clean, d_noisy, d_gates, d_imp, _dl, _di, _dc, d_cv):
+        x, w_gate, task_feat, w1c, w2c, w1t, w2t, importance = ctx.saved_tensors
+        pipe, sts, bounds, top_k = ctx.pipe, ctx.sts, ctx.bounds, ctx.top_k
+        T, D = x.shape
+        cur = torch.cuda.current_stream()
+        d_out = torch.zeros_like(x) if d_out is None else d_out.contiguous()
+        if d_gates is not None and d_gates.numel() == 0:
+            d_gates = None
+        dx = torch.empty(T, D, dtype=x.dtype, device=x.device)
+        parts = []
+        ev_push0 = torch.cuda.Event()
+
+        def sl(t, a, b):
+            return None if t is None else t[a:b]
+        for h, (a, b) in enumerate(bounds):
+            s, epc, st = pipe.streams[h], pipe.ctxs[h], sts[h]
+            grp = epc.group
+            s.wait_stream(cur)
+            with torch.cuda.stream(s):
+                grp.barrier(x.device)
+                if h == 1:
+                    s.wait_event(ev_push0)
+                bs = phase_e_combine_bwd(epc, st, d_out[a:b], top_k)
+                if h == 0:
+                    ev_push0.record(s)
+                grp.barrier(x.device)
+                phase_f_ffn_bwd(epc, st, bs, w1c, w2c, w1t, w2t)
+                dscore = bs.dscore if d_score is None else bs.dscore + d_score[a:b]
+                dz, dwg, dtf, _ = ops.gate_bwd(x[a:b], w_gate, st.g.noisy_logits, st.g.idx_full, top_k, task_feat, dscore,
+                                               sl(d_top, a, b), sl(d_gates, a, b), d_imp, sl(d_clean, a, b),
+                                               sl(d_noisy, a, b), want_dx_gate=False, importance=importance,
+                                               dcv_loss=d_cv)
+                grp.barrier(x.device)
+                phase_g_dispatch_bwd(epc, st, bs, b - a, D, top_k, dz, w_gate, x.dtype, out=dx[a:b])
+                grp.barrier(x.device)
+                grads = bs.grads
+                release_bwd(epc, st, bs)
+                release_fwd(epc, st)
+            parts.append((dwg, dtf, *grads))
+        for s in pipe.streams:
+            cur.wait_stream(s)
+        for p_ in parts:
+            for t in p_:
+                if t is not None:
+                    t.record_stream(cur)
+        dwg = parts[0][0] + parts[1][0]
+        dtf = None if parts[0][1] is None or task_feat is None else (parts[0][1] + parts[1][1]).view_as(task_feat).to(task_feat.dtype)
+        dw1, db1, dw2, db2 = (parts[0][i] + parts[1][i] for i in (2, 3, 4, 5))
+        ctx.sts = None
+        return dx, None, dwg, dtf, dw1, db1, dw2, db2, None, None, None, None, None, None, None
+
+
 class _EPRunner:
     def __init__(self, ep: EPContext):
         self.ep = ep
 
     def forward(self, layer, gate, x, gx, tf, noise, nstd, cdt):
-        return EPMoEFunction.apply(
+        fn = EPPipeMoEFunction if isinstance(self.ep, EPPipe) else EPMoEFunction
+        return fn.apply(
             x, gx, gate.w_gate, tf, layer.experts.htoh4.weight, layer.experts.htoh4.bias,
             layer.experts.h4toh.weight, layer.experts.h4toh.bias, noise, layer.top_k, nstd, cdt,
             layer.RETURN_SUMMARIES, layer._wcache, self.ep)
 
 
-def attach(layer, ep: EPContext) -> None:
+def attach(layer, ep) -> None:
     """Enable expert parallelism on an FMoETransformerMLP built with world_size = ep.world
     (num_expert = experts per rank, as the reference's get_backbone does)."""
     if layer.world_size != ep.world:
