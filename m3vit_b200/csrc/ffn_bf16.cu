@@ -4,16 +4,18 @@
 // Replaces fmoe's FMoELinear pair (per-expert cuBLAS GEMM loop, reached from
 // /root/reference/models/moe/origin/custom_moe_layer.py:36-44) and its backward.
 //
-//   gg_kernel    C[128-row tile, BN] = A[rows,Kd] * B_e[N,Kd]^T   (both K-major)
-//                persistent CTAs over (m_tile, n_tile); warp 0 = TMA producer, warp 1 =
-//                MMA issuer (one thread) + TMEM owner, warps 2-5 = epilogue
-//                (tcgen05.ld -> bias / GELU / GELU' -> bf16 -> global).  Smem ring of
-//                {A 128x64, B BNx64} stages (SWIZZLE_128B), TMEM accumulator double-buffered
-//                so the epilogue of tile i overlaps the MMAs of tile i+1.
+//   gg_kernel    C[256-row pair tile, BN] = A[rows,Kd] * B_e[N,Kd]^T   (both K-major), one tile per CTA PAIR
+//                (cluster of 2, tcgen05.mma.cta_group::2: each CTA loads its 128 rows of A and half of B).
+//                Persistent pairs over (m_pair_tile, n_tile); warp 0 = TMA producer, warp 1 = MMA issuer
+//                (leader CTA, one thread) + TMEM owner, warps 2-9 = epilogue in two groups that alternate
+//                accumulator buffers (tcgen05.ld -> bias / GELU (+GELU') / x saved GELU' -> bf16 -> private
+//                swizzled smem box -> coalesced 128-byte row segments).  Smem ring of {A 128x64, B (BN/2)x64}
+//                stages (SWIZZLE_128B); TMEM accumulator double-buffered so the epilogue of tile i overlaps
+//                the MMAs of tile i+1.
 //   wgrad_kernel dW_e[M,N] = sum_rows X1[rows,M]^T X2[rows,N]     (both MN-major operands,
 //                read straight from the row-major queues - no transposes in memory)
 //
-// Expert queues are padded to 128 rows (route plan), so every tile is full and the expert
+// Expert queues are padded to M3_PAD_ROWS = 256 rows (route plan), so every tile is full and the expert
 // of a tile is a table lookup; padding rows are zero, so they add nothing to dW.
 #include <cstdio>
 #include <cstdlib>
@@ -385,7 +387,7 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tm1, const __grid_constant__ CU
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const int all_chunks = (p.offsets[e + 1] - p.offsets[e]) / BK;   // queues are padded to 128 rows
+  const int all_chunks = (p.offsets[e + 1] - p.offsets[e]) / BK;   // queues are padded to M3_PAD_ROWS (a multiple of BK)
   const int per_split = (all_chunks + nsplit - 1) / nsplit;
   const int c_begin = min(split * per_split, all_chunks), c_end = min(c_begin + per_split, all_chunks);
   const int r0 = p.offsets[e] + c_begin * BK;

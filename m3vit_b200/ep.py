@@ -9,12 +9,15 @@ world_size > 1) is replaced by peer-mapped expert queues:
 
   * every rank owns one CUDA-IPC "arena"; all ranks sub-allocate it in lockstep, so a
     queue lives at the same offset on every rank and `base[p] + offset` is rank p's queue;
-  * forward : all-gather of the [E_tot] count vector (tiny, NCCL, stream-ordered, NO host
-    read-back) -> m3_ep_plan (every slot's owner rank + row) -> the dispatch kernel STORES
-    token rows straight into the owners' queues over NVLink -> barrier -> grouped expert FFN
-    on the local queue -> barrier -> the combine kernel LOADS result rows from the owners;
-  * backward: the same movers mirrored (combine_bwd pushes dyq, dispatch_bwd pulls dxq).
+  * forward : all-gather of the [E_tot] count vector by OUR 1-warp kernel over peer memory
+    (m3_ep_barrier; stream-ordered, NO host read-back, no NCCL on the data path) -> m3_ep_plan
+    (every slot's owner rank + row) -> the dispatch kernel STORES token rows straight into the
+    owners' queues over NVLink -> barrier -> grouped expert FFN on the local queue -> barrier ->
+    the combine kernel LOADS result rows from the owners (and keeps a local copy for backward);
+  * backward: combine_bwd pushes dyq (dscore from the local copy), dispatch_bwd pulls dxq.
     Expert weight gradients need no reduction (each expert's rows are all on its owner).
+  * make_pipelined_context / EPPipeMoEFunction (opt-in): two half-batches on two streams so
+    that the movers of one half overlap the GEMMs of the other.
 
 The protocol is written as explicit phases so that it runs either over torch.distributed
 (one process per GPU, NCCL) or as a single-process multi-rank simulation (tests; one GPU
