@@ -250,3 +250,39 @@ def test_layer_is_cuda_graph_capturable():
         torch.cuda.synchronize()
         assert torch.equal(out, want_out)
         torch.testing.assert_close(x.grad, want_dx, rtol=0, atol=0)
+
+
+def test_layer_under_make_graphed_callables_is_bit_identical():
+    """Small batches are launch-bound (reference config C1: B = 2): torch.cuda.make_graphed_callables captures the
+    layer's forward AND backward (tools/graphed_c1.py: 579 -> 207 us per fwd+bwd call at T = 2402).  The graphed
+    module must reproduce the eager results bit for bit, including the balance-loss gradient."""
+    dev = torch.device("cuda:0")
+    fx, case, data = load_fixture("S1_e16k4_g2_s0.pt")
+
+    class TaskCall(nn.Module):
+        def __init__(self, layer, task):
+            super().__init__()
+            self.layer, self.task = layer, task
+
+        def forward(self, x):
+            return self.layer(x, task_id=self.task), self.layer.gate[self.task].get_loss()
+
+    layer = build_layer(case, data, "origin", dev, compute_dtype=torch.bfloat16).train()
+    go = data["grad_out"].to(dev)
+    w = torch.tensor(0.01, device=dev)
+
+    def step(mod, x):
+        layer.zero_grad(set_to_none=True)
+        out, loss = mod(x)
+        torch.autograd.backward([out, loss], [go, w])
+        return out.detach().clone(), x.grad.clone(), layer.gate[1].w_gate.grad.clone(), layer.experts.h4toh.weight.grad.clone()
+
+    xe = data["x"].to(dev).requires_grad_(True)
+    want = step(TaskCall(layer, 1), xe)
+    graphed = torch.cuda.make_graphed_callables(TaskCall(layer, 1), (data["x"].to(dev).requires_grad_(True),),
+                                                allow_unused_input=True)      # gate[0] gets no gradient
+    for _ in range(2):                                                         # replay twice: static buffers are reused
+        xg = data["x"].to(dev).requires_grad_(True)
+        got = step(graphed, xg)
+        for a, b in zip(got, want):
+            assert torch.equal(a, b)
