@@ -259,7 +259,15 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    def zero_grads():
+        # what optimizer.zero_grad(set_to_none=True) does at the top of every training step: the first task pass
+        # then installs its gradients, the second one accumulates into them
+        for l in layers:
+            for p_ in l.parameters():
+                p_.grad = None
+
     def step_resident():
+        zero_grads()
         for i, (li, t) in enumerate(calls):
             xs[i].grad = None
             one_call(layers[li], xs[i], gs[i & 1], t)
@@ -323,6 +331,7 @@ def main():
             ev_ready[b].record(copy_stream)
 
     def step_e2e():
+        zero_grads()
         cur = torch.cuda.current_stream()
         for b in range(2):
             ev_free[b].record(cur)
@@ -338,7 +347,7 @@ def main():
         hloss.copy_(dloss, non_blocking=True)
         cur.synchronize()
 
-    e2e_steps = max(2, min(args.steps, 5))
+    e2e_steps = max(2, min(args.steps, 10))
     step_e2e()
     barrier()
     e0.record()

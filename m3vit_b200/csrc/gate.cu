@@ -398,8 +398,10 @@ gate_bwd_dz_kernel(const float* __restrict__ logits, const int32_t* __restrict__
 }
 
 // partial dW[chunk][d][e] = sum_{t in chunk} x[t,d] * dz[t,e]; thread tile 4 d x EW experts.
+constexpr int kDwSub = 128;   // tokens of dz staged in shared memory per pass
+
 template <int EW, typename XT, bool LN, int TB>
-__global__ void __launch_bounds__(TB == 8 ? 384 : TB == 4 ? 512 : 1024)
+__global__ void __launch_bounds__(TB == 16 ? 384 : TB == 8 ? 512 : 1024)
 gate_bwd_dw_kernel(const XT* __restrict__ x, int64_t ldx, const float* __restrict__ dz, int T,
                                    int D, int E, int tok_per_chunk, float* __restrict__ part,
                                    float* __restrict__ cs_part, const float* __restrict__ ln_mean,
@@ -425,46 +427,65 @@ gate_bwd_dw_kernel(const XT* __restrict__ x, int64_t ldx, const float* __restric
 #pragma unroll
     for (int i = 0; i < 4; ++i) { lg[i] = __ldg(ln_gamma + dq * 4 + i); lb[i] = __ldg(ln_beta + dq * 4 + i); }
   }
-  // Tokens are processed in batches of TB with ALL loads of a batch issued before the first FMA
-  // (a plain `#pragma unroll` leaves one token's loads in flight per thread: latency-bound).  The
-  // batch tail re-reads the last token with its dz zeroed, so the summation order stays t-ascending.
-  for (int tb = t0; tb < t1; tb += TB) {
-    float xv[TB][4], dv[TB][EW], mu[TB], rs[TB];
-#pragma unroll
-    for (int u = 0; u < TB; ++u) {
-      const int t = min(tb + u, t1 - 1);
-      if constexpr (sizeof(XT) == 4) {
-        float4 v = __ldg(reinterpret_cast<const float4*>(x + (int64_t)t * ldx + dq * 4));
-        xv[u][0] = v.x; xv[u][1] = v.y; xv[u][2] = v.z; xv[u][3] = v.w;
-      } else {
-        uint2 w = __ldg(reinterpret_cast<const uint2*>(x + (int64_t)t * ldx + dq * 4));
-        float2 a = bf16x2_to_float2(w.x), b = bf16x2_to_float2(w.y);
-        xv[u][0] = a.x; xv[u][1] = a.y; xv[u][2] = b.x; xv[u][3] = b.y;
-      }
-#pragma unroll
-      for (int c = 0; c < EW; c += 4) {
-        float4 v = __ldg(reinterpret_cast<const float4*>(dz + (int64_t)t * E + e0 + c));
-        dv[u][c] = v.x; dv[u][c + 1] = v.y; dv[u][c + 2] = v.z; dv[u][c + 3] = v.w;
-      }
-      if constexpr (LN) { mu[u] = __ldg(ln_mean + t); rs[u] = __ldg(ln_rstd + t); }
+  // dz (and the LayerNorm statistics) of kDwSub tokens are staged in shared memory once per CTA pass: every thread of
+  // an expert group reads the same values, and keeping them out of the register file leaves room for TB tokens of x in
+  // flight per thread (the kernel is bound by the latency of those loads, not by bandwidth or FMAs).
+  __shared__ __align__(16) float dzs[kDwSub * 16];
+  __shared__ float lns[LN ? 2 * kDwSub : 2];
+  const int EB = EW * ngrp;                           // experts handled by this CTA (<= 16)
+  const int eb0 = blockIdx.y * EB;
+  for (int ts = t0; ts < t1; ts += kDwSub) {
+    const int n = min(kDwSub, t1 - ts);
+    __syncthreads();                                  // the previous pass has been consumed
+    for (int i = threadIdx.x; i < n * (EB / 4); i += blockDim.x) {
+      const int tok = i / (EB / 4), q = i % (EB / 4);
+      *reinterpret_cast<float4*>(dzs + tok * 16 + q * 4) =
+          __ldg(reinterpret_cast<const float4*>(dz + (int64_t)(ts + tok) * E + eb0 + q * 4));
     }
-#pragma unroll
-    for (int u = 0; u < TB; ++u) {
-      if (tb + u >= t1) {
-#pragma unroll
-        for (int c = 0; c < EW; ++c) dv[u][c] = 0.f;
+    if constexpr (LN) {
+      for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        lns[2 * i] = __ldg(ln_mean + ts + i);
+        lns[2 * i + 1] = __ldg(ln_rstd + ts + i);
       }
-      if constexpr (LN) {
+    }
+    __syncthreads();
+    for (int tb = 0; tb < n; tb += TB) {
+      float xv[TB][4];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) xv[u][i] = fmaf((xv[u][i] - mu[u]) * rs[u], lg[i], lb[i]);
+      for (int u = 0; u < TB; ++u) {                  // all loads of the batch first
+        const int t = ts + min(tb + u, n - 1);
+        if constexpr (sizeof(XT) == 4) {
+          float4 v = __ldg(reinterpret_cast<const float4*>(x + (int64_t)t * ldx + dq * 4));
+          xv[u][0] = v.x; xv[u][1] = v.y; xv[u][2] = v.z; xv[u][3] = v.w;
+        } else {
+          uint2 w = __ldg(reinterpret_cast<const uint2*>(x + (int64_t)t * ldx + dq * 4));
+          float2 a = bf16x2_to_float2(w.x), b = bf16x2_to_float2(w.y);
+          xv[u][0] = a.x; xv[u][1] = a.y; xv[u][2] = b.x; xv[u][3] = b.y;
+        }
       }
 #pragma unroll
-      for (int i = 0; i < 4; ++i)
+      for (int u = 0; u < TB; ++u) {                  // t ascending: deterministic summation order
+        if (tb + u < n) {
+          float dv[EW];
 #pragma unroll
-        for (int c = 0; c < EW; ++c) acc[i][c] = fmaf(xv[u][i], dv[u][c], acc[i][c]);
-      if (dq == 0) {
+          for (int c = 0; c < EW; c += 4) {
+            const float4 v = *reinterpret_cast<const float4*>(dzs + (tb + u) * 16 + eh * EW + c);
+            dv[c] = v.x; dv[c + 1] = v.y; dv[c + 2] = v.z; dv[c + 3] = v.w;
+          }
+          if constexpr (LN) {
+            const float mu = lns[2 * (tb + u)], rs = lns[2 * (tb + u) + 1];
 #pragma unroll
-        for (int c = 0; c < EW; ++c) cs[c] += dv[u][c];
+            for (int i = 0; i < 4; ++i) xv[u][i] = fmaf((xv[u][i] - mu) * rs, lg[i], lb[i]);
+          }
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int c = 0; c < EW; ++c) acc[i][c] = fmaf(xv[u][i], dv[c], acc[i][c]);
+          if (dq == 0) {
+#pragma unroll
+            for (int c = 0; c < EW; ++c) cs[c] += dv[c];
+          }
+        }
       }
     }
   }
@@ -694,9 +715,9 @@ static int gate_bwd_impl(const void* x, int x_dtype, int64_t ldx, const float* t
     // token batch (loads in flight per thread) limited by the register file at large CTAs
 #define M3_DW_LAUNCH(EWV, XT, LNV)                                                                                   \
   do {                                                                                                              \
-    if (threads <= 384) gate_bwd_dw_kernel<EWV, XT, LNV, 8><<<grid, threads, 0, st>>>(M3_DW_ARGS(XT));             \
-    else if (threads <= 512) gate_bwd_dw_kernel<EWV, XT, LNV, 4><<<grid, threads, 0, st>>>(M3_DW_ARGS(XT));        \
-    else gate_bwd_dw_kernel<EWV, XT, LNV, 2><<<grid, threads, 0, st>>>(M3_DW_ARGS(XT));                            \
+    if (threads <= 384) gate_bwd_dw_kernel<EWV, XT, LNV, 16><<<grid, threads, 0, st>>>(M3_DW_ARGS(XT));            \
+    else if (threads <= 512) gate_bwd_dw_kernel<EWV, XT, LNV, 8><<<grid, threads, 0, st>>>(M3_DW_ARGS(XT));        \
+    else gate_bwd_dw_kernel<EWV, XT, LNV, 4><<<grid, threads, 0, st>>>(M3_DW_ARGS(XT));                            \
   } while (0)
     if (ln_mean != nullptr) {
       if (EW == 8) M3_DW_LAUNCH(8, float, true); else M3_DW_LAUNCH(4, float, true);

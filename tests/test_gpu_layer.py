@@ -257,7 +257,7 @@ def test_layer_under_make_graphed_callables_is_bit_identical():
     layer's forward AND backward (tools/graphed_c1.py: 579 -> 207 us per fwd+bwd call at T = 2402).  The graphed
     module must reproduce the eager results bit for bit, including the balance-loss gradient."""
     dev = torch.device("cuda:0")
-    fx, case, data = load_fixture("S1_e16k4_g2_s0.pt")
+    fx, case, data = load_fixture("S8_d128h256_g2_s0.pt")      # bf16 tensor-core path needs D, H multiples of 128
 
     class TaskCall(nn.Module):
         def __init__(self, layer, task):
