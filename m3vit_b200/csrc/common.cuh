@@ -267,36 +267,40 @@ __device__ __forceinline__ f32x2 gelu_fast2(f32x2 v) {
   return mul2(mul2(v, M3_K2(0.5f)), add2(e, M3_K2(1.0f)));
 }
 // returns gelu'(x) for a pair; *g = gelu(x).
-// Both need Phi(x) = (1 + erf(x/sqrt2))/2 AND exp(-x^2/2), so erf comes from Abramowitz-Stegun 7.1.26
+// Both need Phi(x) = (1 + erf(x/sqrt2))/2 AND pdf(x) = exp(-x^2/2)/sqrt(2 pi), so erf comes from Abramowitz-Stegun 7.1.26
 //   erf(u) = 1 - (a1 t + .. + a5 t^5) exp(-u^2),  t = 1/(1 + p u),  u = |x|/sqrt2  (|err| <= 1.5e-7)
-// whose exponential IS the pdf's: one ex2 + one rcp per element, no clamps (exp underflows to the
-// saturated values).  |gelu err| <= 5e-7, |gelu' err| <= 4e-7 against fp64.
+// whose exponential IS the pdf's: one ex2 + one rcp per element, no clamps (exp underflows to the saturated values).
+// Constant folding: the ex2 argument carries log2(1/sqrt(2 pi)) so that ex2 returns the pdf itself, and the
+// coefficients carry -sqrt(2 pi)/2, so that  |Phi(x) - 1/2| = 1/2 + poly(t) * t * pdf  is one FMA.
+// |gelu err| <= 5e-7, |gelu' err| <= 4e-7 against fp64.
+#define M3_GELU_A5 (-1.3302744296f)
+#define M3_GELU_A4 (1.8212559791f)
+#define M3_GELU_A3 (-1.7814779366f)
+#define M3_GELU_A2 (0.3565637812f)
+#define M3_GELU_A1 (-0.3193815303f)
+#define M3_GELU_TK (0.3275911f * 0.70710678118654752440f)
+#define M3_GELU_EC (-0.7213475204444817f)      /* -0.5 * log2(e) */
+#define M3_GELU_EL (-1.3257480647361592f)      /* log2(1 / sqrt(2 pi)) */
 __device__ __forceinline__ f32x2 gelu_fast_grad2(f32x2 x, f32x2* g) {
   float x0, x1;
   unpk2(x, x0, x1);
-  const f32x2 ax = pk2(fabsf(x0), fabsf(x1));
   float d0, d1;
-  unpk2(fma2(ax, M3_K2(0.3275911f * 0.70710678118654752440f), M3_K2(1.0f)), d0, d1);
+  unpk2(fma2(pk2(fabsf(x0), fabsf(x1)), M3_K2(M3_GELU_TK), M3_K2(1.0f)), d0, d1);
   const f32x2 t = pk2(rcp_approx(d0), rcp_approx(d1));
   float a0, a1;
-  unpk2(mul2(mul2(x, x), M3_K2(-0.5f * 1.4426950408889634f)), a0, a1);   // -x^2/2 * log2(e)
-  const f32x2 e = pk2(ex2_approx(a0), ex2_approx(a1));
-  f32x2 p = M3_K2(1.061405429f);
-  p = fma2(p, t, M3_K2(-1.453152027f));
-  p = fma2(p, t, M3_K2(1.421413741f));
-  p = fma2(p, t, M3_K2(-0.284496736f));
-  p = fma2(p, t, M3_K2(0.254829592f));
-  p = mul2(mul2(p, t), e);                                              // 1 - erf(|x|/sqrt2)
+  unpk2(fma2(mul2(x, x), M3_K2(M3_GELU_EC), M3_K2(M3_GELU_EL)), a0, a1);
+  const f32x2 pdf = pk2(ex2_approx(a0), ex2_approx(a1));
+  f32x2 p = fma2(M3_K2(M3_GELU_A5), t, M3_K2(M3_GELU_A4));
+  p = fma2(p, t, M3_K2(M3_GELU_A3));
+  p = fma2(p, t, M3_K2(M3_GELU_A2));
+  p = fma2(p, t, M3_K2(M3_GELU_A1));
   float q0, q1;
-  unpk2(fma2(p, M3_K2(-0.5f), M3_K2(0.5f)), q0, q1);                    // |Phi(x) - 1/2|
+  unpk2(fma2(mul2(p, t), pdf, M3_K2(0.5f)), q0, q1);                    // |Phi(x) - 1/2|
   const f32x2 cdf = add2(pk2(copysignf(q0, x0), copysignf(q1, x1)), M3_K2(0.5f));
   *g = mul2(x, cdf);
-  return fma2(x, mul2(e, M3_K2(0.39894228040143267794f)), cdf);
+  return fma2(x, pdf, cdf);
 }
 
-// The same for NP independent pairs, written stage by stage: every stage is NP independent instructions,
-// so the dependent chains (rcp -> 5-deep Horner -> exp product) of different pairs overlap instead of
-// being issued back to back (the GEMM epilogues run on 2 warps per scheduler: ILP is all they have).
 // volatile variants: ptxas keeps volatile asm statements in program order, which is how the stage-by-stage
 // order below survives into SASS (left alone, its scheduler re-serialises each pair's dependent chain).
 __device__ __forceinline__ f32x2 fma2v(f32x2 a, f32x2 b, f32x2 c) {
@@ -326,27 +330,25 @@ __device__ __forceinline__ void gelu_fast_grad2_batch(const f32x2* x, f32x2* g, 
   for (int i = 0; i < NP; ++i) {
     float x0, x1, d0, d1;
     unpk2(x[i], x0, x1);
-    unpk2(fma2(pk2(fabsf(x0), fabsf(x1)), M3_K2(0.3275911f * 0.70710678118654752440f), M3_K2(1.0f)), d0, d1);
+    unpk2(fma2(pk2(fabsf(x0), fabsf(x1)), M3_K2(M3_GELU_TK), M3_K2(1.0f)), d0, d1);
     t[i] = pk2(rcp_approx_v(d0), rcp_approx_v(d1));
   }
 #pragma unroll
   for (int i = 0; i < NP; ++i) {
     float a0, a1;
-    unpk2(mul2(mul2(x[i], x[i]), M3_K2(-0.5f * 1.4426950408889634f)), a0, a1);
-    e[i] = pk2(ex2_approx_v(a0), ex2_approx_v(a1));
+    unpk2(fma2(mul2(x[i], x[i]), M3_K2(M3_GELU_EC), M3_K2(M3_GELU_EL)), a0, a1);
+    e[i] = pk2(ex2_approx_v(a0), ex2_approx_v(a1));                       // the pdf itself
   }
 #pragma unroll
-  for (int i = 0; i < NP; ++i) p[i] = fma2v(M3_K2(1.061405429f), t[i], M3_K2(-1.453152027f));
+  for (int i = 0; i < NP; ++i) p[i] = fma2v(M3_K2(M3_GELU_A5), t[i], M3_K2(M3_GELU_A4));
 #pragma unroll
-  for (int i = 0; i < NP; ++i) p[i] = fma2v(p[i], t[i], M3_K2(1.421413741f));
+  for (int i = 0; i < NP; ++i) p[i] = fma2v(p[i], t[i], M3_K2(M3_GELU_A3));
 #pragma unroll
-  for (int i = 0; i < NP; ++i) p[i] = fma2v(p[i], t[i], M3_K2(-0.284496736f));
+  for (int i = 0; i < NP; ++i) p[i] = fma2v(p[i], t[i], M3_K2(M3_GELU_A2));
 #pragma unroll
-  for (int i = 0; i < NP; ++i) p[i] = fma2v(p[i], t[i], M3_K2(0.254829592f));
+  for (int i = 0; i < NP; ++i) p[i] = fma2v(p[i], t[i], M3_K2(M3_GELU_A1));
 #pragma unroll
-  for (int i = 0; i < NP; ++i) p[i] = mul2v(p[i], t[i]);
-#pragma unroll
-  for (int i = 0; i < NP; ++i) p[i] = fma2(mul2(p[i], e[i]), M3_K2(-0.5f), M3_K2(0.5f));   // |Phi(x) - 1/2|
+  for (int i = 0; i < NP; ++i) p[i] = fma2(mul2v(p[i], t[i]), e[i], M3_K2(0.5f));    // |Phi(x) - 1/2|
 #pragma unroll
   for (int i = 0; i < NP; ++i) {
     float x0, x1, q0, q1;
@@ -354,7 +356,7 @@ __device__ __forceinline__ void gelu_fast_grad2_batch(const f32x2* x, f32x2* g, 
     unpk2(p[i], q0, q1);
     const f32x2 cdf = add2(pk2(copysignf(q0, x0), copysignf(q1, x1)), M3_K2(0.5f));
     g[i] = mul2(x[i], cdf);
-    gr[i] = fma2(x[i], mul2(e[i], M3_K2(0.39894228040143267794f)), cdf);
+    gr[i] = fma2(x[i], e[i], cdf);
   }
 }
 
