@@ -162,6 +162,22 @@ size_t m3_ffn_saved_bytes(int dtype, int cap_rows, int H);
 /* Process-wide tuning knob: SMs the persistent tcgen05 GEMMs may occupy (default / out of range: all 148).
  * The overlapped expert-parallel mode lowers it so that NVLink row movers run beside a GEMM. */
 int m3_set_gemm_sm_limit(int sms);
+/* Process-wide tuning knobs (A/B measurement; defaults are the shipped configuration).
+ *   M3_KNOB_PDL       1: kernels are launched with programmatic stream serialisation and start their
+ *                     prologue (barrier init, TMEM allocation, descriptor prefetch) under the tail of the
+ *                     previous kernel; every kernel executes griddepcontrol.wait before its first global access.
+ *                     0 (default): plain stream-ordered launches (at bench size the kernels are 30-100 us long and
+ *                     PDL measured no gain; it is meant for the launch-bound small-batch regime).
+ *   M3_KNOB_EPI_WARPS 8 or 16 epilogue warps in the tcgen05 grouped GEMM (0 = per-epilogue default;
+ *                     0x100 | mask: bit e of mask set -> 16 warps for epilogue e = 0 store, 1 bias, 2 fc1, 3 dgelu).
+ *   M3_KNOB_GATE_CFG  0 (default: chosen from T) or 1..4 = force gate_fwd tile configuration 0..3.
+ *   M3_KNOB_DEBUG     measurement only (results are garbage): tcgen05 GEMMs run 1 = without MMAs, 2 = without TMA loads.
+ *   M3_KNOB_TRACE_KERNEL  1 + index of the GEMM launch inside one m3_ffn_fwd / m3_ffn_bwd call that m3_debug_trace_buffer
+ *                     records (0 = every launch).
+ *   M3_KNOB_MOVER_VARIANT  0 (default) or an experimental rows-in-flight / occupancy variant of combine fwd/bwd.
+ * Returns the previous value, or M3_ERR_ARG for an unknown knob. */
+typedef enum { M3_KNOB_PDL = 0, M3_KNOB_EPI_WARPS = 1, M3_KNOB_MOVER_VARIANT = 2, M3_KNOB_GATE_CFG = 3, M3_KNOB_DEBUG = 4, M3_KNOB_TRACE_KERNEL = 5, M3_KNOB_COUNT_ = 8 } m3_knob;
+int m3_set_knob(int knob, int value);
 int m3_ffn_fwd(int dtype, const void* xq, const int32_t* offsets, const int32_t* tile_expert,
                int cap_rows, int E, int D, int H, const void* w1, const float* b1, const void* w2,
                const float* b2, void* saved, void* yq, void* workspace, size_t workspace_bytes,
@@ -276,6 +292,11 @@ int m3_debug_occupy(int n_ctas, long long cycles, int* sink, m3_stream_t stream)
 /* Debug only: clock64 timeline of CTA 0 of the fused FFN kernel (enable, then call again with a host
  * buffer of 2*max_events uint64 to fetch {tag, clock} pairs).  Synchronises the device. */
 int m3_debug_trace(int enable, unsigned long long* host_out, int max_events);
+
+/* Debug only: clock64 timeline of CTA 0 of the tensor-core GEMM kernels (producer / MMA / one epilogue warp), appended
+ * to a caller-owned DEVICE buffer of 4 + 6*max_events uint64 (buf[r] = event count of role r = 0 producer / 1 MMA /
+ * 2 epilogue warp 0, whose {tag, clock} pairs start at buf[4 + 2*r*max_events]; zero it first); NULL = off. */
+int m3_debug_trace_buffer(unsigned long long* dev_buf, int max_events);
 
 /* CUDA IPC plumbing for the peer queues (host pointers in/out; 64-byte handles). */
 int m3_ipc_alloc(size_t bytes, void** dev_ptr, void* handle64);

@@ -43,6 +43,7 @@ SIGNATURES = {
     "m3_ffn_workspace_bytes": (_sz, [_i, _i, _i, _i, _i, _i]),
     "m3_ffn_saved_bytes": (_sz, [_i, _i, _i]),
     "m3_set_gemm_sm_limit": (_i, [_i]),
+    "m3_set_knob": (_i, [_i, _i]),
     "m3_ffn_fwd": (_i, [_i, _p, _p, _p, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _sz, _p]),
     "m3_ffn_bwd": (_i, [_i, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _sz, _p]),
     "m3_cast_weights_bf16": (_i, [_p, _i, _i, _i, _p, _p, _p]),
@@ -64,6 +65,7 @@ SIGNATURES = {
     "m3_ln_bwd_workspace_bytes": (_sz, [_i, _i]),
     "m3_ln_bwd_res": (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _p, _p, _p, _p, _sz, _p]),
     "m3_debug_trace": (_i, [_i, _p, _i]),
+    "m3_debug_trace_buffer": (_i, [_p, _i]),
     "m3_debug_occupy": (_i, [_i, C.c_longlong, _p, _p]),
     "m3_ipc_alloc": (_i, [_sz, C.POINTER(_p), _p]),
     "m3_ipc_open": (_i, [_p, C.POINTER(_p)]),
@@ -94,6 +96,11 @@ def load() -> C.CDLL:
         fn.argtypes = args
     if lib.m3_abi_version() != 1:
         raise M3Error("libm3vit_moe.so ABI version mismatch")
+    # tuning knobs from the environment, e.g. M3_KNOBS="0=1,3=2" (m3_set_knob(knob, value); include/m3vit_moe.h)
+    for kv in filter(None, os.environ.get("M3_KNOBS", "").split(",")):
+        k, v = kv.split("=")
+        if lib.m3_set_knob(int(k), int(v, 0)) < 0:
+            raise M3Error(f"M3_KNOBS: unknown knob {k}")
     _lib = lib
     return lib
 

@@ -58,6 +58,27 @@ extern "C" size_t m3_ffn_workspace_bytes(int dtype, int cap_rows, int D, int H, 
 
 extern "C" int m3_set_gemm_sm_limit(int sms) { return m3_ffn_bf16_set_sm_limit(sms); }
 
+namespace m3 {
+int g_knobs[M3_KNOB_COUNT_] = {/*PDL*/ 0, /*EPI_WARPS*/ 0, /*MOVER_VARIANT*/ 0, /*GATE_CFG*/ 0, /*DEBUG*/ 0};
+}
+namespace m3 { namespace tc {
+unsigned long long* g_trace_buf = nullptr;
+int g_trace_cap = 0;
+} }
+// Debug only: device buffer of 4 + 6*max_events uint64 filled by CTA 0 of the tensor-core GEMM kernels while set
+// (layout: include/m3vit_moe.h); NULL switches tracing off.
+extern "C" int m3_debug_trace_buffer(unsigned long long* dev_buf, int max_events) {
+  m3::tc::g_trace_buf = dev_buf;
+  m3::tc::g_trace_cap = dev_buf ? max_events : 0;
+  return M3_OK;
+}
+extern "C" int m3_set_knob(int knob, int value) {
+  if (knob < 0 || knob >= M3_KNOB_COUNT_) return M3_ERR_ARG;
+  const int old = m3::g_knobs[knob];
+  m3::g_knobs[knob] = value;
+  return old;
+}
+
 extern "C" size_t m3_ffn_saved_bytes(int dtype, int cap_rows, int H) {
   if (cap_rows < 0 || H <= 0) return 0;
   if (dtype == M3_BF16) return m3_ffn_bf16_saved_bytes(cap_rows, H);

@@ -32,6 +32,33 @@ namespace m3 {
 
 constexpr int kNumSMs = 148;  // B200
 
+// ---- programmatic dependent launch (PDL) ------------------------------------
+// Every kernel of the path calls pdl_wait() before its first global-memory access (reads of a predecessor's
+// output AND writes a predecessor might still read) and pdl_trigger() right away, so that the next kernel's
+// CTAs are scheduled as this kernel's last CTAs drain and run their prologue (smem carve-up, mbarrier init,
+// TMEM allocation, tensor-map prefetch) under this kernel's tail.  Both are no-ops for a plain launch.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+extern int g_knobs[M3_KNOB_COUNT_];   // abi.cu (m3_set_knob)
+
+// kern<<<grid, block, smem, st>>>(args...) with the programmatic-stream-serialisation attribute (M3_KNOB_PDL)
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                                   Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = g_knobs[M3_KNOB_PDL] ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -30,8 +30,10 @@ constexpr int BM = 128;  // UMMA M (cta_group::1): accumulator row i <-> TMEM la
 constexpr int BK = 64;   // 64 bf16 = 128 B = one swizzle-128B row
 constexpr int UMMA_K = 16;
 constexpr int kThreads = 192;        // wgrad kernel: 2 + 4 warps
-constexpr int kEpiWarps = 8;          // gg kernel: two warps per TMEM lane quarter
-constexpr int kGGThreads = 64 + kEpiWarps * 32;
+// gg kernel epilogue warps: EW = 8 (one warp per TMEM lane quarter and accumulator buffer, 64-column register
+// blocks) or EW = 16 (two warps per quarter and buffer, interleaved 32-column blocks: twice the warps to hide
+// the dependent erf/exp chains of the GELU epilogues behind, at half the registers per thread)
+constexpr int gg_threads(int EW) { return 64 + EW * 32; }
 constexpr int BOX_BYTES = BM * 64 * 2;  // one [128 rows][64 bf16] swizzle-128B box = 16 KB
 
 enum { EPI_STORE = 0, EPI_BIAS = 1, EPI_FC1 = 2, EPI_DGELU = 3 };
@@ -44,12 +46,15 @@ struct GGParams {
   int save_out2;               // EPI_FC1: also store gelu'(pre-activation) for the backward pass (training)
   __nv_bfloat16* out;          // [rows][N]
   __nv_bfloat16* out2;         // EPI_FC1: gelu'(pre-activation)
+  int dbg;                     // M3_KNOB_DEBUG (measurement only, results are garbage): 1 = no MMAs, 2 = no TMA loads
+  unsigned long long* trace;   // m3_debug_trace_buffer
+  int trace_cap;
 };
 
-constexpr int WBOX_BYTES = 32 * 64 * 2;  // one warp's [32 rows][64 bf16] swizzle-128B box = 4 KB
-
-template <int BN, int EPI, int NCTA>
+template <int BN, int EPI, int NCTA, int EW>
 struct GGCfg {
+  static constexpr int CW = EW == 16 ? 32 : 64;               // columns per epilogue register block
+  static constexpr int WBOX_BYTES = 32 * CW * 2;              // one warp's [32 rows][CW bf16] swizzled box (4 / 2 KB)
   static constexpr int A_BYTES = BM * BK * 2;
   static constexpr int B_BYTES = (BN / NCTA) * BK * 2;      // a CTA pair splits the B tile
   static constexpr int STAGE = A_BYTES + B_BYTES;
@@ -57,7 +62,7 @@ struct GGCfg {
   static constexpr int N_OUT = 1;                            // outputs share one transpose box, flushed in turn
   static constexpr int N_AUX = (EPI == EPI_DGELU) ? 1 : 0;   // EPI_DGELU: gelu'(pre-activation) saved by fc1
   static constexpr int WARP_STAGING = (N_OUT + N_AUX) * WBOX_BYTES;
-  static constexpr int STAGING = kEpiWarps * WARP_STAGING;
+  static constexpr int STAGING = EW * WARP_STAGING;
   static constexpr int BUDGET = 227 * 1024 - 1024 - 512 - STAGING;
   static constexpr int STAGES = (BUDGET / STAGE) < 6 ? (BUDGET / STAGE) : 6;
   static constexpr int TMEM_COLS = (2 * BN <= 256) ? 256 : 512;
@@ -74,20 +79,31 @@ __device__ __forceinline__ f32x2 unpack_bf16x2(uint32_t u) {
   const float2 f = bf16x2_to_float2(u);
   return pk2(f.x, f.y);
 }
-// 16-byte chunk c (0..7) of row r inside a [rows][64 bf16] swizzle-128B box (what TMA reads / writes)
-__device__ __forceinline__ uint32_t box_off(int r, int c) { return (uint32_t)r * 128u + (uint32_t)((c ^ (r & 7)) << 4); }
+// 16-byte chunk c of row r inside a [rows][CW bf16] box as TMA lays it out: CW = 64 -> 128-byte rows, SWIZZLE_128B
+// (chunk ^= row & 7); CW = 32 -> 64-byte rows, SWIZZLE_64B (chunk ^= (row >> 1) & 3).  Conflict-free for the
+// row-per-lane writes and for the row-segment reads of the flush alike.
+template <int CW>
+__device__ __forceinline__ uint32_t box_off(int r, int c) {
+  if (CW == 64) return (uint32_t)r * 128u + (uint32_t)((c ^ (r & 7)) << 4);
+  return (uint32_t)r * 64u + (uint32_t)((c ^ ((r >> 1) & 3)) << 4);
+}
 
-template <int BN, int EPI, int NCTA>
-__global__ void __launch_bounds__(kGGThreads, 1)
+template <int BN, int EPI, int NCTA, int EW>
+__global__ void __launch_bounds__(gg_threads(EW), 1)
 gg_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
           const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmOut2,
           const __grid_constant__ CUtensorMap tmAux, GGParams p) {
-  using Cfg = GGCfg<BN, EPI, NCTA>;
+  using Cfg = GGCfg<BN, EPI, NCTA, EW>;
+  constexpr int kEpiWarps = EW;
+  constexpr int CW = Cfg::CW, WBOX_BYTES = Cfg::WBOX_BYTES;
+  constexpr int NQ = EW / 8;            // warps sharing one (TMEM lane quarter, accumulator buffer)
+  constexpr int NCH = CW / 8;           // 16-byte chunks per box row
   // NCTA == 2: CTA pair (cluster of 2) sharing one 256 x BN MMA tile, see tc_common.cuh
   const uint32_t cta_rank = NCTA == 2 ? cluster_ctarank() : 0u;
   const bool leader_cta = cta_rank == 0;
   constexpr int STAGES = Cfg::STAGES;
-  constexpr int NB = BN / 64;  // 64-column boxes per tile
+  constexpr int NBW = BN / CW / NQ;  // CW-column blocks of a tile handled by one epilogue warp
+  static_assert(BN % (CW * NQ) == 0, "tile width vs epilogue blocks");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* stg = smem + STAGES * Cfg::STAGE;                 // staging boxes (1024-aligned)
@@ -106,7 +122,7 @@ gg_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
   if (warp == 1) {
     if (lane == 0) {
       for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], NCTA); mbar_init(&empty[s], 1); }
-      for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], NCTA * 4 * 32); }
+      for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], NCTA * (EW / 2) * 32); }
       for (int w = 0; w < kEpiWarps; ++w) mbar_init(&aux_full[w], 1);
       fence_barrier_init();
     }
@@ -118,6 +134,10 @@ gg_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
   if (NCTA == 2) cluster_sync(); else __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // everything above is private to this CTA (smem, mbarriers, TMEM): under programmatic dependent launch it
+  // runs beneath the tail of the previous kernel; global memory is only touched from here on
+  pdl_wait();
+  pdl_trigger();
 
   // Tile schedule: a "unit" (CTA or CTA pair) walks pair-tiles pt = unit, unit + n_units, ...;
   // pair-tile pt covers M-tiles (pt / n_tiles) * NCTA + cta_rank (queues are padded to NCTA*128 rows,
@@ -128,63 +148,102 @@ gg_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
   const int kchunks = p.Kd / BK;
   const int unit = blockIdx.x / NCTA, n_units = gridDim.x / NCTA;
 
+  // Producer and MMA warps run their loops CONVERGED (all 32 lanes); every TMA / MMA / commit / arrive is issued by one
+  // elected lane inside its asm block (tc_common.cuh: the single-thread `if (lane == 0)` form cost ~700 clk of scalar
+  // code per 4-MMA k-chunk and bounded every GEMM of the layer).
+  // Both loops walk the smem ring in rounds of STAGES k-chunks with the stage index a compile-time constant (every
+  // barrier address and descriptor is base + immediate); the flat chunk index f runs over all tiles of this unit.
+  const int my_tiles = unit < total ? (total - unit + n_units - 1) / n_units : 0;
+  const int F = my_tiles * kchunks;
   if (warp == 0) {
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int tile = unit; tile < total; tile += n_units) {
-        const int m_blk = (tile / n_tiles) * NCTA + (int)cta_rank, n_blk = tile % n_tiles;
-        const int e = p.tile_expert[(m_blk * BM) / M3_PAD_ROWS];
-        const int b_row = e * p.N + n_blk * BN + (int)cta_rank * (BN / NCTA);
-        for (int kc = 0; kc < kchunks; ++kc) {
-          mbar_wait(&empty[stage], phase ^ 1);
-          uint8_t* sa = smem + stage * Cfg::STAGE;
+    const uint32_t smem_base = smem_u32(smem);
+    const bool no_tma = (p.dbg & 2) != 0;
+    const uint32_t full0 = NCTA == 2 ? mapa_u32(smem_u32(&full[0]), 0) : smem_u32(&full[0]);   // leader's barriers
+    Tracer trc(p.trace, p.trace_cap, 0);
+    uint32_t phase = 0;
+    int tile = unit, kc = 0, m_blk = 0, b_row = 0;
+    for (int f0 = 0; f0 < F; f0 += STAGES) {
+#pragma unroll
+      for (int st = 0; st < STAGES; ++st) {
+        if (f0 + st < F) {
+          if (kc == 0) {
+            m_blk = (tile / n_tiles) * NCTA + (int)cta_rank;
+            const int e = p.tile_expert[(m_blk * BM) / M3_PAD_ROWS];
+            b_row = e * p.N + (tile % n_tiles) * BN + (int)cta_rank * (BN / NCTA);
+          }
+          trc.ev(0x00, f0 + st);
+          mbar_wait(&empty[st], phase ^ 1);
+          trc.ev(0x01, f0 + st);
+          __syncwarp();
+          const uint32_t sa = smem_base + st * Cfg::STAGE, bar = full0 + st * 8;
           if (NCTA == 2) {
             // both CTAs' bytes are accounted on the LEADER's full barrier
-            const uint32_t bar = mapa_u32(smem_u32(&full[stage]), 0);
-            if (leader_cta) mbar_expect_tx(&full[stage], Cfg::STAGE * NCTA);
-            else mbar_arrive_remote(bar);
-            tma_load_2d_2sm(sa, &tmA, bar, kc * BK, m_blk * BM);
-            tma_load_2d_2sm(sa + Cfg::A_BYTES, &tmB, bar, kc * BK, b_row);
+            if (no_tma) {   // measurement only: no loads, the MMAs chew on whatever the stage holds
+              if (leader_cta) mbar_arrive_elect(&full[st]); else mbar_arrive_remote_elect(bar);
+            } else {
+              if (leader_cta) mbar_expect_tx_elect(&full[st], Cfg::STAGE * NCTA);
+              else mbar_arrive_remote_elect(bar);
+              tma_load_2d_2sm_elect(sa, &tmA, bar, kc * BK, m_blk * BM);
+              tma_load_2d_2sm_elect(sa + Cfg::A_BYTES, &tmB, bar, kc * BK, b_row);
+            }
           } else {
-            mbar_expect_tx(&full[stage], Cfg::STAGE);
-            tma_load_2d(sa, &tmA, &full[stage], kc * BK, m_blk * BM);
-            tma_load_2d(sa + Cfg::A_BYTES, &tmB, &full[stage], kc * BK, b_row);
+            mbar_expect_tx_elect(&full[st], Cfg::STAGE);
+            tma_load_2d_elect(sa, &tmA, bar, kc * BK, m_blk * BM);
+            tma_load_2d_elect(sa + Cfg::A_BYTES, &tmB, bar, kc * BK, b_row);
           }
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          if (++kc == kchunks) { kc = 0; tile += n_units; }
         }
       }
+      phase ^= 1;
     }
+    trc.done();
   } else if (warp == 1) {
-    if (lane == 0 && leader_cta) {
+    if (leader_cta) {
+      Tracer trc(p.trace, p.trace_cap, 1);
       constexpr uint32_t idesc = make_idesc_bf16(BM * NCTA, BN, 0, 0);
-      int stage = 0;
-      uint32_t phase = 0, acc = 0, acc_phase = 0;
-      for (int tile = unit; tile < total; tile += n_units) {
-        mbar_wait(&tempty[acc], acc_phase ^ 1);
-        tcgen05_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * BN;
-        for (int kc = 0; kc < kchunks; ++kc) {
-          mbar_wait(&full[stage], phase);
-          tcgen05_fence_after();
-          const uint32_t a_base = smem_u32(smem + stage * Cfg::STAGE);
-          const uint32_t b_base = a_base + Cfg::A_BYTES;
+      const uint32_t tm = __shfl_sync(0xffffffffu, tmem_base, 0);
+      // K-major operand tiles [rows][64 bf16], SWIZZLE_128B: 8-row groups 1024 B apart (SBO); K advances 32 B per UMMA_K
+      const uint32_t a_lo0 = smem_desc_lo(smem_u32(smem), 0), hi = smem_desc_hi(1024);
+      const bool no_mma = (p.dbg & 1) != 0;
+      uint32_t phase = 0, acc = 0, acc_phase = 0, d_tmem = tm;
+      int kc = 0;
+      for (int f0 = 0; f0 < F; f0 += STAGES) {
 #pragma unroll
-          for (int k = 0; k < BK / UMMA_K; ++k) {
-            const uint64_t adesc = make_smem_desc(a_base + k * UMMA_K * 2, 0, 1024);
-            const uint64_t bdesc = make_smem_desc(b_base + k * UMMA_K * 2, 0, 1024);
-            if (NCTA == 2) umma_bf16_2sm(d_tmem, adesc, bdesc, idesc, (kc | k) != 0);
-            else umma_bf16(d_tmem, adesc, bdesc, idesc, (kc | k) != 0);
+        for (int st = 0; st < STAGES; ++st) {
+          if (f0 + st < F) {
+            if (kc == 0) {   // first k-chunk of a tile: its accumulator buffer must have been drained
+              trc.ev(0x10, f0 + st);
+              mbar_wait(&tempty[acc], acc_phase ^ 1);
+              trc.ev(0x11, f0 + st);
+              d_tmem = tm + acc * BN;
+            }
+            mbar_wait(&full[st], phase);
+            trc.ev(0x12, f0 + st);
+            __syncwarp();
+            tcgen05_fence_after();
+            const uint32_t a_lo = a_lo0 + (uint32_t)st * (Cfg::STAGE >> 4), b_lo = a_lo + (Cfg::A_BYTES >> 4);
+            if (!no_mma) {
+#pragma unroll
+              for (int k = 0; k < BK / UMMA_K; ++k) {
+                if (NCTA == 2) umma_bf16_2sm_elect(d_tmem, a_lo + k * (UMMA_K * 2 >> 4), hi, b_lo + k * (UMMA_K * 2 >> 4), hi, idesc, (kc | k) != 0);
+                else umma_bf16_elect(d_tmem, a_lo + k * (UMMA_K * 2 >> 4), hi, b_lo + k * (UMMA_K * 2 >> 4), hi, idesc, (kc | k) != 0);
+              }
+            }
+            // frees the smem stage (in both CTAs of a pair) once these MMAs have read it
+            if (NCTA == 2) umma_commit_2sm_elect(&empty[st], 3); else umma_commit_elect(&empty[st]);
+            trc.ev(0x13, f0 + st);
+            if (++kc == kchunks) {
+              // accumulator complete -> epilogue warps (of both CTAs)
+              if (NCTA == 2) umma_commit_2sm_elect(&tfull[acc], 3); else umma_commit_elect(&tfull[acc]);
+              kc = 0;
+              acc ^= 1;
+              if (acc == 0) acc_phase ^= 1;
+            }
           }
-          // frees the smem stage (in both CTAs of a pair) once these MMAs have read it
-          if (NCTA == 2) umma_commit_2sm(&empty[stage], 3); else umma_commit(&empty[stage]);
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        // accumulator complete -> epilogue warps (of both CTAs)
-        if (NCTA == 2) umma_commit_2sm(&tfull[acc], 3); else umma_commit(&tfull[acc]);
-        acc ^= 1;
-        if (acc == 0) acc_phase ^= 1;
+        phase ^= 1;
       }
+      trc.done();
     }
   } else {
     // ---- epilogue.  Every warp is an independent pipeline: TMEM -> registers -> bias / GELU / GELU'
@@ -192,22 +251,25 @@ gg_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
     // CTA-wide barrier.  Warp w reads TMEM lanes 32*(w%4).. (hardware rule); warps 2-5 serve
     // accumulator buffer 0 (even tiles of this CTA), warps 6-9 buffer 1 (odd tiles), so two tiles
     // are always in flight in the epilogue.
+    Tracer trc(p.trace, p.trace_cap, 2);
     const int q = warp & 3;
-    const int ew = warp - 2;                     // 0..7
-    const uint32_t grp = (uint32_t)ew >> 2;      // accumulator buffer served
+    const int ew = warp - 2;                     // 0..EW-1
+    const uint32_t grp = (uint32_t)ew / (EW / 2);   // accumulator buffer served
+    const int sub = (ew >> 2) % NQ;              // which of the interleaved column blocks (EW = 16)
     uint8_t* my = stg + ew * Cfg::WARP_STAGING;
-    uint8_t* box = my;                     // [32 rows][64 bf16] transpose box (swizzled, conflict-free both ways)
+    const uint32_t box = smem_u32(my);     // [32 rows][CW bf16] transpose box (swizzled, conflict-free both ways)
     uint8_t* ax = my + WBOX_BYTES;
+    const uint32_t ax32 = smem_u32(ax);
     uint64_t* my_aux = &aux_full[ew];
-    // registers -> swizzled box (one row per lane) -> coalesced 128-B row segments in global memory.
+    // registers -> swizzled box (one row per lane) -> coalesced row segments (CW * 2 bytes) in global memory.
     // Plain st.global: fire-and-forget, so the box is reusable right away (a TMA store would have to
     // drain first, and that latency set the tile period through the 2-deep TMEM pipeline).
     auto flush = [&](__nv_bfloat16* dst, int row0, int col) {
       __syncwarp();
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int rr = i * 4 + (lane >> 3), ch = lane & 7;
-        const uint4 u = *reinterpret_cast<const uint4*>(box + box_off(rr, ch));
+      for (int i = 0; i < NCH; ++i) {
+        const int rr = i * (32 / NCH) + lane / NCH, ch = lane % NCH;
+        const uint4 u = lds128(box + box_off<CW>(rr, ch));
         stg_stream(dst + (int64_t)(row0 + rr) * p.N + col + ch * 8, u);
       }
       __syncwarp();
@@ -217,41 +279,52 @@ gg_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
     const uint32_t tempty_remote = NCTA == 2 ? mapa_u32(smem_u32(&tempty[grp]), 0) : 0u;
     if (EPI == EPI_DGELU && lane == 0 && first < total) {
       mbar_expect_tx(my_aux, WBOX_BYTES);
-      tma_load_2d(ax, &tmAux, my_aux, (first % n_tiles) * BN, ((first / n_tiles) * NCTA + (int)cta_rank) * BM + q * 32);
+      tma_load_2d(ax, &tmAux, my_aux, (first % n_tiles) * BN + sub * CW,
+                  ((first / n_tiles) * NCTA + (int)cta_rank) * BM + q * 32);
     }
     uint32_t it = grp;
     for (int tile = first; tile < total; tile += 2 * n_units, it += 2) {
       const int m_blk = (tile / n_tiles) * NCTA + (int)cta_rank, n_blk = tile % n_tiles;
       const int e = p.tile_expert[(m_blk * BM) / M3_PAD_ROWS];
       const int row0 = m_blk * BM + q * 32;
+      if (ew == 0) trc.ev(0x20, it);
       mbar_wait(&tfull[grp], (it >> 1) & 1);
+      if (ew == 0) trc.ev(0x21, it);
       tcgen05_fence_after();
+      if (p.dbg & 4) {   // measurement only: no epilogue work, the accumulator goes straight back
+        tcgen05_fence_before();
+        if (NCTA == 2 && !leader_cta) mbar_arrive_remote(tempty_remote);
+        else mbar_arrive(&tempty[grp]);
+        continue;
+      }
 #pragma unroll 1
-      for (int cb = 0; cb < NB; ++cb) {
-        const int col = n_blk * BN + cb * 64;
-        float v[64];
+      for (int cbi = 0; cbi < NBW; ++cbi) {
+        const int cb = cbi * NQ + sub;                 // CW-column block of the tile
+        const int col = n_blk * BN + cb * CW;
+        float v[CW];
         // bias slice of this column block: issued BEFORE the TMEM read so that its latency hides behind it
         // (loaded after, the first add stalled on it: 14 % of the fc1 kernel's stall samples)
-        float4 bb[16];
+        float4 bb[CW / 4];
         if (EPI == EPI_BIAS || EPI == EPI_FC1) {
           const float4* b4 = reinterpret_cast<const float4*>(p.bias + (int64_t)e * p.N + col);
 #pragma unroll
-          for (int j = 0; j < 16; ++j) bb[j] = __ldg(b4 + j);
+          for (int j = 0; j < CW / 4; ++j) bb[j] = __ldg(b4 + j);
         }
-        const uint32_t taddr = tmem_base + grp * BN + cb * 64 + ((uint32_t)(q * 32) << 16);
+        const uint32_t taddr = tmem_base + grp * BN + cb * CW + ((uint32_t)(q * 32) << 16);
         tmem_ld_32x32(taddr, v);
-        tmem_ld_32x32(taddr + 32, v + 32);
-        if (cb == NB - 1) {  // last TMEM read of this accumulator: hand it back to the MMA warp early
+        if (CW == 64) tmem_ld_32x32(taddr + 32, v + (CW == 64 ? 32 : 0));
+        if (ew == 0) trc.ev(0x22, cbi);
+        if (cbi == NBW - 1) {  // this warp's last TMEM read of the accumulator: hand it back to the MMA warp early
           tcgen05_fence_before();
           if (NCTA == 2 && !leader_cta) mbar_arrive_remote(tempty_remote);   // the MMA issuer lives in the leader CTA
           else mbar_arrive(&tempty[grp]);
         }
-        f32x2 w2[32];
+        f32x2 w2[CW / 2];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) w2[j] = pk2(v[2 * j], v[2 * j + 1]);
+        for (int j = 0; j < CW / 2; ++j) w2[j] = pk2(v[2 * j], v[2 * j + 1]);
         if (EPI == EPI_BIAS || EPI == EPI_FC1) {
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
+          for (int j = 0; j < CW / 4; ++j) {
             const float4 b = bb[j];
             w2[2 * j] = add2(w2[2 * j], pk2(b.x, b.y));
             w2[2 * j + 1] = add2(w2[2 * j + 1], pk2(b.z, b.w));
@@ -262,55 +335,57 @@ gg_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
             // training: h = gelu(z) goes on to fc2 (and is kept for dW2); the backward pass only ever
             // needs gelu'(z), so THAT is saved instead of z: dgelu becomes one multiply per element
 #pragma unroll
-            for (int c2 = 0; c2 < 4; ++c2) {      // 8 pairs = two 16-byte chunks per batch
+            for (int c2 = 0; c2 < CW / 16; ++c2) {      // 8 pairs = two 16-byte chunks per batch
               f32x2 gl[8], gr[8];
               gelu_fast_grad2_batch<8>(&w2[8 * c2], gl, gr);
 #pragma unroll
               for (int i = 0; i < 8; ++i) w2[8 * c2 + i] = gl[i];
-              *reinterpret_cast<uint4*>(box + box_off(lane, 2 * c2)) =
-                  make_uint4(pack_bf16x2(gr[0]), pack_bf16x2(gr[1]), pack_bf16x2(gr[2]), pack_bf16x2(gr[3]));
-              *reinterpret_cast<uint4*>(box + box_off(lane, 2 * c2 + 1)) =
-                  make_uint4(pack_bf16x2(gr[4]), pack_bf16x2(gr[5]), pack_bf16x2(gr[6]), pack_bf16x2(gr[7]));
+              sts128(box + box_off<CW>(lane, 2 * c2),
+                     make_uint4(pack_bf16x2(gr[0]), pack_bf16x2(gr[1]), pack_bf16x2(gr[2]), pack_bf16x2(gr[3])));
+              sts128(box + box_off<CW>(lane, 2 * c2 + 1),
+                     make_uint4(pack_bf16x2(gr[4]), pack_bf16x2(gr[5]), pack_bf16x2(gr[6]), pack_bf16x2(gr[7])));
             }
             flush(p.out2, row0, col);
           } else {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) w2[j] = gelu_fast2(w2[j]);
+            for (int j = 0; j < CW / 2; ++j) w2[j] = gelu_fast2(w2[j]);
           }
         }
         if (EPI == EPI_DGELU) {
           mbar_wait(my_aux, aux_uses & 1);
           ++aux_uses;
-          uint4 hraw[8];
+          uint4 hraw[NCH];
 #pragma unroll
-          for (int c = 0; c < 8; ++c) hraw[c] = *reinterpret_cast<const uint4*>(ax + box_off(lane, c));
+          for (int c = 0; c < NCH; ++c) hraw[c] = lds128(ax32 + box_off<CW>(lane, c));
           __syncwarp();
           if (lane == 0) {  // aux box consumed into registers: prefetch the next one behind the math
-            int nt = tile, ncb = cb + 1;
-            if (ncb == NB) { ncb = 0; nt += 2 * n_units; }
+            int nt = tile, ncbi = cbi + 1;
+            if (ncbi == NBW) { ncbi = 0; nt += 2 * n_units; }
             if (nt < total) {
               mbar_expect_tx(my_aux, WBOX_BYTES);
-              tma_load_2d(ax, &tmAux, my_aux, (nt % n_tiles) * BN + ncb * 64,
+              tma_load_2d(ax, &tmAux, my_aux, (nt % n_tiles) * BN + (ncbi * NQ + sub) * CW,
                           ((nt / n_tiles) * NCTA + (int)cta_rank) * BM + q * 32);
             }
           }
 #pragma unroll
-          for (int c = 0; c < 8; ++c) {
+          for (int c = 0; c < NCH; ++c) {
             const uint32_t hw[4] = {hraw[c].x, hraw[c].y, hraw[c].z, hraw[c].w};
 #pragma unroll
             for (int i = 0; i < 4; ++i) w2[4 * c + i] = mul2(w2[4 * c + i], unpack_bf16x2(hw[i]));   // * gelu'(z)
           }
         }
 #pragma unroll
-        for (int c = 0; c < 8; ++c) {
+        for (int c = 0; c < NCH; ++c) {
           uint4 u;
           u.x = pack_bf16x2(w2[4 * c]); u.y = pack_bf16x2(w2[4 * c + 1]);
           u.z = pack_bf16x2(w2[4 * c + 2]); u.w = pack_bf16x2(w2[4 * c + 3]);
-          *reinterpret_cast<uint4*>(box + box_off(lane, c)) = u;
+          sts128(box + box_off<CW>(lane, c), u);
         }
         flush(p.out, row0, col);
+        if (ew == 0) trc.ev(0x23, cbi);
       }
     }
+    if (ew == 0) trc.done();
   }
   tcgen05_fence_before();
   if (NCTA == 2) cluster_sync(); else __syncthreads();     // a pair's smem / TMEM stay alive until both are done
@@ -329,6 +404,9 @@ struct WGParams {
   float* dW;      // [S][E][M][N]  (S = gridDim.z / E row-splits; S == 1: the final gradient)
   float* db;      // [S][E][M] column sums of X1 over the split's rows (bias gradient)
   int E;
+  int dbg;        // M3_KNOB_DEBUG (measurement only): 1 = no MMAs, 2 = no TMA loads
+  unsigned long long* trace;   // m3_debug_trace_buffer
+  int trace_cap;
 };
 
 template <int BN>
@@ -387,6 +465,8 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tm1, const __grid_constant__ CU
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();      // prologue above overlaps the previous kernel's tail (programmatic dependent launch)
+  pdl_trigger();
   const int all_chunks = (p.offsets[e + 1] - p.offsets[e]) / BK;   // queues are padded to M3_PAD_ROWS (a multiple of BK)
   const int per_split = (all_chunks + nsplit - 1) / nsplit;
   const int c_begin = min(split * per_split, all_chunks), c_end = min(c_begin + per_split, all_chunks);
@@ -394,44 +474,70 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tm1, const __grid_constant__ CU
   const int kchunks = c_end - c_begin;
 
   if (warp == 0) {
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int kc = 0; kc < kchunks; ++kc) {
-        mbar_wait(&empty[stage], phase ^ 1);
-        mbar_expect_tx(&full[stage], Cfg::TMA_BYTES);
-        uint8_t* sa = smem + stage * Cfg::STAGE;
-        const int r = r0 + kc * BK;
+    // converged warp, elected lane issues; ring walked in rounds with a compile-time stage index (see gg_kernel)
+    uint32_t phase = 0;
+    const uint32_t smem_base = smem_u32(smem), full0 = smem_u32(&full[0]);
+    const bool no_tma = (p.dbg & 2) != 0;
+    Tracer trc(p.trace, p.trace_cap, 0);
+    for (int kc0 = 0; kc0 < kchunks; kc0 += STAGES) {
 #pragma unroll
-        for (int b = 0; b < BM / 64; ++b) tma_load_2d(sa + b * Cfg::BOX, &tm1, &full[stage], m0 + b * 64, r);
+      for (int st = 0; st < STAGES; ++st) {
+        if (kc0 + st < kchunks) {
+          trc.ev(0x00, kc0 + st);
+          mbar_wait(&empty[st], phase ^ 1);
+          trc.ev(0x01, kc0 + st);
+          __syncwarp();
+          if (no_tma) {   // measurement only: no loads
+            mbar_arrive_elect(&full[st]);
+          } else {
+            mbar_expect_tx_elect(&full[st], Cfg::TMA_BYTES);
+            const uint32_t sa = smem_base + st * Cfg::STAGE, bar = full0 + st * 8;
+            const int r = r0 + (kc0 + st) * BK;
 #pragma unroll
-        for (int b = 0; b < BN / 64; ++b)
-          tma_load_2d(sa + Cfg::A_BYTES + b * Cfg::BOX, &tm2, &full[stage], n0 + b * 64, r);
-        if (++stage == STAGES) { stage = 0; phase ^= 1; }
-      }
-    }
-  } else if (warp == 1) {
-    if (lane == 0) {
-      const uint32_t idesc = with_db ? make_idesc_bf16(BM, BN + 16, 1, 1) : make_idesc_bf16(BM, BN, 1, 1);
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int kc = 0; kc < kchunks; ++kc) {
-        mbar_wait(&full[stage], phase);
-        tcgen05_fence_after();
-        const uint32_t a_base = smem_u32(smem + stage * Cfg::STAGE);
-        const uint32_t b_base = a_base + Cfg::A_BYTES;
+            for (int b = 0; b < BM / 64; ++b) tma_load_2d_elect(sa + b * Cfg::BOX, &tm1, bar, m0 + b * 64, r);
 #pragma unroll
-        for (int k = 0; k < BK / UMMA_K; ++k) {
-          // MN-major: 16 k-rows = 2 swizzle groups of 8 rows (1024 B each)
-          const uint64_t adesc = make_smem_desc(a_base + k * 2048, Cfg::BOX, 1024);
-          const uint64_t bdesc = make_smem_desc(b_base + k * 2048, Cfg::BOX, 1024);
-          umma_bf16(tmem_base, adesc, bdesc, idesc, (kc | k) != 0);
+            for (int b = 0; b < BN / 64; ++b) tma_load_2d_elect(sa + Cfg::A_BYTES + b * Cfg::BOX, &tm2, bar, n0 + b * 64, r);
+          }
         }
-        umma_commit(&empty[stage]);
-        if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
-      umma_commit(tfull);
+      phase ^= 1;
     }
+    trc.done();
+  } else if (warp == 1) {
+    Tracer trc(p.trace, p.trace_cap, 1);
+    // whole warp, converged; the MMAs / commits are issued by one elected lane (see tc_common.cuh)
+    const uint32_t idesc = with_db ? make_idesc_bf16(BM, BN + 16, 1, 1) : make_idesc_bf16(BM, BN, 1, 1);
+    const uint32_t tm = __shfl_sync(0xffffffffu, tmem_base, 0);
+    // MN-major: 16 k-rows = 2 swizzle groups of 8 rows (1024 B each, SBO); next 64 M/N elements one box further (LBO)
+    const uint32_t a_lo0 = smem_desc_lo(smem_u32(smem), Cfg::BOX), hi = smem_desc_hi(1024);
+    const bool no_mma = (p.dbg & 1) != 0;
+    // The ring is walked in rounds of STAGES chunks with the stage index a compile-time constant, so that every
+    // descriptor is base + immediate and every barrier address an immediate offset (a run-time stage index costs
+    // ~25 SASS instructions per MMA in index arithmetic and vector-to-uniform register moves).
+    uint32_t phase = 0;
+    for (int kc0 = 0; kc0 < kchunks; kc0 += STAGES) {
+#pragma unroll
+      for (int st = 0; st < STAGES; ++st) {
+        if (kc0 + st < kchunks) {
+          trc.ev(0x10, kc0 + st);
+          mbar_wait(&full[st], phase);
+          trc.ev(0x12, kc0 + st);
+          __syncwarp();
+          tcgen05_fence_after();
+          const uint32_t a_lo = a_lo0 + (uint32_t)st * (Cfg::STAGE >> 4), b_lo = a_lo + (Cfg::A_BYTES >> 4);
+          if (!no_mma) {
+#pragma unroll
+            for (int k = 0; k < BK / UMMA_K; ++k)
+              umma_bf16_elect(tm, a_lo + k * (2048 >> 4), hi, b_lo + k * (2048 >> 4), hi, idesc, (kc0 | st | k) != 0);
+          }
+          umma_commit_elect(&empty[st]);
+          trc.ev(0x13, kc0 + st);
+        }
+      }
+      phase ^= 1;
+    }
+    umma_commit_elect(tfull);
+    trc.done();
   } else {
     const int q = warp & 3;
     const int row = m0 + q * 32 + lane;
@@ -487,16 +593,18 @@ static EncodeTiledFn get_encode() {
 }
 
 // 2-D bf16 row-major tensor [rows][cols], box [box_rows][64 cols] (128 B inner), SWIZZLE_128B
-static int make_map(CUtensorMap* m, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows) {
+// (box_cols = 32: 64 B inner, SWIZZLE_64B - the 32-column epilogue blocks of the 16-warp epilogue)
+static int make_map(CUtensorMap* m, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows,
+                    uint32_t box_cols = 64) {
   EncodeTiledFn enc = get_encode();
   if (!enc) return M3_ERR_UNSUPPORTED;
   cuuint64_t dims[2] = {cols, rows};
   cuuint64_t strides[1] = {cols * 2};
-  cuuint32_t box[2] = {64, box_rows};
+  cuuint32_t box[2] = {box_cols, box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, box_cols == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? M3_OK : M3_ERR_ARG;
 }
 
@@ -507,16 +615,35 @@ static int pick_bn(int N, bool heavy_epilogue) {
   return N % 128 == 0 ? 128 : 0;
 }
 
+// measured at T = 38 432, D = H = 384 (tools/variants.py): fc1 (bias + GELU + GELU', two outputs) gains ~8 % from 16
+// warps, the other three epilogues are within noise of each other
+constexpr int kDefaultEpiWarps[4] = {/*STORE*/ 8, /*BIAS*/ 8, /*FC1*/ 16, /*DGELU*/ 8};
+// m3_debug_trace_buffer: M3_KNOB_TRACE_KERNEL = 1 + index of the GEMM launch (within one m3_ffn_fwd / m3_ffn_bwd call) that
+// writes the timeline; 0 = every launch (each overwrites the previous one's events)
+static int g_trace_launch_idx = 0;
+static unsigned long long* trace_buf_for_this_launch() {
+  const int want = g_knobs[M3_KNOB_TRACE_KERNEL], idx = g_trace_launch_idx++;
+  return (want == 0 || want - 1 == idx) ? g_trace_buf : nullptr;
+}
 constexpr int kGGNcta = 2;   // CTA pairs: halves the per-SM weight traffic (the GEMMs are L2 -> SM bound at K = 384)
 
 // SMs the persistent grouped GEMMs may occupy.  Expert parallelism with overlap (ep.py) lowers it so that the NVLink row
 // movers of the other half-batch find free SMs while a GEMM runs (they need ~12-20 SMs: tools/ep_overlap_probe.py).
 static int g_gemm_sms = kNumSMs;
 
-template <int BN, int EPI>
+// epilogue warps per GEMM epilogue: the knob (8 / 16) wins, otherwise the per-epilogue default
+template <int EPI>
+static int epi_warps() {
+  const int k = g_knobs[M3_KNOB_EPI_WARPS];
+  if (k == 8 || k == 16) return k;
+  if (k & 0x100) return ((k >> EPI) & 1) ? 16 : 8;     // 0x100 | mask: bit EPI set -> 16 warps for that epilogue
+  return kDefaultEpiWarps[EPI];
+}
+
+template <int BN, int EPI, int EW>
 static int launch_gg_t(const CUtensorMap* maps, const GGParams& p, int max_tiles, cudaStream_t st) {
-  using Cfg = GGCfg<BN, EPI, kGGNcta>;
-  auto kern = gg_kernel<BN, EPI, kGGNcta>;
+  using Cfg = GGCfg<BN, EPI, kGGNcta, EW>;
+  auto kern = gg_kernel<BN, EPI, kGGNcta, EW>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
   if (e != cudaSuccess) return (int)e;
   int grid = max_tiles < g_gemm_sms ? max_tiles : g_gemm_sms;
@@ -524,16 +651,18 @@ static int launch_gg_t(const CUtensorMap* maps, const GGParams& p, int max_tiles
   if (grid < kGGNcta) grid = kGGNcta;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(grid);
-  cfg.blockDim = dim3(kGGThreads);
+  cfg.blockDim = dim3(gg_threads(EW));
   cfg.dynamicSmemBytes = Cfg::SMEM;
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = kGGNcta;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = g_knobs[M3_KNOB_PDL] ? 2 : 1;
   e = cudaLaunchKernelEx(&cfg, kern, maps[0], maps[1], maps[2], maps[3], maps[4], p);
   if (e != cudaSuccess) return (int)e;
   M3_LAUNCH_CHECK();
@@ -556,18 +685,25 @@ static int launch_gg(const void* A, const void* B, void* out, void* out2, const 
   if (rc) return rc;
   rc = make_map(&maps[3], out2 ? out2 : out, (uint64_t)cap_rows, (uint64_t)p.N, 32);
   if (rc) return rc;
-  rc = make_map(&maps[4], aux ? aux : out, (uint64_t)cap_rows, (uint64_t)p.N, 32);
+  const int ew = epi_warps<EPI>();
+  rc = make_map(&maps[4], aux ? aux : out, (uint64_t)cap_rows, (uint64_t)p.N, 32, ew == 16 ? 32 : 64);
   if (rc) return rc;
   p.out = static_cast<__nv_bfloat16*>(out);
   p.out2 = static_cast<__nv_bfloat16*>(out2);
+  p.dbg = g_knobs[M3_KNOB_DEBUG];
+  p.trace = trace_buf_for_this_launch();
+  p.trace_cap = g_trace_cap;
   const int max_tiles = (cap_rows / BM) * (p.N / BN);
+#define M3_GG_EW(BNV)                                                                \
+  (ew == 16 ? launch_gg_t<BNV, EPI, 16>(maps, p, max_tiles, st) : launch_gg_t<BNV, EPI, 8>(maps, p, max_tiles, st))
   switch (BN) {
-    case 128: return launch_gg_t<128, EPI>(maps, p, max_tiles, st);
-    case 192: return launch_gg_t<192, EPI>(maps, p, max_tiles, st);
+    case 128: return M3_GG_EW(128);
+    case 192: return M3_GG_EW(192);
     default:
-      if constexpr (!heavy) return launch_gg_t<256, EPI>(maps, p, max_tiles, st);
+      if constexpr (!heavy) return M3_GG_EW(256);
       return M3_ERR_SHAPE;
   }
+#undef M3_GG_EW
 }
 
 // out[i] = sum_s part[s][i] (fixed order), float4-wide
@@ -610,8 +746,8 @@ static int launch_wgrad(const void* X1, const void* X2, const int32_t* offsets, 
   const int S = wgrad_splits(E, M, N);
   float* pW = S > 1 ? ws : dW;
   float* pb = S > 1 ? ws + (size_t)S * E * M * N : db;
-  WGParams p{offsets, M, N, pW, pb, E};
-  kern<<<dim3(M / BM, N / BN, E * S), kThreads, Cfg::SMEM, st>>>(t1, t2, p);
+  WGParams p{offsets, M, N, pW, pb, E, g_knobs[M3_KNOB_DEBUG], trace_buf_for_this_launch(), g_trace_cap};
+  launch_k(kern, dim3(M / BM, N / BN, E * S), dim3(kThreads), Cfg::SMEM, st, t1, t2, p);
   M3_LAUNCH_CHECK();
   if (S > 1) {
     const int64_t n4 = (int64_t)E * M * N / 4;
@@ -668,6 +804,7 @@ int m3_ffn_fwd_bf16(const void* xq, const int32_t* offsets, const int32_t* tile_
                     int H, const void* w1, const float* b1, const void* w2, const float* b2, void* saved, void* yq,
                     void* workspace, size_t workspace_bytes, cudaStream_t st) {
   if (workspace == nullptr || workspace_bytes < m3_ffn_bf16_workspace_bytes(cap_rows, D, H, E, 0)) return M3_ERR_WORKSPACE;
+  g_trace_launch_idx = 0;
   if (use_fused(D, H))
     return m3_ffn_fused_fwd(xq, offsets, tile_expert, cap_rows, E, D, H, w1, b1, w2, b2, saved, yq, st);
   const size_t hbytes = align256((size_t)cap_rows * H * 2);
@@ -690,6 +827,7 @@ int m3_ffn_bwd_bf16(const void* xq, const void* saved, const void* dyq, const in
                     void* workspace, size_t workspace_bytes, cudaStream_t st) {
   (void)counts; (void)w1; (void)w2;
   if (workspace_bytes < m3_ffn_bf16_workspace_bytes(cap_rows, D, H, E, 1)) return M3_ERR_WORKSPACE;
+  g_trace_launch_idx = 0;
   const size_t hbytes = align256((size_t)cap_rows * H * 2);
   bf16* dhpre = static_cast<bf16*>(workspace);
   float* part = reinterpret_cast<float*>(static_cast<uint8_t*>(workspace) + 2 * hbytes);

@@ -68,6 +68,8 @@ gate_fwd_kernel(const XT* __restrict__ x, int64_t ldx, const float* __restrict__
                 float* __restrict__ gates, float* __restrict__ imp_partial,
                 int32_t* __restrict__ load_partial, const float* __restrict__ ln_mean,
                 const float* __restrict__ ln_rstd, const float* __restrict__ ln_gb) {
+  pdl_wait();
+  pdl_trigger();
   using C = GateCfg<E, TM, NW>;
   using Row = GateRow<XT>;
   constexpr int EG = C::EG, TG = C::TG, TOK_W = C::TOK_W;
@@ -281,6 +283,7 @@ static size_t gate_fwd_smem() {
 //   0: 1 warp x TG*2 tokens (small T)   1: 4 warps x TG*2   2: 4 warps x TG*4   3: 4 warps x TG*8
 template <int E>
 static int gate_cfg_id(int T) {
+  if (g_knobs[M3_KNOB_GATE_CFG] > 0) return g_knobs[M3_KNOB_GATE_CFG] - 1;   // forced (A/B measurement)
   if (T >= 16 * kNumSMs * GateCfg<E, 8, 4>::TOK_W) return 3;
   if (T >= 16 * kNumSMs * GateCfg<E, 4, 4>::TOK_W) return 2;
   if (T >= 16 * kNumSMs * GateCfg<E, 2, 4>::TOK_W) return 1;
@@ -301,9 +304,9 @@ static int launch_gate_fwd(const void* x, int64_t ldx, const float* task_feat, c
     if (e != cudaSuccess) return (int)e;
   }
   int grid = m3_ceil_div(T, C::TOK_CTA);
-  kern<<<grid, NW * 32, smem, st>>>(static_cast<const XT*>(x), ldx, task_feat, w_gate, noise, noise_stddev, T,
-                                    D, Dt, K, K1, idx, idx_full, score, top_vals, clean, noisy, gates,
-                                    imp_partial, load_partial, ln_mean, ln_rstd, ln_gb);
+  launch_k(kern, grid, NW * 32, smem, st, static_cast<const XT*>(x), ldx, task_feat, w_gate, noise, noise_stddev, T,
+           D, Dt, K, K1, idx, idx_full, score, top_vals, clean, noisy, gates, imp_partial, load_partial, ln_mean,
+           ln_rstd, ln_gb);
   M3_LAUNCH_CHECK();
   return M3_OK;
 }
@@ -327,6 +330,8 @@ gate_bwd_dz_kernel(const float* __restrict__ logits, const int32_t* __restrict__
                    float* __restrict__ dz) {
   constexpr int EG = E / 4;
   // gradient of cv^2(importance) w.r.t. importance[e], scaled by d(cv_loss) (added to dimp)
+  pdl_wait();
+  pdl_trigger();
   __shared__ float gimp[E];
   if (dcv != nullptr) {
     if (threadIdx.x == 0) {
@@ -408,6 +413,8 @@ gate_bwd_dw_kernel(const XT* __restrict__ x, int64_t ldx, const float* __restric
                                    const float* __restrict__ ln_rstd, const float* __restrict__ ln_gamma,
                                    const float* __restrict__ ln_beta) {
   const int ngrp = blockDim.x / (D / 4);          // expert groups per CTA (EB / EW)
+  pdl_wait();
+  pdl_trigger();
   const int dq = threadIdx.x % (D / 4);
   const int eh = threadIdx.x / (D / 4);
   const int e0 = blockIdx.y * (EW * ngrp) + eh * EW;
@@ -510,6 +517,8 @@ gate_bwd_reduce_kernel(const float* __restrict__ part, const float* __restrict__
                        float* __restrict__ dw, float* __restrict__ dtask) {
   __shared__ float red[32][33];
   __shared__ float cs_s[128];
+  pdl_wait();
+  pdl_trigger();
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int64_t n_main = (int64_t)D * E;
   const int64_t i = (int64_t)blockIdx.x * 32 + lane;
@@ -555,6 +564,8 @@ gate_bwd_reduce_kernel(const float* __restrict__ part, const float* __restrict__
 // standalone router dx: dxg[t, d] = sum_e dz[t,e] * w_gate[d,e]
 __global__ void gate_bwd_dx_kernel(const float* __restrict__ dz, const float* __restrict__ w_gate, int T, int D,
                                    int E, float* __restrict__ dxg) {
+  pdl_wait();
+  pdl_trigger();
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (int64_t)T * (D / 4)) return;
   const int64_t t = i / (D / 4);
@@ -694,7 +705,7 @@ static int gate_bwd_impl(const void* x, int x_dtype, int64_t ldx, const float* t
     const int64_t nthr = (int64_t)T * (E / 4);
     const int grid = (int)((nthr + 255) / 256);
 #define M3_DZ_CASE(EE) \
-  case EE: gate_bwd_dz_kernel<EE><<<grid, 256, 0, st>>>(logits, idx_full, T, K, K1, dscore, dtop_vals, dgates, dimportance, dclean, dnoisy, importance, dcv_loss, dz); break;
+  case EE: launch_k(gate_bwd_dz_kernel<EE>, grid, 256, 0, st, logits, idx_full, T, K, K1, dscore, dtop_vals, dgates, dimportance, dclean, dnoisy, importance, dcv_loss, dz); break;
     switch (E) {
       M3_DZ_CASE(4) M3_DZ_CASE(8) M3_DZ_CASE(16) M3_DZ_CASE(32) M3_DZ_CASE(64) M3_DZ_CASE(128)
       default: return M3_ERR_SHAPE;
@@ -715,9 +726,9 @@ static int gate_bwd_impl(const void* x, int x_dtype, int64_t ldx, const float* t
     // token batch (loads in flight per thread) limited by the register file at large CTAs
 #define M3_DW_LAUNCH(EWV, XT, LNV)                                                                                   \
   do {                                                                                                              \
-    if (threads <= 384) gate_bwd_dw_kernel<EWV, XT, LNV, 16><<<grid, threads, 0, st>>>(M3_DW_ARGS(XT));            \
-    else if (threads <= 512) gate_bwd_dw_kernel<EWV, XT, LNV, 8><<<grid, threads, 0, st>>>(M3_DW_ARGS(XT));        \
-    else gate_bwd_dw_kernel<EWV, XT, LNV, 4><<<grid, threads, 0, st>>>(M3_DW_ARGS(XT));                            \
+    if (threads <= 384) launch_k(gate_bwd_dw_kernel<EWV, XT, LNV, 16>, grid, threads, 0, st, M3_DW_ARGS(XT));            \
+    else if (threads <= 512) launch_k(gate_bwd_dw_kernel<EWV, XT, LNV, 8>, grid, threads, 0, st, M3_DW_ARGS(XT));        \
+    else launch_k(gate_bwd_dw_kernel<EWV, XT, LNV, 4>, grid, threads, 0, st, M3_DW_ARGS(XT));                            \
   } while (0)
     if (ln_mean != nullptr) {
       if (EW == 8) M3_DW_LAUNCH(8, float, true); else M3_DW_LAUNCH(4, float, true);
@@ -730,13 +741,13 @@ static int gate_bwd_impl(const void* x, int x_dtype, int64_t ldx, const float* t
   }
   {
     const int main_blocks = (int)(((int64_t)D * E + 31) / 32);
-    gate_bwd_reduce_kernel<<<main_blocks + (Dt > 0 ? 1 : 0), 1024, 0, st>>>(part, cs_part, nchunk, D, Dt, E, task_feat,
-                                                                          w_gate, dw_gate, dtask_feat);
+    launch_k(gate_bwd_reduce_kernel, main_blocks + (Dt > 0 ? 1 : 0), 1024, 0, st, part, cs_part, nchunk, D, Dt, E,
+             task_feat, w_gate, dw_gate, dtask_feat);
     M3_LAUNCH_CHECK();
   }
   if (dx_gate != nullptr) {
     const int64_t n = (int64_t)T * (D / 4);
-    gate_bwd_dx_kernel<<<(int)((n + 255) / 256), 256, 0, st>>>(dz, w_gate, T, D, E, dx_gate);
+    launch_k(gate_bwd_dx_kernel, (int)((n + 255) / 256), 256, 0, st, dz, w_gate, T, D, E, dx_gate);
     M3_LAUNCH_CHECK();
   }
   return M3_OK;

@@ -52,6 +52,8 @@ __device__ __forceinline__ void zero_pad_rows(TO* q, const int32_t* counts, cons
 template <typename TO>
 __global__ void __launch_bounds__(kPermThreads)
 zero_pad_rows_kernel(TO* __restrict__ q, const int32_t* __restrict__ counts, const int32_t* __restrict__ offsets, int D) {
+  pdl_wait();
+  pdl_trigger();
   zero_pad_rows<TO>(q, counts, offsets, blockIdx.x, D);
 }
 
@@ -60,6 +62,8 @@ template <typename TI, typename TO, int NV, bool EP>
 __global__ void __launch_bounds__(kPermThreads)
 dispatch_fwd_kernel(const TI* __restrict__ x, const int32_t* __restrict__ pos, const int32_t* __restrict__ counts,
                     const int32_t* __restrict__ offsets, int T, int K, int D, int tok_ctas, Queue<TO> xq) {
+  pdl_wait();
+  pdl_trigger();
   if ((int)blockIdx.x >= tok_ctas) {
     // zero rows [off[e]+cnt[e], off[e+1]) of expert e (local queue only)
     zero_pad_rows<TO>(xq.local, counts, offsets, blockIdx.x - tok_ctas, D);
@@ -88,10 +92,16 @@ dispatch_fwd_kernel(const TI* __restrict__ x, const int32_t* __restrict__ pos, c
 }
 
 // out[t] = sum_k score[t,k] * yq[pos[t,k]]   (fp32 accumulation, k ascending like bmm)
-template <typename TI, typename TO, int NV, bool EP>
-__global__ void __launch_bounds__(kPermThreads)
+// Rows in flight per thread vs resident CTAs (tools/variants.py, T = 38 432, D = 384): 4 rows at 2 CTAs/SM (128 regs) 44 us,
+// 2 rows at 4 CTAs/SM (<= 64 regs) 39 us - the gather wants warps, not deeper per-thread batches.
+template <typename TI, typename TO, int NV, bool EP,
+          int kGatherK = (NV <= 3 && sizeof(TI) == 2 && !EP ? 2 : m3::kGatherK),
+          int MINB = (NV <= 3 && sizeof(TI) == 2 && !EP ? 4 : 1)>
+__global__ void __launch_bounds__(kPermThreads, MINB)
 combine_fwd_kernel(Queue<const TI> yq, const int32_t* __restrict__ pos, const float* __restrict__ score,
                    int T, int K, int D, TO* __restrict__ out, TI* __restrict__ ysave) {
+  pdl_wait();
+  pdl_trigger();
   const int sub = threadIdx.x % kLanesPerTok;
   const int t = blockIdx.x * kTokPerCta + threadIdx.x / kLanesPerTok;
   if (t >= T) return;
@@ -156,12 +166,14 @@ combine_fwd_kernel(Queue<const TI> yq, const int32_t* __restrict__ pos, const fl
 }
 
 // dscore[t,k] = <g[t], yq[pos[t,k]]>;  dyq[pos[t,k]] = score[t,k] * g[t];  zero dyq padding rows
-template <typename TG, typename TQ, int NV, bool EP>
-__global__ void __launch_bounds__(kPermThreads)
+template <typename TG, typename TQ, int NV, bool EP, int kGatherK = m3::kGatherK, int MINB = 1>
+__global__ void __launch_bounds__(kPermThreads, MINB)
 combine_bwd_kernel(const TG* __restrict__ g, Queue<const TQ> yq, const int32_t* __restrict__ pos,
                    const float* __restrict__ score, const int32_t* __restrict__ counts,
                    const int32_t* __restrict__ offsets, int T, int K, int D, int tok_ctas,
                    Queue<TQ> dyq, float* __restrict__ dscore, const TQ* __restrict__ ysave) {
+  pdl_wait();
+  pdl_trigger();
   if ((int)blockIdx.x >= tok_ctas) {
     zero_pad_rows<TQ>(dyq.local, counts, offsets, blockIdx.x - tok_ctas, D);
     return;
@@ -241,6 +253,8 @@ combine_bwd_kernel(const TG* __restrict__ g, Queue<const TQ> yq, const int32_t* 
 template <typename TI, typename TO, int NV, bool EP>
 __global__ void __launch_bounds__(kPermThreads)
 dispatch_bwd_kernel(Queue<const TI> dxq, const int32_t* __restrict__ pos, int T, int K, int D, TO* __restrict__ dx) {
+  pdl_wait();
+  pdl_trigger();
   const int sub = threadIdx.x % kLanesPerTok;
   const int t = blockIdx.x * kTokPerCta + threadIdx.x / kLanesPerTok;
   if (t >= T) return;
@@ -281,6 +295,8 @@ __global__ void __launch_bounds__(kPermThreads, 2)
 dispatch_bwd_gate_kernel(Queue<const TI> dxq, const int32_t* __restrict__ pos, int T, int K, int D,
                          const float* __restrict__ dz, const float* __restrict__ w_gate, int E,
                          TO* __restrict__ dx) {
+  pdl_wait();
+  pdl_trigger();
   // wt[e][h][c][4]: the 8 columns c*8..c*8+7 of a lane's slice are kept as two float4 in separate
   // planes h = 0/1, so that the 16 lanes of a group read CONSECUTIVE 16-byte words (a plain [E][D]
   // layout makes lanes 32 B apart: 2-way bank conflicts on every read).
@@ -426,7 +442,7 @@ static int dispatch_fwd_impl(const void* x, int x_dtype, const int32_t* pos, con
   if (grid == 0) return M3_OK;
   M3_DTYPE2_SWITCH(x_dtype, xq_dtype, {
     Queue<TB> q{(TB*)xq, (TB* const*)peer, slot_rank};
-    M3_NV_SWITCH((dispatch_fwd_kernel<TA, TB, NV, EP><<<grid, kPermThreads, 0, st>>>((const TA*)x, pos, counts, offsets, T, K, D, tok_ctas, q)))
+    M3_NV_SWITCH((launch_k(dispatch_fwd_kernel<TA, TB, NV, EP>, grid, kPermThreads, 0, st, (const TA*)x, pos, counts, offsets, T, K, D, tok_ctas, q)))
   })
   M3_LAUNCH_CHECK();
   return M3_OK;
@@ -441,9 +457,18 @@ static int combine_fwd_impl(const void* yq, void* const* peer, const int32_t* sl
   if (T == 0) return M3_OK;
   const int nv = perm_nv(D);
   const int grid = m3_ceil_div(T, kTokPerCta);
+  const int var = g_knobs[M3_KNOB_MOVER_VARIANT];
+  if (var != 0 && !EP && nv == 3 && yq_dtype == M3_BF16 && out_dtype == M3_F32) {   // A/B variants (bench shape only)
+    Queue<const bf16> q{(const bf16*)yq, nullptr, nullptr};
+#define M3_CF_VAR(GK, MB) launch_k(combine_fwd_kernel<bf16, float, 3, false, GK, MB>, grid, kPermThreads, 0, st, q, pos, score, T, K, D, (float*)out, (bf16*)ysave)
+    if (var == 1) M3_CF_VAR(2, 3); else if (var == 2) M3_CF_VAR(4, 3); else if (var == 3) M3_CF_VAR(2, 4); else M3_CF_VAR(1, 4);
+#undef M3_CF_VAR
+    M3_LAUNCH_CHECK();
+    return M3_OK;
+  }
   M3_DTYPE2_SWITCH(yq_dtype, out_dtype, {
     Queue<const TA> q{(const TA*)yq, (const TA* const*)peer, slot_rank};
-    M3_NV_SWITCH((combine_fwd_kernel<TA, TB, NV, EP><<<grid, kPermThreads, 0, st>>>(q, pos, score, T, K, D, (TB*)out, (TA*)ysave)))
+    M3_NV_SWITCH((launch_k(combine_fwd_kernel<TA, TB, NV, EP>, grid, kPermThreads, 0, st, q, pos, score, T, K, D, (TB*)out, (TA*)ysave)))
   })
   M3_LAUNCH_CHECK();
   return M3_OK;
@@ -460,10 +485,20 @@ static int combine_bwd_impl(const void* g, int g_dtype, const void* yq, void* co
   const int tok_ctas = m3_ceil_div(T, kTokPerCta);
   const int grid = tok_ctas + (EP ? 0 : E);
   if (grid == 0) return M3_OK;
+  const int var = g_knobs[M3_KNOB_MOVER_VARIANT];
+  if (var != 0 && !EP && nv == 3 && g_dtype == M3_F32 && q_dtype == M3_BF16) {   // A/B variants (bench shape only)
+    Queue<const bf16> qy{(const bf16*)yq, nullptr, nullptr};
+    Queue<bf16> qd{(bf16*)dyq, nullptr, nullptr};
+#define M3_CB_VAR(GK, MB) launch_k(combine_bwd_kernel<float, bf16, 3, false, GK, MB>, grid, kPermThreads, 0, st, (const float*)g, qy, pos, score, counts, offsets, T, K, D, tok_ctas, qd, dscore, (const bf16*)ysave)
+    if (var == 1) M3_CB_VAR(2, 3); else if (var == 2) M3_CB_VAR(4, 3); else if (var == 3) M3_CB_VAR(2, 4); else M3_CB_VAR(1, 4);
+#undef M3_CB_VAR
+    M3_LAUNCH_CHECK();
+    return M3_OK;
+  }
   M3_DTYPE2_SWITCH(g_dtype, q_dtype, {
     Queue<const TB> qy{(const TB*)yq, (const TB* const*)peer_yq, slot_rank};
     Queue<TB> qd{(TB*)dyq, (TB* const*)peer_dyq, slot_rank};
-    M3_NV_SWITCH((combine_bwd_kernel<TA, TB, NV, EP><<<grid, kPermThreads, 0, st>>>((const TA*)g, qy, pos, score, counts, offsets, T, K, D, tok_ctas, qd, dscore, (const TB*)ysave)))
+    M3_NV_SWITCH((launch_k(combine_bwd_kernel<TA, TB, NV, EP>, grid, kPermThreads, 0, st, (const TA*)g, qy, pos, score, counts, offsets, T, K, D, tok_ctas, qd, dscore, (const TB*)ysave)))
   })
   M3_LAUNCH_CHECK();
   return M3_OK;
@@ -481,7 +516,7 @@ static int dispatch_bwd_impl(const void* dxq, void* const* peer, const int32_t* 
     const int grid = m3_ceil_div(T, kTokPerCta);
     M3_DTYPE2_SWITCH(dxq_dtype, dx_dtype, {
       Queue<const TA> q{(const TA*)dxq, (const TA* const*)peer, slot_rank};
-      M3_NV_SWITCH((dispatch_bwd_kernel<TA, TB, NV, EP><<<grid, kPermThreads, 0, st>>>(q, pos, T, K, D, (TB*)dx)))
+      M3_NV_SWITCH((launch_k(dispatch_bwd_kernel<TA, TB, NV, EP>, grid, kPermThreads, 0, st, q, pos, T, K, D, (TB*)dx)))
     })
   } else {
     // router term: w_gate[:D]^T staged once per CTA -> few, grid-striding CTAs (2 per SM)
@@ -497,7 +532,7 @@ static int dispatch_bwd_impl(const void* dxq, void* const* peer, const int32_t* 
           cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
           if (e != cudaSuccess) return (int)e;
         }
-        kern<<<grid, kPermThreads, smem, st>>>(q, pos, T, K, D, dz, w_gate, E, (TB*)dx);
+        launch_k(kern, grid, kPermThreads, smem, st, q, pos, T, K, D, dz, w_gate, E, (TB*)dx);
       })
     })
   }

@@ -24,6 +24,8 @@ __global__ void __launch_bounds__(kRouteThreads)
 route_count_kernel(const int64_t* __restrict__ idx, int R, int E, int32_t* __restrict__ block_hist) {
   extern __shared__ int hist[];
   for (int e = threadIdx.x; e < E; e += kRouteThreads) hist[e] = 0;
+  pdl_wait();
+  pdl_trigger();
   __syncthreads();
   const int base = blockIdx.x * kRouteChunk;
   for (int i = threadIdx.x; i < kRouteChunk; i += kRouteThreads) {
@@ -50,6 +52,8 @@ route_assign_kernel(const int64_t* __restrict__ idx, int R, int E, int pad, int 
   int* off = pre + E;                // [E+1] padded offsets
   int* bh = off + E + 1;             // [kRouteBatches][E] per-warp-batch histogram / prefix
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  pdl_wait();
+  pdl_trigger();
   const int b = blockIdx.x;
 
   for (int i = tid; i < 2 * E; i += kRouteThreads) sm[i] = 0;
@@ -210,12 +214,11 @@ extern "C" int m3_route_plan(const int64_t* idx, int T, int K, int E, int pad, c
   if (nblk < 1) nblk = 1;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   int32_t* block_hist = static_cast<int32_t*>(workspace);
-  route_count_kernel<<<nblk, kRouteThreads, E * sizeof(int), st>>>(idx, R, E, block_hist);
+  launch_k(route_count_kernel, nblk, kRouteThreads, E * sizeof(int), st, idx, R, E, block_hist);
   M3_LAUNCH_CHECK();
   const size_t smem = (size_t)(3 * E + 1 + kRouteBatches * E + 2 * kRouteThreads) * sizeof(int);
-  route_assign_kernel<<<nblk, kRouteThreads, smem, st>>>(idx, R, E, pad, nblk, block_hist, imp_partial, load_partial,
-                                                          n_partial, counts, offsets, pos, tile_expert, importance,
-                                                          load, cv_loss);
+  launch_k(route_assign_kernel, nblk, kRouteThreads, smem, st, idx, R, E, pad, nblk, block_hist, imp_partial,
+           load_partial, n_partial, counts, offsets, pos, tile_expert, importance, load, cv_loss);
   M3_LAUNCH_CHECK();
   return M3_OK;
 }

@@ -15,6 +15,39 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
 
+// Debug timeline (m3_debug_trace_buffer): {tag, clock64} pairs written by CTA 0 with plain stores (no atomics: an
+// atomic round trip per event costs ~1000 clk and drowns what is being measured).  Role r (0 producer, 1 MMA,
+// 2 epilogue warp 0) owns events [r*cap, (r+1)*cap) and counts them in a register; buf[r] = its final count.
+extern unsigned long long* g_trace_buf;   // abi.cu
+extern int g_trace_cap;
+struct Tracer {
+  unsigned long long* buf;
+  int cap, role, n;
+  __device__ __forceinline__ Tracer(unsigned long long* b, int c, int r)
+      : buf((blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && (threadIdx.x & 31) == 0) ? b : nullptr),
+        cap(c), role(r), n(0) {}
+  __device__ __forceinline__ void ev(uint32_t tag, uint32_t j) {
+    if (buf != nullptr && n < cap) {
+      unsigned long long* e = buf + 4 + 2 * ((size_t)role * cap + n);
+      e[0] = ((unsigned long long)tag << 32) | j;
+      e[1] = (unsigned long long)clock64();
+      ++n;
+    }
+  }
+  __device__ __forceinline__ void done() { if (buf != nullptr) buf[role] = (unsigned long long)n; }
+};
+
+// explicit shared-space 128-bit accesses: pointers carved out of the dynamic smem block by integer arithmetic lose
+// their address space and compile to GENERIC LD.E / ST.E (long-scoreboard latency); these stay LDS / STS
+__device__ __forceinline__ void sts128(uint32_t addr, const uint4& v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+
 // ----------------------------------------------------------------- mbarrier
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
@@ -197,6 +230,102 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t 
   d |= (uint64_t)1 << 46;
   d |= (uint64_t)2 << 61;
   return d;
+}
+
+// ------------------------------------------------ lean MMA issue (whole warp converged, one elected lane issues)
+// The issuing warp runs its loop CONVERGED (all 32 lanes wait on the mbarriers and do the - warp-uniform - descriptor
+// arithmetic), and only the tcgen05 instruction itself is predicated on elect.sync.  Inside an `if (lane == 0)` region
+// ptxas cannot prove uniformity and wraps EVERY uniform-datapath instruction (UTCHMMA, UTCBAR, UTMALDG) in an
+// ELECT / R2UR.BROADCAST / BRA.U.ANY loop and recomputes the 64-bit descriptors from scratch: ~17 SASS instructions
+// per MMA, 700 clk per 4-MMA k-chunk - the single issuing thread, not HBM or shared memory, bounded every GEMM here.
+// Descriptors are passed as {lo, hi} halves: hi is loop-invariant, lo = base_lo + ((byte offset) >> 4).
+__device__ __forceinline__ uint32_t smem_desc_lo(uint32_t smem_addr, uint32_t lbo_bytes) {
+  return ((smem_addr & 0x3FFFFu) >> 4) | (((lbo_bytes >> 4) & 0x3FFFu) << 16);
+}
+__device__ __forceinline__ uint32_t smem_desc_hi(uint32_t sbo_bytes) {
+  return ((sbo_bytes >> 4) & 0x3FFFu) | (1u << 14) | (2u << 29);     // version 1, SWIZZLE_128B
+}
+__device__ __forceinline__ void umma_bf16_elect(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo,
+                                                uint32_t b_hi, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p, q;\n"
+      ".reg .b64 da, db;\n"
+      "elect.sync _|q, 0xffffffff;\n"
+      "mov.b64 da, {%1, %2};\n"
+      "mov.b64 db, {%3, %4};\n"
+      "setp.ne.b32 p, %6, 0;\n"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n"
+      "}\n" ::"r"(d_tmem),
+      "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_bf16_2sm_elect(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo,
+                                                    uint32_t b_hi, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p, q;\n"
+      ".reg .b64 da, db;\n"
+      "elect.sync _|q, 0xffffffff;\n"
+      "mov.b64 da, {%1, %2};\n"
+      "mov.b64 db, {%3, %4};\n"
+      "setp.ne.b32 p, %6, 0;\n"
+      "@q tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %5, p;\n"
+      "}\n" ::"r"(d_tmem),
+      "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_elect(uint64_t* bar) {
+  asm volatile(
+      "{\n"
+      ".reg .pred q;\n"
+      "elect.sync _|q, 0xffffffff;\n"
+      "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n"
+      "}\n" ::"r"(smem_u32(bar))
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_2sm_elect(uint64_t* bar, uint16_t mask) {
+  asm volatile(
+      "{\n"
+      ".reg .pred q;\n"
+      "elect.sync _|q, 0xffffffff;\n"
+      "@q tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "h"(mask)
+      : "memory");
+}
+
+// elected-lane variants of the producer-side instructions (same converged-warp scheme)
+__device__ __forceinline__ void mbar_expect_tx_elect(uint64_t* bar, uint32_t bytes) {
+  asm volatile(
+      "{\n.reg .pred q;\nelect.sync _|q, 0xffffffff;\n"
+      "@q mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n}\n" ::"r"(smem_u32(bar)), "r"(bytes)
+      : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_elect(uint64_t* bar) {
+  asm volatile("{\n.reg .pred q;\nelect.sync _|q, 0xffffffff;\n@q mbarrier.arrive.shared::cta.b64 _, [%0];\n}\n" ::"r"(
+                   smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_remote_elect(uint32_t cluster_addr) {
+  asm volatile("{\n.reg .pred q;\nelect.sync _|q, 0xffffffff;\n@q mbarrier.arrive.shared::cluster.b64 _, [%0];\n}\n" ::"r"(
+                   cluster_addr)
+               : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_elect(uint32_t smem_dst, const CUtensorMap* m, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "{\n.reg .pred q;\nelect.sync _|q, 0xffffffff;\n"
+      "@q cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];\n}\n"
+      ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_2sm_elect(uint32_t smem_dst, const CUtensorMap* m, uint32_t bar_cluster_addr,
+                                                      int c0, int c1) {
+  asm volatile(
+      "{\n.reg .pred q;\nelect.sync _|q, 0xffffffff;\n"
+      "@q cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];\n}\n"
+      ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_cluster_addr), "r"(c0), "r"(c1)
+      : "memory");
 }
 
 // ------------------------------------------------------------- tcgen05.ld

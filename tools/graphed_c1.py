@@ -25,6 +25,7 @@ class TaskCall(nn.Module):
 
 def main():
     dev = torch.device("cuda:0")
+    print("M3_KNOBS =", os.environ.get("M3_KNOBS", "(defaults)"))
     D = H = 384
     for B in (2, 8):
         T = B * 1201

@@ -1,0 +1,143 @@
+"""A/B timing of the tuning knobs (m3_set_knob) at bench size, in one process:
+    python tools/variants.py [batch]
+CUDA events, L2 flushed between iterations; also checks that every variant gives the same bits as the default."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import bench
+from m3vit_b200 import ops, _lib
+
+KNOB_PDL, KNOB_EPI, KNOB_MOVER = 0, 1, 2
+lib = _lib.load()
+dev = torch.device("cuda:0")
+B = int(sys.argv[1]) if len(sys.argv) > 1 else 32
+T, D, H, K, E = B * bench.N_TOK, bench.D_MODEL, bench.D_HID, bench.TOP_K, bench.N_EXP
+layers = bench.build_layers(dev, torch.bfloat16)
+layer = layers[0]
+from m3vit_b200.synthetic import device_tokens
+x = device_tokens(T, D, 0, dev)
+wg = layer.gate[0].w_gate.detach()
+b1, b2 = layer.experts.htoh4.bias.detach(), layer.experts.h4toh.bias.detach()
+w1c, w2c, w1t, w2t = layer._wcache.get_bf16(layer.experts.htoh4.weight, layer.experts.h4toh.weight)
+g = ops.gate_fwd(x, wg, K)
+plan = ops.route_plan(g.idx, E, imp_partial=g.imp_partial, load_partial=g.load_partial)
+xq = ops.dispatch_fwd(x, plan, K, out_dtype=torch.bfloat16)
+yq, hpre = ops.ffn_fwd(xq, plan, w1c, b1, w2c, b2)
+go = torch.randn(T, D, device=dev)
+dyq, dscore = ops.combine_bwd(go, yq, plan, g.score)
+flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+
+def timed(name, fn, iters=20):
+    for _ in range(3):
+        fn()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    tot = 0.0
+    for _ in range(iters):
+        flush.zero_(); a.record(); fn(); b.record(); b.synchronize(); tot += a.elapsed_time(b)
+    print(f"{name:58s} {tot / iters * 1e3:8.1f} us", flush=True)
+
+
+ROWS = int(plan.offsets[-1].item())      # queue rows in use (the tail of the capacity buffer is never written)
+
+
+def same(a, b):
+    if isinstance(a, (tuple, list)):
+        return all(same(u, v) for u, v in zip(a, b))
+    if a is None or b is None:
+        return a is b
+    if a.dim() >= 2 and a.shape[0] >= ROWS and a.dtype == torch.bfloat16:
+        return torch.equal(a.reshape(a.shape[0], -1)[:ROWS], b.reshape(b.shape[0], -1)[:ROWS])
+    return torch.equal(a, b)
+
+
+print(f"T={T} D={D} H={H} E={E} K={K} rows={ROWS}")
+KNOB_GATE = 3
+ref_g = ops.gate_fwd(x, wg, K)
+for cfg in (0, 1, 2, 3, 4):
+    lib.m3_set_knob(KNOB_GATE, cfg)
+    og = ops.gate_fwd(x, wg, K)
+    torch.cuda.synchronize()
+    print(f"  [gate cfg knob {cfg}] idx equal {torch.equal(og.idx, ref_g.idx)} score equal {torch.equal(og.score, ref_g.score)}")
+    timed(f"gate_fwd [cfg knob {cfg}]", lambda: ops.gate_fwd(x, wg, K))
+lib.m3_set_knob(KNOB_GATE, 0)
+timed("dispatch_fwd", lambda: ops.dispatch_fwd(x, plan, K, out_dtype=torch.bfloat16))
+dxq_ = torch.randn_like(xq)
+dz_ = torch.randn(T, E, device=dev)
+timed("dispatch_bwd (no router term)", lambda: ops.dispatch_bwd(dxq_, plan, T, K))
+timed("dispatch_bwd (+ dz @ w_gate^T)", lambda: ops.dispatch_bwd(dxq_, plan, T, K, dz=dz_, w_gate=wg))
+timed("gate_bwd", lambda: ops.gate_bwd(x, wg, g.noisy_logits, g.idx_full, K, dscore=g.score))
+timed("route_plan", lambda: ops.route_plan(g.idx, E, imp_partial=g.imp_partial, load_partial=g.load_partial))
+timed("torch x.clone() (59 MB read + 59 MB write)", lambda: x.clone())
+
+# ---------------- GEMM epilogue warps: value 0x100 | mask (bit EPI set -> 16 warps); EPI 0 store 1 bias 2 fc1 3 dgelu
+ref_f = ops.ffn_fwd(xq, plan, w1c, b1, w2c, b2)
+ref_b = ops.ffn_bwd(xq, hpre, dyq, plan, w1c, w2c, w1t, w2t)
+KNOB_DEBUG = 4
+for dbg, name in ((0, "normal"), (1, "no MMAs (loads + epilogue only)"), (2, "no TMA loads (MMAs + epilogue only)"), (3, "neither (epilogue + handshakes)"),
+                  (4, "no epilogue (loads + MMAs)"), (5, "loads only"), (6, "MMAs only"), (7, "handshakes only")):
+    lib.m3_set_knob(KNOB_DEBUG, dbg)
+    timed(f"ffn_fwd (fc1+fc2)      [{name}]", lambda: ops.ffn_fwd(xq, plan, w1c, b1, w2c, b2))
+    timed(f"ffn_bwd (2 dgrad+2 wg) [{name}]", lambda: ops.ffn_bwd(xq, hpre, dyq, plan, w1c, w2c, w1t, w2t))
+lib.m3_set_knob(KNOB_DEBUG, 0)
+for mask, name in ((0, "8 warps everywhere"), (4, "fc1:16")):
+    lib.m3_set_knob(KNOB_EPI, 0x100 | mask)
+    of = ops.ffn_fwd(xq, plan, w1c, b1, w2c, b2)
+    ob = ops.ffn_bwd(xq, hpre, dyq, plan, w1c, w2c, w1t, w2t)
+    torch.cuda.synchronize()
+    print(f"  [{name}] bits equal to default: fwd {same(of, ref_f)}  bwd {same(ob, ref_b)}")
+    timed(f"ffn_fwd (fc1+fc2)      [{name}]", lambda: ops.ffn_fwd(xq, plan, w1c, b1, w2c, b2))
+    timed(f"ffn_bwd (2 dgrad+2 wg) [{name}]", lambda: ops.ffn_bwd(xq, hpre, dyq, plan, w1c, w2c, w1t, w2t))
+lib.m3_set_knob(KNOB_EPI, 0)
+
+# ---------------- combine fwd / bwd variants
+ref_c = ops.combine_fwd(yq, plan, g.score)
+ref_cb = ops.combine_bwd(go, yq, plan, g.score)
+for var, name in ((0, "default (fwd GK2 minb4, bwd GK4)"), (1, "GK2 minb3"), (3, "GK2 minb4")):
+    lib.m3_set_knob(KNOB_MOVER, var)
+    oc = ops.combine_fwd(yq, plan, g.score)
+    ocb = ops.combine_bwd(go, yq, plan, g.score)
+    torch.cuda.synchronize()
+    print(f"  [{name}] bits equal: combine_fwd {same(oc, ref_c)}  combine_bwd {same(ocb, ref_cb)}")
+    timed(f"combine_fwd [{name}]", lambda: ops.combine_fwd(yq, plan, g.score))
+    timed(f"combine_bwd [{name}]", lambda: ops.combine_bwd(go, yq, plan, g.score))
+lib.m3_set_knob(KNOB_MOVER, 0)
+
+# ---------------- whole step (12 layer calls fwd+bwd), PDL on / off
+calls = [(li, t) for t in range(bench.N_TASK) for li in range(bench.N_LAYER)]
+xs = [device_tokens(T, D, i, dev).requires_grad_(True) for i in range(len(calls))]
+gs = [torch.randn(T, D, device=dev) * 0.01 for _ in range(2)]
+
+
+def step():
+    for l in layers:
+        for p_ in l.parameters():
+            p_.grad = None
+    for i, (li, t) in enumerate(calls):
+        xs[i].grad = None
+        bench.one_call(layers[li], xs[i], gs[i & 1], t)
+
+
+def time_step(name, n=10):
+    for _ in range(3):
+        step()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(n):
+        step()
+    b.record(); b.synchronize()
+    ms = a.elapsed_time(b) / n
+    print(f"step {name:52s} {ms:8.3f} ms  -> {len(calls) * T / ms / 1e3:7.2f} M tokens/s", flush=True)
+    return [xs[0].grad.clone(), layers[0].experts.htoh4.weight.grad.clone(), layers[0].gate[0].w_gate.grad.clone()]
+
+
+for rep in range(3):
+    lib.m3_set_knob(KNOB_EPI, 0x100)
+    time_step("fc1: 8 warps")
+    lib.m3_set_knob(KNOB_EPI, 0)
+    time_step("fc1:16 warps (default)")
+lib.m3_set_knob(KNOB_PDL, 1)
+time_step("PDL on")
+lib.m3_set_knob(KNOB_PDL, 0)
+time_step("PDL off (default)")
