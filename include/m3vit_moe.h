@@ -174,9 +174,12 @@ int m3_set_gemm_sm_limit(int sms);
  *   M3_KNOB_DEBUG     measurement only (results are garbage): tcgen05 GEMMs run 1 = without MMAs, 2 = without TMA loads.
  *   M3_KNOB_TRACE_KERNEL  1 + index of the GEMM launch inside one m3_ffn_fwd / m3_ffn_bwd call that m3_debug_trace_buffer
  *                     records (0 = every launch).
- *   M3_KNOB_MOVER_VARIANT  0 (default) or an experimental rows-in-flight / occupancy variant of combine fwd/bwd.
+ *   M3_KNOB_BRES      1: grouped GEMMs with Kd <= 384 keep the expert's weight tile resident in shared memory and stream
+ *                     activations only (bit-identical, measured slower); 0 (default): both operands are streamed.
+ *   M3_KNOB_MOVER_VARIANT  0 (default) or an experimental rows-in-flight / occupancy variant of combine fwd/bwd;
+ *                     9: dispatch_bwd keeps the SIMT fp32 router term for bf16 queues too (default: mma.sync bf16).
  * Returns the previous value, or M3_ERR_ARG for an unknown knob. */
-typedef enum { M3_KNOB_PDL = 0, M3_KNOB_EPI_WARPS = 1, M3_KNOB_MOVER_VARIANT = 2, M3_KNOB_GATE_CFG = 3, M3_KNOB_DEBUG = 4, M3_KNOB_TRACE_KERNEL = 5, M3_KNOB_COUNT_ = 8 } m3_knob;
+typedef enum { M3_KNOB_PDL = 0, M3_KNOB_EPI_WARPS = 1, M3_KNOB_MOVER_VARIANT = 2, M3_KNOB_GATE_CFG = 3, M3_KNOB_DEBUG = 4, M3_KNOB_TRACE_KERNEL = 5, M3_KNOB_BRES = 6, M3_KNOB_COUNT_ = 8 } m3_knob;
 int m3_set_knob(int knob, int value);
 int m3_ffn_fwd(int dtype, const void* xq, const int32_t* offsets, const int32_t* tile_expert,
                int cap_rows, int E, int D, int H, const void* w1, const float* b1, const void* w2,

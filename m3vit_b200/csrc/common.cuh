@@ -81,6 +81,21 @@ __device__ __forceinline__ void stg_stream(void* p, const uint4& v) {
                : "memory");
 }
 
+// 256-bit variants (sm_100: LDG.256 / STG.256): one full 32-byte sector per lane
+struct U8 { uint32_t v[8]; };
+__device__ __forceinline__ U8 ldg_stream256(const void* p) {
+  U8 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r.v[0]), "=r"(r.v[1]), "=r"(r.v[2]), "=r"(r.v[3]), "=r"(r.v[4]), "=r"(r.v[5]), "=r"(r.v[6]), "=r"(r.v[7])
+               : "l"(p));
+  return r;
+}
+__device__ __forceinline__ void stg_stream256(void* p, const U8& r) {
+  asm volatile("st.global.L1::no_allocate.v8.u32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(r.v[0]), "r"(r.v[1]),
+               "r"(r.v[2]), "r"(r.v[3]), "r"(r.v[4]), "r"(r.v[5]), "r"(r.v[6]), "r"(r.v[7])
+               : "memory");
+}
+
 __device__ __forceinline__ float2 bf16x2_to_float2(uint32_t u) {
   __nv_bfloat162 h = *reinterpret_cast<__nv_bfloat162*>(&u);
   return __bfloat1622float2(h);

@@ -51,22 +51,30 @@ struct GGParams {
   int trace_cap;
 };
 
-template <int BN, int EPI, int NCTA, int EW>
+// BRES ("B resident", opt-in: M3_KNOB_BRES = 1): the weight tile of one (expert, N-tile) stays in shared memory across
+// all the M-tiles a unit computes for that expert; the ring then carries A only (43 % fewer L2 -> SM bytes at Kd = 384).
+// Bit-identical to the streaming kernel, but measured SLOWER (fc2 81 vs 50 us): the A stream from DRAM, not the SM's
+// inbound bandwidth, paces the ring - its latency just grows with the extra stages (tools/gemm_timeline.py).
+constexpr int kBresMaxChunks = 6;      // Kd <= 384: 6 x (BN/2 rows x 128 B) = 72 KB of resident weights per CTA at BN = 192
+
+template <int BN, int EPI, int NCTA, int EW, bool BRES>
 struct GGCfg {
   static constexpr int CW = EW == 16 ? 32 : 64;               // columns per epilogue register block
   static constexpr int WBOX_BYTES = 32 * CW * 2;              // one warp's [32 rows][CW bf16] swizzled box (4 / 2 KB)
   static constexpr int A_BYTES = BM * BK * 2;
   static constexpr int B_BYTES = (BN / NCTA) * BK * 2;      // a CTA pair splits the B tile
-  static constexpr int STAGE = A_BYTES + B_BYTES;
+  static constexpr int BRES_BYTES = BRES ? kBresMaxChunks * B_BYTES : 0;
+  static constexpr int STAGE = BRES ? A_BYTES : A_BYTES + B_BYTES;
   // epilogue staging: one private 4 KB box per epilogue warp per output tensor (+ per TMA-loaded aux input)
   static constexpr int N_OUT = 1;                            // outputs share one transpose box, flushed in turn
   static constexpr int N_AUX = (EPI == EPI_DGELU) ? 1 : 0;   // EPI_DGELU: gelu'(pre-activation) saved by fc1
   static constexpr int WARP_STAGING = (N_OUT + N_AUX) * WBOX_BYTES;
   static constexpr int STAGING = EW * WARP_STAGING;
-  static constexpr int BUDGET = 227 * 1024 - 1024 - 512 - STAGING;
-  static constexpr int STAGES = (BUDGET / STAGE) < 6 ? (BUDGET / STAGE) : 6;
+  static constexpr int BUDGET = 227 * 1024 - 1024 - 512 - STAGING - BRES_BYTES;
+  static constexpr int MAX_STAGES = BRES ? 8 : 6;
+  static constexpr int STAGES = (BUDGET / STAGE) < MAX_STAGES ? (BUDGET / STAGE) : MAX_STAGES;
   static constexpr int TMEM_COLS = (2 * BN <= 256) ? 256 : 512;
-  static constexpr int SMEM = STAGES * STAGE + STAGING + 1024 /*align slack*/ + 512 /*barriers*/;
+  static constexpr int SMEM = STAGES * STAGE + BRES_BYTES + STAGING + 1024 /*align slack*/ + 512 /*barriers*/;
   static_assert(STAGES >= 3, "smem ring too shallow");
 };
 
@@ -88,12 +96,12 @@ __device__ __forceinline__ uint32_t box_off(int r, int c) {
   return (uint32_t)r * 64u + (uint32_t)((c ^ ((r >> 1) & 3)) << 4);
 }
 
-template <int BN, int EPI, int NCTA, int EW>
+template <int BN, int EPI, int NCTA, int EW, bool BRES>
 __global__ void __launch_bounds__(gg_threads(EW), 1)
 gg_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
           const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmOut2,
           const __grid_constant__ CUtensorMap tmAux, GGParams p) {
-  using Cfg = GGCfg<BN, EPI, NCTA, EW>;
+  using Cfg = GGCfg<BN, EPI, NCTA, EW, BRES>;
   constexpr int kEpiWarps = EW;
   constexpr int CW = Cfg::CW, WBOX_BYTES = Cfg::WBOX_BYTES;
   constexpr int NQ = EW / 8;            // warps sharing one (TMEM lane quarter, accumulator buffer)
@@ -106,13 +114,17 @@ gg_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
   static_assert(BN % (CW * NQ) == 0, "tile width vs epilogue blocks");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* stg = smem + STAGES * Cfg::STAGE;                 // staging boxes (1024-aligned)
+  uint8_t* bres = smem + STAGES * Cfg::STAGE;                // BRES: resident weight chunks [kchunks][BN/NCTA rows][64]
+  uint8_t* stg = bres + Cfg::BRES_BYTES;                     // staging boxes (1024-aligned)
   uint64_t* full = reinterpret_cast<uint64_t*>(stg + Cfg::STAGING);
   uint64_t* empty = full + STAGES;
   uint64_t* tfull = empty + STAGES;
   uint64_t* tempty = tfull + 2;
   uint64_t* aux_full = tempty + 2;                            // [kEpiWarps]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(aux_full + kEpiWarps);
+  uint64_t* fullB = aux_full + kEpiWarps;                     // [kBresMaxChunks] resident weight chunk loaded
+  uint64_t* emptyB = fullB + kBresMaxChunks;                  // [kBresMaxChunks] ... no longer read by any MMA
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(emptyB + kBresMaxChunks);
+  static_assert((2 * STAGES + 4 + EW + 2 * kBresMaxChunks) * 8 + 4 <= 512, "barrier block");
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (warp == 0 && lane == 0) {
@@ -124,6 +136,7 @@ gg_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
       for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], NCTA); mbar_init(&empty[s], 1); }
       for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], NCTA * (EW / 2) * 32); }
       for (int w = 0; w < kEpiWarps; ++w) mbar_init(&aux_full[w], 1);
+      for (int c = 0; c < kBresMaxChunks; ++c) { mbar_init(&fullB[c], NCTA); mbar_init(&emptyB[c], 1); }
       fence_barrier_init();
     }
     __syncwarp();
@@ -139,37 +152,69 @@ gg_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
   pdl_wait();
   pdl_trigger();
 
-  // Tile schedule: a "unit" (CTA or CTA pair) walks pair-tiles pt = unit, unit + n_units, ...;
-  // pair-tile pt covers M-tiles (pt / n_tiles) * NCTA + cta_rank (queues are padded to NCTA*128 rows,
-  // so both halves of a pair belong to the same expert) and N-tile pt % n_tiles.
+  // Tile schedule.  A "unit" (CTA or CTA pair) computes `my_tiles` pair-tiles, local index i = 0 .. my_tiles-1:
+  //   streaming (BRES = false): pair-tile pt = unit + i * n_units covers M-tiles (pt / n_tiles) * NCTA + cta_rank (queues
+  //     are padded to NCTA*128 rows, so both halves of a pair belong to the same expert) and N-tile pt % n_tiles;
+  //   BRES: unit = su * n_tiles + n keeps N-tile n for its whole life and walks the CONTIGUOUS M-pair-tiles
+  //     [mp0, mp1) of "super-unit" su, so consecutive tiles mostly share the expert (= the resident weights); the
+  //     n_tiles units of a super-unit run in lockstep over the same rows (the second reader of an A tile hits L2).
   const int n_tiles = p.N / BN;
   const int m_tiles = p.offsets[p.E] / BM;
-  const int total = (m_tiles / NCTA) * n_tiles;
   const int kchunks = p.Kd / BK;
   const int unit = blockIdx.x / NCTA, n_units = gridDim.x / NCTA;
+  const int total = (m_tiles / NCTA) * n_tiles;
+  int my_tiles, mp0 = 0;
+  if (BRES) {
+    const int n_su = n_units / n_tiles, su = unit / n_tiles, mt = m_tiles / NCTA;
+    const bool active = su < n_su;
+    mp0 = active ? (int)((int64_t)su * mt / n_su) : 0;
+    my_tiles = active ? (int)((int64_t)(su + 1) * mt / n_su) - mp0 : 0;
+  } else {
+    my_tiles = unit < total ? (total - unit + n_units - 1) / n_units : 0;
+  }
+  // local tile index -> (M-tile of this CTA, N-tile)
+  auto tile_mblk = [&](int i) { return BRES ? (mp0 + i) * NCTA + (int)cta_rank : ((unit + i * n_units) / n_tiles) * NCTA + (int)cta_rank; };
+  auto tile_nblk = [&](int i) { return BRES ? unit % n_tiles : (unit + i * n_units) % n_tiles; };
 
   // Producer and MMA warps run their loops CONVERGED (all 32 lanes); every TMA / MMA / commit / arrive is issued by one
   // elected lane inside its asm block (tc_common.cuh: the single-thread `if (lane == 0)` form cost ~700 clk of scalar
   // code per 4-MMA k-chunk and bounded every GEMM of the layer).
   // Both loops walk the smem ring in rounds of STAGES k-chunks with the stage index a compile-time constant (every
   // barrier address and descriptor is base + immediate); the flat chunk index f runs over all tiles of this unit.
-  const int my_tiles = unit < total ? (total - unit + n_units - 1) / n_units : 0;
   const int F = my_tiles * kchunks;
   if (warp == 0) {
-    const uint32_t smem_base = smem_u32(smem);
+    const uint32_t smem_base = smem_u32(smem), bres_base = smem_u32(bres);
     const bool no_tma = (p.dbg & 2) != 0;
     const uint32_t full0 = NCTA == 2 ? mapa_u32(smem_u32(&full[0]), 0) : smem_u32(&full[0]);   // leader's barriers
+    const uint32_t fullB0 = NCTA == 2 ? mapa_u32(smem_u32(&fullB[0]), 0) : smem_u32(&fullB[0]);
     Tracer trc(p.trace, p.trace_cap, 0);
     uint32_t phase = 0;
-    int tile = unit, kc = 0, m_blk = 0, b_row = 0;
+    int ti = 0, kc = 0, m_blk = 0, b_row = 0;
+    int cur_e = -1, n_loadB = 0;      // BRES: expert whose weights are resident, number of weight loads issued so far
+    bool loadB = false;
     for (int f0 = 0; f0 < F; f0 += STAGES) {
 #pragma unroll
       for (int st = 0; st < STAGES; ++st) {
         if (f0 + st < F) {
           if (kc == 0) {
-            m_blk = (tile / n_tiles) * NCTA + (int)cta_rank;
+            m_blk = tile_mblk(ti);
             const int e = p.tile_expert[(m_blk * BM) / M3_PAD_ROWS];
-            b_row = e * p.N + (tile % n_tiles) * BN + (int)cta_rank * (BN / NCTA);
+            b_row = e * p.N + tile_nblk(ti) * BN + (int)cta_rank * (BN / NCTA);
+            loadB = BRES && e != cur_e;
+            cur_e = e;
+          }
+          if (BRES && loadB) {
+            // weight chunk kc of the new expert: the MMAs of the previous expert's LAST tile must be done with the slot
+            if (n_loadB > 0) mbar_wait(&emptyB[kc], (uint32_t)(n_loadB - 1) & 1u);
+            __syncwarp();
+            const uint32_t barB = fullB0 + kc * 8;
+            if (NCTA == 2) {
+              if (leader_cta) mbar_expect_tx_elect(&fullB[kc], Cfg::B_BYTES * NCTA); else mbar_arrive_remote_elect(barB);
+              tma_load_2d_2sm_elect(bres_base + kc * Cfg::B_BYTES, &tmB, barB, kc * BK, b_row);
+            } else {
+              mbar_expect_tx_elect(&fullB[kc], Cfg::B_BYTES);
+              tma_load_2d_elect(bres_base + kc * Cfg::B_BYTES, &tmB, barB, kc * BK, b_row);
+            }
           }
           trc.ev(0x00, f0 + st);
           mbar_wait(&empty[st], phase ^ 1);
@@ -184,14 +229,18 @@ gg_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
               if (leader_cta) mbar_expect_tx_elect(&full[st], Cfg::STAGE * NCTA);
               else mbar_arrive_remote_elect(bar);
               tma_load_2d_2sm_elect(sa, &tmA, bar, kc * BK, m_blk * BM);
-              tma_load_2d_2sm_elect(sa + Cfg::A_BYTES, &tmB, bar, kc * BK, b_row);
+              if (!BRES) tma_load_2d_2sm_elect(sa + Cfg::A_BYTES, &tmB, bar, kc * BK, b_row);
             }
           } else {
             mbar_expect_tx_elect(&full[st], Cfg::STAGE);
             tma_load_2d_elect(sa, &tmA, bar, kc * BK, m_blk * BM);
-            tma_load_2d_elect(sa + Cfg::A_BYTES, &tmB, bar, kc * BK, b_row);
+            if (!BRES) tma_load_2d_elect(sa + Cfg::A_BYTES, &tmB, bar, kc * BK, b_row);
           }
-          if (++kc == kchunks) { kc = 0; tile += n_units; }
+          if (++kc == kchunks) {
+            kc = 0;
+            ++ti;
+            if (loadB) ++n_loadB;
+          }
         }
       }
       phase ^= 1;
@@ -204,9 +253,12 @@ gg_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
       const uint32_t tm = __shfl_sync(0xffffffffu, tmem_base, 0);
       // K-major operand tiles [rows][64 bf16], SWIZZLE_128B: 8-row groups 1024 B apart (SBO); K advances 32 B per UMMA_K
       const uint32_t a_lo0 = smem_desc_lo(smem_u32(smem), 0), hi = smem_desc_hi(1024);
+      const uint32_t bres_lo0 = smem_desc_lo(smem_u32(bres), 0);
       const bool no_mma = (p.dbg & 1) != 0;
       uint32_t phase = 0, acc = 0, acc_phase = 0, d_tmem = tm;
-      int kc = 0;
+      int kc = 0, ti = 0;
+      int cur_e = -1, n_loadB = 0;       // BRES: mirrors the producer's weight-load sequence
+      bool newB = false, lastB = false;  // first / last tile computed with the resident weights
       for (int f0 = 0; f0 < F; f0 += STAGES) {
 #pragma unroll
         for (int st = 0; st < STAGES; ++st) {
@@ -216,12 +268,21 @@ gg_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
               mbar_wait(&tempty[acc], acc_phase ^ 1);
               trc.ev(0x11, f0 + st);
               d_tmem = tm + acc * BN;
+              if (BRES) {
+                const int e = p.tile_expert[(tile_mblk(ti) * BM) / M3_PAD_ROWS];
+                const int e_next = ti + 1 < my_tiles ? p.tile_expert[(tile_mblk(ti + 1) * BM) / M3_PAD_ROWS] : -1;
+                newB = e != cur_e;
+                lastB = e_next != e;
+                cur_e = e;
+              }
             }
+            if (BRES && newB) mbar_wait(&fullB[kc], (uint32_t)n_loadB & 1u);
             mbar_wait(&full[st], phase);
             trc.ev(0x12, f0 + st);
             __syncwarp();
             tcgen05_fence_after();
-            const uint32_t a_lo = a_lo0 + (uint32_t)st * (Cfg::STAGE >> 4), b_lo = a_lo + (Cfg::A_BYTES >> 4);
+            const uint32_t a_lo = a_lo0 + (uint32_t)st * (Cfg::STAGE >> 4);
+            const uint32_t b_lo = BRES ? bres_lo0 + (uint32_t)kc * (Cfg::B_BYTES >> 4) : a_lo + (Cfg::A_BYTES >> 4);
             if (!no_mma) {
 #pragma unroll
               for (int k = 0; k < BK / UMMA_K; ++k) {
@@ -231,11 +292,16 @@ gg_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
             }
             // frees the smem stage (in both CTAs of a pair) once these MMAs have read it
             if (NCTA == 2) umma_commit_2sm_elect(&empty[st], 3); else umma_commit_elect(&empty[st]);
+            if (BRES && lastB) {   // ... and the resident weight chunk, after the last tile that uses it
+              if (NCTA == 2) umma_commit_2sm_elect(&emptyB[kc], 3); else umma_commit_elect(&emptyB[kc]);
+            }
             trc.ev(0x13, f0 + st);
             if (++kc == kchunks) {
               // accumulator complete -> epilogue warps (of both CTAs)
               if (NCTA == 2) umma_commit_2sm_elect(&tfull[acc], 3); else umma_commit_elect(&tfull[acc]);
               kc = 0;
+              ++ti;
+              if (newB) ++n_loadB;
               acc ^= 1;
               if (acc == 0) acc_phase ^= 1;
             }
@@ -275,16 +341,13 @@ gg_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
       __syncwarp();
     };
     uint32_t aux_uses = 0;
-    const int first = unit + (int)grp * n_units;
     const uint32_t tempty_remote = NCTA == 2 ? mapa_u32(smem_u32(&tempty[grp]), 0) : 0u;
-    if (EPI == EPI_DGELU && lane == 0 && first < total) {
+    if (EPI == EPI_DGELU && lane == 0 && (int)grp < my_tiles) {
       mbar_expect_tx(my_aux, WBOX_BYTES);
-      tma_load_2d(ax, &tmAux, my_aux, (first % n_tiles) * BN + sub * CW,
-                  ((first / n_tiles) * NCTA + (int)cta_rank) * BM + q * 32);
+      tma_load_2d(ax, &tmAux, my_aux, tile_nblk(grp) * BN + sub * CW, tile_mblk(grp) * BM + q * 32);
     }
-    uint32_t it = grp;
-    for (int tile = first; tile < total; tile += 2 * n_units, it += 2) {
-      const int m_blk = (tile / n_tiles) * NCTA + (int)cta_rank, n_blk = tile % n_tiles;
+    for (uint32_t it = grp; (int)it < my_tiles; it += 2) {       // local tile index: this group serves every other tile
+      const int m_blk = tile_mblk(it), n_blk = tile_nblk(it);
       const int e = p.tile_expert[(m_blk * BM) / M3_PAD_ROWS];
       const int row0 = m_blk * BM + q * 32;
       if (ew == 0) trc.ev(0x20, it);
@@ -359,12 +422,11 @@ gg_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
           for (int c = 0; c < NCH; ++c) hraw[c] = lds128(ax32 + box_off<CW>(lane, c));
           __syncwarp();
           if (lane == 0) {  // aux box consumed into registers: prefetch the next one behind the math
-            int nt = tile, ncbi = cbi + 1;
-            if (ncbi == NBW) { ncbi = 0; nt += 2 * n_units; }
-            if (nt < total) {
+            int nt = (int)it, ncbi = cbi + 1;
+            if (ncbi == NBW) { ncbi = 0; nt += 2; }
+            if (nt < my_tiles) {
               mbar_expect_tx(my_aux, WBOX_BYTES);
-              tma_load_2d(ax, &tmAux, my_aux, (nt % n_tiles) * BN + (ncbi * NQ + sub) * CW,
-                          ((nt / n_tiles) * NCTA + (int)cta_rank) * BM + q * 32);
+              tma_load_2d(ax, &tmAux, my_aux, tile_nblk(nt) * BN + (ncbi * NQ + sub) * CW, tile_mblk(nt) * BM + q * 32);
             }
           }
 #pragma unroll
@@ -640,15 +702,21 @@ static int epi_warps() {
   return kDefaultEpiWarps[EPI];
 }
 
-template <int BN, int EPI, int EW>
+template <int BN, int EPI, int EW, bool BRES>
 static int launch_gg_t(const CUtensorMap* maps, const GGParams& p, int max_tiles, cudaStream_t st) {
-  using Cfg = GGCfg<BN, EPI, kGGNcta, EW>;
-  auto kern = gg_kernel<BN, EPI, kGGNcta, EW>;
+  using Cfg = GGCfg<BN, EPI, kGGNcta, EW, BRES>;
+  auto kern = gg_kernel<BN, EPI, kGGNcta, EW, BRES>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
   if (e != cudaSuccess) return (int)e;
   int grid = max_tiles < g_gemm_sms ? max_tiles : g_gemm_sms;
   grid = grid / kGGNcta * kGGNcta;
   if (grid < kGGNcta) grid = kGGNcta;
+  if (BRES) {   // units come in groups of n_tiles (one per N-tile) walking the same rows
+    const int n_tiles = p.N / BN;
+    int units = grid / kGGNcta / n_tiles * n_tiles;
+    if (units < n_tiles) return M3_ERR_SHAPE;     // caller checked
+    grid = units * kGGNcta;
+  }
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(grid);
   cfg.blockDim = dim3(gg_threads(EW));
@@ -694,16 +762,22 @@ static int launch_gg(const void* A, const void* B, void* out, void* out2, const 
   p.trace = trace_buf_for_this_launch();
   p.trace_cap = g_trace_cap;
   const int max_tiles = (cap_rows / BM) * (p.N / BN);
-#define M3_GG_EW(BNV)                                                                \
-  (ew == 16 ? launch_gg_t<BNV, EPI, 16>(maps, p, max_tiles, st) : launch_gg_t<BNV, EPI, 8>(maps, p, max_tiles, st))
+  // resident weights (BRES) where they fit: Kd <= 384, BN <= 192, and enough SMs for one unit per N-tile
+  const int usable = (max_tiles < g_gemm_sms ? max_tiles : g_gemm_sms) / kGGNcta;
+  const bool bres = g_knobs[M3_KNOB_BRES] == 1 && p.Kd / BK <= kBresMaxChunks && BN <= 192 && usable >= p.N / BN;
+#define M3_GG_EW(BNV)                                                                                                   \
+  (ew == 16 ? launch_gg_t<BNV, EPI, 16, false>(maps, p, max_tiles, st) : launch_gg_t<BNV, EPI, 8, false>(maps, p, max_tiles, st))
+#define M3_GG_EW_BRES(BNV)                                                                                              \
+  (ew == 16 ? launch_gg_t<BNV, EPI, 16, true>(maps, p, max_tiles, st) : launch_gg_t<BNV, EPI, 8, true>(maps, p, max_tiles, st))
   switch (BN) {
-    case 128: return M3_GG_EW(128);
-    case 192: return M3_GG_EW(192);
+    case 128: return bres ? M3_GG_EW_BRES(128) : M3_GG_EW(128);
+    case 192: return bres ? M3_GG_EW_BRES(192) : M3_GG_EW(192);
     default:
       if constexpr (!heavy) return M3_GG_EW(256);
       return M3_ERR_SHAPE;
   }
 #undef M3_GG_EW
+#undef M3_GG_EW_BRES
 }
 
 // out[i] = sum_s part[s][i] (fixed order), float4-wide

@@ -397,6 +397,119 @@ dispatch_bwd_gate_kernel(Queue<const TI> dxq, const int32_t* __restrict__ pos, i
   }
 }
 
+// bf16 queues: the same kernel with the router term on the tensor cores (mma.sync m16n8k16, bf16 x bf16 -> fp32).
+// The SIMT version above spends 2 B of shared-memory reads per FMA on w_gate and is bound by them (59 us for a
+// 27 us gather at T = 38 432); here a warp owns 16 tokens, dz[16 x E] is the A operand (fp32 -> bf16 on load), the
+// bf16 copy of w_gate[:D] sits in shared memory as the B operand, and the accumulator fragments of every 64-column
+// group are permuted so that lane (g, t) ends up with 16 CONTIGUOUS columns of tokens g and g+8: exactly the 32-byte
+// sector it gathers (one LDG.256) from each of the K queue rows of a token; the four lanes of a row cover one full
+// 128-byte line.  dz and w_gate are rounded to bf16 (like every other operand of the bf16 path: the queue rows being
+// summed are bf16 already); fp32 queues keep the exact SIMT kernel.
+//   MMA column n of block (J, q), q = 0..7   <->   d = 64 J + 16 (n >> 1) + 2 q + (n & 1)
+__device__ __forceinline__ void mma_bf16_16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+constexpr int kMmaThreads = 128;   // 4 warps x 16 tokens
+constexpr int kMmaKC = 4;          // queue rows per token gathered per batch (8 x 32 B in flight per lane)
+
+template <typename TO, bool EP, int KS>     // KS = E / 16 k-steps
+__global__ void __launch_bounds__(kMmaThreads, 4)
+dispatch_bwd_gate_mma_kernel(Queue<const __nv_bfloat16> dxq, const int32_t* __restrict__ pos, int T, int K, int D,
+                             const float* __restrict__ dz, const float* __restrict__ w_gate, TO* __restrict__ dx) {
+  constexpr int E = 16 * KS;
+  pdl_wait();
+  pdl_trigger();
+  extern __shared__ __align__(16) uint32_t wb[];          // [D][E/2] bf16x2: w_gate[d][2i], w_gate[d][2i+1]
+  for (int i = threadIdx.x; i < D * (E / 2); i += kMmaThreads) {
+    const float2 w = __ldg(reinterpret_cast<const float2*>(w_gate) + i);      // rows 0..D-1 of [Dg][E] are contiguous
+    wb[i] = float2_to_bf16x2(w.x, w.y);
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, t = lane & 3;
+  const int n_tiles = (T + 15) / 16;
+  for (int tile = blockIdx.x * (kMmaThreads / 32) + warp; tile < n_tiles; tile += gridDim.x * (kMmaThreads / 32)) {
+    const int ta_ = tile * 16 + g, tb_ = ta_ + 8;
+    const bool va = ta_ < T, vb = tb_ < T;
+    const int ta = va ? ta_ : T - 1, tb = vb ? tb_ : T - 1;
+    // A operand: dz rows of tokens g / g+8, k = expert
+    uint32_t a[KS][4];
+#pragma unroll
+    for (int ks = 0; ks < KS; ++ks) {
+      const float2 x0 = __ldg(reinterpret_cast<const float2*>(dz + (int64_t)ta * E + 16 * ks + 2 * t));
+      const float2 x1 = __ldg(reinterpret_cast<const float2*>(dz + (int64_t)tb * E + 16 * ks + 2 * t));
+      const float2 x2 = __ldg(reinterpret_cast<const float2*>(dz + (int64_t)ta * E + 16 * ks + 2 * t + 8));
+      const float2 x3 = __ldg(reinterpret_cast<const float2*>(dz + (int64_t)tb * E + 16 * ks + 2 * t + 8));
+      a[ks][0] = float2_to_bf16x2(x0.x, x0.y); a[ks][1] = float2_to_bf16x2(x1.x, x1.y);
+      a[ks][2] = float2_to_bf16x2(x2.x, x2.y); a[ks][3] = float2_to_bf16x2(x3.x, x3.y);
+    }
+    for (int J = 0; J < D / 64; ++J) {
+      const int col = 64 * J + 16 * t;   // this lane's 16 columns
+      float acc[2][16];                  // [token g / g+8][16 contiguous columns]
+      for (int k0 = 0; k0 < K; k0 += kMmaKC) {
+        // gather: every load of this batch is issued before anything is consumed
+        U8 raw[kMmaKC][2];
+#pragma unroll
+        for (int u = 0; u < kMmaKC; ++u) {
+          const int k = k0 + u;
+          const int ra = k < K ? __ldg(pos + (int64_t)ta * K + k) : -1;
+          const int rb = k < K ? __ldg(pos + (int64_t)tb * K + k) : -1;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) { raw[u][0].v[i] = 0u; raw[u][1].v[i] = 0u; }
+          if (ra >= 0) raw[u][0] = ldg_stream256(dxq.template row<EP>((int64_t)ta * K + k, ra, D) + col);
+          if (rb >= 0) raw[u][1] = ldg_stream256(dxq.template row<EP>((int64_t)tb * K + k, rb, D) + col);
+        }
+        if (k0 == 0) {
+          // router term of these 64 columns while the rows are in flight
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            float c[4] = {0.f, 0.f, 0.f, 0.f};
+            const int d = 64 * J + 16 * (g >> 1) + 2 * q + (g & 1);     // B column g of block (J, q)
+#pragma unroll
+            for (int ks = 0; ks < KS; ++ks)
+              mma_bf16_16816(c, a[ks], wb[d * (E / 2) + 8 * ks + t], wb[d * (E / 2) + 8 * ks + t + 4]);
+            acc[0][2 * q] = c[0]; acc[0][2 * q + 1] = c[1];
+            acc[1][2 * q] = c[2]; acc[1][2 * q + 1] = c[3];
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < kMmaKC; ++u)
+#pragma unroll
+          for (int h = 0; h < 2; ++h)
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const float2 f = bf16x2_to_float2(raw[u][h].v[i]);
+              acc[h][2 * i] += f.x;
+              acc[h][2 * i + 1] += f.y;
+            }
+      }
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        if (h == 0 ? va : vb) {
+          TO* dst = dx + (int64_t)(h == 0 ? ta : tb) * D + col;
+          if (sizeof(TO) == 4) {
+            U8 o;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) o.v[i] = __float_as_uint(acc[h][i]);
+            stg_stream256(dst, o);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) o.v[i] = __float_as_uint(acc[h][8 + i]);
+            stg_stream256(dst + 8, o);
+          } else {
+            U8 o;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) o.v[i] = float2_to_bf16x2(acc[h][2 * i], acc[h][2 * i + 1]);
+            stg_stream256(dst, o);
+          }
+        }
+      }
+    }
+  }
+}
+
 static inline int perm_nv(int D) { return m3_ceil_div(D / 8, kLanesPerTok); }
 
 }  // namespace m3
@@ -518,6 +631,29 @@ static int dispatch_bwd_impl(const void* dxq, void* const* peer, const int32_t* 
       Queue<const TA> q{(const TA*)dxq, (const TA* const*)peer, slot_rank};
       M3_NV_SWITCH((launch_k(dispatch_bwd_kernel<TA, TB, NV, EP>, grid, kPermThreads, 0, st, q, pos, T, K, D, (TB*)dx)))
     })
+  } else if (dxq_dtype == M3_BF16 && (E == 16 || E == 32 || E == 64) && D % 64 == 0 && (size_t)D * E * 2 <= 96 * 1024 &&
+             (reinterpret_cast<uintptr_t>(dxq) & 31u) == 0 && (reinterpret_cast<uintptr_t>(dx) & 31u) == 0 &&
+             g_knobs[M3_KNOB_MOVER_VARIANT] != 9) {
+    // bf16 queues: router term on the tensor cores (mma.sync), see dispatch_bwd_gate_mma_kernel
+    const size_t smem = (size_t)D * E * 2;
+    int grid = m3_ceil_div(m3_ceil_div(T, 16), kMmaThreads / 32);
+    if (grid > 8 * kNumSMs) grid = 8 * kNumSMs;
+    Queue<const bf16> q{(const bf16*)dxq, (const bf16* const*)peer, slot_rank};
+#define M3_MMA_LAUNCH(TOV, KSV)                                                                              \
+  do {                                                                                                       \
+    auto kern = dispatch_bwd_gate_mma_kernel<TOV, EP, KSV>;                                                  \
+    if (smem > 48 * 1024) {                                                                                  \
+      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);    \
+      if (e != cudaSuccess) return (int)e;                                                                   \
+    }                                                                                                        \
+    launch_k(kern, grid, kMmaThreads, smem, st, q, pos, T, K, D, dz, w_gate, (TOV*)dx);                      \
+  } while (0)
+#define M3_MMA_KS(TOV) do { if (E == 16) M3_MMA_LAUNCH(TOV, 1); else if (E == 32) M3_MMA_LAUNCH(TOV, 2); else M3_MMA_LAUNCH(TOV, 4); } while (0)
+    if (dx_dtype == M3_F32) M3_MMA_KS(float);
+    else if (dx_dtype == M3_BF16) M3_MMA_KS(bf16);
+    else return M3_ERR_UNSUPPORTED;
+#undef M3_MMA_KS
+#undef M3_MMA_LAUNCH
   } else {
     // router term: w_gate[:D]^T staged once per CTA -> few, grid-striding CTAs (2 per SM)
     const size_t smem = (size_t)D * E * sizeof(float);

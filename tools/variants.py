@@ -65,7 +65,14 @@ timed("dispatch_fwd", lambda: ops.dispatch_fwd(x, plan, K, out_dtype=torch.bfloa
 dxq_ = torch.randn_like(xq)
 dz_ = torch.randn(T, E, device=dev)
 timed("dispatch_bwd (no router term)", lambda: ops.dispatch_bwd(dxq_, plan, T, K))
-timed("dispatch_bwd (+ dz @ w_gate^T)", lambda: ops.dispatch_bwd(dxq_, plan, T, K, dz=dz_, w_gate=wg))
+lib.m3_set_knob(KNOB_MOVER, 9)
+d_simt = ops.dispatch_bwd(dxq_, plan, T, K, dz=dz_, w_gate=wg)
+timed("dispatch_bwd (+ dz @ w_gate^T) [SIMT fp32 router term]", lambda: ops.dispatch_bwd(dxq_, plan, T, K, dz=dz_, w_gate=wg))
+lib.m3_set_knob(KNOB_MOVER, 0)
+d_mma = ops.dispatch_bwd(dxq_, plan, T, K, dz=dz_, w_gate=wg)
+print(f"  mma.sync router term vs SIMT: max abs diff {(d_mma - d_simt).abs().max().item():.3e}, "
+      f"normalised {((d_mma - d_simt).norm() / d_simt.norm()).item():.3e}")
+timed("dispatch_bwd (+ dz @ w_gate^T) [mma.sync bf16 router term]", lambda: ops.dispatch_bwd(dxq_, plan, T, K, dz=dz_, w_gate=wg))
 timed("gate_bwd", lambda: ops.gate_bwd(x, wg, g.noisy_logits, g.idx_full, K, dscore=g.score))
 timed("route_plan", lambda: ops.route_plan(g.idx, E, imp_partial=g.imp_partial, load_partial=g.load_partial))
 timed("torch x.clone() (59 MB read + 59 MB write)", lambda: x.clone())
@@ -74,8 +81,20 @@ timed("torch x.clone() (59 MB read + 59 MB write)", lambda: x.clone())
 ref_f = ops.ffn_fwd(xq, plan, w1c, b1, w2c, b2)
 ref_b = ops.ffn_bwd(xq, hpre, dyq, plan, w1c, w2c, w1t, w2t)
 KNOB_DEBUG = 4
-for dbg, name in ((0, "normal"), (1, "no MMAs (loads + epilogue only)"), (2, "no TMA loads (MMAs + epilogue only)"), (3, "neither (epilogue + handshakes)"),
-                  (4, "no epilogue (loads + MMAs)"), (5, "loads only"), (6, "MMAs only"), (7, "handshakes only")):
+KNOB_BRES = 6
+for off in (1, 0):
+    lib.m3_set_knob(KNOB_BRES, 0 if off else 1)
+    of = ops.ffn_fwd(xq, plan, w1c, b1, w2c, b2)
+    ob = ops.ffn_bwd(xq, hpre, dyq, plan, w1c, w2c, w1t, w2t)
+    torch.cuda.synchronize()
+    if off == 1:
+        ref_f, ref_b = of, ob
+    nm = "streamed weights" if off else "resident weights"
+    print(f"  [{nm}] bits equal to streamed: fwd {same(of, ref_f)}  bwd {same(ob, ref_b)}")
+    timed(f"ffn_fwd (fc1+fc2)      [{nm}]", lambda: ops.ffn_fwd(xq, plan, w1c, b1, w2c, b2))
+    timed(f"ffn_bwd (2 dgrad+2 wg) [{nm}]", lambda: ops.ffn_bwd(xq, hpre, dyq, plan, w1c, w2c, w1t, w2t))
+lib.m3_set_knob(KNOB_BRES, 0)
+for dbg, name in ((0, "normal"), (5, "loads only"), (6, "MMAs only")):
     lib.m3_set_knob(KNOB_DEBUG, dbg)
     timed(f"ffn_fwd (fc1+fc2)      [{name}]", lambda: ops.ffn_fwd(xq, plan, w1c, b1, w2c, b2))
     timed(f"ffn_bwd (2 dgrad+2 wg) [{name}]", lambda: ops.ffn_bwd(xq, hpre, dyq, plan, w1c, w2c, w1t, w2t))
