@@ -169,7 +169,9 @@ int m3_set_gemm_sm_limit(int sms);
  *                     0 (default): plain stream-ordered launches (at bench size the kernels are 30-100 us long and
  *                     PDL measured no gain; it is meant for the launch-bound small-batch regime).
  *   M3_KNOB_EPI_WARPS 8 or 16 epilogue warps in the tcgen05 grouped GEMM (0 = per-epilogue default;
- *                     0x100 | mask: bit e of mask set -> 16 warps for epilogue e = 0 store, 1 bias, 2 fc1, 3 dgelu).
+ *                     0x100 | mask: bit e of mask set -> 16 warps for epilogue e = 0 store, 1 bias, 2 fc1, 3 dgelu;
+ *                     | 0x200: the 8-warp epilogues use 32-column register blocks / 2 KB staging boxes (one more smem
+ *                     stage) instead of 64 / 4 KB).
  *   M3_KNOB_GATE_CFG  0 (default: chosen from T) or 1..4 = force gate_fwd tile configuration 0..3.
  *   M3_KNOB_DEBUG     measurement only (results are garbage): tcgen05 GEMMs run 1 = without MMAs, 2 = without TMA loads.
  *   M3_KNOB_TRACE_KERNEL  1 + index of the GEMM launch inside one m3_ffn_fwd / m3_ffn_bwd call that m3_debug_trace_buffer

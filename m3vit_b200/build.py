@@ -18,6 +18,8 @@ NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC",     # no --use_fast_math: exact erf/exp/div, parity first
 ]
+if os.environ.get("M3_GEMM_TRACE") == "1":      # clock64 timeline in the tensor-core GEMMs (tools/gemm_timeline.py)
+    NVCC_FLAGS.append("-DM3_GEMM_TRACE")
 
 
 def _nvcc():

@@ -57,9 +57,10 @@ struct GGParams {
 // inbound bandwidth, paces the ring - its latency just grows with the extra stages (tools/gemm_timeline.py).
 constexpr int kBresMaxChunks = 6;      // Kd <= 384: 6 x (BN/2 rows x 128 B) = 72 KB of resident weights per CTA at BN = 192
 
-template <int BN, int EPI, int NCTA, int EW, bool BRES>
+template <int BN, int EPI, int NCTA, int EW, bool BRES, int CWP>
 struct GGCfg {
-  static constexpr int CW = EW == 16 ? 32 : 64;               // columns per epilogue register block
+  static constexpr int CW = CWP;                              // columns per epilogue register block (32 or 64)
+  static_assert(CWP == 32 || (CWP == 64 && EW == 8), "epilogue block width");
   static constexpr int WBOX_BYTES = 32 * CW * 2;              // one warp's [32 rows][CW bf16] swizzled box (4 / 2 KB)
   static constexpr int A_BYTES = BM * BK * 2;
   static constexpr int B_BYTES = (BN / NCTA) * BK * 2;      // a CTA pair splits the B tile
@@ -71,7 +72,7 @@ struct GGCfg {
   static constexpr int WARP_STAGING = (N_OUT + N_AUX) * WBOX_BYTES;
   static constexpr int STAGING = EW * WARP_STAGING;
   static constexpr int BUDGET = 227 * 1024 - 1024 - 512 - STAGING - BRES_BYTES;
-  static constexpr int MAX_STAGES = BRES ? 8 : 6;
+  static constexpr int MAX_STAGES = 8;
   static constexpr int STAGES = (BUDGET / STAGE) < MAX_STAGES ? (BUDGET / STAGE) : MAX_STAGES;
   static constexpr int TMEM_COLS = (2 * BN <= 256) ? 256 : 512;
   static constexpr int SMEM = STAGES * STAGE + BRES_BYTES + STAGING + 1024 /*align slack*/ + 512 /*barriers*/;
@@ -96,12 +97,12 @@ __device__ __forceinline__ uint32_t box_off(int r, int c) {
   return (uint32_t)r * 64u + (uint32_t)((c ^ ((r >> 1) & 3)) << 4);
 }
 
-template <int BN, int EPI, int NCTA, int EW, bool BRES>
+template <int BN, int EPI, int NCTA, int EW, bool BRES, int CWP>
 __global__ void __launch_bounds__(gg_threads(EW), 1)
 gg_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
           const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmOut2,
           const __grid_constant__ CUtensorMap tmAux, GGParams p) {
-  using Cfg = GGCfg<BN, EPI, NCTA, EW, BRES>;
+  using Cfg = GGCfg<BN, EPI, NCTA, EW, BRES, CWP>;
   constexpr int kEpiWarps = EW;
   constexpr int CW = Cfg::CW, WBOX_BYTES = Cfg::WBOX_BYTES;
   constexpr int NQ = EW / 8;            // warps sharing one (TMEM lane quarter, accumulator buffer)
@@ -697,15 +698,15 @@ static int g_gemm_sms = kNumSMs;
 template <int EPI>
 static int epi_warps() {
   const int k = g_knobs[M3_KNOB_EPI_WARPS];
-  if (k == 8 || k == 16) return k;
   if (k & 0x100) return ((k >> EPI) & 1) ? 16 : 8;     // 0x100 | mask: bit EPI set -> 16 warps for that epilogue
-  return kDefaultEpiWarps[EPI];
+  if ((k & 0xff) == 8 || (k & 0xff) == 16) return k & 0xff;
+  return kDefaultEpiWarps[EPI];                        // (bit 0x200 selects the block width, see launch_gg)
 }
 
-template <int BN, int EPI, int EW, bool BRES>
+template <int BN, int EPI, int EW, bool BRES, int CWP>
 static int launch_gg_t(const CUtensorMap* maps, const GGParams& p, int max_tiles, cudaStream_t st) {
-  using Cfg = GGCfg<BN, EPI, kGGNcta, EW, BRES>;
-  auto kern = gg_kernel<BN, EPI, kGGNcta, EW, BRES>;
+  using Cfg = GGCfg<BN, EPI, kGGNcta, EW, BRES, CWP>;
+  auto kern = gg_kernel<BN, EPI, kGGNcta, EW, BRES, CWP>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
   if (e != cudaSuccess) return (int)e;
   int grid = max_tiles < g_gemm_sms ? max_tiles : g_gemm_sms;
@@ -754,7 +755,10 @@ static int launch_gg(const void* A, const void* B, void* out, void* out2, const 
   rc = make_map(&maps[3], out2 ? out2 : out, (uint64_t)cap_rows, (uint64_t)p.N, 32);
   if (rc) return rc;
   const int ew = epi_warps<EPI>();
-  rc = make_map(&maps[4], aux ? aux : out, (uint64_t)cap_rows, (uint64_t)p.N, 32, ew == 16 ? 32 : 64);
+  // epilogue register-block / staging-box width of the 8-warp epilogues: 32 columns (2 KB boxes) leave room for a 7th
+  // smem stage, but measured 10 us slower per fc1+fc2 than 64 columns / 6 stages (tools/variants.py): opt-in (0x200)
+  const bool narrow = ew == 16 || (g_knobs[M3_KNOB_EPI_WARPS] & 0x200) != 0;
+  rc = make_map(&maps[4], aux ? aux : out, (uint64_t)cap_rows, (uint64_t)p.N, 32, narrow ? 32 : 64);
   if (rc) return rc;
   p.out = static_cast<__nv_bfloat16*>(out);
   p.out2 = static_cast<__nv_bfloat16*>(out2);
@@ -765,10 +769,14 @@ static int launch_gg(const void* A, const void* B, void* out, void* out2, const 
   // resident weights (BRES) where they fit: Kd <= 384, BN <= 192, and enough SMs for one unit per N-tile
   const int usable = (max_tiles < g_gemm_sms ? max_tiles : g_gemm_sms) / kGGNcta;
   const bool bres = g_knobs[M3_KNOB_BRES] == 1 && p.Kd / BK <= kBresMaxChunks && BN <= 192 && usable >= p.N / BN;
-#define M3_GG_EW(BNV)                                                                                                   \
-  (ew == 16 ? launch_gg_t<BNV, EPI, 16, false>(maps, p, max_tiles, st) : launch_gg_t<BNV, EPI, 8, false>(maps, p, max_tiles, st))
-#define M3_GG_EW_BRES(BNV)                                                                                              \
-  (ew == 16 ? launch_gg_t<BNV, EPI, 16, true>(maps, p, max_tiles, st) : launch_gg_t<BNV, EPI, 8, true>(maps, p, max_tiles, st))
+#define M3_GG_EW(BNV)                                                                          \
+  (ew == 16 ? launch_gg_t<BNV, EPI, 16, false, 32>(maps, p, max_tiles, st)                      \
+            : narrow ? launch_gg_t<BNV, EPI, 8, false, 32>(maps, p, max_tiles, st)              \
+                     : launch_gg_t<BNV, EPI, 8, false, 64>(maps, p, max_tiles, st))
+#define M3_GG_EW_BRES(BNV)                                                                     \
+  (ew == 16 ? launch_gg_t<BNV, EPI, 16, true, 32>(maps, p, max_tiles, st)                       \
+            : narrow ? launch_gg_t<BNV, EPI, 8, true, 32>(maps, p, max_tiles, st)               \
+                     : launch_gg_t<BNV, EPI, 8, true, 64>(maps, p, max_tiles, st))
   switch (BN) {
     case 128: return bres ? M3_GG_EW_BRES(128) : M3_GG_EW(128);
     case 192: return bres ? M3_GG_EW_BRES(192) : M3_GG_EW(192);

@@ -285,7 +285,7 @@ template <int E>
 static int gate_cfg_id(int T) {
   if (g_knobs[M3_KNOB_GATE_CFG] > 0) return g_knobs[M3_KNOB_GATE_CFG] - 1;   // forced (A/B measurement)
   if (T >= 16 * kNumSMs * GateCfg<E, 8, 4>::TOK_W) return 3;
-  if (T >= 16 * kNumSMs * GateCfg<E, 4, 4>::TOK_W) return 2;
+  if (T >= 16 * kNumSMs * GateCfg<E, 4, 4>::TOK_W) return 2;   // (T = 38 432, E = 16: TM = 2 35 us, TM = 4 43 us, TM = 8 60 us)
   if (T >= 16 * kNumSMs * GateCfg<E, 2, 4>::TOK_W) return 1;
   return 0;
 }

@@ -20,6 +20,10 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
 // 2 epilogue warp 0) owns events [r*cap, (r+1)*cap) and counts them in a register; buf[r] = its final count.
 extern unsigned long long* g_trace_buf;   // abi.cu
 extern int g_trace_cap;
+// Compiled in only with -DM3_GEMM_TRACE (M3_GEMM_TRACE=1 python -m m3vit_b200.build --force): even switched off at run
+// time, the per-lane `buf` test is a potentially divergent branch inside the converged producer / MMA loops and cost
+// 5-10 us per GEMM launch.
+#ifdef M3_GEMM_TRACE
 struct Tracer {
   unsigned long long* buf;
   int cap, role, n;
@@ -36,6 +40,13 @@ struct Tracer {
   }
   __device__ __forceinline__ void done() { if (buf != nullptr) buf[role] = (unsigned long long)n; }
 };
+#else
+struct Tracer {
+  __device__ __forceinline__ Tracer(unsigned long long*, int, int) {}
+  __device__ __forceinline__ void ev(uint32_t, uint32_t) {}
+  __device__ __forceinline__ void done() {}
+};
+#endif
 
 // explicit shared-space 128-bit accesses: pointers carved out of the dynamic smem block by integer arithmetic lose
 // their address space and compile to GENERIC LD.E / ST.E (long-scoreboard latency); these stay LDS / STS

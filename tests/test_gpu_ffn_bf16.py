@@ -158,3 +158,44 @@ torch.save([t.float().cpu() for t in (yq[:n], dxq[:n], dw1, db1, dw2, db2)], sys
         # identical arithmetic up to the order of the fp32 accumulation over hidden chunks and the rounding of
         # the saved state (two-kernel path keeps gelu'(z) in bf16, the chain kernel keeps z)
         assert nerr(b, a) < 1e-2, (name, nerr(b, a))
+
+
+@pytest.mark.parametrize("knob,value,name", [
+    (6, 1, "resident weights (M3_KNOB_BRES)"),
+    (1, 0x200, "32-column epilogue blocks, one more smem stage"),
+    (1, 0x100 | 15, "16 epilogue warps in every GEMM"),
+    (1, 0x100, "8 epilogue warps in every GEMM"),
+    (0, 1, "programmatic dependent launch"),
+])
+def test_gemm_tuning_knobs_are_bit_identical(knob, value, name):
+    """Every tuning knob of the tensor-core GEMMs (m3_set_knob) only changes the schedule, never a bit of the result."""
+    from m3vit_b200 import ops, _lib
+    lib = _lib.load()
+    dev = torch.device("cuda:0")
+    torch.manual_seed(3)
+    T, K, E, D, H = 3000, 4, 16, 384, 384
+    x = torch.randn(T, D, device=dev)
+    pri = torch.rand(T, E) * (1.0 / torch.arange(1, E + 1).float()) ** 1.2      # skewed: several weight reloads per unit
+    idx = pri.topk(K, 1).indices.to(dev)
+    plan = ops.route_plan(idx, E)
+    xq = ops.dispatch_fwd(x, plan, K, out_dtype=torch.bfloat16)
+    w1c, w1t = ops.cast_weights_bf16(torch.randn(E, H, D, device=dev) / D ** 0.5, True, True)
+    w2c, w2t = ops.cast_weights_bf16(torch.randn(E, D, H, device=dev) / H ** 0.5, True, True)
+    b1, b2 = torch.randn(E, H, device=dev) * 0.1, torch.randn(E, D, device=dev) * 0.1
+    n = int(plan.offsets[-1])          # rows beyond the live queues are never written
+
+    def run():
+        yq, hpre = ops.ffn_fwd(xq, plan, w1c, b1, w2c, b2)
+        dyq = torch.ones_like(yq) * 0.01
+        dxq, dw1, db1, dw2, db2 = ops.ffn_bwd(xq, hpre, dyq, plan, w1c, w2c, w1t, w2t)
+        torch.cuda.synchronize()
+        return [yq[:n].clone(), dxq[:n].clone(), dw1, db1, dw2, db2]
+
+    ref = run()
+    old = lib.m3_set_knob(knob, value)
+    try:
+        got = run()
+    finally:
+        lib.m3_set_knob(knob, old)
+    for a, b, nm in zip(got, ref, ("yq", "dxq", "dw1", "db1", "dw2", "db2")):
+        assert torch.equal(a, b), (name, nm)

@@ -1,5 +1,6 @@
 """clock64 timeline of CTA 0 of the tensor-core GEMM kernels (producer / MMA / first epilogue warp):
-    python tools/gemm_timeline.py [fwd|bwd] [dbg]        (m3_debug_trace_buffer, include/m3vit_moe.h)"""
+    M3_GEMM_TRACE=1 python -m m3vit_b200.build --force      # trace points are compiled in only on request
+    python tools/gemm_timeline.py [fwd|bwd] [dbg]            (m3_debug_trace_buffer, include/m3vit_moe.h)"""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch

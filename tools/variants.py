@@ -99,8 +99,8 @@ for dbg, name in ((0, "normal"), (5, "loads only"), (6, "MMAs only")):
     timed(f"ffn_fwd (fc1+fc2)      [{name}]", lambda: ops.ffn_fwd(xq, plan, w1c, b1, w2c, b2))
     timed(f"ffn_bwd (2 dgrad+2 wg) [{name}]", lambda: ops.ffn_bwd(xq, hpre, dyq, plan, w1c, w2c, w1t, w2t))
 lib.m3_set_knob(KNOB_DEBUG, 0)
-for mask, name in ((0, "8 warps everywhere"), (4, "fc1:16")):
-    lib.m3_set_knob(KNOB_EPI, 0x100 | mask)
+for mask, name in ((0, "default: fc1 16 warps, others 8 warps x 64-col blocks"), (0x200, "8-warp epilogues with 32-col blocks, 7 stages"), (0x100, "8 warps everywhere")):
+    lib.m3_set_knob(KNOB_EPI, mask)
     of = ops.ffn_fwd(xq, plan, w1c, b1, w2c, b2)
     ob = ops.ffn_bwd(xq, hpre, dyq, plan, w1c, w2c, w1t, w2t)
     torch.cuda.synchronize()
