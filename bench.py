@@ -452,9 +452,9 @@ def kernel_rooflines(layer, x, dev, cdt, pk, iters=20):
         nbytes=T * (K * D * el + K * 4 + D * 4 + E * 4))
     f = st["ffn_fwd"]
     # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture of this exact
-    # configuration (profiles/r1_ncu_all_kernels_final.md: fc1 124.1 + 180.1 MB, fc2 124.1 + 73.1 MB; writes still in
+    # configuration (profiles/r1b_ncu_all_kernels.md: fc1 124.2 + 186.0 MB, fc2 124.1 + 69.7 MB; writes still in
     # L2 at kernel end are not counted by ncu), averaged over the two launches like `achieved`; null for any other size.
-    traffic = 250.7e6 if (cdt == torch.bfloat16 and T == 32 * N_TOK and D == 384 and H == 384 and K == 4) else None
+    traffic = 252.0e6 if (cdt == torch.bfloat16 and T == 32 * N_TOK and D == 384 and H == 384 and K == 4) else None
     roof = {"kernel": "gg_kernel<192> (tcgen05 grouped GEMM; fc1+bias+GELU and fc2+bias launches of m3_ffn_fwd)"
             if cdt == torch.bfloat16 else "sgemm_grouped_kernel (fp32 SIMT)",
             "bound": "tensor", "achieved": f["achieved"], "peak": pk["tf_burst"], "unit": "TFLOP/s",

@@ -655,6 +655,16 @@ static EncodeTiledFn get_encode() {
   return fn;
 }
 
+// L2 sector promotion of the TMA loads (M3_KNOB_DEBUG bits 12-13: 1 = none, 2 = 64 B, 3 = 128 B; default 256 B)
+static CUtensorMapL2promotion l2_promotion() {
+  switch ((g_knobs[M3_KNOB_DEBUG] >> 12) & 3) {
+    case 1: return CU_TENSOR_MAP_L2_PROMOTION_NONE;
+    case 2: return CU_TENSOR_MAP_L2_PROMOTION_L2_64B;
+    case 3: return CU_TENSOR_MAP_L2_PROMOTION_L2_128B;
+    default: return CU_TENSOR_MAP_L2_PROMOTION_L2_256B;
+  }
+}
+
 // 2-D bf16 row-major tensor [rows][cols], box [box_rows][64 cols] (128 B inner), SWIZZLE_128B
 // (box_cols = 32: 64 B inner, SWIZZLE_64B - the 32-column epilogue blocks of the 16-warp epilogue)
 static int make_map(CUtensorMap* m, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows,
@@ -667,7 +677,7 @@ static int make_map(CUtensorMap* m, const void* base, uint64_t rows, uint64_t co
   cuuint32_t estr[2] = {1, 1};
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, box_cols == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
-                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                   l2_promotion(), CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? M3_OK : M3_ERR_ARG;
 }
 

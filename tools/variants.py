@@ -82,6 +82,7 @@ ref_f = ops.ffn_fwd(xq, plan, w1c, b1, w2c, b2)
 ref_b = ops.ffn_bwd(xq, hpre, dyq, plan, w1c, w2c, w1t, w2t)
 KNOB_DEBUG = 4
 KNOB_BRES = 6
+KNOB_DEBUG = 4
 for off in (1, 0):
     lib.m3_set_knob(KNOB_BRES, 0 if off else 1)
     of = ops.ffn_fwd(xq, plan, w1c, b1, w2c, b2)
@@ -94,6 +95,11 @@ for off in (1, 0):
     timed(f"ffn_fwd (fc1+fc2)      [{nm}]", lambda: ops.ffn_fwd(xq, plan, w1c, b1, w2c, b2))
     timed(f"ffn_bwd (2 dgrad+2 wg) [{nm}]", lambda: ops.ffn_bwd(xq, hpre, dyq, plan, w1c, w2c, w1t, w2t))
 lib.m3_set_knob(KNOB_BRES, 0)
+for pr, name in ((0, "L2 promotion 256 B (default)"), (3, "L2 promotion 128 B"), (1, "no L2 promotion"), (0, "L2 promotion 256 B (default)")):
+    lib.m3_set_knob(KNOB_DEBUG, pr << 12)
+    timed(f"ffn_fwd (fc1+fc2)      [{name}]", lambda: ops.ffn_fwd(xq, plan, w1c, b1, w2c, b2))
+    timed(f"ffn_bwd (2 dgrad+2 wg) [{name}]", lambda: ops.ffn_bwd(xq, hpre, dyq, plan, w1c, w2c, w1t, w2t))
+lib.m3_set_knob(KNOB_DEBUG, 0)
 for dbg, name in ((0, "normal"), (5, "loads only"), (6, "MMAs only")):
     lib.m3_set_knob(KNOB_DEBUG, dbg)
     timed(f"ffn_fwd (fc1+fc2)      [{name}]", lambda: ops.ffn_fwd(xq, plan, w1c, b1, w2c, b2))
