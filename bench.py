@@ -209,7 +209,8 @@ def main():
     config = {"workload": "ViT-S M3ViT backbone MoE layers (configs[1]): 6 MoE layers x 2 NYUD task passes, fwd+bwd",
               "d_model": D_MODEL, "d_hidden": D_HID, "experts": N_EXP, "top_k": TOP_K, "tokens_per_image": N_TOK,
               "batch_per_gpu": args.batch, "layer_calls_per_step": N_LAYER * N_TASK, "noise_std": 0,
-              "l2": "inputs_exceed_l2 (12 distinct token buffers per step)"}
+              "l2": "inputs_exceed_l2 (12 distinct token buffers per step); per-stage timing: L2 flushed, then 4 launches on 4 "
+                    "independent operand sets between one event pair"}
 
     if args.impl == "reference":
         if rank != 0:
@@ -387,10 +388,16 @@ def main():
         dist.destroy_process_group()
 
 
-def kernel_rooflines(layer, x, dev, cdt, pk, iters=20):
+def kernel_rooflines(layer, x, dev, cdt, pk, iters=10, nset=4):
     """CUDA-event timing of each stage of one layer call (T tokens), after warm-up, with the
-    algorithmic bytes / flops of SURVEY.md 8(d).  Returns (dominant-kernel roofline, per-stage table)."""
+    algorithmic bytes / flops of SURVEY.md 8(d).  Returns (dominant-kernel roofline, per-stage table).
+
+    Every stage is launched back to back on `nset` INDEPENDENT sets of operands (different tokens, different
+    buffers: each launch streams data no earlier launch touched, as in the real step where 12 layer calls follow each
+    other) between ONE pair of events, after an L2 flush; the average launch duration is that time / launches.  A
+    single launch between two events also measures ~6-8 us of launch latency, 15-25 % of a 30 us mover."""
     from m3vit_b200 import ops
+    from m3vit_b200.synthetic import device_tokens
     T, D = x.shape
     K, E, H = TOP_K, N_EXP, D_HID
     el = 2 if cdt == torch.bfloat16 else 4
@@ -401,28 +408,39 @@ def kernel_rooflines(layer, x, dev, cdt, pk, iters=20):
         w1c, w2c, w1t, w2t = layer._wcache.get_bf16(layer.experts.htoh4.weight, layer.experts.h4toh.weight)
     else:
         w1c, w2c, w1t, w2t = w1, w2, None, None
-    g = ops.gate_fwd(x, wg, K)
-    plan = ops.route_plan(g.idx, E, imp_partial=g.imp_partial, load_partial=g.load_partial)
-    xq = ops.dispatch_fwd(x, plan, K, out_dtype=cdt)
-    yq, hpre = ops.ffn_fwd(xq, plan, w1c, b1, w2c, b2)
-    go = torch.randn(T, D, device=dev)
-    dyq, dscore = ops.combine_bwd(go, yq, plan, g.score)
     R = T * K
+
+    class S:      # one independent set of operands
+        pass
+    sets = []
+    for i in range(nset):
+        o = S()
+        o.x = x if i == 0 else device_tokens(T, D, 7000 + i, dev)
+        o.g = ops.gate_fwd(o.x, wg, K)
+        o.plan = ops.route_plan(o.g.idx, E, imp_partial=o.g.imp_partial, load_partial=o.g.load_partial)
+        o.xq = ops.dispatch_fwd(o.x, o.plan, K, out_dtype=cdt)
+        o.yq, o.hpre = ops.ffn_fwd(o.xq, o.plan, w1c, b1, w2c, b2)
+        o.go = torch.randn(T, D, device=dev)
+        o.dyq, o.dscore = ops.combine_bwd(o.go, o.yq, o.plan, o.g.score)
+        o.dxq = ops.ffn_bwd(o.xq, o.hpre, o.dyq, o.plan, w1c, w2c, w1t, w2t)[0]
+        o.dz = ops.gate_bwd(o.x, wg, o.g.noisy_logits, o.g.idx_full, K, dscore=o.dscore)[0]
+        sets.append(o)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
     def timed(fn, nlaunch):
-        for _ in range(3):
-            fn()
+        for o in sets[:2]:
+            fn(o)
         tot = 0.0
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         for _ in range(iters):
             flush.zero_()                       # L2 flush between timed iterations (256 MiB > 126 MB L2)
             a.record()
-            fn()
+            for o in sets:
+                fn(o)
             b.record()
             b.synchronize()
             tot += a.elapsed_time(b)
-        return tot / iters * 1e-3 / nlaunch     # seconds per launch
+        return tot / iters * 1e-3 / (nlaunch * len(sets))     # seconds per launch
 
     st = {}
 
@@ -436,19 +454,18 @@ def kernel_rooflines(layer, x, dev, cdt, pk, iters=20):
         d["frac"] = d["achieved"] / d["peak"]
         st[name] = d
 
-    add("gate_fwd", lambda: ops.gate_fwd(x, wg, K), 1, nbytes=T * D * 4 + T * (E * 4 + K * 16 + (K + 1) * 8))
-    add("route_plan", lambda: ops.route_plan(g.idx, E, imp_partial=g.imp_partial, load_partial=g.load_partial), 2, nbytes=R * (8 + 8 + 4))
-    add("dispatch_fwd", lambda: ops.dispatch_fwd(x, plan, K, out_dtype=cdt), 1, nbytes=T * (D * 4 + K * D * el + K * 4))
-    add("ffn_fwd", lambda: ops.ffn_fwd(xq, plan, w1c, b1, w2c, b2), 2, flops=4.0 * R * D * H)
-    add("combine_fwd", lambda: ops.combine_fwd(yq, plan, g.score), 1, nbytes=T * (K * D * el + K * 8 + D * 4))
-    add("combine_bwd", lambda: ops.combine_bwd(go, yq, plan, g.score), 1, nbytes=T * (D * 4 + 2 * K * D * el + K * 12))
+    add("gate_fwd", lambda o: ops.gate_fwd(o.x, wg, K), 1, nbytes=T * D * 4 + T * (E * 4 + K * 16 + (K + 1) * 8))
+    add("route_plan", lambda o: ops.route_plan(o.g.idx, E, imp_partial=o.g.imp_partial, load_partial=o.g.load_partial), 2,
+        nbytes=R * (8 + 8 + 4))
+    add("dispatch_fwd", lambda o: ops.dispatch_fwd(o.x, o.plan, K, out_dtype=cdt), 1, nbytes=T * (D * 4 + K * D * el + K * 4))
+    add("ffn_fwd", lambda o: ops.ffn_fwd(o.xq, o.plan, w1c, b1, w2c, b2), 2, flops=4.0 * R * D * H)
+    add("combine_fwd", lambda o: ops.combine_fwd(o.yq, o.plan, o.g.score), 1, nbytes=T * (K * D * el + K * 8 + D * 4))
+    add("combine_bwd", lambda o: ops.combine_bwd(o.go, o.yq, o.plan, o.g.score), 1, nbytes=T * (D * 4 + 2 * K * D * el + K * 12))
     nb = 4 if cdt == torch.bfloat16 else 6
-    add("ffn_bwd", lambda: ops.ffn_bwd(xq, hpre, dyq, plan, w1c, w2c, w1t, w2t), nb, flops=8.0 * R * D * H)
-    dxq = ops.ffn_bwd(xq, hpre, dyq, plan, w1c, w2c, w1t, w2t)[0]
-    dz = ops.gate_bwd(x, wg, g.noisy_logits, g.idx_full, K, dscore=dscore)[0]
-    add("gate_bwd", lambda: ops.gate_bwd(x, wg, g.noisy_logits, g.idx_full, K, dscore=dscore), 3,
+    add("ffn_bwd", lambda o: ops.ffn_bwd(o.xq, o.hpre, o.dyq, o.plan, w1c, w2c, w1t, w2t), nb, flops=8.0 * R * D * H)
+    add("gate_bwd", lambda o: ops.gate_bwd(o.x, wg, o.g.noisy_logits, o.g.idx_full, K, dscore=o.dscore), 3,
         nbytes=T * (D * 4 + E * 12))
-    add("dispatch_bwd", lambda: ops.dispatch_bwd(dxq, plan, T, K, dz=dz, w_gate=wg), 1,
+    add("dispatch_bwd", lambda o: ops.dispatch_bwd(o.dxq, o.plan, T, K, dz=o.dz, w_gate=wg), 1,
         nbytes=T * (K * D * el + K * 4 + D * 4 + E * 4))
     f = st["ffn_fwd"]
     # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture of this exact

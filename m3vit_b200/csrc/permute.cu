@@ -413,10 +413,11 @@ __device__ __forceinline__ void mma_bf16_16816(float (&c)[4], const uint32_t (&a
 }
 
 constexpr int kMmaThreads = 128;   // 4 warps x 16 tokens
-constexpr int kMmaKC = 4;          // queue rows per token gathered per batch (8 x 32 B in flight per lane)
+constexpr int kMmaKC = 2;          // queue rows per token gathered per batch: 2 at 6 CTAs/SM (<= 80 registers) measured 43 us,
+                                   // 4 at 4 CTAs/SM 51 us (tools/variants.py) - like combine_fwd, the gather wants warps
 
-template <typename TO, bool EP, int KS>     // KS = E / 16 k-steps
-__global__ void __launch_bounds__(kMmaThreads, 4)
+template <typename TO, bool EP, int KS, int kMmaKC = m3::kMmaKC, int MINB = 6>     // KS = E / 16 k-steps
+__global__ void __launch_bounds__(kMmaThreads, MINB)
 dispatch_bwd_gate_mma_kernel(Queue<const __nv_bfloat16> dxq, const int32_t* __restrict__ pos, int T, int K, int D,
                              const float* __restrict__ dz, const float* __restrict__ w_gate, TO* __restrict__ dx) {
   constexpr int E = 16 * KS;
@@ -641,7 +642,9 @@ static int dispatch_bwd_impl(const void* dxq, void* const* peer, const int32_t* 
     Queue<const bf16> q{(const bf16*)dxq, (const bf16* const*)peer, slot_rank};
 #define M3_MMA_LAUNCH(TOV, KSV)                                                                              \
   do {                                                                                                       \
-    auto kern = dispatch_bwd_gate_mma_kernel<TOV, EP, KSV>;                                                  \
+    auto kern = g_knobs[M3_KNOB_MOVER_VARIANT] == 8 ? dispatch_bwd_gate_mma_kernel<TOV, EP, KSV, 1, 8>       \
+              : g_knobs[M3_KNOB_MOVER_VARIANT] == 7 ? dispatch_bwd_gate_mma_kernel<TOV, EP, KSV, 4, 4>       \
+                                                    : dispatch_bwd_gate_mma_kernel<TOV, EP, KSV>;            \
     if (smem > 48 * 1024) {                                                                                  \
       cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);    \
       if (e != cudaSuccess) return (int)e;                                                                   \

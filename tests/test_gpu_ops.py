@@ -219,3 +219,42 @@ def test_shape_errors_raise_value_error(dev):
         ops.gate_fwd(x, torch.randn(48, 16, device=dev), 4)
     with pytest.raises(ValueError):
         ops.gate_fwd(torch.randn(8, 64, device=dev), torch.randn(64, 12, device=dev), 4)   # E=12 unsupported
+
+
+@pytest.mark.parametrize("T,K,E,D,out_dtype", [
+    (1000, 4, 16, 384, torch.float32),     # bench shape, ragged last 16-token tile
+    (37, 2, 32, 128, torch.float32),       # two k-steps, tiny ragged T
+    (513, 1, 64, 768, torch.float32),      # four k-steps, ViT-B width
+    (300, 5, 16, 192, torch.bfloat16),     # K > 4 (two gather batches), bf16 dx
+])
+def test_dispatch_bwd_router_term_on_tensor_cores(T, K, E, D, out_dtype, dev):
+    """dispatch_bwd with bf16 queues adds dz @ w_gate[:D]^T on mma.sync (bf16 operands, fp32 accumulate): against an fp64
+    reference fed the same bf16-rounded dz / w_gate (tolerance: fp32 accumulation order only), and against the exact fp32
+    SIMT kernel (tolerance: the bf16 rounding of dz and w_gate, 2^-8 relative per product).  Dropped slots stay out."""
+    from m3vit_b200 import ops, _lib
+    gen = torch.Generator().manual_seed(T + E)
+    idx = torch.stack([torch.randperm(E, generator=gen)[:K] for _ in range(T)])
+    idx[::7, 0] = -1                                             # dropped slots (capacity overflow / masked tokens)
+    plan = ops.route_plan(idx.to(dev), E)
+    n = int(plan.offsets[-1])
+    dxq = torch.randn(plan.cap_rows, D, generator=gen).bfloat16()
+    dz = torch.randn(T, E, generator=gen) * 0.3
+    wg = torch.randn(D + 3, E, generator=gen) / D ** 0.5         # 3 task-feature rows that must be ignored
+    pos = plan.pos.cpu().long().view(T, K)
+    rows = dxq.double()[pos.clamp_min(0)] * (pos >= 0).unsqueeze(-1)
+    ref_gather = rows.sum(1)
+    ref = ref_gather + dz.bfloat16().double() @ wg[:D].bfloat16().double().t()
+    got = ops.dispatch_bwd(dxq.to(dev), plan, T, K, out_dtype=out_dtype, dz=dz.to(dev), w_gate=wg.to(dev))
+    tol = 1e-5 if out_dtype == torch.float32 else 1e-2
+    assert float((got.double().cpu() - ref).abs().max() / ref.abs().max()) < tol
+    exact = ref_gather + dz.double() @ wg[:D].double().t()
+    assert float((got.double().cpu() - exact).norm() / exact.norm()) < (4e-3 if out_dtype == torch.float32 else 8e-3)
+    if D * E * 4 > 100 * 1024:
+        return                                                   # the SIMT kernel stages fp32 w_gate^T in smem: shape unsupported
+    lib = _lib.load()
+    old = lib.m3_set_knob(2, 9)                                  # M3_KNOB_MOVER_VARIANT = 9: exact fp32 SIMT router term
+    try:
+        simt = ops.dispatch_bwd(dxq.to(dev), plan, T, K, out_dtype=torch.float32, dz=dz.to(dev), w_gate=wg.to(dev))
+    finally:
+        lib.m3_set_knob(2, old)
+    assert float((simt.double().cpu() - exact).abs().max() / exact.abs().max()) < 1e-5

@@ -72,7 +72,15 @@ lib.m3_set_knob(KNOB_MOVER, 0)
 d_mma = ops.dispatch_bwd(dxq_, plan, T, K, dz=dz_, w_gate=wg)
 print(f"  mma.sync router term vs SIMT: max abs diff {(d_mma - d_simt).abs().max().item():.3e}, "
       f"normalised {((d_mma - d_simt).norm() / d_simt.norm()).item():.3e}")
-timed("dispatch_bwd (+ dz @ w_gate^T) [mma.sync bf16 router term]", lambda: ops.dispatch_bwd(dxq_, plan, T, K, dz=dz_, w_gate=wg))
+timed("dispatch_bwd (+ dz @ w_gate^T) [mma.sync bf16 router term, 2 rows/batch, 6 CTAs/SM (default)]", lambda: ops.dispatch_bwd(dxq_, plan, T, K, dz=dz_, w_gate=wg))
+lib.m3_set_knob(KNOB_MOVER, 8)
+d_mma2 = ops.dispatch_bwd(dxq_, plan, T, K, dz=dz_, w_gate=wg)
+print("  1 row per batch at 8 CTAs/SM: bits equal", torch.equal(d_mma2, d_mma))
+timed("dispatch_bwd (+ dz @ w_gate^T) [mma.sync, 1 row/batch, 8 CTAs/SM]", lambda: ops.dispatch_bwd(dxq_, plan, T, K, dz=dz_, w_gate=wg))
+lib.m3_set_knob(KNOB_MOVER, 7)
+timed("dispatch_bwd (+ dz @ w_gate^T) [mma.sync, 4 rows/batch, 4 CTAs/SM]", lambda: ops.dispatch_bwd(dxq_, plan, T, K, dz=dz_, w_gate=wg))
+lib.m3_set_knob(KNOB_MOVER, 0)
+timed("dispatch_bwd (+ dz @ w_gate^T) [mma.sync bf16 router term, 2 rows/batch, 6 CTAs/SM (default)]", lambda: ops.dispatch_bwd(dxq_, plan, T, K, dz=dz_, w_gate=wg))
 timed("gate_bwd", lambda: ops.gate_bwd(x, wg, g.noisy_logits, g.idx_full, K, dscore=g.score))
 timed("route_plan", lambda: ops.route_plan(g.idx, E, imp_partial=g.imp_partial, load_partial=g.load_partial))
 timed("torch x.clone() (59 MB read + 59 MB write)", lambda: x.clone())
