@@ -159,6 +159,26 @@ int m3_combine_bwd(const void* g, int g_dtype, const void* yq, int yq_dtype, con
  */
 size_t m3_ffn_workspace_bytes(int dtype, int cap_rows, int D, int H, int E, int backward);
 size_t m3_ffn_saved_bytes(int dtype, int cap_rows, int H);
+/* Gather path (bf16, single GPU): the dispatched queue xq is never materialised.  fc1 and the dW1 GEMM read their
+ * queue rows straight from the [T, D] bf16 token matrix with TMA tile::gather4, four rows per instruction, through
+ * row_token[queue row] = token (values >= T mark padding rows and read as zeros).  Replaces the same reference
+ * seams as m3_dispatch_fwd + m3_ffn_fwd / m3_ffn_bwd (fmoe MOEScatter.forward + FMoELinear,
+ * custom_moe_layer.py:36-44,255-257); results are bit-identical to that pair.
+ *   m3_gather_prepare: ONE launch that casts x fp32 -> x_bf16 (x = x_bf16 = NULL: tokens are bf16 already) and
+ *                      builds row_token [cap_rows] int32 from the route plan (pos, counts, offsets).
+ *   m3_ffn_fwd_gather / m3_ffn_bwd_gather: as m3_ffn_fwd / m3_ffn_bwd (dtype bf16; workspace / saved sizes from
+ *                      m3_ffn_workspace_bytes / m3_ffn_saved_bytes) with (x_bf16, row_token, T) in place of xq.
+ *   D % 64 == 0. */
+int m3_gather_prepare(const float* x, int T, int D, const int32_t* pos, const int32_t* counts,
+                      const int32_t* offsets, int K, int E, void* x_bf16, int32_t* row_token, m3_stream_t stream);
+int m3_ffn_fwd_gather(const void* x_bf16, const int32_t* row_token, int T, const int32_t* offsets,
+                      const int32_t* tile_expert, int cap_rows, int E, int D, int H, const void* w1,
+                      const float* b1, const void* w2, const float* b2, void* saved, void* yq, void* workspace,
+                      size_t workspace_bytes, m3_stream_t stream);
+int m3_ffn_bwd_gather(const void* x_bf16, const int32_t* row_token, int T, const void* saved, const void* dyq,
+                      const int32_t* offsets, const int32_t* tile_expert, int cap_rows, int E, int D, int H,
+                      const void* w1t, const void* w2t, void* dxq, float* dw1, float* db1, float* dw2,
+                      float* db2, void* workspace, size_t workspace_bytes, m3_stream_t stream);
 /* Process-wide tuning knob: SMs the persistent tcgen05 GEMMs may occupy (default / out of range: all 148).
  * The overlapped expert-parallel mode lowers it so that NVLink row movers run beside a GEMM. */
 int m3_set_gemm_sm_limit(int sms);

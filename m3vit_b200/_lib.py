@@ -42,6 +42,9 @@ SIGNATURES = {
     "m3_combine_bwd": (_i, [_p, _i, _p, _i, _p, _p, _p, _p, _i, _i, _i, _i, _p, _i, _p, _p]),
     "m3_ffn_workspace_bytes": (_sz, [_i, _i, _i, _i, _i, _i]),
     "m3_ffn_saved_bytes": (_sz, [_i, _i, _i]),
+    "m3_gather_prepare": (_i, [_p, _i, _i, _p, _p, _p, _i, _i, _p, _p, _p]),
+    "m3_ffn_fwd_gather": (_i, [_p, _p, _i, _p, _p, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _sz, _p]),
+    "m3_ffn_bwd_gather": (_i, [_p, _p, _i, _p, _p, _p, _p, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p, _sz, _p]),
     "m3_set_gemm_sm_limit": (_i, [_i]),
     "m3_set_knob": (_i, [_i, _i]),
     "m3_ffn_fwd": (_i, [_i, _p, _p, _p, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _sz, _p]),

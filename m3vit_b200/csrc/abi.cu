@@ -23,6 +23,15 @@ int m3_ffn_bwd_bf16(const void* xq, const void* hpre, const void* dyq, const int
                     const void* w1, const void* w2, const void* w1t, const void* w2t, void* dxq, float* dw1,
                     float* db1, float* dw2, float* db2, void* workspace, size_t workspace_bytes, cudaStream_t st);
 
+int m3_ffn_fwd_bf16_gather(const void* x_bf16, const int32_t* row_token, int T, const int32_t* offsets,
+                           const int32_t* tile_expert, int cap_rows, int E, int D, int H, const void* w1, const float* b1,
+                           const void* w2, const float* b2, void* saved, void* yq, void* workspace,
+                           size_t workspace_bytes, cudaStream_t st);
+int m3_ffn_bwd_bf16_gather(const void* x_bf16, const int32_t* row_token, int T, const void* saved, const void* dyq,
+                           const int32_t* offsets, const int32_t* tile_expert, int cap_rows, int E, int D, int H,
+                           const void* w1t, const void* w2t, void* dxq, float* dw1, float* db1, float* dw2, float* db2,
+                           void* workspace, size_t workspace_bytes, cudaStream_t st);
+
 extern "C" int m3_abi_version(void) { return M3_ABI_VERSION; }
 
 extern "C" const char* m3_status_string(int status) {
@@ -128,6 +137,34 @@ extern "C" int m3_ffn_bwd(int dtype, const void* xq, const void* hpre, const voi
                            dw1, db1, dw2, db2, workspace, workspace_bytes, st);
   }
   return M3_ERR_UNSUPPORTED;
+}
+
+extern "C" int m3_ffn_fwd_gather(const void* x_bf16, const int32_t* row_token, int T, const int32_t* offsets,
+                                 const int32_t* tile_expert, int cap_rows, int E, int D, int H, const void* w1,
+                                 const float* b1, const void* w2, const float* b2, void* saved, void* yq, void* workspace,
+                                 size_t workspace_bytes, m3_stream_t stream) {
+  M3_CHECK_ARG(x_bf16 && row_token && offsets && tile_expert && w1 && b1 && w2 && b2 && yq && workspace);
+  M3_CHECK_ARG(T >= 1 && cap_rows >= 0 && E >= 1 && D > 0 && H > 0);
+  M3_CHECK_SHAPE(cap_rows % M3_PAD_ROWS == 0 && D % 64 == 0);
+  M3_CHECK_ALIGN16(x_bf16); M3_CHECK_ALIGN16(row_token); M3_CHECK_ALIGN16(yq); M3_CHECK_ALIGN16(w1); M3_CHECK_ALIGN16(w2);
+  M3_CHECK_ALIGN16(workspace);
+  if (saved) M3_CHECK_ALIGN16(saved);
+  if (cap_rows == 0) return M3_OK;
+  return m3_ffn_fwd_bf16_gather(x_bf16, row_token, T, offsets, tile_expert, cap_rows, E, D, H, w1, b1, w2, b2, saved, yq,
+                                workspace, workspace_bytes, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int m3_ffn_bwd_gather(const void* x_bf16, const int32_t* row_token, int T, const void* saved, const void* dyq,
+                                 const int32_t* offsets, const int32_t* tile_expert, int cap_rows, int E, int D, int H,
+                                 const void* w1t, const void* w2t, void* dxq, float* dw1, float* db1, float* dw2,
+                                 float* db2, void* workspace, size_t workspace_bytes, m3_stream_t stream) {
+  M3_CHECK_ARG(x_bf16 && row_token && saved && dyq && offsets && tile_expert && w1t && w2t && dxq && dw1 && db1 && dw2 && db2);
+  M3_CHECK_ARG(T >= 1 && cap_rows >= 0 && E >= 1 && D > 0 && H > 0 && workspace);
+  M3_CHECK_SHAPE(cap_rows % M3_PAD_ROWS == 0 && D % 64 == 0);
+  M3_CHECK_ALIGN16(x_bf16); M3_CHECK_ALIGN16(row_token); M3_CHECK_ALIGN16(saved); M3_CHECK_ALIGN16(dyq); M3_CHECK_ALIGN16(dxq);
+  M3_CHECK_ALIGN16(dw1); M3_CHECK_ALIGN16(dw2); M3_CHECK_ALIGN16(workspace);
+  return m3_ffn_bwd_bf16_gather(x_bf16, row_token, T, saved, dyq, offsets, tile_expert, cap_rows, E, D, H, w1t, w2t, dxq,
+                                dw1, db1, dw2, db2, workspace, workspace_bytes, static_cast<cudaStream_t>(stream));
 }
 
 // ------------------------------------------------------------------ debug: SM occupier

@@ -33,7 +33,10 @@ constexpr int kThreads = 192;        // wgrad kernel: 2 + 4 warps
 // gg kernel epilogue warps: EW = 8 (one warp per TMEM lane quarter and accumulator buffer, 64-column register
 // blocks) or EW = 16 (two warps per quarter and buffer, interleaved 32-column blocks: twice the warps to hide
 // the dependent erf/exp chains of the GELU epilogues behind, at half the registers per thread)
-constexpr int gg_threads(int EW) { return 64 + EW * 32; }
+// GATHER (fc1 reading its A rows straight from the token matrix with TMA gather4): 32 gathers per stage instead of one
+// tiled load is more than one warp can issue per k-chunk, so two more producer warps (behind the epilogue warps) share them
+constexpr int kGatherWarps = 3;
+constexpr int gg_threads(int EW, bool gather = false) { return 64 + EW * 32 + (gather ? (kGatherWarps - 1) * 32 : 0); }
 constexpr int BOX_BYTES = BM * 64 * 2;  // one [128 rows][64 bf16] swizzle-128B box = 16 KB
 
 enum { EPI_STORE = 0, EPI_BIAS = 1, EPI_FC1 = 2, EPI_DGELU = 3 };
@@ -49,6 +52,7 @@ struct GGParams {
   int dbg;                     // M3_KNOB_DEBUG (measurement only, results are garbage): 1 = no MMAs, 2 = no TMA loads
   unsigned long long* trace;   // m3_debug_trace_buffer
   int trace_cap;
+  const int32_t* row_token;    // GATHER: [cap_rows] token of every queue row (>= T for padding rows: reads as zeros)
 };
 
 // BRES ("B resident", opt-in: M3_KNOB_BRES = 1): the weight tile of one (expert, N-tile) stays in shared memory across
@@ -97,8 +101,8 @@ __device__ __forceinline__ uint32_t box_off(int r, int c) {
   return (uint32_t)r * 64u + (uint32_t)((c ^ ((r >> 1) & 3)) << 4);
 }
 
-template <int BN, int EPI, int NCTA, int EW, bool BRES, int CWP>
-__global__ void __launch_bounds__(gg_threads(EW), 1)
+template <int BN, int EPI, int NCTA, int EW, bool BRES, int CWP, bool GATHER = false>
+__global__ void __launch_bounds__(gg_threads(EW, GATHER), 1)
 gg_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
           const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmOut2,
           const __grid_constant__ CUtensorMap tmAux, GGParams p) {
@@ -183,7 +187,54 @@ gg_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
   // Both loops walk the smem ring in rounds of STAGES k-chunks with the stage index a compile-time constant (every
   // barrier address and descriptor is base + immediate); the flat chunk index f runs over all tiles of this unit.
   const int F = my_tiles * kchunks;
-  if (warp == 0) {
+  // GATHER: producer warp pw (0 = warp 0, 1.. = the helper warps behind the epilogue warps) issues row groups
+  // [g0, g1) of every A stage; lane l < g1 - g0 keeps the 4 token indices of group g0 + l in registers
+  constexpr int kGroups = BM / 4;     // 32 gather4 per [128 x 64] A stage
+  auto gather_share = [&](int pw, int& g0, int& g1) {
+    const int per = (kGroups + kGatherWarps - 1) / kGatherWarps;
+    g0 = pw * per;
+    g1 = g0 + per < kGroups ? g0 + per : kGroups;
+  };
+  auto load_idx = [&](int ti, int g0, int g1) -> int4 {
+    int4 v = make_int4(0, 0, 0, 0);
+    if (ti < my_tiles && lane < g1 - g0)
+      v = __ldg(reinterpret_cast<const int4*>(p.row_token + (int64_t)tile_mblk(ti) * BM) + g0 + lane);
+    return v;
+  };
+  auto issue_gathers = [&](const int4& idx, int g0, int g1, uint32_t sa, uint32_t bar, int col) {
+#pragma unroll
+    for (int g = 0; g < (kGroups + kGatherWarps - 1) / kGatherWarps; ++g) {
+      if (g0 + g < g1) {
+        const int r0 = __shfl_sync(0xffffffffu, idx.x, g), r1 = __shfl_sync(0xffffffffu, idx.y, g);
+        const int r2 = __shfl_sync(0xffffffffu, idx.z, g), r3 = __shfl_sync(0xffffffffu, idx.w, g);
+        if (NCTA == 2) tma_gather4_2sm_elect(sa + (g0 + g) * 512, &tmA, bar, col, r0, r1, r2, r3);
+        else tma_gather4_elect(sa + (g0 + g) * 512, &tmA, bar, col, r0, r1, r2, r3);
+      }
+    }
+  };
+  if (GATHER && warp >= 2 + EW) {
+    // helper producer: same ring walk as warp 0, gathers only (warp 0 posts the expected bytes and loads B)
+    int g0, g1;
+    gather_share(warp - (2 + EW) + 1, g0, g1);
+    const uint32_t smem_base = smem_u32(smem);
+    const uint32_t full0 = NCTA == 2 ? mapa_u32(smem_u32(&full[0]), 0) : smem_u32(&full[0]);
+    uint32_t phase = 0;
+    int ti = 0, kc = 0;
+    int4 cur = make_int4(0, 0, 0, 0), nxt = load_idx(0, g0, g1);
+    for (int f0 = 0; f0 < F; f0 += STAGES) {
+#pragma unroll
+      for (int st = 0; st < STAGES; ++st) {
+        if (f0 + st < F) {
+          if (kc == 0) { cur = nxt; nxt = load_idx(ti + 1, g0, g1); }
+          mbar_wait(&empty[st], phase ^ 1);
+          __syncwarp();
+          issue_gathers(cur, g0, g1, smem_base + st * Cfg::STAGE, full0 + st * 8, kc * BK);
+          if (++kc == kchunks) { kc = 0; ++ti; }
+        }
+      }
+      phase ^= 1;
+    }
+  } else if (warp == 0) {
     const uint32_t smem_base = smem_u32(smem), bres_base = smem_u32(bres);
     const bool no_tma = (p.dbg & 2) != 0;
     const uint32_t full0 = NCTA == 2 ? mapa_u32(smem_u32(&full[0]), 0) : smem_u32(&full[0]);   // leader's barriers
@@ -193,11 +244,15 @@ gg_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
     int ti = 0, kc = 0, m_blk = 0, b_row = 0;
     int cur_e = -1, n_loadB = 0;      // BRES: expert whose weights are resident, number of weight loads issued so far
     bool loadB = false;
+    int gg0 = 0, gg1 = 0;
+    if (GATHER) gather_share(0, gg0, gg1);
+    int4 gcur = make_int4(0, 0, 0, 0), gnxt = GATHER ? load_idx(0, gg0, gg1) : make_int4(0, 0, 0, 0);
     for (int f0 = 0; f0 < F; f0 += STAGES) {
 #pragma unroll
       for (int st = 0; st < STAGES; ++st) {
         if (f0 + st < F) {
           if (kc == 0) {
+            if (GATHER) { gcur = gnxt; gnxt = load_idx(ti + 1, gg0, gg1); }
             m_blk = tile_mblk(ti);
             const int e = p.tile_expert[(m_blk * BM) / M3_PAD_ROWS];
             b_row = e * p.N + tile_nblk(ti) * BN + (int)cta_rank * (BN / NCTA);
@@ -229,13 +284,15 @@ gg_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
             } else {
               if (leader_cta) mbar_expect_tx_elect(&full[st], Cfg::STAGE * NCTA);
               else mbar_arrive_remote_elect(bar);
-              tma_load_2d_2sm_elect(sa, &tmA, bar, kc * BK, m_blk * BM);
               if (!BRES) tma_load_2d_2sm_elect(sa + Cfg::A_BYTES, &tmB, bar, kc * BK, b_row);
+              if (GATHER) issue_gathers(gcur, gg0, gg1, sa, bar, kc * BK);
+              else tma_load_2d_2sm_elect(sa, &tmA, bar, kc * BK, m_blk * BM);
             }
           } else {
             mbar_expect_tx_elect(&full[st], Cfg::STAGE);
-            tma_load_2d_elect(sa, &tmA, bar, kc * BK, m_blk * BM);
             if (!BRES) tma_load_2d_elect(sa + Cfg::A_BYTES, &tmB, bar, kc * BK, b_row);
+            if (GATHER) issue_gathers(gcur, gg0, gg1, sa, bar, kc * BK);
+            else tma_load_2d_elect(sa, &tmA, bar, kc * BK, m_blk * BM);
           }
           if (++kc == kchunks) {
             kc = 0;
@@ -312,7 +369,7 @@ gg_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
       }
       trc.done();
     }
-  } else {
+  } else if (warp < 2 + EW) {
     // ---- epilogue.  Every warp is an independent pipeline: TMEM -> registers -> bias / GELU / GELU'
     // (packed f32x2) -> bf16 -> its private swizzled [32 x 64] smem box -> its own TMA store.  No
     // CTA-wide barrier.  Warp w reads TMEM lanes 32*(w%4).. (hardware rule); warps 2-5 serve
@@ -470,6 +527,7 @@ struct WGParams {
   int dbg;        // M3_KNOB_DEBUG (measurement only): 1 = no MMAs, 2 = no TMA loads
   unsigned long long* trace;   // m3_debug_trace_buffer
   int trace_cap;
+  const int32_t* row_token;    // GATHER: X2 is the token matrix, row_token[queue row] = token (>= T: zeros)
 };
 
 template <int BN>
@@ -486,8 +544,10 @@ struct WGCfg {
   static_assert(BN + 16 <= TMEM_COLS, "TMEM");
 };
 
-template <int BN>
-__global__ void __launch_bounds__(kThreads, 1)
+// GATHER: X2 rows are gathered from the [T][N] token matrix with TMA gather4 (16 gathers per [64 x 64] box); two
+// helper producer warps (6, 7) share them with warp 0
+template <int BN, bool GATHER = false>
+__global__ void __launch_bounds__(kThreads + (GATHER ? (kGatherWarps - 1) * 32 : 0), 1)
 wgrad_kernel(const __grid_constant__ CUtensorMap tm1, const __grid_constant__ CUtensorMap tm2, WGParams p) {
   using Cfg = WGCfg<BN>;
   constexpr int STAGES = Cfg::STAGES;
@@ -510,7 +570,7 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tm1, const __grid_constant__ CU
   if (with_db) {
     for (int st = 0; st < STAGES; ++st) {
       uint32_t* ones = reinterpret_cast<uint32_t*>(smem + st * Cfg::STAGE + Cfg::TMA_BYTES);
-      for (int i = threadIdx.x; i < Cfg::ONES_BYTES / 4; i += kThreads) ones[i] = 0x3F803F80u;
+      for (int i = threadIdx.x; i < Cfg::ONES_BYTES / 4; i += blockDim.x) ones[i] = 0x3F803F80u;
     }
     fence_proxy_async_smem();
   }
@@ -536,16 +596,59 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tm1, const __grid_constant__ CU
   const int r0 = p.offsets[e] + c_begin * BK;
   const int kchunks = c_end - c_begin;
 
-  if (warp == 0) {
+  // GATHER: producer warp pw issues row groups [g0, g1) of the 16 groups of a 64-row chunk, for every 64-column box of X2;
+  // lane l < g1 - g0 keeps the 4 token indices of group g0 + l, fetched one chunk ahead
+  constexpr int kGroups = BK / 4;
+  constexpr int kPerWarp = (kGroups + kGatherWarps - 1) / kGatherWarps;
+  auto load_idx = [&](int kc, int g0, int g1) -> int4 {
+    int4 v = make_int4(0, 0, 0, 0);
+    if (kc < kchunks && lane < g1 - g0)
+      v = __ldg(reinterpret_cast<const int4*>(p.row_token + r0 + (int64_t)kc * BK) + g0 + lane);
+    return v;
+  };
+  auto issue_gathers = [&](const int4& idx, int g0, int g1, uint32_t sb, uint32_t bar) {
+#pragma unroll
+    for (int g = 0; g < kPerWarp; ++g) {
+      if (g0 + g < g1) {
+        const int q0 = __shfl_sync(0xffffffffu, idx.x, g), q1 = __shfl_sync(0xffffffffu, idx.y, g);
+        const int q2 = __shfl_sync(0xffffffffu, idx.z, g), q3 = __shfl_sync(0xffffffffu, idx.w, g);
+#pragma unroll
+        for (int b = 0; b < BN / 64; ++b)
+          tma_gather4_elect(sb + b * Cfg::BOX + (g0 + g) * 512, &tm2, bar, n0 + b * 64, q0, q1, q2, q3);
+      }
+    }
+  };
+  if (GATHER && warp >= 6) {
+    const int pw = warp - 6 + 1, g0 = pw * kPerWarp, g1 = g0 + kPerWarp < kGroups ? g0 + kPerWarp : kGroups;
+    const uint32_t smem_base = smem_u32(smem), full0 = smem_u32(&full[0]);
+    uint32_t phase = 0;
+    int4 cur = make_int4(0, 0, 0, 0), nxt = load_idx(0, g0, g1);
+    for (int kc0 = 0; kc0 < kchunks; kc0 += STAGES) {
+#pragma unroll
+      for (int st = 0; st < STAGES; ++st) {
+        if (kc0 + st < kchunks) {
+          cur = nxt;
+          nxt = load_idx(kc0 + st + 1, g0, g1);
+          mbar_wait(&empty[st], phase ^ 1);
+          __syncwarp();
+          issue_gathers(cur, g0, g1, smem_base + st * Cfg::STAGE + Cfg::A_BYTES, full0 + st * 8);
+        }
+      }
+      phase ^= 1;
+    }
+  } else if (warp == 0) {
     // converged warp, elected lane issues; ring walked in rounds with a compile-time stage index (see gg_kernel)
     uint32_t phase = 0;
     const uint32_t smem_base = smem_u32(smem), full0 = smem_u32(&full[0]);
     const bool no_tma = (p.dbg & 2) != 0;
     Tracer trc(p.trace, p.trace_cap, 0);
+    constexpr int gg1 = kPerWarp < kGroups ? kPerWarp : kGroups;
+    int4 gcur = make_int4(0, 0, 0, 0), gnxt = GATHER ? load_idx(0, 0, gg1) : make_int4(0, 0, 0, 0);
     for (int kc0 = 0; kc0 < kchunks; kc0 += STAGES) {
 #pragma unroll
       for (int st = 0; st < STAGES; ++st) {
         if (kc0 + st < kchunks) {
+          if (GATHER) { gcur = gnxt; gnxt = load_idx(kc0 + st + 1, 0, gg1); }
           trc.ev(0x00, kc0 + st);
           mbar_wait(&empty[st], phase ^ 1);
           trc.ev(0x01, kc0 + st);
@@ -558,8 +661,12 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tm1, const __grid_constant__ CU
             const int r = r0 + (kc0 + st) * BK;
 #pragma unroll
             for (int b = 0; b < BM / 64; ++b) tma_load_2d_elect(sa + b * Cfg::BOX, &tm1, bar, m0 + b * 64, r);
+            if (GATHER) {
+              issue_gathers(gcur, 0, gg1, sa + Cfg::A_BYTES, bar);
+            } else {
 #pragma unroll
-            for (int b = 0; b < BN / 64; ++b) tma_load_2d_elect(sa + Cfg::A_BYTES + b * Cfg::BOX, &tm2, bar, n0 + b * 64, r);
+              for (int b = 0; b < BN / 64; ++b) tma_load_2d_elect(sa + Cfg::A_BYTES + b * Cfg::BOX, &tm2, bar, n0 + b * 64, r);
+            }
           }
         }
       }
@@ -601,7 +708,7 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tm1, const __grid_constant__ CU
     }
     umma_commit_elect(tfull);
     trc.done();
-  } else {
+  } else if (warp < 6) {
     const int q = warp & 3;
     const int row = m0 + q * 32 + lane;
     const int64_t se = (int64_t)split * p.E + e;
@@ -713,10 +820,10 @@ static int epi_warps() {
   return kDefaultEpiWarps[EPI];                        // (bit 0x200 selects the block width, see launch_gg)
 }
 
-template <int BN, int EPI, int EW, bool BRES, int CWP>
+template <int BN, int EPI, int EW, bool BRES, int CWP, bool GATHER = false>
 static int launch_gg_t(const CUtensorMap* maps, const GGParams& p, int max_tiles, cudaStream_t st) {
   using Cfg = GGCfg<BN, EPI, kGGNcta, EW, BRES, CWP>;
-  auto kern = gg_kernel<BN, EPI, kGGNcta, EW, BRES, CWP>;
+  auto kern = gg_kernel<BN, EPI, kGGNcta, EW, BRES, CWP, GATHER>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
   if (e != cudaSuccess) return (int)e;
   int grid = max_tiles < g_gemm_sms ? max_tiles : g_gemm_sms;
@@ -730,7 +837,7 @@ static int launch_gg_t(const CUtensorMap* maps, const GGParams& p, int max_tiles
   }
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(grid);
-  cfg.blockDim = dim3(gg_threads(EW));
+  cfg.blockDim = dim3(gg_threads(EW, GATHER));
   cfg.dynamicSmemBytes = Cfg::SMEM;
   cfg.stream = st;
   cudaLaunchAttribute attr[2];
@@ -750,13 +857,16 @@ static int launch_gg_t(const CUtensorMap* maps, const GGParams& p, int max_tiles
 
 // A [cap_rows][Kd] bf16, B [E*N][Kd] bf16 -> out [cap_rows][N] (+ out2 / aux of the same shape)
 template <int EPI>
+// gather_rows > 0 (EPI_FC1 only): A is the [gather_rows][Kd] bf16 TOKEN matrix and p.row_token maps queue rows to tokens
 static int launch_gg(const void* A, const void* B, void* out, void* out2, const void* aux, GGParams p, int cap_rows,
-                     cudaStream_t st) {
+                     cudaStream_t st, int gather_rows = 0) {
   constexpr bool heavy = (EPI == EPI_FC1 || EPI == EPI_DGELU);
   const int BN = pick_bn(p.N, heavy);
   if (BN == 0 || p.Kd % BK != 0 || cap_rows % (BM * kGGNcta) != 0) return M3_ERR_SHAPE;
+  if (gather_rows > 0 && (EPI != EPI_FC1 || p.row_token == nullptr)) return M3_ERR_ARG;
   CUtensorMap maps[5];
-  int rc = make_map(&maps[0], A, (uint64_t)cap_rows, (uint64_t)p.Kd, BM);
+  int rc = gather_rows > 0 ? make_map(&maps[0], A, (uint64_t)gather_rows, (uint64_t)p.Kd, 1)     // box {64, 1}: tile::gather4
+                           : make_map(&maps[0], A, (uint64_t)cap_rows, (uint64_t)p.Kd, BM);
   if (rc) return rc;
   rc = make_map(&maps[1], B, (uint64_t)p.E * p.N, (uint64_t)p.Kd, (uint32_t)(BN / kGGNcta));
   if (rc) return rc;
@@ -787,6 +897,15 @@ static int launch_gg(const void* A, const void* B, void* out, void* out2, const 
   (ew == 16 ? launch_gg_t<BNV, EPI, 16, true, 32>(maps, p, max_tiles, st)                       \
             : narrow ? launch_gg_t<BNV, EPI, 8, true, 32>(maps, p, max_tiles, st)               \
                      : launch_gg_t<BNV, EPI, 8, true, 64>(maps, p, max_tiles, st))
+  if constexpr (EPI == EPI_FC1) {
+    if (gather_rows > 0) {
+      if (BN == 192) return ew == 16 ? launch_gg_t<192, EPI, 16, false, 32, true>(maps, p, max_tiles, st)
+                                     : launch_gg_t<192, EPI, 8, false, 64, true>(maps, p, max_tiles, st);
+      if (BN == 128) return ew == 16 ? launch_gg_t<128, EPI, 16, false, 32, true>(maps, p, max_tiles, st)
+                                     : launch_gg_t<128, EPI, 8, false, 64, true>(maps, p, max_tiles, st);
+      return M3_ERR_SHAPE;
+    }
+  }
   switch (BN) {
     case 128: return bres ? M3_GG_EW_BRES(128) : M3_GG_EW(128);
     case 192: return bres ? M3_GG_EW_BRES(192) : M3_GG_EW(192);
@@ -822,24 +941,33 @@ static size_t wgrad_ws_bytes(int E, int M, int N) {
 }
 
 // dW [E][M][N] fp32 = X1[rows][M]^T X2[rows][N] per expert (+ db [E][M] = column sums of X1)
+// row_token != NULL: X2 is the [gather_rows][N] bf16 token matrix, its queue rows are gathered (tile::gather4)
 static int launch_wgrad(const void* X1, const void* X2, const int32_t* offsets, int cap_rows, int E, int M, int N,
-                        float* dW, float* db, float* ws, cudaStream_t st) {
+                        float* dW, float* db, float* ws, cudaStream_t st, const int32_t* row_token = nullptr,
+                        int gather_rows = 0) {
   constexpr int BN = 128;
   if (M % BM != 0 || N % BN != 0 || (M * (int64_t)N) % 4 != 0) return M3_ERR_SHAPE;
   CUtensorMap t1, t2;
   int rc = make_map(&t1, X1, (uint64_t)cap_rows, (uint64_t)M, BK);
   if (rc) return rc;
-  rc = make_map(&t2, X2, (uint64_t)cap_rows, (uint64_t)N, BK);
+  rc = row_token ? make_map(&t2, X2, (uint64_t)gather_rows, (uint64_t)N, 1) : make_map(&t2, X2, (uint64_t)cap_rows, (uint64_t)N, BK);
   if (rc) return rc;
   using Cfg = WGCfg<BN>;
-  auto kern = wgrad_kernel<BN>;
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
-  if (e != cudaSuccess) return (int)e;
   const int S = wgrad_splits(E, M, N);
   float* pW = S > 1 ? ws : dW;
   float* pb = S > 1 ? ws + (size_t)S * E * M * N : db;
-  WGParams p{offsets, M, N, pW, pb, E, g_knobs[M3_KNOB_DEBUG], trace_buf_for_this_launch(), g_trace_cap};
-  launch_k(kern, dim3(M / BM, N / BN, E * S), dim3(kThreads), Cfg::SMEM, st, t1, t2, p);
+  WGParams p{offsets, M, N, pW, pb, E, g_knobs[M3_KNOB_DEBUG], trace_buf_for_this_launch(), g_trace_cap, row_token};
+  if (row_token) {
+    auto kern = wgrad_kernel<BN, true>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
+    if (e != cudaSuccess) return (int)e;
+    launch_k(kern, dim3(M / BM, N / BN, E * S), dim3(kThreads + (kGatherWarps - 1) * 32), Cfg::SMEM, st, t1, t2, p);
+  } else {
+    auto kern = wgrad_kernel<BN, false>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
+    if (e != cudaSuccess) return (int)e;
+    launch_k(kern, dim3(M / BM, N / BN, E * S), dim3(kThreads), Cfg::SMEM, st, t1, t2, p);
+  }
   M3_LAUNCH_CHECK();
   if (S > 1) {
     const int64_t n4 = (int64_t)E * M * N / 4;
@@ -949,6 +1077,49 @@ int m3_ffn_bwd_bf16(const void* xq, const void* saved, const void* dyq, const in
   rc = launch_wgrad(dyq, h, offsets, cap_rows, E, D, H, dw2, db2, part, st);
   if (rc) return rc;
   return launch_wgrad(dhpre, xq, offsets, cap_rows, E, H, D, dw1, db1, part, st);
+}
+
+// Gather variants: no dispatched queue xq.  x_bf16 is the [T][D] token matrix, row_token[queue row] the token whose copy that
+// row would hold (>= T: a padding row, reads as zeros).  Everything downstream of fc1 is unchanged.
+int m3_ffn_fwd_bf16_gather(const void* x_bf16, const int32_t* row_token, int T, const int32_t* offsets,
+                           const int32_t* tile_expert, int cap_rows, int E, int D, int H, const void* w1, const float* b1,
+                           const void* w2, const float* b2, void* saved, void* yq, void* workspace,
+                           size_t workspace_bytes, cudaStream_t st) {
+  if (workspace == nullptr || workspace_bytes < m3_ffn_bf16_workspace_bytes(cap_rows, D, H, E, 0)) return M3_ERR_WORKSPACE;
+  g_trace_launch_idx = 0;
+  const size_t hbytes = align256((size_t)cap_rows * H * 2);
+  bf16* gp = static_cast<bf16*>(saved);
+  bf16* h = saved ? reinterpret_cast<bf16*>(static_cast<uint8_t*>(saved) + hbytes) : static_cast<bf16*>(workspace);
+  GGParams p{};
+  p.offsets = offsets; p.tile_expert = tile_expert; p.E = E;
+  p.N = H; p.Kd = D; p.bias = b1; p.save_out2 = saved != nullptr; p.row_token = row_token;
+  int rc = launch_gg<EPI_FC1>(x_bf16, w1, h, gp, nullptr, p, cap_rows, st, T);
+  if (rc) return rc;
+  p.N = D; p.Kd = H; p.bias = b2; p.save_out2 = 0; p.row_token = nullptr;
+  return launch_gg<EPI_BIAS>(h, w2, yq, nullptr, nullptr, p, cap_rows, st);
+}
+
+int m3_ffn_bwd_bf16_gather(const void* x_bf16, const int32_t* row_token, int T, const void* saved, const void* dyq,
+                           const int32_t* offsets, const int32_t* tile_expert, int cap_rows, int E, int D, int H,
+                           const void* w1t, const void* w2t, void* dxq, float* dw1, float* db1, float* dw2, float* db2,
+                           void* workspace, size_t workspace_bytes, cudaStream_t st) {
+  if (workspace_bytes < m3_ffn_bf16_workspace_bytes(cap_rows, D, H, E, 1)) return M3_ERR_WORKSPACE;
+  g_trace_launch_idx = 0;
+  const size_t hbytes = align256((size_t)cap_rows * H * 2);
+  bf16* dhpre = static_cast<bf16*>(workspace);
+  float* part = reinterpret_cast<float*>(static_cast<uint8_t*>(workspace) + 2 * hbytes);
+  const bf16* h = reinterpret_cast<const bf16*>(static_cast<const uint8_t*>(saved) + hbytes);
+  GGParams p{};
+  p.offsets = offsets; p.tile_expert = tile_expert; p.E = E;
+  p.N = H; p.Kd = D;
+  int rc = launch_gg<EPI_DGELU>(dyq, w2t, dhpre, nullptr, saved, p, cap_rows, st);
+  if (rc) return rc;
+  p.N = D; p.Kd = H;
+  rc = launch_gg<EPI_STORE>(dhpre, w1t, dxq, nullptr, nullptr, p, cap_rows, st);
+  if (rc) return rc;
+  rc = launch_wgrad(dyq, h, offsets, cap_rows, E, D, H, dw2, db2, part, st);
+  if (rc) return rc;
+  return launch_wgrad(dhpre, x_bf16, offsets, cap_rows, E, H, D, dw1, db1, part, st, row_token, T);   // dW1 = dz^T gather(x)
 }
 
 int m3_ffn_bf16_set_sm_limit(int sms) {

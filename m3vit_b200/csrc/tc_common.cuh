@@ -339,6 +339,29 @@ __device__ __forceinline__ void tma_load_2d_2sm_elect(uint32_t smem_dst, const C
       : "memory");
 }
 
+// TMA tile::gather4: four arbitrary rows (r0..r3) of a 2-D row-major tensor whose map has box {64 columns, 1 row} land as
+// four consecutive 128-byte rows of a SWIZZLE_128B box (the swizzle is a function of the shared-memory address, so 32
+// gathers fill the same [128 rows][64 bf16] operand tile one tiled load would); a row index past the tensor reads as zeros
+// (verified on a B200: tools/microbench/tma_gather4.cu).  Elected-lane issue like the other producer instructions.
+__device__ __forceinline__ void tma_gather4_elect(uint32_t smem_dst, const CUtensorMap* m, uint32_t bar, int c0, int r0,
+                                                  int r1, int r2, int r3) {
+  asm volatile(
+      "{\n.reg .pred q;\nelect.sync _|q, 0xffffffff;\n"
+      "@q cp.async.bulk.tensor.2d.shared::cluster.global.tile::gather4.mbarrier::complete_tx::bytes "
+      "[%0], [%1, {%3, %4, %5, %6, %7}], [%2];\n}\n" ::"r"(smem_dst),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(r0), "r"(r1), "r"(r2), "r"(r3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_gather4_2sm_elect(uint32_t smem_dst, const CUtensorMap* m, uint32_t bar_cluster_addr,
+                                                      int c0, int r0, int r1, int r2, int r3) {
+  asm volatile(
+      "{\n.reg .pred q;\nelect.sync _|q, 0xffffffff;\n"
+      "@q cp.async.bulk.tensor.2d.shared::cluster.global.tile::gather4.mbarrier::complete_tx::bytes.cta_group::2 "
+      "[%0], [%1, {%3, %4, %5, %6, %7}], [%2];\n}\n" ::"r"(smem_dst),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_cluster_addr), "r"(c0), "r"(r0), "r"(r1), "r"(r2), "r"(r3)
+      : "memory");
+}
+
 // ------------------------------------------------------------- tcgen05.ld
 // 32 lanes x 32 columns of fp32: thread i of the warp gets TMEM lane (lane_base + i), 32 consecutive columns.
 __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, float* v) {

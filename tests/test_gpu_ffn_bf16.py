@@ -199,3 +199,45 @@ def test_gemm_tuning_knobs_are_bit_identical(knob, value, name):
         lib.m3_set_knob(knob, old)
     for a, b, nm in zip(got, ref, ("yq", "dxq", "dw1", "db1", "dw2", "db2")):
         assert torch.equal(a, b), (name, nm)
+
+
+@pytest.mark.parametrize("T,K,E,D,H,skew", [
+    (3000, 4, 16, 384, 384, True),      # bench shape, skewed (an empty expert, ragged queues)
+    (777, 2, 8, 128, 256, False),
+    (1025, 4, 16, 768, 768, True),      # ViT-B width
+    (50, 1, 16, 384, 384, False),       # fewer tokens than one tile
+])
+def test_gather_path_is_bit_identical_to_dispatch_path(T, K, E, D, H, skew):
+    """fc1 / dW1 gathering their rows from the token matrix with TMA gather4 (m3_gather_prepare + m3_ffn_fwd_gather /
+    m3_ffn_bwd_gather) against m3_dispatch_fwd + m3_ffn_fwd / m3_ffn_bwd: the same bf16 values reach the same MMAs."""
+    from m3vit_b200 import ops
+    dev = torch.device("cuda:0")
+    x, idx, w1, b1, w2, b2 = make(T, K, E, D, H, seed=T + D + 1, skew=skew)
+    x, idx, b1, b2 = x.to(dev), idx.to(dev), b1.to(dev), b2.to(dev)
+    idx[::5, 0] = -1                                            # dropped slots
+    plan = ops.route_plan(idx, E)
+    n = int(plan.offsets[-1])
+    w1c, w1t = ops.cast_weights_bf16(w1.to(dev), True, True)
+    w2c, w2t = ops.cast_weights_bf16(w2.to(dev), True, True)
+    xq = ops.dispatch_fwd(x, plan, K, out_dtype=torch.bfloat16)
+    yq, hpre = ops.ffn_fwd(xq, plan, w1c, b1, w2c, b2)
+    dyq = torch.zeros_like(yq)
+    dyq[:n] = (torch.randn(n, D, device=dev) * 0.05).bfloat16()
+    ref = [yq[:n]] + [t if i else t[:n] for i, t in enumerate(ops.ffn_bwd(xq, hpre, dyq, plan, w1c, w2c, w1t, w2t))]
+
+    xb, row_token = ops.gather_prepare(x, plan, K)
+    assert torch.equal(xb, x.bfloat16())
+    rt = row_token[:n].cpu()
+    pos = plan.pos.cpu().long()
+    live = pos >= 0
+    assert torch.equal(rt[pos[live]], (torch.arange(T * K) // K)[live].int())      # inverse of the plan
+    pad = torch.ones(n, dtype=torch.bool)
+    pad[pos[live]] = False
+    assert bool((rt[pad] >= T).all())                                                # padding rows read as zeros
+    yq2, hpre2 = ops.ffn_fwd_gather(xb, row_token, plan, w1c, b1, w2c, b2)
+    got = [yq2[:n]] + [t if i else t[:n] for i, t in enumerate(ops.ffn_bwd_gather(xb, row_token, hpre2, dyq, plan, w1t, w2t))]
+    for a, b, nm in zip(got, ref, ("yq", "dxq", "dw1", "db1", "dw2", "db2")):
+        assert torch.equal(a, b), nm
+    # bf16 tokens: nothing to cast
+    xb2, rt2 = ops.gather_prepare(xb, plan, K)
+    assert xb2 is xb and torch.equal(rt2[:n], row_token[:n])

@@ -90,6 +90,17 @@ ref_f = ops.ffn_fwd(xq, plan, w1c, b1, w2c, b2)
 ref_b = ops.ffn_bwd(xq, hpre, dyq, plan, w1c, w2c, w1t, w2t)
 KNOB_DEBUG = 4
 KNOB_BRES = 6
+xb_, rt_ = ops.gather_prepare(x, plan, K)
+yq_g, hpre_g = ops.ffn_fwd_gather(xb_, rt_, plan, w1c, b1, w2c, b2)
+print("  gather path: yq bits equal to dispatch path:", same(yq_g, yq), " saved state:", same(hpre_g, hpre))
+gb = ops.ffn_bwd_gather(xb_, rt_, hpre_g, dyq, plan, w1t, w2t)
+rb = ops.ffn_bwd(xq, hpre, dyq, plan, w1c, w2c, w1t, w2t)
+print("  gather path: backward bits equal:", same(gb, rb))
+timed("gather_prepare (cast + row_token)", lambda: ops.gather_prepare(x, plan, K))
+timed("ffn_fwd        [dispatch path: reads xq]", lambda: ops.ffn_fwd(xq, plan, w1c, b1, w2c, b2))
+timed("ffn_fwd_gather [fc1 gathers from x_bf16]", lambda: ops.ffn_fwd_gather(xb_, rt_, plan, w1c, b1, w2c, b2))
+timed("ffn_bwd        [dispatch path]", lambda: ops.ffn_bwd(xq, hpre, dyq, plan, w1c, w2c, w1t, w2t))
+timed("ffn_bwd_gather [dW1 gathers from x_bf16]", lambda: ops.ffn_bwd_gather(xb_, rt_, hpre_g, dyq, plan, w1t, w2t))
 KNOB_DEBUG = 4
 for off in (1, 0):
     lib.m3_set_knob(KNOB_BRES, 0 if off else 1)
