@@ -6,14 +6,18 @@
 //
 //   gg_kernel    C[256-row pair tile, BN] = A[rows,Kd] * B_e[N,Kd]^T   (both K-major), one tile per CTA PAIR
 //                (cluster of 2, tcgen05.mma.cta_group::2: each CTA loads its 128 rows of A and half of B).
-//                Persistent pairs over (m_pair_tile, n_tile); warp 0 = TMA producer, warp 1 = MMA issuer
-//                (leader CTA, one thread) + TMEM owner, warps 2-9 = epilogue in two groups that alternate
-//                accumulator buffers (tcgen05.ld -> bias / GELU (+GELU') / x saved GELU' -> bf16 -> private
-//                swizzled smem box -> coalesced 128-byte row segments).  Smem ring of {A 128x64, B (BN/2)x64}
+//                Persistent pairs over (m_pair_tile, n_tile); warp 0 = TMA producer, warp 1 = MMA issuer (leader
+//                CTA) + TMEM owner - both run their loops CONVERGED, every TMA / MMA / commit predicated on
+//                elect.sync inside its asm block (tc_common.cuh) - warps 2.. = 8 or 16 epilogue warps in two groups
+//                that alternate accumulator buffers (tcgen05.ld -> bias / GELU (+GELU') / x saved GELU' -> bf16 ->
+//                private swizzled smem box -> coalesced row segments).  Smem ring of {A 128x64, B (BN/2)x64}
 //                stages (SWIZZLE_128B); TMEM accumulator double-buffered so the epilogue of tile i overlaps
-//                the MMAs of tile i+1.
+//                the MMAs of tile i+1.  Opt-in variants, all bit-identical: BRES (the expert's weight tile stays
+//                resident in smem), GATHER (fc1's A rows fetched from the token matrix with TMA gather4, no
+//                dispatched queue; two more producer warps), 32-column epilogue blocks.
 //   wgrad_kernel dW_e[M,N] = sum_rows X1[rows,M]^T X2[rows,N]     (both MN-major operands,
-//                read straight from the row-major queues - no transposes in memory)
+//                read straight from the row-major queues - no transposes in memory); same converged producer / MMA
+//                warps; GATHER: X2 rows gathered from the token matrix
 //
 // Expert queues are padded to M3_PAD_ROWS = 256 rows (route plan), so every tile is full and the expert
 // of a tile is a table lookup; padding rows are zero, so they add nothing to dW.
