@@ -108,7 +108,6 @@ __device__ __forceinline__ uint32_t box_off(int r, int c) {
 template <int BN, int EPI, int NCTA, int EW, bool BRES, int CWP, bool GATHER = false>
 __global__ void __launch_bounds__(gg_threads(EW, GATHER), 1)
 gg_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-          const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmOut2,
           const __grid_constant__ CUtensorMap tmAux, GGParams p) {
   using Cfg = GGCfg<BN, EPI, NCTA, EW, BRES, CWP>;
   constexpr int kEpiWarps = EW;
@@ -853,7 +852,7 @@ static int launch_gg_t(const CUtensorMap* maps, const GGParams& p, int max_tiles
   attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = g_knobs[M3_KNOB_PDL] ? 2 : 1;
-  e = cudaLaunchKernelEx(&cfg, kern, maps[0], maps[1], maps[2], maps[3], maps[4], p);
+  e = cudaLaunchKernelEx(&cfg, kern, maps[0], maps[1], maps[2], p);
   if (e != cudaSuccess) return (int)e;
   M3_LAUNCH_CHECK();
   return M3_OK;
@@ -868,21 +867,17 @@ static int launch_gg(const void* A, const void* B, void* out, void* out2, const 
   const int BN = pick_bn(p.N, heavy);
   if (BN == 0 || p.Kd % BK != 0 || cap_rows % (BM * kGGNcta) != 0) return M3_ERR_SHAPE;
   if (gather_rows > 0 && (EPI != EPI_FC1 || p.row_token == nullptr)) return M3_ERR_ARG;
-  CUtensorMap maps[5];
+  CUtensorMap maps[3];      // A (or the token matrix), B, aux (saved gelu' of the dgelu epilogue); outputs use plain stores
   int rc = gather_rows > 0 ? make_map(&maps[0], A, (uint64_t)gather_rows, (uint64_t)p.Kd, 1)     // box {64, 1}: tile::gather4
                            : make_map(&maps[0], A, (uint64_t)cap_rows, (uint64_t)p.Kd, BM);
   if (rc) return rc;
   rc = make_map(&maps[1], B, (uint64_t)p.E * p.N, (uint64_t)p.Kd, (uint32_t)(BN / kGGNcta));
   if (rc) return rc;
-  rc = make_map(&maps[2], out, (uint64_t)cap_rows, (uint64_t)p.N, 32);      // per-warp [32 x 64] boxes
-  if (rc) return rc;
-  rc = make_map(&maps[3], out2 ? out2 : out, (uint64_t)cap_rows, (uint64_t)p.N, 32);
-  if (rc) return rc;
   const int ew = epi_warps<EPI>();
   // epilogue register-block / staging-box width of the 8-warp epilogues: 32 columns (2 KB boxes) leave room for a 7th
   // smem stage, but measured 10 us slower per fc1+fc2 than 64 columns / 6 stages (tools/variants.py): opt-in (0x200)
   const bool narrow = ew == 16 || (g_knobs[M3_KNOB_EPI_WARPS] & 0x200) != 0;
-  rc = make_map(&maps[4], aux ? aux : out, (uint64_t)cap_rows, (uint64_t)p.N, 32, narrow ? 32 : 64);
+  rc = make_map(&maps[2], aux ? aux : out, (uint64_t)cap_rows, (uint64_t)p.N, 32, narrow ? 32 : 64);   // per-warp [32 x CW] boxes
   if (rc) return rc;
   p.out = static_cast<__nv_bfloat16*>(out);
   p.out2 = static_cast<__nv_bfloat16*>(out2);
