@@ -27,7 +27,7 @@ def main():
     dev = torch.device("cuda:0")
     print("M3_KNOBS =", os.environ.get("M3_KNOBS", "(defaults)"))
     D = H = 384
-    for B in (2, 8):
+    for B in ([int(a) for a in sys.argv[1:]] or [2, 8]):
         T = B * 1201
         torch.manual_seed(0)
         layer = M.FMoETransformerMLP(num_expert=16, d_model=D, d_gate=D + 2, d_hidden=H,
