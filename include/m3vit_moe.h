@@ -150,35 +150,17 @@ int m3_combine_bwd(const void* g, int g_dtype, const void* yq, int yq_dtype, con
  *   dtype M3_BF16: tcgen05/TMEM/TMA path (bf16 operands, fp32 accumulation)
  *   xq [rows, D], yq [rows, D]; rows = offsets[E] (<= cap_rows); w1 [E,H,D], w2 [E,D,H] in
  *   `dtype`; b1 [E,H], b2 [E,D] fp32.   tile_expert / offsets from m3_route_plan (pad M3_PAD_ROWS).
- *   saved: OPAQUE activation state of m3_ffn_saved_bytes(dtype, cap_rows, H) bytes that m3_ffn_fwd
+ *   saved: OPAQUE activation state of m3_ffn_saved_bytes(dtype, cap_rows, D, H) bytes that m3_ffn_fwd
  *   fills and m3_ffn_bwd consumes (NULL when not training).  fp32: the pre-activation z [rows, H];
- *   bf16: gelu'(z) and h = gelu(z) as two [rows, H] planes, so that the backward GEMM epilogue is a
- *   single multiply and h is not recomputed (autograd would keep z and re-evaluate erf/exp).
+ *   bf16: gelu'(z) and h = gelu(z) as two [rows, H] planes, so that the backward GEMM epilogue is a single multiply
+ *   and h is not recomputed (autograd would keep z and re-evaluate erf/exp).
  *   bf16 backward additionally needs transposed weight copies w1t [E,D,H], w2t [E,H,D].
  *   Weight / bias gradients are fp32 and OVERWRITTEN (caller accumulates).
  */
 size_t m3_ffn_workspace_bytes(int dtype, int cap_rows, int D, int H, int E, int backward);
-size_t m3_ffn_saved_bytes(int dtype, int cap_rows, int H);
-/* Gather path (bf16, single GPU): the dispatched queue xq is never materialised.  fc1 and the dW1 GEMM read their
- * queue rows straight from the [T, D] bf16 token matrix with TMA tile::gather4, four rows per instruction, through
- * row_token[queue row] = token (values >= T mark padding rows and read as zeros).  Replaces the same reference
- * seams as m3_dispatch_fwd + m3_ffn_fwd / m3_ffn_bwd (fmoe MOEScatter.forward + FMoELinear,
- * custom_moe_layer.py:36-44,255-257); results are bit-identical to that pair.
- *   m3_gather_prepare: ONE launch that casts x fp32 -> x_bf16 (x = x_bf16 = NULL: tokens are bf16 already) and
- *                      builds row_token [cap_rows] int32 from the route plan (pos, counts, offsets).
- *   m3_ffn_fwd_gather / m3_ffn_bwd_gather: as m3_ffn_fwd / m3_ffn_bwd (dtype bf16; workspace / saved sizes from
- *                      m3_ffn_workspace_bytes / m3_ffn_saved_bytes) with (x_bf16, row_token, T) in place of xq.
- *   D % 64 == 0. */
-int m3_gather_prepare(const float* x, int T, int D, const int32_t* pos, const int32_t* counts,
-                      const int32_t* offsets, int K, int E, void* x_bf16, int32_t* row_token, m3_stream_t stream);
-int m3_ffn_fwd_gather(const void* x_bf16, const int32_t* row_token, int T, const int32_t* offsets,
-                      const int32_t* tile_expert, int cap_rows, int E, int D, int H, const void* w1,
-                      const float* b1, const void* w2, const float* b2, void* saved, void* yq, void* workspace,
-                      size_t workspace_bytes, m3_stream_t stream);
-int m3_ffn_bwd_gather(const void* x_bf16, const int32_t* row_token, int T, const void* saved, const void* dyq,
-                      const int32_t* offsets, const int32_t* tile_expert, int cap_rows, int E, int D, int H,
-                      const void* w1t, const void* w2t, void* dxq, float* dw1, float* db1, float* dw2,
-                      float* db2, void* workspace, size_t workspace_bytes, m3_stream_t stream);
+size_t m3_ffn_saved_bytes(int dtype, int cap_rows, int D, int H);
+/* 1 if m3_ffn_fwd with saved == NULL runs this (dtype, D, H) as the chain kernel (launch accounting, tests). */
+int m3_ffn_uses_chain(int dtype, int D, int H);
 /* Process-wide tuning knob: SMs the persistent tcgen05 GEMMs may occupy (default / out of range: all 148).
  * The overlapped expert-parallel mode lowers it so that NVLink row movers run beside a GEMM. */
 int m3_set_gemm_sm_limit(int sms);
@@ -196,12 +178,13 @@ int m3_set_gemm_sm_limit(int sms);
  *   M3_KNOB_DEBUG     measurement only (results are garbage): tcgen05 GEMMs run 1 = without MMAs, 2 = without TMA loads.
  *   M3_KNOB_TRACE_KERNEL  1 + index of the GEMM launch inside one m3_ffn_fwd / m3_ffn_bwd call that m3_debug_trace_buffer
  *                     records (0 = every launch).
- *   M3_KNOB_BRES      1: grouped GEMMs with Kd <= 384 keep the expert's weight tile resident in shared memory and stream
- *                     activations only (bit-identical, measured slower); 0 (default): both operands are streamed.
+ *   M3_KNOB_FFN_CHAIN 1 (default): a bf16 forward that keeps no state (saved = NULL) with D in {128, 256, 384} and
+ *                     H <= 2 D runs as ONE chain kernel (fc1 -> GELU -> fc2, h never leaves the SM; ffn_chain.cu);
+ *                     0: always the two grouped GEMMs.
  *   M3_KNOB_MOVER_VARIANT  0 (default) or an experimental rows-in-flight / occupancy variant of combine fwd/bwd;
  *                     9: dispatch_bwd keeps the SIMT fp32 router term for bf16 queues too (default: mma.sync bf16).
  * Returns the previous value, or M3_ERR_ARG for an unknown knob. */
-typedef enum { M3_KNOB_PDL = 0, M3_KNOB_EPI_WARPS = 1, M3_KNOB_MOVER_VARIANT = 2, M3_KNOB_GATE_CFG = 3, M3_KNOB_DEBUG = 4, M3_KNOB_TRACE_KERNEL = 5, M3_KNOB_BRES = 6, M3_KNOB_COUNT_ = 8 } m3_knob;
+typedef enum { M3_KNOB_PDL = 0, M3_KNOB_EPI_WARPS = 1, M3_KNOB_MOVER_VARIANT = 2, M3_KNOB_GATE_CFG = 3, M3_KNOB_DEBUG = 4, M3_KNOB_TRACE_KERNEL = 5, M3_KNOB_FFN_CHAIN = 6, M3_KNOB_COUNT_ = 8 } m3_knob;
 int m3_set_knob(int knob, int value);
 int m3_ffn_fwd(int dtype, const void* xq, const int32_t* offsets, const int32_t* tile_expert,
                int cap_rows, int E, int D, int H, const void* w1, const float* b1, const void* w2,
@@ -313,10 +296,6 @@ int m3_ln_bwd_res(const float* dxn, const float* x, const float* mean, const flo
 
 /* Debug only: occupy `n_ctas` whole SMs for `cycles` clocks (measures what other kernels get from the rest). */
 int m3_debug_occupy(int n_ctas, long long cycles, int* sink, m3_stream_t stream);
-
-/* Debug only: clock64 timeline of CTA 0 of the fused FFN kernel (enable, then call again with a host
- * buffer of 2*max_events uint64 to fetch {tag, clock} pairs).  Synchronises the device. */
-int m3_debug_trace(int enable, unsigned long long* host_out, int max_events);
 
 /* Debug only: clock64 timeline of CTA 0 of the tensor-core GEMM kernels (producer / MMA / one epilogue warp), appended
  * to a caller-owned DEVICE buffer of 4 + 6*max_events uint64 (buf[r] = event count of role r = 0 producer / 1 MMA /

@@ -11,7 +11,8 @@ import os
 import torch
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "lib", "libm3vit_moe.so")
+# M3_LIB_PATH: a diagnosis build of the SAME library (e.g. lib/libm3vit_moe_trace.so, M3_GEMM_TRACE=1 python -m m3vit_b200.build)
+LIB_PATH = os.environ.get("M3_LIB_PATH") or os.path.join(HERE, "lib", "libm3vit_moe.so")
 
 M3_F32, M3_BF16 = 0, 1
 PAD_ROWS = 256     # expert queues are padded to the 256-row CTA-pair tile of the tensor-core GEMM
@@ -41,10 +42,8 @@ SIGNATURES = {
     "m3_combine_fwd": (_i, [_p, _i, _p, _p, _i, _i, _i, _p, _i, _p]),
     "m3_combine_bwd": (_i, [_p, _i, _p, _i, _p, _p, _p, _p, _i, _i, _i, _i, _p, _i, _p, _p]),
     "m3_ffn_workspace_bytes": (_sz, [_i, _i, _i, _i, _i, _i]),
-    "m3_ffn_saved_bytes": (_sz, [_i, _i, _i]),
-    "m3_gather_prepare": (_i, [_p, _i, _i, _p, _p, _p, _i, _i, _p, _p, _p]),
-    "m3_ffn_fwd_gather": (_i, [_p, _p, _i, _p, _p, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _sz, _p]),
-    "m3_ffn_bwd_gather": (_i, [_p, _p, _i, _p, _p, _p, _p, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p, _sz, _p]),
+    "m3_ffn_saved_bytes": (_sz, [_i, _i, _i, _i]),
+    "m3_ffn_uses_chain": (_i, [_i, _i, _i]),
     "m3_set_gemm_sm_limit": (_i, [_i]),
     "m3_set_knob": (_i, [_i, _i]),
     "m3_ffn_fwd": (_i, [_i, _p, _p, _p, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _sz, _p]),
@@ -67,7 +66,6 @@ SIGNATURES = {
                             _p, _p, _p, _p, _p, _sz, _p]),
     "m3_ln_bwd_workspace_bytes": (_sz, [_i, _i]),
     "m3_ln_bwd_res": (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _p, _p, _p, _p, _sz, _p]),
-    "m3_debug_trace": (_i, [_i, _p, _i]),
     "m3_debug_trace_buffer": (_i, [_p, _i]),
     "m3_debug_occupy": (_i, [_i, C.c_longlong, _p, _p]),
     "m3_ipc_alloc": (_i, [_sz, C.POINTER(_p), _p]),

@@ -13,13 +13,15 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libm3vit_moe.so")
-SOURCES = ["abi.cu", "gate.cu", "route.cu", "permute.cu", "ffn_f32.cu", "ffn_bf16.cu", "ffn_fused.cu", "block.cu"]
+SOURCES = ["abi.cu", "gate.cu", "route.cu", "permute.cu", "ffn_f32.cu", "ffn_bf16.cu", "ffn_chain.cu", "block.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC",     # no --use_fast_math: exact erf/exp/div, parity first
 ]
-if os.environ.get("M3_GEMM_TRACE") == "1":      # clock64 timeline in the tensor-core GEMMs (tools/gemm_timeline.py)
-    NVCC_FLAGS.append("-DM3_GEMM_TRACE")
+TRACE = os.environ.get("M3_GEMM_TRACE") == "1"
+if TRACE:      # clock64 timeline in the tensor-core kernels (tools/gemm_timeline.py, tools/chain_timeline.py): a SEPARATE
+    NVCC_FLAGS.append("-DM3_GEMM_TRACE")       # library, loaded with M3_LIB_PATH=.../libm3vit_moe_trace.so
+    LIB = os.path.join(LIBDIR, "libm3vit_moe_trace.so")
 
 
 def _nvcc():
@@ -42,12 +44,12 @@ def _digest(paths):
 def build(force: bool = False, verbose: bool = False) -> str:
     os.makedirs(LIBDIR, exist_ok=True)
     deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(HERE, "..", "include", "m3vit_moe.h")]
-    stamp = os.path.join(LIBDIR, "build.sha256")
+    stamp = os.path.join(LIBDIR, "build_trace.sha256" if TRACE else "build.sha256")
     digest = _digest(deps)
     if not force and os.path.exists(LIB) and os.path.exists(stamp) and open(stamp).read().strip() == digest:
         return LIB
     nvcc = _nvcc()
-    objdir = os.path.join(LIBDIR, "obj")
+    objdir = os.path.join(LIBDIR, "obj_trace" if TRACE else "obj")
     os.makedirs(objdir, exist_ok=True)
 
     def compile_one(src):

@@ -13,7 +13,8 @@ int m3_ffn_bwd_f32(const float* xq, const float* hpre, const float* dyq, const i
                    const float* w1, const float* w2, float* dxq, float* dw1, float* db1, float* dw2, float* db2,
                    void* workspace, size_t workspace_bytes, cudaStream_t st);
 size_t m3_ffn_bf16_workspace_bytes(int cap_rows, int D, int H, int E, int backward);
-size_t m3_ffn_bf16_saved_bytes(int cap_rows, int H);
+size_t m3_ffn_bf16_saved_bytes(int cap_rows, int D, int H);
+int m3_ffn_bf16_chain_mode(int D, int H);
 int m3_ffn_bf16_set_sm_limit(int sms);
 int m3_ffn_fwd_bf16(const void* xq, const int32_t* offsets, const int32_t* tile_expert, int cap_rows, int E, int D,
                     int H, const void* w1, const float* b1, const void* w2, const float* b2, void* hpre, void* yq,
@@ -22,15 +23,6 @@ int m3_ffn_bwd_bf16(const void* xq, const void* hpre, const void* dyq, const int
                     const int32_t* offsets, const int32_t* tile_expert, int cap_rows, int E, int D, int H,
                     const void* w1, const void* w2, const void* w1t, const void* w2t, void* dxq, float* dw1,
                     float* db1, float* dw2, float* db2, void* workspace, size_t workspace_bytes, cudaStream_t st);
-
-int m3_ffn_fwd_bf16_gather(const void* x_bf16, const int32_t* row_token, int T, const int32_t* offsets,
-                           const int32_t* tile_expert, int cap_rows, int E, int D, int H, const void* w1, const float* b1,
-                           const void* w2, const float* b2, void* saved, void* yq, void* workspace,
-                           size_t workspace_bytes, cudaStream_t st);
-int m3_ffn_bwd_bf16_gather(const void* x_bf16, const int32_t* row_token, int T, const void* saved, const void* dyq,
-                           const int32_t* offsets, const int32_t* tile_expert, int cap_rows, int E, int D, int H,
-                           const void* w1t, const void* w2t, void* dxq, float* dw1, float* db1, float* dw2, float* db2,
-                           void* workspace, size_t workspace_bytes, cudaStream_t st);
 
 extern "C" int m3_abi_version(void) { return M3_ABI_VERSION; }
 
@@ -68,7 +60,8 @@ extern "C" size_t m3_ffn_workspace_bytes(int dtype, int cap_rows, int D, int H, 
 extern "C" int m3_set_gemm_sm_limit(int sms) { return m3_ffn_bf16_set_sm_limit(sms); }
 
 namespace m3 {
-int g_knobs[M3_KNOB_COUNT_] = {/*PDL*/ 0, /*EPI_WARPS*/ 0, /*MOVER_VARIANT*/ 0, /*GATE_CFG*/ 0, /*DEBUG*/ 0};
+int g_knobs[M3_KNOB_COUNT_] = {/*PDL*/ 0, /*EPI_WARPS*/ 0, /*MOVER_VARIANT*/ 0, /*GATE_CFG*/ 0, /*DEBUG*/ 0, /*TRACE_KERNEL*/ 0,
+                                /*FFN_CHAIN*/ 1};      // 1: chain kernel for state-free forwards
 }
 namespace m3 { namespace tc {
 unsigned long long* g_trace_buf = nullptr;
@@ -88,10 +81,14 @@ extern "C" int m3_set_knob(int knob, int value) {
   return old;
 }
 
-extern "C" size_t m3_ffn_saved_bytes(int dtype, int cap_rows, int H) {
-  if (cap_rows < 0 || H <= 0) return 0;
-  if (dtype == M3_BF16) return m3_ffn_bf16_saved_bytes(cap_rows, H);
+extern "C" size_t m3_ffn_saved_bytes(int dtype, int cap_rows, int D, int H) {
+  if (cap_rows < 0 || H <= 0 || D <= 0) return 0;
+  if (dtype == M3_BF16) return m3_ffn_bf16_saved_bytes(cap_rows, D, H);
   return (size_t)cap_rows * H * sizeof(float);      // fp32 parity path: the pre-activation
+}
+
+extern "C" int m3_ffn_uses_chain(int dtype, int D, int H) {
+  return dtype == M3_BF16 ? m3_ffn_bf16_chain_mode(D, H) : 0;
 }
 
 extern "C" int m3_ffn_fwd(int dtype, const void* xq, const int32_t* offsets, const int32_t* tile_expert, int cap_rows,
@@ -137,34 +134,6 @@ extern "C" int m3_ffn_bwd(int dtype, const void* xq, const void* hpre, const voi
                            dw1, db1, dw2, db2, workspace, workspace_bytes, st);
   }
   return M3_ERR_UNSUPPORTED;
-}
-
-extern "C" int m3_ffn_fwd_gather(const void* x_bf16, const int32_t* row_token, int T, const int32_t* offsets,
-                                 const int32_t* tile_expert, int cap_rows, int E, int D, int H, const void* w1,
-                                 const float* b1, const void* w2, const float* b2, void* saved, void* yq, void* workspace,
-                                 size_t workspace_bytes, m3_stream_t stream) {
-  M3_CHECK_ARG(x_bf16 && row_token && offsets && tile_expert && w1 && b1 && w2 && b2 && yq && workspace);
-  M3_CHECK_ARG(T >= 1 && cap_rows >= 0 && E >= 1 && D > 0 && H > 0);
-  M3_CHECK_SHAPE(cap_rows % M3_PAD_ROWS == 0 && D % 64 == 0);
-  M3_CHECK_ALIGN16(x_bf16); M3_CHECK_ALIGN16(row_token); M3_CHECK_ALIGN16(yq); M3_CHECK_ALIGN16(w1); M3_CHECK_ALIGN16(w2);
-  M3_CHECK_ALIGN16(workspace);
-  if (saved) M3_CHECK_ALIGN16(saved);
-  if (cap_rows == 0) return M3_OK;
-  return m3_ffn_fwd_bf16_gather(x_bf16, row_token, T, offsets, tile_expert, cap_rows, E, D, H, w1, b1, w2, b2, saved, yq,
-                                workspace, workspace_bytes, static_cast<cudaStream_t>(stream));
-}
-
-extern "C" int m3_ffn_bwd_gather(const void* x_bf16, const int32_t* row_token, int T, const void* saved, const void* dyq,
-                                 const int32_t* offsets, const int32_t* tile_expert, int cap_rows, int E, int D, int H,
-                                 const void* w1t, const void* w2t, void* dxq, float* dw1, float* db1, float* dw2,
-                                 float* db2, void* workspace, size_t workspace_bytes, m3_stream_t stream) {
-  M3_CHECK_ARG(x_bf16 && row_token && saved && dyq && offsets && tile_expert && w1t && w2t && dxq && dw1 && db1 && dw2 && db2);
-  M3_CHECK_ARG(T >= 1 && cap_rows >= 0 && E >= 1 && D > 0 && H > 0 && workspace);
-  M3_CHECK_SHAPE(cap_rows % M3_PAD_ROWS == 0 && D % 64 == 0);
-  M3_CHECK_ALIGN16(x_bf16); M3_CHECK_ALIGN16(row_token); M3_CHECK_ALIGN16(saved); M3_CHECK_ALIGN16(dyq); M3_CHECK_ALIGN16(dxq);
-  M3_CHECK_ALIGN16(dw1); M3_CHECK_ALIGN16(dw2); M3_CHECK_ALIGN16(workspace);
-  return m3_ffn_bwd_bf16_gather(x_bf16, row_token, T, saved, dyq, offsets, tile_expert, cap_rows, E, D, H, w1t, w2t, dxq,
-                                dw1, db1, dw2, db2, workspace, workspace_bytes, static_cast<cudaStream_t>(stream));
 }
 
 // ------------------------------------------------------------------ debug: SM occupier

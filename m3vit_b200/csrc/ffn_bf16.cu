@@ -12,12 +12,10 @@
 //                that alternate accumulator buffers (tcgen05.ld -> bias / GELU (+GELU') / x saved GELU' -> bf16 ->
 //                private swizzled smem box -> coalesced row segments).  Smem ring of {A 128x64, B (BN/2)x64}
 //                stages (SWIZZLE_128B); TMEM accumulator double-buffered so the epilogue of tile i overlaps
-//                the MMAs of tile i+1.  Opt-in variants, all bit-identical: BRES (the expert's weight tile stays
-//                resident in smem), GATHER (fc1's A rows fetched from the token matrix with TMA gather4, no
-//                dispatched queue; two more producer warps), 32-column epilogue blocks.
+//                the MMAs of tile i+1.  Opt-in variant (bit-identical): 32-column epilogue blocks.
 //   wgrad_kernel dW_e[M,N] = sum_rows X1[rows,M]^T X2[rows,N]     (both MN-major operands,
 //                read straight from the row-major queues - no transposes in memory); same converged producer / MMA
-//                warps; GATHER: X2 rows gathered from the token matrix
+//                warps
 //
 // Expert queues are padded to M3_PAD_ROWS = 256 rows (route plan), so every tile is full and the expert
 // of a tile is a table lookup; padding rows are zero, so they add nothing to dW.
@@ -37,10 +35,7 @@ constexpr int kThreads = 192;        // wgrad kernel: 2 + 4 warps
 // gg kernel epilogue warps: EW = 8 (one warp per TMEM lane quarter and accumulator buffer, 64-column register
 // blocks) or EW = 16 (two warps per quarter and buffer, interleaved 32-column blocks: twice the warps to hide
 // the dependent erf/exp chains of the GELU epilogues behind, at half the registers per thread)
-// GATHER (fc1 reading its A rows straight from the token matrix with TMA gather4): 32 gathers per stage instead of one
-// tiled load is more than one warp can issue per k-chunk, so two more producer warps (behind the epilogue warps) share them
-constexpr int kGatherWarps = 3;
-constexpr int gg_threads(int EW, bool gather = false) { return 64 + EW * 32 + (gather ? (kGatherWarps - 1) * 32 : 0); }
+constexpr int gg_threads(int EW) { return 64 + EW * 32; }
 constexpr int BOX_BYTES = BM * 64 * 2;  // one [128 rows][64 bf16] swizzle-128B box = 16 KB
 
 enum { EPI_STORE = 0, EPI_BIAS = 1, EPI_FC1 = 2, EPI_DGELU = 3 };
@@ -56,34 +51,26 @@ struct GGParams {
   int dbg;                     // M3_KNOB_DEBUG (measurement only, results are garbage): 1 = no MMAs, 2 = no TMA loads
   unsigned long long* trace;   // m3_debug_trace_buffer
   int trace_cap;
-  const int32_t* row_token;    // GATHER: [cap_rows] token of every queue row (>= T for padding rows: reads as zeros)
 };
 
-// BRES ("B resident", opt-in: M3_KNOB_BRES = 1): the weight tile of one (expert, N-tile) stays in shared memory across
-// all the M-tiles a unit computes for that expert; the ring then carries A only (43 % fewer L2 -> SM bytes at Kd = 384).
-// Bit-identical to the streaming kernel, but measured SLOWER (fc2 81 vs 50 us): the A stream from DRAM, not the SM's
-// inbound bandwidth, paces the ring - its latency just grows with the extra stages (tools/gemm_timeline.py).
-constexpr int kBresMaxChunks = 6;      // Kd <= 384: 6 x (BN/2 rows x 128 B) = 72 KB of resident weights per CTA at BN = 192
-
-template <int BN, int EPI, int NCTA, int EW, bool BRES, int CWP>
+template <int BN, int EPI, int NCTA, int EW, int CWP>
 struct GGCfg {
   static constexpr int CW = CWP;                              // columns per epilogue register block (32 or 64)
   static_assert(CWP == 32 || (CWP == 64 && EW == 8), "epilogue block width");
   static constexpr int WBOX_BYTES = 32 * CW * 2;              // one warp's [32 rows][CW bf16] swizzled box (4 / 2 KB)
   static constexpr int A_BYTES = BM * BK * 2;
   static constexpr int B_BYTES = (BN / NCTA) * BK * 2;      // a CTA pair splits the B tile
-  static constexpr int BRES_BYTES = BRES ? kBresMaxChunks * B_BYTES : 0;
-  static constexpr int STAGE = BRES ? A_BYTES : A_BYTES + B_BYTES;
+  static constexpr int STAGE = A_BYTES + B_BYTES;
   // epilogue staging: one private 4 KB box per epilogue warp per output tensor (+ per TMA-loaded aux input)
   static constexpr int N_OUT = 1;                            // outputs share one transpose box, flushed in turn
   static constexpr int N_AUX = (EPI == EPI_DGELU) ? 1 : 0;   // EPI_DGELU: gelu'(pre-activation) saved by fc1
   static constexpr int WARP_STAGING = (N_OUT + N_AUX) * WBOX_BYTES;
   static constexpr int STAGING = EW * WARP_STAGING;
-  static constexpr int BUDGET = 227 * 1024 - 1024 - 512 - STAGING - BRES_BYTES;
+  static constexpr int BUDGET = 227 * 1024 - 1024 - 512 - STAGING;
   static constexpr int MAX_STAGES = 8;
   static constexpr int STAGES = (BUDGET / STAGE) < MAX_STAGES ? (BUDGET / STAGE) : MAX_STAGES;
   static constexpr int TMEM_COLS = (2 * BN <= 256) ? 256 : 512;
-  static constexpr int SMEM = STAGES * STAGE + BRES_BYTES + STAGING + 1024 /*align slack*/ + 512 /*barriers*/;
+  static constexpr int SMEM = STAGES * STAGE + STAGING + 1024 /*align slack*/ + 512 /*barriers*/;
   static_assert(STAGES >= 3, "smem ring too shallow");
 };
 
@@ -105,11 +92,11 @@ __device__ __forceinline__ uint32_t box_off(int r, int c) {
   return (uint32_t)r * 64u + (uint32_t)((c ^ ((r >> 1) & 3)) << 4);
 }
 
-template <int BN, int EPI, int NCTA, int EW, bool BRES, int CWP, bool GATHER = false>
-__global__ void __launch_bounds__(gg_threads(EW, GATHER), 1)
+template <int BN, int EPI, int NCTA, int EW, int CWP>
+__global__ void __launch_bounds__(gg_threads(EW), 1)
 gg_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
           const __grid_constant__ CUtensorMap tmAux, GGParams p) {
-  using Cfg = GGCfg<BN, EPI, NCTA, EW, BRES, CWP>;
+  using Cfg = GGCfg<BN, EPI, NCTA, EW, CWP>;
   constexpr int kEpiWarps = EW;
   constexpr int CW = Cfg::CW, WBOX_BYTES = Cfg::WBOX_BYTES;
   constexpr int NQ = EW / 8;            // warps sharing one (TMEM lane quarter, accumulator buffer)
@@ -122,17 +109,14 @@ gg_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
   static_assert(BN % (CW * NQ) == 0, "tile width vs epilogue blocks");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* bres = smem + STAGES * Cfg::STAGE;                // BRES: resident weight chunks [kchunks][BN/NCTA rows][64]
-  uint8_t* stg = bres + Cfg::BRES_BYTES;                     // staging boxes (1024-aligned)
+  uint8_t* stg = smem + STAGES * Cfg::STAGE;                 // staging boxes (1024-aligned)
   uint64_t* full = reinterpret_cast<uint64_t*>(stg + Cfg::STAGING);
   uint64_t* empty = full + STAGES;
   uint64_t* tfull = empty + STAGES;
   uint64_t* tempty = tfull + 2;
   uint64_t* aux_full = tempty + 2;                            // [kEpiWarps]
-  uint64_t* fullB = aux_full + kEpiWarps;                     // [kBresMaxChunks] resident weight chunk loaded
-  uint64_t* emptyB = fullB + kBresMaxChunks;                  // [kBresMaxChunks] ... no longer read by any MMA
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(emptyB + kBresMaxChunks);
-  static_assert((2 * STAGES + 4 + EW + 2 * kBresMaxChunks) * 8 + 4 <= 512, "barrier block");
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(aux_full + kEpiWarps);
+  static_assert((2 * STAGES + 4 + EW) * 8 + 4 <= 512, "barrier block");
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (warp == 0 && lane == 0) {
@@ -144,7 +128,6 @@ gg_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
       for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], NCTA); mbar_init(&empty[s], 1); }
       for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], NCTA * (EW / 2) * 32); }
       for (int w = 0; w < kEpiWarps; ++w) mbar_init(&aux_full[w], 1);
-      for (int c = 0; c < kBresMaxChunks; ++c) { mbar_init(&fullB[c], NCTA); mbar_init(&emptyB[c], 1); }
       fence_barrier_init();
     }
     __syncwarp();
@@ -161,28 +144,17 @@ gg_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
   pdl_trigger();
 
   // Tile schedule.  A "unit" (CTA or CTA pair) computes `my_tiles` pair-tiles, local index i = 0 .. my_tiles-1:
-  //   streaming (BRES = false): pair-tile pt = unit + i * n_units covers M-tiles (pt / n_tiles) * NCTA + cta_rank (queues
-  //     are padded to NCTA*128 rows, so both halves of a pair belong to the same expert) and N-tile pt % n_tiles;
-  //   BRES: unit = su * n_tiles + n keeps N-tile n for its whole life and walks the CONTIGUOUS M-pair-tiles
-  //     [mp0, mp1) of "super-unit" su, so consecutive tiles mostly share the expert (= the resident weights); the
-  //     n_tiles units of a super-unit run in lockstep over the same rows (the second reader of an A tile hits L2).
+  // pair-tile pt = unit + i * n_units covers M-tiles (pt / n_tiles) * NCTA + cta_rank (queues are padded to NCTA*128
+  // rows, so both halves of a pair belong to the same expert) and N-tile pt % n_tiles.
   const int n_tiles = p.N / BN;
   const int m_tiles = p.offsets[p.E] / BM;
   const int kchunks = p.Kd / BK;
   const int unit = blockIdx.x / NCTA, n_units = gridDim.x / NCTA;
   const int total = (m_tiles / NCTA) * n_tiles;
-  int my_tiles, mp0 = 0;
-  if (BRES) {
-    const int n_su = n_units / n_tiles, su = unit / n_tiles, mt = m_tiles / NCTA;
-    const bool active = su < n_su;
-    mp0 = active ? (int)((int64_t)su * mt / n_su) : 0;
-    my_tiles = active ? (int)((int64_t)(su + 1) * mt / n_su) - mp0 : 0;
-  } else {
-    my_tiles = unit < total ? (total - unit + n_units - 1) / n_units : 0;
-  }
+  const int my_tiles = unit < total ? (total - unit + n_units - 1) / n_units : 0;
   // local tile index -> (M-tile of this CTA, N-tile)
-  auto tile_mblk = [&](int i) { return BRES ? (mp0 + i) * NCTA + (int)cta_rank : ((unit + i * n_units) / n_tiles) * NCTA + (int)cta_rank; };
-  auto tile_nblk = [&](int i) { return BRES ? unit % n_tiles : (unit + i * n_units) % n_tiles; };
+  auto tile_mblk = [&](int i) { return ((unit + i * n_units) / n_tiles) * NCTA + (int)cta_rank; };
+  auto tile_nblk = [&](int i) { return (unit + i * n_units) % n_tiles; };
 
   // Producer and MMA warps run their loops CONVERGED (all 32 lanes); every TMA / MMA / commit / arrive is issued by one
   // elected lane inside its asm block (tc_common.cuh: the single-thread `if (lane == 0)` form cost ~700 clk of scalar
@@ -190,90 +162,21 @@ gg_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
   // Both loops walk the smem ring in rounds of STAGES k-chunks with the stage index a compile-time constant (every
   // barrier address and descriptor is base + immediate); the flat chunk index f runs over all tiles of this unit.
   const int F = my_tiles * kchunks;
-  // GATHER: producer warp pw (0 = warp 0, 1.. = the helper warps behind the epilogue warps) issues row groups
-  // [g0, g1) of every A stage; lane l < g1 - g0 keeps the 4 token indices of group g0 + l in registers
-  constexpr int kGroups = BM / 4;     // 32 gather4 per [128 x 64] A stage
-  auto gather_share = [&](int pw, int& g0, int& g1) {
-    const int per = (kGroups + kGatherWarps - 1) / kGatherWarps;
-    g0 = pw * per;
-    g1 = g0 + per < kGroups ? g0 + per : kGroups;
-  };
-  auto load_idx = [&](int ti, int g0, int g1) -> int4 {
-    int4 v = make_int4(0, 0, 0, 0);
-    if (ti < my_tiles && lane < g1 - g0)
-      v = __ldg(reinterpret_cast<const int4*>(p.row_token + (int64_t)tile_mblk(ti) * BM) + g0 + lane);
-    return v;
-  };
-  auto issue_gathers = [&](const int4& idx, int g0, int g1, uint32_t sa, uint32_t bar, int col) {
-#pragma unroll
-    for (int g = 0; g < (kGroups + kGatherWarps - 1) / kGatherWarps; ++g) {
-      if (g0 + g < g1) {
-        const int r0 = __shfl_sync(0xffffffffu, idx.x, g), r1 = __shfl_sync(0xffffffffu, idx.y, g);
-        const int r2 = __shfl_sync(0xffffffffu, idx.z, g), r3 = __shfl_sync(0xffffffffu, idx.w, g);
-        if (NCTA == 2) tma_gather4_2sm_elect(sa + (g0 + g) * 512, &tmA, bar, col, r0, r1, r2, r3);
-        else tma_gather4_elect(sa + (g0 + g) * 512, &tmA, bar, col, r0, r1, r2, r3);
-      }
-    }
-  };
-  if (GATHER && warp >= 2 + EW) {
-    // helper producer: same ring walk as warp 0, gathers only (warp 0 posts the expected bytes and loads B)
-    int g0, g1;
-    gather_share(warp - (2 + EW) + 1, g0, g1);
+  if (warp == 0) {
     const uint32_t smem_base = smem_u32(smem);
-    const uint32_t full0 = NCTA == 2 ? mapa_u32(smem_u32(&full[0]), 0) : smem_u32(&full[0]);
-    uint32_t phase = 0;
-    int ti = 0, kc = 0;
-    int4 cur = make_int4(0, 0, 0, 0), nxt = load_idx(0, g0, g1);
-    for (int f0 = 0; f0 < F; f0 += STAGES) {
-#pragma unroll
-      for (int st = 0; st < STAGES; ++st) {
-        if (f0 + st < F) {
-          if (kc == 0) { cur = nxt; nxt = load_idx(ti + 1, g0, g1); }
-          mbar_wait(&empty[st], phase ^ 1);
-          __syncwarp();
-          issue_gathers(cur, g0, g1, smem_base + st * Cfg::STAGE, full0 + st * 8, kc * BK);
-          if (++kc == kchunks) { kc = 0; ++ti; }
-        }
-      }
-      phase ^= 1;
-    }
-  } else if (warp == 0) {
-    const uint32_t smem_base = smem_u32(smem), bres_base = smem_u32(bres);
     const bool no_tma = (p.dbg & 2) != 0;
     const uint32_t full0 = NCTA == 2 ? mapa_u32(smem_u32(&full[0]), 0) : smem_u32(&full[0]);   // leader's barriers
-    const uint32_t fullB0 = NCTA == 2 ? mapa_u32(smem_u32(&fullB[0]), 0) : smem_u32(&fullB[0]);
     Tracer trc(p.trace, p.trace_cap, 0);
     uint32_t phase = 0;
     int ti = 0, kc = 0, m_blk = 0, b_row = 0;
-    int cur_e = -1, n_loadB = 0;      // BRES: expert whose weights are resident, number of weight loads issued so far
-    bool loadB = false;
-    int gg0 = 0, gg1 = 0;
-    if (GATHER) gather_share(0, gg0, gg1);
-    int4 gcur = make_int4(0, 0, 0, 0), gnxt = GATHER ? load_idx(0, gg0, gg1) : make_int4(0, 0, 0, 0);
     for (int f0 = 0; f0 < F; f0 += STAGES) {
 #pragma unroll
       for (int st = 0; st < STAGES; ++st) {
         if (f0 + st < F) {
           if (kc == 0) {
-            if (GATHER) { gcur = gnxt; gnxt = load_idx(ti + 1, gg0, gg1); }
             m_blk = tile_mblk(ti);
             const int e = p.tile_expert[(m_blk * BM) / M3_PAD_ROWS];
             b_row = e * p.N + tile_nblk(ti) * BN + (int)cta_rank * (BN / NCTA);
-            loadB = BRES && e != cur_e;
-            cur_e = e;
-          }
-          if (BRES && loadB) {
-            // weight chunk kc of the new expert: the MMAs of the previous expert's LAST tile must be done with the slot
-            if (n_loadB > 0) mbar_wait(&emptyB[kc], (uint32_t)(n_loadB - 1) & 1u);
-            __syncwarp();
-            const uint32_t barB = fullB0 + kc * 8;
-            if (NCTA == 2) {
-              if (leader_cta) mbar_expect_tx_elect(&fullB[kc], Cfg::B_BYTES * NCTA); else mbar_arrive_remote_elect(barB);
-              tma_load_2d_2sm_elect(bres_base + kc * Cfg::B_BYTES, &tmB, barB, kc * BK, b_row);
-            } else {
-              mbar_expect_tx_elect(&fullB[kc], Cfg::B_BYTES);
-              tma_load_2d_elect(bres_base + kc * Cfg::B_BYTES, &tmB, barB, kc * BK, b_row);
-            }
           }
           trc.ev(0x00, f0 + st);
           mbar_wait(&empty[st], phase ^ 1);
@@ -287,20 +190,17 @@ gg_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
             } else {
               if (leader_cta) mbar_expect_tx_elect(&full[st], Cfg::STAGE * NCTA);
               else mbar_arrive_remote_elect(bar);
-              if (!BRES) tma_load_2d_2sm_elect(sa + Cfg::A_BYTES, &tmB, bar, kc * BK, b_row);
-              if (GATHER) issue_gathers(gcur, gg0, gg1, sa, bar, kc * BK);
-              else tma_load_2d_2sm_elect(sa, &tmA, bar, kc * BK, m_blk * BM);
+              tma_load_2d_2sm_elect(sa + Cfg::A_BYTES, &tmB, bar, kc * BK, b_row);
+              tma_load_2d_2sm_elect(sa, &tmA, bar, kc * BK, m_blk * BM);
             }
           } else {
             mbar_expect_tx_elect(&full[st], Cfg::STAGE);
-            if (!BRES) tma_load_2d_elect(sa + Cfg::A_BYTES, &tmB, bar, kc * BK, b_row);
-            if (GATHER) issue_gathers(gcur, gg0, gg1, sa, bar, kc * BK);
-            else tma_load_2d_elect(sa, &tmA, bar, kc * BK, m_blk * BM);
+            tma_load_2d_elect(sa + Cfg::A_BYTES, &tmB, bar, kc * BK, b_row);
+            tma_load_2d_elect(sa, &tmA, bar, kc * BK, m_blk * BM);
           }
           if (++kc == kchunks) {
             kc = 0;
             ++ti;
-            if (loadB) ++n_loadB;
           }
         }
       }
@@ -314,12 +214,9 @@ gg_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
       const uint32_t tm = __shfl_sync(0xffffffffu, tmem_base, 0);
       // K-major operand tiles [rows][64 bf16], SWIZZLE_128B: 8-row groups 1024 B apart (SBO); K advances 32 B per UMMA_K
       const uint32_t a_lo0 = smem_desc_lo(smem_u32(smem), 0), hi = smem_desc_hi(1024);
-      const uint32_t bres_lo0 = smem_desc_lo(smem_u32(bres), 0);
       const bool no_mma = (p.dbg & 1) != 0;
       uint32_t phase = 0, acc = 0, acc_phase = 0, d_tmem = tm;
-      int kc = 0, ti = 0;
-      int cur_e = -1, n_loadB = 0;       // BRES: mirrors the producer's weight-load sequence
-      bool newB = false, lastB = false;  // first / last tile computed with the resident weights
+      int kc = 0;
       for (int f0 = 0; f0 < F; f0 += STAGES) {
 #pragma unroll
         for (int st = 0; st < STAGES; ++st) {
@@ -329,21 +226,13 @@ gg_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
               mbar_wait(&tempty[acc], acc_phase ^ 1);
               trc.ev(0x11, f0 + st);
               d_tmem = tm + acc * BN;
-              if (BRES) {
-                const int e = p.tile_expert[(tile_mblk(ti) * BM) / M3_PAD_ROWS];
-                const int e_next = ti + 1 < my_tiles ? p.tile_expert[(tile_mblk(ti + 1) * BM) / M3_PAD_ROWS] : -1;
-                newB = e != cur_e;
-                lastB = e_next != e;
-                cur_e = e;
-              }
             }
-            if (BRES && newB) mbar_wait(&fullB[kc], (uint32_t)n_loadB & 1u);
             mbar_wait(&full[st], phase);
             trc.ev(0x12, f0 + st);
             __syncwarp();
             tcgen05_fence_after();
             const uint32_t a_lo = a_lo0 + (uint32_t)st * (Cfg::STAGE >> 4);
-            const uint32_t b_lo = BRES ? bres_lo0 + (uint32_t)kc * (Cfg::B_BYTES >> 4) : a_lo + (Cfg::A_BYTES >> 4);
+            const uint32_t b_lo = a_lo + (Cfg::A_BYTES >> 4);
             if (!no_mma) {
 #pragma unroll
               for (int k = 0; k < BK / UMMA_K; ++k) {
@@ -353,16 +242,11 @@ gg_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
             }
             // frees the smem stage (in both CTAs of a pair) once these MMAs have read it
             if (NCTA == 2) umma_commit_2sm_elect(&empty[st], 3); else umma_commit_elect(&empty[st]);
-            if (BRES && lastB) {   // ... and the resident weight chunk, after the last tile that uses it
-              if (NCTA == 2) umma_commit_2sm_elect(&emptyB[kc], 3); else umma_commit_elect(&emptyB[kc]);
-            }
             trc.ev(0x13, f0 + st);
             if (++kc == kchunks) {
               // accumulator complete -> epilogue warps (of both CTAs)
               if (NCTA == 2) umma_commit_2sm_elect(&tfull[acc], 3); else umma_commit_elect(&tfull[acc]);
               kc = 0;
-              ++ti;
-              if (newB) ++n_loadB;
               acc ^= 1;
               if (acc == 0) acc_phase ^= 1;
             }
@@ -530,7 +414,6 @@ struct WGParams {
   int dbg;        // M3_KNOB_DEBUG (measurement only): 1 = no MMAs, 2 = no TMA loads
   unsigned long long* trace;   // m3_debug_trace_buffer
   int trace_cap;
-  const int32_t* row_token;    // GATHER: X2 is the token matrix, row_token[queue row] = token (>= T: zeros)
 };
 
 template <int BN>
@@ -547,10 +430,8 @@ struct WGCfg {
   static_assert(BN + 16 <= TMEM_COLS, "TMEM");
 };
 
-// GATHER: X2 rows are gathered from the [T][N] token matrix with TMA gather4 (16 gathers per [64 x 64] box); two
-// helper producer warps (6, 7) share them with warp 0
-template <int BN, bool GATHER = false>
-__global__ void __launch_bounds__(kThreads + (GATHER ? (kGatherWarps - 1) * 32 : 0), 1)
+template <int BN>
+__global__ void __launch_bounds__(kThreads, 1)
 wgrad_kernel(const __grid_constant__ CUtensorMap tm1, const __grid_constant__ CUtensorMap tm2, WGParams p) {
   using Cfg = WGCfg<BN>;
   constexpr int STAGES = Cfg::STAGES;
@@ -599,59 +480,16 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tm1, const __grid_constant__ CU
   const int r0 = p.offsets[e] + c_begin * BK;
   const int kchunks = c_end - c_begin;
 
-  // GATHER: producer warp pw issues row groups [g0, g1) of the 16 groups of a 64-row chunk, for every 64-column box of X2;
-  // lane l < g1 - g0 keeps the 4 token indices of group g0 + l, fetched one chunk ahead
-  constexpr int kGroups = BK / 4;
-  constexpr int kPerWarp = (kGroups + kGatherWarps - 1) / kGatherWarps;
-  auto load_idx = [&](int kc, int g0, int g1) -> int4 {
-    int4 v = make_int4(0, 0, 0, 0);
-    if (kc < kchunks && lane < g1 - g0)
-      v = __ldg(reinterpret_cast<const int4*>(p.row_token + r0 + (int64_t)kc * BK) + g0 + lane);
-    return v;
-  };
-  auto issue_gathers = [&](const int4& idx, int g0, int g1, uint32_t sb, uint32_t bar) {
-#pragma unroll
-    for (int g = 0; g < kPerWarp; ++g) {
-      if (g0 + g < g1) {
-        const int q0 = __shfl_sync(0xffffffffu, idx.x, g), q1 = __shfl_sync(0xffffffffu, idx.y, g);
-        const int q2 = __shfl_sync(0xffffffffu, idx.z, g), q3 = __shfl_sync(0xffffffffu, idx.w, g);
-#pragma unroll
-        for (int b = 0; b < BN / 64; ++b)
-          tma_gather4_elect(sb + b * Cfg::BOX + (g0 + g) * 512, &tm2, bar, n0 + b * 64, q0, q1, q2, q3);
-      }
-    }
-  };
-  if (GATHER && warp >= 6) {
-    const int pw = warp - 6 + 1, g0 = pw * kPerWarp, g1 = g0 + kPerWarp < kGroups ? g0 + kPerWarp : kGroups;
-    const uint32_t smem_base = smem_u32(smem), full0 = smem_u32(&full[0]);
-    uint32_t phase = 0;
-    int4 cur = make_int4(0, 0, 0, 0), nxt = load_idx(0, g0, g1);
-    for (int kc0 = 0; kc0 < kchunks; kc0 += STAGES) {
-#pragma unroll
-      for (int st = 0; st < STAGES; ++st) {
-        if (kc0 + st < kchunks) {
-          cur = nxt;
-          nxt = load_idx(kc0 + st + 1, g0, g1);
-          mbar_wait(&empty[st], phase ^ 1);
-          __syncwarp();
-          issue_gathers(cur, g0, g1, smem_base + st * Cfg::STAGE + Cfg::A_BYTES, full0 + st * 8);
-        }
-      }
-      phase ^= 1;
-    }
-  } else if (warp == 0) {
+  if (warp == 0) {
     // converged warp, elected lane issues; ring walked in rounds with a compile-time stage index (see gg_kernel)
     uint32_t phase = 0;
     const uint32_t smem_base = smem_u32(smem), full0 = smem_u32(&full[0]);
     const bool no_tma = (p.dbg & 2) != 0;
     Tracer trc(p.trace, p.trace_cap, 0);
-    constexpr int gg1 = kPerWarp < kGroups ? kPerWarp : kGroups;
-    int4 gcur = make_int4(0, 0, 0, 0), gnxt = GATHER ? load_idx(0, 0, gg1) : make_int4(0, 0, 0, 0);
     for (int kc0 = 0; kc0 < kchunks; kc0 += STAGES) {
 #pragma unroll
       for (int st = 0; st < STAGES; ++st) {
         if (kc0 + st < kchunks) {
-          if (GATHER) { gcur = gnxt; gnxt = load_idx(kc0 + st + 1, 0, gg1); }
           trc.ev(0x00, kc0 + st);
           mbar_wait(&empty[st], phase ^ 1);
           trc.ev(0x01, kc0 + st);
@@ -664,12 +502,8 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tm1, const __grid_constant__ CU
             const int r = r0 + (kc0 + st) * BK;
 #pragma unroll
             for (int b = 0; b < BM / 64; ++b) tma_load_2d_elect(sa + b * Cfg::BOX, &tm1, bar, m0 + b * 64, r);
-            if (GATHER) {
-              issue_gathers(gcur, 0, gg1, sa + Cfg::A_BYTES, bar);
-            } else {
 #pragma unroll
-              for (int b = 0; b < BN / 64; ++b) tma_load_2d_elect(sa + Cfg::A_BYTES + b * Cfg::BOX, &tm2, bar, n0 + b * 64, r);
-            }
+            for (int b = 0; b < BN / 64; ++b) tma_load_2d_elect(sa + Cfg::A_BYTES + b * Cfg::BOX, &tm2, bar, n0 + b * 64, r);
           }
         }
       }
@@ -823,24 +657,18 @@ static int epi_warps() {
   return kDefaultEpiWarps[EPI];                        // (bit 0x200 selects the block width, see launch_gg)
 }
 
-template <int BN, int EPI, int EW, bool BRES, int CWP, bool GATHER = false>
+template <int BN, int EPI, int EW, int CWP>
 static int launch_gg_t(const CUtensorMap* maps, const GGParams& p, int max_tiles, cudaStream_t st) {
-  using Cfg = GGCfg<BN, EPI, kGGNcta, EW, BRES, CWP>;
-  auto kern = gg_kernel<BN, EPI, kGGNcta, EW, BRES, CWP, GATHER>;
+  using Cfg = GGCfg<BN, EPI, kGGNcta, EW, CWP>;
+  auto kern = gg_kernel<BN, EPI, kGGNcta, EW, CWP>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
   if (e != cudaSuccess) return (int)e;
   int grid = max_tiles < g_gemm_sms ? max_tiles : g_gemm_sms;
   grid = grid / kGGNcta * kGGNcta;
   if (grid < kGGNcta) grid = kGGNcta;
-  if (BRES) {   // units come in groups of n_tiles (one per N-tile) walking the same rows
-    const int n_tiles = p.N / BN;
-    int units = grid / kGGNcta / n_tiles * n_tiles;
-    if (units < n_tiles) return M3_ERR_SHAPE;     // caller checked
-    grid = units * kGGNcta;
-  }
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(grid);
-  cfg.blockDim = dim3(gg_threads(EW, GATHER));
+  cfg.blockDim = dim3(gg_threads(EW));
   cfg.dynamicSmemBytes = Cfg::SMEM;
   cfg.stream = st;
   cudaLaunchAttribute attr[2];
@@ -860,16 +688,13 @@ static int launch_gg_t(const CUtensorMap* maps, const GGParams& p, int max_tiles
 
 // A [cap_rows][Kd] bf16, B [E*N][Kd] bf16 -> out [cap_rows][N] (+ out2 / aux of the same shape)
 template <int EPI>
-// gather_rows > 0 (EPI_FC1 only): A is the [gather_rows][Kd] bf16 TOKEN matrix and p.row_token maps queue rows to tokens
 static int launch_gg(const void* A, const void* B, void* out, void* out2, const void* aux, GGParams p, int cap_rows,
-                     cudaStream_t st, int gather_rows = 0) {
+                     cudaStream_t st) {
   constexpr bool heavy = (EPI == EPI_FC1 || EPI == EPI_DGELU);
   const int BN = pick_bn(p.N, heavy);
   if (BN == 0 || p.Kd % BK != 0 || cap_rows % (BM * kGGNcta) != 0) return M3_ERR_SHAPE;
-  if (gather_rows > 0 && (EPI != EPI_FC1 || p.row_token == nullptr)) return M3_ERR_ARG;
-  CUtensorMap maps[3];      // A (or the token matrix), B, aux (saved gelu' of the dgelu epilogue); outputs use plain stores
-  int rc = gather_rows > 0 ? make_map(&maps[0], A, (uint64_t)gather_rows, (uint64_t)p.Kd, 1)     // box {64, 1}: tile::gather4
-                           : make_map(&maps[0], A, (uint64_t)cap_rows, (uint64_t)p.Kd, BM);
+  CUtensorMap maps[3];      // A, B, aux (saved gelu' of the dgelu epilogue); outputs use plain stores
+  int rc = make_map(&maps[0], A, (uint64_t)cap_rows, (uint64_t)p.Kd, BM);
   if (rc) return rc;
   rc = make_map(&maps[1], B, (uint64_t)p.E * p.N, (uint64_t)p.Kd, (uint32_t)(BN / kGGNcta));
   if (rc) return rc;
@@ -885,35 +710,18 @@ static int launch_gg(const void* A, const void* B, void* out, void* out2, const 
   p.trace = trace_buf_for_this_launch();
   p.trace_cap = g_trace_cap;
   const int max_tiles = (cap_rows / BM) * (p.N / BN);
-  // resident weights (BRES) where they fit: Kd <= 384, BN <= 192, and enough SMs for one unit per N-tile
-  const int usable = (max_tiles < g_gemm_sms ? max_tiles : g_gemm_sms) / kGGNcta;
-  const bool bres = g_knobs[M3_KNOB_BRES] == 1 && p.Kd / BK <= kBresMaxChunks && BN <= 192 && usable >= p.N / BN;
-#define M3_GG_EW(BNV)                                                                          \
-  (ew == 16 ? launch_gg_t<BNV, EPI, 16, false, 32>(maps, p, max_tiles, st)                      \
-            : narrow ? launch_gg_t<BNV, EPI, 8, false, 32>(maps, p, max_tiles, st)              \
-                     : launch_gg_t<BNV, EPI, 8, false, 64>(maps, p, max_tiles, st))
-#define M3_GG_EW_BRES(BNV)                                                                     \
-  (ew == 16 ? launch_gg_t<BNV, EPI, 16, true, 32>(maps, p, max_tiles, st)                       \
-            : narrow ? launch_gg_t<BNV, EPI, 8, true, 32>(maps, p, max_tiles, st)               \
-                     : launch_gg_t<BNV, EPI, 8, true, 64>(maps, p, max_tiles, st))
-  if constexpr (EPI == EPI_FC1) {
-    if (gather_rows > 0) {
-      if (BN == 192) return ew == 16 ? launch_gg_t<192, EPI, 16, false, 32, true>(maps, p, max_tiles, st)
-                                     : launch_gg_t<192, EPI, 8, false, 64, true>(maps, p, max_tiles, st);
-      if (BN == 128) return ew == 16 ? launch_gg_t<128, EPI, 16, false, 32, true>(maps, p, max_tiles, st)
-                                     : launch_gg_t<128, EPI, 8, false, 64, true>(maps, p, max_tiles, st);
-      return M3_ERR_SHAPE;
-    }
-  }
+#define M3_GG_EW(BNV)                                                                   \
+  (ew == 16 ? launch_gg_t<BNV, EPI, 16, 32>(maps, p, max_tiles, st)                      \
+            : narrow ? launch_gg_t<BNV, EPI, 8, 32>(maps, p, max_tiles, st)              \
+                     : launch_gg_t<BNV, EPI, 8, 64>(maps, p, max_tiles, st))
   switch (BN) {
-    case 128: return bres ? M3_GG_EW_BRES(128) : M3_GG_EW(128);
-    case 192: return bres ? M3_GG_EW_BRES(192) : M3_GG_EW(192);
+    case 128: return M3_GG_EW(128);
+    case 192: return M3_GG_EW(192);
     default:
       if constexpr (!heavy) return M3_GG_EW(256);
       return M3_ERR_SHAPE;
   }
 #undef M3_GG_EW
-#undef M3_GG_EW_BRES
 }
 
 // out[i] = sum_s part[s][i] (fixed order), float4-wide
@@ -940,33 +748,24 @@ static size_t wgrad_ws_bytes(int E, int M, int N) {
 }
 
 // dW [E][M][N] fp32 = X1[rows][M]^T X2[rows][N] per expert (+ db [E][M] = column sums of X1)
-// row_token != NULL: X2 is the [gather_rows][N] bf16 token matrix, its queue rows are gathered (tile::gather4)
 static int launch_wgrad(const void* X1, const void* X2, const int32_t* offsets, int cap_rows, int E, int M, int N,
-                        float* dW, float* db, float* ws, cudaStream_t st, const int32_t* row_token = nullptr,
-                        int gather_rows = 0) {
+                        float* dW, float* db, float* ws, cudaStream_t st) {
   constexpr int BN = 128;
   if (M % BM != 0 || N % BN != 0 || (M * (int64_t)N) % 4 != 0) return M3_ERR_SHAPE;
   CUtensorMap t1, t2;
   int rc = make_map(&t1, X1, (uint64_t)cap_rows, (uint64_t)M, BK);
   if (rc) return rc;
-  rc = row_token ? make_map(&t2, X2, (uint64_t)gather_rows, (uint64_t)N, 1) : make_map(&t2, X2, (uint64_t)cap_rows, (uint64_t)N, BK);
+  rc = make_map(&t2, X2, (uint64_t)cap_rows, (uint64_t)N, BK);
   if (rc) return rc;
   using Cfg = WGCfg<BN>;
   const int S = wgrad_splits(E, M, N);
   float* pW = S > 1 ? ws : dW;
   float* pb = S > 1 ? ws + (size_t)S * E * M * N : db;
-  WGParams p{offsets, M, N, pW, pb, E, g_knobs[M3_KNOB_DEBUG], trace_buf_for_this_launch(), g_trace_cap, row_token};
-  if (row_token) {
-    auto kern = wgrad_kernel<BN, true>;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
-    if (e != cudaSuccess) return (int)e;
-    launch_k(kern, dim3(M / BM, N / BN, E * S), dim3(kThreads + (kGatherWarps - 1) * 32), Cfg::SMEM, st, t1, t2, p);
-  } else {
-    auto kern = wgrad_kernel<BN, false>;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
-    if (e != cudaSuccess) return (int)e;
-    launch_k(kern, dim3(M / BM, N / BN, E * S), dim3(kThreads), Cfg::SMEM, st, t1, t2, p);
-  }
+  WGParams p{offsets, M, N, pW, pb, E, g_knobs[M3_KNOB_DEBUG], trace_buf_for_this_launch(), g_trace_cap};
+  auto kern = wgrad_kernel<BN>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
+  if (e != cudaSuccess) return (int)e;
+  launch_k(kern, dim3(M / BM, N / BN, E * S), dim3(kThreads), Cfg::SMEM, st, t1, t2, p);
   M3_LAUNCH_CHECK();
   if (S > 1) {
     const int64_t n4 = (int64_t)E * M * N / 4;
@@ -988,31 +787,29 @@ using namespace m3;
 using namespace m3::tc;
 typedef __nv_bfloat16 bf16;
 
-// ffn_fused.cu
-int m3_ffn_fused_supported(int D, int H);
-int m3_ffn_fused_fwd(const void* xq, const int32_t* offsets, const int32_t* tile_expert, int cap_rows, int E, int D,
-                     int H, const void* w1, const float* b1, const void* w2, const float* b2, void* hpre, void* yq,
+// ffn_chain.cu
+int m3_ffn_chain_supported(int D, int H);
+int m3_ffn_chain_fwd(const void* xq, const int32_t* offsets, const int32_t* tile_expert, int cap_rows, int E, int D,
+                     int H, const void* w1, const float* b1, const void* w2, const float* b2, void* yq, int max_ctas,
                      cudaStream_t st);
-int m3_ffn_fused_bwd(const void* dyq, const void* hpre, const int32_t* offsets, const int32_t* tile_expert,
-                     int cap_rows, int E, int D, int H, const void* w2t, const void* w1t, void* dhpre, void* h,
-                     void* dxq, cudaStream_t st);
-// M3_FFN_FUSED=1 selects the single-kernel fc1->GELU->fc2 chain (ffn_fused.cu) where the shape allows.
-// It is parity-tested but currently slower than the two CTA-pair GEMMs at D = H = 384 (its N = 64
-// chunk MMAs re-read the whole resident x tile from shared memory), so the
-// two-kernel path stays the default.
-static bool use_fused(int D, int H) {
-  static const bool on = [] { const char* v = getenv("M3_FFN_FUSED"); return v != nullptr && v[0] == '1'; }();
-  return on && m3_ffn_fused_supported(D, H);
+// The single-kernel fc1 -> GELU -> fc2 chain (ffn_chain.cu) runs the forwards that keep NO state (inference), where its
+// [128 x D] output accumulator fits TMEM (D = 128 / 256 / 384) and H <= 2 D: 2 queue-sized planes of DRAM traffic instead
+// of 4, 121 vs 125 us at the bench shape (at H = 4 D the two GEMMs win: 395 vs 403 us).  M3_KNOB_FFN_CHAIN = 0 switches it
+// off.  Training keeps the two grouped GEMMs: a chain forward that saves z (one plane instead of two) measured 128 vs
+// 143 us, but the backward then has to rebuild h = gelu(z) AND gelu'(z) - in the first GEMM's epilogue 258 vs 230 us, as a
+// backward chain kernel 285 us - so every variant lost over forward + backward and none is kept.
+static bool chain_inference(int D, int H) {
+  return g_knobs[M3_KNOB_FFN_CHAIN] != 0 && m3_ffn_chain_supported(D, H) && H <= 2 * D;
 }
+int m3_ffn_bf16_chain_mode(int D, int H) { return chain_inference(D, H) ? 1 : 0; }
 
 // Opaque activation state handed from m3_ffn_fwd to m3_ffn_bwd (bf16): two [cap][H] planes,
-//   plane 0 = gelu'(z) (two-kernel path) or z (fused chain kernel),  plane 1 = h = gelu(z) (two-kernel path).
-size_t m3_ffn_bf16_saved_bytes(int cap_rows, int H) { return 2 * align256((size_t)cap_rows * H * 2); }
+//   plane 0 = gelu'(z),  plane 1 = h = gelu(z)
+size_t m3_ffn_bf16_saved_bytes(int cap_rows, int D, int H) { (void)D; return 2 * align256((size_t)cap_rows * H * 2); }
 
-// workspace: forward  : h [cap][H] bf16 (inference only; training keeps h in the saved state)
-//            backward : dz [cap][H] bf16 | h [cap][H] bf16 (fused path only) | wgrad split-K partials fp32
+// workspace: forward  : h [cap][H] bf16 (two-kernel inference only; training keeps h in the saved state)
+//            backward : dz [cap][H] bf16 | (unused [cap][H]) | wgrad split-K partials fp32
 size_t m3_ffn_bf16_workspace_bytes(int cap_rows, int D, int H, int E, int backward) {
-  (void)E;
   const size_t hbytes = align256((size_t)cap_rows * H * 2);
   if (!backward) return hbytes;
   const size_t wg = wgrad_ws_bytes(E, D, H) > wgrad_ws_bytes(E, H, D) ? wgrad_ws_bytes(E, D, H) : wgrad_ws_bytes(E, H, D);
@@ -1024,8 +821,8 @@ int m3_ffn_fwd_bf16(const void* xq, const int32_t* offsets, const int32_t* tile_
                     void* workspace, size_t workspace_bytes, cudaStream_t st) {
   if (workspace == nullptr || workspace_bytes < m3_ffn_bf16_workspace_bytes(cap_rows, D, H, E, 0)) return M3_ERR_WORKSPACE;
   g_trace_launch_idx = 0;
-  if (use_fused(D, H))
-    return m3_ffn_fused_fwd(xq, offsets, tile_expert, cap_rows, E, D, H, w1, b1, w2, b2, saved, yq, st);
+  if (saved == nullptr && chain_inference(D, H))
+    return m3_ffn_chain_fwd(xq, offsets, tile_expert, cap_rows, E, D, H, w1, b1, w2, b2, yq, g_gemm_sms, st);
   const size_t hbytes = align256((size_t)cap_rows * H * 2);
   bf16* gp = static_cast<bf16*>(saved);
   bf16* h = saved ? reinterpret_cast<bf16*>(static_cast<uint8_t*>(saved) + hbytes) : static_cast<bf16*>(workspace);
@@ -1048,77 +845,28 @@ int m3_ffn_bwd_bf16(const void* xq, const void* saved, const void* dyq, const in
   if (workspace_bytes < m3_ffn_bf16_workspace_bytes(cap_rows, D, H, E, 1)) return M3_ERR_WORKSPACE;
   g_trace_launch_idx = 0;
   const size_t hbytes = align256((size_t)cap_rows * H * 2);
-  bf16* dhpre = static_cast<bf16*>(workspace);
+  bf16* dz = static_cast<bf16*>(workspace);
   float* part = reinterpret_cast<float*>(static_cast<uint8_t*>(workspace) + 2 * hbytes);
   const bf16* h;
   int rc;
-  if (use_fused(D, H)) {
-    // one kernel: dz = (dyq W2) * gelu'(z), h = gelu(z), dxq = dz W1      (saved plane 0 = z)
-    bf16* hw = reinterpret_cast<bf16*>(static_cast<uint8_t*>(workspace) + hbytes);
-    rc = m3_ffn_fused_bwd(dyq, saved, offsets, tile_expert, cap_rows, E, D, H, w2t, w1t, dhpre, hw, dxq, st);
-    if (rc) return rc;
-    h = hw;
-  } else {
+  {
     h = reinterpret_cast<const bf16*>(static_cast<const uint8_t*>(saved) + hbytes);
     GGParams p{};
     p.offsets = offsets; p.tile_expert = tile_expert; p.E = E;
     // dz = (dyq W2) * gelu'(z)                              B = W2^T [E][H][D] (K-major in D)
     p.N = H; p.Kd = D;
-    rc = launch_gg<EPI_DGELU>(dyq, w2t, dhpre, nullptr, saved, p, cap_rows, st);
+    rc = launch_gg<EPI_DGELU>(dyq, w2t, dz, nullptr, saved, p, cap_rows, st);
     if (rc) return rc;
     // dxq = dz W1                                           B = W1^T [E][D][H] (K-major in H)
     p.N = D; p.Kd = H;
-    rc = launch_gg<EPI_STORE>(dhpre, w1t, dxq, nullptr, nullptr, p, cap_rows, st);
+    rc = launch_gg<EPI_STORE>(dz, w1t, dxq, nullptr, nullptr, p, cap_rows, st);
     if (rc) return rc;
   }
   // dW2[e] = dyq_e^T h_e  [D][H];   dW1[e] = dz_e^T xq_e  [H][D]
   // the bias gradients ride along in the same MMA against a tile of ones
   rc = launch_wgrad(dyq, h, offsets, cap_rows, E, D, H, dw2, db2, part, st);
   if (rc) return rc;
-  return launch_wgrad(dhpre, xq, offsets, cap_rows, E, H, D, dw1, db1, part, st);
-}
-
-// Gather variants: no dispatched queue xq.  x_bf16 is the [T][D] token matrix, row_token[queue row] the token whose copy that
-// row would hold (>= T: a padding row, reads as zeros).  Everything downstream of fc1 is unchanged.
-int m3_ffn_fwd_bf16_gather(const void* x_bf16, const int32_t* row_token, int T, const int32_t* offsets,
-                           const int32_t* tile_expert, int cap_rows, int E, int D, int H, const void* w1, const float* b1,
-                           const void* w2, const float* b2, void* saved, void* yq, void* workspace,
-                           size_t workspace_bytes, cudaStream_t st) {
-  if (workspace == nullptr || workspace_bytes < m3_ffn_bf16_workspace_bytes(cap_rows, D, H, E, 0)) return M3_ERR_WORKSPACE;
-  g_trace_launch_idx = 0;
-  const size_t hbytes = align256((size_t)cap_rows * H * 2);
-  bf16* gp = static_cast<bf16*>(saved);
-  bf16* h = saved ? reinterpret_cast<bf16*>(static_cast<uint8_t*>(saved) + hbytes) : static_cast<bf16*>(workspace);
-  GGParams p{};
-  p.offsets = offsets; p.tile_expert = tile_expert; p.E = E;
-  p.N = H; p.Kd = D; p.bias = b1; p.save_out2 = saved != nullptr; p.row_token = row_token;
-  int rc = launch_gg<EPI_FC1>(x_bf16, w1, h, gp, nullptr, p, cap_rows, st, T);
-  if (rc) return rc;
-  p.N = D; p.Kd = H; p.bias = b2; p.save_out2 = 0; p.row_token = nullptr;
-  return launch_gg<EPI_BIAS>(h, w2, yq, nullptr, nullptr, p, cap_rows, st);
-}
-
-int m3_ffn_bwd_bf16_gather(const void* x_bf16, const int32_t* row_token, int T, const void* saved, const void* dyq,
-                           const int32_t* offsets, const int32_t* tile_expert, int cap_rows, int E, int D, int H,
-                           const void* w1t, const void* w2t, void* dxq, float* dw1, float* db1, float* dw2, float* db2,
-                           void* workspace, size_t workspace_bytes, cudaStream_t st) {
-  if (workspace_bytes < m3_ffn_bf16_workspace_bytes(cap_rows, D, H, E, 1)) return M3_ERR_WORKSPACE;
-  g_trace_launch_idx = 0;
-  const size_t hbytes = align256((size_t)cap_rows * H * 2);
-  bf16* dhpre = static_cast<bf16*>(workspace);
-  float* part = reinterpret_cast<float*>(static_cast<uint8_t*>(workspace) + 2 * hbytes);
-  const bf16* h = reinterpret_cast<const bf16*>(static_cast<const uint8_t*>(saved) + hbytes);
-  GGParams p{};
-  p.offsets = offsets; p.tile_expert = tile_expert; p.E = E;
-  p.N = H; p.Kd = D;
-  int rc = launch_gg<EPI_DGELU>(dyq, w2t, dhpre, nullptr, saved, p, cap_rows, st);
-  if (rc) return rc;
-  p.N = D; p.Kd = H;
-  rc = launch_gg<EPI_STORE>(dhpre, w1t, dxq, nullptr, nullptr, p, cap_rows, st);
-  if (rc) return rc;
-  rc = launch_wgrad(dyq, h, offsets, cap_rows, E, D, H, dw2, db2, part, st);
-  if (rc) return rc;
-  return launch_wgrad(dhpre, x_bf16, offsets, cap_rows, E, H, D, dw1, db1, part, st, row_token, T);   // dW1 = dz^T gather(x)
+  return launch_wgrad(dz, xq, offsets, cap_rows, E, H, D, dw1, db1, part, st);
 }
 
 int m3_ffn_bf16_set_sm_limit(int sms) {

@@ -511,34 +511,6 @@ dispatch_bwd_gate_mma_kernel(Queue<const __nv_bfloat16> dxq, const int32_t* __re
   }
 }
 
-// Gather path (no dispatched queue): fc1 and the dW1 GEMM read their queue rows straight from the token matrix with TMA
-// gather4 (ffn_bf16.cu).  One launch prepares what they need:
-//   CTAs [0, cast_ctas)            x_bf16 = bf16(x)                      (skipped when x is bf16 already)
-//   CTAs [cast_ctas, +slot_ctas)   row_token[pos[t,k]] = t               (the inverse of the route plan)
-//   last E CTAs                    row_token[padding rows of expert e] = T   (past the tensor: gather4 reads zeros)
-__global__ void __launch_bounds__(256)
-gather_prepare_kernel(const float* __restrict__ x, int64_t n8, __nv_bfloat16* __restrict__ xb,
-                      const int32_t* __restrict__ pos, const int32_t* __restrict__ counts,
-                      const int32_t* __restrict__ offsets, int T, int K, int cast_ctas, int slot_ctas,
-                      int32_t* __restrict__ row_token) {
-  pdl_wait();
-  pdl_trigger();
-  const int b = blockIdx.x;
-  if (b < cast_ctas) {
-    for (int64_t i = (int64_t)b * 256 + threadIdx.x; i < n8; i += (int64_t)cast_ctas * 256)
-      store8<__nv_bfloat16>(xb + i * 8, load8<float>(x + i * 8));
-  } else if (b < cast_ctas + slot_ctas) {
-    const int64_t s = (int64_t)(b - cast_ctas) * 256 + threadIdx.x;
-    if (s < (int64_t)T * K) {
-      const int r = __ldg(pos + s);
-      if (r >= 0) row_token[r] = (int)(s / K);
-    }
-  } else {
-    const int e = b - cast_ctas - slot_ctas;
-    for (int r = offsets[e] + counts[e] + threadIdx.x; r < offsets[e + 1]; r += 256) row_token[r] = T;
-  }
-}
-
 static inline int perm_nv(int D) { return m3_ceil_div(D / 8, kLanesPerTok); }
 
 }  // namespace m3
@@ -796,20 +768,3 @@ extern "C" int m3_zero_pad_rows(void* q, int dtype, const int32_t* counts, const
   return M3_OK;
 }
 
-extern "C" int m3_gather_prepare(const float* x, int T, int D, const int32_t* pos, const int32_t* counts,
-                                 const int32_t* offsets, int K, int E, void* x_bf16, int32_t* row_token,
-                                 m3_stream_t stream) {
-  M3_CHECK_ARG(pos && counts && offsets && row_token && T >= 0 && K >= 1 && E >= 1 && D >= 8);
-  M3_CHECK_ARG((x == nullptr) == (x_bf16 == nullptr));
-  M3_CHECK_SHAPE(D % 8 == 0);
-  if (x) { M3_CHECK_ALIGN16(x); M3_CHECK_ALIGN16(x_bf16); }
-  M3_CHECK_ALIGN16(row_token);
-  const int64_t n8 = (int64_t)T * D / 8;
-  int cast_ctas = x ? (int)((n8 + 255) / 256) : 0;
-  if (cast_ctas > 16 * kNumSMs) cast_ctas = 16 * kNumSMs;
-  const int slot_ctas = (int)(((int64_t)T * K + 255) / 256);
-  launch_k(gather_prepare_kernel, cast_ctas + slot_ctas + E, 256, 0, static_cast<cudaStream_t>(stream), x, n8,
-           static_cast<bf16*>(x_bf16), pos, counts, offsets, T, K, cast_ctas, slot_ctas, row_token);
-  M3_LAUNCH_CHECK();
-  return M3_OK;
-}

@@ -85,16 +85,38 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-// Bounded wait: a protocol bug must fault the kernel (trap), never hang the GPU.
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  if (mbar_try_wait(bar, parity)) return;
+// Bounded wait: a protocol bug must fault the kernel (trap), never hang the GPU.  The polling loop with its time-out
+// lives OUT OF LINE: inlined at every wait site (~35 SASS instructions each, printf call included) it bloated the
+// warp-specialised loops past the instruction cache.
+static __device__ __noinline__ void mbar_wait_slow(uint32_t bar, uint32_t parity) {
   const long long t0 = clock64();
-  while (!mbar_try_wait(bar, parity)) {
+  for (;;) {
+    uint32_t ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (ok) return;
     if (clock64() - t0 > 4000000000LL) {  // ~2 s
       printf("m3 tcgen05: mbarrier timeout (block %d thread %d parity %u)\n", blockIdx.x, threadIdx.x, parity);
       __trap();
     }
   }
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  if (!mbar_try_wait(bar, parity)) mbar_wait_slow(smem_u32(bar), parity);
+}
+// two barriers at once: both try_waits are in flight together (a try_wait on a completed barrier still takes ~90 clk,
+// and the issuing warps of the chain kernel do little else)
+__device__ __forceinline__ void mbar_wait2(uint64_t* a, uint32_t pa, uint64_t* b, uint32_t pb) {
+  const bool oa = mbar_try_wait(a, pa), ob = mbar_try_wait(b, pb);
+  if (!oa) mbar_wait_slow(smem_u32(a), pa);
+  if (!ob) mbar_wait_slow(smem_u32(b), pb);
 }
 
 // generic-proxy smem writes -> visible to the async proxy (TMA / tcgen05 operand reads)
@@ -243,6 +265,15 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t 
   return d;
 }
 
+// 1-D bulk copy global -> shared (this CTA), completion on a local mbarrier; bytes % 16 == 0, both addresses 16-byte aligned
+__device__ __forceinline__ void bulk_load_1d_elect(uint32_t smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+  asm volatile(
+      "{\n.reg .pred q;\nelect.sync _|q, 0xffffffff;\n"
+      "@q cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n}\n"
+      ::"r"(smem_dst), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+      : "memory");
+}
+
 // ------------------------------------------------ lean MMA issue (whole warp converged, one elected lane issues)
 // The issuing warp runs its loop CONVERGED (all 32 lanes wait on the mbarriers and do the - warp-uniform - descriptor
 // arithmetic), and only the tcgen05 instruction itself is predicated on elect.sync.  Inside an `if (lane == 0)` region
@@ -285,6 +316,41 @@ __device__ __forceinline__ void umma_bf16_2sm_elect(uint32_t d_tmem, uint32_t a_
       "}\n" ::"r"(d_tmem),
       "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
       : "memory");
+}
+// Several k-boxes of MMAs under ONE election: the descriptor halves reach the uniform datapath once and advance there
+// (~3 SASS instructions per MMA instead of ~16 with one asm block per MMA).  It matters for the N = 64 MMAs of the
+// chain kernel, whose floor is 32 clk each: issued one by one they cost ~60-100 clk apiece and the issuing thread,
+// not the tensor pipe, set the pace.
+//   NBOX boxes of 4 MMAs (UMMA_K = 16: descriptors 32 B = 2 units apart inside a 64-wide SWIZZLE_128B k-box); between
+//   boxes A advances by a_box and B by b_box (descriptor units of 16 bytes); all accumulate into d_tmem, the very first
+//   MMA with `accumulate_first`.
+#define M3_MMA2(ACC) "@q tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %4, " ACC ";\n"
+#define M3_ADV2 "add.s64 da, da, 2;\nadd.s64 db, db, 2;\n"
+#define M3_BOX_REST M3_ADV2 M3_MMA2("1") M3_ADV2 M3_MMA2("1") M3_ADV2 M3_MMA2("1")
+#define M3_NEXT_BOX "add.s64 da, da, %6;\nadd.s64 db, db, %7;\n" M3_MMA2("1") M3_BOX_REST
+template <int NBOX>
+__device__ __forceinline__ void umma_bf16_2sm_elect_boxes(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t hi,
+                                                          uint32_t idesc, uint32_t accumulate_first, uint32_t a_box,
+                                                          uint32_t b_box) {
+  static_assert(NBOX >= 1 && NBOX <= 6, "boxes per block");
+  // after a box the descriptors stand 6 units past its start
+  const unsigned long long sa = (unsigned long long)a_box - 6ull, sb = (unsigned long long)b_box - 6ull;
+#define M3_BLOCK(BODY)                                                                                                  \
+  asm volatile("{\n.reg .pred p, q;\n.reg .b64 da, db;\nelect.sync _|q, 0xffffffff;\nmov.b64 da, {%1, %3};\n"           \
+               "mov.b64 db, {%2, %3};\nsetp.ne.b32 p, %5, 0;\n" M3_MMA2("p") M3_BOX_REST BODY "}\n" ::"r"(d_tmem),       \
+               "r"(a_lo), "r"(b_lo), "r"(hi), "r"(idesc), "r"(accumulate_first), "l"(sa), "l"(sb)                       \
+               : "memory")
+  if constexpr (NBOX == 1) M3_BLOCK("");
+  if constexpr (NBOX == 2) M3_BLOCK(M3_NEXT_BOX);
+  if constexpr (NBOX == 3) M3_BLOCK(M3_NEXT_BOX M3_NEXT_BOX);
+  if constexpr (NBOX == 4) M3_BLOCK(M3_NEXT_BOX M3_NEXT_BOX M3_NEXT_BOX);
+  if constexpr (NBOX == 5) M3_BLOCK(M3_NEXT_BOX M3_NEXT_BOX M3_NEXT_BOX M3_NEXT_BOX);
+  if constexpr (NBOX == 6) M3_BLOCK(M3_NEXT_BOX M3_NEXT_BOX M3_NEXT_BOX M3_NEXT_BOX M3_NEXT_BOX);
+#undef M3_BLOCK
+}
+__device__ __forceinline__ void umma_bf16_2sm_elect_x4(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t hi,
+                                                       uint32_t idesc, uint32_t accumulate_first) {
+  umma_bf16_2sm_elect_boxes<1>(d_tmem, a_lo, b_lo, hi, idesc, accumulate_first, 6, 6);
 }
 __device__ __forceinline__ void umma_commit_elect(uint64_t* bar) {
   asm volatile(
@@ -336,29 +402,6 @@ __device__ __forceinline__ void tma_load_2d_2sm_elect(uint32_t smem_dst, const C
       "{\n.reg .pred q;\nelect.sync _|q, 0xffffffff;\n"
       "@q cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];\n}\n"
       ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_cluster_addr), "r"(c0), "r"(c1)
-      : "memory");
-}
-
-// TMA tile::gather4: four arbitrary rows (r0..r3) of a 2-D row-major tensor whose map has box {64 columns, 1 row} land as
-// four consecutive 128-byte rows of a SWIZZLE_128B box (the swizzle is a function of the shared-memory address, so 32
-// gathers fill the same [128 rows][64 bf16] operand tile one tiled load would); a row index past the tensor reads as zeros
-// (verified on a B200: tools/microbench/tma_gather4.cu).  Elected-lane issue like the other producer instructions.
-__device__ __forceinline__ void tma_gather4_elect(uint32_t smem_dst, const CUtensorMap* m, uint32_t bar, int c0, int r0,
-                                                  int r1, int r2, int r3) {
-  asm volatile(
-      "{\n.reg .pred q;\nelect.sync _|q, 0xffffffff;\n"
-      "@q cp.async.bulk.tensor.2d.shared::cluster.global.tile::gather4.mbarrier::complete_tx::bytes "
-      "[%0], [%1, {%3, %4, %5, %6, %7}], [%2];\n}\n" ::"r"(smem_dst),
-      "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(r0), "r"(r1), "r"(r2), "r"(r3)
-      : "memory");
-}
-__device__ __forceinline__ void tma_gather4_2sm_elect(uint32_t smem_dst, const CUtensorMap* m, uint32_t bar_cluster_addr,
-                                                      int c0, int r0, int r1, int r2, int r3) {
-  asm volatile(
-      "{\n.reg .pred q;\nelect.sync _|q, 0xffffffff;\n"
-      "@q cp.async.bulk.tensor.2d.shared::cluster.global.tile::gather4.mbarrier::complete_tx::bytes.cta_group::2 "
-      "[%0], [%1, {%3, %4, %5, %6, %7}], [%2];\n}\n" ::"r"(smem_dst),
-      "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_cluster_addr), "r"(c0), "r"(r0), "r"(r1), "r"(r2), "r"(r3)
       : "memory");
 }
 

@@ -281,7 +281,7 @@ def phase_c_ffn(ctx: EPContext, st: EPFwdState, w1c, b1, w2c, b2, save_hpre: boo
     dt = dtype_code(st.xq)
     st.off_yq = ctx.arena.alloc(st.nbytes_q)
     st.yq = ctx.arena.view(st.off_yq, cap, D, st.xq.dtype)
-    st.hpre = (torch.empty(max(int(lib.m3_ffn_saved_bytes(dt, cap, H)), 16), dtype=torch.uint8, device=st.xq.device)
+    st.hpre = (torch.empty(max(int(lib.m3_ffn_saved_bytes(dt, cap, D, H)), 16), dtype=torch.uint8, device=st.xq.device)
                if save_hpre else None)        # opaque activation state for phase F
     ws = torch.empty(max(lib.m3_ffn_workspace_bytes(dt, cap, D, H, E_loc, 0), 16), dtype=torch.uint8, device=st.xq.device)
     check(lib.m3_ffn_fwd(dt, ptr(st.xq), ptr(st.recv.offsets), ptr(st.recv.tile_expert), cap, E_loc, D, H, ptr(w1c),

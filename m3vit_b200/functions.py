@@ -51,20 +51,13 @@ class MoEFunction(torch.autograd.Function):
         else:
             w1c, w2c, w1t, w2t = w1, w2, None, None
         needs_grad = any(ctx.needs_input_grad)
-        gather = ops.USE_GATHER and compute_dtype == torch.bfloat16 and D % 64 == 0 and T > 0
-        if gather:
-            # no dispatched queue: fc1 (and dW1 in backward) gather their rows from the bf16 token matrix (TMA gather4)
-            xq, row_token = ops.gather_prepare(x, plan, top_k)          # xq := x_bf16 [T, D]
-            yq, hpre = ops.ffn_fwd_gather(xq, row_token, plan, w1c, b1, w2c, b2, save_hpre=needs_grad)
-        else:
-            row_token = None
-            xq = ops.dispatch_fwd(x, plan, top_k, out_dtype=compute_dtype)
-            yq, hpre = ops.ffn_fwd(xq, plan, w1c, b1, w2c, b2, save_hpre=needs_grad)
+        xq = ops.dispatch_fwd(x, plan, top_k, out_dtype=compute_dtype)
+        yq, hpre = ops.ffn_fwd(xq, plan, w1c, b1, w2c, b2, save_hpre=needs_grad)
         out = ops.combine_fwd(yq, plan, g.score, out_dtype=x.dtype)
         if needs_grad:
             ctx.save_for_backward(x, gate_x, w_gate, task_feat, w1c, w2c, w1t, w2t, xq, hpre, yq, g.score,
                                   g.noisy_logits, g.idx_full, plan.counts, plan.offsets, plan.pos, plan.tile_expert,
-                                  plan.importance, row_token)
+                                  plan.importance)
             ctx.cfg = (top_k, plan.cap_rows, gate_x is not None)
         gates = g.gates if g.gates is not None else x.new_empty(0)
         ctx.mark_non_differentiable(g.idx, plan.load, plan.counts)
@@ -79,17 +72,14 @@ class MoEFunction(torch.autograd.Function):
     @staticmethod
     def backward(ctx, d_out, d_score, d_top, d_clean, d_noisy, d_gates, d_imp, _dl, _di, _dc, d_cv):
         (x, gate_x, w_gate, task_feat, w1c, w2c, w1t, w2t, xq, hpre, yq, score, logits, idx_full, counts, offsets,
-         pos, tile_expert, importance, row_token) = ctx.saved_tensors
+         pos, tile_expert, importance) = ctx.saved_tensors
         top_k, cap_rows, separate_gate_inp = ctx.cfg
         T, D = x.shape
         plan = ops.Plan(counts, offsets, pos, tile_expert, cap_rows, PAD_ROWS)
         if d_out is None:
             d_out = torch.zeros_like(x)
         dyq, dscore = ops.combine_bwd(_c(d_out), yq, plan, score)
-        if row_token is not None:
-            dxq, dw1, db1, dw2, db2 = ops.ffn_bwd_gather(xq, row_token, hpre, dyq, plan, w1t, w2t)
-        else:
-            dxq, dw1, db1, dw2, db2 = ops.ffn_bwd(xq, hpre, dyq, plan, w1c, w2c, w1t, w2t)
+        dxq, dw1, db1, dw2, db2 = ops.ffn_bwd(xq, hpre, dyq, plan, w1c, w2c, w1t, w2t)
         if d_score is not None:
             dscore = dscore + d_score
         if d_gates is not None and d_gates.numel() == 0:

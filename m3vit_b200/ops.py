@@ -19,13 +19,8 @@ from ._lib import PAD_ROWS, check, dtype_code, load, ptr, require_device, stream
 # kernels launched by each C entry point (our own kernels; used for bench.py's `gpu_launches`)
 LAUNCHES = {"gate_fwd": 1, "gate_bwd": 3, "gate_bwd_dx": 1, "route_plan": 2, "dispatch_fwd": 1, "dispatch_bwd": 1,
             "combine_fwd": 1, "combine_bwd": 1, "cast_weights": 1, "ffn_fwd": 2, "ffn_bwd_f32": 6, "ffn_bwd_bf16": 4,
-            "ln_stats": 1, "ln_fold_gate": 1, "ln_bwd_res": 2, "gather_prepare": 1}
+            "ln_stats": 1, "ln_fold_gate": 1, "ln_bwd_res": 2, "ffn_chain": 1}
 launch_count = 0
-
-# bf16 single-GPU layer: fc1 / dW1 gather their rows from the token matrix (TMA gather4) instead of reading a dispatched
-# queue (M3_GATHER=0 restores dispatch_fwd + ffn_fwd; bit-identical results either way)
-import os as _os
-USE_GATHER = _os.environ.get("M3_GATHER", "0") != "0"
 
 
 def _count(name, n=1):
@@ -241,13 +236,13 @@ def ffn_fwd(xq, plan: Plan, w1, b1, w2, b2, save_hpre=True):
     E, H, _ = w1.shape
     dt = dtype_code(xq)
     assert w1.dtype == xq.dtype and w2.dtype == xq.dtype and b1.dtype == torch.float32
-    # opaque activation state for the backward pass (fp32: pre-activation; bf16: gelu'(z) and h planes)
-    hpre = _ws(lib.m3_ffn_saved_bytes(dt, cap, H), xq.device) if save_hpre else None
+    # opaque activation state for the backward pass (fp32: pre-activation; bf16: z, or gelu'(z) and h planes)
+    hpre = _ws(lib.m3_ffn_saved_bytes(dt, cap, D, H), xq.device) if save_hpre else None
     yq = torch.empty(cap, D, dtype=xq.dtype, device=xq.device)
     ws = _ws(lib.m3_ffn_workspace_bytes(dt, cap, D, H, E, 0), xq.device)
     check(lib.m3_ffn_fwd(dt, ptr(xq), ptr(plan.offsets), ptr(plan.tile_expert), cap, E, D, H, ptr(w1), ptr(b1),
                          ptr(w2), ptr(b2), ptr(hpre), ptr(yq), ptr(ws), ws.numel(), stream_ptr()), "m3_ffn_fwd")
-    _count("ffn_fwd")
+    _count("ffn_chain" if (not save_hpre and lib.m3_ffn_uses_chain(dt, D, H)) else "ffn_fwd")
     return yq, hpre
 
 
@@ -273,60 +268,6 @@ def ffn_bwd(xq, hpre, dyq, plan: Plan, w1, w2, w1t=None, w2t=None):
             _count("cast_weights", 4)                # 2 x (dW + db) split-K reduce launches
     else:
         _count("ffn_bwd_f32")
-    return dxq, dw1, db1, dw2, db2
-
-
-# ------------------------------------------------- gather path: no dispatched queue (bf16, single GPU)
-def gather_prepare(x, plan: Plan, top_k):
-    """x [T,D] fp32|bf16 -> (x_bf16 [T,D], row_token [cap_rows] int32): what fc1 / the dW1 GEMM gather their rows through."""
-    require_device(x)
-    T, D = x.shape
-    E = plan.counts.numel()
-    row_token = torch.empty(plan.cap_rows, dtype=torch.int32, device=x.device)
-    if x.dtype == torch.bfloat16:
-        xb, src = x, None
-    else:
-        assert x.dtype == torch.float32
-        xb, src = torch.empty(T, D, dtype=torch.bfloat16, device=x.device), x
-    check(load().m3_gather_prepare(ptr(src), T, D, ptr(plan.pos), ptr(plan.counts), ptr(plan.offsets), top_k, E,
-                                   ptr(xb) if src is not None else None, ptr(row_token), stream_ptr()), "m3_gather_prepare")
-    _count("gather_prepare")
-    return xb, row_token
-
-
-def ffn_fwd_gather(xb, row_token, plan: Plan, w1, b1, w2, b2, save_hpre=True):
-    """as ffn_fwd, the A rows of fc1 gathered from the token matrix xb [T,D] bf16 through row_token."""
-    require_device(xb)
-    lib = load()
-    T, D = xb.shape
-    E, H, _ = w1.shape
-    cap = plan.cap_rows
-    assert xb.dtype == torch.bfloat16 and w1.dtype == torch.bfloat16 and w2.dtype == torch.bfloat16
-    hpre = _ws(lib.m3_ffn_saved_bytes(L.M3_BF16, cap, H), xb.device) if save_hpre else None
-    yq = torch.empty(cap, D, dtype=torch.bfloat16, device=xb.device)
-    ws = _ws(lib.m3_ffn_workspace_bytes(L.M3_BF16, cap, D, H, E, 0), xb.device)
-    check(lib.m3_ffn_fwd_gather(ptr(xb), ptr(row_token), T, ptr(plan.offsets), ptr(plan.tile_expert), cap, E, D, H,
-                                ptr(w1), ptr(b1), ptr(w2), ptr(b2), ptr(hpre), ptr(yq), ptr(ws), ws.numel(),
-                                stream_ptr()), "m3_ffn_fwd_gather")
-    _count("ffn_fwd")
-    return yq, hpre
-
-
-def ffn_bwd_gather(xb, row_token, hpre, dyq, plan: Plan, w1t, w2t):
-    """as ffn_bwd (bf16), dW1 = dz^T gather(xb)."""
-    require_device(xb)
-    lib = load()
-    T, D = xb.shape
-    E, _, H = w1t.shape          # w1t [E, D, H]
-    cap = plan.cap_rows
-    dev = xb.device
-    dxq = torch.empty(cap, D, dtype=torch.bfloat16, device=dev)
-    dw1, db1, dw2, db2 = _f32((E, H, D), dev), _f32((E, H), dev), _f32((E, D, H), dev), _f32((E, D), dev)
-    ws = _ws(lib.m3_ffn_workspace_bytes(L.M3_BF16, cap, D, H, E, 1), dev)
-    check(lib.m3_ffn_bwd_gather(ptr(xb), ptr(row_token), T, ptr(hpre), ptr(dyq), ptr(plan.offsets), ptr(plan.tile_expert),
-                                cap, E, D, H, ptr(w1t), ptr(w2t), ptr(dxq), ptr(dw1), ptr(db1), ptr(dw2), ptr(db2),
-                                ptr(ws), ws.numel(), stream_ptr()), "m3_ffn_bwd_gather")
-    _count("ffn_bwd_bf16")
     return dxq, dw1, db1, dw2, db2
 
 

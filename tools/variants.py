@@ -89,31 +89,18 @@ timed("torch x.clone() (59 MB read + 59 MB write)", lambda: x.clone())
 ref_f = ops.ffn_fwd(xq, plan, w1c, b1, w2c, b2)
 ref_b = ops.ffn_bwd(xq, hpre, dyq, plan, w1c, w2c, w1t, w2t)
 KNOB_DEBUG = 4
-KNOB_BRES = 6
-xb_, rt_ = ops.gather_prepare(x, plan, K)
-yq_g, hpre_g = ops.ffn_fwd_gather(xb_, rt_, plan, w1c, b1, w2c, b2)
-print("  gather path: yq bits equal to dispatch path:", same(yq_g, yq), " saved state:", same(hpre_g, hpre))
-gb = ops.ffn_bwd_gather(xb_, rt_, hpre_g, dyq, plan, w1t, w2t)
-rb = ops.ffn_bwd(xq, hpre, dyq, plan, w1c, w2c, w1t, w2t)
-print("  gather path: backward bits equal:", same(gb, rb))
-timed("gather_prepare (cast + row_token)", lambda: ops.gather_prepare(x, plan, K))
-timed("ffn_fwd        [dispatch path: reads xq]", lambda: ops.ffn_fwd(xq, plan, w1c, b1, w2c, b2))
-timed("ffn_fwd_gather [fc1 gathers from x_bf16]", lambda: ops.ffn_fwd_gather(xb_, rt_, plan, w1c, b1, w2c, b2))
-timed("ffn_bwd        [dispatch path]", lambda: ops.ffn_bwd(xq, hpre, dyq, plan, w1c, w2c, w1t, w2t))
-timed("ffn_bwd_gather [dW1 gathers from x_bf16]", lambda: ops.ffn_bwd_gather(xb_, rt_, hpre_g, dyq, plan, w1t, w2t))
-KNOB_DEBUG = 4
-for off in (1, 0):
-    lib.m3_set_knob(KNOB_BRES, 0 if off else 1)
-    of = ops.ffn_fwd(xq, plan, w1c, b1, w2c, b2)
-    ob = ops.ffn_bwd(xq, hpre, dyq, plan, w1c, w2c, w1t, w2t)
-    torch.cuda.synchronize()
-    if off == 1:
-        ref_f, ref_b = of, ob
-    nm = "streamed weights" if off else "resident weights"
-    print(f"  [{nm}] bits equal to streamed: fwd {same(of, ref_f)}  bwd {same(ob, ref_b)}")
-    timed(f"ffn_fwd (fc1+fc2)      [{nm}]", lambda: ops.ffn_fwd(xq, plan, w1c, b1, w2c, b2))
-    timed(f"ffn_bwd (2 dgrad+2 wg) [{nm}]", lambda: ops.ffn_bwd(xq, hpre, dyq, plan, w1c, w2c, w1t, w2t))
-lib.m3_set_knob(KNOB_BRES, 0)
+KNOB_CHAIN = 6
+for chain_on, nm in ((0, "two grouped GEMMs"), (2, "chain kernel (training too)")):
+    lib.m3_set_knob(KNOB_CHAIN, chain_on)
+    yq_c, hpre_c = ops.ffn_fwd(xq, plan, w1c, b1, w2c, b2)
+    timed(f"ffn_fwd training  [{nm}]", lambda: ops.ffn_fwd(xq, plan, w1c, b1, w2c, b2))
+    timed(f"ffn_fwd inference [{nm}]", lambda: ops.ffn_fwd(xq, plan, w1c, b1, w2c, b2, save_hpre=False))
+    timed(f"ffn_bwd           [{nm}]", lambda: ops.ffn_bwd(xq, hpre_c, dyq, plan, w1c, w2c, w1t, w2t))
+# the knob sweeps below exercise the grouped GEMM kernels
+lib.m3_set_knob(KNOB_CHAIN, 0)
+yq, hpre = ops.ffn_fwd(xq, plan, w1c, b1, w2c, b2)
+ref_f = ops.ffn_fwd(xq, plan, w1c, b1, w2c, b2)
+ref_b = ops.ffn_bwd(xq, hpre, dyq, plan, w1c, w2c, w1t, w2t)
 for pr, name in ((0, "L2 promotion 256 B (default)"), (3, "L2 promotion 128 B"), (1, "no L2 promotion"), (0, "L2 promotion 256 B (default)")):
     lib.m3_set_knob(KNOB_DEBUG, pr << 12)
     timed(f"ffn_fwd (fc1+fc2)      [{name}]", lambda: ops.ffn_fwd(xq, plan, w1c, b1, w2c, b2))
@@ -133,6 +120,7 @@ for mask, name in ((0, "default: fc1 16 warps, others 8 warps x 64-col blocks"),
     timed(f"ffn_fwd (fc1+fc2)      [{name}]", lambda: ops.ffn_fwd(xq, plan, w1c, b1, w2c, b2))
     timed(f"ffn_bwd (2 dgrad+2 wg) [{name}]", lambda: ops.ffn_bwd(xq, hpre, dyq, plan, w1c, w2c, w1t, w2t))
 lib.m3_set_knob(KNOB_EPI, 0)
+lib.m3_set_knob(KNOB_CHAIN, 1)
 
 # ---------------- combine fwd / bwd variants
 ref_c = ops.combine_fwd(yq, plan, g.score)
@@ -177,10 +165,10 @@ def time_step(name, n=10):
 
 
 for rep in range(3):
-    lib.m3_set_knob(KNOB_EPI, 0x100)
-    time_step("fc1: 8 warps")
-    lib.m3_set_knob(KNOB_EPI, 0)
-    time_step("fc1:16 warps (default)")
+    lib.m3_set_knob(KNOB_CHAIN, 0)
+    time_step("two grouped GEMMs per direction")
+    lib.m3_set_knob(KNOB_CHAIN, 2)
+    time_step("chain kernel in training (saves z)")
 lib.m3_set_knob(KNOB_PDL, 1)
 time_step("PDL on")
 lib.m3_set_knob(KNOB_PDL, 0)
