@@ -16,8 +16,14 @@ e2e    : same step through the public module API with HOST (pinned) token buffer
          double-buffered) and D2H of the loss scalars inside the timed region.
 roofline: the grouped expert-FFN GEMM kernel (gg_kernel), tensor-bound, timed live.
 cpu_baseline / --impl reference: the CPU oracle port of the reference layer
-         (oracle/moe_oracle.py, fp32 PyTorch on the host cores) on a bounded
-         sample (config C1: B = 2).
+         (oracle/moe_oracle.py, fp32 PyTorch on the host cores) on the SAME workload
+         (same B, same N, both task gates); each step is a bounded sample of the 12
+         layer calls of a step (as many as fit the time budget; the line says how many).
+configs: the other BASELINE.json configurations (C1 reference batch, C3 ViT-B 5-gate,
+         C4 task-conditioned 8193 tokens, ratio-4 experts, E = 64 / top-2), one layer
+         call fwd+bwd each, reported beside the headline line under "configs".
+ep_parity (N > 1): an untimed comparison of the expert-parallel layer with the same layer
+         holding all experts locally, on this rank's tokens (max over ranks).
 """
 from __future__ import annotations
 
@@ -115,34 +121,52 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------- CPU reference arm
-def cpu_reference(steps, warmup, batch=2, threads=None):
-    """The reference layer's CPU implementation (oracle port, fp32 PyTorch) on the host cores:
-    config C1 sample (B=2, one task-gate layer call fwd+bwd per step)."""
+def cpu_reference(steps, warmup, batch, budget_s=150.0, threads=None):
+    """The reference layer's CPU implementation (oracle port of models/moe/origin/custom_moe_layer.py +
+    noisy_gate_vmoe.py, fp32 PyTorch) on the host cores, on the bench workload itself: B = `batch` images x 1201
+    tokens per layer call, both task gates, fwd+bwd with the balance loss.  One step = `calls` of the 12 layer calls
+    of a step (distinct layers / gates in the step's order); `calls` is the largest number <= 12 for which
+    (warmup + steps) steps fit `budget_s`, measured on the first call."""
     from oracle import moe_oracle as O
     from m3vit_b200.synthetic import MoECase, make_weights, make_tokens
     threads = threads or os.cpu_count()
     torch.set_num_threads(threads)
-    case = MoECase("C1", batch=batch, tokens=N_TOK, d_model=D_MODEL, d_hidden=D_HID, num_expert=N_EXP, top_k=TOP_K,
+    case = MoECase("C2", batch=batch, tokens=N_TOK, d_model=D_MODEL, d_hidden=D_HID, num_expert=N_EXP, top_k=TOP_K,
                    num_gates=N_TASK)
-    w = make_weights(case, 0)
+    layers = []
+    for li in range(N_LAYER):
+        w = make_weights(case, li)
+        layers.append(([w[k].clone().requires_grad_(True) for k in ("w1", "b1", "w2", "b2")],
+                       [wg.clone().requires_grad_(True) for wg in w["w_gate"]]))
     x0 = make_tokens(case, 0)
-    g = torch.randn(x0.shape, generator=torch.Generator().manual_seed(1))
-    params = [w[k].clone().requires_grad_(True) for k in ("w1", "b1", "w2", "b2")]
-    gates = [wg.clone().requires_grad_(True) for wg in w["w_gate"]]
+    g = torch.randn(x0.shape, generator=torch.Generator().manual_seed(1)) * 0.01
+    order = [(li, t) for t in range(N_TASK) for li in range(N_LAYER)]
+
+    def call(i):
+        li, t = order[i % len(order)]
+        params, gates = layers[li]
+        x = x0.clone().requires_grad_(True)
+        out, gd = O.layer_forward(x, gates[t], *params, TOP_K, training=True)
+        ((out * g).sum() + 0.01 * gd["loss"]).backward()
+
+    t0 = time.perf_counter()
+    call(0)                                   # also the first warm-up (page-in, thread pool start)
+    t_first = time.perf_counter() - t0
+    calls = int(max(1, min(len(order), budget_s / max(t_first * (steps + warmup), 1e-9))))
     times = []
     for it in range(warmup + steps):
-        x = x0.clone().requires_grad_(True)
         t0 = time.perf_counter()
-        out, gd = O.layer_forward(x, gates[it % N_TASK], *params, TOP_K, training=True)
-        ((out * g).sum() + 0.01 * gd["loss"]).backward()
+        for i in range(calls):
+            call(it * calls + i)
         dt = time.perf_counter() - t0
         if it >= warmup:
             times.append(dt)
     med = statistics.median(times)
-    return dict(value=case.T / med, unit="tokens/s", cores=threads, kind="port",
-                sample=f"config C1: 1 layer call fwd+bwd, B={batch} x {N_TOK} tokens, fp32 PyTorch CPU oracle "
-                       f"(oracle/moe_oracle.py), median of {steps} after {warmup} warm-up",
-                ms_per_call=med * 1e3)
+    return dict(value=calls * case.T / med, unit="tokens/s", cores=threads, kind="port",
+                sample=f"{calls} of the {len(order)} layer calls of a step per timed step, B={batch} x {N_TOK} tokens per call "
+                       f"(the bench workload), fp32 PyTorch CPU oracle port (oracle/moe_oracle.py; pinned bit-exact to the "
+                       f"reference's own files by tests/test_oracle.py), median of {steps} steps after {warmup} warm-up",
+                calls_per_step=calls, ms_per_step=med * 1e3, ms_per_call=med * 1e3 / calls)
 
 
 # ----------------------------------------------------------------------------- our arm
@@ -189,6 +213,126 @@ def one_call(layer, x, g, task):
     return gate_loss
 
 
+def other_configs(dev, cdt, pk, iters=8):
+    """The other BASELINE.json configurations, one MoE layer call each (fwd and fwd+bwd, CUDA events): C1 (the
+    reference's own batch of 2), C3 (ViT-B, PASCAL-Context 5 task gates), C4 (task-conditioned shared router on
+    Cityscapes-sized 8193-token images) and the C5 sweep corners.  `tflops` counts the algorithmic flops of SURVEY 8(d):
+    3 x (2 Dg E + 4 K D H) per token; `frac` is against the sustained bf16 peak (a whole call: GEMMs, movers, router)."""
+    import m3vit_b200 as M
+    from m3vit_b200.synthetic import device_tokens
+    cases = [
+        ("c1_vits_nyud_b2", dict(B=2, N=1201, D=384, H=384, E=16, K=4, gates=2, Dt=0)),
+        ("c3_vitb_pascal_5gate_b8", dict(B=8, N=1025, D=768, H=768, E=16, K=4, gates=5, Dt=0)),
+        ("c3_vitb_pascal_5gate_b32", dict(B=32, N=1025, D=768, H=768, E=16, K=4, gates=5, Dt=0)),
+        ("c4_taskcond_cityscapes_b4", dict(B=4, N=8193, D=384, H=384, E=16, K=4, gates=0, Dt=64)),
+        ("c5_ratio4_b32", dict(B=32, N=1201, D=384, H=1536, E=16, K=4, gates=2, Dt=0)),
+        ("c5_e64_top2_b32", dict(B=32, N=1201, D=384, H=384, E=64, K=2, gates=2, Dt=0)),
+        ("c5_e32_top1_b32", dict(B=32, N=1201, D=384, H=384, E=32, K=1, gates=2, Dt=0)),
+    ]
+    res = {}
+    w01 = torch.tensor(0.01, device=dev)
+    for name, c in cases:
+        torch.manual_seed(0)
+        B, N, D, H, E, K, G, Dt = (c[k] for k in ("B", "N", "D", "H", "E", "K", "gates", "Dt"))
+        act = torch.nn.Sequential(torch.nn.GELU(), torch.nn.Dropout(0.0))
+        if Dt > 0:      # one shared router conditioned on a task embedding (gate_task_specific_dim > 0, task_one_hot loop)
+            layer = M.FMoETransformerMLP(num_expert=E, d_model=D, d_gate=D, d_hidden=H, activation=act, gate=M.NoisyGate_VMoE,
+                                         top_k=K, vmoe_noisy_std=0, multi_gate=False, gate_task_specific_dim=Dt,
+                                         compute_dtype=cdt).to(dev).train()
+            feat = torch.randn(Dt, device=dev)
+            gate = layer.gate
+            fwd = lambda x: layer(x, task_id=1, task_specific_feature=feat)
+        else:
+            layer = M.FMoETransformerMLP(num_expert=E, d_model=D, d_gate=D + G, d_hidden=H, activation=act,
+                                         gate=M.NoisyGate_VMoE, top_k=K, vmoe_noisy_std=0, multi_gate=True,
+                                         compute_dtype=cdt).to(dev).train()
+            gate = layer.gate[G - 1]
+            fwd = lambda x: layer(x, task_id=G - 1)
+        T = B * N
+        x = device_tokens(T, D, 0, dev).requires_grad_(True)
+        g = torch.randn(T, D, device=dev) * 0.01
+
+        def step(bwd):
+            x.grad = None
+            out = fwd(x)
+            if bwd:
+                torch.autograd.backward([out, gate.get_loss()], [g, w01])
+        t = []
+        for bwd in (False, True):
+            for _ in range(2):
+                step(bwd)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            e0.record()
+            for _ in range(iters):
+                step(bwd)
+            e1.record()
+            e1.synchronize()
+            t.append(e0.elapsed_time(e1) / iters * 1e-3)
+        flops = 3.0 * (2 * (D + Dt) * E + 4 * K * D * H) * T
+        res[name] = {**c, "tokens_per_call": T, "fwd_us": t[0] * 1e6, "fwd_bwd_us": t[1] * 1e6,
+                     "tokens_per_s": T / t[1], "tflops": flops / t[1] / 1e12, "frac_of_sustained_bf16": flops / t[1] / 1e12 / pk["tf_sus"]}
+        del layer, x, g
+    return res
+
+
+def ep_parity(layers, ep_layer_inputs, dev, cdt, rank, world, dist):
+    """Untimed: the expert-parallel layer against the SAME layer with all experts local, on this rank's tokens.
+    Returns the largest absolute differences over all ranks (out, dx) and the largest normalised difference of the
+    local experts' weight gradients against the matching slice of the replicated layer's - which sees only this
+    rank's tokens, so that check is done at world-summed level with an all-reduce of the replicated gradients."""
+    ep_layer, x0, g0 = ep_layer_inputs
+    full = build_layers(dev, cdt)[0]                       # all experts local, same seeds
+    res = {}
+    outs = []
+    for layer in (ep_layer, full):
+        for p_ in layer.parameters():
+            p_.grad = None
+        x = x0.detach().clone().requires_grad_(True)
+        out = layer(x, task_id=1)
+        torch.autograd.backward([out], [g0])
+        outs.append((out.detach(), x.grad.detach(), layer.experts.htoh4.weight.grad.detach().clone(),
+                     layer.gate[1].w_gate.grad.detach().clone()))
+    (o_ep, dx_ep, dw_ep, dg_ep), (o_f, dx_f, dw_f, dg_f) = outs
+    e_loc = N_EXP // world
+    dist.all_reduce(dw_f)                                  # an expert's gradient sums over every rank's tokens
+    dw_ref = dw_f[rank * e_loc:(rank + 1) * e_loc]
+    vals = torch.stack([(o_ep - o_f).abs().max(), (dx_ep - dx_f).abs().max(),
+                        (dw_ep - dw_ref).abs().max() / dw_ref.abs().max().clamp_min(1e-20),
+                        (dg_ep - dg_f).abs().max() / dg_f.abs().max().clamp_min(1e-20)]).float()
+    dist.all_reduce(vals, op=dist.ReduceOp.MAX)
+    v = [float(t) for t in vals]
+    res = {"out_max_abs_diff": v[0], "dx_max_abs_diff": v[1], "expert_wgrad_max_rel_diff": v[2],
+           "router_wgrad_max_rel_diff": v[3],
+           "ok": bool(v[0] <= 1e-6 and v[1] <= 1e-6 and v[2] <= 1e-4 and v[3] <= 1e-4),
+           "what": "EP layer vs the same layer with all 16 experts local on each rank's tokens (max over ranks); rows take the "
+                   "same arithmetic in both, so out / dx are expected to be bit-identical"}
+    for p_ in ep_layer.parameters():
+        p_.grad = None
+    del full
+    return res
+
+
+def ncu_traffic(kernel_key):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture, valid only for
+    the kernel sources it was taken from (profiles/ncu_traffic.json records their sha256): a stale capture reads as null."""
+    import hashlib
+    p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if not os.path.exists(p):
+        return None, "no capture"
+    d = json.load(open(p))
+    e = d.get(kernel_key)
+    if e is None:
+        return None, "no capture for this configuration"
+    h = hashlib.sha256()
+    for f in e["sources"]:
+        with open(os.path.join(ROOT, f), "rb") as fh:
+            h.update(fh.read())
+    if h.hexdigest() != e["sources_sha256"]:
+        return None, "capture is older than the kernel sources"
+    return e["dram_bytes_per_launch"], e["capture"]
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -198,6 +342,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-configs", action="store_true", help="skip the other BASELINE configurations (\"configs\" key)")
     ap.add_argument("--capacity-factor", type=float, default=2.0,
                     help="EP receive-queue rows as a multiple of the local T*K (overflow is detected and raised)")
     args = ap.parse_args()
@@ -215,9 +360,11 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return
-        cb = cpu_reference(max(args.steps, 3), warmup)
+        cb = cpu_reference(max(args.steps, 3), warmup, args.batch)
+        config["reference_sample"] = (f"each timed step = {cb['calls_per_step']} of the {N_LAYER * N_TASK} layer calls (bounded "
+                                      "sample of the same workload: same B, N, D, H, E, K, both task gates)")
         line = {"metric": METRIC, "value": cb["value"], "unit": "tokens/s", "n_gpus": args.gpus, "steps": args.steps,
-                "warmup": warmup, "ms_per_step": cb["ms_per_call"], "higher_is_better": True, "scaling": "weak",
+                "warmup": warmup, "ms_per_step": cb["ms_per_step"], "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic", "impl": "reference", "config": config,
                 "cpu_baseline": cb,
                 "e2e": {"value": cb["value"], "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -241,14 +388,8 @@ def main():
         assert N_EXP % world == 0
         el = 2 if cdt == torch.bfloat16 else 4
         q_bytes = ((int(args.capacity_factor * T * TOP_K) + (N_EXP // world) * 255 + 255) // 256 * 256) * D_MODEL * el
-        if os.environ.get("M3_EP_OVERLAP", "0") == "1":
-            # opt-in: two half-batches on two streams, the NVLink movers of one half overlap the GEMMs of the other.
-            # Correct (tools/ep_multiproc_check.py ... pipe) but host-launch-bound from Python today.
-            ep_ctx = ep.make_pipelined_context(ep.TorchDistGroup(), dev, arena_bytes=6 * (q_bytes // 2 + (1 << 20)),
-                                               capacity_factor=args.capacity_factor)
-        else:
-            ep_ctx = ep.make_context(ep.TorchDistGroup(), dev, arena_bytes=6 * (q_bytes + 4096),
-                                     capacity_factor=args.capacity_factor)
+        ep_ctx = ep.make_context(ep.TorchDistGroup(), dev, arena_bytes=10 * (q_bytes + 4096),
+                                 capacity_factor=args.capacity_factor)
     layers = build_layers(dev, cdt, rank, world, ep_ctx)
     from m3vit_b200.synthetic import device_tokens
     calls = [(li, t) for t in range(N_TASK) for li in range(N_LAYER)]      # per task: a full backbone pass
@@ -362,16 +503,23 @@ def main():
         dist.all_reduce(tms, op=dist.ReduceOp.MAX)
         ems = float(tms.item())
     e2e = {"value": tokens_per_step / (ems * 1e-3), "unit": "tokens/s", "ms_per_step": ems,
-           "h2d_bytes_per_step": len(calls) * T * D_MODEL * 4, "d2h_bytes_per_step": len(calls) * 4}
+           "h2d_bytes_per_step": len(calls) * T * D_MODEL * 4, "d2h_bytes_per_step": len(calls) * 4,
+           "note": "PCIe-bound: the fp32 token matrices of the 12 layer calls cross the bus every step (prefetched one call "
+                   "ahead on a copy stream); h2d_bytes_per_step / ms_per_step is the achieved H2D rate"}
 
     # ---- roofline of the dominant kernel family, timed live on this stream
     pk = peaks()
     roof, stages = None, {}
+    parity = None
     if ep_ctx is not None:
         ep_ctx.check_overflow()
+        parity = ep_parity(layers, (layers[0], xs[0], gs[0]), dev, cdt, rank, world, dist)
     if rank == 0:
         ref_layer = layers[0] if world == 1 else build_layers(dev, cdt)[0]     # all-experts-local layer for the table
         roof, stages = kernel_rooflines(ref_layer, xs[0].detach(), dev, cdt, pk)
+    extra = None
+    if rank == 0 and world == 1 and not args.no_configs:
+        extra = other_configs(dev, cdt, pk)
 
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": "tokens/s", "n_gpus": world, "steps": args.steps,
@@ -381,8 +529,12 @@ def main():
                 "parallelism": (f"expert-parallel ep{world}: {N_EXP // world} experts/GPU, router replicated, token rows "
                                 "pushed/pulled over NVLink peer queues (no NCCL on the data path)") if world > 1
                 else "single GPU, all experts local"}
+        if parity is not None:
+            line["ep_parity"] = parity
+        if extra is not None:
+            line["configs"] = extra
         if not args.no_cpu_baseline:
-            line["cpu_baseline"] = cpu_reference(5, 2)
+            line["cpu_baseline"] = cpu_reference(3, 1, args.batch, budget_s=25.0)
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -459,6 +611,11 @@ def kernel_rooflines(layer, x, dev, cdt, pk, iters=10, nset=4):
         nbytes=R * (8 + 8 + 4))
     add("dispatch_fwd", lambda o: ops.dispatch_fwd(o.x, o.plan, K, out_dtype=cdt), 1, nbytes=T * (D * 4 + K * D * el + K * 4))
     add("ffn_fwd", lambda o: ops.ffn_fwd(o.xq, o.plan, w1c, b1, w2c, b2), 2, flops=4.0 * R * D * H)
+    from m3vit_b200 import _lib as L_
+    chain = bool(L_.load().m3_ffn_uses_chain(1 if cdt == torch.bfloat16 else 0, D, H))
+    add("ffn_fwd_inference", lambda o: ops.ffn_fwd(o.xq, o.plan, w1c, b1, w2c, b2, save_hpre=False), 1 if chain else 2,
+        flops=4.0 * R * D * H)
+    st["ffn_fwd_inference"]["kernel"] = "ffn_chain_kernel (fc1 -> GELU -> fc2 in one launch)" if chain else "gg_kernel x 2"
     add("combine_fwd", lambda o: ops.combine_fwd(o.yq, o.plan, o.g.score), 1, nbytes=T * (K * D * el + K * 8 + D * 4))
     add("combine_bwd", lambda o: ops.combine_bwd(o.go, o.yq, o.plan, o.g.score), 1, nbytes=T * (D * 4 + 2 * K * D * el + K * 12))
     nb = 4 if cdt == torch.bfloat16 else 6
@@ -468,14 +625,14 @@ def kernel_rooflines(layer, x, dev, cdt, pk, iters=10, nset=4):
     add("dispatch_bwd", lambda o: ops.dispatch_bwd(o.dxq, o.plan, T, K, dz=o.dz, w_gate=wg), 1,
         nbytes=T * (K * D * el + K * 4 + D * 4 + E * 4))
     f = st["ffn_fwd"]
-    # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture of this exact
-    # configuration (profiles/r1b_ncu_all_kernels.md: fc1 124.2 + 186.0 MB, fc2 124.1 + 69.7 MB; writes still in
-    # L2 at kernel end are not counted by ncu), averaged over the two launches like `achieved`; null for any other size.
-    traffic = 252.0e6 if (cdt == torch.bfloat16 and T == 32 * N_TOK and D == 384 and H == 384 and K == 4) else None
+    # dram__bytes_read.sum + dram__bytes_write.sum per launch (average of the fc1 and fc2 launches, like `achieved`) from
+    # the committed `ncu --set full` capture of this configuration; null when there is none or the kernels changed since
+    traffic, traffic_src = ncu_traffic(f"ffn_fwd_train:{'bf16' if cdt == torch.bfloat16 else 'f32'}:T{T}:D{D}:H{H}:E{E}:K{K}")
     roof = {"kernel": "gg_kernel<192> (tcgen05 grouped GEMM; fc1+bias+GELU and fc2+bias launches of m3_ffn_fwd)"
             if cdt == torch.bfloat16 else "sgemm_grouped_kernel (fp32 SIMT)",
             "bound": "tensor", "achieved": f["achieved"], "peak": pk["tf_burst"], "unit": "TFLOP/s",
-            "frac": f["frac"], "traffic": traffic, "traffic_unit": "bytes per launch (ncu dram read+write)", "peak_source": pk["src"] + " (burst, kernel timed alone)",
+            "frac": f["frac"], "traffic": traffic, "traffic_unit": "bytes per launch (ncu dram read+write)",
+            "traffic_source": traffic_src, "peak_source": pk["src"] + " (burst, kernel timed alone)",
             "flops_per_launch": 2.0 * R * D * H, "us_per_launch": f["us_per_launch"]}
     return roof, st
 

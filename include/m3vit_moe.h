@@ -161,8 +161,8 @@ size_t m3_ffn_workspace_bytes(int dtype, int cap_rows, int D, int H, int E, int 
 size_t m3_ffn_saved_bytes(int dtype, int cap_rows, int D, int H);
 /* 1 if m3_ffn_fwd with saved == NULL runs this (dtype, D, H) as the chain kernel (launch accounting, tests). */
 int m3_ffn_uses_chain(int dtype, int D, int H);
-/* Process-wide tuning knob: SMs the persistent tcgen05 GEMMs may occupy (default / out of range: all 148).
- * The overlapped expert-parallel mode lowers it so that NVLink row movers run beside a GEMM. */
+/* Process-wide tuning knob: SMs the persistent tcgen05 GEMMs may occupy (default / out of range: all 148), for callers
+ * that run other kernels beside them on another stream. */
 int m3_set_gemm_sm_limit(int sms);
 /* Process-wide tuning knobs (A/B measurement; defaults are the shipped configuration).
  *   M3_KNOB_PDL       1: kernels are launched with programmatic stream serialisation and start their
@@ -246,8 +246,10 @@ int m3_zero_pad_rows(void* q, int dtype, const int32_t* counts, const int32_t* o
 /* Device-side rendezvous of the W ranks over peer memory (replaces an NCCL barrier / the
  * fmoe expert_exchange count all-to-all): a 1-warp kernel stores `epoch` into slot `rank` of every
  * peer's flag array (system-scope release) and, if `payload` != NULL, first copies `payload_ints`
- * int32 into row `rank` of every peer's gather buffer; it then spins (bounded, acquire) until all W
- * slots of ITS OWN flag array have reached `epoch`.  Every rank must call it with the same epoch.
+ * int32 into row `rank` of every peer's gather buffer; it then spins (acquire) until all W slots of ITS OWN flag array
+ * have reached `epoch`.  Every rank must call it with the same epoch.  The spin gives up after 30 minutes
+ * (M3_EP_BARRIER_TIMEOUT_S seconds, read once; 0 = never) with a device-side message and a trap, so that a dead rank
+ * cannot hang a GPU for ever.
  *   peer_flags[W]  device array: base of every rank's flag array (W int32 each)
  *   peer_gather[W] device array: base of every rank's gather buffer [W][payload_ints] (or NULL)
  * Only valid with one process per GPU (ranks must be co-resident on different devices). */
@@ -293,9 +295,6 @@ size_t m3_ln_bwd_workspace_bytes(int T, int D);
 int m3_ln_bwd_res(const float* dxn, const float* x, const float* mean, const float* rstd,
                   const float* gamma, const float* dres, int T, int D, float* dx, float* dgamma,
                   float* dbeta, void* workspace, size_t workspace_bytes, m3_stream_t stream);
-
-/* Debug only: occupy `n_ctas` whole SMs for `cycles` clocks (measures what other kernels get from the rest). */
-int m3_debug_occupy(int n_ctas, long long cycles, int* sink, m3_stream_t stream);
 
 /* Debug only: clock64 timeline of CTA 0 of the tensor-core GEMM kernels (producer / MMA / one epilogue warp), appended
  * to a caller-owned DEVICE buffer of 4 + 6*max_events uint64 (buf[r] = event count of role r = 0 producer / 1 MMA /

@@ -67,7 +67,6 @@ SIGNATURES = {
     "m3_ln_bwd_workspace_bytes": (_sz, [_i, _i]),
     "m3_ln_bwd_res": (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _p, _p, _p, _p, _sz, _p]),
     "m3_debug_trace_buffer": (_i, [_p, _i]),
-    "m3_debug_occupy": (_i, [_i, C.c_longlong, _p, _p]),
     "m3_ipc_alloc": (_i, [_sz, C.POINTER(_p), _p]),
     "m3_ipc_open": (_i, [_p, C.POINTER(_p)]),
     "m3_ipc_close": (_i, [_p]),
@@ -123,6 +122,9 @@ def require_device(t: torch.Tensor) -> None:
     if not t.is_cuda:
         raise M3Error("m3vit_b200 runs on B200 GPUs only: got a CPU tensor (there is no CPU fallback)")
     dev = t.device.index
+    if dev != torch.cuda.current_device():
+        raise M3Error(f"tensor on cuda:{dev} but the current device is cuda:{torch.cuda.current_device()}: the kernels launch "
+                      "on the current device's stream (use torch.cuda.set_device / torch.cuda.device(...))")
     if dev not in _device_ok:
         with torch.cuda.device(dev):
             check(load().m3_check_device(), "m3_check_device")
@@ -146,7 +148,8 @@ _raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
 
 def stream_ptr() -> int:
     """cudaStream_t of torch's current stream on the current device.  The raw C accessor is ~50x cheaper than
-    torch.cuda.current_stream() (16 us of Python per call: it showed up as a quarter of the host time per layer call)."""
+    torch.cuda.current_stream() (16 us of Python per call: it showed up as a quarter of the host time per layer call).
+    Kernels are launched on the CURRENT device: require_device() refuses tensors that live on another one."""
     if _raw_stream is not None:
         return _raw_stream(torch.cuda.current_device())
     return torch.cuda.current_stream().cuda_stream

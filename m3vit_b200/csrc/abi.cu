@@ -1,6 +1,7 @@
 // C-ABI glue: status strings, device check, FFN dtype dispatch, weight casts,
 // expert-parallel plan, CUDA-IPC plumbing.  See include/m3vit_moe.h.
 #include <cstdio>
+#include <cstdlib>
 
 #include "common.cuh"
 
@@ -136,29 +137,6 @@ extern "C" int m3_ffn_bwd(int dtype, const void* xq, const void* hpre, const voi
   return M3_ERR_UNSUPPORTED;
 }
 
-// ------------------------------------------------------------------ debug: SM occupier
-namespace m3 {
-// Fills whole SMs (1024 threads, > 32 registers each, 200 KB of shared memory: nothing else co-resides) and
-// spins for `cycles`.  Used by tools/ep_overlap_probe.py to measure what the NVLink row movers achieve on the
-// SMs a concurrently running persistent GEMM leaves free.
-__global__ void __launch_bounds__(1024) occupy_kernel(long long cycles, int* sink) {
-  extern __shared__ int occupy_smem[];
-  const long long t0 = clock64();
-  int acc = 0;
-  while (clock64() - t0 < cycles) acc += occupy_smem[threadIdx.x & 255];
-  if (acc == 0x7fffffff) *sink = acc;
-}
-}  // namespace m3
-
-extern "C" int m3_debug_occupy(int n_ctas, long long cycles, int* sink, m3_stream_t stream) {
-  M3_CHECK_ARG(n_ctas > 0 && cycles > 0 && sink);
-  const int smem = 200 * 1024;
-  cudaError_t e = cudaFuncSetAttribute(m3::occupy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-  if (e != cudaSuccess) return (int)e;
-  m3::occupy_kernel<<<n_ctas, 1024, smem, static_cast<cudaStream_t>(stream)>>>(cycles, sink);
-  M3_LAUNCH_CHECK();
-  return M3_OK;
-}
 
 // ------------------------------------------------------------------ weight cast
 namespace m3 {
@@ -254,7 +232,8 @@ __global__ void ep_plan_kernel(const int64_t* __restrict__ idx, const int32_t* _
 }
 // Flag barrier (+ optional small all-gather) over peer memory; see m3_ep_barrier in the header.
 __global__ void ep_barrier_kernel(int32_t* const* __restrict__ peer_flags, int32_t* const* __restrict__ peer_gather,
-                                  const int32_t* __restrict__ payload, int n, int rank, int W, int epoch) {
+                                  const int32_t* __restrict__ payload, int n, int rank, int W, int epoch,
+                                  long long timeout_clk) {
   const int lane = threadIdx.x;
   if (peer_gather != nullptr) {
     for (int p = 0; p < W; ++p) {
@@ -274,7 +253,7 @@ __global__ void ep_barrier_kernel(int32_t* const* __restrict__ peer_flags, int32
     int v;
     do {
       asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(mine) : "memory");
-      if (clock64() - t0 > 20000000000LL) {   // ~10 s: a peer never arrived
+      if (timeout_clk > 0 && clock64() - t0 > timeout_clk) {   // a peer never arrived (a dead rank must not hang the GPU)
         printf("m3_ep_barrier: rank %d timed out waiting for rank %d (epoch %d, have %d)\n", rank, lane, epoch, v);
         __trap();
       }
@@ -288,9 +267,17 @@ extern "C" int m3_ep_barrier(void* const* peer_flags, void* const* peer_gather, 
                              int payload_ints, int rank, int W, int epoch, m3_stream_t stream) {
   M3_CHECK_ARG(peer_flags && W >= 1 && W <= 32 && rank >= 0 && rank < W && epoch > 0);
   M3_CHECK_ARG((peer_gather == nullptr) == (payload == nullptr) && payload_ints >= 0);
+  // Ranks are routinely far apart (data-loader start-up at epoch boundaries, rank-0-only evaluation or checkpoint writing,
+  // first-iteration lazy initialisation): wait 30 minutes by default like a collective library would, not seconds.
+  // M3_EP_BARRIER_TIMEOUT_S overrides (0 = wait for ever).
+  static const long long timeout_clk = [] {
+    const char* v = getenv("M3_EP_BARRIER_TIMEOUT_S");
+    const double sec = v != nullptr ? atof(v) : 1800.0;
+    return sec <= 0 ? 0LL : (long long)(sec * 2.0e9);
+  }();
   m3::ep_barrier_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(
       reinterpret_cast<int32_t* const*>(peer_flags), reinterpret_cast<int32_t* const*>(peer_gather), payload,
-      payload_ints, rank, W, epoch);
+      payload_ints, rank, W, epoch, timeout_clk);
   M3_LAUNCH_CHECK();
   return M3_OK;
 }

@@ -644,8 +644,8 @@ static unsigned long long* trace_buf_for_this_launch() {
 }
 constexpr int kGGNcta = 2;   // CTA pairs: halves the per-SM weight traffic (the GEMMs are L2 -> SM bound at K = 384)
 
-// SMs the persistent grouped GEMMs may occupy.  Expert parallelism with overlap (ep.py) lowers it so that the NVLink row
-// movers of the other half-batch find free SMs while a GEMM runs (they need ~12-20 SMs: tools/ep_overlap_probe.py).
+// SMs the persistent grouped GEMMs may occupy (m3_set_gemm_sm_limit): a caller that runs other kernels beside them on
+// another stream (e.g. NVLink row movers, which need ~12-20 SMs) lowers it.
 static int g_gemm_sms = kNumSMs;
 
 // epilogue warps per GEMM epilogue: the knob (8 / 16) wins, otherwise the per-epilogue default

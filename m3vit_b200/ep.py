@@ -16,8 +16,6 @@ world_size > 1) is replaced by peer-mapped expert queues:
     the combine kernel LOADS result rows from the owners (and keeps a local copy for backward);
   * backward: combine_bwd pushes dyq (dscore from the local copy), dispatch_bwd pulls dxq.
     Expert weight gradients need no reduction (each expert's rows are all on its owner).
-  * make_pipelined_context / EPPipeMoEFunction (opt-in): two half-batches on two streams so
-    that the movers of one half overlap the GEMMs of the other.
 
 The protocol is written as explicit phases so that it runs either over torch.distributed
 (one process per GPU, NCCL) or as a single-process multi-rank simulation (tests; one GPU
@@ -172,7 +170,7 @@ class EPContext:
     group: object
     arena: Arena
     bases: torch.Tensor                 # [W] int64 device tensor: arena base pointer of every rank
-    capacity_factor: Optional[float]    # receive-queue rows = factor * T*K (None: worst case W)
+    capacity_factor: Optional[float]    # receive-queue rows = factor * T*K (None: worst case W - nothing can be dropped)
     overflow: torch.Tensor              # [1] int32 device flag set by m3_ep_plan
 
     def peer_ptrs(self, off: int) -> torch.Tensor:
@@ -194,12 +192,66 @@ class EPContext:
         if int(self.overflow.item()) != 0:
             raise RuntimeError("EP receive queue overflow: tokens were dropped; raise capacity_factor")
 
+    def poll_overflow(self) -> None:
+        """Asynchronous check, run by every layer call: the flag of an EARLIER call is copied to pinned host memory on the
+        stream (no synchronisation) and read once that copy has completed - a dropped slot raises at most a few calls
+        late instead of silently corrupting the step.  With capacity_factor=None queues cannot overflow and this is free."""
+        if self.capacity_factor is None:
+            return
+        st = self.__dict__.setdefault("_ovf", {})
+        if "host" not in st:
+            st["host"] = torch.zeros(1, dtype=torch.int32).pin_memory()
+            st["event"] = None
+        ev = st["event"]
+        if ev is not None and ev.query():
+            if int(st["host"][0]) != 0:
+                raise RuntimeError("EP receive queue overflow: a rank received more than capacity_factor * T * K rows and "
+                                   "slots were dropped; raise capacity_factor (None = worst case, nothing can be dropped)")
+            ev = None
+        if ev is None:
+            st["host"].copy_(self.overflow, non_blocking=True)
+            st["event"] = torch.cuda.Event()
+            st["event"].record()
 
-def make_context(group, device, arena_bytes: int, capacity_factor: Optional[float] = 2.0,
+    def check_same_tokens(self, T: int) -> None:
+        """The lockstep arena gives a queue the same offset on every rank only if every rank sizes it the same, i.e. runs the
+        same number of tokens per call.  Checked on the host once per distinct T (a bootstrap-group all-gather)."""
+        seen = self.__dict__.setdefault("_seen_T", set())
+        if T in seen:
+            return
+        boot = getattr(self.group, "bootstrap", self.group)
+        if hasattr(boot, "exchange_bytes"):
+            all_T = [int(b.decode()) for b in boot.exchange_bytes(str(int(T)).encode())]
+            if any(t != T for t in all_T):
+                raise RuntimeError(f"expert parallelism needs the same number of tokens per call on every rank (the peer queues "
+                                   f"live at lockstep arena offsets); got {all_T}.  Pad the local batch to a common size.")
+        seen.add(T)
+
+    # Arena blocks of a finished call are handed back only after the NEXT rendezvous (the count all-gather that opens every
+    # forward): a peer that has passed it has finished every pull of the previous call, so no separate closing barrier is
+    # needed (one rendezvous kernel fewer per forward-only call and per backward).
+    def defer_free(self, off: int, nbytes: int) -> None:
+        self.__dict__.setdefault("_pending", []).append((off, nbytes))
+
+    def apply_deferred_frees(self) -> None:
+        for off, nb in self.__dict__.get("_pending", []):
+            self.arena.free(off, nb)
+        self.__dict__["_pending"] = []
+
+
+def make_context(group, device, arena_bytes: int, capacity_factor: Optional[float] = None,
                  device_barrier: bool = True) -> EPContext:
     """Collective: allocates the arena, exchanges IPC handles, maps the peers.  With
     device_barrier=True (default) the per-layer rendezvous / count exchange run as our own
-    peer-memory kernel; otherwise through the torch.distributed group (NCCL)."""
+    peer-memory kernel; otherwise through the torch.distributed group (NCCL).
+
+    capacity_factor=None (default) sizes every receive queue for the worst case (all W ranks route everything to one
+    rank): like the reference's FastMoE path, nothing can ever be dropped.  A float caps the queue at factor * T * K
+    rows (less arena memory); an overflow then drops slots on the device and RAISES on the host within a few calls
+    (EPContext.poll_overflow, run by every layer call).
+
+    Evaluation must run under torch.no_grad(): a forward with grad enabled keeps its queues until its backward runs, and
+    frees must happen in the same order on every rank (garbage-collection order is not), so they are never freed by GC."""
     arena = Arena(arena_bytes + PeerFlagGroup.HEADER, device)
     handles = group.exchange_bytes(arena.handle_bytes())
     bases = []
@@ -373,7 +425,7 @@ def phase_g_dispatch_bwd(ctx: EPContext, st: EPFwdState, bs: EPBwdState, T, D, t
 def release_fwd(ctx: EPContext, st: EPFwdState) -> None:
     for off in (st.off_yq, st.off_xq):
         if off >= 0:
-            ctx.arena.free(off, st.nbytes_q)
+            ctx.defer_free(off, st.nbytes_q)
     st.off_xq = st.off_yq = -1
     st.xq = st.yq = None
 
@@ -381,7 +433,7 @@ def release_fwd(ctx: EPContext, st: EPFwdState) -> None:
 def release_bwd(ctx: EPContext, st: EPFwdState, bs: EPBwdState) -> None:
     for off in (bs.off_dxq, bs.off_dyq):
         if off >= 0:
-            ctx.arena.free(off, st.nbytes_q)
+            ctx.defer_free(off, st.nbytes_q)
     bs.off_dxq = bs.off_dyq = -1
     bs.dxq = bs.dyq = None
 
@@ -402,8 +454,11 @@ class EPMoEFunction(torch.autograd.Function):
         x = x.contiguous()
         gx = x if gate_x is None else gate_x.contiguous()
         grp = ep.group
+        ep.check_same_tokens(T)
+        ep.poll_overflow()
         st = phase_a_gate(gx, w_gate, top_k, task_feat, noise, noise_stddev, want_gates, E_tot)
         cnt_all = grp.all_gather_counts(st.plan_local.counts)         # also: "all queues are free" rendezvous
+        ep.apply_deferred_frees()                                     # ... so the previous call's blocks can be reused
         phase_b_dispatch(ep, st, x, cnt_all, E_loc, top_k, compute_dtype)
         if compute_dtype == torch.bfloat16:
             w1c, w2c, w1t, w2t = wcache.get_bf16(w1, w2)
@@ -420,8 +475,7 @@ class EPMoEFunction(torch.autograd.Function):
             ctx.save_for_backward(x, gate_x, w_gate, task_feat, w1c, w2c, w1t, w2t, pl.importance)
             ctx.cfg = (top_k, gate_x is not None)
         else:
-            grp.barrier(x.device)                                     # peers are done reading my yq
-            release_fwd(ep, st)
+            release_fwd(ep, st)                                       # handed back after the next rendezvous
         gates = g.gates if g.gates is not None else x.new_empty(0)
         ctx.mark_non_differentiable(g.idx, pl.load, pl.counts)
         noisy = g.clean_logits.view_as(g.clean_logits) if noise is None else g.noisy_logits
@@ -436,8 +490,7 @@ class EPMoEFunction(torch.autograd.Function):
         grp = ep.group
         if d_out is None:
             d_out = torch.zeros_like(x)
-        grp.barrier(x.device)                                         # previous backward's pulls are finished
-        bs = phase_e_combine_bwd(ep, st, d_out.contiguous(), top_k)
+        bs = phase_e_combine_bwd(ep, st, d_out.contiguous(), top_k)     # (fresh dyq block: nobody reads or writes it yet)
         grp.barrier(x.device)
         phase_f_ffn_bwd(ep, st, bs, w1c, w2c, w1t, w2t)
         dscore = bs.dscore if d_score is None else bs.dscore + d_score
@@ -455,8 +508,7 @@ class EPMoEFunction(torch.autograd.Function):
             dx = phase_g_dispatch_bwd(ep, st, bs, T, D, top_k, dz, w_gate, x.dtype)
             dgx = None
         dw1, db1, dw2, db2 = bs.grads
-        grp.barrier(x.device)                                         # peers are done pulling my dxq / yq
-        release_bwd(ep, st, bs)
+        release_bwd(ep, st, bs)                                       # handed back after the next rendezvous
         release_fwd(ep, st)
         ctx.st = None
         if dtf is not None and task_feat is not None:
@@ -464,176 +516,12 @@ class EPMoEFunction(torch.autograd.Function):
         return dx, dgx, dwg, dtf, dw1, db1, dw2, db2, None, None, None, None, None, None, None
 
 
-# ----------------------------------------------------------------------------- overlapped variant
-@dataclass
-class EPPipe:
-    """Two independent EP contexts (arena + flag group each) and two side streams: the token batch is cut in
-    two halves whose phase sequences run on different streams, so the NVLink movers of one half overlap the
-    GEMMs of the other.  The persistent GEMMs are confined to `gemm_sms` SMs (m3_set_gemm_sm_limit) so that
-    the movers always find free SMs (they need 12-20: tools/ep_overlap_probe.py)."""
-    ctxs: List[EPContext]
-    streams: List[torch.cuda.Stream]
-    rank: int
-    world: int
-
-    def check_overflow(self) -> None:
-        for c in self.ctxs:
-            c.check_overflow()
-
-
-def make_pipelined_context(group, device, arena_bytes: int, capacity_factor: Optional[float] = 2.0,
-                           gemm_sms: Optional[int] = None) -> EPPipe:
-    """Collective.  `arena_bytes` is per half-batch context."""
-    import os
-    if gemm_sms is None:
-        gemm_sms = int(os.environ.get("M3_EP_GEMM_SMS", "128"))
-    check(load().m3_set_gemm_sm_limit(int(gemm_sms)), "m3_set_gemm_sm_limit")
-    ctxs = [make_context(group, device, arena_bytes, capacity_factor) for _ in range(2)]
-    with torch.cuda.device(device):
-        streams = [torch.cuda.Stream(device=device) for _ in range(2)]
-    return EPPipe(ctxs, streams, group.rank, group.world)
-
-
-def _cv_squared(v: torch.Tensor) -> torch.Tensor:
-    """noisy_gate_vmoe.py:127-141 on a tiny [E] vector (overlapped mode only: the halves' sums are added first)."""
-    if v.numel() == 1:
-        return v.new_zeros(())
-    v = v.float()
-    return v.var() / (v.mean() ** 2 + 1e-10)
-
-
-class EPPipeMoEFunction(torch.autograd.Function):
-    """EPMoEFunction with the token batch processed as two half-batches on two streams (see EPPipe)."""
-
-    @staticmethod
-    def forward(ctx, x, gate_x, w_gate, task_feat, w1, b1, w2, b2, noise, top_k, noise_stddev, compute_dtype,
-                want_gates, wcache, pipe: EPPipe):
-        ctx.set_materialize_grads(False)
-        if gate_x is not None:
-            raise NotImplementedError("overlapped EP: gate_inp must be the layer input")
-        T, D = x.shape
-        E_loc = w1.shape[0]
-        E_tot = w_gate.shape[1]
-        assert E_tot == E_loc * pipe.world
-        x = x.contiguous()
-        cur = torch.cuda.current_stream()
-        if compute_dtype == torch.bfloat16:
-            w1c, w2c, w1t, w2t = wcache.get_bf16(w1, w2)
-        else:
-            w1c, w2c, w1t, w2t = w1, w2, None, None
-        needs_grad = any(ctx.needs_input_grad)
-        T0 = min(T, ((T + 1) // 2 + 15) // 16 * 16)
-        bounds = [(0, T0), (T0, T)]
-        out = torch.empty(T, D, dtype=x.dtype, device=x.device)
-        sts = []
-        ev_push0 = torch.cuda.Event()
-        for h, (a, b) in enumerate(bounds):
-            s, epc = pipe.streams[h], pipe.ctxs[h]
-            s.wait_stream(cur)
-            with torch.cuda.stream(s):
-                xs = x[a:b]
-                nz = noise[a:b].contiguous() if noise is not None else None
-                st = phase_a_gate(xs, w_gate, top_k, task_feat, nz, noise_stddev, want_gates, E_tot)
-                cnt_all = epc.group.all_gather_counts(st.plan_local.counts)
-                if h == 1:
-                    s.wait_event(ev_push0)          # stagger: my push overlaps the other half's GEMM
-                phase_b_dispatch(epc, st, xs, cnt_all, E_loc, top_k, compute_dtype)
-                if h == 0:
-                    ev_push0.record(s)
-                epc.group.barrier(x.device)
-                phase_c_ffn(epc, st, w1c, b1, w2c, b2, needs_grad)
-                epc.group.barrier(x.device)
-                phase_d_combine(epc, st, b - a, D, top_k, x.dtype, keep_rows=needs_grad, out=out[a:b])
-                if not needs_grad:
-                    epc.group.barrier(x.device)
-                    release_fwd(epc, st)
-            sts.append(st)
-        for s in pipe.streams:
-            cur.wait_stream(s)
-        gs, pls = [st.g for st in sts], [st.plan_local for st in sts]
-
-        def cat(ts):
-            t = torch.cat(ts, 0)
-            for u in ts:
-                u.record_stream(cur)
-            return t
-        score, top_vals, clean, idx = (cat([getattr(g, n) for g in gs]) for n in ("score", "top_vals", "clean_logits", "idx"))
-        noisy = clean.view_as(clean) if noise is None else cat([g.noisy_logits for g in gs])
-        gates = cat([g.gates for g in gs]) if gs[0].gates is not None else x.new_empty(0)
-        for p_ in pls:
-            for t in (p_.importance, p_.load, p_.counts):
-                t.record_stream(cur)
-        importance = pls[0].importance + pls[1].importance
-        load_v = pls[0].load + pls[1].load
-        counts = pls[0].counts + pls[1].counts
-        cv_loss = _cv_squared(importance) + _cv_squared(load_v)
-        if needs_grad:
-            ctx.sts, ctx.pipe, ctx.bounds = sts, pipe, bounds
-            ctx.save_for_backward(x, w_gate, task_feat, w1c, w2c, w1t, w2t, importance)
-            ctx.top_k = top_k
-        ctx.mark_non_differentiable(idx, load_v, counts)
-        return out, score, top_vals, clean, noisy, gates, importance, load_v, idx, counts, cv_loss
-
-    @staticmethod
-    def backward(ctx, d_out, d_score, d_top, d_clean, d_noisy, d_gates, d_imp, _dl, _di, _dc, d_cv):
-        x, w_gate, task_feat, w1c, w2c, w1t, w2t, importance = ctx.saved_tensors
-        pipe, sts, bounds, top_k = ctx.pipe, ctx.sts, ctx.bounds, ctx.top_k
-        T, D = x.shape
-        cur = torch.cuda.current_stream()
-        d_out = torch.zeros_like(x) if d_out is None else d_out.contiguous()
-        if d_gates is not None and d_gates.numel() == 0:
-            d_gates = None
-        dx = torch.empty(T, D, dtype=x.dtype, device=x.device)
-        parts = []
-        ev_push0 = torch.cuda.Event()
-
-        def sl(t, a, b):
-            return None if t is None else t[a:b]
-        for h, (a, b) in enumerate(bounds):
-            s, epc, st = pipe.streams[h], pipe.ctxs[h], sts[h]
-            grp = epc.group
-            s.wait_stream(cur)
-            with torch.cuda.stream(s):
-                grp.barrier(x.device)
-                if h == 1:
-                    s.wait_event(ev_push0)
-                bs = phase_e_combine_bwd(epc, st, d_out[a:b], top_k)
-                if h == 0:
-                    ev_push0.record(s)
-                grp.barrier(x.device)
-                phase_f_ffn_bwd(epc, st, bs, w1c, w2c, w1t, w2t)
-                dscore = bs.dscore if d_score is None else bs.dscore + d_score[a:b]
-                dz, dwg, dtf, _ = ops.gate_bwd(x[a:b], w_gate, st.g.noisy_logits, st.g.idx_full, top_k, task_feat, dscore,
-                                               sl(d_top, a, b), sl(d_gates, a, b), d_imp, sl(d_clean, a, b),
-                                               sl(d_noisy, a, b), want_dx_gate=False, importance=importance,
-                                               dcv_loss=d_cv)
-                grp.barrier(x.device)
-                phase_g_dispatch_bwd(epc, st, bs, b - a, D, top_k, dz, w_gate, x.dtype, out=dx[a:b])
-                grp.barrier(x.device)
-                grads = bs.grads
-                release_bwd(epc, st, bs)
-                release_fwd(epc, st)
-            parts.append((dwg, dtf, *grads))
-        for s in pipe.streams:
-            cur.wait_stream(s)
-        for p_ in parts:
-            for t in p_:
-                if t is not None:
-                    t.record_stream(cur)
-        dwg = parts[0][0] + parts[1][0]
-        dtf = None if parts[0][1] is None or task_feat is None else (parts[0][1] + parts[1][1]).view_as(task_feat).to(task_feat.dtype)
-        dw1, db1, dw2, db2 = (parts[0][i] + parts[1][i] for i in (2, 3, 4, 5))
-        ctx.sts = None
-        return dx, None, dwg, dtf, dw1, db1, dw2, db2, None, None, None, None, None, None, None
-
-
 class _EPRunner:
     def __init__(self, ep: EPContext):
         self.ep = ep
 
     def forward(self, layer, gate, x, gx, tf, noise, nstd, cdt):
-        fn = EPPipeMoEFunction if isinstance(self.ep, EPPipe) else EPMoEFunction
-        return fn.apply(
+        return EPMoEFunction.apply(
             x, gx, gate.w_gate, tf, layer.experts.htoh4.weight, layer.experts.htoh4.bias,
             layer.experts.h4toh.weight, layer.experts.h4toh.bias, noise, layer.top_k, nstd, cdt,
             layer.RETURN_SUMMARIES, layer._wcache, self.ep)

@@ -234,14 +234,35 @@ class ExpertsFunction(torch.autograd.Function):
 
 
 class WeightCache:
-    """bf16 (and transposed bf16) copies of the fp32 expert weights, re-cast only
-    when a parameter changed (optimizer step / load_state_dict bump `_version`)."""
+    """bf16 (and transposed bf16) copies of the fp32 expert weights.
+
+    Eager mode: re-cast only when a parameter changed - optimizer steps and load_state_dict bump `_version`; in-place
+    updates through `param.data` do NOT (`p.data.add_(..)`): call `invalidate()` after those.
+    Under CUDA-graph capture (`torch.cuda.graph`, `make_graphed_callables`): the casts are ALWAYS launched, into the
+    cache's persistent buffers, so that they are part of the captured graph and every replay re-reads the current fp32
+    masters - a graph captured with a warm cache would otherwise keep training on the weights it was captured with."""
 
     def __init__(self):
         self._key = None
         self._val = None
+        self._graph_val = None      # persistent buffers the captured graphs read (never replaced while the cache lives)
+        self._graph_shapes = None
+
+    def invalidate(self):
+        self._key = None
 
     def get_bf16(self, w1, w2):
+        if torch.cuda.is_current_stream_capturing():
+            shapes = (w1.device, tuple(w1.shape), tuple(w2.shape))
+            if self._graph_val is None or self._graph_shapes != shapes:
+                self._graph_val = (torch.empty_like(w1, dtype=torch.bfloat16), torch.empty_like(w2, dtype=torch.bfloat16),
+                                   torch.empty(w1.shape[0], w1.shape[2], w1.shape[1], dtype=torch.bfloat16, device=w1.device),
+                                   torch.empty(w2.shape[0], w2.shape[2], w2.shape[1], dtype=torch.bfloat16, device=w2.device))
+                self._graph_shapes = shapes
+            w1c, w2c, w1t, w2t = self._graph_val
+            ops.cast_weights_bf16(w1.detach(), out=(w1c, w1t))       # captured: every replay re-reads the fp32 masters
+            ops.cast_weights_bf16(w2.detach(), out=(w2c, w2t))
+            return self._graph_val
         key = (w1.data_ptr(), w1._version, w2.data_ptr(), w2._version, w1.device)
         if key != self._key:
             w1c, w1t = ops.cast_weights_bf16(w1.detach(), True, True)

@@ -215,13 +215,18 @@ def combine_bwd(g, yq, plan: Plan, score):
 
 
 # -------------------------------------------------------------------- expert FFN
-def cast_weights_bf16(w, want_plain=True, want_transposed=False):
-    """fp32 [E,R,C] -> bf16 [E,R,C] and/or bf16 transposed [E,C,R]"""
+def cast_weights_bf16(w, want_plain=True, want_transposed=False, out=None):
+    """fp32 [E,R,C] -> bf16 [E,R,C] and/or bf16 transposed [E,C,R]; `out` = (plain, transposed) buffers to overwrite"""
     require_device(w)
     E, R, Cc = w.shape
     w = w.contiguous()
-    o = torch.empty(E, R, Cc, dtype=torch.bfloat16, device=w.device) if want_plain else None
-    ot = torch.empty(E, Cc, R, dtype=torch.bfloat16, device=w.device) if want_transposed else None
+    if out is not None:
+        o, ot = out
+        assert (o is None or (o.shape == (E, R, Cc) and o.dtype == torch.bfloat16 and o.is_contiguous()))
+        assert (ot is None or (ot.shape == (E, Cc, R) and ot.dtype == torch.bfloat16 and ot.is_contiguous()))
+    else:
+        o = torch.empty(E, R, Cc, dtype=torch.bfloat16, device=w.device) if want_plain else None
+        ot = torch.empty(E, Cc, R, dtype=torch.bfloat16, device=w.device) if want_transposed else None
     check(load().m3_cast_weights_bf16(ptr(w), E, R, Cc, ptr(o), ptr(ot), stream_ptr()), "m3_cast_weights_bf16")
     _count("cast_weights")
     return o, ot

@@ -286,3 +286,46 @@ def test_layer_under_make_graphed_callables_is_bit_identical():
         got = step(graphed, xg)
         for a, b in zip(got, want):
             assert torch.equal(a, b)
+
+
+def test_graphed_layer_follows_optimizer_steps():
+    """a graph captured with a warm weight cache must not keep training on the bf16 expert weights it was
+    captured with - the fp32 -> bf16 casts are part of the captured graph, so a replay after optimizer.step() equals the
+    eager layer with the updated weights."""
+    dev = torch.device("cuda:0")
+    fx, case, data = load_fixture("S8_d128h256_g2_s0.pt")
+    layer = build_layer(case, data, "origin", dev, compute_dtype=torch.bfloat16).train()
+    opt = torch.optim.SGD(layer.parameters(), lr=0.5)
+    go = data["grad_out"].to(dev)
+
+    class TaskCall(nn.Module):
+        def __init__(self, layer):
+            super().__init__()
+            self.layer = layer
+
+        def forward(self, x):
+            return self.layer(x, task_id=1)
+
+    graphed = torch.cuda.make_graphed_callables(TaskCall(layer), (data["x"].to(dev).requires_grad_(True),),
+                                                allow_unused_input=True)
+    for it in range(3):
+        layer.zero_grad(set_to_none=True)
+        xg = data["x"].to(dev).requires_grad_(True)
+        out_g = graphed(xg)
+        out_g.backward(go)
+        got = (out_g.detach().clone(), xg.grad.clone(), layer.experts.htoh4.weight.grad.clone())
+        layer.zero_grad(set_to_none=True)
+        xe = data["x"].to(dev).requires_grad_(True)
+        out_e = layer(xe, task_id=1)
+        out_e.backward(go)
+        want = (out_e.detach(), xe.grad, layer.experts.htoh4.weight.grad)
+        for a, b in zip(got, want):
+            assert torch.equal(a, b), it
+        opt.step()                                   # changes the fp32 masters (and bumps their version)
+    # in-place update through .data does not bump the version: invalidate() is the documented way
+    w = layer.experts.htoh4.weight
+    before = layer(data["x"].to(dev), task_id=1).detach().clone()
+    w.data.mul_(1.5)
+    layer._wcache.invalidate()
+    after = layer(data["x"].to(dev), task_id=1).detach()
+    assert not torch.equal(before, after)

@@ -40,10 +40,7 @@ def main():
         for n in ("htoh4", "h4toh"):
             getattr(shard.experts, n).weight.copy_(getattr(full.experts, n).weight[rank * E_loc:(rank + 1) * E_loc])
             getattr(shard.experts, n).bias.copy_(getattr(full.experts, n).bias[rank * E_loc:(rank + 1) * E_loc])
-    if "pipe" in sys.argv:      # overlapped mode: two half-batches on two streams
-        ctx = ep.make_pipelined_context(ep.TorchDistGroup(), dev, arena_bytes=1 << 29, capacity_factor=None)
-    else:
-        ctx = ep.make_context(ep.TorchDistGroup(), dev, arena_bytes=1 << 30, capacity_factor=None)
+    ctx = ep.make_context(ep.TorchDistGroup(), dev, arena_bytes=1 << 30, capacity_factor=None)
     ep.attach(shard, ctx)
     full.train(); shard.train()
     gen = torch.Generator(device=dev).manual_seed(100 + rank)     # different tokens per rank
