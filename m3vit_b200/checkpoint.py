@@ -14,6 +14,11 @@ job of W ranks owns the contiguous slice [r*E_loc, (r+1)*E_loc).  The reference
 
 These helpers reproduce that format so real M3ViT checkpoints load into the B200 layer at any W.
 Pure host code (torch CPU tensors); no CUDA involved.
+
+Parity: `oracle/make_ckpt_golden.py` executes the reference's own functions (utils/moe_utils.py:34-198 under the
+fmoe shim, pretrain/utils/moe_checkpoint.py:57-212 as is, `save_moe_model_to_dir` under a 2-rank gloo group) on a
+fixed set of state dicts and records what they return / raise in tests/golden/ckpt_reference.pt;
+tests/test_checkpoint.py holds every helper here to those records.
 """
 from __future__ import annotations
 
@@ -71,11 +76,17 @@ def merge_expert_shards(shards: List[Dict[str, torch.Tensor]]) -> "OrderedDict":
 
 def expert_format(checkpoint: dict, state_dict, local_experts: int, world_size: int) -> str:
     """Classify a single-file checkpoint as "global" (usable at any W) or raise ValueError for a
-    rank-local one, following the reference's rules (utils/moe_utils.py:34-106)."""
-    dim0 = first_expert_dim0(state_dict)
-    if dim0 is None or int(world_size) <= 1:
+    rank-local one, following the reference's rules in their order
+    (validate_single_file_moe_checkpoint_or_raise, utils/moe_utils.py:34-106): world size 1 or no expert tensors ->
+    fine; meta.expert_format; the checkpoint's own args (world_size x dim0 == moe_experts -> rank-local); dim0 against
+    local_experts x world_size."""
+    if int(world_size) <= 1:
         return "global"
-    expected_global = int(local_experts) * int(world_size)
+    dim0 = first_expert_dim0(state_dict)
+    if dim0 is None:
+        return "global"
+    local_experts, world_size = int(local_experts), int(world_size)
+    expected_global = local_experts * world_size
     meta = checkpoint.get("meta", {}) if isinstance(checkpoint, dict) else {}
     fmt = meta.get("expert_format") if isinstance(meta, dict) else None
     if fmt == "global":
@@ -84,10 +95,87 @@ def expert_format(checkpoint: dict, state_dict, local_experts: int, world_size: 
         return "global"
     if fmt == "local":
         raise ValueError("checkpoint holds rank-local experts only; merge the shard directory first")
+    args = checkpoint.get("args", {}) if isinstance(checkpoint, dict) else {}
+    ck_world = args.get("world_size") if isinstance(args, dict) else None
+    ck_global = args.get("moe_experts") if isinstance(args, dict) else None
+    if ck_world is not None and ck_global is not None:
+        if int(ck_world) > 1 and dim0 * int(ck_world) == int(ck_global):
+            raise ValueError(f"single-file checkpoint holds rank-local experts only (dim0={dim0}, written by "
+                             f"{int(ck_world)} ranks for {int(ck_global)} experts); merge the shard directory first")
     if dim0 == expected_global:
         return "global"
+    if dim0 == local_experts:
+        raise ValueError(f"single-file checkpoint holds rank-local experts only (dim0={dim0} == local_experts); "
+                         "merge the shard directory first")
     raise ValueError(f"cannot verify global expert format: expert dim0={dim0}, expected {expected_global} "
                      f"(local_experts={local_experts}, world_size={world_size})")
+
+
+def infer_expert_format(checkpoint, state_dict, expected_global_experts=None, expected_world_size=None) -> str:
+    """'global' | 'local' | 'dense' | 'unknown' for one state dict (pretrain/utils/moe_checkpoint.py:137-180): the meta tag
+    wins, a state dict without expert tensors is dense, otherwise dim 0 is held against the expected (or the
+    checkpoint's own args.moe_experts / args.world_size) expert count."""
+    if isinstance(checkpoint, dict):
+        meta = checkpoint.get("meta", {})
+        if isinstance(meta, dict) and meta.get("expert_format") in ("global", "local"):
+            return meta["expert_format"]
+    dim0 = None
+    for k, v in state_dict.items():                      # NOT prefix-stripped here, like the reference
+        if is_expert_key(k) and torch.is_tensor(v):
+            dim0 = int(v.shape[0])
+            break
+    if dim0 is None:
+        return "dense"
+    if expected_global_experts is None and isinstance(checkpoint, dict):
+        args = checkpoint.get("args", {})
+        if isinstance(args, dict):
+            expected_global_experts = args.get("moe_experts")
+            if expected_world_size is None:
+                expected_world_size = args.get("world_size")
+    if expected_global_experts is not None:
+        g = int(expected_global_experts)
+        if dim0 == g:
+            return "global"
+        if expected_world_size is not None and int(expected_world_size) > 1 and dim0 * int(expected_world_size) == g:
+            return "local"
+    return "unknown"
+
+
+def to_backbone_state_dict(state_dict):
+    """wrapper / DDP key space -> backbone key space of the multi-task loader (pretrain/utils/moe_checkpoint.py:23-47):
+    `module.` and a leading `encoder.` are stripped, wrapper-only top-level `head.*` / `norm.*` are dropped.
+    Returns (state, dropped keys)."""
+    out, dropped = OrderedDict(), []
+    for k, v in state_dict.items():
+        if k.startswith("module."):
+            k = k[len("module."):]
+        if k.startswith("encoder."):
+            out[k[len("encoder."):]] = v
+        elif k.startswith("head.") or k.startswith("norm."):
+            dropped.append(k)
+        else:
+            out[k] = v
+    return out, dropped
+
+
+def build_meta(state_dict, source, world_size: int = 1, moe_experts_global=None, moe_experts_local=None) -> dict:
+    """meta block of a global-expert checkpoint (pretrain/utils/moe_checkpoint.py:82-113)"""
+    dim0 = None
+    for k, v in state_dict.items():
+        if is_expert_key(k) and torch.is_tensor(v):
+            dim0 = int(v.shape[0])
+            break
+    if moe_experts_global is None and dim0 is not None:
+        moe_experts_global = dim0
+    if moe_experts_local is None:
+        if dim0 is None:
+            moe_experts_local = 0
+        elif world_size > 0 and dim0 % world_size == 0:
+            moe_experts_local = dim0 // world_size
+        else:
+            moe_experts_local = dim0
+    return {"expert_format": "global", "moe_experts_global": int(moe_experts_global) if moe_experts_global is not None else 0,
+            "moe_experts_local": int(moe_experts_local), "world_size": int(world_size), "source": str(source)}
 
 
 def save_ep_shard(state: dict, dirname: str, rank: int) -> str:
@@ -99,6 +187,38 @@ def save_ep_shard(state: dict, dirname: str, rank: int) -> str:
     path = os.path.join(dirname, f"{rank}.pth")
     torch.save(state, path)
     return path
+
+
+def _state_of(ckpt):
+    if isinstance(ckpt, dict) and "state_dict" in ckpt:
+        return ckpt["state_dict"]
+    if isinstance(ckpt, dict) and "model" in ckpt:
+        return ckpt["model"]
+    return ckpt
+
+
+def merge_shard_dir(dirname: str, map_location="cpu"):
+    """`{0,1,..}.pth` of a train_fastmoe-style shard directory -> (rank-0 checkpoint, merged global state dict, number
+    of shards), as pretrain/utils/moe_checkpoint.py:196-225: files are taken in numeric rank order, rank 0 must exist,
+    expert tensors are concatenated on dim 0, other keys a later shard brings are added."""
+    files = sorted((int(os.path.splitext(n)[0]), os.path.join(dirname, n)) for n in os.listdir(dirname)
+                   if n.endswith(".pth") and os.path.splitext(n)[0].isdigit())
+    if not files:
+        raise ValueError(f"No rank shard '*.pth' files found in: {dirname}")
+    if files[0][0] != 0:
+        raise ValueError("Shard directory must contain rank-0 checkpoint file '0.pth'")
+    base = torch.load(files[0][1], map_location=map_location, weights_only=False)
+    if not isinstance(base, dict):
+        raise ValueError(f"Checkpoint at {files[0][1]} must be a dict, got {type(base)}")
+    merged = OrderedDict(_state_of(base))
+    for _, path in files[1:]:
+        shard = _state_of(torch.load(path, map_location=map_location, weights_only=False))
+        for k, v in shard.items():
+            if is_expert_key(k):
+                merged[k] = torch.cat([merged[k], v], dim=0) if k in merged else v
+            elif k not in merged:
+                merged[k] = v
+    return base, merged, len(files)
 
 
 def load_ep_dir(dirname: str, world_size: int, map_location="cpu") -> dict:
