@@ -3,7 +3,8 @@
 Public surface (mirrors the reference's `models/moe` names):
 
     FMoETransformerMLP, FMoETransformerMLPCkpt   m3vit_b200.custom_moe_layer
-    NoisyGate_VMoE                               m3vit_b200.noisy_gate_vmoe
+    NoisyGate_VMoE, TokenNoisyGate_VMoE          m3vit_b200.noisy_gate_vmoe
+    TokenFMoETransformerMLP                      m3vit_b200.custom_moe_layer (token-MoE experts-only entry)
     build_moe_mlp, MoEBlockMlp                   m3vit_b200.block
     ops (one wrapper per C-ABI entry point)      m3vit_b200.ops
 
@@ -13,8 +14,8 @@ calling anything does, and fails loudly otherwise.
 """
 from .custom_moe_layer import (FMoETransformerMLP, FMoETransformerMLPCkpt, TokenFMoETransformerMLP,  # noqa: F401
                                FMoELinear)
-from .noisy_gate_vmoe import NoisyGate_VMoE, cv_squared  # noqa: F401
+from .noisy_gate_vmoe import NoisyGate_VMoE, TokenNoisyGate_VMoE, cv_squared  # noqa: F401
 from .block import build_moe_mlp, MoEBlockMlp, collect_noisy_gating_loss  # noqa: F401
 
-__all__ = ["FMoETransformerMLP", "FMoETransformerMLPCkpt", "TokenFMoETransformerMLP", "FMoELinear", "NoisyGate_VMoE", "cv_squared",
+__all__ = ["FMoETransformerMLP", "FMoETransformerMLPCkpt", "TokenFMoETransformerMLP", "FMoELinear", "NoisyGate_VMoE", "TokenNoisyGate_VMoE", "cv_squared",
            "build_moe_mlp", "MoEBlockMlp", "collect_noisy_gating_loss"]

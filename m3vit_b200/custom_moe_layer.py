@@ -274,6 +274,8 @@ class TokenFMoETransformerMLP(nn.Module):
         if self.drop_p > 0 and self.training:
             raise NotImplementedError("expert dropout > 0 in training is not implemented")
         shape = inp.shape
+        if inp.numel() == 0:          # an empty token subset (the token Block routes masked subsets, token/vision_transformer_moe.py:753)
+            return inp.clone()
         x = inp.reshape(-1, self.d_model)
         idx = gate_top_k_idx.reshape(-1, self.top_k)
         score = gate_score.reshape(-1, self.top_k)

@@ -184,8 +184,15 @@ class NoisyGate_VMoE(BaseGate):
         inp2 = inp.reshape(-1, shape_input[-1])
         T = inp2.shape[0]
         noise = self.draw_noise(T, inp2.device)
+        w_gate = self.w_gate
+        pad = (-inp2.shape[1]) % 32
+        if pad:
+            # the kernel walks the router input in 32-column chunks; a width like d_model + task embedding (token-MoE,
+            # 384 + 64 is fine, 64 + 16 is not) is zero-padded - trailing +0*0 terms leave every logit bit-identical
+            inp2 = torch.nn.functional.pad(inp2, (0, pad))
+            w_gate = torch.nn.functional.pad(w_gate, (0, 0, 0, pad))
         (score, top_vals, clean, noisy, gates, importance, cv_loss, load, idx, *_plan) = GateFunction.apply(
-            inp2, self.w_gate, None, noise, self.top_k, float(self.noise_stddev()), self.return_summaries)
+            inp2, w_gate, None, noise, self.top_k, float(self.noise_stddev()), self.return_summaries)
         self._record(clean, noisy, importance, load, top_vals, cv_loss)
         self.last_plan = _plan
         top_k_indices = idx.reshape(other_dim + [self.top_k])
@@ -193,3 +200,30 @@ class NoisyGate_VMoE(BaseGate):
         if self.return_summaries:
             return (top_k_indices, top_k_gates), clean, noisy, self.noise_stddev(), top_vals, gates
         return top_k_indices, top_k_gates
+
+
+class TokenNoisyGate_VMoE(NoisyGate_VMoE):
+    """Router of the reference's token-MoE variant (/root/reference/models/moe/token/noisy_gate_vmoe.py:13-113): same
+    arithmetic as NoisyGate_VMoE (softmax over all experts, top-(K+1), the first K probabilities un-renormalised) but it
+    ALWAYS returns `((top_k_indices, top_k_gates), clean_logits, noisy_logits, noise_stddev, top_logits, gates)` (:94-101),
+    never sets `self.loss` (the token Block computes the balance loss itself from these, token/vision_transformer_moe.py
+    :268-300) and records no activation.  The token Block calls it on a VARIABLE subset of the tokens (:753-768); any
+    number of rows, including zero, is accepted."""
+
+    def __init__(self, d_model, num_expert, world_size, top_k=2, noise_std=1, no_noise=False, num_experts_pertask=-1,
+                 num_tasks=-1):
+        super().__init__(d_model, num_expert, world_size, top_k=top_k, noise_std=noise_std, no_noise=no_noise,
+                         num_experts_pertask=num_experts_pertask, num_tasks=num_tasks, return_summaries=True)
+
+    def _record(self, *args, **kwargs):      # no loss, no activation (token/noisy_gate_vmoe.py:86-88)
+        pass
+
+    def forward(self, inp, task_id=None, sem=None):
+        if inp.numel() == 0:                 # an empty subset: nothing to route
+            other = list(inp.shape[:-1])
+            E, K1 = self.tot_expert, min(self.top_k + 1, self.tot_expert)
+            z = inp.new_zeros(0, E, dtype=torch.float32)
+            return ((torch.zeros(other + [self.top_k], dtype=torch.int64, device=inp.device),
+                     inp.new_zeros(other + [self.top_k], dtype=torch.float32)), z, z, self.noise_stddev(),
+                    inp.new_zeros(0, K1, dtype=torch.float32), z)
+        return super().forward(inp, task_id=task_id, sem=sem)

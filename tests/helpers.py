@@ -28,7 +28,7 @@ def load_fixture(fname):
 
 def all_fixtures(prefix=""):
     """MoE-layer fixtures (S*, C*); the Block-level ones (B*) are listed by block_fixtures()."""
-    return sorted(f for f in os.listdir(GOLDEN) if f.endswith(".pt") and f.startswith(prefix) and not f.startswith("B"))
+    return sorted(f for f in os.listdir(GOLDEN) if f.endswith(".pt") and f.startswith(prefix) and f[0] in "SC")
 
 
 def block_fixtures():
