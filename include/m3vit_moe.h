@@ -78,6 +78,15 @@ int m3_gate_fwd(const void* x, int x_dtype, int64_t ldx, const float* task_feat,
                 int64_t* idx, int32_t* idx_full, float* score, float* top_vals, float* clean_logits,
                 float* noisy_logits, float* gates, float* imp_partial, int32_t* load_partial,
                 m3_stream_t stream);
+/* m3_gate_fwd with the router noise drawn IN the kernel (noisy_gate_vmoe.py:226 draws it with torch.randn_like):
+ * rng_state = {uint64 seed, uint64 call counter} in device memory, 16-byte aligned (csrc/philox.cuh: Philox4x32-7 +
+ * Box-Muller, four normals per lane); the [T, E] noise tensor is never materialised.  Not torch's stream: statistical
+ * parity.  noisy_logits is required. */
+int m3_gate_fwd_rng(const void* x, int x_dtype, int64_t ldx, const float* task_feat,
+                    const float* w_gate, const void* rng_state, float noise_stddev, int T, int D, int Dt,
+                    int E, int K, int64_t* idx, int32_t* idx_full, float* score, float* top_vals,
+                    float* clean_logits, float* noisy_logits, float* gates, float* imp_partial,
+                    int32_t* load_partial, m3_stream_t stream);
 
 /* Router backward (autograd through noisy_gate_vmoe.py:179-265): softmax
  * Jacobian over all E from the gradients of every differentiable gate output,
@@ -195,6 +204,24 @@ int m3_ffn_bwd(int dtype, const void* xq, const void* saved, const void* dyq, co
                const void* w1, const void* w2, const void* w1t, const void* w2t, void* dxq,
                float* dw1, float* db1, float* dw2, float* db2, void* workspace,
                size_t workspace_bytes, m3_stream_t stream);
+
+/* The same pair with EXPERT DROPOUT behind the GELU: the reference's experts apply nn.Sequential(GELU, Dropout(p))
+ * (models/moe/origin/vision_transformer_moe.py:248-251; drop_rate 0.1 in configs/nyud/vit_moe/*drop0.1*.yml), i.e.
+ * h = m * gelu(z), m = 0 with probability p and 1/(1-p) otherwise.  The mask is a counter-based function (Philox4x32-7,
+ * csrc/philox.cuh) of the element's queue coordinates and of `rng_state` = {uint64 seed, uint64 call counter} in DEVICE
+ * memory (16-byte aligned; read by the kernels, so that a caller can bump the counter with a stream-ordered op and stay
+ * CUDA-graph capturable).  The backward call must be given the rng_state VALUES of its forward call (keep a copy).
+ * bf16: the saved planes carry the mask, the backward does not regenerate it; fp32: regenerated.  Not torch's random
+ * stream: parity with the reference is statistical.  drop_p = 0 is m3_ffn_fwd / m3_ffn_bwd; saved must not be NULL. */
+int m3_ffn_fwd_dropout(int dtype, const void* xq, const int32_t* offsets, const int32_t* tile_expert,
+                       int cap_rows, int E, int D, int H, const void* w1, const float* b1, const void* w2,
+                       const float* b2, void* saved, void* yq, void* workspace, size_t workspace_bytes,
+                       float drop_p, const void* rng_state, m3_stream_t stream);
+int m3_ffn_bwd_dropout(int dtype, const void* xq, const void* saved, const void* dyq, const int32_t* counts,
+                       const int32_t* offsets, const int32_t* tile_expert, int cap_rows, int E, int D, int H,
+                       const void* w1, const void* w2, const void* w1t, const void* w2t, void* dxq,
+                       float* dw1, float* db1, float* dw2, float* db2, void* workspace,
+                       size_t workspace_bytes, float drop_p, const void* rng_state, m3_stream_t stream);
 
 /* fp32 master weights [E,R,C] -> bf16 copy [E,R,C] and (optional) bf16 transpose [E,C,R]. */
 int m3_cast_weights_bf16(const float* w, int E, int R, int C, void* w_bf16, void* wt_bf16,

@@ -30,6 +30,7 @@ SIGNATURES = {
     "m3_check_device": (_i, []),
     "m3_gate_num_partials": (_i, [_i, _i]),
     "m3_gate_fwd": (_i, [_p, _i, _i64, _p, _p, _p, _f, _i, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
+    "m3_gate_fwd_rng": (_i, [_p, _i, _i64, _p, _p, _p, _f, _i, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
     "m3_gate_bwd_workspace_bytes": (_sz, [_i, _i, _i, _i]),
     "m3_gate_bwd": (_i, [_p, _i, _i64, _p, _p, _p, _p, _i, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p,
                          _p, _p, _p, _sz, _p]),
@@ -47,7 +48,10 @@ SIGNATURES = {
     "m3_set_gemm_sm_limit": (_i, [_i]),
     "m3_set_knob": (_i, [_i, _i]),
     "m3_ffn_fwd": (_i, [_i, _p, _p, _p, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _sz, _p]),
+    "m3_ffn_fwd_dropout": (_i, [_i, _p, _p, _p, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _sz, _f, _p, _p]),
     "m3_ffn_bwd": (_i, [_i, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _sz, _p]),
+    "m3_ffn_bwd_dropout": (_i, [_i, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _sz, _f,
+                                _p, _p]),
     "m3_cast_weights_bf16": (_i, [_p, _i, _i, _i, _p, _p, _p]),
     "m3_ep_plan": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p]),
     "m3_ep_dispatch_fwd": (_i, [_p, _i, _p, _p, _i, _i, _i, _p, _i, _p]),

@@ -8,18 +8,18 @@
 // implemented in ffn_f32.cu / ffn_bf16.cu
 int m3_ffn_fwd_f32(const float* xq, const int32_t* offsets, const int32_t* tile_expert, int cap_rows, int E, int D,
                    int H, const float* w1, const float* b1, const float* w2, const float* b2, float* hpre,
-                   float* yq, void* workspace, size_t workspace_bytes, cudaStream_t st);
+                   float* yq, void* workspace, size_t workspace_bytes, float drop_p, const void* rng, cudaStream_t st);
 int m3_ffn_bwd_f32(const float* xq, const float* hpre, const float* dyq, const int32_t* counts,
                    const int32_t* offsets, const int32_t* tile_expert, int cap_rows, int E, int D, int H,
                    const float* w1, const float* w2, float* dxq, float* dw1, float* db1, float* dw2, float* db2,
-                   void* workspace, size_t workspace_bytes, cudaStream_t st);
+                   void* workspace, size_t workspace_bytes, float drop_p, const void* rng, cudaStream_t st);
 size_t m3_ffn_bf16_workspace_bytes(int cap_rows, int D, int H, int E, int backward);
 size_t m3_ffn_bf16_saved_bytes(int cap_rows, int D, int H);
 int m3_ffn_bf16_chain_mode(int D, int H);
 int m3_ffn_bf16_set_sm_limit(int sms);
 int m3_ffn_fwd_bf16(const void* xq, const int32_t* offsets, const int32_t* tile_expert, int cap_rows, int E, int D,
                     int H, const void* w1, const float* b1, const void* w2, const float* b2, void* hpre, void* yq,
-                    void* workspace, size_t workspace_bytes, cudaStream_t st);
+                    void* workspace, size_t workspace_bytes, float drop_p, const void* rng, cudaStream_t st);
 int m3_ffn_bwd_bf16(const void* xq, const void* hpre, const void* dyq, const int32_t* counts,
                     const int32_t* offsets, const int32_t* tile_expert, int cap_rows, int E, int D, int H,
                     const void* w1, const void* w2, const void* w1t, const void* w2t, void* dxq, float* dw1,
@@ -92,9 +92,12 @@ extern "C" int m3_ffn_uses_chain(int dtype, int D, int H) {
   return dtype == M3_BF16 ? m3_ffn_bf16_chain_mode(D, H) : 0;
 }
 
-extern "C" int m3_ffn_fwd(int dtype, const void* xq, const int32_t* offsets, const int32_t* tile_expert, int cap_rows,
-                          int E, int D, int H, const void* w1, const float* b1, const void* w2, const float* b2,
-                          void* hpre, void* yq, void* workspace, size_t workspace_bytes, m3_stream_t stream) {
+static int ffn_fwd_impl(int dtype, const void* xq, const int32_t* offsets, const int32_t* tile_expert, int cap_rows,
+                        int E, int D, int H, const void* w1, const float* b1, const void* w2, const float* b2,
+                        void* hpre, void* yq, void* workspace, size_t workspace_bytes, float drop_p, const void* rng,
+                        m3_stream_t stream) {
+  M3_CHECK_ARG(drop_p >= 0.f && drop_p < 1.f);
+  if (rng) M3_CHECK_ALIGN16(rng);
   M3_CHECK_ARG(xq && offsets && tile_expert && w1 && b1 && w2 && b2 && yq);
   M3_CHECK_ARG(cap_rows >= 0 && E >= 1 && D > 0 && H > 0);
   M3_CHECK_SHAPE(cap_rows % M3_PAD_ROWS == 0);
@@ -106,18 +109,34 @@ extern "C" int m3_ffn_fwd(int dtype, const void* xq, const int32_t* offsets, con
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (dtype == M3_F32)
     return m3_ffn_fwd_f32((const float*)xq, offsets, tile_expert, cap_rows, E, D, H, (const float*)w1, b1,
-                          (const float*)w2, b2, (float*)hpre, (float*)yq, workspace, workspace_bytes, st);
+                          (const float*)w2, b2, (float*)hpre, (float*)yq, workspace, workspace_bytes, drop_p, rng, st);
   if (dtype == M3_BF16)
     return m3_ffn_fwd_bf16(xq, offsets, tile_expert, cap_rows, E, D, H, w1, b1, w2, b2, hpre, yq, workspace,
-                           workspace_bytes, st);
+                           workspace_bytes, drop_p, rng, st);
   return M3_ERR_UNSUPPORTED;
 }
 
-extern "C" int m3_ffn_bwd(int dtype, const void* xq, const void* hpre, const void* dyq, const int32_t* counts,
-                          const int32_t* offsets, const int32_t* tile_expert, int cap_rows, int E, int D, int H,
-                          const void* w1, const void* w2, const void* w1t, const void* w2t, void* dxq, float* dw1,
-                          float* db1, float* dw2, float* db2, void* workspace, size_t workspace_bytes,
-                          m3_stream_t stream) {
+extern "C" int m3_ffn_fwd(int dtype, const void* xq, const int32_t* offsets, const int32_t* tile_expert, int cap_rows,
+                          int E, int D, int H, const void* w1, const float* b1, const void* w2, const float* b2,
+                          void* hpre, void* yq, void* workspace, size_t workspace_bytes, m3_stream_t stream) {
+  return ffn_fwd_impl(dtype, xq, offsets, tile_expert, cap_rows, E, D, H, w1, b1, w2, b2, hpre, yq, workspace,
+                      workspace_bytes, 0.f, nullptr, stream);
+}
+
+extern "C" int m3_ffn_fwd_dropout(int dtype, const void* xq, const int32_t* offsets, const int32_t* tile_expert,
+                                  int cap_rows, int E, int D, int H, const void* w1, const float* b1, const void* w2,
+                                  const float* b2, void* saved, void* yq, void* workspace, size_t workspace_bytes,
+                                  float drop_p, const void* rng_state, m3_stream_t stream) {
+  return ffn_fwd_impl(dtype, xq, offsets, tile_expert, cap_rows, E, D, H, w1, b1, w2, b2, saved, yq, workspace,
+                      workspace_bytes, drop_p, rng_state, stream);
+}
+
+static int ffn_bwd_impl(int dtype, const void* xq, const void* hpre, const void* dyq, const int32_t* counts,
+                        const int32_t* offsets, const int32_t* tile_expert, int cap_rows, int E, int D, int H,
+                        const void* w1, const void* w2, const void* w1t, const void* w2t, void* dxq, float* dw1,
+                        float* db1, float* dw2, float* db2, void* workspace, size_t workspace_bytes, float drop_p,
+                        const void* rng, m3_stream_t stream) {
+  M3_CHECK_ARG(drop_p >= 0.f && drop_p < 1.f);
   M3_CHECK_ARG(xq && hpre && dyq && counts && offsets && tile_expert && w1 && w2 && dxq && dw1 && db1 && dw2 && db2);
   M3_CHECK_ARG(cap_rows >= 0 && E >= 1 && D > 0 && H > 0 && workspace);
   M3_CHECK_SHAPE(cap_rows % M3_PAD_ROWS == 0);
@@ -128,13 +147,32 @@ extern "C" int m3_ffn_bwd(int dtype, const void* xq, const void* hpre, const voi
   if (dtype == M3_F32)
     return m3_ffn_bwd_f32((const float*)xq, (const float*)hpre, (const float*)dyq, counts, offsets, tile_expert,
                           cap_rows, E, D, H, (const float*)w1, (const float*)w2, (float*)dxq, dw1, db1, dw2, db2,
-                          workspace, workspace_bytes, st);
+                          workspace, workspace_bytes, drop_p, rng, st);
   if (dtype == M3_BF16) {
     M3_CHECK_ARG(w1t && w2t);
+    // bf16: the saved planes already carry the forward's keep-scale (h = m gelu(z), m gelu'(z)): nothing to regenerate
     return m3_ffn_bwd_bf16(xq, hpre, dyq, counts, offsets, tile_expert, cap_rows, E, D, H, w1, w2, w1t, w2t, dxq,
                            dw1, db1, dw2, db2, workspace, workspace_bytes, st);
   }
   return M3_ERR_UNSUPPORTED;
+}
+
+extern "C" int m3_ffn_bwd(int dtype, const void* xq, const void* hpre, const void* dyq, const int32_t* counts,
+                          const int32_t* offsets, const int32_t* tile_expert, int cap_rows, int E, int D, int H,
+                          const void* w1, const void* w2, const void* w1t, const void* w2t, void* dxq, float* dw1,
+                          float* db1, float* dw2, float* db2, void* workspace, size_t workspace_bytes,
+                          m3_stream_t stream) {
+  return ffn_bwd_impl(dtype, xq, hpre, dyq, counts, offsets, tile_expert, cap_rows, E, D, H, w1, w2, w1t, w2t, dxq, dw1,
+                      db1, dw2, db2, workspace, workspace_bytes, 0.f, nullptr, stream);
+}
+
+extern "C" int m3_ffn_bwd_dropout(int dtype, const void* xq, const void* saved, const void* dyq, const int32_t* counts,
+                                  const int32_t* offsets, const int32_t* tile_expert, int cap_rows, int E, int D, int H,
+                                  const void* w1, const void* w2, const void* w1t, const void* w2t, void* dxq,
+                                  float* dw1, float* db1, float* dw2, float* db2, void* workspace,
+                                  size_t workspace_bytes, float drop_p, const void* rng_state, m3_stream_t stream) {
+  return ffn_bwd_impl(dtype, xq, saved, dyq, counts, offsets, tile_expert, cap_rows, E, D, H, w1, w2, w1t, w2t, dxq, dw1,
+                      db1, dw2, db2, workspace, workspace_bytes, drop_p, rng_state, stream);
 }
 
 

@@ -23,6 +23,7 @@
 #include <cstdlib>
 #include <mutex>
 
+#include "philox.cuh"
 #include "tc_common.cuh"
 
 namespace m3 {
@@ -51,6 +52,11 @@ struct GGParams {
   int dbg;                     // M3_KNOB_DEBUG (measurement only, results are garbage): 1 = no MMAs, 2 = no TMA loads
   unsigned long long* trace;   // m3_debug_trace_buffer
   int trace_cap;
+  // EPI_FC1, training: expert dropout behind the GELU (philox.cuh).  Both saved planes carry the keep-scale, h = m gelu(z)
+  // and m gelu'(z) with m in {0, 1/(1-p)}, so the backward pass needs neither the mask nor the random stream again.
+  uint32_t drop_thr;           // p * 2^32 (0 = no dropout)
+  float drop_inv_keep;         // 1 / (1 - p)
+  const RngState* rng;
 };
 
 template <int BN, int EPI, int NCTA, int EW, int CWP>
@@ -346,6 +352,17 @@ gg_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
             for (int c2 = 0; c2 < CW / 16; ++c2) {      // 8 pairs = two 16-byte chunks per batch
               f32x2 gl[8], gr[8];
               gelu_fast_grad2_batch<8>(&w2[8 * c2], gl, gr);
+              if (p.drop_thr != 0u) {
+                const RngState rs = *p.rng;
+#pragma unroll
+                for (int q4 = 0; q4 < 4; ++q4) {
+                  float sc[4];
+                  dropout_scale4(rs, (uint32_t)(row0 + lane), (uint32_t)((col + 16 * c2) / 4 + q4), p.drop_thr, p.drop_inv_keep, sc);
+                  const f32x2 s01 = pk2(sc[0], sc[1]), s23 = pk2(sc[2], sc[3]);
+                  gl[2 * q4] = mul2(gl[2 * q4], s01); gl[2 * q4 + 1] = mul2(gl[2 * q4 + 1], s23);
+                  gr[2 * q4] = mul2(gr[2 * q4], s01); gr[2 * q4 + 1] = mul2(gr[2 * q4 + 1], s23);
+                }
+              }
 #pragma unroll
               for (int i = 0; i < 8; ++i) w2[8 * c2 + i] = gl[i];
               sts128(box + box_off<CW>(lane, 2 * c2),
@@ -818,7 +835,8 @@ size_t m3_ffn_bf16_workspace_bytes(int cap_rows, int D, int H, int E, int backwa
 
 int m3_ffn_fwd_bf16(const void* xq, const int32_t* offsets, const int32_t* tile_expert, int cap_rows, int E, int D,
                     int H, const void* w1, const float* b1, const void* w2, const float* b2, void* saved, void* yq,
-                    void* workspace, size_t workspace_bytes, cudaStream_t st) {
+                    void* workspace, size_t workspace_bytes, float drop_p, const void* rng, cudaStream_t st) {
+  if (drop_p > 0.f && (saved == nullptr || rng == nullptr)) return M3_ERR_ARG;     // dropout is a training-time op
   if (workspace == nullptr || workspace_bytes < m3_ffn_bf16_workspace_bytes(cap_rows, D, H, E, 0)) return M3_ERR_WORKSPACE;
   g_trace_launch_idx = 0;
   if (saved == nullptr && chain_inference(D, H))
@@ -830,10 +848,15 @@ int m3_ffn_fwd_bf16(const void* xq, const int32_t* offsets, const int32_t* tile_
   p.offsets = offsets; p.tile_expert = tile_expert; p.E = E;
   // fc1: h = gelu(xq W1^T + b1); gelu'(.) saved for backward
   p.N = H; p.Kd = D; p.bias = b1; p.save_out2 = saved != nullptr;
+  if (drop_p > 0.f) {
+    p.drop_thr = dropout_threshold(drop_p);
+    p.drop_inv_keep = 1.0f / (1.0f - drop_p);
+    p.rng = static_cast<const RngState*>(rng);
+  }
   int rc = launch_gg<EPI_FC1>(xq, w1, h, gp, nullptr, p, cap_rows, st);
   if (rc) return rc;
   // fc2: yq = h W2^T + b2
-  p.N = D; p.Kd = H; p.bias = b2; p.save_out2 = 0;
+  p.N = D; p.Kd = H; p.bias = b2; p.save_out2 = 0; p.drop_thr = 0u;
   return launch_gg<EPI_BIAS>(h, w2, yq, nullptr, nullptr, p, cap_rows, st);
 }
 

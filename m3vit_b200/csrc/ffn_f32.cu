@@ -10,6 +10,7 @@
 //
 // 64x64x16 tiles, 256 threads, 4x4 register tile, sequential-k fp32 FMA.
 #include "common.cuh"
+#include "philox.cuh"
 
 namespace m3 {
 
@@ -31,6 +32,12 @@ struct SgemmParams {
   int pad;
   int M, N, Kdim;      // rows-grouped: M unused;  TN: M x N output, K = rows of expert
   int E;
+  // expert dropout behind the GELU (philox.cuh): the keep-scale m(row, col) in {0, 1/(1-p)} is a pure function of the
+  // element's queue coordinates, regenerated wherever gelu(z) or gelu'(z) is formed (fc1 epilogue, dgelu epilogue, the
+  // B operand of dW2) - only z is stored
+  uint32_t drop_thr;   // p * 2^32 (0 = no dropout)
+  float drop_inv_keep;
+  const RngState* rng;
 };
 
 template <int LAY, int EPI, bool BGELU>
@@ -90,7 +97,14 @@ __global__ void __launch_bounds__(SG_THREADS) sgemm_grouped_kernel(SgemmParams p
       float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
       if (LAY == LAY_NN || k0 + k < kvalid_end)
         v = *reinterpret_cast<const float4*>(Bexp + (int64_t)(k0 + k) * p.N + n0 + n4 * 4);
-      if (BGELU) { v.x = gelu_erf(v.x); v.y = gelu_erf(v.y); v.z = gelu_erf(v.z); v.w = gelu_erf(v.w); }
+      if (BGELU) {
+        v.x = gelu_erf(v.x); v.y = gelu_erf(v.y); v.z = gelu_erf(v.z); v.w = gelu_erf(v.w);
+        if (p.drop_thr != 0u) {
+          float sc[4];
+          dropout_scale4(*p.rng, (uint32_t)(k0 + k), (uint32_t)((n0 + n4 * 4) / 4), p.drop_thr, p.drop_inv_keep, sc);
+          v.x *= sc[0]; v.y *= sc[1]; v.z *= sc[2]; v.w *= sc[3];
+        }
+      }
       if (BGELU && !(k0 + k < kvalid_end)) v = make_float4(0.f, 0.f, 0.f, 0.f);
       *reinterpret_cast<float4*>(&Bs[k][n4 * 4]) = v;
     }
@@ -122,15 +136,18 @@ __global__ void __launch_bounds__(SG_THREADS) sgemm_grouped_kernel(SgemmParams p
     float v[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) v[j] = acc[i][j] + bias[j];
+    float sc[4] = {1.f, 1.f, 1.f, 1.f};
+    if ((EPI == EPI_BIAS_GELU_SAVE || EPI == EPI_GELU_GRAD) && p.drop_thr != 0u)
+      dropout_scale4(*p.rng, (uint32_t)(m0 + ty * 4 + i), (uint32_t)((n0 + tx * 4) / 4), p.drop_thr, p.drop_inv_keep, sc);
     if (EPI == EPI_BIAS_GELU_SAVE) {
       if (p.aux_out != nullptr) *reinterpret_cast<float4*>(p.aux_out + off) = make_float4(v[0], v[1], v[2], v[3]);
 #pragma unroll
-      for (int j = 0; j < 4; ++j) v[j] = gelu_erf(v[j]);
+      for (int j = 0; j < 4; ++j) v[j] = gelu_erf(v[j]) * sc[j];
     }
     if (EPI == EPI_GELU_GRAD) {
       const float4 h = *reinterpret_cast<const float4*>(p.aux + off);
-      v[0] *= gelu_erf_grad(h.x); v[1] *= gelu_erf_grad(h.y);
-      v[2] *= gelu_erf_grad(h.z); v[3] *= gelu_erf_grad(h.w);
+      v[0] *= gelu_erf_grad(h.x) * sc[0]; v[1] *= gelu_erf_grad(h.y) * sc[1];
+      v[2] *= gelu_erf_grad(h.z) * sc[2]; v[3] *= gelu_erf_grad(h.w) * sc[3];
     }
     *reinterpret_cast<float4*>(Cbase + off) = make_float4(v[0], v[1], v[2], v[3]);
   }
@@ -154,14 +171,20 @@ using namespace m3;
 
 int m3_ffn_fwd_f32(const float* xq, const int32_t* offsets, const int32_t* tile_expert, int cap_rows, int E, int D,
                    int H, const float* w1, const float* b1, const float* w2, const float* b2, float* hpre,
-                   float* yq, void* workspace, size_t workspace_bytes, cudaStream_t st) {
+                   float* yq, void* workspace, size_t workspace_bytes, float drop_p, const void* rng, cudaStream_t st) {
   M3_CHECK_SHAPE(D % BN == 0 && H % BN == 0 && cap_rows % BM == 0);
+  if (drop_p > 0.f && (hpre == nullptr || rng == nullptr)) return M3_ERR_ARG;      // dropout is a training-time op
   if (workspace_bytes < (size_t)cap_rows * H * sizeof(float)) return M3_ERR_WORKSPACE;
   float* h = static_cast<float*>(workspace);
   SgemmParams p{};
   p.offsets = offsets; p.tile_expert = tile_expert; p.pad = M3_PAD_ROWS; p.E = E;
   // fc1: h = gelu(xq W1^T + b1)
   p.A = xq; p.B = w1; p.C = h; p.bias = b1; p.aux_out = hpre; p.N = H; p.Kdim = D;
+  if (drop_p > 0.f) {
+    p.drop_thr = dropout_threshold(drop_p);
+    p.drop_inv_keep = 1.0f / (1.0f - drop_p);
+    p.rng = static_cast<const RngState*>(rng);
+  }
   sgemm_grouped_kernel<LAY_NT, EPI_BIAS_GELU_SAVE, false><<<dim3(cap_rows / BM, H / BN), SG_THREADS, 0, st>>>(p);
   M3_LAUNCH_CHECK();
   // fc2: yq = h W2^T + b2
@@ -174,12 +197,18 @@ int m3_ffn_fwd_f32(const float* xq, const int32_t* offsets, const int32_t* tile_
 int m3_ffn_bwd_f32(const float* xq, const float* hpre, const float* dyq, const int32_t* counts,
                    const int32_t* offsets, const int32_t* tile_expert, int cap_rows, int E, int D, int H,
                    const float* w1, const float* w2, float* dxq, float* dw1, float* db1, float* dw2, float* db2,
-                   void* workspace, size_t workspace_bytes, cudaStream_t st) {
+                   void* workspace, size_t workspace_bytes, float drop_p, const void* rng, cudaStream_t st) {
   M3_CHECK_SHAPE(D % BN == 0 && H % BN == 0 && cap_rows % BM == 0);
+  if (drop_p > 0.f && rng == nullptr) return M3_ERR_ARG;
   if (workspace_bytes < (size_t)cap_rows * H * sizeof(float)) return M3_ERR_WORKSPACE;
   float* dhpre = static_cast<float*>(workspace);
   SgemmParams p{};
   p.offsets = offsets; p.counts = counts; p.tile_expert = tile_expert; p.pad = M3_PAD_ROWS; p.E = E;
+  if (drop_p > 0.f) {      // the forward's mask again, from the same (seed, counter) the caller kept
+    p.drop_thr = dropout_threshold(drop_p);
+    p.drop_inv_keep = 1.0f / (1.0f - drop_p);
+    p.rng = static_cast<const RngState*>(rng);
+  }
   // dhpre = (dyq W2) * gelu'(hpre)                     [rows, D] x [D, H]
   p.A = dyq; p.B = w2; p.C = dhpre; p.aux = hpre; p.N = H; p.Kdim = D;
   sgemm_grouped_kernel<LAY_NN, EPI_GELU_GRAD, false><<<dim3(cap_rows / BM, H / BN), SG_THREADS, 0, st>>>(p);

@@ -15,6 +15,7 @@
 // Roofline: HBM-bound on reading x once (T*D*el bytes) for large T, FFMA-bound
 // below that; 2*Dg*E flop per token.
 #include "common.cuh"
+#include "philox.cuh"
 
 namespace m3 {
 
@@ -67,7 +68,7 @@ gate_fwd_kernel(const XT* __restrict__ x, int64_t ldx, const float* __restrict__
                 float* __restrict__ clean_logits, float* __restrict__ noisy_logits,
                 float* __restrict__ gates, float* __restrict__ imp_partial,
                 int32_t* __restrict__ load_partial, const float* __restrict__ ln_mean,
-                const float* __restrict__ ln_rstd, const float* __restrict__ ln_gb) {
+                const float* __restrict__ ln_rstd, const float* __restrict__ ln_gb, const RngState* __restrict__ rng) {
   pdl_wait();
   pdl_trigger();
   using C = GateCfg<E, TM, NW>;
@@ -186,8 +187,17 @@ gate_fwd_kernel(const XT* __restrict__ x, int64_t ldx, const float* __restrict__
     const int64_t te = (int64_t)(valid ? t : 0) * E + eg * 4;
     float z[4] = {acc[j][0], acc[j][1], acc[j][2], acc[j][3]};
     if (valid) *reinterpret_cast<float4*>(clean_logits + te) = make_float4(z[0], z[1], z[2], z[3]);
-    if (noise != nullptr) {
-      float4 n = valid ? __ldg(reinterpret_cast<const float4*>(noise + te)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    if (noise != nullptr || rng != nullptr) {
+      // noisy = clean + N(0,1) * stddev (noisy_gate_vmoe.py:226): the normals come from the caller (torch.randn_like, the
+      // reference's stream) or are drawn here, four per lane, from the counter-based generator (philox.cuh)
+      float4 n = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (noise != nullptr) {
+        if (valid) n = __ldg(reinterpret_cast<const float4*>(noise + te));
+      } else {
+        float nn[4];
+        normal4(*rng, (uint32_t)(valid ? t : 0), (uint32_t)eg, nn);
+        n = make_float4(nn[0], nn[1], nn[2], nn[3]);
+      }
       z[0] += n.x * noise_stddev; z[1] += n.y * noise_stddev;
       z[2] += n.z * noise_stddev; z[3] += n.w * noise_stddev;
       if (valid && noisy_logits != nullptr)
@@ -295,7 +305,8 @@ static int launch_gate_fwd(const void* x, int64_t ldx, const float* task_feat, c
                            const float* noise, float noise_stddev, int T, int D, int Dt, int K, int K1,
                            int64_t* idx, int32_t* idx_full, float* score, float* top_vals, float* clean,
                            float* noisy, float* gates, float* imp_partial, int32_t* load_partial,
-                           const float* ln_mean, const float* ln_rstd, const float* ln_gb, cudaStream_t st) {
+                           const float* ln_mean, const float* ln_rstd, const float* ln_gb, const RngState* rng,
+                           cudaStream_t st) {
   using C = GateCfg<E, TM, NW>;
   size_t smem = gate_fwd_smem<E, TM, NW, XT>();
   auto kern = gate_fwd_kernel<E, TM, NW, XT>;
@@ -306,7 +317,7 @@ static int launch_gate_fwd(const void* x, int64_t ldx, const float* task_feat, c
   int grid = m3_ceil_div(T, C::TOK_CTA);
   launch_k(kern, grid, NW * 32, smem, st, static_cast<const XT*>(x), ldx, task_feat, w_gate, noise, noise_stddev, T,
            D, Dt, K, K1, idx, idx_full, score, top_vals, clean, noisy, gates, imp_partial, load_partial, ln_mean,
-           ln_rstd, ln_gb);
+           ln_rstd, ln_gb, rng);
   M3_LAUNCH_CHECK();
   return M3_OK;
 }
@@ -609,7 +620,7 @@ extern "C" int m3_gate_num_partials(int T, int E) {
 
 #define M3_GATE_ARGS x, ldx, task_feat, w_gate, noise, noise_stddev, T, D, Dt, K, K1, idx, idx_full, score, \
                      top_vals, clean_logits, noisy_logits, gates, imp_partial, load_partial, ln_mean, ln_rstd, \
-                     ln_gb, st
+                     ln_gb, rng, st
 #define M3_GATE_CASE_T(EE, XT)                                               \
   switch (gate_cfg_id<EE>(T)) {                                              \
     case 3: return launch_gate_fwd<EE, 8, 4, XT>(M3_GATE_ARGS);              \
@@ -626,8 +637,12 @@ static int gate_fwd_impl(const void* x, int x_dtype, int64_t ldx, const float* t
                          const float* noise, float noise_stddev, int T, int D, int Dt, int E, int K,
                          int64_t* idx, int32_t* idx_full, float* score, float* top_vals, float* clean_logits,
                          float* noisy_logits, float* gates, float* imp_partial, int32_t* load_partial,
-                         const float* ln_mean, const float* ln_rstd, const float* ln_gb, m3_stream_t stream) {
+                         const float* ln_mean, const float* ln_rstd, const float* ln_gb, const void* rng_state,
+                         m3_stream_t stream) {
   M3_CHECK_ARG(x && w_gate && idx && idx_full && score && top_vals && clean_logits && imp_partial && load_partial);
+  M3_CHECK_ARG(!(noise && rng_state));
+  if (rng_state) M3_CHECK_ALIGN16(rng_state);
+  const RngState* rng = static_cast<const RngState*>(rng_state);
   M3_CHECK_ARG(T >= 0 && D > 0 && Dt >= 0 && (Dt == 0 || task_feat));
   M3_CHECK_SHAPE(D % kGateDC == 0 && K >= 1 && K <= E && K <= 8);
   M3_CHECK_SHAPE(x_dtype == M3_F32 || x_dtype == M3_BF16);
@@ -658,7 +673,21 @@ extern "C" int m3_gate_fwd(const void* x, int x_dtype, int64_t ldx, const float*
                            m3_stream_t stream) {
   return gate_fwd_impl(x, x_dtype, ldx, task_feat, w_gate, noise, noise_stddev, T, D, Dt, E, K, idx, idx_full, score,
                        top_vals, clean_logits, noisy_logits, gates, imp_partial, load_partial, nullptr, nullptr,
-                       nullptr, stream);
+                       nullptr, nullptr, stream);
+}
+
+// The same kernel drawing the router noise itself: noisy = clean + N(0,1) * noise_stddev with the normals generated in
+// registers from rng_state = {uint64 seed, uint64 call counter} (device memory, philox.cuh) - no [T, E] noise tensor is
+// ever written or read.  noisy_logits must be given (the backward pass and the load estimator read them).
+extern "C" int m3_gate_fwd_rng(const void* x, int x_dtype, int64_t ldx, const float* task_feat, const float* w_gate,
+                               const void* rng_state, float noise_stddev, int T, int D, int Dt, int E, int K,
+                               int64_t* idx, int32_t* idx_full, float* score, float* top_vals, float* clean_logits,
+                               float* noisy_logits, float* gates, float* imp_partial, int32_t* load_partial,
+                               m3_stream_t stream) {
+  M3_CHECK_ARG(rng_state && noisy_logits);
+  return gate_fwd_impl(x, x_dtype, ldx, task_feat, w_gate, nullptr, noise_stddev, T, D, Dt, E, K, idx, idx_full, score,
+                       top_vals, clean_logits, noisy_logits, gates, imp_partial, load_partial, nullptr, nullptr,
+                       nullptr, rng_state, stream);
 }
 
 // Block-level fusion: x = RAW fp32 residual stream, w_gate_folded / ln_gb from m3_ln_fold_gate,
@@ -673,7 +702,7 @@ extern "C" int m3_gate_fwd_ln(const float* x, int64_t ldx, const float* ln_mean,
   M3_CHECK_ALIGN16(ln_gb);
   return gate_fwd_impl(x, M3_F32, ldx, task_feat, w_gate_folded, noise, noise_stddev, T, D, Dt, E, K, idx, idx_full,
                        score, top_vals, clean_logits, noisy_logits, gates, imp_partial, load_partial, ln_mean,
-                       ln_rstd, ln_gb, stream);
+                       ln_rstd, ln_gb, nullptr, stream);
 }
 
 extern "C" size_t m3_gate_bwd_workspace_bytes(int T, int D, int Dt, int E) {

@@ -82,6 +82,22 @@ def _check_activation(activation):
     return max([d.p for d in drop], default=0.0)
 
 
+def _next_dropout_state(layer, device):
+    """Expert dropout (the Dropout(p) behind the experts' GELU, origin/vision_transformer_moe.py:248-251): None in eval or
+    at p = 0, else (p, rng) with rng = a SNAPSHOT {seed, call counter} int64[2] of the layer's device-side generator state,
+    whose counter is then bumped by a stream-ordered add - no host read-back, CUDA-graph capturable (a replay draws new
+    masks).  The seed follows torch.manual_seed at the time of the layer's first dropout call."""
+    if not (layer.drop_p > 0 and layer.training):
+        return None
+    st = getattr(layer, "_drop_rng", None)
+    if st is None or st.device != device:
+        seed = (torch.initial_seed() * 0x9E3779B97F4A7C15 + id(layer)) & 0x7FFFFFFFFFFFFFFF
+        st = layer._drop_rng = torch.tensor([seed, 0], dtype=torch.int64, device=device)
+    snap = st.clone()
+    st[1:].add_(1)
+    return (float(layer.drop_p), snap)
+
+
 class FMoETransformerMLP(nn.Module):
     # flipped by the ckpt subclass
     RETURN_SUMMARIES = False
@@ -181,8 +197,6 @@ class FMoETransformerMLP(nn.Module):
         """Reference signature (origin:161).  `fused_norm` is the B200 Block-level extension:
         when given, `inp` is the RAW residual stream and the call returns  inp + MoE(fused_norm(inp))
         with the LayerNorm and the residual add fused into the layer's kernels (MoEBlockMlp uses it)."""
-        if self.drop_p > 0 and self.training:
-            raise NotImplementedError("expert dropout > 0 in training is not implemented (SURVEY.md 8 f4)")
         original_shape = inp.shape
         x = inp.reshape(-1, self.d_model)
         gx = None
@@ -207,7 +221,8 @@ class FMoETransformerMLP(nn.Module):
         if x.dtype not in (torch.float32, torch.bfloat16):
             raise ValueError(f"unsupported input dtype {x.dtype}")
         nstd = float(gate.noise_stddev())
-        noise = gate.draw_noise(T, x.device)
+        noise = gate.draw_noise(T, x.device, as_tensor=fused_norm is not None)     # (the LN-fused gate entry takes a tensor)
+        drop = _next_dropout_state(self, x.device)
         if fused_norm is not None:
             if self.world_size > 1 or gx is not None or x.dtype != torch.float32:
                 raise NotImplementedError("fused_norm: single-GPU, fp32 residual stream, gate_inp is inp")
@@ -217,16 +232,16 @@ class FMoETransformerMLP(nn.Module):
             res = F_.MoEBlockFunction.apply(
                 x, ln_w, ln_b, gate.w_gate, tf, self.experts.htoh4.weight, self.experts.htoh4.bias,
                 self.experts.h4toh.weight, self.experts.h4toh.bias, noise, float(fused_norm.eps), self.top_k, nstd,
-                cdt, self.RETURN_SUMMARIES, self._wcache)
+                cdt, self.RETURN_SUMMARIES, self._wcache, drop)
         elif self.world_size > 1:
             if self._ep is None:
                 raise RuntimeError("world_size > 1 needs m3vit_b200.ep.attach(layer, group) before the first forward")
-            res = self._ep.forward(self, gate, x, gx, tf, noise, nstd, cdt)
+            res = self._ep.forward(self, gate, x, gx, tf, noise, nstd, cdt, drop)
         else:
             res = F_.MoEFunction.apply(
                 x, gx, gate.w_gate, tf, self.experts.htoh4.weight, self.experts.htoh4.bias,
                 self.experts.h4toh.weight, self.experts.h4toh.bias, noise, self.top_k, nstd, cdt,
-                self.RETURN_SUMMARIES, self._wcache)
+                self.RETURN_SUMMARIES, self._wcache, drop)
         out, score, top_vals, clean, noisy, gates, importance, load, idx, counts, cv_loss = res
         self.last_counts = counts                 # device tensor, no sync: for monitoring / tests
         if self.gate_hook is not None:
@@ -271,8 +286,6 @@ class TokenFMoETransformerMLP(nn.Module):
         self._wcache = F_.WeightCache()
 
     def forward(self, inp: torch.Tensor, gate_top_k_idx: torch.Tensor, gate_score: torch.Tensor):
-        if self.drop_p > 0 and self.training:
-            raise NotImplementedError("expert dropout > 0 in training is not implemented")
         shape = inp.shape
         if inp.numel() == 0:          # an empty token subset (the token Block routes masked subsets, token/vision_transformer_moe.py:753)
             return inp.clone()
@@ -281,5 +294,6 @@ class TokenFMoETransformerMLP(nn.Module):
         score = gate_score.reshape(-1, self.top_k)
         cdt = self.compute_dtype or (torch.bfloat16 if x.dtype == torch.bfloat16 else torch.float32)
         out = F_.ExpertsFunction.apply(x, idx, score, self.experts.htoh4.weight, self.experts.htoh4.bias,
-                                       self.experts.h4toh.weight, self.experts.h4toh.bias, cdt, self._wcache, None)
+                                       self.experts.h4toh.weight, self.experts.h4toh.bias, cdt, self._wcache, None,
+                                       _next_dropout_state(self, x.device))
         return out.reshape(shape)

@@ -325,7 +325,7 @@ def phase_b_dispatch(ctx: EPContext, st: EPFwdState, x, cnt_all, E_loc, top_k, c
     ops.launch_count += 3
 
 
-def phase_c_ffn(ctx: EPContext, st: EPFwdState, w1c, b1, w2c, b2, save_hpre: bool) -> None:
+def phase_c_ffn(ctx: EPContext, st: EPFwdState, w1c, b1, w2c, b2, save_hpre: bool, drop=None) -> None:
     """local: grouped expert FFN over this rank's receive queue -> yq (in the arena, peers read it)"""
     lib = load()
     cap, D = st.xq.shape
@@ -336,9 +336,14 @@ def phase_c_ffn(ctx: EPContext, st: EPFwdState, w1c, b1, w2c, b2, save_hpre: boo
     st.hpre = (torch.empty(max(int(lib.m3_ffn_saved_bytes(dt, cap, D, H)), 16), dtype=torch.uint8, device=st.xq.device)
                if save_hpre else None)        # opaque activation state for phase F
     ws = torch.empty(max(lib.m3_ffn_workspace_bytes(dt, cap, D, H, E_loc, 0), 16), dtype=torch.uint8, device=st.xq.device)
-    check(lib.m3_ffn_fwd(dt, ptr(st.xq), ptr(st.recv.offsets), ptr(st.recv.tile_expert), cap, E_loc, D, H, ptr(w1c),
-                         ptr(b1), ptr(w2c), ptr(b2), ptr(st.hpre), ptr(st.yq), ptr(ws), ws.numel(), stream_ptr()),
-          "m3_ffn_fwd")
+    if drop is not None and drop[0] > 0 and save_hpre:      # expert dropout: the mask is a function of the OWNER's queue row
+        check(lib.m3_ffn_fwd_dropout(dt, ptr(st.xq), ptr(st.recv.offsets), ptr(st.recv.tile_expert), cap, E_loc, D, H,
+                                     ptr(w1c), ptr(b1), ptr(w2c), ptr(b2), ptr(st.hpre), ptr(st.yq), ptr(ws), ws.numel(),
+                                     float(drop[0]), ptr(drop[1]), stream_ptr()), "m3_ffn_fwd_dropout")
+    else:
+        check(lib.m3_ffn_fwd(dt, ptr(st.xq), ptr(st.recv.offsets), ptr(st.recv.tile_expert), cap, E_loc, D, H, ptr(w1c),
+                             ptr(b1), ptr(w2c), ptr(b2), ptr(st.hpre), ptr(st.yq), ptr(ws), ws.numel(), stream_ptr()),
+              "m3_ffn_fwd")
     ops.launch_count += 2
 
 
@@ -387,7 +392,7 @@ def phase_e_combine_bwd(ctx: EPContext, st: EPFwdState, g_out, top_k) -> EPBwdSt
     return bs
 
 
-def phase_f_ffn_bwd(ctx: EPContext, st: EPFwdState, bs: EPBwdState, w1c, w2c, w1t, w2t) -> None:
+def phase_f_ffn_bwd(ctx: EPContext, st: EPFwdState, bs: EPBwdState, w1c, w2c, w1t, w2t, drop=None) -> None:
     lib = load()
     cap, D = st.xq.shape
     E_loc, H, _ = w1c.shape
@@ -400,10 +405,16 @@ def phase_f_ffn_bwd(ctx: EPContext, st: EPFwdState, bs: EPBwdState, w1c, w2c, w1
     dw2 = torch.empty(E_loc, D, H, dtype=torch.float32, device=dev)
     db2 = torch.empty(E_loc, D, dtype=torch.float32, device=dev)
     ws = torch.empty(max(lib.m3_ffn_workspace_bytes(dt, cap, D, H, E_loc, 1), 16), dtype=torch.uint8, device=dev)
-    check(lib.m3_ffn_bwd(dt, ptr(st.xq), ptr(st.hpre), ptr(bs.dyq), ptr(st.recv.counts), ptr(st.recv.offsets),
-                         ptr(st.recv.tile_expert), cap, E_loc, D, H, ptr(w1c), ptr(w2c), ptr(w1t), ptr(w2t),
-                         ptr(bs.dxq), ptr(dw1), ptr(db1), ptr(dw2), ptr(db2), ptr(ws), ws.numel(), stream_ptr()),
-          "m3_ffn_bwd")
+    if drop is not None and drop[0] > 0:
+        check(lib.m3_ffn_bwd_dropout(dt, ptr(st.xq), ptr(st.hpre), ptr(bs.dyq), ptr(st.recv.counts), ptr(st.recv.offsets),
+                                     ptr(st.recv.tile_expert), cap, E_loc, D, H, ptr(w1c), ptr(w2c), ptr(w1t), ptr(w2t),
+                                     ptr(bs.dxq), ptr(dw1), ptr(db1), ptr(dw2), ptr(db2), ptr(ws), ws.numel(),
+                                     float(drop[0]), ptr(drop[1]), stream_ptr()), "m3_ffn_bwd_dropout")
+    else:
+        check(lib.m3_ffn_bwd(dt, ptr(st.xq), ptr(st.hpre), ptr(bs.dyq), ptr(st.recv.counts), ptr(st.recv.offsets),
+                             ptr(st.recv.tile_expert), cap, E_loc, D, H, ptr(w1c), ptr(w2c), ptr(w1t), ptr(w2t),
+                             ptr(bs.dxq), ptr(dw1), ptr(db1), ptr(dw2), ptr(db2), ptr(ws), ws.numel(), stream_ptr()),
+              "m3_ffn_bwd")
     ops.launch_count += 4 if dt == 1 else 6
     bs.grads = (dw1, db1, dw2, db2)
 
@@ -445,7 +456,7 @@ class EPMoEFunction(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, gate_x, w_gate, task_feat, w1, b1, w2, b2, noise, top_k, noise_stddev, compute_dtype,
-                want_gates, wcache, ep: EPContext):
+                want_gates, wcache, ep: EPContext, drop=None):
         ctx.set_materialize_grads(False)      # undefined output grads stay None (no zero fills)
         T, D = x.shape
         E_loc = w1.shape[0]
@@ -466,7 +477,7 @@ class EPMoEFunction(torch.autograd.Function):
             w1c, w2c, w1t, w2t = w1, w2, None, None
         needs_grad = any(ctx.needs_input_grad)
         grp.barrier(x.device)                                         # every push has landed
-        phase_c_ffn(ep, st, w1c, b1, w2c, b2, needs_grad)
+        phase_c_ffn(ep, st, w1c, b1, w2c, b2, needs_grad, drop)
         grp.barrier(x.device)                                         # every owner's yq is complete
         out = phase_d_combine(ep, st, T, D, top_k, x.dtype, keep_rows=needs_grad)
         g, pl = st.g, st.plan_local
@@ -474,6 +485,7 @@ class EPMoEFunction(torch.autograd.Function):
             ctx.st, ctx.ep = st, ep
             ctx.save_for_backward(x, gate_x, w_gate, task_feat, w1c, w2c, w1t, w2t, pl.importance)
             ctx.cfg = (top_k, gate_x is not None)
+            ctx.drop = drop
         else:
             release_fwd(ep, st)                                       # handed back after the next rendezvous
         gates = g.gates if g.gates is not None else x.new_empty(0)
@@ -492,7 +504,7 @@ class EPMoEFunction(torch.autograd.Function):
             d_out = torch.zeros_like(x)
         bs = phase_e_combine_bwd(ep, st, d_out.contiguous(), top_k)     # (fresh dyq block: nobody reads or writes it yet)
         grp.barrier(x.device)
-        phase_f_ffn_bwd(ep, st, bs, w1c, w2c, w1t, w2t)
+        phase_f_ffn_bwd(ep, st, bs, w1c, w2c, w1t, w2t, ctx.drop)
         dscore = bs.dscore if d_score is None else bs.dscore + d_score
         if d_gates is not None and d_gates.numel() == 0:
             d_gates = None
@@ -513,18 +525,18 @@ class EPMoEFunction(torch.autograd.Function):
         ctx.st = None
         if dtf is not None and task_feat is not None:
             dtf = dtf.view_as(task_feat).to(task_feat.dtype)
-        return dx, dgx, dwg, dtf, dw1, db1, dw2, db2, None, None, None, None, None, None, None
+        return dx, dgx, dwg, dtf, dw1, db1, dw2, db2, None, None, None, None, None, None, None, None
 
 
 class _EPRunner:
     def __init__(self, ep: EPContext):
         self.ep = ep
 
-    def forward(self, layer, gate, x, gx, tf, noise, nstd, cdt):
+    def forward(self, layer, gate, x, gx, tf, noise, nstd, cdt, drop=None):
         return EPMoEFunction.apply(
             x, gx, gate.w_gate, tf, layer.experts.htoh4.weight, layer.experts.htoh4.bias,
             layer.experts.h4toh.weight, layer.experts.h4toh.bias, noise, layer.top_k, nstd, cdt,
-            layer.RETURN_SUMMARIES, layer._wcache, self.ep)
+            layer.RETURN_SUMMARIES, layer._wcache, self.ep, drop)
 
 
 def attach(layer, ep) -> None:

@@ -38,7 +38,7 @@ class MoEFunction(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, gate_x, w_gate, task_feat, w1, b1, w2, b2, noise, top_k, noise_stddev, compute_dtype,
-                want_gates, wcache):
+                want_gates, wcache, drop=None):
         ctx.set_materialize_grads(False)      # undefined output grads stay None (no zero fills)
         T, D = x.shape
         E, H, _ = w1.shape
@@ -52,13 +52,14 @@ class MoEFunction(torch.autograd.Function):
             w1c, w2c, w1t, w2t = w1, w2, None, None
         needs_grad = any(ctx.needs_input_grad)
         xq = ops.dispatch_fwd(x, plan, top_k, out_dtype=compute_dtype)
-        yq, hpre = ops.ffn_fwd(xq, plan, w1c, b1, w2c, b2, save_hpre=needs_grad)
+        yq, hpre = ops.ffn_fwd(xq, plan, w1c, b1, w2c, b2, save_hpre=needs_grad, drop=drop if needs_grad else None)
         out = ops.combine_fwd(yq, plan, g.score, out_dtype=x.dtype)
         if needs_grad:
             ctx.save_for_backward(x, gate_x, w_gate, task_feat, w1c, w2c, w1t, w2t, xq, hpre, yq, g.score,
                                   g.noisy_logits, g.idx_full, plan.counts, plan.offsets, plan.pos, plan.tile_expert,
                                   plan.importance)
             ctx.cfg = (top_k, plan.cap_rows, gate_x is not None)
+            ctx.drop = drop
         gates = g.gates if g.gates is not None else x.new_empty(0)
         ctx.mark_non_differentiable(g.idx, plan.load, plan.counts)
         if noise is None:
@@ -79,7 +80,7 @@ class MoEFunction(torch.autograd.Function):
         if d_out is None:
             d_out = torch.zeros_like(x)
         dyq, dscore = ops.combine_bwd(_c(d_out), yq, plan, score)
-        dxq, dw1, db1, dw2, db2 = ops.ffn_bwd(xq, hpre, dyq, plan, w1c, w2c, w1t, w2t)
+        dxq, dw1, db1, dw2, db2 = ops.ffn_bwd(xq, hpre, dyq, plan, w1c, w2c, w1t, w2t, drop=ctx.drop)
         if d_score is not None:
             dscore = dscore + d_score
         if d_gates is not None and d_gates.numel() == 0:
@@ -96,7 +97,7 @@ class MoEFunction(torch.autograd.Function):
             dgx = None
         if dtf is not None and task_feat is not None:
             dtf = dtf.view_as(task_feat).to(task_feat.dtype)
-        return dx, dgx, dwg, dtf, dw1, db1, dw2, db2, None, None, None, None, None, None
+        return dx, dgx, dwg, dtf, dw1, db1, dw2, db2, None, None, None, None, None, None, None
 
 
 class MoEBlockFunction(torch.autograd.Function):
@@ -109,7 +110,7 @@ class MoEBlockFunction(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, ln_w, ln_b, w_gate, task_feat, w1, b1, w2, b2, noise, eps, top_k, noise_stddev,
-                compute_dtype, want_gates, wcache):
+                compute_dtype, want_gates, wcache, drop=None):
         ctx.set_materialize_grads(False)      # undefined output grads stay None (no zero fills)
         T, D = x.shape
         E = w1.shape[0]
@@ -123,13 +124,14 @@ class MoEBlockFunction(torch.autograd.Function):
         else:
             w1c, w2c, w1t, w2t = w1, w2, None, None
         needs_grad = any(ctx.needs_input_grad)
-        yq, hpre = ops.ffn_fwd(xq, plan, w1c, b1, w2c, b2, save_hpre=needs_grad)
+        yq, hpre = ops.ffn_fwd(xq, plan, w1c, b1, w2c, b2, save_hpre=needs_grad, drop=drop if needs_grad else None)
         out = ops.combine_fwd_res(yq, plan, g.score, x)
         if needs_grad:
             ctx.save_for_backward(x, ln.mean, ln.rstd, ln.gamma, ln.beta, w_gate, task_feat, w1c, w2c, w1t, w2t, xq,
                                   hpre, yq, g.score, g.noisy_logits, g.idx_full, plan.counts, plan.offsets, plan.pos,
                                   plan.tile_expert, plan.importance)
             ctx.cfg = (top_k, plan.cap_rows)
+            ctx.drop = drop
         gates = g.gates if g.gates is not None else x.new_empty(0)
         ctx.mark_non_differentiable(g.idx, plan.load, plan.counts)
         noisy = g.clean_logits.view_as(g.clean_logits) if noise is None else g.noisy_logits
@@ -146,7 +148,7 @@ class MoEBlockFunction(torch.autograd.Function):
         ln = ops.LnState(mean, rstd, gamma, beta, None, None)
         d_out = torch.zeros_like(x) if d_out is None else _c(d_out).float()
         dyq, dscore = ops.combine_bwd(d_out, yq, plan, score)
-        dxq, dw1, db1, dw2, db2 = ops.ffn_bwd(xq, hpre, dyq, plan, w1c, w2c, w1t, w2t)
+        dxq, dw1, db1, dw2, db2 = ops.ffn_bwd(xq, hpre, dyq, plan, w1c, w2c, w1t, w2t, drop=ctx.drop)
         if d_score is not None:
             dscore = dscore + d_score
         if d_gates is not None and d_gates.numel() == 0:
@@ -157,7 +159,7 @@ class MoEBlockFunction(torch.autograd.Function):
         dx, dgamma, dbeta = ops.ln_bwd_res(dxn, x, ln, d_out)
         if dtf is not None and task_feat is not None:
             dtf = dtf.view_as(task_feat).to(task_feat.dtype)
-        return dx, dgamma, dbeta, dwg, dtf, dw1, db1, dw2, db2, None, None, None, None, None, None, None
+        return dx, dgamma, dbeta, dwg, dtf, dw1, db1, dw2, db2, None, None, None, None, None, None, None, None
 
 
 class GateFunction(torch.autograd.Function):
@@ -197,7 +199,7 @@ class ExpertsFunction(torch.autograd.Function):
     (models/moe/token/custom_moe_layer.py:88-156)."""
 
     @staticmethod
-    def forward(ctx, x, idx, score, w1, b1, w2, b2, compute_dtype, wcache, plan: Optional[ops.Plan]):
+    def forward(ctx, x, idx, score, w1, b1, w2, b2, compute_dtype, wcache, plan: Optional[ops.Plan], drop=None):
         ctx.set_materialize_grads(False)      # undefined output grads stay None (no zero fills)
         T, D = x.shape
         E = w1.shape[0]
@@ -212,12 +214,13 @@ class ExpertsFunction(torch.autograd.Function):
         else:
             w1c, w2c, w1t, w2t = w1, w2, None, None
         needs_grad = any(ctx.needs_input_grad)
-        yq, hpre = ops.ffn_fwd(xq, plan, w1c, b1, w2c, b2, save_hpre=needs_grad)
+        yq, hpre = ops.ffn_fwd(xq, plan, w1c, b1, w2c, b2, save_hpre=needs_grad, drop=drop if needs_grad else None)
         out = ops.combine_fwd(yq, plan, score, out_dtype=x.dtype)
         if needs_grad:
             ctx.save_for_backward(x, w1c, w2c, w1t, w2t, xq, hpre, yq, score, plan.counts, plan.offsets, plan.pos,
                                   plan.tile_expert)
             ctx.cfg = (K, plan.cap_rows)
+            ctx.drop = drop
         return out
 
     @staticmethod
@@ -228,9 +231,9 @@ class ExpertsFunction(torch.autograd.Function):
         if d_out is None:
             d_out = torch.zeros_like(x)
         dyq, dscore = ops.combine_bwd(_c(d_out), yq, plan, score)
-        dxq, dw1, db1, dw2, db2 = ops.ffn_bwd(xq, hpre, dyq, plan, w1c, w2c, w1t, w2t)
+        dxq, dw1, db1, dw2, db2 = ops.ffn_bwd(xq, hpre, dyq, plan, w1c, w2c, w1t, w2t, drop=ctx.drop)
         dx = ops.dispatch_bwd(dxq, plan, x.shape[0], K, out_dtype=x.dtype)
-        return dx, None, dscore, dw1, db1, dw2, db2, None, None, None
+        return dx, None, dscore, dw1, db1, dw2, db2, None, None, None, None
 
 
 class WeightCache:

@@ -137,11 +137,23 @@ class NoisyGate_VMoE(BaseGate):
             s *= 0
         return s
 
-    def draw_noise(self, T, device):
-        """The reference always calls randn_like (origin:226).  We only draw when the
-        noise is actually used; set `gate.strict_rng = True` to consume the RNG stream
-        exactly like the reference even at std 0."""
-        if abs(self.noise_stddev()) > 0 or getattr(self, "strict_rng", False):
+    def draw_noise(self, T, device, as_tensor=False):
+        """The router noise of origin:226 (`torch.randn_like(clean_logits) * noise_stddev`).  Nothing when the stddev is 0
+        (eval, noise_std 0).  Otherwise, by default, a SNAPSHOT int64[2] = {seed, call counter} of this gate's device-side
+        generator state: the gate kernel draws the normals itself (csrc/philox.cuh) and no [T, E] tensor exists; the
+        counter is bumped by a stream-ordered add (no host read-back, CUDA-graph capturable).  `gate.strict_rng = True`
+        (or as_tensor) draws them with torch.randn instead - the reference's own stream, consumed even at stddev 0 like
+        the reference does."""
+        strict = getattr(self, "strict_rng", False)
+        if abs(self.noise_stddev()) > 0 and not (strict or as_tensor):
+            st = getattr(self, "_noise_rng", None)
+            if st is None or st.device != device:
+                seed = (torch.initial_seed() * 0x9E3779B97F4A7C15 + id(self)) & 0x7FFFFFFFFFFFFFFF
+                st = self._noise_rng = torch.tensor([seed, 0], dtype=torch.int64, device=device)
+            snap = st.clone()
+            st[1:].add_(1)
+            return snap
+        if abs(self.noise_stddev()) > 0 or strict:
             return torch.randn(T, self.tot_expert, device=device, dtype=torch.float32)
         return None
 

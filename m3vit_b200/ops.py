@@ -81,6 +81,15 @@ def gate_fwd(x, w_gate, top_k, task_feat=None, noise=None, noise_stddev=0.0, wan
     gates = _f32((T, E), dev) if want_gates else None
     imp_p = _f32((max(n_part, 1), E), dev)
     load_p = torch.empty(max(n_part, 1), E, dtype=torch.int32, device=dev)
+    if noise is not None and noise.dtype == torch.int64:
+        # a generator state {seed, call counter} instead of a [T, E] tensor of normals: the kernel draws them itself
+        assert noise.numel() == 2 and noise.is_contiguous()
+        check(lib.m3_gate_fwd_rng(ptr(x), dtype_code(x), x.stride(0), ptr(task_feat), ptr(w_gate), ptr(noise),
+                                  float(noise_stddev), T, D, Dt, E, K, ptr(idx), ptr(idx_full), ptr(score), ptr(top_vals),
+                                  ptr(clean), ptr(noisy), ptr(gates), ptr(imp_p), ptr(load_p), stream_ptr()),
+              "m3_gate_fwd_rng")
+        _count("gate_fwd")
+        return GateOut(idx, idx_full, score, top_vals, clean, noisy, gates, imp_p[:n_part], load_p[:n_part])
     if noise is not None:
         assert noise.shape == (T, E) and noise.dtype == torch.float32 and noise.is_contiguous()
     check(lib.m3_gate_fwd(ptr(x), dtype_code(x), x.stride(0), ptr(task_feat), ptr(w_gate), ptr(noise),
@@ -232,9 +241,10 @@ def cast_weights_bf16(w, want_plain=True, want_transposed=False, out=None):
     return o, ot
 
 
-def ffn_fwd(xq, plan: Plan, w1, b1, w2, b2, save_hpre=True):
+def ffn_fwd(xq, plan: Plan, w1, b1, w2, b2, save_hpre=True, drop=None):
     """xq [cap,D] (fp32|bf16); w1 [E,H,D], w2 [E,D,H] same dtype as xq; b1,b2 fp32.
-    Returns (yq, saved): `saved` is the library's opaque activation state for ffn_bwd (uint8)."""
+    Returns (yq, saved): `saved` is the library's opaque activation state for ffn_bwd (uint8).
+    drop = (p, rng_state int64[2] = {seed, call counter} on the device): expert dropout behind the GELU."""
     require_device(xq)
     lib = load()
     cap, D = xq.shape
@@ -245,14 +255,20 @@ def ffn_fwd(xq, plan: Plan, w1, b1, w2, b2, save_hpre=True):
     hpre = _ws(lib.m3_ffn_saved_bytes(dt, cap, D, H), xq.device) if save_hpre else None
     yq = torch.empty(cap, D, dtype=xq.dtype, device=xq.device)
     ws = _ws(lib.m3_ffn_workspace_bytes(dt, cap, D, H, E, 0), xq.device)
-    check(lib.m3_ffn_fwd(dt, ptr(xq), ptr(plan.offsets), ptr(plan.tile_expert), cap, E, D, H, ptr(w1), ptr(b1),
-                         ptr(w2), ptr(b2), ptr(hpre), ptr(yq), ptr(ws), ws.numel(), stream_ptr()), "m3_ffn_fwd")
+    if drop is not None and drop[0] > 0:
+        assert save_hpre, "expert dropout is a training-time op"
+        check(lib.m3_ffn_fwd_dropout(dt, ptr(xq), ptr(plan.offsets), ptr(plan.tile_expert), cap, E, D, H, ptr(w1), ptr(b1),
+                                     ptr(w2), ptr(b2), ptr(hpre), ptr(yq), ptr(ws), ws.numel(), float(drop[0]), ptr(drop[1]),
+                                     stream_ptr()), "m3_ffn_fwd_dropout")
+    else:
+        check(lib.m3_ffn_fwd(dt, ptr(xq), ptr(plan.offsets), ptr(plan.tile_expert), cap, E, D, H, ptr(w1), ptr(b1),
+                             ptr(w2), ptr(b2), ptr(hpre), ptr(yq), ptr(ws), ws.numel(), stream_ptr()), "m3_ffn_fwd")
     _count("ffn_chain" if (not save_hpre and lib.m3_ffn_uses_chain(dt, D, H)) else "ffn_fwd")
     return yq, hpre
 
 
-def ffn_bwd(xq, hpre, dyq, plan: Plan, w1, w2, w1t=None, w2t=None):
-    """returns dxq, dw1 [E,H,D] fp32, db1 [E,H], dw2 [E,D,H], db2 [E,D]"""
+def ffn_bwd(xq, hpre, dyq, plan: Plan, w1, w2, w1t=None, w2t=None, drop=None):
+    """returns dxq, dw1 [E,H,D] fp32, db1 [E,H], dw2 [E,D,H], db2 [E,D]; `drop` = what the forward call was given"""
     require_device(xq)
     lib = load()
     cap, D = xq.shape
@@ -262,9 +278,15 @@ def ffn_bwd(xq, hpre, dyq, plan: Plan, w1, w2, w1t=None, w2t=None):
     dxq = torch.empty_like(xq)
     dw1, db1, dw2, db2 = _f32((E, H, D), dev), _f32((E, H), dev), _f32((E, D, H), dev), _f32((E, D), dev)
     ws = _ws(lib.m3_ffn_workspace_bytes(dt, cap, D, H, E, 1), dev)
-    check(lib.m3_ffn_bwd(dt, ptr(xq), ptr(hpre), ptr(dyq), ptr(plan.counts), ptr(plan.offsets), ptr(plan.tile_expert),
-                         cap, E, D, H, ptr(w1), ptr(w2), ptr(w1t), ptr(w2t), ptr(dxq), ptr(dw1), ptr(db1), ptr(dw2),
-                         ptr(db2), ptr(ws), ws.numel(), stream_ptr()), "m3_ffn_bwd")
+    if drop is not None and drop[0] > 0:
+        check(lib.m3_ffn_bwd_dropout(dt, ptr(xq), ptr(hpre), ptr(dyq), ptr(plan.counts), ptr(plan.offsets),
+                                     ptr(plan.tile_expert), cap, E, D, H, ptr(w1), ptr(w2), ptr(w1t), ptr(w2t), ptr(dxq),
+                                     ptr(dw1), ptr(db1), ptr(dw2), ptr(db2), ptr(ws), ws.numel(), float(drop[0]),
+                                     ptr(drop[1]), stream_ptr()), "m3_ffn_bwd_dropout")
+    else:
+        check(lib.m3_ffn_bwd(dt, ptr(xq), ptr(hpre), ptr(dyq), ptr(plan.counts), ptr(plan.offsets), ptr(plan.tile_expert),
+                             cap, E, D, H, ptr(w1), ptr(w2), ptr(w1t), ptr(w2t), ptr(dxq), ptr(dw1), ptr(db1), ptr(dw2),
+                             ptr(db2), ptr(ws), ws.numel(), stream_ptr()), "m3_ffn_bwd")
     if dt == L.M3_BF16:
         tiles = (D // 128) * (H // 128) * E          # mirrors wgrad_splits() in ffn_bf16.cu
         splits = min(16, max(1, 148 // tiles))

@@ -191,8 +191,8 @@ def test_token_moe_experts_only_entry():
 
 
 def test_noisy_training_path_matches_oracle_with_same_noise():
-    """f4: vmoe_noisy_std > 0 in training.  The noise is drawn by torch on the device; replaying the same
-    generator state gives the oracle the identical noise tensor, so routing and the normal-CDF load loss
+    """f4: vmoe_noisy_std > 0 in training.  With gate.strict_rng the noise is drawn by torch on the device; replaying the
+    same generator state gives the oracle the identical noise tensor, so routing and the normal-CDF load loss
     (origin/noisy_gate_vmoe.py:82-125,267-283) can be compared directly."""
     from oracle import moe_oracle as O
     dev = torch.device("cuda:0")
@@ -200,6 +200,7 @@ def test_noisy_training_path_matches_oracle_with_same_noise():
     layer = build_layer(case, data, "origin", dev)
     for g in layer.gate:
         g.noise_std = 1.0
+        g.strict_rng = True          # torch.randn, the reference's stream (default: drawn inside the gate kernel)
     layer.train()
     x = data["x"].to(dev).requires_grad_(True)
     torch.manual_seed(1234)
