@@ -20,6 +20,7 @@
 namespace m3 {
 
 constexpr int kGateDC = 32;  // columns of x per smem chunk
+constexpr int kGateBigCfg = 5;  // tile configuration for big batches and E >= 16 (see gate_cfg_id)
 constexpr int kGateStages = 4;  // cp.async ring depth (chunks in flight per CTA)
 
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
@@ -51,15 +52,15 @@ struct GateRow<__nv_bfloat16> {
   }
 };
 
-template <int E, int TM, int NW>
+template <int E, int TM, int NW, int EPL = 4>
 struct GateCfg {
-  static constexpr int EG = E / 4;          // lanes per token
+  static constexpr int EG = E / EPL;        // lanes per token (EPL experts per lane: 4, or 8 for the big-batch tile)
   static constexpr int TG = 32 / EG;        // tokens per warp "row"
   static constexpr int TOK_W = TG * TM;     // tokens per warp
   static constexpr int TOK_CTA = TOK_W * NW;
 };
 
-template <int E, int TM, int NW, typename XT>
+template <int E, int TM, int NW, typename XT, int EPL = 4>
 __global__ void __launch_bounds__(NW * 32)
 gate_fwd_kernel(const XT* __restrict__ x, int64_t ldx, const float* __restrict__ task_feat,
                 const float* __restrict__ w_gate, const float* __restrict__ noise, float noise_stddev,
@@ -71,9 +72,11 @@ gate_fwd_kernel(const XT* __restrict__ x, int64_t ldx, const float* __restrict__
                 const float* __restrict__ ln_rstd, const float* __restrict__ ln_gb, const RngState* __restrict__ rng) {
   pdl_wait();
   pdl_trigger();
-  using C = GateCfg<E, TM, NW>;
+  using C = GateCfg<E, TM, NW, EPL>;
   using Row = GateRow<XT>;
   constexpr int EG = C::EG, TG = C::TG, TOK_W = C::TOK_W;
+  constexpr int EQ = EPL / 4;                      // float4 groups of experts per lane
+  static_assert(EPL == 4 || EPL == 8, "experts per lane");
   constexpr int ROWB = Row::kBytes;
   constexpr int XS_STAGE = TOK_W * ROWB;           // bytes per warp per stage
   constexpr int WS_STAGE = kGateDC * E * 4;        // bytes per stage
@@ -106,11 +109,11 @@ gate_fwd_kernel(const XT* __restrict__ x, int64_t ldx, const float* __restrict__
     cp_async_commit();
   };
 
-  float acc[TM][4];
+  float acc[TM][EPL];
 #pragma unroll
   for (int j = 0; j < TM; ++j)
 #pragma unroll
-    for (int c = 0; c < 4; ++c) acc[j][c] = 0.f;
+    for (int c = 0; c < EPL; ++c) acc[j][c] = 0.f;
 
   // S-deep ring: chunks c .. c+S-2 are in flight while chunk c is consumed.  One barrier per chunk:
   // it publishes chunk c and proves that every warp has finished chunk c-1, whose stage is refilled.
@@ -128,19 +131,26 @@ gate_fwd_kernel(const XT* __restrict__ x, int64_t ldx, const float* __restrict__
     const float* wst = reinterpret_cast<const float*>(ws + (c % S) * WS_STAGE);
 #pragma unroll 2
     for (int d4 = 0; d4 < kGateDC; d4 += 4) {
-      float4 w[4];
+      // EPL = 8, TM = 4: 8 + 4 LDS.128 per 128 FMAs instead of 4 + 2 per 32 - the kernel is bound by the 4 clk an
+      // LDS.128 takes on the return path, not by the FMAs
+      float4 w[4][EQ];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) w[i] = *reinterpret_cast<const float4*>(wst + (d4 + i) * E + eg * 4);
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int h = 0; h < EQ; ++h) w[i][h] = *reinterpret_cast<const float4*>(wst + (d4 + i) * E + eg * EPL + 4 * h);
 #pragma unroll
       for (int j = 0; j < TM; ++j) {
         float4 xv = Row::ld4(xst + (tg + TG * j) * ROWB, d4);
         const float xa[4] = {xv.x, xv.y, xv.z, xv.w};
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-          acc[j][0] = fmaf(xa[i], w[i].x, acc[j][0]);
-          acc[j][1] = fmaf(xa[i], w[i].y, acc[j][1]);
-          acc[j][2] = fmaf(xa[i], w[i].z, acc[j][2]);
-          acc[j][3] = fmaf(xa[i], w[i].w, acc[j][3]);
+#pragma unroll
+          for (int h = 0; h < EQ; ++h) {
+            acc[j][4 * h + 0] = fmaf(xa[i], w[i][h].x, acc[j][4 * h + 0]);
+            acc[j][4 * h + 1] = fmaf(xa[i], w[i][h].y, acc[j][4 * h + 1]);
+            acc[j][4 * h + 2] = fmaf(xa[i], w[i][h].z, acc[j][4 * h + 2]);
+            acc[j][4 * h + 3] = fmaf(xa[i], w[i][h].w, acc[j][4 * h + 3]);
+          }
         }
       }
     }
@@ -149,72 +159,90 @@ gate_fwd_kernel(const XT* __restrict__ x, int64_t ldx, const float* __restrict__
   // Block-level fusion (block.cu): x is the RAW residual stream and w_gate is gamma-folded and
   // column-centred, so  LayerNorm(x) @ W = rstd * (x @ W') + B,   B = ln_gb[E:2E]
   if (ln_mean != nullptr) {
-    const float4 B = __ldg(reinterpret_cast<const float4*>(ln_gb + E + eg * 4));
+    float Bv[EPL];
+#pragma unroll
+    for (int c = 0; c < EPL; ++c) Bv[c] = __ldg(ln_gb + E + eg * EPL + c);
 #pragma unroll
     for (int j = 0; j < TM; ++j) {
       const int t = min(tok_w0 + tg + TG * j, T - 1);
       const float rs = __ldg(ln_rstd + t);
-      acc[j][0] = fmaf(rs, acc[j][0], B.x);
-      acc[j][1] = fmaf(rs, acc[j][1], B.y);
-      acc[j][2] = fmaf(rs, acc[j][2], B.z);
-      acc[j][3] = fmaf(rs, acc[j][3], B.w);
+#pragma unroll
+      for (int c = 0; c < EPL; ++c) acc[j][c] = fmaf(rs, acc[j][c], Bv[c]);
     }
   }
 
   // task-conditioned router: constant contribution of the task feature rows
   // (the reference concatenates it onto every token, custom_moe_layer.py:176-179)
   if (Dt > 0) {
-    float tb[4] = {0.f, 0.f, 0.f, 0.f};
+    float tb[EPL];
+#pragma unroll
+    for (int c = 0; c < EPL; ++c) tb[c] = 0.f;
     for (int j = 0; j < Dt; ++j) {
       float f = __ldg(task_feat + j);
-      float4 w = __ldg(reinterpret_cast<const float4*>(w_gate + (int64_t)(D + j) * E + eg * 4));
-      tb[0] = fmaf(f, w.x, tb[0]); tb[1] = fmaf(f, w.y, tb[1]);
-      tb[2] = fmaf(f, w.z, tb[2]); tb[3] = fmaf(f, w.w, tb[3]);
+#pragma unroll
+      for (int c = 0; c < EPL; ++c) tb[c] = fmaf(f, __ldg(w_gate + (int64_t)(D + j) * E + eg * EPL + c), tb[c]);
     }
 #pragma unroll
     for (int j = 0; j < TM; ++j)
 #pragma unroll
-      for (int c = 0; c < 4; ++c) acc[j][c] += tb[c];
+      for (int c = 0; c < EPL; ++c) acc[j][c] += tb[c];
   }
 
-  float imp[4] = {0.f, 0.f, 0.f, 0.f};
-  int ld[4] = {0, 0, 0, 0};
+  float imp[EPL];
+  int ld[EPL];
+#pragma unroll
+  for (int c = 0; c < EPL; ++c) { imp[c] = 0.f; ld[c] = 0; }
 
 #pragma unroll
   for (int j = 0; j < TM; ++j) {
     const int t = tok_w0 + tg + TG * j;
     const bool valid = t < T;
-    const int64_t te = (int64_t)(valid ? t : 0) * E + eg * 4;
-    float z[4] = {acc[j][0], acc[j][1], acc[j][2], acc[j][3]};
-    if (valid) *reinterpret_cast<float4*>(clean_logits + te) = make_float4(z[0], z[1], z[2], z[3]);
+    const int64_t te = (int64_t)(valid ? t : 0) * E + eg * EPL;
+    float z[EPL];
+#pragma unroll
+    for (int c = 0; c < EPL; ++c) z[c] = acc[j][c];
+    if (valid) {
+#pragma unroll
+      for (int h = 0; h < EQ; ++h)
+        *reinterpret_cast<float4*>(clean_logits + te + 4 * h) = make_float4(z[4 * h], z[4 * h + 1], z[4 * h + 2], z[4 * h + 3]);
+    }
     if (noise != nullptr || rng != nullptr) {
       // noisy = clean + N(0,1) * stddev (noisy_gate_vmoe.py:226): the normals come from the caller (torch.randn_like, the
-      // reference's stream) or are drawn here, four per lane, from the counter-based generator (philox.cuh)
-      float4 n = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (noise != nullptr) {
-        if (valid) n = __ldg(reinterpret_cast<const float4*>(noise + te));
-      } else {
-        float nn[4];
-        normal4(*rng, (uint32_t)(valid ? t : 0), (uint32_t)eg, nn);
-        n = make_float4(nn[0], nn[1], nn[2], nn[3]);
+      // reference's stream) or are drawn here, four per expert quad, from the counter-based generator (philox.cuh)
+#pragma unroll
+      for (int h = 0; h < EQ; ++h) {
+        float nn[4] = {0.f, 0.f, 0.f, 0.f};
+        if (noise != nullptr) {
+          if (valid) {
+            const float4 n = __ldg(reinterpret_cast<const float4*>(noise + te + 4 * h));
+            nn[0] = n.x; nn[1] = n.y; nn[2] = n.z; nn[3] = n.w;
+          }
+        } else {
+          normal4(*rng, (uint32_t)(valid ? t : 0), (uint32_t)(eg * EQ + h), nn);
+        }
+#pragma unroll
+        for (int c = 0; c < 4; ++c) z[4 * h + c] += nn[c] * noise_stddev;
       }
-      z[0] += n.x * noise_stddev; z[1] += n.y * noise_stddev;
-      z[2] += n.z * noise_stddev; z[3] += n.w * noise_stddev;
-      if (valid && noisy_logits != nullptr)
-        *reinterpret_cast<float4*>(noisy_logits + te) = make_float4(z[0], z[1], z[2], z[3]);
+      if (valid && noisy_logits != nullptr) {
+#pragma unroll
+        for (int h = 0; h < EQ; ++h)
+          *reinterpret_cast<float4*>(noisy_logits + te + 4 * h) = make_float4(z[4 * h], z[4 * h + 1], z[4 * h + 2], z[4 * h + 3]);
+      }
     }
-    // softmax over all E experts of this token (EG lanes x 4)
-    float m = fmaxf(fmaxf(z[0], z[1]), fmaxf(z[2], z[3]));
+    // softmax over all E experts of this token (EG lanes x EPL)
+    float m = z[0];
+#pragma unroll
+    for (int c = 1; c < EPL; ++c) m = fmaxf(m, z[c]);
 #pragma unroll
     for (int o = EG / 2; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-    float p[4];
+    float p[EPL];
     float s = 0.f;
 #pragma unroll
-    for (int c = 0; c < 4; ++c) { p[c] = expf(z[c] - m); s += p[c]; }
+    for (int c = 0; c < EPL; ++c) { p[c] = expf(z[c] - m); s += p[c]; }
 #pragma unroll
     for (int o = EG / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
 #pragma unroll
-    for (int c = 0; c < 4; ++c) p[c] = p[c] / s;
+    for (int c = 0; c < EPL; ++c) p[c] = p[c] / s;
 
     // top-K1 on the probabilities, descending, lowest index wins ties
     unsigned taken = 0, takenK = 0;
@@ -222,8 +250,8 @@ gate_fwd_kernel(const XT* __restrict__ x, int64_t ldx, const float* __restrict__
       float bv = -1.f;
       int bi = 0x7fffffff;
 #pragma unroll
-      for (int c = 0; c < 4; ++c)
-        if (!((taken >> c) & 1u) && p[c] > bv) { bv = p[c]; bi = eg * 4 + c; }
+      for (int c = 0; c < EPL; ++c)
+        if (!((taken >> c) & 1u) && p[c] > bv) { bv = p[c]; bi = eg * EPL + c; }
 #pragma unroll
       for (int o = EG / 2; o > 0; o >>= 1) {
         float ov = __shfl_xor_sync(0xffffffffu, bv, o);
@@ -231,9 +259,9 @@ gate_fwd_kernel(const XT* __restrict__ x, int64_t ldx, const float* __restrict__
         if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
       }
       if (bi >= E) { bi = r; bv = 0.f; }  // NaN row: keep indices in range
-      if ((bi >> 2) == eg) {
-        taken |= 1u << (bi & 3);
-        if (r < K) takenK |= 1u << (bi & 3);
+      if ((bi / EPL) == eg) {
+        taken |= 1u << (bi % EPL);
+        if (r < K) takenK |= 1u << (bi % EPL);
       }
       if (valid && eg == 0) {
         idx_full[(int64_t)t * K1 + r] = bi;
@@ -244,20 +272,24 @@ gate_fwd_kernel(const XT* __restrict__ x, int64_t ldx, const float* __restrict__
         }
       }
     }
-    float g[4];
+    float g[EPL];
 #pragma unroll
-    for (int c = 0; c < 4; ++c) {
+    for (int c = 0; c < EPL; ++c) {
       const bool sel = valid && ((takenK >> c) & 1u);
       g[c] = sel ? p[c] : 0.f;
       imp[c] += g[c];
       ld[c] += (sel && p[c] > 0.f) ? 1 : 0;
     }
-    if (valid && gates != nullptr) *reinterpret_cast<float4*>(gates + te) = make_float4(g[0], g[1], g[2], g[3]);
+    if (valid && gates != nullptr) {
+#pragma unroll
+      for (int h = 0; h < EQ; ++h)
+        *reinterpret_cast<float4*>(gates + te + 4 * h) = make_float4(g[4 * h], g[4 * h + 1], g[4 * h + 2], g[4 * h + 3]);
+    }
   }
 
   // importance / load partials: fixed-order reduction -> deterministic
 #pragma unroll
-  for (int c = 0; c < 4; ++c) {
+  for (int c = 0; c < EPL; ++c) {
 #pragma unroll
     for (int o = EG; o < 32; o <<= 1) {
       imp[c] += __shfl_xor_sync(0xffffffffu, imp[c], o);
@@ -266,9 +298,9 @@ gate_fwd_kernel(const XT* __restrict__ x, int64_t ldx, const float* __restrict__
   }
   if (tg == 0) {
 #pragma unroll
-    for (int c = 0; c < 4; ++c) {
-      red_imp[warp * E + eg * 4 + c] = imp[c];
-      red_load[warp * E + eg * 4 + c] = ld[c];
+    for (int c = 0; c < EPL; ++c) {
+      red_imp[warp * E + eg * EPL + c] = imp[c];
+      red_load[warp * E + eg * EPL + c] = ld[c];
     }
   }
   __syncthreads();
@@ -281,9 +313,9 @@ gate_fwd_kernel(const XT* __restrict__ x, int64_t ldx, const float* __restrict__
   }
 }
 
-template <int E, int TM, int NW, typename XT>
+template <int E, int TM, int NW, typename XT, int EPL = 4>
 static size_t gate_fwd_smem() {
-  using C = GateCfg<E, TM, NW>;
+  using C = GateCfg<E, TM, NW, EPL>;
   return (size_t)kGateStages * kGateDC * E * 4 + (size_t)NW * kGateStages * C::TOK_W * GateRow<XT>::kBytes +
          (size_t)NW * E * 8;
 }
@@ -291,25 +323,31 @@ static size_t gate_fwd_smem() {
 // Three tile configurations; pick the largest that still puts >= 16 warps on every SM (the kernel
 // hides its smem / HBM latency with warps, not with ILP).
 //   0: 1 warp x TG*2 tokens (small T)   1: 4 warps x TG*2   2: 4 warps x TG*4   3: 4 warps x TG*8
+//   4 / 5 (E >= 16): 8 experts per lane - 1 warp x TG*4 tokens / 2 warps x TG*2 tokens per CTA: half the LDS per FMA
 template <int E>
 static int gate_cfg_id(int T) {
-  if (g_knobs[M3_KNOB_GATE_CFG] > 0) return g_knobs[M3_KNOB_GATE_CFG] - 1;   // forced (A/B measurement)
+  if (g_knobs[M3_KNOB_GATE_CFG] > 0) {                                       // forced (A/B measurement)
+    const int id = g_knobs[M3_KNOB_GATE_CFG] - 1;
+    return (id >= 4 && E < 16) ? 1 : id;
+  }
+  // measured at T = 38 432, E = 16 (tools/ab_gate.py): cfg 1 32.9 us, cfg 4 35.7 us, cfg 5 29.9 us
+  if (E >= 16 && T >= 4 * kNumSMs * GateCfg<(E >= 16 ? E : 16), 2, 2, 8>::TOK_CTA) return kGateBigCfg;
   if (T >= 16 * kNumSMs * GateCfg<E, 8, 4>::TOK_W) return 3;
   if (T >= 16 * kNumSMs * GateCfg<E, 4, 4>::TOK_W) return 2;   // (T = 38 432, E = 16: TM = 2 35 us, TM = 4 43 us, TM = 8 60 us)
   if (T >= 16 * kNumSMs * GateCfg<E, 2, 4>::TOK_W) return 1;
   return 0;
 }
 
-template <int E, int TM, int NW, typename XT>
+template <int E, int TM, int NW, typename XT, int EPL = 4>
 static int launch_gate_fwd(const void* x, int64_t ldx, const float* task_feat, const float* w_gate,
                            const float* noise, float noise_stddev, int T, int D, int Dt, int K, int K1,
                            int64_t* idx, int32_t* idx_full, float* score, float* top_vals, float* clean,
                            float* noisy, float* gates, float* imp_partial, int32_t* load_partial,
                            const float* ln_mean, const float* ln_rstd, const float* ln_gb, const RngState* rng,
                            cudaStream_t st) {
-  using C = GateCfg<E, TM, NW>;
-  size_t smem = gate_fwd_smem<E, TM, NW, XT>();
-  auto kern = gate_fwd_kernel<E, TM, NW, XT>;
+  using C = GateCfg<E, TM, NW, EPL>;
+  size_t smem = gate_fwd_smem<E, TM, NW, XT, EPL>();
+  auto kern = gate_fwd_kernel<E, TM, NW, XT, EPL>;
   if (smem > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
@@ -325,7 +363,9 @@ static int launch_gate_fwd(const void* x, int64_t ldx, const float* task_feat, c
 template <int E>
 static int gate_tokens_per_cta(int T) {
   const int id = gate_cfg_id<E>(T);
-  return id == 3 ? GateCfg<E, 8, 4>::TOK_CTA : id == 2 ? GateCfg<E, 4, 4>::TOK_CTA
+  constexpr int E8 = E >= 16 ? E : 16;       // (the 8-experts-per-lane tiles exist for E >= 16 only)
+  return id == 5 ? GateCfg<E8, 2, 2, 8>::TOK_CTA : id == 4 ? GateCfg<E8, 4, 1, 8>::TOK_CTA
+       : id == 3 ? GateCfg<E, 8, 4>::TOK_CTA : id == 2 ? GateCfg<E, 4, 4>::TOK_CTA
        : id == 1 ? GateCfg<E, 2, 4>::TOK_CTA : GateCfg<E, 2, 1>::TOK_CTA;
 }
 
@@ -623,6 +663,8 @@ extern "C" int m3_gate_num_partials(int T, int E) {
                      ln_gb, rng, st
 #define M3_GATE_CASE_T(EE, XT)                                               \
   switch (gate_cfg_id<EE>(T)) {                                              \
+    case 5: if constexpr (EE >= 16) return launch_gate_fwd<EE, 2, 2, XT, 8>(M3_GATE_ARGS); else return M3_ERR_SHAPE; \
+    case 4: if constexpr (EE >= 16) return launch_gate_fwd<EE, 4, 1, XT, 8>(M3_GATE_ARGS); else return M3_ERR_SHAPE; \
     case 3: return launch_gate_fwd<EE, 8, 4, XT>(M3_GATE_ARGS);              \
     case 2: return launch_gate_fwd<EE, 4, 4, XT>(M3_GATE_ARGS);              \
     case 1: return launch_gate_fwd<EE, 2, 4, XT>(M3_GATE_ARGS);              \
