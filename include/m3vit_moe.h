@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define M3_ABI_VERSION 1
+#define M3_ABI_VERSION 2
 #define M3_PAD_ROWS 256 /* queue padding = M-tile of a CTA pair (cta_group::2) in the grouped GEMM */
 
 typedef void* m3_stream_t; /* cudaStream_t */
@@ -223,6 +223,16 @@ int m3_ffn_bwd_dropout(int dtype, const void* xq, const void* saved, const void*
                        float* dw1, float* db1, float* dw2, float* db2, void* workspace,
                        size_t workspace_bytes, float drop_p, const void* rng_state, m3_stream_t stream);
 
+/* m3_ffn_bwd(_dropout) in two halves, for callers that run them on different streams: parts = 1 the data gradients
+ * (dxq; the intermediate dz stays in `workspace`), parts = 2 the weight / bias gradients (needs the workspace a parts = 1
+ * call with the same arguments filled), parts = 3 both.  The expert-parallel backward launches the weight gradients on a
+ * side stream so that they run beside the NVLink pull of dxq (m3_ep_dispatch_bwd), which needs the data gradients only. */
+int m3_ffn_bwd_parts(int dtype, const void* xq, const void* saved, const void* dyq, const int32_t* counts,
+                     const int32_t* offsets, const int32_t* tile_expert, int cap_rows, int E, int D, int H,
+                     const void* w1, const void* w2, const void* w1t, const void* w2t, void* dxq, float* dw1,
+                     float* db1, float* dw2, float* db2, void* workspace, size_t workspace_bytes,
+                     float drop_p, const void* rng_state, int parts, m3_stream_t stream);
+
 /* fp32 master weights [E,R,C] -> bf16 copy [E,R,C] and (optional) bf16 transpose [E,C,R]. */
 int m3_cast_weights_bf16(const float* w, int E, int R, int C, void* w_bf16, void* wt_bf16,
                          m3_stream_t stream);
@@ -252,9 +262,34 @@ int m3_cast_weights_bf16(const float* w, int E, int R, int C, void* w_bf16, void
 int m3_ep_plan(const int64_t* idx, const int32_t* pos_local, const int32_t* cnt_all, int rank, int W,
                int E_loc, int T, int K, int pad, int cap_rows, int32_t* dst_rank, int32_t* dst_row,
                int32_t* recv_counts, int32_t* recv_offsets, int32_t* recv_tile_expert,
-               int32_t* overflow_flag, m3_stream_t stream);
+               int32_t* overflow_flag, int32_t* pos_id, m3_stream_t stream);
+/* pos_id[T*K] (may be NULL): s for a live slot, -1 for a dropped one - the "queue position" of slot s in a
+ * slot-ordered return buffer (m3_ep_ffn_fwd below), to be handed to m3_combine_fwd / m3_dispatch_bwd.
+ *
+ * peer_meta[W] (may be NULL): base of every rank's int32 row-origin array [cap_rows]; the push also records
+ * meta[dst_row] = (rank << 24) | slot at the owner (needs T*K <= 2^24), which is what the return store needs. */
 int m3_ep_dispatch_fwd(const void* x, int x_dtype, const int32_t* dst_rank, const int32_t* dst_row,
-                       int T, int K, int D, void* const* peer_xq, int xq_dtype, m3_stream_t stream);
+                       int T, int K, int D, void* const* peer_xq, int xq_dtype, void* const* peer_meta,
+                       int rank, m3_stream_t stream);
+/* The expert FFN FUSED WITH THE RETURN HALF OF THE ALL-TO-ALL (bf16 / tcgen05 path only).  Same arithmetic as
+ * m3_ffn_fwd_dropout / m3_ffn_bwd_parts over this rank's receive queue, but the epilogue of the LAST GEMM (fc2 in the
+ * forward, dxq = dz W1 in the backward) stores every result row straight into the SOURCE rank's slot-ordered return
+ * buffer over NVLink - row r goes to peer_ret[meta[r] >> 24] + (meta[r] & 0xffffff) * D, rows with meta[r] < 0
+ * (padding) go nowhere - so the exchange that FastMoE runs as a separate global_gather after the expert GEMM
+ * (fmoe MOEGather, reached from models/moe/origin/custom_moe_layer.py:255-257) overlaps the GEMM tile by tile and no
+ * result queue exists on the owner.  After a rendezvous the source combines its return buffer locally
+ * (m3_combine_fwd / m3_dispatch_bwd with pos = pos_id).
+ *   ret_meta[cap_rows]  row origins written by the sources' m3_ep_dispatch_fwd (+ m3_zero_pad_rows for padding rows)
+ *   peer_yret / peer_dxret[W]  device array: every rank's [T*K, D] bf16 return buffer */
+int m3_ep_ffn_fwd(int dtype, const void* xq, const int32_t* offsets, const int32_t* tile_expert, int cap_rows,
+                  int E, int D, int H, const void* w1, const float* b1, const void* w2, const float* b2,
+                  void* saved, const int32_t* ret_meta, void* const* peer_yret, void* workspace,
+                  size_t workspace_bytes, float drop_p, const void* rng_state, m3_stream_t stream);
+int m3_ep_ffn_bwd(int dtype, const void* xq, const void* saved, const void* dyq, const int32_t* counts,
+                  const int32_t* offsets, const int32_t* tile_expert, int cap_rows, int E, int D, int H,
+                  const void* w1, const void* w2, const void* w1t, const void* w2t, const int32_t* ret_meta,
+                  void* const* peer_dxret, float* dw1, float* db1, float* dw2, float* db2, void* workspace,
+                  size_t workspace_bytes, float drop_p, const void* rng_state, int parts, m3_stream_t stream);
 /* ysave [T*K, D] (queue dtype, may be NULL): m3_ep_combine_fwd keeps a LOCAL copy, in slot order, of
  * the result rows it pulls over NVLink; given to m3_ep_combine_bwd, dscore = <g, y> is computed from
  * that copy and the backward pass only PUSHES dyq (peer_yq may then be NULL). */
@@ -268,8 +303,9 @@ int m3_ep_combine_bwd(const void* g, int g_dtype, void* const* peer_yq, void* co
 int m3_ep_dispatch_bwd(void* const* peer_dxq, int dxq_dtype, const int32_t* dst_rank,
                        const int32_t* dst_row, int T, int K, int D, const float* dz,
                        const float* w_gate, int E, void* dx, int dx_dtype, m3_stream_t stream);
+/* zeroes the padding rows of a receive queue; meta (may be NULL): also marks them -1 in the row-origin array */
 int m3_zero_pad_rows(void* q, int dtype, const int32_t* counts, const int32_t* offsets, int E, int D,
-                     m3_stream_t stream);
+                     int32_t* meta, m3_stream_t stream);
 /* Device-side rendezvous of the W ranks over peer memory (replaces an NCCL barrier / the
  * fmoe expert_exchange count all-to-all): a 1-warp kernel stores `epoch` into slot `rank` of every
  * peer's flag array (system-scope release) and, if `payload` != NULL, first copies `payload_ints`

@@ -50,15 +50,20 @@ SIGNATURES = {
     "m3_ffn_fwd": (_i, [_i, _p, _p, _p, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _sz, _p]),
     "m3_ffn_fwd_dropout": (_i, [_i, _p, _p, _p, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _sz, _f, _p, _p]),
     "m3_ffn_bwd": (_i, [_i, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _sz, _p]),
+    "m3_ffn_bwd_parts": (_i, [_i, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _sz, _f,
+                              _p, _i, _p]),
     "m3_ffn_bwd_dropout": (_i, [_i, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _sz, _f,
                                 _p, _p]),
     "m3_cast_weights_bf16": (_i, [_p, _i, _i, _i, _p, _p, _p]),
-    "m3_ep_plan": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p]),
-    "m3_ep_dispatch_fwd": (_i, [_p, _i, _p, _p, _i, _i, _i, _p, _i, _p]),
+    "m3_ep_plan": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p]),
+    "m3_ep_dispatch_fwd": (_i, [_p, _i, _p, _p, _i, _i, _i, _p, _i, _p, _i, _p]),
+    "m3_ep_ffn_fwd": (_i, [_i, _p, _p, _p, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p, _sz, _f, _p, _p]),
+    "m3_ep_ffn_bwd": (_i, [_i, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _sz, _f,
+                           _p, _i, _p]),
     "m3_ep_combine_fwd": (_i, [_p, _i, _p, _p, _p, _i, _i, _i, _p, _i, _p, _p]),
     "m3_ep_combine_bwd": (_i, [_p, _i, _p, _p, _i, _p, _p, _p, _i, _i, _i, _p, _p, _p]),
     "m3_ep_dispatch_bwd": (_i, [_p, _i, _p, _p, _i, _i, _i, _p, _p, _i, _p, _i, _p]),
-    "m3_zero_pad_rows": (_i, [_p, _i, _p, _p, _i, _i, _p]),
+    "m3_zero_pad_rows": (_i, [_p, _i, _p, _p, _i, _i, _p, _p]),
     "m3_ep_barrier": (_i, [_p, _p, _p, _i, _i, _i, _i, _p]),
     "m3_ln_stats": (_i, [_p, _i, _i, _f, _p, _p, _p]),
     "m3_ln_fold_gate": (_i, [_p, _p, _p, _i, _i, _i, _p, _p, _p]),
@@ -98,7 +103,7 @@ def load() -> C.CDLL:
         fn = getattr(lib, name)          # AttributeError => header/library mismatch: fail loudly
         fn.restype = res
         fn.argtypes = args
-    if lib.m3_abi_version() != 1:
+    if lib.m3_abi_version() != 2:
         raise M3Error("libm3vit_moe.so ABI version mismatch")
     # tuning knobs from the environment, e.g. M3_KNOBS="0=1,3=2" (m3_set_knob(knob, value); include/m3vit_moe.h)
     for kv in filter(None, os.environ.get("M3_KNOBS", "").split(",")):

@@ -12,18 +12,20 @@ int m3_ffn_fwd_f32(const float* xq, const int32_t* offsets, const int32_t* tile_
 int m3_ffn_bwd_f32(const float* xq, const float* hpre, const float* dyq, const int32_t* counts,
                    const int32_t* offsets, const int32_t* tile_expert, int cap_rows, int E, int D, int H,
                    const float* w1, const float* w2, float* dxq, float* dw1, float* db1, float* dw2, float* db2,
-                   void* workspace, size_t workspace_bytes, float drop_p, const void* rng, cudaStream_t st);
+                   void* workspace, size_t workspace_bytes, float drop_p, const void* rng, int parts, cudaStream_t st);
 size_t m3_ffn_bf16_workspace_bytes(int cap_rows, int D, int H, int E, int backward);
 size_t m3_ffn_bf16_saved_bytes(int cap_rows, int D, int H);
 int m3_ffn_bf16_chain_mode(int D, int H);
 int m3_ffn_bf16_set_sm_limit(int sms);
 int m3_ffn_fwd_bf16(const void* xq, const int32_t* offsets, const int32_t* tile_expert, int cap_rows, int E, int D,
                     int H, const void* w1, const float* b1, const void* w2, const float* b2, void* hpre, void* yq,
-                    void* workspace, size_t workspace_bytes, float drop_p, const void* rng, cudaStream_t st);
+                    void* workspace, size_t workspace_bytes, float drop_p, const void* rng, const int32_t* ret_meta,
+                    void* const* ret_bases, cudaStream_t st);
 int m3_ffn_bwd_bf16(const void* xq, const void* hpre, const void* dyq, const int32_t* counts,
                     const int32_t* offsets, const int32_t* tile_expert, int cap_rows, int E, int D, int H,
                     const void* w1, const void* w2, const void* w1t, const void* w2t, void* dxq, float* dw1,
-                    float* db1, float* dw2, float* db2, void* workspace, size_t workspace_bytes, cudaStream_t st);
+                    float* db1, float* dw2, float* db2, void* workspace, size_t workspace_bytes, int parts,
+                    const int32_t* ret_meta, void* const* ret_bases, cudaStream_t st);
 
 extern "C" int m3_abi_version(void) { return M3_ABI_VERSION; }
 
@@ -95,13 +97,16 @@ extern "C" int m3_ffn_uses_chain(int dtype, int D, int H) {
 static int ffn_fwd_impl(int dtype, const void* xq, const int32_t* offsets, const int32_t* tile_expert, int cap_rows,
                         int E, int D, int H, const void* w1, const float* b1, const void* w2, const float* b2,
                         void* hpre, void* yq, void* workspace, size_t workspace_bytes, float drop_p, const void* rng,
-                        m3_stream_t stream) {
+                        const int32_t* ret_meta, void* const* ret_bases, m3_stream_t stream) {
   M3_CHECK_ARG(drop_p >= 0.f && drop_p < 1.f);
   if (rng) M3_CHECK_ALIGN16(rng);
-  M3_CHECK_ARG(xq && offsets && tile_expert && w1 && b1 && w2 && b2 && yq);
+  M3_CHECK_ARG(xq && offsets && tile_expert && w1 && b1 && w2 && b2 && (yq || ret_meta));
+  M3_CHECK_ARG((ret_meta == nullptr) == (ret_bases == nullptr));
+  if (ret_meta && dtype != M3_BF16) return M3_ERR_UNSUPPORTED;      // the return store lives in the tcgen05 epilogue
   M3_CHECK_ARG(cap_rows >= 0 && E >= 1 && D > 0 && H > 0);
   M3_CHECK_SHAPE(cap_rows % M3_PAD_ROWS == 0);
-  M3_CHECK_ALIGN16(xq); M3_CHECK_ALIGN16(yq); M3_CHECK_ALIGN16(w1); M3_CHECK_ALIGN16(w2);
+  M3_CHECK_ALIGN16(xq); M3_CHECK_ALIGN16(w1); M3_CHECK_ALIGN16(w2);
+  if (yq) M3_CHECK_ALIGN16(yq);
   M3_CHECK_ALIGN16(b1); M3_CHECK_ALIGN16(b2);
   if (hpre) M3_CHECK_ALIGN16(hpre);
   if (workspace) M3_CHECK_ALIGN16(workspace);
@@ -112,7 +117,7 @@ static int ffn_fwd_impl(int dtype, const void* xq, const int32_t* offsets, const
                           (const float*)w2, b2, (float*)hpre, (float*)yq, workspace, workspace_bytes, drop_p, rng, st);
   if (dtype == M3_BF16)
     return m3_ffn_fwd_bf16(xq, offsets, tile_expert, cap_rows, E, D, H, w1, b1, w2, b2, hpre, yq, workspace,
-                           workspace_bytes, drop_p, rng, st);
+                           workspace_bytes, drop_p, rng, ret_meta, ret_bases, st);
   return M3_ERR_UNSUPPORTED;
 }
 
@@ -120,7 +125,7 @@ extern "C" int m3_ffn_fwd(int dtype, const void* xq, const int32_t* offsets, con
                           int E, int D, int H, const void* w1, const float* b1, const void* w2, const float* b2,
                           void* hpre, void* yq, void* workspace, size_t workspace_bytes, m3_stream_t stream) {
   return ffn_fwd_impl(dtype, xq, offsets, tile_expert, cap_rows, E, D, H, w1, b1, w2, b2, hpre, yq, workspace,
-                      workspace_bytes, 0.f, nullptr, stream);
+                      workspace_bytes, 0.f, nullptr, nullptr, nullptr, stream);
 }
 
 extern "C" int m3_ffn_fwd_dropout(int dtype, const void* xq, const int32_t* offsets, const int32_t* tile_expert,
@@ -128,16 +133,28 @@ extern "C" int m3_ffn_fwd_dropout(int dtype, const void* xq, const int32_t* offs
                                   const float* b2, void* saved, void* yq, void* workspace, size_t workspace_bytes,
                                   float drop_p, const void* rng_state, m3_stream_t stream) {
   return ffn_fwd_impl(dtype, xq, offsets, tile_expert, cap_rows, E, D, H, w1, b1, w2, b2, saved, yq, workspace,
-                      workspace_bytes, drop_p, rng_state, stream);
+                      workspace_bytes, drop_p, rng_state, nullptr, nullptr, stream);
+}
+
+extern "C" int m3_ep_ffn_fwd(int dtype, const void* xq, const int32_t* offsets, const int32_t* tile_expert, int cap_rows,
+                             int E, int D, int H, const void* w1, const float* b1, const void* w2, const float* b2,
+                             void* saved, const int32_t* ret_meta, void* const* peer_yret, void* workspace,
+                             size_t workspace_bytes, float drop_p, const void* rng_state, m3_stream_t stream) {
+  M3_CHECK_ARG(ret_meta && peer_yret);
+  return ffn_fwd_impl(dtype, xq, offsets, tile_expert, cap_rows, E, D, H, w1, b1, w2, b2, saved, nullptr, workspace,
+                      workspace_bytes, drop_p, rng_state, ret_meta, peer_yret, stream);
 }
 
 static int ffn_bwd_impl(int dtype, const void* xq, const void* hpre, const void* dyq, const int32_t* counts,
                         const int32_t* offsets, const int32_t* tile_expert, int cap_rows, int E, int D, int H,
                         const void* w1, const void* w2, const void* w1t, const void* w2t, void* dxq, float* dw1,
                         float* db1, float* dw2, float* db2, void* workspace, size_t workspace_bytes, float drop_p,
-                        const void* rng, m3_stream_t stream) {
-  M3_CHECK_ARG(drop_p >= 0.f && drop_p < 1.f);
-  M3_CHECK_ARG(xq && hpre && dyq && counts && offsets && tile_expert && w1 && w2 && dxq && dw1 && db1 && dw2 && db2);
+                        const void* rng, int parts, const int32_t* ret_meta, void* const* ret_bases,
+                        m3_stream_t stream) {
+  M3_CHECK_ARG(drop_p >= 0.f && drop_p < 1.f && parts >= 1 && parts <= 3);
+  M3_CHECK_ARG(xq && hpre && dyq && counts && offsets && tile_expert && w1 && w2 && (dxq || ret_meta) && dw1 && db1 && dw2 && db2);
+  M3_CHECK_ARG((ret_meta == nullptr) == (ret_bases == nullptr));
+  if (ret_meta && dtype != M3_BF16) return M3_ERR_UNSUPPORTED;
   M3_CHECK_ARG(cap_rows >= 0 && E >= 1 && D > 0 && H > 0 && workspace);
   M3_CHECK_SHAPE(cap_rows % M3_PAD_ROWS == 0);
   M3_CHECK_ALIGN16(xq); M3_CHECK_ALIGN16(hpre); M3_CHECK_ALIGN16(dyq); M3_CHECK_ALIGN16(dxq);
@@ -147,12 +164,12 @@ static int ffn_bwd_impl(int dtype, const void* xq, const void* hpre, const void*
   if (dtype == M3_F32)
     return m3_ffn_bwd_f32((const float*)xq, (const float*)hpre, (const float*)dyq, counts, offsets, tile_expert,
                           cap_rows, E, D, H, (const float*)w1, (const float*)w2, (float*)dxq, dw1, db1, dw2, db2,
-                          workspace, workspace_bytes, drop_p, rng, st);
+                          workspace, workspace_bytes, drop_p, rng, parts, st);
   if (dtype == M3_BF16) {
     M3_CHECK_ARG(w1t && w2t);
     // bf16: the saved planes already carry the forward's keep-scale (h = m gelu(z), m gelu'(z)): nothing to regenerate
     return m3_ffn_bwd_bf16(xq, hpre, dyq, counts, offsets, tile_expert, cap_rows, E, D, H, w1, w2, w1t, w2t, dxq,
-                           dw1, db1, dw2, db2, workspace, workspace_bytes, st);
+                           dw1, db1, dw2, db2, workspace, workspace_bytes, parts, ret_meta, ret_bases, st);
   }
   return M3_ERR_UNSUPPORTED;
 }
@@ -163,7 +180,27 @@ extern "C" int m3_ffn_bwd(int dtype, const void* xq, const void* hpre, const voi
                           float* db1, float* dw2, float* db2, void* workspace, size_t workspace_bytes,
                           m3_stream_t stream) {
   return ffn_bwd_impl(dtype, xq, hpre, dyq, counts, offsets, tile_expert, cap_rows, E, D, H, w1, w2, w1t, w2t, dxq, dw1,
-                      db1, dw2, db2, workspace, workspace_bytes, 0.f, nullptr, stream);
+                      db1, dw2, db2, workspace, workspace_bytes, 0.f, nullptr, 3, nullptr, nullptr, stream);
+}
+
+extern "C" int m3_ffn_bwd_parts(int dtype, const void* xq, const void* saved, const void* dyq, const int32_t* counts,
+                                const int32_t* offsets, const int32_t* tile_expert, int cap_rows, int E, int D, int H,
+                                const void* w1, const void* w2, const void* w1t, const void* w2t, void* dxq, float* dw1,
+                                float* db1, float* dw2, float* db2, void* workspace, size_t workspace_bytes,
+                                float drop_p, const void* rng_state, int parts, m3_stream_t stream) {
+  return ffn_bwd_impl(dtype, xq, saved, dyq, counts, offsets, tile_expert, cap_rows, E, D, H, w1, w2, w1t, w2t, dxq, dw1,
+                      db1, dw2, db2, workspace, workspace_bytes, drop_p, rng_state, parts, nullptr, nullptr, stream);
+}
+
+extern "C" int m3_ep_ffn_bwd(int dtype, const void* xq, const void* saved, const void* dyq, const int32_t* counts,
+                             const int32_t* offsets, const int32_t* tile_expert, int cap_rows, int E, int D, int H,
+                             const void* w1, const void* w2, const void* w1t, const void* w2t, const int32_t* ret_meta,
+                             void* const* peer_dxret, float* dw1, float* db1, float* dw2, float* db2, void* workspace,
+                             size_t workspace_bytes, float drop_p, const void* rng_state, int parts, m3_stream_t stream) {
+  M3_CHECK_ARG(ret_meta && peer_dxret);
+  return ffn_bwd_impl(dtype, xq, saved, dyq, counts, offsets, tile_expert, cap_rows, E, D, H, w1, w2, w1t, w2t, nullptr,
+                      dw1, db1, dw2, db2, workspace, workspace_bytes, drop_p, rng_state, parts, ret_meta, peer_dxret,
+                      stream);
 }
 
 extern "C" int m3_ffn_bwd_dropout(int dtype, const void* xq, const void* saved, const void* dyq, const int32_t* counts,
@@ -172,7 +209,7 @@ extern "C" int m3_ffn_bwd_dropout(int dtype, const void* xq, const void* saved, 
                                   float* dw1, float* db1, float* dw2, float* db2, void* workspace,
                                   size_t workspace_bytes, float drop_p, const void* rng_state, m3_stream_t stream) {
   return ffn_bwd_impl(dtype, xq, saved, dyq, counts, offsets, tile_expert, cap_rows, E, D, H, w1, w2, w1t, w2t, dxq, dw1,
-                      db1, dw2, db2, workspace, workspace_bytes, drop_p, rng_state, stream);
+                      db1, dw2, db2, workspace, workspace_bytes, drop_p, rng_state, 3, nullptr, nullptr, stream);
 }
 
 
@@ -206,7 +243,8 @@ __global__ void ep_plan_kernel(const int64_t* __restrict__ idx, const int32_t* _
                                const int32_t* __restrict__ cnt_all, int rank, int W, int E_loc, int R, int pad,
                                int cap_rows, int32_t* __restrict__ dst_rank, int32_t* __restrict__ dst_row,
                                int32_t* __restrict__ recv_counts, int32_t* __restrict__ recv_offsets,
-                               int32_t* __restrict__ recv_tile_expert, int32_t* __restrict__ overflow_flag) {
+                               int32_t* __restrict__ recv_tile_expert, int32_t* __restrict__ overflow_flag,
+                               int32_t* __restrict__ pos_id) {
   extern __shared__ int sm[];
   const int E_tot = W * E_loc;
   int* loc_off = sm;            // [E_tot] exclusive prefix of this rank's counts (pad 1)
@@ -241,14 +279,20 @@ __global__ void ep_plan_kernel(const int64_t* __restrict__ idx, const int32_t* _
   for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < R; s += gridDim.x * blockDim.x) {
     const int64_t ge = idx[s];
     const int p = pos_local[s];
-    if (ge < 0 || ge >= E_tot || p < 0) { dst_rank[s] = 0; dst_row[s] = -1; continue; }
+    if (ge < 0 || ge >= E_tot || p < 0) {
+      dst_rank[s] = 0; dst_row[s] = -1;
+      if (pos_id != nullptr) pos_id[s] = -1;
+      continue;
+    }
     const int row = base[ge] + (p - loc_off[ge]);
     dst_rank[s] = (int)(ge / E_loc);
     if (row >= cap_rows) {           // receive queue too small: drop the slot, tell the host
       dst_row[s] = -1;
       if (overflow_flag != nullptr) *overflow_flag = 1;
+      if (pos_id != nullptr) pos_id[s] = -1;
     } else {
       dst_row[s] = row;
+      if (pos_id != nullptr) pos_id[s] = s;      // return buffers are in slot order: row of slot s = s
     }
   }
   if (blockIdx.x == 0) {
@@ -333,7 +377,7 @@ extern "C" int m3_cast_weights_bf16(const float* w, int E, int R, int C, void* w
 extern "C" int m3_ep_plan(const int64_t* idx, const int32_t* pos_local, const int32_t* cnt_all, int rank, int W,
                           int E_loc, int T, int K, int pad, int cap_rows, int32_t* dst_rank, int32_t* dst_row,
                           int32_t* recv_counts, int32_t* recv_offsets, int32_t* recv_tile_expert,
-                          int32_t* overflow_flag, m3_stream_t stream) {
+                          int32_t* overflow_flag, int32_t* pos_id, m3_stream_t stream) {
   M3_CHECK_ARG(idx && pos_local && cnt_all && dst_rank && dst_row && recv_counts && recv_offsets && recv_tile_expert);
   M3_CHECK_ARG(W >= 1 && rank >= 0 && rank < W && E_loc >= 1 && T >= 0 && K >= 1 && pad >= 1 && cap_rows >= 0);
   M3_CHECK_SHAPE(W * E_loc <= 1024);
@@ -343,7 +387,7 @@ extern "C" int m3_ep_plan(const int64_t* idx, const int32_t* pos_local, const in
   if (grid > 2 * m3::kNumSMs) grid = 2 * m3::kNumSMs;
   m3::ep_plan_kernel<<<grid, 256, 3 * W * E_loc * sizeof(int), static_cast<cudaStream_t>(stream)>>>(
       idx, pos_local, cnt_all, rank, W, E_loc, R, pad, cap_rows, dst_rank, dst_row, recv_counts, recv_offsets,
-      recv_tile_expert, overflow_flag);
+      recv_tile_expert, overflow_flag, pos_id);
   M3_LAUNCH_CHECK();
   return M3_OK;
 }

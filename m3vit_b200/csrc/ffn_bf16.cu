@@ -57,6 +57,12 @@ struct GGParams {
   uint32_t drop_thr;           // p * 2^32 (0 = no dropout)
   float drop_inv_keep;         // 1 / (1 - p)
   const RngState* rng;
+  // Expert parallel, EPI_BIAS / EPI_STORE ("return store"): the output row of queue row r does not go to out[r] but straight
+  // to the rank the row came from, over NVLink, from this epilogue: ret_meta[r] = (source rank << 24) | slot (or -1: padding
+  // row, nothing stored), destination = ret_bases[source rank] + slot * N.  The exchange that FastMoE runs as a separate
+  // global_gather after the expert GEMM overlaps the GEMM tile by tile; see m3_ep_ffn_fwd in the header.
+  const int32_t* ret_meta;     // [rows] or nullptr
+  __nv_bfloat16* const* ret_bases;   // [W] peer-mapped [T*K][N] return buffers
 };
 
 template <int BN, int EPI, int NCTA, int EW, int CWP>
@@ -291,6 +297,20 @@ gg_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
       }
       __syncwarp();
     };
+    // return store (expert parallel): every lane carries the destination of ITS row of the warp's 32-row quarter
+    auto flush_ret = [&](unsigned long long rowdst, int col) {
+      __syncwarp();
+#pragma unroll
+      for (int i = 0; i < NCH; ++i) {
+        const int rr = i * (32 / NCH) + lane / NCH, ch = lane % NCH;
+        const uint4 u = lds128(box + box_off<CW>(rr, ch));
+        const unsigned long long d = __shfl_sync(0xffffffffu, rowdst, rr);
+        if (d != 0ull) stg_stream(reinterpret_cast<__nv_bfloat16*>(d) + col + ch * 8, u);
+      }
+      __syncwarp();
+    };
+    constexpr bool kCanRet = (EPI == EPI_BIAS || EPI == EPI_STORE);
+    const bool ret = kCanRet && p.ret_meta != nullptr;
     uint32_t aux_uses = 0;
     const uint32_t tempty_remote = NCTA == 2 ? mapa_u32(smem_u32(&tempty[grp]), 0) : 0u;
     if (EPI == EPI_DGELU && lane == 0 && (int)grp < my_tiles) {
@@ -301,6 +321,12 @@ gg_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
       const int m_blk = tile_mblk(it), n_blk = tile_nblk(it);
       const int e = p.tile_expert[(m_blk * BM) / M3_PAD_ROWS];
       const int row0 = m_blk * BM + q * 32;
+      unsigned long long rowdst = 0ull;
+      if (kCanRet && ret) {
+        const int meta = __ldg(p.ret_meta + row0 + lane);
+        if (meta >= 0)
+          rowdst = reinterpret_cast<unsigned long long>(p.ret_bases[meta >> 24] + (int64_t)(meta & 0xffffff) * p.N);
+      }
       if (ew == 0) trc.ev(0x20, it);
       mbar_wait(&tfull[grp], (it >> 1) & 1);
       if (ew == 0) trc.ev(0x21, it);
@@ -405,7 +431,8 @@ gg_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
           u.z = pack_bf16x2(w2[4 * c + 2]); u.w = pack_bf16x2(w2[4 * c + 3]);
           sts128(box + box_off<CW>(lane, c), u);
         }
-        flush(p.out, row0, col);
+        if (kCanRet && ret) flush_ret(rowdst, col);
+        else flush(p.out, row0, col);
         if (ew == 0) trc.ev(0x23, cbi);
       }
     }
@@ -835,11 +862,13 @@ size_t m3_ffn_bf16_workspace_bytes(int cap_rows, int D, int H, int E, int backwa
 
 int m3_ffn_fwd_bf16(const void* xq, const int32_t* offsets, const int32_t* tile_expert, int cap_rows, int E, int D,
                     int H, const void* w1, const float* b1, const void* w2, const float* b2, void* saved, void* yq,
-                    void* workspace, size_t workspace_bytes, float drop_p, const void* rng, cudaStream_t st) {
+                    void* workspace, size_t workspace_bytes, float drop_p, const void* rng, const int32_t* ret_meta,
+                    void* const* ret_bases, cudaStream_t st) {
   if (drop_p > 0.f && (saved == nullptr || rng == nullptr)) return M3_ERR_ARG;     // dropout is a training-time op
+  if ((ret_meta == nullptr) != (ret_bases == nullptr) || (ret_meta == nullptr && yq == nullptr)) return M3_ERR_ARG;
   if (workspace == nullptr || workspace_bytes < m3_ffn_bf16_workspace_bytes(cap_rows, D, H, E, 0)) return M3_ERR_WORKSPACE;
   g_trace_launch_idx = 0;
-  if (saved == nullptr && chain_inference(D, H))
+  if (saved == nullptr && ret_meta == nullptr && chain_inference(D, H))
     return m3_ffn_chain_fwd(xq, offsets, tile_expert, cap_rows, E, D, H, w1, b1, w2, b2, yq, g_gemm_sms, st);
   const size_t hbytes = align256((size_t)cap_rows * H * 2);
   bf16* gp = static_cast<bf16*>(saved);
@@ -857,14 +886,17 @@ int m3_ffn_fwd_bf16(const void* xq, const int32_t* offsets, const int32_t* tile_
   if (rc) return rc;
   // fc2: yq = h W2^T + b2
   p.N = D; p.Kd = H; p.bias = b2; p.save_out2 = 0; p.drop_thr = 0u;
-  return launch_gg<EPI_BIAS>(h, w2, yq, nullptr, nullptr, p, cap_rows, st);
+  p.ret_meta = ret_meta; p.ret_bases = reinterpret_cast<bf16* const*>(ret_bases);      // expert parallel: rows go home
+  return launch_gg<EPI_BIAS>(h, w2, ret_meta ? static_cast<void*>(h) : yq, nullptr, nullptr, p, cap_rows, st);
 }
 
 int m3_ffn_bwd_bf16(const void* xq, const void* saved, const void* dyq, const int32_t* counts, const int32_t* offsets,
                     const int32_t* tile_expert, int cap_rows, int E, int D, int H, const void* w1, const void* w2,
                     const void* w1t, const void* w2t, void* dxq, float* dw1, float* db1, float* dw2, float* db2,
-                    void* workspace, size_t workspace_bytes, cudaStream_t st) {
+                    void* workspace, size_t workspace_bytes, int parts, const int32_t* ret_meta, void* const* ret_bases,
+                    cudaStream_t st) {
   (void)counts; (void)w1; (void)w2;
+  if ((ret_meta == nullptr) != (ret_bases == nullptr) || (ret_meta == nullptr && dxq == nullptr)) return M3_ERR_ARG;
   if (workspace_bytes < m3_ffn_bf16_workspace_bytes(cap_rows, D, H, E, 1)) return M3_ERR_WORKSPACE;
   g_trace_launch_idx = 0;
   const size_t hbytes = align256((size_t)cap_rows * H * 2);
@@ -872,8 +904,8 @@ int m3_ffn_bwd_bf16(const void* xq, const void* saved, const void* dyq, const in
   float* part = reinterpret_cast<float*>(static_cast<uint8_t*>(workspace) + 2 * hbytes);
   const bf16* h;
   int rc;
-  {
-    h = reinterpret_cast<const bf16*>(static_cast<const uint8_t*>(saved) + hbytes);
+  h = reinterpret_cast<const bf16*>(static_cast<const uint8_t*>(saved) + hbytes);
+  if (parts & 1) {      // data gradients: dz (kept in the workspace for the weight-gradient part) and dxq
     GGParams p{};
     p.offsets = offsets; p.tile_expert = tile_expert; p.E = E;
     // dz = (dyq W2) * gelu'(z)                              B = W2^T [E][H][D] (K-major in D)
@@ -882,9 +914,11 @@ int m3_ffn_bwd_bf16(const void* xq, const void* saved, const void* dyq, const in
     if (rc) return rc;
     // dxq = dz W1                                           B = W1^T [E][D][H] (K-major in H)
     p.N = D; p.Kd = H;
-    rc = launch_gg<EPI_STORE>(dz, w1t, dxq, nullptr, nullptr, p, cap_rows, st);
+    p.ret_meta = ret_meta; p.ret_bases = reinterpret_cast<bf16* const*>(ret_bases);    // expert parallel: rows go home
+    rc = launch_gg<EPI_STORE>(dz, w1t, ret_meta ? static_cast<void*>(dz) : dxq, nullptr, nullptr, p, cap_rows, st);
     if (rc) return rc;
   }
+  if (!(parts & 2)) return M3_OK;
   // dW2[e] = dyq_e^T h_e  [D][H];   dW1[e] = dz_e^T xq_e  [H][D]
   // the bias gradients ride along in the same MMA against a tile of ones
   rc = launch_wgrad(dyq, h, offsets, cap_rows, E, D, H, dw2, db2, part, st);

@@ -197,7 +197,7 @@ int m3_ffn_fwd_f32(const float* xq, const int32_t* offsets, const int32_t* tile_
 int m3_ffn_bwd_f32(const float* xq, const float* hpre, const float* dyq, const int32_t* counts,
                    const int32_t* offsets, const int32_t* tile_expert, int cap_rows, int E, int D, int H,
                    const float* w1, const float* w2, float* dxq, float* dw1, float* db1, float* dw2, float* db2,
-                   void* workspace, size_t workspace_bytes, float drop_p, const void* rng, cudaStream_t st) {
+                   void* workspace, size_t workspace_bytes, float drop_p, const void* rng, int parts, cudaStream_t st) {
   M3_CHECK_SHAPE(D % BN == 0 && H % BN == 0 && cap_rows % BM == 0);
   if (drop_p > 0.f && rng == nullptr) return M3_ERR_ARG;
   if (workspace_bytes < (size_t)cap_rows * H * sizeof(float)) return M3_ERR_WORKSPACE;
@@ -209,14 +209,17 @@ int m3_ffn_bwd_f32(const float* xq, const float* hpre, const float* dyq, const i
     p.drop_inv_keep = 1.0f / (1.0f - drop_p);
     p.rng = static_cast<const RngState*>(rng);
   }
-  // dhpre = (dyq W2) * gelu'(hpre)                     [rows, D] x [D, H]
-  p.A = dyq; p.B = w2; p.C = dhpre; p.aux = hpre; p.N = H; p.Kdim = D;
-  sgemm_grouped_kernel<LAY_NN, EPI_GELU_GRAD, false><<<dim3(cap_rows / BM, H / BN), SG_THREADS, 0, st>>>(p);
-  M3_LAUNCH_CHECK();
-  // dxq = dhpre W1                                     [rows, H] x [H, D]
-  p.A = dhpre; p.B = w1; p.C = dxq; p.aux = nullptr; p.N = D; p.Kdim = H;
-  sgemm_grouped_kernel<LAY_NN, EPI_NONE, false><<<dim3(cap_rows / BM, D / BN), SG_THREADS, 0, st>>>(p);
-  M3_LAUNCH_CHECK();
+  if (parts & 1) {      // data gradients (dhpre stays in the workspace for the weight-gradient part)
+    // dhpre = (dyq W2) * gelu'(hpre)                     [rows, D] x [D, H]
+    p.A = dyq; p.B = w2; p.C = dhpre; p.aux = hpre; p.N = H; p.Kdim = D;
+    sgemm_grouped_kernel<LAY_NN, EPI_GELU_GRAD, false><<<dim3(cap_rows / BM, H / BN), SG_THREADS, 0, st>>>(p);
+    M3_LAUNCH_CHECK();
+    // dxq = dhpre W1                                     [rows, H] x [H, D]
+    p.A = dhpre; p.B = w1; p.C = dxq; p.aux = nullptr; p.N = D; p.Kdim = H;
+    sgemm_grouped_kernel<LAY_NN, EPI_NONE, false><<<dim3(cap_rows / BM, D / BN), SG_THREADS, 0, st>>>(p);
+    M3_LAUNCH_CHECK();
+  }
+  if (!(parts & 2)) return M3_OK;
   // dW2[e] = dyq_e^T gelu(hpre_e)                      [D, H]
   p.A = dyq; p.B = hpre; p.C = dw2; p.M = D; p.N = H;
   sgemm_grouped_kernel<LAY_TN, EPI_NONE, true><<<dim3(D / BM, H / BN, E), SG_THREADS, 0, st>>>(p);

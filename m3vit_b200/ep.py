@@ -16,6 +16,13 @@ world_size > 1) is replaced by peer-mapped expert queues:
     the combine kernel LOADS result rows from the owners (and keeps a local copy for backward);
   * backward: combine_bwd pushes dyq (dscore from the local copy), dispatch_bwd pulls dxq.
     Expert weight gradients need no reduction (each expert's rows are all on its owner).
+  * bf16 (the tcgen05 path), default: the RETURN half of both exchanges is fused into the expert GEMMs
+    ("return store", m3_ep_ffn_fwd / m3_ep_ffn_bwd): the push also records every row's origin
+    (source rank, slot) at the owner, and the epilogue of fc2 (forward) / of dxq = dz W1 (backward) stores each
+    result row straight into the source rank's slot-ordered return buffer over NVLink, tile by tile, while the
+    tensor cores work on the next tile.  No result queue exists on the owner, nothing is pulled; after the
+    rendezvous the source combines its own return buffer with the local kernels.  M3_EP_RETURN=0 (or fp32
+    queues) selects the pull protocol above.
 
 The protocol is written as explicit phases so that it runs either over torch.distributed
 (one process per GPU, NCCL) or as a single-process multi-rank simulation (tests; one GPU
@@ -192,6 +199,12 @@ class EPContext:
         if int(self.overflow.item()) != 0:
             raise RuntimeError("EP receive queue overflow: tokens were dropped; raise capacity_factor")
 
+    def fused_return(self, cdt, T: int, K: int) -> bool:
+        """Return store (module docstring): bf16 queues, row origins packed into 32 bits."""
+        import os
+        return (cdt == torch.bfloat16 and os.environ.get("M3_EP_RETURN", "1") != "0" and self.world < 128
+                and T * K <= (1 << 24))
+
     def poll_overflow(self) -> None:
         """Asynchronous check, run by every layer call: the flag of an EARLIER call is copied to pinned host memory on the
         stream (no synchronisation) and read once that copy has completed - a dropped slot raises at most a few calls
@@ -287,6 +300,13 @@ class EPFwdState:
     hpre: Optional[torch.Tensor] = None
     ysave: Optional[torch.Tensor] = None      # local copy of the pulled result rows [T*K, D]
     nbytes_q: int = 0
+    # return-store protocol (bf16): row origins of my receive queue, my slot-ordered return buffer (= ysave), identity plan
+    ret: bool = False
+    off_meta: int = -1
+    off_yret: int = -1
+    meta: Optional[torch.Tensor] = None
+    pos_id: Optional[torch.Tensor] = None
+    nbytes_ret: int = 0
 
 
 def phase_a_gate(gx, w_gate, top_k, task_feat, noise, noise_stddev, want_gates, E_tot) -> EPFwdState:
@@ -309,18 +329,26 @@ def phase_b_dispatch(ctx: EPContext, st: EPFwdState, x, cnt_all, E_loc, top_k, c
     rc = torch.empty(E_loc, dtype=torch.int32, device=dev)
     ro = torch.empty(E_loc + 1, dtype=torch.int32, device=dev)
     rt = torch.empty(st.cap // PAD_ROWS, dtype=torch.int32, device=dev)
+    st.ret = ctx.fused_return(cdt, T, top_k)
+    st.pos_id = torch.empty(R, dtype=torch.int32, device=dev) if st.ret else None
     check(lib.m3_ep_plan(ptr(st.g.idx), ptr(st.plan_local.pos), ptr(cnt_all), ctx.rank, W, E_loc, T, top_k, PAD_ROWS,
                          st.cap, ptr(st.dst_rank), ptr(st.dst_row), ptr(rc), ptr(ro), ptr(rt), ptr(ctx.overflow),
-                         stream_ptr()), "m3_ep_plan")
+                         ptr(st.pos_id), stream_ptr()), "m3_ep_plan")
     st.recv = ops.Plan(rc, ro, None, rt, st.cap, PAD_ROWS)
     el = 2 if cdt == torch.bfloat16 else 4
     st.nbytes_q = st.cap * D * el
     st.off_xq = ctx.arena.alloc(st.nbytes_q)
     st.xq = ctx.arena.view(st.off_xq, st.cap, D, cdt)
     peers = ctx.peer_ptrs(st.off_xq)
+    peers_meta = None
+    if st.ret:
+        st.nbytes_ret = R * D * el
+        st.off_meta = ctx.arena.alloc(st.cap * 4)
+        st.meta = ctx.arena.view(st.off_meta, st.cap, 1, torch.int32)
+        peers_meta = ctx.peer_ptrs(st.off_meta)
     check(lib.m3_ep_dispatch_fwd(ptr(x), dtype_code(x), ptr(st.dst_rank), ptr(st.dst_row), T, top_k, D, ptr(peers),
-                                 dtype_code(st.xq), stream_ptr()), "m3_ep_dispatch_fwd")
-    check(lib.m3_zero_pad_rows(ptr(st.xq), dtype_code(st.xq), ptr(rc), ptr(ro), E_loc, D, stream_ptr()),
+                                 dtype_code(st.xq), ptr(peers_meta), ctx.rank, stream_ptr()), "m3_ep_dispatch_fwd")
+    check(lib.m3_zero_pad_rows(ptr(st.xq), dtype_code(st.xq), ptr(rc), ptr(ro), E_loc, D, ptr(st.meta), stream_ptr()),
           "m3_zero_pad_rows")
     ops.launch_count += 3
 
@@ -331,11 +359,20 @@ def phase_c_ffn(ctx: EPContext, st: EPFwdState, w1c, b1, w2c, b2, save_hpre: boo
     cap, D = st.xq.shape
     E_loc, H, _ = w1c.shape
     dt = dtype_code(st.xq)
-    st.off_yq = ctx.arena.alloc(st.nbytes_q)
-    st.yq = ctx.arena.view(st.off_yq, cap, D, st.xq.dtype)
     st.hpre = (torch.empty(max(int(lib.m3_ffn_saved_bytes(dt, cap, D, H)), 16), dtype=torch.uint8, device=st.xq.device)
                if save_hpre else None)        # opaque activation state for phase F
     ws = torch.empty(max(lib.m3_ffn_workspace_bytes(dt, cap, D, H, E_loc, 0), 16), dtype=torch.uint8, device=st.xq.device)
+    p_drop, rng = (float(drop[0]), ptr(drop[1])) if (drop is not None and drop[0] > 0 and save_hpre) else (0.0, None)
+    if st.ret:      # fc2's epilogue stores every result row into its SOURCE rank's return buffer (slot order)
+        st.off_yret = ctx.arena.alloc(st.nbytes_ret)
+        st.ysave = ctx.arena.view(st.off_yret, st.nbytes_ret // (D * 2), D, st.xq.dtype)
+        check(lib.m3_ep_ffn_fwd(dt, ptr(st.xq), ptr(st.recv.offsets), ptr(st.recv.tile_expert), cap, E_loc, D, H, ptr(w1c),
+                                ptr(b1), ptr(w2c), ptr(b2), ptr(st.hpre), ptr(st.meta), ptr(ctx.peer_ptrs(st.off_yret)),
+                                ptr(ws), ws.numel(), p_drop, rng, stream_ptr()), "m3_ep_ffn_fwd")
+        ops.launch_count += 2
+        return
+    st.off_yq = ctx.arena.alloc(st.nbytes_q)
+    st.yq = ctx.arena.view(st.off_yq, cap, D, st.xq.dtype)
     if drop is not None and drop[0] > 0 and save_hpre:      # expert dropout: the mask is a function of the OWNER's queue row
         check(lib.m3_ffn_fwd_dropout(dt, ptr(st.xq), ptr(st.recv.offsets), ptr(st.recv.tile_expert), cap, E_loc, D, H,
                                      ptr(w1c), ptr(b1), ptr(w2c), ptr(b2), ptr(st.hpre), ptr(st.yq), ptr(ws), ws.numel(),
@@ -354,6 +391,11 @@ def phase_d_combine(ctx: EPContext, st: EPFwdState, T, D, top_k, out_dtype, keep
     if out is None:
         out = torch.empty(T, D, dtype=out_dtype, device=st.g.score.device)
     assert out.is_contiguous() and out.shape == (T, D)
+    if st.ret:      # every owner has stored my rows into my return buffer: an ordinary local combine over it
+        check(load().m3_combine_fwd(ptr(st.ysave), dtype_code(st.ysave), ptr(st.pos_id), ptr(st.g.score), T, top_k, D,
+                                    ptr(out), dtype_code(out), stream_ptr()), "m3_combine_fwd")
+        ops.launch_count += 1
+        return out
     peers = ctx.peer_ptrs(st.off_yq)
     st.ysave = torch.empty(T * top_k, D, dtype=st.yq.dtype, device=out.device) if keep_rows else None
     check(load().m3_ep_combine_fwd(ptr(peers), dtype_code(st.yq), ptr(st.dst_rank), ptr(st.dst_row), ptr(st.g.score),
@@ -371,6 +413,9 @@ class EPBwdState:
     dxq: Optional[torch.Tensor] = None
     dscore: Optional[torch.Tensor] = None
     grads: Optional[tuple] = None
+    ws: Optional[torch.Tensor] = None
+    off_dxret: int = -1
+    dxret: Optional[torch.Tensor] = None      # return store: my slot-ordered [T*K, D] buffer the owners fill
 
 
 def phase_e_combine_bwd(ctx: EPContext, st: EPFwdState, g_out, top_k) -> EPBwdState:
@@ -382,41 +427,51 @@ def phase_e_combine_bwd(ctx: EPContext, st: EPFwdState, g_out, top_k) -> EPBwdSt
     bs.off_dyq = ctx.arena.alloc(st.nbytes_q)
     bs.dyq = ctx.arena.view(bs.off_dyq, st.cap, D, st.xq.dtype)
     bs.dscore = torch.empty(T, top_k, dtype=torch.float32, device=g_out.device)
-    py, pd = ctx.peer_ptrs(st.off_yq), ctx.peer_ptrs(bs.off_dyq)
+    py = ctx.peer_ptrs(st.off_yq) if st.off_yq >= 0 else None      # (not needed: dscore comes from the local copy)
+    pd = ctx.peer_ptrs(bs.off_dyq)
     check(lib.m3_ep_combine_bwd(ptr(g_out), dtype_code(g_out), ptr(py), ptr(pd), dtype_code(bs.dyq), ptr(st.dst_rank),
                                 ptr(st.dst_row), ptr(st.g.score), T, top_k, D, ptr(bs.dscore), ptr(st.ysave),
                                 stream_ptr()), "m3_ep_combine_bwd")
     check(lib.m3_zero_pad_rows(ptr(bs.dyq), dtype_code(bs.dyq), ptr(st.recv.counts), ptr(st.recv.offsets), E_loc, D,
-                               stream_ptr()), "m3_zero_pad_rows")
+                               None, stream_ptr()), "m3_zero_pad_rows")
     ops.launch_count += 2
     return bs
 
 
-def phase_f_ffn_bwd(ctx: EPContext, st: EPFwdState, bs: EPBwdState, w1c, w2c, w1t, w2t, drop=None) -> None:
+def phase_f_ffn_bwd(ctx: EPContext, st: EPFwdState, bs: EPBwdState, w1c, w2c, w1t, w2t, drop=None, parts: int = 3) -> None:
+    """local: expert FFN backward over this rank's receive queue.  parts = 1: data gradients (dxq, which the peers pull
+    next - or, with the return store, which the epilogue sends straight back to them), 2: weight gradients, 3: both."""
     lib = load()
     cap, D = st.xq.shape
     E_loc, H, _ = w1c.shape
     dt = dtype_code(st.xq)
     dev = st.xq.device
-    bs.off_dxq = ctx.arena.alloc(st.nbytes_q)
-    bs.dxq = ctx.arena.view(bs.off_dxq, cap, D, st.xq.dtype)
-    dw1 = torch.empty(E_loc, H, D, dtype=torch.float32, device=dev)
-    db1 = torch.empty(E_loc, H, dtype=torch.float32, device=dev)
-    dw2 = torch.empty(E_loc, D, H, dtype=torch.float32, device=dev)
-    db2 = torch.empty(E_loc, D, dtype=torch.float32, device=dev)
-    ws = torch.empty(max(lib.m3_ffn_workspace_bytes(dt, cap, D, H, E_loc, 1), 16), dtype=torch.uint8, device=dev)
-    if drop is not None and drop[0] > 0:
-        check(lib.m3_ffn_bwd_dropout(dt, ptr(st.xq), ptr(st.hpre), ptr(bs.dyq), ptr(st.recv.counts), ptr(st.recv.offsets),
-                                     ptr(st.recv.tile_expert), cap, E_loc, D, H, ptr(w1c), ptr(w2c), ptr(w1t), ptr(w2t),
-                                     ptr(bs.dxq), ptr(dw1), ptr(db1), ptr(dw2), ptr(db2), ptr(ws), ws.numel(),
-                                     float(drop[0]), ptr(drop[1]), stream_ptr()), "m3_ffn_bwd_dropout")
+    if parts & 1:
+        if st.ret:
+            bs.off_dxret = ctx.arena.alloc(st.nbytes_ret)
+            bs.dxret = ctx.arena.view(bs.off_dxret, st.nbytes_ret // (D * 2), D, st.xq.dtype)
+        else:
+            bs.off_dxq = ctx.arena.alloc(st.nbytes_q)
+            bs.dxq = ctx.arena.view(bs.off_dxq, cap, D, st.xq.dtype)
+        bs.grads = (torch.empty(E_loc, H, D, dtype=torch.float32, device=dev), torch.empty(E_loc, H, dtype=torch.float32, device=dev),
+                    torch.empty(E_loc, D, H, dtype=torch.float32, device=dev), torch.empty(E_loc, D, dtype=torch.float32, device=dev))
+        bs.ws = torch.empty(max(lib.m3_ffn_workspace_bytes(dt, cap, D, H, E_loc, 1), 16), dtype=torch.uint8, device=dev)
+    dw1, db1, dw2, db2 = bs.grads
+    p, rng = (float(drop[0]), ptr(drop[1])) if (drop is not None and drop[0] > 0) else (0.0, None)
+    if st.ret:
+        check(lib.m3_ep_ffn_bwd(dt, ptr(st.xq), ptr(st.hpre), ptr(bs.dyq), ptr(st.recv.counts), ptr(st.recv.offsets),
+                                ptr(st.recv.tile_expert), cap, E_loc, D, H, ptr(w1c), ptr(w2c), ptr(w1t), ptr(w2t),
+                                ptr(st.meta), ptr(ctx.peer_ptrs(bs.off_dxret)), ptr(dw1), ptr(db1), ptr(dw2), ptr(db2),
+                                ptr(bs.ws), bs.ws.numel(), p, rng, int(parts), stream_ptr()), "m3_ep_ffn_bwd")
     else:
-        check(lib.m3_ffn_bwd(dt, ptr(st.xq), ptr(st.hpre), ptr(bs.dyq), ptr(st.recv.counts), ptr(st.recv.offsets),
-                             ptr(st.recv.tile_expert), cap, E_loc, D, H, ptr(w1c), ptr(w2c), ptr(w1t), ptr(w2t),
-                             ptr(bs.dxq), ptr(dw1), ptr(db1), ptr(dw2), ptr(db2), ptr(ws), ws.numel(), stream_ptr()),
-              "m3_ffn_bwd")
-    ops.launch_count += 4 if dt == 1 else 6
-    bs.grads = (dw1, db1, dw2, db2)
+        check(lib.m3_ffn_bwd_parts(dt, ptr(st.xq), ptr(st.hpre), ptr(bs.dyq), ptr(st.recv.counts), ptr(st.recv.offsets),
+                                   ptr(st.recv.tile_expert), cap, E_loc, D, H, ptr(w1c), ptr(w2c), ptr(w1t), ptr(w2t),
+                                   ptr(bs.dxq), ptr(dw1), ptr(db1), ptr(dw2), ptr(db2), ptr(bs.ws), bs.ws.numel(), p, rng,
+                                   int(parts), stream_ptr()), "m3_ffn_bwd_parts")
+    if parts & 1:
+        ops.launch_count += 2 if dt == 1 else 2
+    if parts & 2:
+        ops.launch_count += 2 if dt == 1 else 4
 
 
 def phase_g_dispatch_bwd(ctx: EPContext, st: EPFwdState, bs: EPBwdState, T, D, top_k, dz, w_gate, out_dtype,
@@ -424,8 +479,14 @@ def phase_g_dispatch_bwd(ctx: EPContext, st: EPFwdState, bs: EPBwdState, T, D, t
     """PULL dxq rows from the owners and sum them per token (+ the router's dx)."""
     dx = out if out is not None else torch.empty(T, D, dtype=out_dtype, device=st.g.score.device)
     assert dx.is_contiguous() and dx.shape == (T, D)
-    peers = ctx.peer_ptrs(bs.off_dxq)
     E = w_gate.shape[1] if dz is not None else 0
+    if st.ret:      # the owners' dgrad epilogues have filled my return buffer: local gather-sum (+ the router's dx)
+        check(load().m3_dispatch_bwd(ptr(bs.dxret), dtype_code(bs.dxret), ptr(st.pos_id), T, top_k, D, ptr(dz),
+                                     ptr(w_gate) if dz is not None else None, E, ptr(dx), dtype_code(dx), stream_ptr()),
+              "m3_dispatch_bwd")
+        ops.launch_count += 1
+        return dx
+    peers = ctx.peer_ptrs(bs.off_dxq)
     check(load().m3_ep_dispatch_bwd(ptr(peers), dtype_code(bs.dxq), ptr(st.dst_rank), ptr(st.dst_row), T, top_k, D,
                                     ptr(dz), ptr(w_gate) if dz is not None else None, E, ptr(dx), dtype_code(dx),
                                     stream_ptr()), "m3_ep_dispatch_bwd")
@@ -437,16 +498,23 @@ def release_fwd(ctx: EPContext, st: EPFwdState) -> None:
     for off in (st.off_yq, st.off_xq):
         if off >= 0:
             ctx.defer_free(off, st.nbytes_q)
-    st.off_xq = st.off_yq = -1
-    st.xq = st.yq = None
+    if st.off_meta >= 0:
+        ctx.defer_free(st.off_meta, st.cap * 4)
+    if st.off_yret >= 0:
+        ctx.defer_free(st.off_yret, st.nbytes_ret)
+        st.ysave = None
+    st.off_xq = st.off_yq = st.off_meta = st.off_yret = -1
+    st.xq = st.yq = st.meta = None
 
 
 def release_bwd(ctx: EPContext, st: EPFwdState, bs: EPBwdState) -> None:
     for off in (bs.off_dxq, bs.off_dyq):
         if off >= 0:
             ctx.defer_free(off, st.nbytes_q)
-    bs.off_dxq = bs.off_dyq = -1
-    bs.dxq = bs.dyq = None
+    if bs.off_dxret >= 0:
+        ctx.defer_free(bs.off_dxret, st.nbytes_ret)
+    bs.off_dxq = bs.off_dyq = bs.off_dxret = -1
+    bs.dxq = bs.dyq = bs.dxret = None
 
 
 # ----------------------------------------------------------------------------- autograd over torch.distributed
@@ -504,7 +572,12 @@ class EPMoEFunction(torch.autograd.Function):
             d_out = torch.zeros_like(x)
         bs = phase_e_combine_bwd(ep, st, d_out.contiguous(), top_k)     # (fresh dyq block: nobody reads or writes it yet)
         grp.barrier(x.device)
-        phase_f_ffn_bwd(ep, st, bs, w1c, w2c, w1t, w2t, ctx.drop)
+        # Data gradients first: they are what the peers wait for (with the return store the dgrad epilogue sends every dxq
+        # row home over NVLink while the tensor cores run the next tile).  The weight gradients and the router backward
+        # need nothing from the peers and run before the rendezvous, where they also absorb rank skew.  (Running the weight
+        # gradients on a side stream beside the pull was measured at 2 GPUs and gains nothing: a GEMM CTA holds ~60 k of
+        # an SM's 64 k registers, so the movers cannot become resident next to it.)
+        phase_f_ffn_bwd(ep, st, bs, w1c, w2c, w1t, w2t, ctx.drop, parts=1)
         dscore = bs.dscore if d_score is None else bs.dscore + d_score
         if d_gates is not None and d_gates.numel() == 0:
             d_gates = None
@@ -512,7 +585,8 @@ class EPMoEFunction(torch.autograd.Function):
         dz, dwg, dtf, dxg = ops.gate_bwd(gx, w_gate, st.g.noisy_logits, st.g.idx_full, top_k, task_feat, dscore, d_top,
                                          d_gates, d_imp, d_clean, d_noisy, want_dx_gate=separate,
                                          importance=importance, dcv_loss=d_cv)
-        grp.barrier(x.device)                                         # every owner's dxq is complete
+        phase_f_ffn_bwd(ep, st, bs, w1c, w2c, w1t, w2t, ctx.drop, parts=2)
+        grp.barrier(x.device)                                         # every owner's dxq is complete / has come home
         if separate:
             dx = phase_g_dispatch_bwd(ep, st, bs, T, D, top_k, None, w_gate, x.dtype)
             dgx = dxg.to(gate_x.dtype)

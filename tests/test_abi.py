@@ -44,7 +44,7 @@ def test_ctypes_signatures_match_header(built_lib):
     for name, n in fns.items():
         assert len(_lib.SIGNATURES[name][1]) == n, f"{name}: header has {n} args, binding {len(_lib.SIGNATURES[name][1])}"
     lib = _lib.load()
-    assert lib.m3_abi_version() == 1
+    assert lib.m3_abi_version() == 2
     assert lib.m3_status_string(-2).decode() == "unsupported shape"
 
 

@@ -45,12 +45,15 @@ def test_ep_plan_kernel_bit_exact(W, E_loc, K):
         cap = int(ro[-1]) + 2 * PAD
         o = dict(dst_rank=torch.empty(R, dtype=torch.int32, device=dev), dst_row=torch.empty(R, dtype=torch.int32, device=dev),
                  rc=torch.empty(E_loc, dtype=torch.int32, device=dev), ro=torch.empty(E_loc + 1, dtype=torch.int32, device=dev),
-                 rt=torch.full((cap // PAD,), -7, dtype=torch.int32, device=dev), fl=torch.zeros(1, dtype=torch.int32, device=dev))
+                 rt=torch.full((cap // PAD,), -7, dtype=torch.int32, device=dev), fl=torch.zeros(1, dtype=torch.int32, device=dev),
+                 pid=torch.full((R,), -9, dtype=torch.int32, device=dev))
         _lib.check(lib.m3_ep_plan(idx.data_ptr(), pl.pos.data_ptr(), cnt_all.to(dev).data_ptr(), r, W, E_loc, Ts[r], K,
                                   PAD, cap, o["dst_rank"].data_ptr(), o["dst_row"].data_ptr(), o["rc"].data_ptr(),
-                                  o["ro"].data_ptr(), o["rt"].data_ptr(), o["fl"].data_ptr(),
+                                  o["ro"].data_ptr(), o["rt"].data_ptr(), o["fl"].data_ptr(), o["pid"].data_ptr(),
                                   torch.cuda.current_stream().cuda_stream), "m3_ep_plan")
         assert torch.equal(o["dst_rank"].cpu(), dr) and torch.equal(o["dst_row"].cpu(), drow)
+        # identity plan of the slot-ordered return buffers: s for a live slot, -1 for a dropped one
+        assert torch.equal(o["pid"].cpu(), torch.where(drow >= 0, torch.arange(R, dtype=torch.int32), torch.tensor(-1, dtype=torch.int32)))
         assert torch.equal(o["rc"].cpu(), rc) and torch.equal(o["ro"].cpu(), ro)
         assert int(o["fl"]) == 0
         te = o["rt"].cpu()[: int(ro[-1]) // PAD]
@@ -59,9 +62,12 @@ def test_ep_plan_kernel_bit_exact(W, E_loc, K):
 
 
 @pytest.mark.parametrize("W", [2, 4])
-@pytest.mark.parametrize("cdt", [torch.float32, torch.bfloat16])
-def test_ep_simulation_matches_single_gpu(W, cdt):
+@pytest.mark.parametrize("cdt,ret", [(torch.float32, "0"), (torch.bfloat16, "0"), (torch.bfloat16, "1")])
+def test_ep_simulation_matches_single_gpu(W, cdt, ret, monkeypatch):
+    """ret = "1": the return store (fc2 / dgrad epilogues send every result row straight into the source rank's return
+    buffer; m3_ep_ffn_fwd / m3_ep_ffn_bwd), "0": the pull protocol.  Both must equal the single-GPU layer bit for bit."""
     from m3vit_b200 import ep, ops, functions as F_
+    monkeypatch.setenv("M3_EP_RETURN", ret)
     dev = torch.device("cuda:0")
     E_tot, K, D, H, T = 16, 4, 128, 256, 333
     E_loc = E_tot // W
@@ -103,6 +109,7 @@ def test_ep_simulation_matches_single_gpu(W, cdt):
         ep.phase_b_dispatch(ctxs[r], sts[r], xs[r], cnt_all, E_loc, K, cdt)
     for r in range(W):
         ep.phase_c_ffn(ctxs[r], sts[r], wl[r][0], sl(b1, r), wl[r][1], sl(b2, r), True)
+    assert all(s.ret == (ret == "1") for s in sts)
     outs = [ep.phase_d_combine(ctxs[r], sts[r], T, D, K, torch.float32) for r in range(W)]
     for c in ctxs:
         c.check_overflow()

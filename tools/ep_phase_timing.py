@@ -22,7 +22,7 @@ def main():
     E_loc = E // world
     cdt = torch.bfloat16
     q_bytes = ((int(2.0 * T * K) + E_loc * 255 + 255) // 256 * 256) * D * 2
-    ctx = ep.make_context(ep.TorchDistGroup(), dev, arena_bytes=6 * (q_bytes + 4096), capacity_factor=2.0)
+    ctx = ep.make_context(ep.TorchDistGroup(), dev, arena_bytes=8 * (q_bytes + 4096), capacity_factor=2.0)
     w = make_weights(MoECase("C2", 1, bench.N_TOK, D, H, E, K, 2), 0)
     sl = slice(rank * E_loc, (rank + 1) * E_loc)
     wg = w["w_gate"][0].to(dev)
@@ -43,18 +43,19 @@ def main():
         mark("start")
         st = ep.phase_a_gate(x, wg, K, None, None, 0.0, False, E); mark("A gate+plan")
         cnt = grp.all_gather_counts(st.plan_local.counts); mark("  counts gather")
+        ctx.apply_deferred_frees()
         ep.phase_b_dispatch(ctx, st, x, cnt, E_loc, K, cdt); mark("B ep_plan+push x")
         grp.barrier(dev); mark("  barrier")
         ep.phase_c_ffn(ctx, st, w1c, b1, w2c, b2, True); mark("C ffn fwd")
         grp.barrier(dev); mark("  barrier")
-        out = ep.phase_d_combine(ctx, st, T, D, K, torch.float32); mark("D pull y + combine")
+        out = ep.phase_d_combine(ctx, st, T, D, K, torch.float32); mark("D combine (pull y | local)")
         grp.barrier(dev); mark("  barrier")
-        bs = ep.phase_e_combine_bwd(ctx, st, go, K); mark("E pull y, push dy")
+        bs = ep.phase_e_combine_bwd(ctx, st, go, K); mark("E push dy")
         grp.barrier(dev); mark("  barrier")
         ep.phase_f_ffn_bwd(ctx, st, bs, w1c, w2c, w1t, w2t); mark("F ffn bwd")
         dz, dwg, _, _ = ops.gate_bwd(x, wg, st.g.noisy_logits, st.g.idx_full, K, dscore=bs.dscore); mark("  gate bwd")
         grp.barrier(dev); mark("  barrier")
-        dx = ep.phase_g_dispatch_bwd(ctx, st, bs, T, D, K, dz, wg, torch.float32); mark("G pull dx")
+        dx = ep.phase_g_dispatch_bwd(ctx, st, bs, T, D, K, dz, wg, torch.float32); mark("G dx (pull | local)")
         grp.barrier(dev); mark("  barrier")
         ep.release_bwd(ctx, st, bs); ep.release_fwd(ctx, st)
         if timed:
