@@ -40,8 +40,9 @@ struct Queue {
 
 template <typename TO>
 __device__ __forceinline__ void zero_pad_rows(TO* q, const int32_t* counts, const int32_t* offsets, int e, int D,
-                                              int32_t* meta = nullptr) {
+                                              int32_t* meta = nullptr, int32_t* tgt = nullptr) {
   const int r0 = offsets[e] + counts[e], r1 = offsets[e + 1];
+  if (tgt != nullptr && threadIdx.x == 0) tgt[e] += counts[e];      // arrival target of the overlapped push (ep_push.cuh)
   if (meta != nullptr)      // expert parallel, return store: a padding row has no home (m3_ep_ffn_fwd)
     for (int i = threadIdx.x; i < r1 - r0; i += kPermThreads) meta[r0 + i] = -1;
   const int nvec = D / 8;
@@ -55,18 +56,17 @@ __device__ __forceinline__ void zero_pad_rows(TO* q, const int32_t* counts, cons
 template <typename TO>
 __global__ void __launch_bounds__(kPermThreads)
 zero_pad_rows_kernel(TO* __restrict__ q, const int32_t* __restrict__ counts, const int32_t* __restrict__ offsets, int D,
-                     int32_t* __restrict__ meta) {
+                     int32_t* __restrict__ meta, int32_t* __restrict__ tgt) {
   pdl_wait();
   pdl_trigger();
-  zero_pad_rows<TO>(q, counts, offsets, blockIdx.x, D, meta);
+  zero_pad_rows<TO>(q, counts, offsets, blockIdx.x, D, meta, tgt);
 }
 
 // xq[pos[t,k]] = cast(x[t]); trailing CTAs zero the padding rows of every queue.
 template <typename TI, typename TO, int NV, bool EP>
 __global__ void __launch_bounds__(kPermThreads)
 dispatch_fwd_kernel(const TI* __restrict__ x, const int32_t* __restrict__ pos, const int32_t* __restrict__ counts,
-                    const int32_t* __restrict__ offsets, int T, int K, int D, int tok_ctas, Queue<TO> xq,
-                    int32_t* const* __restrict__ peer_meta, int meta_tag) {
+                    const int32_t* __restrict__ offsets, int T, int K, int D, int tok_ctas, Queue<TO> xq) {
   pdl_wait();
   pdl_trigger();
   if ((int)blockIdx.x >= tok_ctas) {
@@ -93,10 +93,6 @@ dispatch_fwd_kernel(const TI* __restrict__ x, const int32_t* __restrict__ pos, c
       const int c = sub + i * kLanesPerTok;
       if (c < nvec) store8<TO>(dst + c * 8, v[i]);
     }
-    // expert parallel, return store: tell the owner where this row came from (source rank << 24 | slot), so that its
-    // fc2 / dgrad epilogue can send the result row straight back
-    if (EP && peer_meta != nullptr && sub == 0)
-      peer_meta[__ldg(xq.slot_rank + (int64_t)t * K + k)][row] = meta_tag | (t * K + k);
   }
 }
 
@@ -556,8 +552,7 @@ static int perm_common_check(int T, int K, int D) {
 template <bool EP>
 static int dispatch_fwd_impl(const void* x, int x_dtype, const int32_t* pos, const int32_t* counts,
                              const int32_t* offsets, int T, int K, int D, int E, void* xq, void* const* peer,
-                             const int32_t* slot_rank, int xq_dtype, void* const* peer_meta, int meta_tag,
-                             cudaStream_t st) {
+                             const int32_t* slot_rank, int xq_dtype, cudaStream_t st) {
   int rc = perm_common_check(T, K, D);
   if (rc) return rc;
   const int nv = perm_nv(D);
@@ -566,7 +561,7 @@ static int dispatch_fwd_impl(const void* x, int x_dtype, const int32_t* pos, con
   if (grid == 0) return M3_OK;
   M3_DTYPE2_SWITCH(x_dtype, xq_dtype, {
     Queue<TB> q{(TB*)xq, (TB* const*)peer, slot_rank};
-    M3_NV_SWITCH((launch_k(dispatch_fwd_kernel<TA, TB, NV, EP>, grid, kPermThreads, 0, st, (const TA*)x, pos, counts, offsets, T, K, D, tok_ctas, q, (int32_t* const*)peer_meta, meta_tag)))
+    M3_NV_SWITCH((launch_k(dispatch_fwd_kernel<TA, TB, NV, EP>, grid, kPermThreads, 0, st, (const TA*)x, pos, counts, offsets, T, K, D, tok_ctas, q)))
   })
   M3_LAUNCH_CHECK();
   return M3_OK;
@@ -695,7 +690,7 @@ extern "C" int m3_dispatch_fwd(const void* x, int x_dtype, const int32_t* pos, c
   M3_CHECK_ARG(x && pos && counts && offsets && xq && E >= 1);
   M3_CHECK_ALIGN16(x); M3_CHECK_ALIGN16(xq);
   return dispatch_fwd_impl<false>(x, x_dtype, pos, counts, offsets, T, K, D, E, xq, nullptr, nullptr, xq_dtype,
-                                  nullptr, 0, static_cast<cudaStream_t>(stream));
+                                  static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int m3_combine_fwd(const void* yq, int yq_dtype, const int32_t* pos, const float* score, int T, int K,
@@ -729,13 +724,11 @@ extern "C" int m3_dispatch_bwd(const void* dxq, int dxq_dtype, const int32_t* po
 
 // ---- expert-parallel variants: rows live in the owner rank's queue (peer pointers)
 extern "C" int m3_ep_dispatch_fwd(const void* x, int x_dtype, const int32_t* dst_rank, const int32_t* dst_row, int T,
-                                  int K, int D, void* const* peer_xq, int xq_dtype, void* const* peer_meta, int rank,
-                                  m3_stream_t stream) {
+                                  int K, int D, void* const* peer_xq, int xq_dtype, m3_stream_t stream) {
   M3_CHECK_ARG(x && dst_rank && dst_row && peer_xq);
-  M3_CHECK_ARG(peer_meta == nullptr || (rank >= 0 && rank < 128 && (int64_t)T * K <= (1 << 24)));
   M3_CHECK_ALIGN16(x);
   return dispatch_fwd_impl<true>(x, x_dtype, dst_row, nullptr, nullptr, T, K, D, 0, nullptr, peer_xq, dst_rank,
-                                 xq_dtype, peer_meta, rank << 24, static_cast<cudaStream_t>(stream));
+                                 xq_dtype, static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int m3_ep_combine_fwd(void* const* peer_yq, int yq_dtype, const int32_t* dst_rank, const int32_t* dst_row,
@@ -769,12 +762,12 @@ extern "C" int m3_ep_dispatch_bwd(void* const* peer_dxq, int dxq_dtype, const in
 }
 
 extern "C" int m3_zero_pad_rows(void* q, int dtype, const int32_t* counts, const int32_t* offsets, int E, int D,
-                                int32_t* meta, m3_stream_t stream) {
+                                int32_t* meta, int32_t* arrival_target, m3_stream_t stream) {
   M3_CHECK_ARG(q && counts && offsets && E >= 1 && D >= 8 && D % 8 == 0);
   M3_CHECK_ALIGN16(q);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (dtype == M3_F32) zero_pad_rows_kernel<float><<<E, kPermThreads, 0, st>>>((float*)q, counts, offsets, D, meta);
-  else if (dtype == M3_BF16) zero_pad_rows_kernel<bf16><<<E, kPermThreads, 0, st>>>((bf16*)q, counts, offsets, D, meta);
+  if (dtype == M3_F32) zero_pad_rows_kernel<float><<<E, kPermThreads, 0, st>>>((float*)q, counts, offsets, D, meta, arrival_target);
+  else if (dtype == M3_BF16) zero_pad_rows_kernel<bf16><<<E, kPermThreads, 0, st>>>((bf16*)q, counts, offsets, D, meta, arrival_target);
   else return M3_ERR_UNSUPPORTED;
   M3_LAUNCH_CHECK();
   return M3_OK;

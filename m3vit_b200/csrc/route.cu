@@ -45,7 +45,7 @@ route_assign_kernel(const int64_t* __restrict__ idx, int R, int E, int pad, int 
                     const int32_t* __restrict__ load_partial, int n_partial, int32_t* __restrict__ counts,
                     int32_t* __restrict__ offsets, int32_t* __restrict__ pos,
                     int32_t* __restrict__ tile_expert, float* __restrict__ importance,
-                    float* __restrict__ load, float* __restrict__ cv_loss) {
+                    float* __restrict__ load, float* __restrict__ cv_loss, int32_t* __restrict__ inv_pos) {
   extern __shared__ int sm[];
   int* tot = sm;                     // [E] total count per expert
   int* pre = tot + E;                // [E] count in blocks before this one
@@ -112,7 +112,9 @@ route_assign_kernel(const int64_t* __restrict__ idx, int R, int E, int pad, int 
     const int s = base + wb * 32 + lane;
     if (s < R) {
       const int e = my_e[i];
-      pos[s] = e >= 0 ? off[e] + pre[e] + bh[wb * E + e] + my_rank[i] : -1;
+      const int p = e >= 0 ? off[e] + pre[e] + bh[wb * E + e] + my_rank[i] : -1;
+      pos[s] = p;
+      if (inv_pos != nullptr && p >= 0) inv_pos[p] = s;      // queue row -> slot (expert parallel: the sorted send order)
     }
   }
   if (b == 0) {
@@ -201,7 +203,7 @@ extern "C" int m3_route_max_tiles(int T, int K, int E, int pad) { return m3_rout
 extern "C" int m3_route_plan(const int64_t* idx, int T, int K, int E, int pad, const float* imp_partial,
                              const int32_t* load_partial, int n_partial, int32_t* counts, int32_t* offsets,
                              int32_t* pos, int32_t* tile_expert, float* importance, float* load, float* cv_loss,
-                             void* workspace, size_t workspace_bytes, m3_stream_t stream) {
+                             int32_t* inv_pos, void* workspace, size_t workspace_bytes, m3_stream_t stream) {
   M3_CHECK_ARG(idx && counts && offsets && pos && workspace);   // tile_expert may be NULL (pad-1 plans)
   M3_CHECK_ARG(T >= 0 && K >= 1 && E >= 1 && pad >= 1);
   M3_CHECK_SHAPE(E <= 128);
@@ -218,7 +220,7 @@ extern "C" int m3_route_plan(const int64_t* idx, int T, int K, int E, int pad, c
   M3_LAUNCH_CHECK();
   const size_t smem = (size_t)(3 * E + 1 + kRouteBatches * E + 2 * kRouteThreads) * sizeof(int);
   launch_k(route_assign_kernel, nblk, kRouteThreads, smem, st, idx, R, E, pad, nblk, block_hist, imp_partial,
-           load_partial, n_partial, counts, offsets, pos, tile_expert, importance, load, cv_loss);
+           load_partial, n_partial, counts, offsets, pos, tile_expert, importance, load, cv_loss, inv_pos);
   M3_LAUNCH_CHECK();
   return M3_OK;
 }

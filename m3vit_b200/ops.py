@@ -149,7 +149,8 @@ class Plan:
     cv_loss: Optional[torch.Tensor] = None      # 0-dim: cv^2(importance) + cv^2(load)
 
 
-def route_plan(idx, num_expert, pad=PAD_ROWS, imp_partial=None, load_partial=None) -> Plan:
+def route_plan(idx, num_expert, pad=PAD_ROWS, imp_partial=None, load_partial=None, inv_pos=None) -> Plan:
+    """inv_pos: optional int32 [>= rows] buffer that receives the inverse map queue row -> slot (expert parallel)."""
     require_device(idx)
     lib = load()
     assert idx.dtype == torch.int64 and idx.is_contiguous()
@@ -166,8 +167,8 @@ def route_plan(idx, num_expert, pad=PAD_ROWS, imp_partial=None, load_partial=Non
         imp, load_v, cv = _f32((E,), dev), _f32((E,), dev), _f32((), dev)
     ws = _ws(lib.m3_route_plan_workspace_bytes(T, K, E), dev)
     check(lib.m3_route_plan(ptr(idx), T, K, E, pad, ptr(imp_partial), ptr(load_partial), n_part, ptr(counts),
-                            ptr(offsets), ptr(pos), ptr(tile_expert), ptr(imp), ptr(load_v), ptr(cv), ptr(ws),
-                            ws.numel(), stream_ptr()), "m3_route_plan")
+                            ptr(offsets), ptr(pos), ptr(tile_expert), ptr(imp), ptr(load_v), ptr(cv), ptr(inv_pos),
+                            ptr(ws), ws.numel(), stream_ptr()), "m3_route_plan")
     _count("route_plan")
     return Plan(counts, offsets, pos, tile_expert, cap_rows, pad, imp, load_v, cv)
 

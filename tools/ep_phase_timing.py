@@ -41,17 +41,19 @@ def main():
                 e = torch.cuda.Event(enable_timing=True); e.record(); evs.append((n, e))
         grp = ctx.group
         mark("start")
-        st = ep.phase_a_gate(x, wg, K, None, None, 0.0, False, E); mark("A gate+plan")
+        st = ep.phase_a_gate(x, wg, K, None, None, 0.0, False, E, ctx, cdt); mark("A gate+plan")
         cnt = grp.all_gather_counts(st.plan_local.counts); mark("  counts gather")
         ctx.apply_deferred_frees()
         ep.phase_b_dispatch(ctx, st, x, cnt, E_loc, K, cdt); mark("B ep_plan+push x")
-        grp.barrier(dev); mark("  barrier")
+        if not st.ovl:
+            grp.barrier(dev); mark("  barrier")
         ep.phase_c_ffn(ctx, st, w1c, b1, w2c, b2, True); mark("C ffn fwd")
         grp.barrier(dev); mark("  barrier")
         out = ep.phase_d_combine(ctx, st, T, D, K, torch.float32); mark("D combine (pull y | local)")
         grp.barrier(dev); mark("  barrier")
         bs = ep.phase_e_combine_bwd(ctx, st, go, K); mark("E push dy")
-        grp.barrier(dev); mark("  barrier")
+        if not st.ovl:
+            grp.barrier(dev); mark("  barrier")
         ep.phase_f_ffn_bwd(ctx, st, bs, w1c, w2c, w1t, w2t); mark("F ffn bwd")
         dz, dwg, _, _ = ops.gate_bwd(x, wg, st.g.noisy_logits, st.g.idx_full, K, dscore=bs.dscore); mark("  gate bwd")
         grp.barrier(dev); mark("  barrier")

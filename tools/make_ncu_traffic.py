@@ -33,12 +33,9 @@ def to_bytes(r, c, units_row=rows[1]):
     return v * {"byte": 1, "kbyte": 1e3, "mbyte": 1e6, "gbyte": 1e9}.get(u, 1)
 
 
-# forward GEMMs of the training path: gg_kernel with EPI = 1 (fc1: bias + GELU) and EPI = 0 (fc2: bias)
-fwd = [r for r in data if "gg_kernel" in r[ix["Kernel Name"]] and ("<192, 1," in r[ix["Kernel Name"]] or "<192, 0," in r[ix["Kernel Name"]])]
-# the function name column may not carry template arguments: fall back to the first two gg_kernel launches of a call
-if not fwd:
-    gg = [r for r in data if "gg_kernel" in r[ix["Kernel Name"]]]
-    fwd = gg[:2]
+# forward GEMMs of the training path = the first two gg_kernel launches of a layer call (fc1: bias + GELU, fc2: bias)
+gg = [r for r in data if "gg_kernel" in r[ix["Kernel Name"]]]
+fwd = gg[:2]
 per = [to_bytes(r, "dram__bytes_read.sum") + to_bytes(r, "dram__bytes_write.sum") for r in fwd]
 T, D, H, E, K = B * bench.N_TOK, bench.D_MODEL, bench.D_HID, bench.N_EXP, bench.TOP_K
 sources = ["m3vit_b200/csrc/ffn_bf16.cu", "m3vit_b200/csrc/tc_common.cuh", "m3vit_b200/csrc/common.cuh"]
