@@ -12,7 +12,12 @@
  *     unless stated otherwise.  The library never allocates, frees or retains
  *     device memory: every buffer (outputs, workspaces) is caller-owned.
  *   - every launch goes to the `stream` passed in (a cudaStream_t); no implicit
- *     device synchronisation, no host read-back.  Re-entrant, no global state.
+ *     device synchronisation, no host read-back.  The compute entry points keep no state between
+ *     calls and may be called from several host threads on different streams.  The only
+ *     process-wide state is the DIAGNOSIS interface at the end of this header (m3_set_knob,
+ *     m3_set_gemm_sm_limit, m3_debug_trace_buffer): tuning / measurement switches read at launch
+ *     time, never needed for results (every knob setting is bit-identical or documented as
+ *     "measurement only") and not meant to be changed while other threads are launching.
  *   - return value: 0 ok; <0 argument error (m3_status); >0 a cudaError_t.
  *   - activations may be fp32 or bf16 (m3_dtype); router math is always fp32.
  *   - expert queues use the PADDED layout: expert e owns rows
@@ -266,45 +271,17 @@ int m3_ep_plan(const int64_t* idx, const int32_t* pos_local, const int32_t* cnt_
                int E_loc, int T, int K, int pad, int cap_rows, int32_t* dst_rank, int32_t* dst_row,
                int32_t* recv_counts, int32_t* recv_offsets, int32_t* recv_tile_expert,
                int32_t* overflow_flag, int32_t* pos_id, void* const* peer_inv, int32_t* meta,
-               int32_t* seg_tab, int32_t* arrival_target, m3_stream_t stream);
-/* Optional outputs of m3_ep_plan (each may be NULL) for the fused exchange below:
+               m3_stream_t stream);
+/* Optional outputs of m3_ep_plan (each may be NULL) for the fused return store below:
  *   pos_id[T*K]   s for a live slot, -1 for a dropped one: the "queue position" of slot s in a slot-ordered return
  *                 buffer, to be handed to m3_combine_fwd / m3_dispatch_bwd.
  *   meta[cap_rows] + peer_inv[W] (both or neither; needs T*K <= 2^24, W <= 128): row origins of MY receive queue,
  *                 meta[r] = (source rank << 24) | slot, read from the sources' inverse plans (peer_inv[r] = rank r's
- *                 inv_pos from m3_route_plan(pad = 1), complete before the count exchange).  Padding rows are set to -1
- *                 by m3_zero_pad_rows.
- *   seg_tab[2 + 6 * W * E_loc]  send schedule of the sorted push: {V, live rows, V x {first row of the segment in send
- *                 order, first sorted position, owner rank, first row in the owner's queue, local expert at the
- *                 owner, rows}}; segments ordered by local expert, owners rotated by rank.
- *   arrival_target[E_loc]  += rows every local expert receives in this call (running target of the arrival counters). */
+ *                 inv_pos from m3_route_plan(pad = 1), complete before the count exchange): coalesced 4-byte reads,
+ *                 ~T*K*4 bytes per rank, instead of a separate 4-byte remote store with every pushed row.  Padding
+ *                 rows are set to -1 by m3_zero_pad_rows. */
 int m3_ep_dispatch_fwd(const void* x, int x_dtype, const int32_t* dst_rank, const int32_t* dst_row,
                        int T, int K, int D, void* const* peer_xq, int xq_dtype, m3_stream_t stream);
-
-/* The PUSH half of the exchange run INSIDE the first expert GEMM of m3_ep_ffn_fwd / m3_ep_ffn_bwd (csrc/ep_push.cuh):
- * the last `push_ctas` CTAs of that launch store this rank's rows (sorted by destination expert, schedule seg_tab) into
- * the owners' queues and publish them chunk by chunk on the owners' arrival counters (fence.sys + red.release.sys);
- * the GEMM CTAs of the same launch wait for my_counters[e] to reach my_targets[e] before the first tile of local expert
- * e.  No separate dispatch kernel, no rendezvous between push and GEMM: replaces fmoe's global_scatter + the wait for
- * it (MOEScatter, reached from models/moe/origin/custom_moe_layer.py:255-257).  Every rank must run the same call.
- *   forward : src = x [T, D], rows are cast to bf16 like m3_dispatch_fwd.
- *   backward: src = g [T, D]; pushes score[s] * g[t] and writes dscore[s] = <g[t], ysave[s]> like m3_combine_bwd. */
-typedef struct m3_ep_push {
-  const void* src;
-  int src_dtype;                 /* M3_F32 / M3_BF16 */
-  const int32_t* inv_pos;        /* [T*K] sorted position -> slot (m3_route_plan, pad 1) */
-  const int32_t* seg_tab;        /* m3_ep_plan */
-  void* const* peer_queue;       /* [W] every rank's receive queue (xq / dyq), bf16 [cap_rows, D] */
-  void* const* peer_counters;    /* [W] every rank's arrival counters, int32 [E_loc] */
-  const int32_t* my_counters;    /* = peer_counters[rank] */
-  const int32_t* my_targets;     /* [E_loc] running targets (m3_ep_plan / m3_zero_pad_rows) */
-  int K;
-  int push_ctas;                 /* even; CTAs of the GEMM launch that push instead of multiplying */
-  int sm_limit;                  /* total CTAs of that launch (0 = all SMs) */
-  const float* score;            /* backward: [T*K] */
-  const void* ysave;             /* backward: [T*K, D] bf16 result rows in slot order */
-  float* dscore;                 /* backward: [T*K] out */
-} m3_ep_push_t;
 /* The expert FFN FUSED WITH THE RETURN HALF OF THE ALL-TO-ALL (bf16 / tcgen05 path only).  Same arithmetic as
  * m3_ffn_fwd_dropout / m3_ffn_bwd_parts over this rank's receive queue, but the epilogue of the LAST GEMM (fc2 in the
  * forward, dxq = dz W1 in the backward) stores every result row straight into the SOURCE rank's slot-ordered return
@@ -318,15 +295,12 @@ typedef struct m3_ep_push {
 int m3_ep_ffn_fwd(int dtype, const void* xq, const int32_t* offsets, const int32_t* tile_expert, int cap_rows,
                   int E, int D, int H, const void* w1, const float* b1, const void* w2, const float* b2,
                   void* saved, const int32_t* ret_meta, void* const* peer_yret, void* workspace,
-                  size_t workspace_bytes, float drop_p, const void* rng_state, const m3_ep_push_t* push,
-                  m3_stream_t stream);
+                  size_t workspace_bytes, float drop_p, const void* rng_state, m3_stream_t stream);
 int m3_ep_ffn_bwd(int dtype, const void* xq, const void* saved, const void* dyq, const int32_t* counts,
                   const int32_t* offsets, const int32_t* tile_expert, int cap_rows, int E, int D, int H,
                   const void* w1, const void* w2, const void* w1t, const void* w2t, const int32_t* ret_meta,
                   void* const* peer_dxret, float* dw1, float* db1, float* dw2, float* db2, void* workspace,
-                  size_t workspace_bytes, float drop_p, const void* rng_state, int parts,
-                  const m3_ep_push_t* push, m3_stream_t stream);
-/* `push` (may be NULL: rows were pushed by m3_ep_dispatch_fwd / m3_ep_combine_bwd and a rendezvous has passed). */
+                  size_t workspace_bytes, float drop_p, const void* rng_state, int parts, m3_stream_t stream);
 /* ysave [T*K, D] (queue dtype, may be NULL): m3_ep_combine_fwd keeps a LOCAL copy, in slot order, of
  * the result rows it pulls over NVLink; given to m3_ep_combine_bwd, dscore = <g, y> is computed from
  * that copy and the backward pass only PUSHES dyq (peer_yq may then be NULL). */
@@ -340,10 +314,9 @@ int m3_ep_combine_bwd(const void* g, int g_dtype, void* const* peer_yq, void* co
 int m3_ep_dispatch_bwd(void* const* peer_dxq, int dxq_dtype, const int32_t* dst_rank,
                        const int32_t* dst_row, int T, int K, int D, const float* dz,
                        const float* w_gate, int E, void* dx, int dx_dtype, m3_stream_t stream);
-/* zeroes the padding rows of a receive queue; meta (may be NULL): also marks them -1 in the row-origin array;
- * arrival_target (may be NULL): [E] += counts (running target of the overlapped push of the backward pass) */
+/* zeroes the padding rows of a receive queue; meta (may be NULL): also marks them -1 in the row-origin array */
 int m3_zero_pad_rows(void* q, int dtype, const int32_t* counts, const int32_t* offsets, int E, int D,
-                     int32_t* meta, int32_t* arrival_target, m3_stream_t stream);
+                     int32_t* meta, m3_stream_t stream);
 /* Device-side rendezvous of the W ranks over peer memory (replaces an NCCL barrier / the
  * fmoe expert_exchange count all-to-all): a 1-warp kernel stores `epoch` into slot `rank` of every
  * peer's flag array (system-scope release) and, if `payload` != NULL, first copies `payload_ints`

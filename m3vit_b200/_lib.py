@@ -23,13 +23,6 @@ _i64 = C.c_int64
 _f = C.c_float
 _sz = C.c_size_t
 
-class EpPush(C.Structure):
-    """m3_ep_push_t (include/m3vit_moe.h): the push half of the exchange run inside the first expert GEMM."""
-    _fields_ = [("src", _p), ("src_dtype", _i), ("inv_pos", _p), ("seg_tab", _p), ("peer_queue", _p),
-                ("peer_counters", _p), ("my_counters", _p), ("my_targets", _p), ("K", _i), ("push_ctas", _i),
-                ("sm_limit", _i), ("score", _p), ("ysave", _p), ("dscore", _p)]
-
-
 # name -> (restype, argtypes); mirrors include/m3vit_moe.h one to one
 SIGNATURES = {
     "m3_abi_version": (_i, []),
@@ -62,15 +55,15 @@ SIGNATURES = {
     "m3_ffn_bwd_dropout": (_i, [_i, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _sz, _f,
                                 _p, _p]),
     "m3_cast_weights_bf16": (_i, [_p, _i, _i, _i, _p, _p, _p]),
-    "m3_ep_plan": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
+    "m3_ep_plan": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
     "m3_ep_dispatch_fwd": (_i, [_p, _i, _p, _p, _i, _i, _i, _p, _i, _p]),
-    "m3_ep_ffn_fwd": (_i, [_i, _p, _p, _p, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p, _sz, _f, _p, _p, _p]),
+    "m3_ep_ffn_fwd": (_i, [_i, _p, _p, _p, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p, _sz, _f, _p, _p]),
     "m3_ep_ffn_bwd": (_i, [_i, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _sz, _f,
-                           _p, _i, _p, _p]),
+                           _p, _i, _p]),
     "m3_ep_combine_fwd": (_i, [_p, _i, _p, _p, _p, _i, _i, _i, _p, _i, _p, _p]),
     "m3_ep_combine_bwd": (_i, [_p, _i, _p, _p, _i, _p, _p, _p, _i, _i, _i, _p, _p, _p]),
     "m3_ep_dispatch_bwd": (_i, [_p, _i, _p, _p, _i, _i, _i, _p, _p, _i, _p, _i, _p]),
-    "m3_zero_pad_rows": (_i, [_p, _i, _p, _p, _i, _i, _p, _p, _p]),
+    "m3_zero_pad_rows": (_i, [_p, _i, _p, _p, _i, _i, _p, _p]),
     "m3_ep_barrier": (_i, [_p, _p, _p, _i, _i, _i, _i, _p]),
     "m3_ln_stats": (_i, [_p, _i, _i, _f, _p, _p, _p]),
     "m3_ln_fold_gate": (_i, [_p, _p, _p, _i, _i, _i, _p, _p, _p]),

@@ -20,12 +20,12 @@ int m3_ffn_bf16_set_sm_limit(int sms);
 int m3_ffn_fwd_bf16(const void* xq, const int32_t* offsets, const int32_t* tile_expert, int cap_rows, int E, int D,
                     int H, const void* w1, const float* b1, const void* w2, const float* b2, void* hpre, void* yq,
                     void* workspace, size_t workspace_bytes, float drop_p, const void* rng, const int32_t* ret_meta,
-                    void* const* ret_bases, const m3_ep_push_t* push, cudaStream_t st);
+                    void* const* ret_bases, cudaStream_t st);
 int m3_ffn_bwd_bf16(const void* xq, const void* hpre, const void* dyq, const int32_t* counts,
                     const int32_t* offsets, const int32_t* tile_expert, int cap_rows, int E, int D, int H,
                     const void* w1, const void* w2, const void* w1t, const void* w2t, void* dxq, float* dw1,
                     float* db1, float* dw2, float* db2, void* workspace, size_t workspace_bytes, int parts,
-                    const int32_t* ret_meta, void* const* ret_bases, const m3_ep_push_t* push, cudaStream_t st);
+                    const int32_t* ret_meta, void* const* ret_bases, cudaStream_t st);
 
 extern "C" int m3_abi_version(void) { return M3_ABI_VERSION; }
 
@@ -97,10 +97,8 @@ extern "C" int m3_ffn_uses_chain(int dtype, int D, int H) {
 static int ffn_fwd_impl(int dtype, const void* xq, const int32_t* offsets, const int32_t* tile_expert, int cap_rows,
                         int E, int D, int H, const void* w1, const float* b1, const void* w2, const float* b2,
                         void* hpre, void* yq, void* workspace, size_t workspace_bytes, float drop_p, const void* rng,
-                        const int32_t* ret_meta, void* const* ret_bases, const m3_ep_push_t* push,
-                        m3_stream_t stream) {
+                        const int32_t* ret_meta, void* const* ret_bases, m3_stream_t stream) {
   M3_CHECK_ARG(drop_p >= 0.f && drop_p < 1.f);
-  M3_CHECK_ARG(push == nullptr || ret_meta != nullptr);
   if (rng) M3_CHECK_ALIGN16(rng);
   M3_CHECK_ARG(xq && offsets && tile_expert && w1 && b1 && w2 && b2 && (yq || ret_meta));
   M3_CHECK_ARG((ret_meta == nullptr) == (ret_bases == nullptr));
@@ -119,7 +117,7 @@ static int ffn_fwd_impl(int dtype, const void* xq, const int32_t* offsets, const
                           (const float*)w2, b2, (float*)hpre, (float*)yq, workspace, workspace_bytes, drop_p, rng, st);
   if (dtype == M3_BF16)
     return m3_ffn_fwd_bf16(xq, offsets, tile_expert, cap_rows, E, D, H, w1, b1, w2, b2, hpre, yq, workspace,
-                           workspace_bytes, drop_p, rng, ret_meta, ret_bases, push, st);
+                           workspace_bytes, drop_p, rng, ret_meta, ret_bases, st);
   return M3_ERR_UNSUPPORTED;
 }
 
@@ -127,7 +125,7 @@ extern "C" int m3_ffn_fwd(int dtype, const void* xq, const int32_t* offsets, con
                           int E, int D, int H, const void* w1, const float* b1, const void* w2, const float* b2,
                           void* hpre, void* yq, void* workspace, size_t workspace_bytes, m3_stream_t stream) {
   return ffn_fwd_impl(dtype, xq, offsets, tile_expert, cap_rows, E, D, H, w1, b1, w2, b2, hpre, yq, workspace,
-                      workspace_bytes, 0.f, nullptr, nullptr, nullptr, nullptr, stream);
+                      workspace_bytes, 0.f, nullptr, nullptr, nullptr, stream);
 }
 
 extern "C" int m3_ffn_fwd_dropout(int dtype, const void* xq, const int32_t* offsets, const int32_t* tile_expert,
@@ -135,17 +133,16 @@ extern "C" int m3_ffn_fwd_dropout(int dtype, const void* xq, const int32_t* offs
                                   const float* b2, void* saved, void* yq, void* workspace, size_t workspace_bytes,
                                   float drop_p, const void* rng_state, m3_stream_t stream) {
   return ffn_fwd_impl(dtype, xq, offsets, tile_expert, cap_rows, E, D, H, w1, b1, w2, b2, saved, yq, workspace,
-                      workspace_bytes, drop_p, rng_state, nullptr, nullptr, nullptr, stream);
+                      workspace_bytes, drop_p, rng_state, nullptr, nullptr, stream);
 }
 
 extern "C" int m3_ep_ffn_fwd(int dtype, const void* xq, const int32_t* offsets, const int32_t* tile_expert, int cap_rows,
                              int E, int D, int H, const void* w1, const float* b1, const void* w2, const float* b2,
                              void* saved, const int32_t* ret_meta, void* const* peer_yret, void* workspace,
-                             size_t workspace_bytes, float drop_p, const void* rng_state, const m3_ep_push_t* push,
-                             m3_stream_t stream) {
+                             size_t workspace_bytes, float drop_p, const void* rng_state, m3_stream_t stream) {
   M3_CHECK_ARG(ret_meta && peer_yret);
   return ffn_fwd_impl(dtype, xq, offsets, tile_expert, cap_rows, E, D, H, w1, b1, w2, b2, saved, nullptr, workspace,
-                      workspace_bytes, drop_p, rng_state, ret_meta, peer_yret, push, stream);
+                      workspace_bytes, drop_p, rng_state, ret_meta, peer_yret, stream);
 }
 
 static int ffn_bwd_impl(int dtype, const void* xq, const void* hpre, const void* dyq, const int32_t* counts,
@@ -153,12 +150,11 @@ static int ffn_bwd_impl(int dtype, const void* xq, const void* hpre, const void*
                         const void* w1, const void* w2, const void* w1t, const void* w2t, void* dxq, float* dw1,
                         float* db1, float* dw2, float* db2, void* workspace, size_t workspace_bytes, float drop_p,
                         const void* rng, int parts, const int32_t* ret_meta, void* const* ret_bases,
-                        const m3_ep_push_t* push, m3_stream_t stream) {
+                        m3_stream_t stream) {
   M3_CHECK_ARG(drop_p >= 0.f && drop_p < 1.f && parts >= 1 && parts <= 3);
   M3_CHECK_ARG(xq && hpre && dyq && counts && offsets && tile_expert && w1 && w2 && (dxq || ret_meta) && dw1 && db1 && dw2 && db2);
   M3_CHECK_ARG((ret_meta == nullptr) == (ret_bases == nullptr));
   if (ret_meta && dtype != M3_BF16) return M3_ERR_UNSUPPORTED;
-  M3_CHECK_ARG(push == nullptr || (ret_meta != nullptr && (parts & 1)));
   M3_CHECK_ARG(cap_rows >= 0 && E >= 1 && D > 0 && H > 0 && workspace);
   M3_CHECK_SHAPE(cap_rows % M3_PAD_ROWS == 0);
   M3_CHECK_ALIGN16(xq); M3_CHECK_ALIGN16(hpre); M3_CHECK_ALIGN16(dyq); M3_CHECK_ALIGN16(dxq);
@@ -173,7 +169,7 @@ static int ffn_bwd_impl(int dtype, const void* xq, const void* hpre, const void*
     M3_CHECK_ARG(w1t && w2t);
     // bf16: the saved planes already carry the forward's keep-scale (h = m gelu(z), m gelu'(z)): nothing to regenerate
     return m3_ffn_bwd_bf16(xq, hpre, dyq, counts, offsets, tile_expert, cap_rows, E, D, H, w1, w2, w1t, w2t, dxq,
-                           dw1, db1, dw2, db2, workspace, workspace_bytes, parts, ret_meta, ret_bases, push, st);
+                           dw1, db1, dw2, db2, workspace, workspace_bytes, parts, ret_meta, ret_bases, st);
   }
   return M3_ERR_UNSUPPORTED;
 }
@@ -184,7 +180,7 @@ extern "C" int m3_ffn_bwd(int dtype, const void* xq, const void* hpre, const voi
                           float* db1, float* dw2, float* db2, void* workspace, size_t workspace_bytes,
                           m3_stream_t stream) {
   return ffn_bwd_impl(dtype, xq, hpre, dyq, counts, offsets, tile_expert, cap_rows, E, D, H, w1, w2, w1t, w2t, dxq, dw1,
-                      db1, dw2, db2, workspace, workspace_bytes, 0.f, nullptr, 3, nullptr, nullptr, nullptr, stream);
+                      db1, dw2, db2, workspace, workspace_bytes, 0.f, nullptr, 3, nullptr, nullptr, stream);
 }
 
 extern "C" int m3_ffn_bwd_parts(int dtype, const void* xq, const void* saved, const void* dyq, const int32_t* counts,
@@ -193,19 +189,18 @@ extern "C" int m3_ffn_bwd_parts(int dtype, const void* xq, const void* saved, co
                                 float* db1, float* dw2, float* db2, void* workspace, size_t workspace_bytes,
                                 float drop_p, const void* rng_state, int parts, m3_stream_t stream) {
   return ffn_bwd_impl(dtype, xq, saved, dyq, counts, offsets, tile_expert, cap_rows, E, D, H, w1, w2, w1t, w2t, dxq, dw1,
-                      db1, dw2, db2, workspace, workspace_bytes, drop_p, rng_state, parts, nullptr, nullptr, nullptr, stream);
+                      db1, dw2, db2, workspace, workspace_bytes, drop_p, rng_state, parts, nullptr, nullptr, stream);
 }
 
 extern "C" int m3_ep_ffn_bwd(int dtype, const void* xq, const void* saved, const void* dyq, const int32_t* counts,
                              const int32_t* offsets, const int32_t* tile_expert, int cap_rows, int E, int D, int H,
                              const void* w1, const void* w2, const void* w1t, const void* w2t, const int32_t* ret_meta,
                              void* const* peer_dxret, float* dw1, float* db1, float* dw2, float* db2, void* workspace,
-                             size_t workspace_bytes, float drop_p, const void* rng_state, int parts,
-                             const m3_ep_push_t* push, m3_stream_t stream) {
+                             size_t workspace_bytes, float drop_p, const void* rng_state, int parts, m3_stream_t stream) {
   M3_CHECK_ARG(ret_meta && peer_dxret);
   return ffn_bwd_impl(dtype, xq, saved, dyq, counts, offsets, tile_expert, cap_rows, E, D, H, w1, w2, w1t, w2t, nullptr,
                       dw1, db1, dw2, db2, workspace, workspace_bytes, drop_p, rng_state, parts, ret_meta, peer_dxret,
-                      push, stream);
+                      stream);
 }
 
 extern "C" int m3_ffn_bwd_dropout(int dtype, const void* xq, const void* saved, const void* dyq, const int32_t* counts,
@@ -214,7 +209,7 @@ extern "C" int m3_ffn_bwd_dropout(int dtype, const void* xq, const void* saved, 
                                   float* dw1, float* db1, float* dw2, float* db2, void* workspace,
                                   size_t workspace_bytes, float drop_p, const void* rng_state, m3_stream_t stream) {
   return ffn_bwd_impl(dtype, xq, saved, dyq, counts, offsets, tile_expert, cap_rows, E, D, H, w1, w2, w1t, w2t, dxq, dw1,
-                      db1, dw2, db2, workspace, workspace_bytes, drop_p, rng_state, 3, nullptr, nullptr, nullptr, stream);
+                      db1, dw2, db2, workspace, workspace_bytes, drop_p, rng_state, 3, nullptr, nullptr, stream);
 }
 
 
@@ -250,7 +245,7 @@ __global__ void ep_plan_kernel(const int64_t* __restrict__ idx, const int32_t* _
                                int32_t* __restrict__ recv_counts, int32_t* __restrict__ recv_offsets,
                                int32_t* __restrict__ recv_tile_expert, int32_t* __restrict__ overflow_flag,
                                int32_t* __restrict__ pos_id, int32_t* const* __restrict__ peer_inv,
-                               int32_t* __restrict__ meta, int32_t* __restrict__ seg_tab, int32_t* __restrict__ tgt_x) {
+                               int32_t* __restrict__ meta) {
   extern __shared__ int sm[];
   const int E_tot = W * E_loc;
   int* loc_off = sm;            // [E_tot] exclusive prefix of this rank's counts (pad 1)
@@ -280,24 +275,6 @@ __global__ void ep_plan_kernel(const int64_t* __restrict__ idx, const int32_t* _
       }
       if (o == rank && blockIdx.x == 0) recv_offsets[E_loc] = roff;
     }
-    if (blockIdx.x == 0 && seg_tab != nullptr) {
-      // send schedule of the sorted push (ep_push.cuh): local expert index first, owners rotated by rank (remote first,
-      // myself last), so that every rank feeds a different owner at any moment and queues fill expert by expert
-      int v = 0, n = 0;
-      for (int le = 0; le < E_loc; ++le)
-        for (int i = 1; i <= W; ++i) {
-          const int o = (rank + i) % W, ge = o * E_loc + le;
-          const int c = cnt_all[rank * E_tot + ge];
-          int32_t* s = seg_tab + 2 + n * 6;
-          s[0] = v; s[1] = loc_off[ge]; s[2] = o; s[3] = base[ge]; s[4] = le; s[5] = c;
-          v += c;
-          ++n;
-        }
-      seg_tab[0] = n;
-      seg_tab[1] = v;
-    }
-    if (blockIdx.x == 0 && tgt_x != nullptr)      // rows my experts will have received once this call's pushes are in
-      for (int le = 0; le < E_loc; ++le) tgt_x[le] += tot[rank * E_loc + le];
   }
   __syncthreads();
   if (meta != nullptr && peer_inv != nullptr) {
@@ -305,22 +282,37 @@ __global__ void ep_plan_kernel(const int64_t* __restrict__ idx, const int32_t* _
     // the i-th row of src's sorted send list for that expert, i.e. slot inv_src[loc_off_src[ge] + i].  Pulled from the
     // sources' inverse plans (coalesced 4-byte reads over NVLink, ~T*K*4 bytes in total) instead of having every
     // pushed row carry a separate 4-byte remote store.
-    __shared__ int pr[2];
-    for (int pair = blockIdx.x; pair < E_loc * W; pair += gridDim.x) {
+    // every (local expert, source) sub-segment is spread over ALL blocks: the reads are latency-bound (NVLink round
+    // trips), so they want every SM's worth of loads in flight, not one block per sub-segment
+    const int NP = E_loc * W;
+    int* pr = tot + E_tot;       // [3 * NP]: first sorted position at the source, first row in my queue, flat prefix
+    for (int pair = threadIdx.x; pair < NP; pair += blockDim.x) {
       const int le = pair / W, src = pair % W, ge = rank * E_loc + le;
-      if (threadIdx.x == 0) {
-        int p0 = 0, r0 = 0;
-        for (int g2 = 0; g2 < ge; ++g2) p0 += cnt_all[src * E_tot + g2];
-        for (int l2 = 0; l2 < le; ++l2) r0 += (tot[rank * E_loc + l2] + pad - 1) / pad * pad;
-        for (int s2 = 0; s2 < src; ++s2) r0 += cnt_all[s2 * E_tot + ge];
-        pr[0] = p0; pr[1] = r0;
+      int p0 = 0, r0 = 0;
+      for (int g2 = 0; g2 < ge; ++g2) p0 += cnt_all[src * E_tot + g2];
+      for (int l2 = 0; l2 < le; ++l2) r0 += (tot[rank * E_loc + l2] + pad - 1) / pad * pad;
+      for (int s2 = 0; s2 < src; ++s2) r0 += cnt_all[s2 * E_tot + ge];
+      pr[3 * pair] = p0; pr[3 * pair + 1] = r0;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      int run = 0;
+      for (int pair = 0; pair < NP; ++pair) {
+        pr[3 * pair + 2] = run;
+        run += cnt_all[(pair % W) * E_tot + rank * E_loc + pair / W];
       }
-      __syncthreads();
-      const int n = cnt_all[src * E_tot + ge], p0 = pr[0], r0 = pr[1];
-      const int32_t* inv = peer_inv[src];
-      for (int i = threadIdx.x; i < n; i += blockDim.x)
-        if (r0 + i < cap_rows) meta[r0 + i] = (src << 24) | inv[p0 + i];
-      __syncthreads();
+      pr[3 * NP] = run;
+    }
+    __syncthreads();
+    const int total = pr[3 * NP];
+    for (int f = blockIdx.x * blockDim.x + threadIdx.x; f < total; f += gridDim.x * blockDim.x) {
+      int lo = 0, hi = NP;       // largest pair whose flat prefix <= f (empty pairs share their successor's prefix)
+      while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (pr[3 * mid + 2] <= f) lo = mid; else hi = mid;
+      }
+      const int i = f - pr[3 * lo + 2], src = lo % W, row = pr[3 * lo + 1] + i;
+      if (row < cap_rows) meta[row] = (src << 24) | peer_inv[src][pr[3 * lo] + i];
     }
   }
   for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < R; s += gridDim.x * blockDim.x) {
@@ -425,7 +417,7 @@ extern "C" int m3_ep_plan(const int64_t* idx, const int32_t* pos_local, const in
                           int E_loc, int T, int K, int pad, int cap_rows, int32_t* dst_rank, int32_t* dst_row,
                           int32_t* recv_counts, int32_t* recv_offsets, int32_t* recv_tile_expert,
                           int32_t* overflow_flag, int32_t* pos_id, void* const* peer_inv, int32_t* meta,
-                          int32_t* seg_tab, int32_t* tgt_x, m3_stream_t stream) {
+                          m3_stream_t stream) {
   M3_CHECK_ARG(idx && pos_local && cnt_all && dst_rank && dst_row && recv_counts && recv_offsets && recv_tile_expert);
   M3_CHECK_ARG(W >= 1 && rank >= 0 && rank < W && E_loc >= 1 && T >= 0 && K >= 1 && pad >= 1 && cap_rows >= 0);
   M3_CHECK_SHAPE(W * E_loc <= 1024);
@@ -435,9 +427,9 @@ extern "C" int m3_ep_plan(const int64_t* idx, const int32_t* pos_local, const in
   int grid = m3_ceil_div(R, 256);
   if (grid < 1) grid = 1;
   if (grid > 2 * m3::kNumSMs) grid = 2 * m3::kNumSMs;
-  m3::ep_plan_kernel<<<grid, 256, 3 * W * E_loc * sizeof(int), static_cast<cudaStream_t>(stream)>>>(
+  m3::ep_plan_kernel<<<grid, 256, (6 * W * E_loc + 1) * sizeof(int), static_cast<cudaStream_t>(stream)>>>(
       idx, pos_local, cnt_all, rank, W, E_loc, R, pad, cap_rows, dst_rank, dst_row, recv_counts, recv_offsets,
-      recv_tile_expert, overflow_flag, pos_id, reinterpret_cast<int32_t* const*>(peer_inv), meta, seg_tab, tgt_x);
+      recv_tile_expert, overflow_flag, pos_id, reinterpret_cast<int32_t* const*>(peer_inv), meta);
   M3_LAUNCH_CHECK();
   return M3_OK;
 }

@@ -25,7 +25,6 @@
 
 #include "philox.cuh"
 #include "tc_common.cuh"
-#include "ep_push.cuh"
 
 namespace m3 {
 namespace tc {
@@ -64,14 +63,6 @@ struct GGParams {
   // global_gather after the expert GEMM overlaps the GEMM tile by tile; see m3_ep_ffn_fwd in the header.
   const int32_t* ret_meta;     // [rows] or nullptr
   __nv_bfloat16* const* ret_bases;   // [W] peer-mapped [T*K][N] return buffers
-  // Expert parallel, EPI_FC1 / EPI_DGELU ("overlapped push", ep_push.cuh): the LAST push_ctas CTAs of the grid do not
-  // run the GEMM but push this rank's rows into the owners' queues; the GEMM CTAs' producers wait for arrive[e] to reach
-  // target[e] before the first tile of local expert e.
-  const int32_t* arrive;       // [E] arrival counters of MY queue (peers add to them), or nullptr
-  const int32_t* target;       // [E]
-  int push_ctas;               // even (whole CTA pairs); 0 = no pusher in this launch
-  int sm_limit;                // host side only: CTAs of this launch (GEMM + pushers), 0 = the library default
-  EpPush push;
 };
 
 template <int BN, int EPI, int NCTA, int EW, int CWP>
@@ -140,15 +131,6 @@ gg_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
   static_assert((2 * STAGES + 4 + EW) * 8 + 4 <= 512, "barrier block");
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  constexpr bool kCanPush = (EPI == EPI_FC1 || EPI == EPI_DGELU);
-  const int gemm_ctas = (int)gridDim.x - (kCanPush ? p.push_ctas : 0);
-  if (kCanPush && (int)blockIdx.x >= gemm_ctas) {
-    // pusher CTA (whole clusters of them: no cluster barrier, TMEM or mbarrier of the GEMM is touched)
-    pdl_wait();
-    pdl_trigger();
-    ep_push_rows(p.push, (int)blockIdx.x - gemm_ctas, p.push_ctas, smem, Cfg::SMEM - 1024);
-    return;
-  }
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
@@ -179,7 +161,7 @@ gg_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
   const int n_tiles = p.N / BN;
   const int m_tiles = p.offsets[p.E] / BM;
   const int kchunks = p.Kd / BK;
-  const int unit = blockIdx.x / NCTA, n_units = gemm_ctas / NCTA;
+  const int unit = blockIdx.x / NCTA, n_units = gridDim.x / NCTA;
   const int total = (m_tiles / NCTA) * n_tiles;
   const int my_tiles = unit < total ? (total - unit + n_units - 1) / n_units : 0;
   // local tile index -> (M-tile of this CTA, N-tile)
@@ -198,7 +180,7 @@ gg_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
     const uint32_t full0 = NCTA == 2 ? mapa_u32(smem_u32(&full[0]), 0) : smem_u32(&full[0]);   // leader's barriers
     Tracer trc(p.trace, p.trace_cap, 0);
     uint32_t phase = 0;
-    int ti = 0, kc = 0, m_blk = 0, b_row = 0, arrived_e = -1;
+    int ti = 0, kc = 0, m_blk = 0, b_row = 0;
     for (int f0 = 0; f0 < F; f0 += STAGES) {
 #pragma unroll
       for (int st = 0; st < STAGES; ++st) {
@@ -207,10 +189,6 @@ gg_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
             m_blk = tile_mblk(ti);
             const int e = p.tile_expert[(m_blk * BM) / M3_PAD_ROWS];
             b_row = e * p.N + tile_nblk(ti) * BN + (int)cta_rank * (BN / NCTA);
-            if (kCanPush && p.arrive != nullptr && e != arrived_e) {   // overlapped push: expert e's rows must be in
-              ep_wait_arrival(p.arrive + e, p.target[e]);
-              arrived_e = e;
-            }
           }
           trc.ev(0x00, f0 + st);
           mbar_wait(&empty[st], phase ^ 1);
@@ -729,15 +707,9 @@ static int launch_gg_t(const CUtensorMap* maps, const GGParams& p, int max_tiles
   auto kern = gg_kernel<BN, EPI, kGGNcta, EW, CWP>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
   if (e != cudaSuccess) return (int)e;
-  const int push_ctas = (EPI == EPI_FC1 || EPI == EPI_DGELU) ? p.push_ctas : 0;
-  int sms = g_gemm_sms;
-  if (p.sm_limit > 0 && p.sm_limit < sms) sms = p.sm_limit;
-  sms -= push_ctas;                          // the pusher CTAs of an overlapped launch need SMs of their own
-  if (sms < kGGNcta) return M3_ERR_ARG;
-  int grid = max_tiles < sms ? max_tiles : sms;
+  int grid = max_tiles < g_gemm_sms ? max_tiles : g_gemm_sms;
   grid = grid / kGGNcta * kGGNcta;
   if (grid < kGGNcta) grid = kGGNcta;
-  grid += push_ctas;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(grid);
   cfg.blockDim = dim3(gg_threads(EW));
@@ -875,23 +847,6 @@ static bool chain_inference(int D, int H) {
 }
 int m3_ffn_bf16_chain_mode(int D, int H) { return chain_inference(D, H) ? 1 : 0; }
 
-// overlapped push (ep_push.cuh): the first GEMM of the call also carries the pusher CTAs and waits on arrival counters
-static int fill_push(GGParams& p, const m3_ep_push_t& u, int mode, int D, int cap_rows) {
-  if (!u.src || !u.inv_pos || !u.seg_tab || !u.peer_queue || !u.peer_counters || !u.my_counters || !u.my_targets)
-    return M3_ERR_ARG;
-  if (u.push_ctas < 2 || (u.push_ctas & 1) || u.K < 1 || (u.src_dtype != M3_F32 && u.src_dtype != M3_BF16)) return M3_ERR_ARG;
-  if (mode == 1 && (!u.score || !u.ysave || !u.dscore)) return M3_ERR_ARG;
-  if (D % 8 != 0) return M3_ERR_SHAPE;
-  p.arrive = u.my_counters; p.target = u.my_targets; p.push_ctas = u.push_ctas; p.sm_limit = u.sm_limit;
-  p.push.src = u.src; p.push.src_f32 = u.src_dtype == M3_F32; p.push.mode = mode;
-  p.push.inv = u.inv_pos; p.push.seg = u.seg_tab;
-  p.push.dst_bases = reinterpret_cast<bf16* const*>(u.peer_queue);
-  p.push.cnt_bases = reinterpret_cast<int32_t* const*>(u.peer_counters);
-  p.push.K = u.K; p.push.D = D; p.push.cap_rows = cap_rows;
-  p.push.score = u.score; p.push.ysave = static_cast<const bf16*>(u.ysave); p.push.dscore = u.dscore;
-  return M3_OK;
-}
-
 // Opaque activation state handed from m3_ffn_fwd to m3_ffn_bwd (bf16): two [cap][H] planes,
 //   plane 0 = gelu'(z),  plane 1 = h = gelu(z)
 size_t m3_ffn_bf16_saved_bytes(int cap_rows, int D, int H) { (void)D; return 2 * align256((size_t)cap_rows * H * 2); }
@@ -908,7 +863,7 @@ size_t m3_ffn_bf16_workspace_bytes(int cap_rows, int D, int H, int E, int backwa
 int m3_ffn_fwd_bf16(const void* xq, const int32_t* offsets, const int32_t* tile_expert, int cap_rows, int E, int D,
                     int H, const void* w1, const float* b1, const void* w2, const float* b2, void* saved, void* yq,
                     void* workspace, size_t workspace_bytes, float drop_p, const void* rng, const int32_t* ret_meta,
-                    void* const* ret_bases, const m3_ep_push_t* push, cudaStream_t st) {
+                    void* const* ret_bases, cudaStream_t st) {
   if (drop_p > 0.f && (saved == nullptr || rng == nullptr)) return M3_ERR_ARG;     // dropout is a training-time op
   if ((ret_meta == nullptr) != (ret_bases == nullptr) || (ret_meta == nullptr && yq == nullptr)) return M3_ERR_ARG;
   if (workspace == nullptr || workspace_bytes < m3_ffn_bf16_workspace_bytes(cap_rows, D, H, E, 0)) return M3_ERR_WORKSPACE;
@@ -919,7 +874,6 @@ int m3_ffn_fwd_bf16(const void* xq, const int32_t* offsets, const int32_t* tile_
   bf16* gp = static_cast<bf16*>(saved);
   bf16* h = saved ? reinterpret_cast<bf16*>(static_cast<uint8_t*>(saved) + hbytes) : static_cast<bf16*>(workspace);
   GGParams p{};
-  int rc_push = 0;
   p.offsets = offsets; p.tile_expert = tile_expert; p.E = E;
   // fc1: h = gelu(xq W1^T + b1); gelu'(.) saved for backward
   p.N = H; p.Kd = D; p.bias = b1; p.save_out2 = saved != nullptr;
@@ -928,13 +882,8 @@ int m3_ffn_fwd_bf16(const void* xq, const int32_t* offsets, const int32_t* tile_
     p.drop_inv_keep = 1.0f / (1.0f - drop_p);
     p.rng = static_cast<const RngState*>(rng);
   }
-  if (push != nullptr) {
-    rc_push = fill_push(p, *push, 0, D, cap_rows);
-    if (rc_push) return rc_push;
-  }
   int rc = launch_gg<EPI_FC1>(xq, w1, h, gp, nullptr, p, cap_rows, st);
   if (rc) return rc;
-  p.push_ctas = 0; p.arrive = nullptr;
   // fc2: yq = h W2^T + b2
   p.N = D; p.Kd = H; p.bias = b2; p.save_out2 = 0; p.drop_thr = 0u;
   p.ret_meta = ret_meta; p.ret_bases = reinterpret_cast<bf16* const*>(ret_bases);      // expert parallel: rows go home
@@ -945,7 +894,7 @@ int m3_ffn_bwd_bf16(const void* xq, const void* saved, const void* dyq, const in
                     const int32_t* tile_expert, int cap_rows, int E, int D, int H, const void* w1, const void* w2,
                     const void* w1t, const void* w2t, void* dxq, float* dw1, float* db1, float* dw2, float* db2,
                     void* workspace, size_t workspace_bytes, int parts, const int32_t* ret_meta, void* const* ret_bases,
-                    const m3_ep_push_t* push, cudaStream_t st) {
+                    cudaStream_t st) {
   (void)counts; (void)w1; (void)w2;
   if ((ret_meta == nullptr) != (ret_bases == nullptr) || (ret_meta == nullptr && dxq == nullptr)) return M3_ERR_ARG;
   if (workspace_bytes < m3_ffn_bf16_workspace_bytes(cap_rows, D, H, E, 1)) return M3_ERR_WORKSPACE;
@@ -961,13 +910,8 @@ int m3_ffn_bwd_bf16(const void* xq, const void* saved, const void* dyq, const in
     p.offsets = offsets; p.tile_expert = tile_expert; p.E = E;
     // dz = (dyq W2) * gelu'(z)                              B = W2^T [E][H][D] (K-major in D)
     p.N = H; p.Kd = D;
-    if (push != nullptr) {
-      rc = fill_push(p, *push, 1, D, cap_rows);
-      if (rc) return rc;
-    }
     rc = launch_gg<EPI_DGELU>(dyq, w2t, dz, nullptr, saved, p, cap_rows, st);
     if (rc) return rc;
-    p.push_ctas = 0; p.arrive = nullptr;
     // dxq = dz W1                                           B = W1^T [E][D][H] (K-major in H)
     p.N = D; p.Kd = H;
     p.ret_meta = ret_meta; p.ret_bases = reinterpret_cast<bf16* const*>(ret_bases);    // expert parallel: rows go home

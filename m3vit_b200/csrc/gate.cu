@@ -763,7 +763,7 @@ static int gate_bwd_impl(const void* x, int x_dtype, int64_t ldx, const float* t
                          m3_stream_t stream) {
   if ((importance == nullptr) != (dcv_loss == nullptr)) return M3_ERR_ARG;
   M3_CHECK_ARG(x && w_gate && logits && idx_full && dz && dw_gate && workspace);
-  M3_CHECK_ARG(T > 0 && D > 0 && Dt >= 0 && (Dt == 0 || task_feat));
+  M3_CHECK_ARG(T >= 0 && D > 0 && Dt >= 0 && (Dt == 0 || task_feat));
   M3_CHECK_SHAPE(D % 4 == 0 && D / 4 * 2 <= 1024 && K >= 1 && K <= E);
   M3_CHECK_SHAPE(x_dtype == M3_F32 || x_dtype == M3_BF16);
   M3_CHECK_ALIGN16(x); M3_CHECK_ALIGN16(w_gate); M3_CHECK_ALIGN16(logits); M3_CHECK_ALIGN16(dz);
@@ -772,6 +772,11 @@ static int gate_bwd_impl(const void* x, int x_dtype, int64_t ldx, const float* t
   if (workspace_bytes < m3_gate_bwd_workspace_bytes(T, D, Dt, E)) return M3_ERR_WORKSPACE;
   const int K1 = K + 1 < E ? K + 1 : E;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (T == 0) {      // an empty token subset (m3_gate_fwd accepts it too): the weight gradients are zero
+    cudaError_t e = cudaMemsetAsync(dw_gate, 0, (size_t)(D + Dt) * E * sizeof(float), st);
+    if (e == cudaSuccess && dtask_feat != nullptr && Dt > 0) e = cudaMemsetAsync(dtask_feat, 0, (size_t)Dt * sizeof(float), st);
+    return e == cudaSuccess ? M3_OK : (int)e;
+  }
   {
     const int64_t nthr = (int64_t)T * (E / 4);
     const int grid = (int)((nthr + 255) / 256);

@@ -40,9 +40,8 @@ struct Queue {
 
 template <typename TO>
 __device__ __forceinline__ void zero_pad_rows(TO* q, const int32_t* counts, const int32_t* offsets, int e, int D,
-                                              int32_t* meta = nullptr, int32_t* tgt = nullptr) {
+                                              int32_t* meta = nullptr) {
   const int r0 = offsets[e] + counts[e], r1 = offsets[e + 1];
-  if (tgt != nullptr && threadIdx.x == 0) tgt[e] += counts[e];      // arrival target of the overlapped push (ep_push.cuh)
   if (meta != nullptr)      // expert parallel, return store: a padding row has no home (m3_ep_ffn_fwd)
     for (int i = threadIdx.x; i < r1 - r0; i += kPermThreads) meta[r0 + i] = -1;
   const int nvec = D / 8;
@@ -56,10 +55,10 @@ __device__ __forceinline__ void zero_pad_rows(TO* q, const int32_t* counts, cons
 template <typename TO>
 __global__ void __launch_bounds__(kPermThreads)
 zero_pad_rows_kernel(TO* __restrict__ q, const int32_t* __restrict__ counts, const int32_t* __restrict__ offsets, int D,
-                     int32_t* __restrict__ meta, int32_t* __restrict__ tgt) {
+                     int32_t* __restrict__ meta) {
   pdl_wait();
   pdl_trigger();
-  zero_pad_rows<TO>(q, counts, offsets, blockIdx.x, D, meta, tgt);
+  zero_pad_rows<TO>(q, counts, offsets, blockIdx.x, D, meta);
 }
 
 // xq[pos[t,k]] = cast(x[t]); trailing CTAs zero the padding rows of every queue.
@@ -762,12 +761,12 @@ extern "C" int m3_ep_dispatch_bwd(void* const* peer_dxq, int dxq_dtype, const in
 }
 
 extern "C" int m3_zero_pad_rows(void* q, int dtype, const int32_t* counts, const int32_t* offsets, int E, int D,
-                                int32_t* meta, int32_t* arrival_target, m3_stream_t stream) {
+                                int32_t* meta, m3_stream_t stream) {
   M3_CHECK_ARG(q && counts && offsets && E >= 1 && D >= 8 && D % 8 == 0);
   M3_CHECK_ALIGN16(q);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (dtype == M3_F32) zero_pad_rows_kernel<float><<<E, kPermThreads, 0, st>>>((float*)q, counts, offsets, D, meta, arrival_target);
-  else if (dtype == M3_BF16) zero_pad_rows_kernel<bf16><<<E, kPermThreads, 0, st>>>((bf16*)q, counts, offsets, D, meta, arrival_target);
+  if (dtype == M3_F32) zero_pad_rows_kernel<float><<<E, kPermThreads, 0, st>>>((float*)q, counts, offsets, D, meta);
+  else if (dtype == M3_BF16) zero_pad_rows_kernel<bf16><<<E, kPermThreads, 0, st>>>((bf16*)q, counts, offsets, D, meta);
   else return M3_ERR_UNSUPPORTED;
   M3_LAUNCH_CHECK();
   return M3_OK;

@@ -102,7 +102,7 @@ static __device__ __noinline__ void mbar_wait_slow(uint32_t bar, uint32_t parity
         : "r"(bar), "r"(parity)
         : "memory");
     if (ok) return;
-    if (clock64() - t0 > 20000000000LL) {  // ~10 s (the producer of an overlapped EP launch may be waiting for a peer)
+    if (clock64() - t0 > 4000000000LL) {  // ~2 s
       printf("m3 tcgen05: mbarrier timeout (block %d thread %d parity %u)\n", blockIdx.x, threadIdx.x, parity);
       __trap();
     }

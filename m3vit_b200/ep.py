@@ -23,12 +23,9 @@ world_size > 1) is replaced by peer-mapped expert queues:
     tensor cores work on the next tile.  No result queue exists on the owner, nothing is pulled; after the
     rendezvous the source combines its own return buffer with the local kernels.  M3_EP_RETURN=0 (or fp32
     queues) selects the pull protocol above.
-  * ... and the PUSH half runs inside the first expert GEMM ("overlapped push", csrc/ep_push.cuh; M3_EP_OVERLAP=0
-    switches it off): the last M3_EP_PUSH_CTAS (32) CTAs of the fc1 launch (forward) / of the dz launch (backward)
-    store this rank's rows, sorted by destination expert, into the owners' queues and publish them chunk by chunk on
-    the owners' arrival counters; the GEMM CTAs of the same launch wait per local expert for their rows.  No dispatch
-    kernel, no rendezvous between push and GEMM: 3 device rendezvous per layer call (forward + backward) instead
-    of 5, and every NVLink transfer of the layer runs under a GEMM.
+    The push half stays a kernel of its own: running it on 16-64 CTAs of the first GEMM's launch behind arrival
+    counters was built and measured (cp.async row pipelines, TMA bulk copies; bit-identical) and lost, 72.8 M against
+    83.6 M tokens/s at 2 GPUs - a row mover needs all 148 SMs to keep NVLink busy.
 
 The protocol is written as explicit phases so that it runs either over torch.distributed
 (one process per GPU, NCCL) or as a single-process multi-rank simulation (tests; one GPU
@@ -43,7 +40,7 @@ from typing import List, Optional
 import torch
 
 from . import ops
-from ._lib import PAD_ROWS, EpPush, check, dtype_code, load, ptr, stream_ptr
+from ._lib import PAD_ROWS, check, dtype_code, load, ptr, stream_ptr
 
 
 # ----------------------------------------------------------------------------- arena
@@ -186,19 +183,6 @@ class EPContext:
     capacity_factor: Optional[float]    # receive-queue rows = factor * T*K (None: worst case W - nothing can be dropped)
     overflow: torch.Tensor              # [1] int32 device flag set by m3_ep_plan
 
-    def __post_init__(self):
-        import os
-        # arrival counters of the overlapped push: [0:1024] forward (x rows), [1024:2048] backward (dy rows), one per
-        # local expert; they only ever grow (peers add to them), the owner keeps running targets in `tgt`
-        self.off_cnt = self.arena.alloc(8192)
-        self.arena._bytes[self.off_cnt:self.off_cnt + 8192].zero_()
-        self.cnt_peers = (self.bases + self.off_cnt, self.bases + (self.off_cnt + 4096))
-        self.cnt_mine = (self.arena.base + self.off_cnt, self.arena.base + self.off_cnt + 4096)
-        self.tgt = torch.zeros(2, 1024, dtype=torch.int32, device=self.arena.device)
-        self.overlap = os.environ.get("M3_EP_OVERLAP", "1") != "0"
-        self.push_ctas = int(os.environ.get("M3_EP_PUSH_CTAS", "32"))
-        self.sm_limit = 0                  # CTAs of an overlapped GEMM launch (tests: several ranks share one GPU)
-
     def peer_ptrs(self, off: int) -> torch.Tensor:
         """[W] device array of `arena base + off` of every rank.  Cached: the lockstep allocator hands out the same
         few offsets call after call, and `bases + off` would otherwise launch a kernel each time."""
@@ -299,12 +283,8 @@ def make_context(group, device, arena_bytes: int, capacity_factor: Optional[floa
                 bases.append(p.value)
     bases_t = torch.tensor(bases, dtype=torch.int64, device=device)
     sync_group = PeerFlagGroup(group.rank, group.world, arena, bases_t, group) if device_barrier else group
-    ctx = EPContext(group.rank, group.world, sync_group, arena, bases_t, capacity_factor,
-                    torch.zeros(1, dtype=torch.int32, device=device))
-    torch.cuda.synchronize(device)           # arrival counters are zeroed everywhere before anybody pushes
-    group.barrier(device)
-    torch.cuda.synchronize(device)
-    return ctx
+    return EPContext(group.rank, group.world, sync_group, arena, bases_t, capacity_factor,
+                     torch.zeros(1, dtype=torch.int32, device=device))
 
 
 # ----------------------------------------------------------------------------- phases
@@ -325,11 +305,8 @@ class EPFwdState:
     nbytes_q: int = 0
     # return-store protocol (bf16): row origins of my receive queue, my slot-ordered return buffer (= ysave), identity plan
     ret: bool = False
-    ovl: bool = False                         # overlapped push (ret only)
     off_inv: int = -1
     inv: Optional[torch.Tensor] = None        # [T*K] sorted position -> slot, in the arena (peers read it)
-    seg_tab: Optional[torch.Tensor] = None
-    x: Optional[torch.Tensor] = None
     off_meta: int = -1
     off_yret: int = -1
     meta: Optional[torch.Tensor] = None
@@ -367,42 +344,26 @@ def phase_b_dispatch(ctx: EPContext, st: EPFwdState, x, cnt_all, E_loc, top_k, c
     ro = torch.empty(E_loc + 1, dtype=torch.int32, device=dev)
     rt = torch.empty(st.cap // PAD_ROWS, dtype=torch.int32, device=dev)
     st.ret = st.ret and st.inv is not None
-    st.ovl = st.ret and ctx.overlap
     el = 2 if cdt == torch.bfloat16 else 4
-    peers_inv = tgt = None
+    peers_inv = None
     if st.ret:
         st.pos_id = torch.empty(R, dtype=torch.int32, device=dev)
         st.nbytes_ret = R * D * el
         st.off_meta = ctx.arena.alloc(st.cap * 4)
         st.meta = ctx.arena.view(st.off_meta, st.cap, 1, torch.int32)
         peers_inv = ctx.peer_ptrs(st.off_inv)
-    if st.ovl:
-        st.seg_tab = torch.empty(2 + 6 * W * E_loc, dtype=torch.int32, device=dev)
-        st.x = x
-        tgt = ctx.tgt[0]
     check(lib.m3_ep_plan(ptr(st.g.idx), ptr(st.plan_local.pos), ptr(cnt_all), ctx.rank, W, E_loc, T, top_k, PAD_ROWS,
                          st.cap, ptr(st.dst_rank), ptr(st.dst_row), ptr(rc), ptr(ro), ptr(rt), ptr(ctx.overflow),
-                         ptr(st.pos_id), ptr(peers_inv), ptr(st.meta), ptr(st.seg_tab), ptr(tgt), stream_ptr()),
-          "m3_ep_plan")
+                         ptr(st.pos_id), ptr(peers_inv), ptr(st.meta), stream_ptr()), "m3_ep_plan")
     st.recv = ops.Plan(rc, ro, None, rt, st.cap, PAD_ROWS)
     st.nbytes_q = st.cap * D * el
     st.off_xq = ctx.arena.alloc(st.nbytes_q)
     st.xq = ctx.arena.view(st.off_xq, st.cap, D, cdt)
-    if not st.ovl:      # (overlapped push: the rows leave from inside the fc1 launch of phase C)
-        check(lib.m3_ep_dispatch_fwd(ptr(x), dtype_code(x), ptr(st.dst_rank), ptr(st.dst_row), T, top_k, D,
-                                     ptr(ctx.peer_ptrs(st.off_xq)), dtype_code(st.xq), stream_ptr()), "m3_ep_dispatch_fwd")
-        ops.launch_count += 1
-    check(lib.m3_zero_pad_rows(ptr(st.xq), dtype_code(st.xq), ptr(rc), ptr(ro), E_loc, D, ptr(st.meta), None,
-                               stream_ptr()), "m3_zero_pad_rows")
-    ops.launch_count += 2
-
-
-def _push_desc(ctx: EPContext, st: EPFwdState, which: int, src, off_queue: int, score=None, ysave=None, dscore=None) -> EpPush:
-    """m3_ep_push_t of the overlapped push: which = 0 forward (x rows), 1 backward (score * g rows + dscore)."""
-    K = st.g.score.shape[1]
-    return EpPush(ptr(src), dtype_code(src), ptr(st.inv), ptr(st.seg_tab), ptr(ctx.peer_ptrs(off_queue)),
-                  ptr(ctx.cnt_peers[which]), ctx.cnt_mine[which], ptr(ctx.tgt[which]), K, ctx.push_ctas, ctx.sm_limit,
-                  ptr(score), ptr(ysave), ptr(dscore))
+    check(lib.m3_ep_dispatch_fwd(ptr(x), dtype_code(x), ptr(st.dst_rank), ptr(st.dst_row), T, top_k, D,
+                                 ptr(ctx.peer_ptrs(st.off_xq)), dtype_code(st.xq), stream_ptr()), "m3_ep_dispatch_fwd")
+    check(lib.m3_zero_pad_rows(ptr(st.xq), dtype_code(st.xq), ptr(rc), ptr(ro), E_loc, D, ptr(st.meta), stream_ptr()),
+          "m3_zero_pad_rows")
+    ops.launch_count += 3
 
 
 def phase_c_ffn(ctx: EPContext, st: EPFwdState, w1c, b1, w2c, b2, save_hpre: bool, drop=None) -> None:
@@ -418,13 +379,9 @@ def phase_c_ffn(ctx: EPContext, st: EPFwdState, w1c, b1, w2c, b2, save_hpre: boo
     if st.ret:      # fc2's epilogue stores every result row into its SOURCE rank's return buffer (slot order)
         st.off_yret = ctx.arena.alloc(st.nbytes_ret)
         st.ysave = ctx.arena.view(st.off_yret, st.nbytes_ret // (D * 2), D, st.xq.dtype)
-        push = None
-        if st.ovl:      # the fc1 launch also pushes my rows to their owners and waits for the rows of my experts
-            push = C.byref(_push_desc(ctx, st, 0, st.x, st.off_xq))
         check(lib.m3_ep_ffn_fwd(dt, ptr(st.xq), ptr(st.recv.offsets), ptr(st.recv.tile_expert), cap, E_loc, D, H, ptr(w1c),
                                 ptr(b1), ptr(w2c), ptr(b2), ptr(st.hpre), ptr(st.meta), ptr(ctx.peer_ptrs(st.off_yret)),
-                                ptr(ws), ws.numel(), p_drop, rng, push, stream_ptr()), "m3_ep_ffn_fwd")
-        st.x = None
+                                ptr(ws), ws.numel(), p_drop, rng, stream_ptr()), "m3_ep_ffn_fwd")
         ops.launch_count += 2
         return
     st.off_yq = ctx.arena.alloc(st.nbytes_q)
@@ -472,7 +429,6 @@ class EPBwdState:
     ws: Optional[torch.Tensor] = None
     off_dxret: int = -1
     dxret: Optional[torch.Tensor] = None      # return store: my slot-ordered [T*K, D] buffer the owners fill
-    g_out: Optional[torch.Tensor] = None      # overlapped push: the output gradient, pushed from inside the dz launch
 
 
 def phase_e_combine_bwd(ctx: EPContext, st: EPFwdState, g_out, top_k) -> EPBwdState:
@@ -484,19 +440,13 @@ def phase_e_combine_bwd(ctx: EPContext, st: EPFwdState, g_out, top_k) -> EPBwdSt
     bs.off_dyq = ctx.arena.alloc(st.nbytes_q)
     bs.dyq = ctx.arena.view(bs.off_dyq, st.cap, D, st.xq.dtype)
     bs.dscore = torch.empty(T, top_k, dtype=torch.float32, device=g_out.device)
-    if st.ovl:      # overlapped push: score * g rows leave (and dscore is computed) inside the dz launch of phase F
-        bs.g_out = g_out
-        check(lib.m3_zero_pad_rows(ptr(bs.dyq), dtype_code(bs.dyq), ptr(st.recv.counts), ptr(st.recv.offsets), E_loc, D,
-                                   None, ptr(ctx.tgt[1]), stream_ptr()), "m3_zero_pad_rows")
-        ops.launch_count += 1
-        return bs
     py = ctx.peer_ptrs(st.off_yq) if st.off_yq >= 0 else None      # (not needed: dscore comes from the local copy)
     pd = ctx.peer_ptrs(bs.off_dyq)
     check(lib.m3_ep_combine_bwd(ptr(g_out), dtype_code(g_out), ptr(py), ptr(pd), dtype_code(bs.dyq), ptr(st.dst_rank),
                                 ptr(st.dst_row), ptr(st.g.score), T, top_k, D, ptr(bs.dscore), ptr(st.ysave),
                                 stream_ptr()), "m3_ep_combine_bwd")
     check(lib.m3_zero_pad_rows(ptr(bs.dyq), dtype_code(bs.dyq), ptr(st.recv.counts), ptr(st.recv.offsets), E_loc, D,
-                               None, None, stream_ptr()), "m3_zero_pad_rows")
+                               None, stream_ptr()), "m3_zero_pad_rows")
     ops.launch_count += 2
     return bs
 
@@ -522,15 +472,10 @@ def phase_f_ffn_bwd(ctx: EPContext, st: EPFwdState, bs: EPBwdState, w1c, w2c, w1
     dw1, db1, dw2, db2 = bs.grads
     p, rng = (float(drop[0]), ptr(drop[1])) if (drop is not None and drop[0] > 0) else (0.0, None)
     if st.ret:
-        push = None
-        if st.ovl and (parts & 1):
-            push = C.byref(_push_desc(ctx, st, 1, bs.g_out, bs.off_dyq, st.g.score, st.ysave, bs.dscore))
         check(lib.m3_ep_ffn_bwd(dt, ptr(st.xq), ptr(st.hpre), ptr(bs.dyq), ptr(st.recv.counts), ptr(st.recv.offsets),
                                 ptr(st.recv.tile_expert), cap, E_loc, D, H, ptr(w1c), ptr(w2c), ptr(w1t), ptr(w2t),
                                 ptr(st.meta), ptr(ctx.peer_ptrs(bs.off_dxret)), ptr(dw1), ptr(db1), ptr(dw2), ptr(db2),
-                                ptr(bs.ws), bs.ws.numel(), p, rng, int(parts), push, stream_ptr()), "m3_ep_ffn_bwd")
-        if parts & 1:
-            bs.g_out = None
+                                ptr(bs.ws), bs.ws.numel(), p, rng, int(parts), stream_ptr()), "m3_ep_ffn_bwd")
     else:
         check(lib.m3_ffn_bwd_parts(dt, ptr(st.xq), ptr(st.hpre), ptr(bs.dyq), ptr(st.recv.counts), ptr(st.recv.offsets),
                                    ptr(st.recv.tile_expert), cap, E_loc, D, H, ptr(w1c), ptr(w2c), ptr(w1t), ptr(w2t),
@@ -615,8 +560,7 @@ class EPMoEFunction(torch.autograd.Function):
         else:
             w1c, w2c, w1t, w2t = w1, w2, None, None
         needs_grad = any(ctx.needs_input_grad)
-        if not st.ovl:
-            grp.barrier(x.device)                                     # every push has landed
+        grp.barrier(x.device)                                         # every push has landed
         phase_c_ffn(ep, st, w1c, b1, w2c, b2, needs_grad, drop)
         grp.barrier(x.device)                                         # every owner's yq is complete
         out = phase_d_combine(ep, st, T, D, top_k, x.dtype, keep_rows=needs_grad)
@@ -643,8 +587,7 @@ class EPMoEFunction(torch.autograd.Function):
         if d_out is None:
             d_out = torch.zeros_like(x)
         bs = phase_e_combine_bwd(ep, st, d_out.contiguous(), top_k)     # (fresh dyq block: nobody reads or writes it yet)
-        if not st.ovl:
-            grp.barrier(x.device)                                     # every dy push has landed
+        grp.barrier(x.device)                                         # every dy push has landed
         # Data gradients first: they are what the peers wait for (with the return store the dgrad epilogue sends every dxq
         # row home over NVLink while the tensor cores run the next tile).  The weight gradients and the router backward
         # need nothing from the peers and run before the rendezvous, where they also absorb rank skew.  (Running the weight

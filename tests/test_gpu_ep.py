@@ -46,31 +46,11 @@ def test_ep_plan_kernel_bit_exact(W, E_loc, K):
         o = dict(dst_rank=torch.empty(R, dtype=torch.int32, device=dev), dst_row=torch.empty(R, dtype=torch.int32, device=dev),
                  rc=torch.empty(E_loc, dtype=torch.int32, device=dev), ro=torch.empty(E_loc + 1, dtype=torch.int32, device=dev),
                  rt=torch.full((cap // PAD,), -7, dtype=torch.int32, device=dev), fl=torch.zeros(1, dtype=torch.int32, device=dev),
-                 pid=torch.full((R,), -9, dtype=torch.int32, device=dev),
-                 seg=torch.full((2 + 6 * E_tot,), -3, dtype=torch.int32, device=dev),
-                 tgt=torch.full((E_loc,), 5, dtype=torch.int32, device=dev))
+                 pid=torch.full((R,), -9, dtype=torch.int32, device=dev))
         _lib.check(lib.m3_ep_plan(idx.data_ptr(), pl.pos.data_ptr(), cnt_all.to(dev).data_ptr(), r, W, E_loc, Ts[r], K,
                                   PAD, cap, o["dst_rank"].data_ptr(), o["dst_row"].data_ptr(), o["rc"].data_ptr(),
                                   o["ro"].data_ptr(), o["rt"].data_ptr(), o["fl"].data_ptr(), o["pid"].data_ptr(),
-                                  None, None, o["seg"].data_ptr(), o["tgt"].data_ptr(),
-                                  torch.cuda.current_stream().cuda_stream), "m3_ep_plan")
-        # send schedule of the overlapped push: every live slot exactly once, segments contiguous in the owner's queue
-        seg = o["seg"].cpu().tolist()
-        V, live = seg[0], seg[1]
-        assert V == E_tot and live == int((drow >= 0).sum())
-        inv = torch.empty(R, dtype=torch.int64)
-        inv[pl.pos.cpu().long()] = torch.arange(R)
-        seen, run = torch.zeros(R, dtype=torch.bool), 0
-        for v in range(V):
-            vstart, src0, orank, row0, le, n = seg[2 + 6 * v: 8 + 6 * v]
-            assert vstart == run and n == int(cnt_all[r, orank * E_loc + le])
-            slots = inv[src0:src0 + n]
-            assert torch.equal(dr[slots], torch.full((n,), orank, dtype=torch.int32))
-            assert torch.equal(drow[slots], torch.arange(row0, row0 + n, dtype=torch.int32))
-            seen[slots] = True
-            run += n
-        assert bool(seen.all())
-        assert torch.equal(o["tgt"].cpu()[:E_loc], rc + 5)       # running target: += rows received per local expert
+                                  None, None, torch.cuda.current_stream().cuda_stream), "m3_ep_plan")
         assert torch.equal(o["dst_rank"].cpu(), dr) and torch.equal(o["dst_row"].cpu(), drow)
         # identity plan of the slot-ordered return buffers: s for a live slot, -1 for a dropped one
         assert torch.equal(o["pid"].cpu(), torch.where(drow >= 0, torch.arange(R, dtype=torch.int32), torch.tensor(-1, dtype=torch.int32)))
@@ -82,17 +62,13 @@ def test_ep_plan_kernel_bit_exact(W, E_loc, K):
 
 
 @pytest.mark.parametrize("W", [2, 4])
-@pytest.mark.parametrize("cdt,mode", [(torch.float32, "pull"), (torch.bfloat16, "pull"), (torch.bfloat16, "ret"),
-                                      (torch.bfloat16, "ovl")])
+@pytest.mark.parametrize("cdt,mode", [(torch.float32, "pull"), (torch.bfloat16, "pull"), (torch.bfloat16, "ret")])
 def test_ep_simulation_matches_single_gpu(W, cdt, mode, monkeypatch):
-    """pull: rows pushed by the dispatch kernels, results pulled by the combine kernels (5 rendezvous per call).
-    ret: the return store (fc2 / dgrad epilogues send every result row straight into the source rank's return buffer;
-    m3_ep_ffn_fwd / m3_ep_ffn_bwd).  ovl: ret + the push run by CTAs of the first GEMM launch, which waits on arrival
-    counters - every simulated rank then needs its own stream and a share of the SMs, because its GEMM CTAs spin until the
-    OTHER ranks' pusher CTAs have delivered.  All three must equal the single-GPU layer bit for bit."""
+    """pull: results pulled by the combine kernels.  ret: the return store (fc2 / dgrad epilogues send every result row
+    straight into the source rank's return buffer; m3_ep_ffn_fwd / m3_ep_ffn_bwd; row origins read from the sources' inverse
+    plans).  Both must equal the single-GPU layer bit for bit."""
     from m3vit_b200 import ep, ops, functions as F_
     monkeypatch.setenv("M3_EP_RETURN", "0" if mode == "pull" else "1")
-    monkeypatch.setenv("M3_EP_OVERLAP", "1" if mode == "ovl" else "0")
     dev = torch.device("cuda:0")
     E_tot, K, D, H, T = 16, 4, 128, 256, 333
     E_loc = E_tot // W
@@ -118,20 +94,6 @@ def test_ep_simulation_matches_single_gpu(W, cdt, mode, monkeypatch):
 
     # ---- EP simulation in lockstep
     ctxs = make_sim(W, dev, 64 << 20)
-    streams = [torch.cuda.Stream() for _ in range(W)] if mode == "ovl" else None
-    for c in ctxs:
-        c.sm_limit, c.push_ctas = (148 // W) // 2 * 2, 4
-
-    def on_rank_stream(r, fn):
-        if streams is None:
-            return fn()
-        streams[r].wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(streams[r]):
-            return fn()
-
-    def join():
-        for s_ in streams or []:
-            torch.cuda.current_stream().wait_stream(s_)
     sl = lambda t, r: t[r * E_loc:(r + 1) * E_loc].contiguous()
     if cdt == torch.bfloat16:
         wl = []
@@ -147,9 +109,8 @@ def test_ep_simulation_matches_single_gpu(W, cdt, mode, monkeypatch):
         assert torch.equal(sts[r].plan_local.counts, ref[r]["counts"])
         ep.phase_b_dispatch(ctxs[r], sts[r], xs[r], cnt_all, E_loc, K, cdt)
     for r in range(W):
-        on_rank_stream(r, lambda: ep.phase_c_ffn(ctxs[r], sts[r], wl[r][0], sl(b1, r), wl[r][1], sl(b2, r), True))
-    join()
-    assert all(s.ret == (mode != "pull") and s.ovl == (mode == "ovl") for s in sts)
+        ep.phase_c_ffn(ctxs[r], sts[r], wl[r][0], sl(b1, r), wl[r][1], sl(b2, r), True)
+    assert all(s.ret == (mode != "pull") for s in sts)
     outs = [ep.phase_d_combine(ctxs[r], sts[r], T, D, K, torch.float32) for r in range(W)]
     for c in ctxs:
         c.check_overflow()
@@ -159,8 +120,7 @@ def test_ep_simulation_matches_single_gpu(W, cdt, mode, monkeypatch):
         torch.testing.assert_close(outs[r], ref[r]["out"], **tol)
     bss = [ep.phase_e_combine_bwd(ctxs[r], sts[r], gos[r], K) for r in range(W)]
     for r in range(W):
-        on_rank_stream(r, lambda: ep.phase_f_ffn_bwd(ctxs[r], sts[r], bss[r], *wl[r]))
-    join()
+        ep.phase_f_ffn_bwd(ctxs[r], sts[r], bss[r], *wl[r])
     g_tol = 1e-5 if cdt == torch.float32 else 2e-2
     sum_ref = {k: sum(ref[r][k] for r in range(W)) for k in ("dw1", "db1", "dw2", "db2")}
     for r in range(W):

@@ -134,6 +134,15 @@ def test_layer_bf16_within_tolerance(fname):
         assert nerr(dict(layer.named_parameters())[gname].grad.cpu(), rec["grads"][gname]) <= 3e-2
         assert nerr(layer.experts.h4toh.bias.grad.cpu(), rec["grads"]["experts.h4toh.bias"]) <= 3e-2
         assert nerr(layer.experts.htoh4.bias.grad.cpu(), rec["grads"]["experts.htoh4.bias"]) <= 3e-2
+        # expert weight gradients of the tcgen05 wgrad kernels against the reference's own fp32 gradients
+        for name in ("experts.htoh4.weight", "experts.h4toh.weight"):
+            p, want = dict(layer.named_parameters())[name], rec["grads"][name]
+            got = p.grad.cpu()
+            if got.shape != want.shape:      # large fixtures keep experts 0 and E-1, every max(stride, 4)-th row, + a checksum
+                got = got[[0, case.num_expert - 1]][:, ::max(stride, 4)]
+                s, a = rec["grads"][name + ".checksum"]
+                assert abs(float(p.grad.double().sum()) - s) <= 3e-2 * a + 1e-6, name
+            assert nerr(got, want) <= 3e-2, (name, nerr(got, want))
 
 
 def test_full_size_properties_bf16_and_fp32():

@@ -45,15 +45,13 @@ def main():
         cnt = grp.all_gather_counts(st.plan_local.counts); mark("  counts gather")
         ctx.apply_deferred_frees()
         ep.phase_b_dispatch(ctx, st, x, cnt, E_loc, K, cdt); mark("B ep_plan+push x")
-        if not st.ovl:
-            grp.barrier(dev); mark("  barrier")
+        grp.barrier(dev); mark("  barrier")
         ep.phase_c_ffn(ctx, st, w1c, b1, w2c, b2, True); mark("C ffn fwd")
         grp.barrier(dev); mark("  barrier")
         out = ep.phase_d_combine(ctx, st, T, D, K, torch.float32); mark("D combine (pull y | local)")
         grp.barrier(dev); mark("  barrier")
         bs = ep.phase_e_combine_bwd(ctx, st, go, K); mark("E push dy")
-        if not st.ovl:
-            grp.barrier(dev); mark("  barrier")
+        grp.barrier(dev); mark("  barrier")
         ep.phase_f_ffn_bwd(ctx, st, bs, w1c, w2c, w1t, w2t); mark("F ffn bwd")
         dz, dwg, _, _ = ops.gate_bwd(x, wg, st.g.noisy_logits, st.g.idx_full, K, dscore=bs.dscore); mark("  gate bwd")
         grp.barrier(dev); mark("  barrier")
