@@ -14,7 +14,10 @@ value  : tokens resident in HBM, CUDA-event timed, max over ranks.
 e2e    : same step through the public module API with HOST (pinned) token buffers:
          per layer call H2D of the tokens (prefetched one call ahead on a copy stream,
          double-buffered) and D2H of the loss scalars inside the timed region.
-roofline: the grouped expert-FFN GEMM kernel (gg_kernel), tensor-bound, timed live.
+roofline: the grouped expert-FFN GEMM kernel (gg_kernel: the fc1 / fc2 launches of a training forward), timed
+         live.  Both rooflines are reported (algorithmic bytes / HBM copy peak and flops / cuBLAS bf16 peak); `bound`
+         is the one that binds - at D = H = 384 with the activation planes kept for backward the pair runs at
+         154 flop/B, below the ridge of 250 flop/B, so that is HBM.
 cpu_baseline / --impl reference: the CPU oracle port of the reference layer
          (oracle/moe_oracle.py, fp32 PyTorch on the host cores) on the SAME workload
          (same B, same N, both task gates); each step is a bounded sample of the 12
@@ -597,29 +600,48 @@ def kernel_rooflines(layer, x, dev, cdt, pk, iters=10, nset=4):
     st = {}
 
     def add(name, fn, nlaunch, flops=None, nbytes=None):
+        """flops / nbytes: ALGORITHMIC work of the whole stage (all its launches).  A GEMM stage gets both: the roofline
+        that bounds it is the one with the larger floor time (at D = H = 384 with the activation planes kept for backward
+        the grouped GEMMs sit BELOW the ridge of 250 flop/B: HBM-bound by the model); the other fraction is kept too."""
         t = timed(fn, nlaunch)
         d = {"us_per_launch": t * 1e6, "launches": nlaunch}
+        tens = hbm = None
         if flops is not None:
-            d.update(bound="tensor", achieved=flops / nlaunch / t / 1e12, peak=pk["tf_burst"], unit="TFLOP/s")
+            tens = dict(achieved=flops / nlaunch / t / 1e12, peak=pk["tf_burst"], unit="TFLOP/s")
+            tens["frac"] = tens["achieved"] / tens["peak"]
+        if nbytes is not None:
+            hbm = dict(achieved=nbytes / nlaunch / t / 1e9, peak=pk["hbm"], unit="GB/s")
+            hbm["frac"] = hbm["achieved"] / hbm["peak"]
+        if tens is not None and (hbm is None or tens["frac"] >= hbm["frac"]):
+            d.update(bound="tensor", **tens)
         else:
-            d.update(bound="hbm", achieved=nbytes / nlaunch / t / 1e9, peak=pk["hbm"], unit="GB/s")
-        d["frac"] = d["achieved"] / d["peak"]
+            d.update(bound="hbm", **hbm)
+        if tens is not None and hbm is not None:
+            d["tensor"], d["hbm"] = tens, hbm
+            d["flop_per_byte"] = flops / nbytes
         st[name] = d
 
     add("gate_fwd", lambda o: ops.gate_fwd(o.x, wg, K), 1, nbytes=T * D * 4 + T * (E * 4 + K * 16 + (K + 1) * 8))
     add("route_plan", lambda o: ops.route_plan(o.g.idx, E, imp_partial=o.g.imp_partial, load_partial=o.g.load_partial), 2,
         nbytes=R * (8 + 8 + 4))
     add("dispatch_fwd", lambda o: ops.dispatch_fwd(o.x, o.plan, K, out_dtype=cdt), 1, nbytes=T * (D * 4 + K * D * el + K * 4))
-    add("ffn_fwd", lambda o: ops.ffn_fwd(o.xq, o.plan, w1c, b1, w2c, b2), 2, flops=4.0 * R * D * H)
+    # algorithmic bytes of the expert GEMMs (bf16 path; queue rows R x width x el, weights E x D x H x el per launch):
+    #   fc1 (training): xq in, h and gelu'(z) out          fc2: h in, yq out
+    #   dz = (dyq W2) * gelu': dyq + gelu' in, dz out      dxq = dz W1: dz in, dxq out
+    #   dW2 = dyq^T h, dW1 = dz^T xq: two queue planes in each (fp32 dW out is E x D x H x 4)
+    wb = E * D * H * el
+    add("ffn_fwd", lambda o: ops.ffn_fwd(o.xq, o.plan, w1c, b1, w2c, b2), 2, flops=4.0 * R * D * H,
+        nbytes=R * el * (D + 2 * H) + R * el * (H + D) + 2 * wb)
     from m3vit_b200 import _lib as L_
     chain = bool(L_.load().m3_ffn_uses_chain(1 if cdt == torch.bfloat16 else 0, D, H))
     add("ffn_fwd_inference", lambda o: ops.ffn_fwd(o.xq, o.plan, w1c, b1, w2c, b2, save_hpre=False), 1 if chain else 2,
-        flops=4.0 * R * D * H)
+        flops=4.0 * R * D * H, nbytes=(2 * R * el * D if chain else 2 * R * el * (D + H)) + 2 * wb)
     st["ffn_fwd_inference"]["kernel"] = "ffn_chain_kernel (fc1 -> GELU -> fc2 in one launch)" if chain else "gg_kernel x 2"
     add("combine_fwd", lambda o: ops.combine_fwd(o.yq, o.plan, o.g.score), 1, nbytes=T * (K * D * el + K * 8 + D * 4))
     add("combine_bwd", lambda o: ops.combine_bwd(o.go, o.yq, o.plan, o.g.score), 1, nbytes=T * (D * 4 + 2 * K * D * el + K * 12))
     nb = 4 if cdt == torch.bfloat16 else 6
-    add("ffn_bwd", lambda o: ops.ffn_bwd(o.xq, o.hpre, o.dyq, o.plan, w1c, w2c, w1t, w2t), nb, flops=8.0 * R * D * H)
+    add("ffn_bwd", lambda o: ops.ffn_bwd(o.xq, o.hpre, o.dyq, o.plan, w1c, w2c, w1t, w2t), nb, flops=8.0 * R * D * H,
+        nbytes=R * el * (D + 2 * H) + R * el * (H + D) + 2 * R * el * (D + H) + 2 * wb + 2 * E * D * H * 4)
     add("gate_bwd", lambda o: ops.gate_bwd(o.x, wg, o.g.noisy_logits, o.g.idx_full, K, dscore=o.dscore), 3,
         nbytes=T * (D * 4 + E * 12))
     add("dispatch_bwd", lambda o: ops.dispatch_bwd(o.dxq, o.plan, T, K, dz=o.dz, w_gate=wg), 1,
@@ -630,10 +652,17 @@ def kernel_rooflines(layer, x, dev, cdt, pk, iters=10, nset=4):
     traffic, traffic_src = ncu_traffic(f"ffn_fwd_train:{'bf16' if cdt == torch.bfloat16 else 'f32'}:T{T}:D{D}:H{H}:E{E}:K{K}")
     roof = {"kernel": "gg_kernel<192> (tcgen05 grouped GEMM; fc1+bias+GELU and fc2+bias launches of m3_ffn_fwd)"
             if cdt == torch.bfloat16 else "sgemm_grouped_kernel (fp32 SIMT)",
-            "bound": "tensor", "achieved": f["achieved"], "peak": pk["tf_burst"], "unit": "TFLOP/s",
+            "bound": f["bound"], "achieved": f["achieved"], "peak": f["peak"], "unit": f["unit"],
             "frac": f["frac"], "traffic": traffic, "traffic_unit": "bytes per launch (ncu dram read+write)",
             "traffic_source": traffic_src, "peak_source": pk["src"] + " (burst, kernel timed alone)",
             "flops_per_launch": 2.0 * R * D * H, "us_per_launch": f["us_per_launch"]}
+    if "tensor" in f:      # both rooflines of the GEMM pair: the binding one above, the other for reference
+        roof.update(tensor=f["tensor"], hbm=f["hbm"], flop_per_byte=f["flop_per_byte"],
+                    algorithmic_bytes_per_launch=f["hbm"]["achieved"] * 1e9 * f["us_per_launch"] * 1e-6,
+                    note="mean over the fc1 (+bias, GELU, saves gelu') and fc2 (+bias) launches of one training forward; at "
+                         "%.0f flop/B the pair sits below the ridge (%.0f flop/B): the HBM roofline binds, the tensor "
+                         "fraction is what the same time means against the cuBLAS bf16 peak"
+                         % (f["flop_per_byte"], pk["tf_burst"] * 1e12 / (pk["hbm"] * 1e9)))
     return roof, st
 
 

@@ -37,20 +37,31 @@ def test_ep_plan_kernel_bit_exact(W, E_loc, K):
     idxs = [torch.stack([torch.randperm(E_tot, generator=gen)[:K] for _ in range(T)]) for T in Ts]
     cnt_all = torch.stack([torch.bincount(i.reshape(-1), minlength=E_tot) for i in idxs]).int()
     lib = _lib.load()
+    # every rank's inverse route plan (queue row -> slot, pad 1): what the owners read the origins of their rows from
+    invs = [torch.full((Ts[r] * K,), -5, dtype=torch.int32, device=dev) for r in range(W)]
+    pls = [ops.route_plan(idxs[r].to(dev), E_tot, 1, inv_pos=invs[r]) for r in range(W)]
     for r in range(W):
-        dr, drow, rc, ro = ep_oracle.ep_plan(idxs[r], cnt_all, r, W, E_loc, PAD)
+        inv_ref = torch.empty(Ts[r] * K, dtype=torch.int64)
+        inv_ref[pls[r].pos.cpu().long()] = torch.arange(Ts[r] * K)
+        assert torch.equal(invs[r].cpu().long(), inv_ref)
+    peer_inv = torch.tensor([t.data_ptr() for t in invs], dtype=torch.int64, device=dev)
+    plans = [ep_oracle.ep_plan(idxs[r], cnt_all, r, W, E_loc, PAD) for r in range(W)]
+    for r in range(W):
+        dr, drow, rc, ro = plans[r]
         idx = idxs[r].to(dev)
-        pl = ops.route_plan(idx, E_tot, 1)
+        pl = pls[r]
         R = Ts[r] * K
         cap = int(ro[-1]) + 2 * PAD
         o = dict(dst_rank=torch.empty(R, dtype=torch.int32, device=dev), dst_row=torch.empty(R, dtype=torch.int32, device=dev),
                  rc=torch.empty(E_loc, dtype=torch.int32, device=dev), ro=torch.empty(E_loc + 1, dtype=torch.int32, device=dev),
                  rt=torch.full((cap // PAD,), -7, dtype=torch.int32, device=dev), fl=torch.zeros(1, dtype=torch.int32, device=dev),
-                 pid=torch.full((R,), -9, dtype=torch.int32, device=dev))
+                 pid=torch.full((R,), -9, dtype=torch.int32, device=dev),
+                 meta=torch.full((cap,), -1, dtype=torch.int32, device=dev))
         _lib.check(lib.m3_ep_plan(idx.data_ptr(), pl.pos.data_ptr(), cnt_all.to(dev).data_ptr(), r, W, E_loc, Ts[r], K,
                                   PAD, cap, o["dst_rank"].data_ptr(), o["dst_row"].data_ptr(), o["rc"].data_ptr(),
                                   o["ro"].data_ptr(), o["rt"].data_ptr(), o["fl"].data_ptr(), o["pid"].data_ptr(),
-                                  None, None, torch.cuda.current_stream().cuda_stream), "m3_ep_plan")
+                                  peer_inv.data_ptr(), o["meta"].data_ptr(), torch.cuda.current_stream().cuda_stream),
+                   "m3_ep_plan")
         assert torch.equal(o["dst_rank"].cpu(), dr) and torch.equal(o["dst_row"].cpu(), drow)
         # identity plan of the slot-ordered return buffers: s for a live slot, -1 for a dropped one
         assert torch.equal(o["pid"].cpu(), torch.where(drow >= 0, torch.arange(R, dtype=torch.int32), torch.tensor(-1, dtype=torch.int32)))
@@ -59,6 +70,13 @@ def test_ep_plan_kernel_bit_exact(W, E_loc, K):
         te = o["rt"].cpu()[: int(ro[-1]) // PAD]
         for i, e in enumerate(te.tolist()):
             assert int(ro[e]) <= i * PAD < int(ro[e + 1])
+        # row origins of rank r's receive queue: slot s of source src went to (dst_rank, dst_row) = (r, row)
+        want = torch.full((cap,), -1, dtype=torch.int32)
+        for src in range(W):
+            sdr, sdrow = plans[src][0], plans[src][1]
+            mine = (sdr == r) & (sdrow >= 0)
+            want[sdrow[mine].long()] = (src << 24) | torch.nonzero(mine).flatten().int()
+        assert torch.equal(o["meta"].cpu(), want)
 
 
 @pytest.mark.parametrize("W", [2, 4])
