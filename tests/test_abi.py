@@ -65,3 +65,25 @@ def test_null_arguments_are_rejected_not_dereferenced(built_lib):
     lib = _lib.load()
     assert lib.m3_dispatch_fwd(None, 0, None, None, None, 1, 1, 64, 16, None, 0, None) == -1
     assert lib.m3_ffn_fwd(0, None, None, None, 128, 16, 64, 64, None, None, None, None, None, None, None, 0, None) == -1
+
+
+def test_expert_parallel_entry_points_validate_before_touching_the_device(built_lib):
+    """The fused-return entry points (round 2) reject bad argument sets on the host: no launch, no dereference."""
+    from m3vit_b200 import _lib
+    lib = _lib.load()
+    P = 0x1000      # a 16-byte aligned fake device address (never dereferenced on these paths)
+    # return store needs BOTH the row origins and the peers' return buffers
+    assert lib.m3_ep_ffn_fwd(1, P, P, P, 256, 2, 64, 64, P, P, P, P, None, None, P, P, 1 << 20, 0.0, None, None) == -1
+    assert lib.m3_ep_ffn_fwd(1, P, P, P, 256, 2, 64, 64, P, P, P, P, None, P, None, P, 1 << 20, 0.0, None, None) == -1
+    # ... and lives in the tcgen05 epilogue only: fp32 queues are refused, not silently run without the return
+    assert lib.m3_ep_ffn_fwd(0, P, P, P, 256, 2, 64, 64, P, P, P, P, None, P, P, P, 1 << 20, 0.0, None, None) == -4
+    assert lib.m3_ep_ffn_bwd(0, P, P, P, P, P, P, 256, 2, 64, 64, P, P, P, P, P, P, P, P, P, P, P, 1 << 20, 0.0, None, 3,
+                             None) == -4
+    # parts of the split backward: 1 = data gradients, 2 = weight gradients, 3 = both
+    assert lib.m3_ffn_bwd_parts(1, P, P, P, P, P, P, 256, 2, 64, 64, P, P, P, P, P, P, P, P, P, P, 1 << 20, 0.0, None, 0,
+                                None) == -1
+    # row origins and the sources' inverse plans come together; slots must fit 24 bits
+    assert lib.m3_ep_plan(P, P, P, 0, 2, 2, 16, 2, 256, 512, P, P, P, P, P, None, None, None, P, None) == -1
+    assert lib.m3_ep_plan(P, P, P, 0, 2, 2, 1 << 23, 4, 256, 512, P, P, P, P, P, None, None, P, P, None) == -1
+    # an empty call is a no-op
+    assert lib.m3_ep_ffn_fwd(1, P, P, P, 0, 2, 64, 64, P, P, P, P, None, P, P, P, 1 << 20, 0.0, None, None) == 0

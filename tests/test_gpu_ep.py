@@ -79,8 +79,9 @@ def test_ep_plan_kernel_bit_exact(W, E_loc, K):
         assert torch.equal(o["meta"].cpu(), want)
 
 
-@pytest.mark.parametrize("W", [2, 4])
-@pytest.mark.parametrize("cdt,mode", [(torch.float32, "pull"), (torch.bfloat16, "pull"), (torch.bfloat16, "ret")])
+@pytest.mark.parametrize("W,cdt,mode", [(2, torch.float32, "pull"), (4, torch.float32, "pull"),
+                                        (2, torch.bfloat16, "pull"), (4, torch.bfloat16, "pull"),
+                                        (2, torch.bfloat16, "ret"), (4, torch.bfloat16, "ret"), (8, torch.bfloat16, "ret")])
 def test_ep_simulation_matches_single_gpu(W, cdt, mode, monkeypatch):
     """pull: results pulled by the combine kernels.  ret: the return store (fc2 / dgrad epilogues send every result row
     straight into the source rank's return buffer; m3_ep_ffn_fwd / m3_ep_ffn_bwd; row origins read from the sources' inverse
