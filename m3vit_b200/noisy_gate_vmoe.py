@@ -172,11 +172,15 @@ class NoisyGate_VMoE(BaseGate):
                 self.set_loss(balance_loss(importance, load, clean_logits, noisy_logits, nstd, top_vals, self.top_k,
                                            self.tot_expert, self.training))
         self._last_logits = noisy_logits.detach()
+        self._act_lead = None          # leading dimensions of the router input (stand-alone forward on an N-d input)
 
     def get_activation(self, clear=True):
-        """origin:284,299-303: softmax probabilities of the last forward (lazy here)."""
+        """origin:284,299-303: softmax probabilities of the last forward, shaped like the router input's leading
+        dimensions + [E] (lazy here: the softmax runs only if somebody asks)."""
         if self.activation is None and self._last_logits is not None:
-            self.activation = torch.softmax(self._last_logits, dim=1)
+            act = torch.softmax(self._last_logits, dim=1)
+            lead = getattr(self, "_act_lead", None)
+            self.activation = act.reshape(list(lead) + [-1]).contiguous() if lead else act
         activation = self.activation
         if clear:
             self.activation = None
@@ -206,6 +210,7 @@ class NoisyGate_VMoE(BaseGate):
         (score, top_vals, clean, noisy, gates, importance, cv_loss, load, idx, *_plan) = GateFunction.apply(
             inp2, w_gate, None, noise, self.top_k, float(self.noise_stddev()), self.return_summaries)
         self._record(clean, noisy, importance, load, top_vals, cv_loss)
+        self._act_lead = other_dim
         self.last_plan = _plan
         top_k_indices = idx.reshape(other_dim + [self.top_k])
         top_k_gates = score.reshape(other_dim + [self.top_k])

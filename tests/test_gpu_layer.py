@@ -339,3 +339,21 @@ def test_graphed_layer_follows_optimizer_steps():
     layer._wcache.invalidate()
     after = layer(data["x"].to(dev), task_id=1).detach()
     assert not torch.equal(before, after)
+
+
+def test_standalone_gate_activation_keeps_leading_dims():
+    """origin/noisy_gate_vmoe.py:284,299-303: `get_activation()` returns the softmax probabilities shaped like the router
+    input's leading dimensions + [E]; `clear=True` forgets them."""
+    import m3vit_b200 as M
+    dev = torch.device("cuda:0")
+    gate = M.NoisyGate_VMoE(64, 8, 1, top_k=2, noise_std=0).to(dev).eval()
+    x = torch.randn(3, 5, 64, device=dev)
+    idx, score = gate(x)
+    assert idx.shape == (3, 5, 2) and score.shape == (3, 5, 2)
+    assert gate.has_activation
+    act = gate.get_activation(clear=False)
+    assert act.shape == (3, 5, 8)
+    want = torch.softmax(x.reshape(-1, 64) @ gate.w_gate, dim=1).reshape(3, 5, 8)
+    torch.testing.assert_close(act, want, rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(act.gather(-1, idx), score, rtol=1e-5, atol=1e-6)
+    assert gate.get_activation() is not None and not gate.has_activation
