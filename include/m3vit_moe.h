@@ -231,10 +231,10 @@ int m3_ffn_bwd_dropout(int dtype, const void* xq, const void* saved, const void*
                        float* dw1, float* db1, float* dw2, float* db2, void* workspace,
                        size_t workspace_bytes, float drop_p, const void* rng_state, m3_stream_t stream);
 
-/* m3_ffn_bwd(_dropout) in two halves, for callers that run them on different streams: parts = 1 the data gradients
- * (dxq; the intermediate dz stays in `workspace`), parts = 2 the weight / bias gradients (needs the workspace a parts = 1
- * call with the same arguments filled), parts = 3 both.  The expert-parallel backward launches the weight gradients on a
- * side stream so that they run beside the NVLink pull of dxq (m3_ep_dispatch_bwd), which needs the data gradients only. */
+/* m3_ffn_bwd(_dropout) in two halves: parts = 1 the data gradients (dxq; the intermediate dz stays in `workspace`),
+ * parts = 2 the weight / bias gradients (needs the workspace a parts = 1 call with the same arguments filled), parts = 3
+ * both.  The expert-parallel backward issues the data gradients first - they are what the peers wait for - and runs the
+ * router backward and the weight gradients before the last rendezvous, where they absorb rank skew. */
 int m3_ffn_bwd_parts(int dtype, const void* xq, const void* saved, const void* dyq, const int32_t* counts,
                      const int32_t* offsets, const int32_t* tile_expert, int cap_rows, int E, int D, int H,
                      const void* w1, const void* w2, const void* w1t, const void* w2t, void* dxq, float* dw1,
