@@ -275,8 +275,51 @@ def other_configs(dev, cdt, pk, iters=8):
         flops = 3.0 * (2 * (D + Dt) * E + 4 * K * D * H) * T
         res[name] = {**c, "tokens_per_call": T, "fwd_us": t[0] * 1e6, "fwd_bwd_us": t[1] * 1e6,
                      "tokens_per_s": T / t[1], "tflops": flops / t[1] / 1e12, "frac_of_sustained_bf16": flops / t[1] / 1e12 / pk["tf_sus"]}
+        if cdt == torch.bfloat16:
+            res[name]["gemm_roofline"] = config_gemm_roofline(layer, gate, x.detach(), K, E, D, H, Dt, feat if Dt > 0 else None,
+                                                              cdt, pk, iters)
         del layer, x, g
     return res
+
+
+def config_gemm_roofline(layer, gate, x, K, E, D, H, Dt, feat, cdt, pk, iters):
+    """The expert GEMMs of one configuration on their own (training forward: fc1 + fc2; backward: dz, dxq, dW2, dW1), timed
+    with CUDA events over `iters` back-to-back launches on this configuration's own dispatched queue, against BOTH rooflines
+    (algorithmic bytes / HBM copy peak, flops / cuBLAS bf16 burst peak); `bound` is the one with the larger floor."""
+    from m3vit_b200 import ops
+    T = x.shape[0]
+    R, el = T * K, 2
+    with torch.no_grad():
+        g = ops.gate_fwd(x, gate.w_gate.detach(), K, feat)
+        plan = ops.route_plan(g.idx, E, imp_partial=g.imp_partial, load_partial=g.load_partial)
+        xq = ops.dispatch_fwd(x, plan, K, out_dtype=cdt)
+        w1c, w2c, w1t, w2t = layer._wcache.get_bf16(layer.experts.htoh4.weight, layer.experts.h4toh.weight)
+        b1, b2 = layer.experts.htoh4.bias.detach(), layer.experts.h4toh.bias.detach()
+        yq, hpre = ops.ffn_fwd(xq, plan, w1c, b1, w2c, b2)
+        dyq = torch.randn_like(yq) * 0.01
+
+        def timed(fn):
+            for _ in range(2):
+                fn()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            e0.record()
+            for _ in range(iters):
+                fn()
+            e1.record()
+            e1.synchronize()
+            return e0.elapsed_time(e1) / iters * 1e-3
+        tf = timed(lambda: ops.ffn_fwd(xq, plan, w1c, b1, w2c, b2))
+        tb = timed(lambda: ops.ffn_bwd(xq, hpre, dyq, plan, w1c, w2c, w1t, w2t))
+    wb = E * D * H * el
+    out = {}
+    for nm, t, flops, nbytes in (("ffn_fwd", tf, 4.0 * R * D * H, R * el * (D + 2 * H) + R * el * (H + D) + 2 * wb),
+                                 ("ffn_bwd", tb, 8.0 * R * D * H, R * el * (D + 2 * H) + R * el * (H + D) + 2 * R * el * (D + H)
+                                  + 2 * wb + 2 * E * D * H * 4)):
+        ft, fh = flops / t / 1e12 / pk["tf_burst"], nbytes / t / 1e9 / pk["hbm"]
+        out[nm] = {"us": t * 1e6, "tflops": flops / t / 1e12, "tensor_frac": ft, "hbm_frac": fh,
+                   "bound": "tensor" if ft >= fh else "hbm", "frac": max(ft, fh), "flop_per_byte": flops / nbytes}
+    return out
 
 
 def ep_parity(layers, ep_layer_inputs, dev, cdt, rank, world, dist):
