@@ -497,61 +497,74 @@ def main():
     value = tokens_per_step / (ms_per_step * 1e-3)
 
     # ---- e2e: host (pinned) token buffers, H2D per layer call, D2H of the loss scalars
-    hx = [torch.empty(T, D_MODEL, dtype=torch.float32).pin_memory() for _ in range(2)]
-    for h in hx:
-        h.copy_(xs[0].detach().cpu())
-    hloss = torch.empty(len(calls), dtype=torch.float32).pin_memory()
-    dloss = torch.empty(len(calls), dtype=torch.float32, device=dev)
+    def run_e2e(tok_dtype):
+        """One e2e measurement with host token buffers of `tok_dtype`.  The next call's tokens are prefetched on a copy
+        stream into a double-buffered device slot while the current call computes (what an input pipeline does); every
+        byte still crosses PCIe inside the timed region and the compute stream waits for each copy's event."""
+        hx = [torch.empty(T, D_MODEL, dtype=tok_dtype).pin_memory() for _ in range(2)]
+        for h in hx:
+            h.copy_(xs[0].detach().cpu().to(tok_dtype))
+        hloss = torch.empty(len(calls), dtype=torch.float32).pin_memory()
+        dloss = torch.empty(len(calls), dtype=torch.float32, device=dev)
+        ge = [g_.to(tok_dtype) for g_ in gs]
+        copy_stream = torch.cuda.Stream(device=dev)
+        xbuf = [torch.empty(T, D_MODEL, device=dev, dtype=tok_dtype) for _ in range(2)]
+        ev_ready = [torch.cuda.Event() for _ in range(2)]
+        ev_free = [torch.cuda.Event() for _ in range(2)]
 
-    # The next call's tokens are prefetched on a copy stream into a double-buffered device slot
-    # while the current call computes (what an input pipeline does); every byte still crosses PCIe
-    # inside the timed region and the compute stream waits for each copy's event.
-    copy_stream = torch.cuda.Stream(device=dev)
-    xbuf = [torch.empty(T, D_MODEL, device=dev) for _ in range(2)]
-    ev_ready = [torch.cuda.Event() for _ in range(2)]
-    ev_free = [torch.cuda.Event() for _ in range(2)]
-
-    def prefetch(i):
-        b = i & 1
-        with torch.cuda.stream(copy_stream):
-            copy_stream.wait_event(ev_free[b])          # slot b's previous fwd+bwd has finished
-            xbuf[b].copy_(hx[b], non_blocking=True)
-            ev_ready[b].record(copy_stream)
-
-    def step_e2e():
-        zero_grads()
-        cur = torch.cuda.current_stream()
-        for b in range(2):
-            ev_free[b].record(cur)
-        prefetch(0)
-        for i, (li, t) in enumerate(calls):
+        def prefetch(i):
             b = i & 1
-            if i + 1 < len(calls):
-                prefetch(i + 1)
-            cur.wait_event(ev_ready[b])
-            x = xbuf[b].detach().requires_grad_(True)
-            dloss[i] = one_call(layers[li], x, gs[b], t).detach()
-            ev_free[b].record(cur)
-        hloss.copy_(dloss, non_blocking=True)
-        cur.synchronize()
+            with torch.cuda.stream(copy_stream):
+                copy_stream.wait_event(ev_free[b])          # slot b's previous fwd+bwd has finished
+                xbuf[b].copy_(hx[b], non_blocking=True)
+                ev_ready[b].record(copy_stream)
 
-    e2e_steps = max(2, min(args.steps, 10))
-    step_e2e()
-    barrier()
-    e0.record()
-    for _ in range(e2e_steps):
-        step_e2e()
-    e1.record()
-    barrier()
-    ems = e0.elapsed_time(e1) / e2e_steps
-    if world > 1:
-        tms = torch.tensor([ems], device=dev)
-        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
-        ems = float(tms.item())
-    e2e = {"value": tokens_per_step / (ems * 1e-3), "unit": "tokens/s", "ms_per_step": ems,
-           "h2d_bytes_per_step": len(calls) * T * D_MODEL * 4, "d2h_bytes_per_step": len(calls) * 4,
-           "note": "PCIe-bound: the fp32 token matrices of the 12 layer calls cross the bus every step (prefetched one call "
-                   "ahead on a copy stream); h2d_bytes_per_step / ms_per_step is the achieved H2D rate"}
+        def step_e2e(first=False):
+            zero_grads()
+            cur = torch.cuda.current_stream()
+            if first:                                       # prime the pipeline (untimed warm-up step only)
+                for b in range(2):
+                    ev_free[b].record(cur)
+                prefetch(0)
+            for i, (li, t) in enumerate(calls):
+                b = i & 1
+                # the NEXT call's tokens start crossing the bus now; after the last call of a step that is call 0 of the
+                # next step (len(calls) is even, so the slot parity carries over): an input pipeline does not drain
+                # between steps
+                prefetch(i + 1)
+                cur.wait_event(ev_ready[b])
+                x = xbuf[b].detach().requires_grad_(True)
+                dloss[i] = one_call(layers[li], x, ge[b], t).detach()
+                ev_free[b].record(cur)
+            hloss.copy_(dloss, non_blocking=True)
+            cur.synchronize()                               # the step's result (12 balance losses) is on the host
+
+        assert len(calls) % 2 == 0
+        e2e_steps = max(2, min(args.steps, 10))
+        step_e2e(first=True)
+        barrier()
+        e0.record()
+        for _ in range(e2e_steps):
+            step_e2e()
+        e1.record()
+        barrier()
+        ems = e0.elapsed_time(e1) / e2e_steps
+        if world > 1:
+            tms = torch.tensor([ems], device=dev)
+            dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+            ems = float(tms.item())
+        nb = len(calls) * T * D_MODEL * hx[0].element_size()
+        return {"value": tokens_per_step / (ems * 1e-3), "unit": "tokens/s", "ms_per_step": ems,
+                "h2d_bytes_per_step": nb, "d2h_bytes_per_step": len(calls) * 4, "h2d_gb_per_s": nb / (ems * 1e-3) / 1e9}
+
+    e2e = run_e2e(torch.float32)
+    e2e["note"] = ("PCIe-bound: the fp32 token matrices of the 12 layer calls (what the reference's layer is handed) cross the bus "
+                   "every step, prefetched one call ahead on a copy stream, across step boundaries too (each timed step issues 12 "
+                   "copies, the last of which serves the following step); h2d_gb_per_s is the achieved H2D rate.  "
+                   "`bf16_tokens` is the same measurement for a bf16 model (bf16 tokens in, bf16 out / dx): half the bytes on "
+                   "the bus - informational, the reference arm and `value` use fp32 tokens")
+    if cdt == torch.bfloat16 and world == 1:
+        e2e["bf16_tokens"] = run_e2e(torch.bfloat16)
 
     # ---- roofline of the dominant kernel family, timed live on this stream
     pk = peaks()

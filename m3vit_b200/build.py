@@ -19,9 +19,13 @@ NVCC_FLAGS = [
     "-Xcompiler", "-fPIC",     # no --use_fast_math: exact erf/exp/div, parity first
 ]
 TRACE = os.environ.get("M3_GEMM_TRACE") == "1"
+VARIANT = "trace" if TRACE else os.environ.get("M3_BUILD_VARIANT", "")
 if TRACE:      # clock64 timeline in the tensor-core kernels (tools/gemm_timeline.py, tools/chain_timeline.py): a SEPARATE
     NVCC_FLAGS.append("-DM3_GEMM_TRACE")       # library, loaded with M3_LIB_PATH=.../libm3vit_moe_trace.so
-    LIB = os.path.join(LIBDIR, "libm3vit_moe_trace.so")
+elif VARIANT:  # A/B build with extra defines (tools/ab_libs.py): M3_BUILD_VARIANT=name M3_BUILD_DEFS="-DX=1 -DY=2"
+    NVCC_FLAGS += os.environ.get("M3_BUILD_DEFS", "").split()
+if VARIANT:
+    LIB = os.path.join(LIBDIR, f"libm3vit_moe_{VARIANT}.so")
 
 
 def _nvcc():
@@ -44,12 +48,12 @@ def _digest(paths):
 def build(force: bool = False, verbose: bool = False) -> str:
     os.makedirs(LIBDIR, exist_ok=True)
     deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(HERE, "..", "include", "m3vit_moe.h")]
-    stamp = os.path.join(LIBDIR, "build_trace.sha256" if TRACE else "build.sha256")
+    stamp = os.path.join(LIBDIR, f"build_{VARIANT}.sha256" if VARIANT else "build.sha256")
     digest = _digest(deps)
     if not force and os.path.exists(LIB) and os.path.exists(stamp) and open(stamp).read().strip() == digest:
         return LIB
     nvcc = _nvcc()
-    objdir = os.path.join(LIBDIR, "obj_trace" if TRACE else "obj")
+    objdir = os.path.join(LIBDIR, "obj_trace" if TRACE else os.path.join("obj", VARIANT) if VARIANT else "obj")
     os.makedirs(objdir, exist_ok=True)
 
     def compile_one(src):

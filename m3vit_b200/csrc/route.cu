@@ -10,13 +10,19 @@
 //
 // Two launches: per-block histograms, then a block-local stable rank + the
 // cross-block prefix (each block re-derives its own prefix from the histogram
-// table, so there is no inter-block dependency and no atomics).
+// table, so there is no inter-block dependency and no atomics).  One extra block
+// of the second launch writes counts / offsets / tile map and reduces the router's
+// importance / load partials into the cv^2 balance loss.
 // Integer work only; HBM traffic = 8+4 B per slot.  Bit-exact vs the oracle.
 #include "common.cuh"
 
 namespace m3 {
 
-constexpr int kRouteChunk = 2048;   // slots per block
+#ifndef M3_ROUTE_CHUNK
+#define M3_ROUTE_CHUNK 2048
+#endif
+constexpr int kRouteChunk = M3_ROUTE_CHUNK;   // slots per block
+static_assert(kRouteChunk % 256 == 0, "8 warps x 32 slots per pass");
 constexpr int kRouteThreads = 256;
 constexpr int kRouteBatches = kRouteChunk / 32;
 
@@ -77,6 +83,9 @@ route_assign_kernel(const int64_t* __restrict__ idx, int R, int E, int pad, int 
     }
     off[E] = run;
   }
+  // Block `nblk` (one past the last chunk) has no slots: it writes the plan's per-expert outputs and reduces the router's
+  // importance / load partials, beside the position blocks instead of as the tail of one of them.
+  const bool summary_block = b == nblk;
   // stable rank inside the block: pass 1, per-batch histograms via match_any
   const int base = b * kRouteChunk;
   int my_e[kRouteBatches / 8], my_rank[kRouteBatches / 8];
@@ -117,7 +126,7 @@ route_assign_kernel(const int64_t* __restrict__ idx, int R, int E, int pad, int 
       if (inv_pos != nullptr && p >= 0) inv_pos[p] = s;      // queue row -> slot (expert parallel: the sorted send order)
     }
   }
-  if (b == 0) {
+  if (summary_block) {
     for (int e = tid; e < E; e += kRouteThreads) counts[e] = tot[e];
     for (int e = tid; e <= E; e += kRouteThreads) offsets[e] = off[e];
     const int ntile = tile_expert != nullptr ? off[E] / pad : 0;
@@ -142,7 +151,19 @@ route_assign_kernel(const int64_t* __restrict__ idx, int R, int E, int pad, int 
         const int e = tid % E, part = tid / E;
         float a = 0.f;
         int l = 0;
-        for (int i = part; i < n_partial; i += P) {
+        int i = part;
+        for (; i + 3 * P < n_partial; i += 4 * P) {      // four partials in flight; summed in the same order as one by one
+          float v[4];
+          int u[4];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            v[q] = __ldg(imp_partial + (int64_t)(i + q * P) * E + e);
+            u[q] = __ldg(load_partial + (int64_t)(i + q * P) * E + e);
+          }
+#pragma unroll
+          for (int q = 0; q < 4; ++q) { a += v[q]; l += u[q]; }
+        }
+        for (; i < n_partial; i += P) {
           a += imp_partial[(int64_t)i * E + e];
           l += load_partial[(int64_t)i * E + e];
         }
@@ -219,7 +240,7 @@ extern "C" int m3_route_plan(const int64_t* idx, int T, int K, int E, int pad, c
   launch_k(route_count_kernel, nblk, kRouteThreads, E * sizeof(int), st, idx, R, E, block_hist);
   M3_LAUNCH_CHECK();
   const size_t smem = (size_t)(3 * E + 1 + kRouteBatches * E + 2 * kRouteThreads) * sizeof(int);
-  launch_k(route_assign_kernel, nblk, kRouteThreads, smem, st, idx, R, E, pad, nblk, block_hist, imp_partial,
+  launch_k(route_assign_kernel, nblk + 1, kRouteThreads, smem, st, idx, R, E, pad, nblk, block_hist, imp_partial,
            load_partial, n_partial, counts, offsets, pos, tile_expert, importance, load, cv_loss, inv_pos);
   M3_LAUNCH_CHECK();
   return M3_OK;

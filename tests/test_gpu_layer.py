@@ -145,6 +145,45 @@ def test_layer_bf16_within_tolerance(fname):
             assert nerr(got, want) <= 3e-2, (name, nerr(got, want))
 
 
+@pytest.mark.parametrize("fname", [f for f in ALL if f.startswith(("S1", "S4", "S8", "C1"))])
+def test_layer_bf16_tokens_match_fp32_tokens(fname):
+    """A bf16 model hands the layer bf16 tokens (and expects bf16 out / dx).  Against the SAME layer fed the same
+    (bf16-representable) values as fp32 tokens: routing identical (the router reads the tokens exactly and computes in
+    fp32 either way), expert counts identical, outputs / dx equal up to the bf16 rounding of the results (2^-8 relative
+    per element -> 1e-2 of the tensor's max magnitude), parameter gradients within 1e-2."""
+    dev = torch.device("cuda:0")
+    fx, case, data = load_fixture(fname)
+    layer = build_layer(case, data, "origin", dev, compute_dtype=torch.bfloat16).train()
+    xb = data["x"].to(dev).bfloat16()
+    gb = data["grad_out"].to(dev).bfloat16()
+    task = 0 if case.num_gates > 1 else None
+    res = {}
+    for name, x0, g0 in (("f32", xb.float(), gb.float()), ("bf16", xb, gb)):
+        layer.zero_grad(set_to_none=True)
+        x = x0.clone().requires_grad_(True)
+        kwargs = dict(task_id=task) if task is not None else {}
+        if data["task_feat"] is not None:
+            kwargs = dict(task_id=0, task_specific_feature=data["task_feat"].to(dev))
+        cap = {}
+        layer.gate_hook = lambda idx, score, _: cap.update(idx=idx.detach().clone(), score=score.detach().clone())
+        out = layer(x, **kwargs)
+        assert out.dtype == x0.dtype
+        (out * g0).sum().backward()
+        assert x.grad.dtype == x0.dtype
+        res[name] = dict(out=out.detach().float(), dx=x.grad.float(), idx=cap["idx"], score=cap["score"],
+                         counts=layer.last_counts.clone(),
+                         grads={n: p.grad.detach().clone() for n, p in layer.named_parameters() if p.grad is not None})
+    layer.gate_hook = None
+    a, b = res["f32"], res["bf16"]
+    assert torch.equal(a["idx"], b["idx"]) and torch.equal(a["counts"], b["counts"])
+    assert torch.equal(a["score"], b["score"])
+    assert nerr(b["out"], a["out"]) <= 1e-2
+    assert nerr(b["dx"], a["dx"]) <= 1e-2
+    assert a["grads"].keys() == b["grads"].keys()
+    for n in a["grads"]:
+        assert nerr(b["grads"][n], a["grads"][n]) <= 1e-2, n
+
+
 def test_full_size_properties_bf16_and_fp32():
     """BASELINE-size batch (ViT-S / NYUD, B=32): size-independent properties.
     (1) sum of counts == T*K, (2) permutation invariance: shuffling the tokens
