@@ -318,6 +318,7 @@ def config_gemm_roofline(layer, gate, x, K, E, D, H, Dt, feat, cdt, pk, iters):
                                   + 2 * wb + 2 * E * D * H * 4)):
         ft, fh = flops / t / 1e12 / pk["tf_burst"], nbytes / t / 1e9 / pk["hbm"]
         out[nm] = {"us": t * 1e6, "tflops": flops / t / 1e12, "tensor_frac": ft, "hbm_frac": fh,
+                   "tensor_frac_of_sustained_peak": flops / t / 1e12 / pk["tf_sus"],      # (informational: launches run back to back)
                    "bound": "tensor" if ft >= fh else "hbm", "frac": max(ft, fh), "flop_per_byte": flops / nbytes}
     return out
 
