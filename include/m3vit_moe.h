@@ -198,8 +198,8 @@ int m3_set_gemm_sm_limit(int sms);
  *   M3_KNOB_FFN_CHAIN 1 (default): a bf16 forward that keeps no state (saved = NULL) with D in {128, 256, 384} and
  *                     H <= 2 D runs as ONE chain kernel (fc1 -> GELU -> fc2, h never leaves the SM; ffn_chain.cu);
  *                     0: always the two grouped GEMMs.
- *   M3_KNOB_MOVER_VARIANT  0 (default) or an experimental rows-in-flight / occupancy variant of combine fwd/bwd;
- *                     9: dispatch_bwd keeps the SIMT fp32 router term for bf16 queues too (default: mma.sync bf16).
+ *   M3_KNOB_MOVER_VARIANT  0 (default); 9: dispatch_bwd keeps the exact SIMT fp32 router term for bf16 queues too
+ *                     (default: mma.sync bf16; the test of that kernel compares the two).
  * Returns the previous value, or M3_ERR_ARG for an unknown knob. */
 typedef enum { M3_KNOB_PDL = 0, M3_KNOB_EPI_WARPS = 1, M3_KNOB_MOVER_VARIANT = 2, M3_KNOB_GATE_CFG = 3, M3_KNOB_DEBUG = 4, M3_KNOB_TRACE_KERNEL = 5, M3_KNOB_FFN_CHAIN = 6, M3_KNOB_COUNT_ = 8 } m3_knob;
 int m3_set_knob(int knob, int value);

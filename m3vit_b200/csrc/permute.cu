@@ -575,15 +575,6 @@ static int combine_fwd_impl(const void* yq, void* const* peer, const int32_t* sl
   if (T == 0) return M3_OK;
   const int nv = perm_nv(D);
   const int grid = m3_ceil_div(T, kTokPerCta);
-  const int var = g_knobs[M3_KNOB_MOVER_VARIANT];
-  if (var != 0 && !EP && nv == 3 && yq_dtype == M3_BF16 && out_dtype == M3_F32) {   // A/B variants (bench shape only)
-    Queue<const bf16> q{(const bf16*)yq, nullptr, nullptr};
-#define M3_CF_VAR(GK, MB) launch_k(combine_fwd_kernel<bf16, float, 3, false, GK, MB>, grid, kPermThreads, 0, st, q, pos, score, T, K, D, (float*)out, (bf16*)ysave)
-    if (var == 1) M3_CF_VAR(2, 3); else if (var == 2) M3_CF_VAR(4, 3); else if (var == 3) M3_CF_VAR(2, 4); else M3_CF_VAR(1, 4);
-#undef M3_CF_VAR
-    M3_LAUNCH_CHECK();
-    return M3_OK;
-  }
   M3_DTYPE2_SWITCH(yq_dtype, out_dtype, {
     Queue<const TA> q{(const TA*)yq, (const TA* const*)peer, slot_rank};
     M3_NV_SWITCH((launch_k(combine_fwd_kernel<TA, TB, NV, EP>, grid, kPermThreads, 0, st, q, pos, score, T, K, D, (TB*)out, (TA*)ysave)))
@@ -603,16 +594,6 @@ static int combine_bwd_impl(const void* g, int g_dtype, const void* yq, void* co
   const int tok_ctas = m3_ceil_div(T, kTokPerCta);
   const int grid = tok_ctas + (EP ? 0 : E);
   if (grid == 0) return M3_OK;
-  const int var = g_knobs[M3_KNOB_MOVER_VARIANT];
-  if (var != 0 && !EP && nv == 3 && g_dtype == M3_F32 && q_dtype == M3_BF16) {   // A/B variants (bench shape only)
-    Queue<const bf16> qy{(const bf16*)yq, nullptr, nullptr};
-    Queue<bf16> qd{(bf16*)dyq, nullptr, nullptr};
-#define M3_CB_VAR(GK, MB) launch_k(combine_bwd_kernel<float, bf16, 3, false, GK, MB>, grid, kPermThreads, 0, st, (const float*)g, qy, pos, score, counts, offsets, T, K, D, tok_ctas, qd, dscore, (const bf16*)ysave)
-    if (var == 1) M3_CB_VAR(2, 3); else if (var == 2) M3_CB_VAR(4, 3); else if (var == 3) M3_CB_VAR(2, 4); else M3_CB_VAR(1, 4);
-#undef M3_CB_VAR
-    M3_LAUNCH_CHECK();
-    return M3_OK;
-  }
   M3_DTYPE2_SWITCH(g_dtype, q_dtype, {
     Queue<const TB> qy{(const TB*)yq, (const TB* const*)peer_yq, slot_rank};
     Queue<TB> qd{(TB*)dyq, (TB* const*)peer_dyq, slot_rank};
@@ -646,9 +627,7 @@ static int dispatch_bwd_impl(const void* dxq, void* const* peer, const int32_t* 
     Queue<const bf16> q{(const bf16*)dxq, (const bf16* const*)peer, slot_rank};
 #define M3_MMA_LAUNCH(TOV, KSV)                                                                              \
   do {                                                                                                       \
-    auto kern = g_knobs[M3_KNOB_MOVER_VARIANT] == 8 ? dispatch_bwd_gate_mma_kernel<TOV, EP, KSV, 1, 8>       \
-              : g_knobs[M3_KNOB_MOVER_VARIANT] == 7 ? dispatch_bwd_gate_mma_kernel<TOV, EP, KSV, 4, 4>       \
-                                                    : dispatch_bwd_gate_mma_kernel<TOV, EP, KSV>;            \
+    auto kern = dispatch_bwd_gate_mma_kernel<TOV, EP, KSV>;                                                  \
     if (smem > 48 * 1024) {                                                                                  \
       cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);    \
       if (e != cudaSuccess) return (int)e;                                                                   \

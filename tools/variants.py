@@ -73,14 +73,6 @@ d_mma = ops.dispatch_bwd(dxq_, plan, T, K, dz=dz_, w_gate=wg)
 print(f"  mma.sync router term vs SIMT: max abs diff {(d_mma - d_simt).abs().max().item():.3e}, "
       f"normalised {((d_mma - d_simt).norm() / d_simt.norm()).item():.3e}")
 timed("dispatch_bwd (+ dz @ w_gate^T) [mma.sync bf16 router term, 2 rows/batch, 6 CTAs/SM (default)]", lambda: ops.dispatch_bwd(dxq_, plan, T, K, dz=dz_, w_gate=wg))
-lib.m3_set_knob(KNOB_MOVER, 8)
-d_mma2 = ops.dispatch_bwd(dxq_, plan, T, K, dz=dz_, w_gate=wg)
-print("  1 row per batch at 8 CTAs/SM: bits equal", torch.equal(d_mma2, d_mma))
-timed("dispatch_bwd (+ dz @ w_gate^T) [mma.sync, 1 row/batch, 8 CTAs/SM]", lambda: ops.dispatch_bwd(dxq_, plan, T, K, dz=dz_, w_gate=wg))
-lib.m3_set_knob(KNOB_MOVER, 7)
-timed("dispatch_bwd (+ dz @ w_gate^T) [mma.sync, 4 rows/batch, 4 CTAs/SM]", lambda: ops.dispatch_bwd(dxq_, plan, T, K, dz=dz_, w_gate=wg))
-lib.m3_set_knob(KNOB_MOVER, 0)
-timed("dispatch_bwd (+ dz @ w_gate^T) [mma.sync bf16 router term, 2 rows/batch, 6 CTAs/SM (default)]", lambda: ops.dispatch_bwd(dxq_, plan, T, K, dz=dz_, w_gate=wg))
 timed("gate_bwd", lambda: ops.gate_bwd(x, wg, g.noisy_logits, g.idx_full, K, dscore=g.score))
 timed("route_plan", lambda: ops.route_plan(g.idx, E, imp_partial=g.imp_partial, load_partial=g.load_partial))
 timed("torch x.clone() (59 MB read + 59 MB write)", lambda: x.clone())
@@ -122,18 +114,9 @@ for mask, name in ((0, "default: fc1 16 warps, others 8 warps x 64-col blocks"),
 lib.m3_set_knob(KNOB_EPI, 0)
 lib.m3_set_knob(KNOB_CHAIN, 1)
 
-# ---------------- combine fwd / bwd variants
-ref_c = ops.combine_fwd(yq, plan, g.score)
-ref_cb = ops.combine_bwd(go, yq, plan, g.score)
-for var, name in ((0, "default (fwd GK2 minb4, bwd GK4)"), (1, "GK2 minb3"), (3, "GK2 minb4")):
-    lib.m3_set_knob(KNOB_MOVER, var)
-    oc = ops.combine_fwd(yq, plan, g.score)
-    ocb = ops.combine_bwd(go, yq, plan, g.score)
-    torch.cuda.synchronize()
-    print(f"  [{name}] bits equal: combine_fwd {same(oc, ref_c)}  combine_bwd {same(ocb, ref_cb)}")
-    timed(f"combine_fwd [{name}]", lambda: ops.combine_fwd(yq, plan, g.score))
-    timed(f"combine_bwd [{name}]", lambda: ops.combine_bwd(go, yq, plan, g.score))
-lib.m3_set_knob(KNOB_MOVER, 0)
+# ---------------- combine fwd / bwd (the rows-in-flight / occupancy variants of round 1 were pruned: profiles/r1b_knob_variants.log)
+timed("combine_fwd", lambda: ops.combine_fwd(yq, plan, g.score))
+timed("combine_bwd", lambda: ops.combine_bwd(go, yq, plan, g.score))
 
 # ---------------- whole step (12 layer calls fwd+bwd), PDL on / off
 calls = [(li, t) for t in range(bench.N_TASK) for li in range(bench.N_LAYER)]
