@@ -22,27 +22,36 @@ namespace m3 {
 #define M3_ROUTE_CHUNK 2048
 #endif
 constexpr int kRouteChunk = M3_ROUTE_CHUNK;   // slots per block
-static_assert(kRouteChunk % 256 == 0, "8 warps x 32 slots per pass");
+static_assert(kRouteChunk % 1024 == 0, "8 warps x 32 slots per pass, whole batches per lane in the scan");
 constexpr int kRouteThreads = 256;
 constexpr int kRouteBatches = kRouteChunk / 32;
 
 __global__ void __launch_bounds__(kRouteThreads)
 route_count_kernel(const int64_t* __restrict__ idx, int R, int E, int32_t* __restrict__ block_hist) {
-  extern __shared__ int hist[];
-  for (int e = threadIdx.x; e < E; e += kRouteThreads) hist[e] = 0;
+  extern __shared__ int hist[];      // [warps][E]: one private histogram per warp (shared-memory atomics on 16 bins from
+  constexpr int NW = kRouteThreads / 32;                       // 256 threads serialise on the bins; 32 lanes do not)
+  for (int i = threadIdx.x; i < NW * E; i += kRouteThreads) hist[i] = 0;
   pdl_wait();
   pdl_trigger();
   __syncthreads();
   const int base = blockIdx.x * kRouteChunk;
-  for (int i = threadIdx.x; i < kRouteChunk; i += kRouteThreads) {
-    const int s = base + i;
-    if (s < R) {
-      const int64_t e = idx[s];
-      if (e >= 0 && e < E) atomicAdd(&hist[(int)e], 1);
-    }
+  int* mine = hist + (threadIdx.x >> 5) * E;
+  int64_t e[kRouteChunk / kRouteThreads];
+#pragma unroll
+  for (int i = 0; i < kRouteChunk / kRouteThreads; ++i) {      // all loads first
+    const int s = base + i * kRouteThreads + threadIdx.x;
+    e[i] = s < R ? idx[s] : -1;
   }
+#pragma unroll
+  for (int i = 0; i < kRouteChunk / kRouteThreads; ++i)
+    if (e[i] >= 0 && e[i] < E) atomicAdd(&mine[(int)e[i]], 1);
   __syncthreads();
-  for (int e = threadIdx.x; e < E; e += kRouteThreads) block_hist[(int64_t)blockIdx.x * E + e] = hist[e];
+  for (int x = threadIdx.x; x < E; x += kRouteThreads) {
+    int c = 0;
+#pragma unroll
+    for (int w = 0; w < NW; ++w) c += hist[w * E + x];
+    block_hist[(int64_t)blockIdx.x * E + x] = c;
+  }
 }
 
 __global__ void __launch_bounds__(kRouteThreads)
@@ -62,17 +71,37 @@ route_assign_kernel(const int64_t* __restrict__ idx, int R, int E, int pad, int 
   pdl_trigger();
   const int b = blockIdx.x;
 
-  for (int i = tid; i < 2 * E; i += kRouteThreads) sm[i] = 0;
+  // this block's slots first: their latency hides behind the histogram-table pass
+  const int base = b * kRouteChunk;
+  int64_t ee[kRouteBatches / 8];
+#pragma unroll
+  for (int i = 0; i < kRouteBatches / 8; ++i) {
+    const int s = base + (warp + 8 * i) * 32 + lane;
+    ee[i] = s < R ? idx[s] : -1;
+  }
   for (int i = tid; i < kRouteBatches * E; i += kRouteThreads) bh[i] = 0;
-  __syncthreads();
-  // totals and this block's cross-block prefix (integer adds: order-free)
-  for (int i = tid; i < nblk * E; i += kRouteThreads) {
-    const int bb = i / E, e = i % E;
-    const int v = block_hist[i];
-    if (v) {
-      atomicAdd(&tot[e], v);
-      if (bb < b) atomicAdd(&pre[e], v);
+  // totals and this block's cross-block prefix: thread (part, e) sums a strided set of histogram rows in registers, the
+  // parts are combined through shared memory (integer adds: order-free; no atomics - 256 threads on 2 E bins serialise)
+  int* red_t = bh + kRouteBatches * E;          // [parts][E], the scratch the summary block later reuses
+  int* red_p = red_t + kRouteThreads;
+  const int parts = kRouteThreads / E;          // >= 2 (E <= 128)
+  if (tid < parts * E) {
+    const int e = tid % E, part = tid / E;
+    int t = 0, q = 0;
+    for (int bb = part; bb < nblk; bb += parts) {
+      const int v = block_hist[bb * E + e];
+      t += v;
+      if (bb < b) q += v;
     }
+    red_t[tid] = t;
+    red_p[tid] = q;
+  }
+  __syncthreads();
+  for (int e = tid; e < E; e += kRouteThreads) {
+    int t = 0, q = 0;
+    for (int part = 0; part < parts; ++part) { t += red_t[part * E + e]; q += red_p[part * E + e]; }
+    tot[e] = t;
+    pre[e] = q;
   }
   __syncthreads();
   if (tid == 0) {
@@ -87,17 +116,11 @@ route_assign_kernel(const int64_t* __restrict__ idx, int R, int E, int pad, int 
   // importance / load partials, beside the position blocks instead of as the tail of one of them.
   const bool summary_block = b == nblk;
   // stable rank inside the block: pass 1, per-batch histograms via match_any
-  const int base = b * kRouteChunk;
   int my_e[kRouteBatches / 8], my_rank[kRouteBatches / 8];
 #pragma unroll
   for (int i = 0; i < kRouteBatches / 8; ++i) {
     const int wb = warp + 8 * i;
-    const int s = base + wb * 32 + lane;
-    int e = -1;
-    if (s < R) {
-      const int64_t ee = idx[s];
-      if (ee >= 0 && ee < E) e = (int)ee;
-    }
+    const int e = (ee[i] >= 0 && ee[i] < E) ? (int)ee[i] : -1;
     const unsigned mask = __match_any_sync(0xffffffffu, e);
     const int rank = __popc(mask & ((1u << lane) - 1u));
     if (e >= 0 && rank == 0) bh[wb * E + e] = __popc(mask);
@@ -105,14 +128,21 @@ route_assign_kernel(const int64_t* __restrict__ idx, int R, int E, int pad, int 
     my_rank[i] = rank;
   }
   __syncthreads();
-  // exclusive scan over batches, per expert
-  for (int e = tid; e < E; e += kRouteThreads) {
-    int run = 0;
-    for (int wb = 0; wb < kRouteBatches; ++wb) {
-      const int v = bh[wb * E + e];
-      bh[wb * E + e] = run;
-      run += v;
+  // exclusive scan over batches, per expert: a warp per expert, BPL consecutive batches per lane, shuffle scan over lanes
+  constexpr int BPL = kRouteBatches / 32;
+  for (int e = warp; e < E; e += kRouteThreads / 32) {
+    int v[BPL], sum = 0;
+#pragma unroll
+    for (int j = 0; j < BPL; ++j) { v[j] = bh[(lane * BPL + j) * E + e]; sum += v[j]; }
+    int incl = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int up = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += up;
     }
+    int run = incl - sum;
+#pragma unroll
+    for (int j = 0; j < BPL; ++j) { bh[(lane * BPL + j) * E + e] = run; run += v[j]; }
   }
   __syncthreads();
 #pragma unroll
@@ -142,33 +172,66 @@ route_assign_kernel(const int64_t* __restrict__ idx, int R, int E, int pad, int 
       tile_expert[i] = lo;
     }
     if (importance != nullptr && imp_partial != nullptr) {
-      // fixed assignment (thread -> partials p = part, part+P, ...) and fixed-order final sum:
-      // deterministic, but 256 threads wide instead of E
-      float* fs = reinterpret_cast<float*>(bh + kRouteBatches * E);   // [P][E] scratch behind bh
-      int* is = bh + kRouteBatches * E + kRouteThreads;               // [P][E]
-      const int P = kRouteThreads / E > 0 ? kRouteThreads / E : 1;
-      if (tid < P * E) {
-        const int e = tid % E, part = tid / E;
-        float a = 0.f;
-        int l = 0;
-        int i = part;
-        for (; i + 3 * P < n_partial; i += 4 * P) {      // four partials in flight; summed in the same order as one by one
-          float v[4];
-          int u[4];
+      // fixed assignment (thread -> partials part, part + P, ...), fixed-order combination: deterministic.  The block
+      // is the critical path of the launch (n_partial x E values behind one L2 / DRAM latency per dependent round), so
+      // it reads 16-byte quads of experts with up to 8 partial rows in flight per thread.
+      const int Q = E / 4;
+      const bool quads = E % 4 == 0 && (Q & (Q - 1)) == 0 && Q <= 32 &&
+                         ((reinterpret_cast<uintptr_t>(imp_partial) | reinterpret_cast<uintptr_t>(load_partial)) & 15u) == 0;
+      int P;      // rows of fs / is to combine
+      // [P][E] each: one row per warp in the batch table (this block has no slots, and the scan above is behind a
+      // barrier), or one row per part in the scratch behind it (P E <= 256)
+      float* fs = reinterpret_cast<float*>(quads ? bh : bh + kRouteBatches * E);
+      int* is = quads ? bh + (kRouteThreads / 32) * E : bh + kRouteBatches * E + kRouteThreads;
+      if (quads) {
+        const int ppw = 32 / Q, q = lane % Q;               // a warp: ppw parts x Q quads
+        const int NP = ppw * (kRouteThreads / 32);
+        const int part = warp * ppw + lane / Q;
+        float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+        int4 l = make_int4(0, 0, 0, 0);
+        constexpr int U = 8;
+        for (int i0 = part; i0 < n_partial; i0 += U * NP) {
+          float4 v[U];
+          int4 u[U];
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            v[q] = __ldg(imp_partial + (int64_t)(i + q * P) * E + e);
-            u[q] = __ldg(load_partial + (int64_t)(i + q * P) * E + e);
+          for (int j = 0; j < U; ++j) {
+            const int i = i0 + j * NP;
+            const bool ok = i < n_partial;
+            v[j] = ok ? __ldg(reinterpret_cast<const float4*>(imp_partial + (int64_t)i * E) + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+            u[j] = ok ? __ldg(reinterpret_cast<const int4*>(load_partial + (int64_t)i * E) + q) : make_int4(0, 0, 0, 0);
           }
 #pragma unroll
-          for (int q = 0; q < 4; ++q) { a += v[q]; l += u[q]; }
+          for (int j = 0; j < U; ++j) {
+            a.x += v[j].x; a.y += v[j].y; a.z += v[j].z; a.w += v[j].w;
+            l.x += u[j].x; l.y += u[j].y; l.z += u[j].z; l.w += u[j].w;
+          }
         }
-        for (; i < n_partial; i += P) {
-          a += imp_partial[(int64_t)i * E + e];
-          l += load_partial[(int64_t)i * E + e];
+        for (int o = Q; o < 32; o <<= 1) {                  // the parts of this warp (xor tree: fixed order)
+          a.x += __shfl_xor_sync(0xffffffffu, a.x, o); a.y += __shfl_xor_sync(0xffffffffu, a.y, o);
+          a.z += __shfl_xor_sync(0xffffffffu, a.z, o); a.w += __shfl_xor_sync(0xffffffffu, a.w, o);
+          l.x += __shfl_xor_sync(0xffffffffu, l.x, o); l.y += __shfl_xor_sync(0xffffffffu, l.y, o);
+          l.z += __shfl_xor_sync(0xffffffffu, l.z, o); l.w += __shfl_xor_sync(0xffffffffu, l.w, o);
         }
-        fs[part * E + e] = a;
-        is[part * E + e] = l;
+        if (lane < Q) {
+          float* f = fs + warp * E + 4 * q;       // (the scratch is only 4-byte aligned)
+          int* g = is + warp * E + 4 * q;
+          f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w;
+          g[0] = l.x; g[1] = l.y; g[2] = l.z; g[3] = l.w;
+        }
+        P = kRouteThreads / 32;
+      } else {
+        P = kRouteThreads / E > 0 ? kRouteThreads / E : 1;
+        if (tid < P * E) {
+          const int e = tid % E, part = tid / E;
+          float a = 0.f;
+          int l = 0;
+          for (int i = part; i < n_partial; i += P) {
+            a += imp_partial[(int64_t)i * E + e];
+            l += load_partial[(int64_t)i * E + e];
+          }
+          fs[part * E + e] = a;
+          is[part * E + e] = l;
+        }
       }
       __syncthreads();
       for (int e = tid; e < E; e += kRouteThreads) {
@@ -237,7 +300,7 @@ extern "C" int m3_route_plan(const int64_t* idx, int T, int K, int E, int pad, c
   if (nblk < 1) nblk = 1;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   int32_t* block_hist = static_cast<int32_t*>(workspace);
-  launch_k(route_count_kernel, nblk, kRouteThreads, E * sizeof(int), st, idx, R, E, block_hist);
+  launch_k(route_count_kernel, nblk, kRouteThreads, (kRouteThreads / 32) * E * sizeof(int), st, idx, R, E, block_hist);
   M3_LAUNCH_CHECK();
   const size_t smem = (size_t)(3 * E + 1 + kRouteBatches * E + 2 * kRouteThreads) * sizeof(int);
   launch_k(route_assign_kernel, nblk + 1, kRouteThreads, smem, st, idx, R, E, pad, nblk, block_hist, imp_partial,
