@@ -454,7 +454,7 @@ gate_bwd_dz_kernel(const float* __restrict__ logits, const int32_t* __restrict__
 }
 
 // partial dW[chunk][d][e] = sum_{t in chunk} x[t,d] * dz[t,e]; thread tile 4 d x EW experts.
-constexpr int kDwSub = 128;   // tokens of dz staged in shared memory per pass
+constexpr int kDwSub = 160;   // tokens of dz staged in shared memory per pass (T = 38 432 on 296 chunks: 130 per chunk = one pass)
 
 template <int EW, typename XT, bool LN, int TB>
 __global__ void __launch_bounds__(TB == 16 ? 384 : TB == 8 ? 512 : 1024)
@@ -557,6 +557,165 @@ gate_bwd_dw_kernel(const XT* __restrict__ x, int64_t ldx, const float* __restric
 #pragma unroll
     for (int c = 0; c < EW; ++c) cs_part[(int64_t)blockIdx.x * E + e0 + c] = cs[c];
   }
+}
+
+// The same partial sums with x, dz (and the LayerNorm statistics) streamed through a cp.async ring of S stages x
+// kDwTS tokens.  The register-batch kernel above is bound by LOAD LATENCY: all warps of a CTA issue a batch of loads,
+// wait ~1.5 us for DRAM, then compute for ~0.4 us, 9 times per chunk, and two 6-warp CTAs per SM cannot hide that
+// (27 us at T = 38 432 against 9 us of HBM time; two register half-batches were no better: a thread cannot hold the
+// 4-5 batches in flight that the latency asks for).  A shared-memory ring can: S - 1 stages are always in flight,
+// regardless of the register file, and both expert groups of the CTA read ONE copy of x.  Same thread tile, same
+// summation order (t ascending) - bit-identical partials.
+constexpr int kDwTS = 16;     // tokens per stage
+
+__device__ __forceinline__ void cp_async4(void* smem, const void* gmem) {
+  uint32_t s = static_cast<uint32_t>(__cvta_generic_to_shared(smem));
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(s), "l"(gmem) : "memory");
+}
+
+template <typename XT, bool LN>
+__host__ __device__ constexpr int dw_stage_bytes(int D) {
+  return kDwTS * D * (int)sizeof(XT) + kDwTS * 16 * 4 + (LN ? kDwTS * 2 * 4 : 0);
+}
+
+template <int EW, typename XT, bool LN, int S, int DPT>
+__global__ void __launch_bounds__(512)
+gate_bwd_dw_ring_kernel(const XT* __restrict__ x, int64_t ldx, const float* __restrict__ dz, int T, int D, int E,
+                        int tok_per_chunk, float* __restrict__ part, float* __restrict__ cs_part,
+                        const float* __restrict__ ln_mean, const float* __restrict__ ln_rstd,
+                        const float* __restrict__ ln_gamma, const float* __restrict__ ln_beta) {
+  extern __shared__ __align__(16) unsigned char dw_smem[];
+  const int nthr = blockDim.x;
+  static_assert(DPT == 2 || DPT == 4, "columns of x per thread");
+  const int ngrp = nthr / (D / DPT);              // expert groups per CTA (EB / EW)
+  pdl_wait();
+  pdl_trigger();
+  const int dq = threadIdx.x % (D / DPT);         // thread tile: DPT columns x EW experts (DPT = 2: twice the warps per
+  const int eh = threadIdx.x / (D / DPT);         // SM behind the same stalls - the kernel is latency-, not issue-bound)
+  const int EB = EW * ngrp;                       // experts handled by this CTA (<= 16)
+  const int eb0 = blockIdx.y * EB;
+  const int e0 = eb0 + eh * EW;
+  const int t0 = blockIdx.x * tok_per_chunk;
+  const int t1 = min(T, t0 + tok_per_chunk);
+  const int rowb = D * (int)sizeof(XT);
+  const int stage_bytes = dw_stage_bytes<XT, LN>(D);
+  const int nst = (t1 - t0 + kDwTS - 1) / kDwTS;
+
+  const int nvec = rowb / 16;
+  const int xq = threadIdx.x % nvec, xr = threadIdx.x / nvec, xstep = nthr / nvec;
+  auto issue = [&](int c) {
+    unsigned char* st = dw_smem + (c % S) * stage_bytes;
+    const int tb = t0 + c * kDwTS;
+    // nthr is a multiple of the 16-byte vectors of a row (D / 4 threads per expert group): a thread keeps its column
+    // vector xq and walks the rows xr, xr + xstep, ... - no divisions in the copy loop
+    for (int r = xr; r < kDwTS; r += xstep) {
+      const int t = min(tb + r, t1 - 1);          // rows past the chunk re-read its last token (never consumed)
+      cp_async16(st + r * rowb + xq * 16, reinterpret_cast<const unsigned char*>(x + (int64_t)t * ldx) + xq * 16);
+    }
+    float* dzs = reinterpret_cast<float*>(st + kDwTS * rowb);
+    for (int v = threadIdx.x; v < kDwTS * (EB / 4); v += nthr) {
+      const int r = v / (EB / 4), q = v % (EB / 4);
+      const int t = min(tb + r, t1 - 1);
+      cp_async16(dzs + r * 16 + q * 4, dz + (int64_t)t * E + eb0 + q * 4);
+    }
+    if constexpr (LN) {
+      float* lns = dzs + kDwTS * 16;
+      for (int v = threadIdx.x; v < kDwTS; v += nthr) {
+        const int t = min(tb + v, t1 - 1);
+        cp_async4(lns + 2 * v, ln_mean + t);
+        cp_async4(lns + 2 * v + 1, ln_rstd + t);
+      }
+    }
+    cp_async_commit();
+  };
+
+  // accumulators as fp32 PAIRS of neighbouring experts: fma.rn.f32x2 is the same IEEE fma per half, at half the
+  // instructions (the kernel is issue-bound: ncu counted 88 warp instructions per warp-token for 32 FMAs' worth of work)
+  f32x2 acc2[DPT][EW / 2];
+  float cs1 = 0.f;
+#pragma unroll
+  for (int i = 0; i < DPT; ++i)
+#pragma unroll
+    for (int c = 0; c < EW / 2; ++c) acc2[i][c] = pk2(0.f, 0.f);
+  float lg[DPT], lb[DPT];
+#pragma unroll
+  for (int i = 0; i < DPT; ++i) { lg[i] = 1.f; lb[i] = 0.f; }
+  if constexpr (LN) {
+#pragma unroll
+    for (int i = 0; i < DPT; ++i) { lg[i] = __ldg(ln_gamma + dq * DPT + i); lb[i] = __ldg(ln_beta + dq * DPT + i); }
+  }
+
+#pragma unroll
+  for (int p0 = 0; p0 < S - 1; ++p0) {
+    if (p0 < nst) issue(p0);
+    else cp_async_commit();
+  }
+  for (int c = 0; c < nst; ++c) {
+    cp_async_wait<S - 2>();
+    __syncthreads();              // stage c has landed for every thread; stage c - 1 (refilled next) has been consumed
+    if (c + S - 1 < nst) issue(c + S - 1);
+    else cp_async_commit();
+    const unsigned char* st = dw_smem + (c % S) * stage_bytes;
+    const float* dzs = reinterpret_cast<const float*>(st + kDwTS * rowb);
+    const int n = min(kDwTS, t1 - (t0 + c * kDwTS));
+    auto token = [&](int u) {
+      float xv[DPT];
+      if constexpr (sizeof(XT) == 4 && DPT == 4) {
+        const float4 v = *reinterpret_cast<const float4*>(st + u * rowb + dq * 16);
+        xv[0] = v.x; xv[1] = v.y; xv[2] = v.z; xv[3] = v.w;
+      } else if constexpr (sizeof(XT) == 4) {
+        const float2 v = *reinterpret_cast<const float2*>(st + u * rowb + dq * 8);
+        xv[0] = v.x; xv[1] = v.y;
+      } else if constexpr (DPT == 4) {
+        const uint2 w = *reinterpret_cast<const uint2*>(st + u * rowb + dq * 8);
+        const float2 a = bf16x2_to_float2(w.x), b = bf16x2_to_float2(w.y);
+        xv[0] = a.x; xv[1] = a.y; xv[2] = b.x; xv[3] = b.y;
+      } else {
+        const float2 a = bf16x2_to_float2(*reinterpret_cast<const uint32_t*>(st + u * rowb + dq * 4));
+        xv[0] = a.x; xv[1] = a.y;
+      }
+      f32x2 dv2[EW / 2];
+#pragma unroll
+      for (int k = 0; k < EW; k += 4) {
+        const ulonglong2 v = *reinterpret_cast<const ulonglong2*>(dzs + u * 16 + eh * EW + k);
+        dv2[k / 2] = v.x; dv2[k / 2 + 1] = v.y;
+      }
+      if constexpr (LN) {
+        const float* lns = dzs + kDwTS * 16;
+        const float mu = lns[2 * u], rs = lns[2 * u + 1];
+#pragma unroll
+        for (int i = 0; i < DPT; ++i) xv[i] = fmaf((xv[i] - mu) * rs, lg[i], lb[i]);
+      }
+#pragma unroll
+      for (int i = 0; i < DPT; ++i) {
+        const f32x2 xx = pk2(xv[i], xv[i]);
+#pragma unroll
+        for (int k = 0; k < EW / 2; ++k) acc2[i][k] = fma2(xx, dv2[k], acc2[i][k]);
+      }
+    };
+    // t ascending: deterministic summation order.  Full stages run without a per-token branch.
+    if (n == kDwTS) {
+#pragma unroll
+      for (int u = 0; u < kDwTS; ++u) token(u);
+    } else {
+      for (int u = 0; u < n; ++u) token(u);
+    }
+    // column sums of dz (task-feature rows of dW): thread dq < EW of each expert group owns one expert, away from the
+    // FMA stream (as predicated adds inside it they cost every warp 8 issue slots per token)
+    if (dq < EW)
+      for (int u = 0; u < n; ++u) cs1 += dzs[u * 16 + eh * EW + dq];
+  }
+  float* dst = part + ((int64_t)blockIdx.x * D + dq * DPT) * E + e0;
+#pragma unroll
+  for (int i = 0; i < DPT; ++i)
+#pragma unroll
+    for (int c = 0; c < EW; c += 4) {
+      float a0, a1, a2, a3;
+      unpk2(acc2[i][c / 2], a0, a1);
+      unpk2(acc2[i][c / 2 + 1], a2, a3);
+      *reinterpret_cast<float4*>(dst + (int64_t)i * E + c) = make_float4(a0, a1, a2, a3);
+    }
+  if (dq < EW) cs_part[(int64_t)blockIdx.x * E + e0 + dq] = cs1;
 }
 
 // dW[d][e] = sum_chunks part (fixed order); task rows from the column sums of dz.
@@ -806,7 +965,42 @@ static int gate_bwd_impl(const void* x, int x_dtype, int64_t ldx, const float* t
     else if (threads <= 512) launch_k(gate_bwd_dw_kernel<EWV, XT, LNV, 8>, grid, threads, 0, st, M3_DW_ARGS(XT));        \
     else launch_k(gate_bwd_dw_kernel<EWV, XT, LNV, 4>, grid, threads, 0, st, M3_DW_ARGS(XT));                            \
   } while (0)
-    if (ln_mean != nullptr) {
+    // cp.async ring variant (see gate_bwd_dw_ring_kernel): 16-byte copies need 16-byte rows; >= 2 CTAs per SM want
+    // S stages within ~100 KB
+    const int el = x_dtype == M3_F32 ? 4 : 2;
+    const bool ring_ok = (D * el) % 16 == 0 && (ldx * el) % 16 == 0 && (reinterpret_cast<uintptr_t>(x) & 15u) == 0 &&
+                         EB % 4 == 0 && threads <= 512 && (reinterpret_cast<uintptr_t>(dz) & 15u) == 0;
+#define M3_DW_RING_S(EWV, XT, LNV, SV, DPTV)                                                                        \
+  do {                                                                                                              \
+    auto kern = gate_bwd_dw_ring_kernel<EWV, XT, LNV, SV, DPTV>;                                                    \
+    if (smem > 48 * 1024) {                                                                                         \
+      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);           \
+      if (e != cudaSuccess) return (int)e;                                                                          \
+    }                                                                                                               \
+    launch_k(kern, grid, threads * (4 / DPTV), smem, st, M3_DW_ARGS(XT));                                           \
+  } while (0)
+#define M3_DW_RING(EWV, XT, LNV)                                                                                    \
+  do {                                                                                                              \
+    const int sb = dw_stage_bytes<XT, LNV>(D);                                                                      \
+    const int S = 4 * sb <= 100 * 1024 ? 4 : 3 * sb <= 100 * 1024 ? 3 : 2;                                          \
+    const size_t smem = (size_t)S * sb;                                                                             \
+    if (2 * threads <= 512) {       /* two columns per thread: twice the warps */                                   \
+      if (S == 4) M3_DW_RING_S(EWV, XT, LNV, 4, 2); else if (S == 3) M3_DW_RING_S(EWV, XT, LNV, 3, 2);              \
+      else M3_DW_RING_S(EWV, XT, LNV, 2, 2);                                                                        \
+    } else {                                                                                                        \
+      if (S == 4) M3_DW_RING_S(EWV, XT, LNV, 4, 4); else if (S == 3) M3_DW_RING_S(EWV, XT, LNV, 3, 4);              \
+      else M3_DW_RING_S(EWV, XT, LNV, 2, 4);                                                                        \
+    }                                                                                                               \
+  } while (0)
+    if (ring_ok && 2 * dw_stage_bytes<float, true>(D) <= 200 * 1024) {
+      if (ln_mean != nullptr) {
+        if (EW == 8) M3_DW_RING(8, float, true); else M3_DW_RING(4, float, true);
+      } else if (x_dtype == M3_F32) {
+        if (EW == 8) M3_DW_RING(8, float, false); else M3_DW_RING(4, float, false);
+      } else {
+        if (EW == 8) M3_DW_RING(8, __nv_bfloat16, false); else M3_DW_RING(4, __nv_bfloat16, false);
+      }
+    } else if (ln_mean != nullptr) {
       if (EW == 8) M3_DW_LAUNCH(8, float, true); else M3_DW_LAUNCH(4, float, true);
     } else if (x_dtype == M3_F32) {
       if (EW == 8) M3_DW_LAUNCH(8, float, false); else M3_DW_LAUNCH(4, float, false);
