@@ -593,7 +593,7 @@ def main():
             line["ep_parity"] = parity
         if extra is not None:
             line["configs"] = extra
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:      # (rank 0 at N = 1 only: the other ranks would idle behind it)
             line["cpu_baseline"] = cpu_reference(3, 1, args.batch, budget_s=25.0)
         print(json.dumps(line))
     if world > 1:
