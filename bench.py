@@ -407,7 +407,7 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return
-        cb = cpu_reference(max(args.steps, 3), warmup, args.batch)
+        cb = cpu_reference(max(args.steps, 1), warmup, args.batch)      # exactly K timed steps (median), W >= 3 warm-up
         config["reference_sample"] = (f"each timed step = {cb['calls_per_step']} of the {N_LAYER * N_TASK} layer calls (bounded "
                                       "sample of the same workload: same B, N, D, H, E, K, both task gates)")
         line = {"metric": METRIC, "value": cb["value"], "unit": "tokens/s", "n_gpus": args.gpus, "steps": args.steps,

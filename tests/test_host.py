@@ -102,3 +102,26 @@ def test_cv_squared_matches_reference_formula():
     x = torch.tensor([1.0, 2.0, 3.0, 6.0])
     assert torch.allclose(M.cv_squared(x), x.var() / (x.mean() ** 2 + 1e-10))
     assert float(M.cv_squared(torch.tensor([5.0]))) == 0.0
+
+
+def test_bench_reference_arm_line_contract():
+    """`bench.py --impl reference` (the CPU oracle port on the host cores) prints ONE JSON line with the contract's keys,
+    times exactly K steps, and needs no GPU.  Tiny batch: the workload shape is the bench's, the sample is bounded."""
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "2", "--warmup", "3",
+                        "--batch", "1"], capture_output=True, text=True, timeout=600, cwd=root)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "moe_layer_tokens_per_s_fwd_bwd" and d["unit"] == "tokens/s"
+    assert d["steps"] == 2 and d["warmup"] >= 3 and d["higher_is_better"] is True and d["value"] > 0
+    assert d["gpu_launches"] == 0 and d["e2e"]["value"] == d["value"]
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
+    cb = d["cpu_baseline"]
+    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and "sample" in cb
+    assert d["config"]["batch_per_gpu"] == 1 and d["config"]["layer_calls_per_step"] == 12
