@@ -12,7 +12,9 @@ job of W ranks owns the contiguous slice [r*E_loc, (r+1)*E_loc).  The reference
   * tags single-file checkpoints with meta.expert_format in {"global","local"} and refuses
     rank-local ones (utils/moe_utils.py:34-106, pretrain/utils/moe_checkpoint.py:57-112).
 
-These helpers reproduce that format so real M3ViT checkpoints load into the B200 layer at any W.
+These helpers reproduce that format so real M3ViT checkpoints load into the B200 layer at any W, and
+`upcycle_dense_mlp` / `inject_experts_from_dense_mlp` build the expert tensors from a dense DeiT / ViT MLP the way
+the reference's upcycling does (utils/helpers.py:481-713; golden: oracle/make_upcycle_golden.py).
 Pure host code (torch CPU tensors); no CUDA involved.
 
 Parity: `oracle/make_ckpt_golden.py` executes the reference's own functions (utils/moe_utils.py:34-198 under the
@@ -231,3 +233,90 @@ def load_ep_dir(dirname: str, world_size: int, map_location="cpu") -> dict:
     meta["expert_format"] = "global"
     out["meta"] = meta
     return out
+
+
+# ----------------------------------------------------------------------------- dense MLP -> experts ("upcycling")
+def upcycle_dense_mlp(fc1_w: torch.Tensor, fc1_b: torch.Tensor, fc2_w: torch.Tensor, fc2_b: torch.Tensor, *,
+                      local_experts: int, total_experts: Optional[int] = None, expert_hidden: Optional[int] = None,
+                      top_k: int = 4, split: Optional[bool] = None, weight_scaling: bool = False,
+                      require_granularity_4: bool = False):
+    """Expert parameters of ONE MoE block from the dense DeiT / ViT MLP it replaces
+    (/root/reference/utils/helpers.py:481-713, `_inject_moe_expert_from_deit_mlp`, the per-block body).
+
+      fc1_w [Hd, D], fc1_b [Hd], fc2_w [D, Hd], fc2_b [D]   ->
+      (htoh4.weight [E_loc, He, D], htoh4.bias [E_loc, He], h4toh.weight [E_loc, D, He], h4toh.bias [E_loc, D])
+
+    * copy mode (`split=False`; the reference's moe_mlp_ratio != 1 path): every local expert is a copy of the dense MLP.
+    * split mode (`split=True`; moe_mlp_ratio == 1 or deit_init_mode == "deit_warm_start"): the dense hidden dimension is
+      cut into G = Hd / He groups - expert j of a group owns rows [j He, (j+1) He) of fc1 and the matching columns of fc2,
+      fc2's bias is repeated per expert.  E_loc a multiple of G: the group template is repeated; otherwise the first E_loc
+      experts of the template are used.  `weight_scaling` multiplies fc1 (weight and bias) and fc2 (weight) by
+      sqrt(E G^2 / top_k) with E = total_experts / G (the reference's GELU / softmax-then-top-k rule).
+    `split=None` picks split mode iff the expert hidden size differs from the dense one.  `require_granularity_4`
+    reproduces the refusal of the warm-start mode for any other split."""
+    Hd = int(fc1_w.shape[0])
+    if total_experts is None or total_experts <= 0:
+        total_experts = local_experts
+    if expert_hidden is None:
+        expert_hidden = Hd
+    if split is None:
+        split = expert_hidden != Hd
+    if not split:
+        rep3 = lambda t: t.unsqueeze(0).repeat(local_experts, 1, 1).contiguous()
+        rep2 = lambda t: t.unsqueeze(0).repeat(local_experts, 1).contiguous()
+        return rep3(fc1_w), rep2(fc1_b), rep3(fc2_w), rep2(fc2_b)
+    G = Hd // int(expert_hidden)
+    if G <= 0 or Hd % G != 0:
+        raise AssertionError(f"invalid granularity {G} for dense hidden size {Hd}")
+    if total_experts % G != 0:
+        raise AssertionError(f"total_experts={total_experts} must be divisible by granularity={G}")
+    if require_granularity_4 and G != 4:
+        raise ValueError(f"deit_warm_start requires dense_hidden / expert_hidden == 4, got {G}")
+    scale = 1.0
+    if weight_scaling:
+        scale = (((total_experts // G) * G * G) / float(max(int(top_k), 1))) ** 0.5
+    e1_w = torch.stack((fc1_w * scale).chunk(G, dim=0), dim=0)          # [G, He, D]
+    e1_b = torch.stack((fc1_b * scale).chunk(G, dim=0), dim=0)          # [G, He]
+    e2_w = torch.stack((fc2_w * scale).chunk(G, dim=1), dim=0)          # [G, D, He]
+    if local_experts % G == 0:
+        reps = local_experts // G
+        return (e1_w.repeat(reps, 1, 1).contiguous(), e1_b.repeat(reps, 1).contiguous(),
+                e2_w.repeat(reps, 1, 1).contiguous(), fc2_b.unsqueeze(0).repeat(local_experts, 1).contiguous())
+    return (e1_w[:local_experts].contiguous(), e1_b[:local_experts].contiguous(), e2_w[:local_experts].contiguous(),
+            fc2_b.unsqueeze(0).repeat(local_experts, 1).contiguous())
+
+
+def inject_experts_from_dense_mlp(state_dict, moe_blocks: Dict[int, dict], *, moe_mlp_ratio: float = 4.0,
+                                  mlp_ratio: float = 4.0, mode: str = "deit_upcycling", weight_scaling: bool = False,
+                                  default_top_k: int = 4):
+    """State-dict level form of the same helper: for every MoE block index i in `moe_blocks` whose dense keys
+    `blocks.{i}.mlp.fc1/fc2.{weight,bias}` are present, ADD `blocks.{i}.mlp.experts.htoh4/h4toh.{weight,bias}` (the dense
+    keys stay, as in the reference; blocks without dense keys are skipped).  `moe_blocks[i]` describes the layer the
+    tensors are for: {"local_experts", "world_size" (1), "total_experts" (local x world), "top_k" (default_top_k),
+    "expert_hidden" (dense hidden)} - e.g. from a constructed model:
+        {i: dict(local_experts=b.mlp.num_expert, world_size=b.mlp.world_size, top_k=b.mlp.top_k,
+                 expert_hidden=b.mlp.experts.htoh4.weight.shape[1]) for i, b in enumerate(model.blocks) if b.moe}
+    A negative `moe_mlp_ratio` means "same as the dense MLP", i.e. `mlp_ratio` (reference :497-499)."""
+    mode = str(mode).strip().lower()
+    if mode not in ("scratch", "deit_warm_start", "deit_upcycling"):
+        raise ValueError(f"Unsupported deit_init_mode '{mode}'")
+    force_split = mode == "deit_warm_start"
+    ratio = float(mlp_ratio) if moe_mlp_ratio < 0 else float(moe_mlp_ratio)
+    for i, info in moe_blocks.items():
+        keys = [f"blocks.{i}.mlp.{n}" for n in ("fc1.weight", "fc1.bias", "fc2.weight", "fc2.bias")]
+        if keys[0] not in state_dict or keys[2] not in state_dict:
+            continue
+        fc1_w, fc1_b, fc2_w, fc2_b = (state_dict[k] for k in keys)
+        e_loc = int(info["local_experts"])
+        world = max(int(info.get("world_size", 1)), 1)
+        total = int(info.get("total_experts", e_loc * world))
+        e1w, e1b, e2w, e2b = upcycle_dense_mlp(
+            fc1_w, fc1_b, fc2_w, fc2_b, local_experts=e_loc, total_experts=total if total > 0 else e_loc * world,
+            expert_hidden=info.get("expert_hidden") if (force_split or ratio == 1.0) else None,
+            top_k=int(info.get("top_k", default_top_k)), split=force_split or ratio == 1.0,
+            weight_scaling=weight_scaling, require_granularity_4=force_split)
+        state_dict[f"blocks.{i}.mlp.experts.htoh4.weight"] = e1w
+        state_dict[f"blocks.{i}.mlp.experts.htoh4.bias"] = e1b
+        state_dict[f"blocks.{i}.mlp.experts.h4toh.weight"] = e2w
+        state_dict[f"blocks.{i}.mlp.experts.h4toh.bias"] = e2b
+    return state_dict

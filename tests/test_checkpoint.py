@@ -144,3 +144,52 @@ def test_shard_directory_written_by_the_reference(gold, tmp_path):
         assert res == ("raise", "ValueError")
         with pytest.raises(ValueError):
             C.merge_shard_dir(str(d))
+
+
+# ----------------------------------------------------------------------------- dense MLP -> experts (upcycling)
+def _upcycle_golden():
+    import os
+    p = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "upcycle_reference.pt")
+    return torch.load(p, weights_only=False)
+
+
+@pytest.mark.parametrize("name", ["ratio4_copy", "ratio1_split_repeat", "ratio1_split_scaled", "ratio1_split_truncate",
+                                  "ratio2_split_g2_warm_refused", "ratio_minus1_uses_mlp_ratio"])
+def test_upcycling_matches_reference_function(name):
+    """inject_experts_from_dense_mlp against what the reference's own `_inject_moe_expert_from_deit_mlp`
+    (utils/helpers.py:481-713, executed verbatim by oracle/make_upcycle_golden.py) returned or raised: bit-exact."""
+    rec = _upcycle_golden()["cases"][name]
+    c = rec["case"]
+    sd = {k: v.clone() for k, v in rec["input"].items()}
+    blocks = {i: dict(local_experts=c["E_local"], world_size=c["world"], total_experts=c["total"], top_k=c["top_k"],
+                      expert_hidden=c["He"]) for i in (0, 2)}                 # block 1 is dense
+    kw = dict(moe_mlp_ratio=c["ratio"], mode=c["mode"], weight_scaling=bool(c["cfg"].get("use_weight_scaling", False)))
+    if "raises" in rec:
+        with pytest.raises(ValueError if rec["raises"] == "ValueError" else AssertionError):
+            C.inject_experts_from_dense_mlp(sd, blocks, **kw)
+        return
+    out = C.inject_experts_from_dense_mlp(sd, blocks, **kw)
+    want = rec["output"]
+    assert set(out) == set(want)
+    for k in want:
+        assert out[k].shape == want[k].shape and torch.equal(out[k], want[k]), k
+    assert not any(k.startswith("blocks.1.mlp.experts") for k in out)
+
+
+def test_upcycled_experts_reproduce_the_dense_mlp():
+    """Function-level property (size independent): with every expert a full copy (copy mode) any routing whose scores sum
+    to 1 reproduces the dense MLP; in split mode the G experts of a group together are the dense MLP minus (G-1) fc2 biases."""
+    torch.manual_seed(0)
+    D, Hd, G = 8, 32, 4
+    fc1_w, fc1_b, fc2_w, fc2_b = torch.randn(Hd, D), torch.randn(Hd), torch.randn(D, Hd), torch.randn(D)
+    x = torch.randn(5, D)
+    dense = torch.nn.functional.gelu(x @ fc1_w.t() + fc1_b) @ fc2_w.t() + fc2_b
+    w1, b1, w2, b2 = C.upcycle_dense_mlp(fc1_w, fc1_b, fc2_w, fc2_b, local_experts=3)
+    for e in range(3):
+        y = torch.nn.functional.gelu(x @ w1[e].t() + b1[e]) @ w2[e].t() + b2[e]
+        assert torch.allclose(y, dense, atol=1e-5)
+    w1, b1, w2, b2 = C.upcycle_dense_mlp(fc1_w, fc1_b, fc2_w, fc2_b, local_experts=8, total_experts=8, expert_hidden=Hd // G)
+    assert w1.shape == (8, Hd // G, D) and w2.shape == (8, D, Hd // G)
+    group = sum(torch.nn.functional.gelu(x @ w1[e].t() + b1[e]) @ w2[e].t() + b2[e] for e in range(G))
+    assert torch.allclose(group, dense + (G - 1) * fc2_b, atol=1e-4)
+    assert torch.equal(w1[:G], w1[G:]) and torch.equal(b2[0], fc2_b)
