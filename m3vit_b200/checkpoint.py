@@ -320,3 +320,36 @@ def inject_experts_from_dense_mlp(state_dict, moe_blocks: Dict[int, dict], *, mo
         state_dict[f"blocks.{i}.mlp.experts.h4toh.weight"] = e2w
         state_dict[f"blocks.{i}.mlp.experts.h4toh.bias"] = e2b
     return state_dict
+
+
+# ----------------------------------------------------------------------------- router keys of a pretrained checkpoint
+def convert_gate_keys(state_dict, *, multi_gate: bool, num_tasks: int, task_one_hot: bool = False,
+                      gate_task_specific_dim: int = -1, regu_experts_fromtask: bool = False,
+                      replicate_all_tasks: bool = False):
+    """The router part of the reference's `cvt_state_dict` (/root/reference/utils/common_config.py:47-68): a checkpoint
+    trained with ONE shared router per MoE block (`...mlp.gate.w_gate [D, E]`) is adapted, in place, to the layer it is
+    loaded into:
+
+      * shared router fed a task vector (`task_one_hot`, not `multi_gate`, not `regu_experts_fromtask`): zero rows are
+        appended for the extra gate inputs - `num_tasks` rows if `gate_task_specific_dim < 0`, else that many
+        (the new inputs start without influence on the logits);
+      * `multi_gate`: every `...gate.w_gate` becomes `...gate.{t}.w_gate`, one copy per task gate, and the shared key is
+        removed.  REFERENCE QUIRK kept by default: copies exist for tasks 0 and 1, plus 2 and 3 when `num_tasks == 4`, plus
+        2, 3, 4 when `num_tasks == 5` - any other task count gets TWO gates (the rest keep their initialisation under
+        `strict=False`).  `replicate_all_tasks=True` writes all `num_tasks` copies instead.
+    Other keys are untouched.  Returns the same dict."""
+    if task_one_hot and not multi_gate and not regu_experts_fromtask:
+        rows = num_tasks if gate_task_specific_dim < 0 else gate_task_specific_dim
+        for k in list(state_dict.keys()):
+            if "mlp.gate.w_gate" in k:
+                w = state_dict[k]
+                state_dict[k] = torch.cat((w, torch.zeros((rows, w.shape[-1]))), 0)
+    if multi_gate:
+        n = num_tasks if (replicate_all_tasks or num_tasks in (4, 5)) else 2
+        for k in list(state_dict.keys()):
+            if "mlp.gate.w_gate" in k:
+                stem = k[:-len("w_gate")]
+                for t in range(n):
+                    state_dict[f"{stem}{t}.w_gate"] = state_dict[k]
+                del state_dict[k]
+    return state_dict

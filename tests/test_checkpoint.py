@@ -193,3 +193,46 @@ def test_upcycled_experts_reproduce_the_dense_mlp():
     group = sum(torch.nn.functional.gelu(x @ w1[e].t() + b1[e]) @ w2[e].t() + b2[e] for e in range(G))
     assert torch.allclose(group, dense + (G - 1) * fc2_b, atol=1e-4)
     assert torch.equal(w1[:G], w1[G:]) and torch.equal(b2[0], fc2_b)
+
+
+# ----------------------------------------------------------------------------- router keys (cvt_state_dict)
+@pytest.mark.parametrize("name", ["shared_gate_untouched", "one_hot_pads_num_tasks_rows", "one_hot_pads_task_dim_rows",
+                                  "one_hot_regu_untouched", "multi_gate_2", "multi_gate_4", "multi_gate_5",
+                                  "multi_gate_3_gets_two"])
+def test_gate_key_conversion_matches_reference_function(name):
+    """convert_gate_keys against the state dict the reference's own `cvt_state_dict` (utils/common_config.py:31-100, its
+    source segment executed verbatim by oracle/make_gatekeys_golden.py) handed to load_state_dict: same keys, same bits."""
+    import os
+    rec = torch.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "gatekeys_reference.pt"),
+                     weights_only=False)["cases"][name]
+    c = rec["case"]
+    sd = {k: v.clone() for k, v in rec["input"].items()}
+    out = C.convert_gate_keys(sd, multi_gate=c["multi_gate"], num_tasks=c["num_tasks"], task_one_hot=c["task_one_hot"],
+                              gate_task_specific_dim=c["gtsd"], regu_experts_fromtask=c["regu"])
+    want = rec["output"]
+    assert set(out) == set(want)
+    for k in want:
+        assert out[k].shape == want[k].shape and torch.equal(out[k], want[k]), k
+
+
+def test_gate_key_conversion_loads_into_the_layer():
+    """The converted keys are exactly what the drop-in layer's state dict expects (multi-gate: one gate per task;
+    task-conditioned shared router: D + D_t rows), and `replicate_all_tasks` covers task counts the reference forgets."""
+    torch.manual_seed(0)
+    shared = {"gate.w_gate": torch.randn(64, 8)}
+    mg = M.FMoETransformerMLP(num_expert=8, d_model=64, d_gate=64 + 3, d_hidden=64, activation=nn.Sequential(nn.GELU(), nn.Dropout(0.0)),
+                              gate=M.NoisyGate_VMoE, top_k=2, vmoe_noisy_std=0, multi_gate=True)
+    sd = C.convert_gate_keys({"mlp." + k: v.clone() for k, v in shared.items()}, multi_gate=True, num_tasks=3,
+                             replicate_all_tasks=True)
+    sd = {k[len("mlp."):]: v for k, v in sd.items()}
+    missing, unexpected = mg.load_state_dict(sd, strict=False)
+    assert not unexpected and not [k for k in missing if "gate" in k]
+    assert all(torch.equal(g.w_gate, shared["gate.w_gate"]) for g in mg.gate)
+    tc = M.FMoETransformerMLP(num_expert=8, d_model=64, d_gate=64, d_hidden=64, activation=nn.Sequential(nn.GELU(), nn.Dropout(0.0)),
+                              gate=M.NoisyGate_VMoE, top_k=2, vmoe_noisy_std=0, multi_gate=False, gate_task_specific_dim=6)
+    sd = C.convert_gate_keys({"mlp.gate.w_gate": shared["gate.w_gate"].clone()}, multi_gate=False, num_tasks=2,
+                             task_one_hot=True, gate_task_specific_dim=6)
+    missing, unexpected = tc.load_state_dict({k[len("mlp."):]: v for k, v in sd.items()}, strict=False)
+    assert not unexpected and not [k for k in missing if "gate" in k]
+    assert tc.gate.w_gate.shape == (70, 8) and torch.equal(tc.gate.w_gate[:64], shared["gate.w_gate"])
+    assert float(tc.gate.w_gate.detach()[64:].abs().max()) == 0.0
