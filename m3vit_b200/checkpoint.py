@@ -14,7 +14,9 @@ job of W ranks owns the contiguous slice [r*E_loc, (r+1)*E_loc).  The reference
 
 These helpers reproduce that format so real M3ViT checkpoints load into the B200 layer at any W, and
 `upcycle_dense_mlp` / `inject_experts_from_dense_mlp` build the expert tensors from a dense DeiT / ViT MLP the way
-the reference's upcycling does (utils/helpers.py:481-713; golden: oracle/make_upcycle_golden.py).
+the reference's upcycling does (utils/helpers.py:481-713; golden: oracle/make_upcycle_golden.py), with the router side of it:
+`convert_gate_keys` (utils/common_config.py:47-68; oracle/make_gatekeys_golden.py) and the virtual-group router
+initialisation (utils/helpers.py:715-866; oracle/make_vgi_golden.py).
 Pure host code (torch CPU tensors); no CUDA involved.
 
 Parity: `oracle/make_ckpt_golden.py` executes the reference's own functions (utils/moe_utils.py:34-198 under the
@@ -352,4 +354,81 @@ def convert_gate_keys(state_dict, *, multi_gate: bool, num_tasks: int, task_one_
                 for t in range(n):
                     state_dict[f"{stem}{t}.w_gate"] = state_dict[k]
                 del state_dict[k]
+    return state_dict
+
+
+# ----------------------------------------------------------------------------- router init for upcycled experts
+def auto_virtual_group_size(tot_experts: int, *, local_experts=None, world_size=None, dense_hidden=None,
+                            expert_hidden=None) -> int:
+    """Size G of a "virtual group" of router columns (/root/reference/utils/helpers.py:715-754): the split granularity
+    dense_hidden / expert_hidden when it is whole (else the local expert count, else tot / world, else 1), reduced to a
+    common divisor of the local and the total expert count."""
+    import math
+    tot_experts = int(tot_experts)
+    if tot_experts <= 0:
+        return 1
+    primary = None
+    if dense_hidden is not None and expert_hidden is not None and expert_hidden > 0 and dense_hidden % expert_hidden == 0:
+        primary = int(dense_hidden // expert_hidden)
+    if primary is None or primary <= 0:
+        if local_experts is not None and int(local_experts) > 0:
+            primary = int(local_experts)
+        elif world_size is not None and int(world_size) > 0 and tot_experts % int(world_size) == 0:
+            primary = int(tot_experts // int(world_size))
+        else:
+            primary = 1
+    g = int(primary)
+    if local_experts is not None and int(local_experts) > 0:
+        g = math.gcd(g, int(local_experts))
+    g = math.gcd(g, tot_experts)
+    if g <= 0 or tot_experts % g != 0:
+        g = 1
+    return g
+
+
+def virtual_group_gate_init(like: torch.Tensor, group_size: int, std: float = 0.02) -> torch.Tensor:
+    """A router matrix [D_g, E_tot] for experts that were upcycled in groups of `group_size` (reference
+    `build_grouped_w_gate`, utils/helpers.py:783-803): N(0, std) everywhere, then the first group's columns repeated for
+    every group - the copies of one dense-MLP slice start with the same logit.  Draws from torch's global CPU generator
+    exactly like the reference (one normal_ over the full matrix), so a fixed torch seed gives the same bits."""
+    d_model, tot = like.shape
+    if group_size < 1 or tot % group_size != 0:
+        raise AssertionError(f"group_size={group_size} must divide tot_experts={tot}")
+    w = torch.empty((d_model, tot), device=like.device, dtype=like.dtype)
+    torch.nn.init.normal_(w, mean=0.0, std=std)
+    if group_size == 1:
+        return w
+    proto = torch.tensor_split(w, tot // group_size, dim=1)[0]
+    return torch.cat([proto] * (tot // group_size), dim=1).contiguous()
+
+
+def inject_virtual_group_gate_init(state_dict, model_state: Dict[str, torch.Tensor], moe_blocks: Dict[int, dict],
+                                   std: float = 0.02):
+    """State-dict level form (reference `_inject_virtual_group_init_for_gates`, utils/helpers.py:757-866): every router key
+    of `model_state` (`blocks.{i}[.mlp].gate[.{t}].w_gate`, `blocks.{i}.shared_gate.w_gate`), in `model_state` order, is
+    (re)initialised with `virtual_group_gate_init`; G comes from `auto_virtual_group_size` with the block's
+    {"local_experts", "world_size"} of `moe_blocks[i]`, the dense hidden size of `blocks.{i}.mlp.fc1.weight` in `state_dict`
+    and the expert hidden size of `blocks.{i}.mlp.experts.htoh4.weight` in `model_state` (else `state_dict`)."""
+    import re
+    pat = re.compile(r"^blocks\.\d+\.(?:mlp\.)?(?:gate(?:\.\d+)?|shared_gate)\.w_gate$")
+    keys = [k for k in model_state.keys() if pat.search(k)]
+    if not keys:
+        raise KeyError("no router w_gate keys (blocks.{i}[.mlp].gate[.{j}].w_gate | blocks.{i}.shared_gate.w_gate)")
+    for k in keys:
+        ref = state_dict.get(k, model_state[k])
+        i = int(re.search(r"^blocks\.(\d+)\.", k).group(1))
+        info = moe_blocks.get(i, {})
+        world = info.get("world_size", 1)
+        world = 1 if world is None or int(world) < 1 else int(world)
+        dense_hidden = expert_hidden = None
+        if f"blocks.{i}.mlp.fc1.weight" in state_dict:
+            dense_hidden = int(state_dict[f"blocks.{i}.mlp.fc1.weight"].shape[0])
+        ek = f"blocks.{i}.mlp.experts.htoh4.weight"
+        if ek in model_state:
+            expert_hidden = int(model_state[ek].shape[1])
+        elif ek in state_dict:
+            expert_hidden = int(state_dict[ek].shape[1])
+        g = auto_virtual_group_size(int(ref.shape[1]), local_experts=info.get("local_experts"), world_size=world,
+                                    dense_hidden=dense_hidden, expert_hidden=expert_hidden)
+        state_dict[k] = virtual_group_gate_init(ref, g, std).cpu()
     return state_dict

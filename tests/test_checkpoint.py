@@ -236,3 +236,42 @@ def test_gate_key_conversion_loads_into_the_layer():
     assert not unexpected and not [k for k in missing if "gate" in k]
     assert tc.gate.w_gate.shape == (70, 8) and torch.equal(tc.gate.w_gate[:64], shared["gate.w_gate"])
     assert float(tc.gate.w_gate.detach()[64:].abs().max()) == 0.0
+
+
+# ----------------------------------------------------------------------------- virtual-group router init
+def _vgi_golden():
+    import os
+    return torch.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "vgi_reference.pt"), weights_only=False)
+
+
+def test_virtual_group_size_matches_reference_function():
+    """auto_virtual_group_size on the 1 800-point grid the reference's `_auto_virtual_group_size` was run on."""
+    for (tot, loc, world, dh, eh), want in _vgi_golden()["group_size"]:
+        got = C.auto_virtual_group_size(tot, local_experts=loc, world_size=world, dense_hidden=dh, expert_hidden=eh)
+        assert got == want, (tot, loc, world, dh, eh, got, want)
+
+
+@pytest.mark.parametrize("name", ["split_g4_shared_gate", "split_g4_two_task_gates", "copy_g_is_local"])
+def test_virtual_group_gate_init_matches_reference_function(name):
+    """Same torch seed -> the same router matrices, bit for bit, as `_inject_virtual_group_init_for_gates` run verbatim;
+    and the structure it is for: the columns of a group repeat across groups."""
+    rec = _vgi_golden()["cases"][name]
+    D, Hd, He, E_local, world, gates = rec["shape"]
+    tot = E_local * world
+    sd = {f"blocks.{i}.mlp.fc1.weight": torch.zeros(Hd, D) for i in (0, 2)}
+    model_state = {}
+    for i in (0, 2):
+        model_state[f"blocks.{i}.mlp.experts.htoh4.weight"] = torch.empty(E_local, He, D)
+        for t in ([None] if gates is None else range(gates)):
+            model_state[f"blocks.{i}.mlp.gate.w_gate" if t is None else f"blocks.{i}.mlp.gate.{t}.w_gate"] = torch.zeros(D, tot)
+    torch.manual_seed(rec["seed"])
+    out = C.inject_virtual_group_gate_init(sd, model_state, {i: dict(local_experts=E_local, world_size=world) for i in (0, 2)})
+    want = rec["gates"]
+    assert {k for k in out if k.endswith("w_gate")} == set(want)
+    for k in want:
+        assert torch.equal(out[k], want[k]), k
+    G = C.auto_virtual_group_size(tot, local_experts=E_local, world_size=world, dense_hidden=Hd, expert_hidden=He)
+    for k in want:
+        w = out[k]
+        for grp in range(1, tot // G if G > 1 else 1):          # (G = 1: plain normal init, nothing repeats)
+            assert torch.equal(w[:, :G], w[:, grp * G:(grp + 1) * G])
