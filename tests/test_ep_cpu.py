@@ -110,3 +110,68 @@ def test_arena_allocator_is_deterministic():
     assert replay() == replay()
     o = replay()
     assert o[2] == o[0] and all(v % 1024 == 0 for v in o)
+
+
+def _sync_worker(rank, world, port, q):
+    import torch.distributed as dist
+    import torch.nn as nn
+    import m3vit_b200 as M
+    from m3vit_b200 import dist_utils as U
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.manual_seed(10 + rank)                       # every rank starts with DIFFERENT weights
+    blk = nn.Module()
+    blk.mlp = M.FMoETransformerMLP(num_expert=2, d_model=16, d_gate=16 + 2, d_hidden=16,
+                                   activation=nn.Sequential(nn.GELU(), nn.Dropout(0.0)), gate=M.NoisyGate_VMoE, world_size=world,
+                                   top_k=2, vmoe_noisy_std=0, multi_gate=True)
+    blk.norm = nn.LayerNorm(16)
+    with torch.no_grad():
+        blk.norm.weight.add_(rank + 1.0)
+    before = {k: v.clone() for k, v in blk.state_dict().items()}
+    U.sync_weights(blk)
+    after = blk.state_dict()
+    gathered = {}
+    ok = True
+    for k, v in after.items():
+        both = [torch.empty_like(v) for _ in range(world)]
+        dist.all_gather(both, v.contiguous())
+        expert = any(w in k for w in U.EXPERT_KEY_WORDS)
+        if expert:
+            ok &= torch.equal(v, before[k])                                           # rank-local, untouched
+            if k.endswith("weight"):                                                  # (biases start at zero everywhere)
+                ok &= not torch.equal(both[0], both[1])
+        else:
+            ok &= torch.equal(both[0], both[1])                                       # rank 0's copy everywhere
+            if rank == 0:
+                ok &= torch.equal(v, before[k])
+    # gradients: the router and the LayerNorm average over the world, experts keep theirs, an unused task gate gets zeros
+    tags = {n: getattr(p, "dp_comm", "dp") for n, p in blk.named_parameters()}
+    ok &= tags["mlp.experts.htoh4.weight"] == "none" and tags["mlp.gate.0.w_gate"] == "gate"
+    for n, p in blk.named_parameters():
+        p.grad = None if n == "mlp.gate.1.w_gate" else torch.full_like(p, float(rank + 1))
+    nred = U.allreduce_replicated_grads(blk)
+    ok &= nred == 4                                                                   # 2 task gates + LayerNorm weight, bias
+    for n, p in blk.named_parameters():
+        if tags[n] == "none":
+            ok &= bool((p.grad == rank + 1).all())
+        elif n == "mlp.gate.1.w_gate":
+            ok &= bool((p.grad == 0).all())
+        else:
+            ok &= bool((p.grad == 1.5).all())                                         # mean of 1 and 2
+    q.put((rank, bool(ok)))
+    dist.destroy_process_group()
+
+
+def test_replicated_parameter_sync_world2_gloo():
+    """sync_weights / allreduce_replicated_grads (the reference's sync_weights + allreduce_params contract around an
+    expert-parallel layer) on 2 gloo ranks: experts stay rank-local, everything else follows rank 0 / averages."""
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_sync_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+    assert res == [(0, True), (1, True)]
