@@ -15,7 +15,9 @@ calling anything does, and fails loudly otherwise.
 from .custom_moe_layer import (FMoETransformerMLP, FMoETransformerMLPCkpt, TokenFMoETransformerMLP,  # noqa: F401
                                FMoELinear)
 from .noisy_gate_vmoe import NoisyGate_VMoE, TokenNoisyGate_VMoE, cv_squared  # noqa: F401
-from .block import build_moe_mlp, MoEBlockMlp, collect_noisy_gating_loss  # noqa: F401
+from .block import (build_moe_mlp, MoEBlockMlp, collect_noisy_gating_loss, collect_moe_activation,  # noqa: F401
+                    set_moe_layer_train_mode)
 
 __all__ = ["FMoETransformerMLP", "FMoETransformerMLPCkpt", "TokenFMoETransformerMLP", "FMoELinear", "NoisyGate_VMoE", "TokenNoisyGate_VMoE", "cv_squared",
-           "build_moe_mlp", "MoEBlockMlp", "collect_noisy_gating_loss"]
+           "build_moe_mlp", "MoEBlockMlp", "collect_noisy_gating_loss", "collect_moe_activation",
+           "set_moe_layer_train_mode"]

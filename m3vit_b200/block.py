@@ -102,3 +102,32 @@ def collect_noisy_gating_loss(model, weight):
         if isinstance(module, NoisyGate_VMoE) and module.has_loss:
             loss += module.get_loss()
     return loss * weight
+
+
+def collect_moe_activation(model, batch_size, activation_suppress="pool", return_name=False):
+    """utils/moe_utils.py:226-250: the router probabilities every gate cached in its last forward, as [B, E] ("pool":
+    mean over the tokens of an image), [B, N, E] ("origin") or [B, N*E] ("concat" - the reference's line for it,
+    `torch.reshape(activation.shape[0], -1)`, raises a TypeError; the documented intent is implemented here)."""
+    gate_activations, names = [], []
+    for name, module in model.named_modules():
+        if isinstance(module, NoisyGate_VMoE) and module.has_activation:
+            activation = module.get_activation()
+            c = activation.shape[-1]
+            activation = activation.reshape(batch_size, -1, c)
+            if activation_suppress == "pool":
+                activation = activation.mean(dim=1)
+            elif activation_suppress == "concat":
+                activation = activation.reshape(activation.shape[0], -1)
+            elif activation_suppress != "origin":
+                raise ValueError("No activation_suppress of {}".format(activation_suppress))
+            gate_activations.append(activation)
+            names.append(name)
+    return (gate_activations, names) if return_name else gate_activations
+
+
+def set_moe_layer_train_mode(model):
+    """utils/moe_utils.py:303-306: put every MoE layer (and nothing else) into train mode."""
+    from .custom_moe_layer import FMoETransformerMLP
+    for module in model.modules():
+        if isinstance(module, FMoETransformerMLP):
+            module.train()

@@ -125,3 +125,44 @@ def test_bench_reference_arm_line_contract():
     cb = d["cpu_baseline"]
     assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and "sample" in cb
     assert d["config"]["batch_per_gpu"] == 1 and d["config"]["layer_calls_per_step"] == 12
+
+
+def test_model_walkers_of_the_reference_utils():
+    """collect_noisy_gating_loss / collect_moe_activation / set_moe_layer_train_mode (utils/moe_utils.py:201-207,
+    :226-250, :303-306) find the drop-in layer's gates and layers; activations and losses are planted by hand (no GPU)."""
+    torch.manual_seed(0)
+    B, N, E = 2, 5, 8
+    model = nn.Module()
+    model.blocks = nn.ModuleList()
+    for _ in range(2):
+        blk = nn.Module()
+        blk.mlp = M.FMoETransformerMLP(num_expert=E, d_model=16, d_gate=16 + 2, d_hidden=16,
+                                       activation=nn.Sequential(nn.GELU(), nn.Dropout(0.0)), gate=M.NoisyGate_VMoE, top_k=2,
+                                       vmoe_noisy_std=0, multi_gate=True)
+        blk.norm = nn.LayerNorm(16)
+        model.blocks.append(blk)
+    model.eval()
+    M.set_moe_layer_train_mode(model)
+    assert all(b.mlp.training and not b.norm.training for b in model.blocks)
+    probs = []
+    for b in model.blocks:                                      # task gate 1 ran, task gate 0 did not
+        p = torch.softmax(torch.randn(B * N, E), dim=1)
+        b.mlp.gate[1].activation = p
+        b.mlp.gate[1].set_loss(torch.tensor(0.25))
+        probs.append(p)
+    acts, names = M.collect_moe_activation(model, B, return_name=True)
+    assert names == ["blocks.0.mlp.gate.1", "blocks.1.mlp.gate.1"]
+    assert all(torch.allclose(a, p.reshape(B, N, E).mean(1)) for a, p in zip(acts, probs))
+    assert not any(b.mlp.gate[1].has_activation for b in model.blocks)          # consumed, like the reference's getter
+    for b, p in zip(model.blocks, probs):
+        b.mlp.gate[1].activation = p
+    assert M.collect_moe_activation(model, B, "origin")[0].shape == (B, N, E)
+    for b, p in zip(model.blocks, probs):
+        b.mlp.gate[1].activation = p
+    assert M.collect_moe_activation(model, B, "concat")[1].shape == (B, N * E)
+    for b, p in zip(model.blocks, probs):
+        b.mlp.gate[1].activation = p
+    with pytest.raises(ValueError):
+        M.collect_moe_activation(model, B, "median")
+    assert float(M.collect_noisy_gating_loss(model, 0.01)) == pytest.approx(0.005)
+    assert float(M.collect_noisy_gating_loss(model, 0.01)) == 0.0               # get_loss clears
