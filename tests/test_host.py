@@ -166,3 +166,28 @@ def test_model_walkers_of_the_reference_utils():
         M.collect_moe_activation(model, B, "median")
     assert float(M.collect_noisy_gating_loss(model, 0.01)) == pytest.approx(0.005)
     assert float(M.collect_noisy_gating_loss(model, 0.01)) == 0.0               # get_loss clears
+
+
+def test_committed_evidence_is_current_and_complete():
+    """The committed measurement files stay usable: (1) the ncu traffic capture that `bench.py` reports as
+    `roofline.traffic` was taken from the kernel sources as they are now (its sha256 matches, else the bench prints null);
+    (2) the committed N = 1 bench line carries every key of the bench contract."""
+    import json
+    import os
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, root)
+    import bench
+    key = (f"ffn_fwd_train:bf16:T{32 * bench.N_TOK}:D{bench.D_MODEL}:H{bench.D_HID}:E{bench.N_EXP}:K{bench.TOP_K}")
+    traffic, src = bench.ncu_traffic(key)
+    assert traffic is not None and traffic > 1e8, src
+    line = json.loads(open(os.path.join(root, "profiles", "r2_bench_n1.json")).read().strip().splitlines()[-1])
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+              "vs_baseline", "dtype", "data", "config", "clocks", "e2e", "gpu_launches", "roofline", "cpu_baseline", "stages"):
+        assert k in line, k
+    assert line["metric"] == bench.METRIC and line["n_gpus"] == 1 and line["gpu_launches"] > 0
+    assert line["e2e"]["h2d_bytes_per_step"] == 12 * 32 * bench.N_TOK * bench.D_MODEL * 4 and line["e2e"]["value"] < line["value"]
+    r = line["roofline"]
+    assert r["bound"] in ("hbm", "tensor") and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9 and r["traffic"] is not None
+    assert line["cpu_baseline"]["kind"] in ("port", "reference") and line["cpu_baseline"]["cores"] >= 1
+    assert "workload" in line["config"] and not any(k in line["config"] for k in ("model", "seq_len"))
